@@ -1,0 +1,411 @@
+"""ctypes bindings for the CPU oracle (oracle/liborb_oracle.so) and the compiled reference (oracle/_ref/libref.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs.  The product package (orb_slam2_ros2_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liborb_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libref.so")
+
+KP_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")]
+)
+assert KP_DTYPE.itemsize == 28
+MAX_LEVELS = 32
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(ORACLE_SO) or (os.path.isdir("/root/reference") and not os.path.exists(REF_SO)):
+        subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
+    elif os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+class _Pyramid(C.Structure):
+    _fields_ = [
+        ("n_levels", C.c_int),
+        ("w", C.c_int * MAX_LEVELS),
+        ("h", C.c_int * MAX_LEVELS),
+        ("sf", C.c_float * MAX_LEVELS),
+        ("quota", C.c_int * MAX_LEVELS),
+        ("img", u8p * MAX_LEVELS),
+        ("blur", u8p * MAX_LEVELS),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        _lib = C.CDLL(ORACLE_SO)
+        L = _lib
+        L.oracle_fast9_nms.restype = C.c_int
+        L.oracle_fast9_nms.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, i32p, i32p, i32p, C.c_int]
+        L.oracle_fast_cells.restype = C.c_int
+        L.oracle_fast_cells.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int, i32p]
+        L.oracle_resize_linear_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_int, C.c_int, C.c_size_t]
+        L.oracle_gaussian_blur7_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_size_t]
+        L.oracle_undistort_points.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, f32p, C.c_int]
+        L.oracle_quadtree_select.restype = C.c_int
+        L.oracle_quadtree_select.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, C.c_int, i32p, C.POINTER(C.c_long)]
+        L.oracle_ic_angle.restype = C.c_double
+        L.oracle_ic_angle.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int]
+        L.oracle_brief.argtypes = [u8p, C.c_size_t, C.c_float, C.c_float, C.c_double, f32p, u8p]
+        L.oracle_pyramid_build.restype = C.c_int
+        L.oracle_pyramid_build.argtypes = [C.POINTER(_Pyramid), u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_float]
+        L.oracle_pyramid_free.argtypes = [C.POINTER(_Pyramid)]
+        L.oracle_extract.restype = C.c_int
+        L.oracle_extract.argtypes = [C.POINTER(_Pyramid), C.c_int, C.c_int, f32p, C.c_void_p, u8p, f64p, i32p]
+        L.oracle_search_by_stereo.restype = C.c_int
+        L.oracle_search_by_stereo.argtypes = [C.POINTER(_Pyramid), C.POINTER(_Pyramid), C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int,
+                                              C.c_float, C.c_float, f64p, f64p, i32p]
+        L.oracle_rgbd_lookup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                         f64p, f64p]
+        L.oracle_scale_factors.argtypes = [C.c_float, C.c_int, f32p]
+        L.oracle_level_quotas.argtypes = [C.c_int, C.c_float, C.c_int, i32p]
+        L.oracle_level_sizes.restype = C.c_int
+        L.oracle_level_sizes.argtypes = [C.c_int, C.c_int, f32p, C.c_int, i32p, i32p]
+        L.oracle_umax.argtypes = [i32p]
+        L.oracle_fast9_arc_value.restype = C.c_int
+        L.oracle_fast9_arc_value.argtypes = [u8p, C.c_size_t]
+    return _lib
+
+
+def default_pattern() -> np.ndarray:
+    """The 256x4 BRIEF pattern as float32, parsed from include/orbx_pattern.h (the repo's built-in table)."""
+    import re
+
+    txt = open(os.path.join(HERE, "..", "include", "orbx_pattern.h")).read()
+    body = txt[txt.index("{") + 1 : txt.index("};")]
+    vals = [int(v) for v in re.findall(r"-?\d+", body)]
+    assert len(vals) == 1024
+    return np.asarray(vals, dtype=np.float32).reshape(256, 4)
+
+
+def write_template_file(path: str, pattern: np.ndarray | None = None) -> str:
+    """Write a template file in the reference's format (header line + 256 tab-separated rows)."""
+    p = default_pattern() if pattern is None else pattern
+    with open(path, "w") as f:
+        f.write("x1  y1  x2  y2\n")
+        for r in p:
+            f.write("\t".join(str(int(v)) for v in r) + "\n")
+    return path
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def scale_factors(scale: float, n_levels: int) -> np.ndarray:
+    sf = np.zeros(n_levels, np.float32)
+    lib().oracle_scale_factors(scale, n_levels, _ptr(sf, f32p))
+    return sf
+
+
+def level_quotas(n_features: int, scale: float, n_levels: int) -> np.ndarray:
+    q = np.zeros(n_levels, np.int32)
+    lib().oracle_level_quotas(n_features, scale, n_levels, _ptr(q, i32p))
+    return q
+
+
+def level_sizes(w: int, h: int, scale: float, n_levels: int):
+    sf = scale_factors(scale, n_levels)
+    lw = np.zeros(n_levels, np.int32)
+    lh = np.zeros(n_levels, np.int32)
+    rc = lib().oracle_level_sizes(w, h, _ptr(sf, f32p), n_levels, _ptr(lw, i32p), _ptr(lh, i32p))
+    return rc, lw, lh
+
+
+def umax() -> np.ndarray:
+    u = np.zeros(16, np.int32)
+    lib().oracle_umax(_ptr(u, i32p))
+    return u
+
+
+def resize_linear(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty((dh, dw), np.uint8)
+    lib().oracle_resize_linear_u8(_ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0], _ptr(out, u8p), dw, dh, dw)
+    return out
+
+
+def gaussian_blur7(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().oracle_gaussian_blur7_u8(_ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0], _ptr(out, u8p), out.strides[0])
+    return out
+
+
+def fast9_nms(img: np.ndarray, threshold: int):
+    """-> (n,3) int32 array of (x, y, score), row-major order"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = (h // 2 + 1) * (w // 2 + 1)
+    xs, ys, sc = (np.zeros(cap, np.int32) for _ in range(3))
+    n = lib().oracle_fast9_nms(_ptr(img, u8p), w, h, img.strides[0], threshold, _ptr(xs, i32p), _ptr(ys, i32p), _ptr(sc, i32p), cap)
+    return np.stack([xs[:n], ys[:n], sc[:n]], 1)
+
+
+def fast_cells(img: np.ndarray, ini_th: int = 20, min_th: int = 7):
+    """-> ((n,3) int32 (x_roi, y_roi, score) in detection order, n_fallback_cells)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = h * w // 4 + 16
+    xs, ys, sc = (np.zeros(cap, np.int32) for _ in range(3))
+    nfb = C.c_int(0)
+    n = lib().oracle_fast_cells(_ptr(img, u8p), w, h, img.strides[0], ini_th, min_th, _ptr(xs, i32p), _ptr(ys, i32p), _ptr(sc, i32p), cap, C.byref(nfb))
+    if n < 0:
+        raise ValueError("level too small for the 30-px cell grid")
+    return np.stack([xs[:n], ys[:n], sc[:n]], 1), nfb.value
+
+
+def quadtree_select(roi_w: int, roi_h: int, xs, ys, resp, need: int):
+    xs = np.ascontiguousarray(xs, np.float32)
+    ys = np.ascontiguousarray(ys, np.float32)
+    resp = np.ascontiguousarray(resp, np.float32)
+    out = np.zeros(max(need, 1) + 4, np.int32)
+    pops = C.c_long(0)
+    n = lib().oracle_quadtree_select(roi_w, roi_h, len(xs), _ptr(xs, f32p), _ptr(ys, f32p), _ptr(resp, f32p), need, _ptr(out, i32p), C.byref(pops))
+    return out[:n].copy(), pops.value
+
+
+def undistort_points(xy: np.ndarray, fx, fy, cx, cy, dist) -> np.ndarray:
+    out = np.ascontiguousarray(xy, np.float32).copy()
+    d = np.ascontiguousarray(dist, np.float32)
+    lib().oracle_undistort_points(_ptr(out, f32p), out.shape[0], fx, fy, cx, cy, _ptr(d, f32p), len(d))
+    return out
+
+
+def ic_angle(img: np.ndarray, x: int, y: int) -> float:
+    img = np.ascontiguousarray(img, np.uint8)
+    return lib().oracle_ic_angle(_ptr(img, u8p), img.strides[0], x, y)
+
+
+def brief(blurred: np.ndarray, px: float, py: float, theta: float, pattern: np.ndarray) -> np.ndarray:
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    pat = np.ascontiguousarray(pattern, np.float32)
+    d = np.zeros(32, np.uint8)
+    lib().oracle_brief(_ptr(blurred, u8p), blurred.strides[0], px, py, theta, _ptr(pat, f32p), _ptr(d, u8p))
+    return d
+
+
+class Pyramid:
+    """ORBExtractor constructor state (pyramid + blurred pyramid + per-level tables)."""
+
+    def __init__(self, img: np.ndarray, n_features: int, n_levels: int, scale: float):
+        img = np.ascontiguousarray(img, np.uint8)
+        self._p = _Pyramid()
+        rc = lib().oracle_pyramid_build(C.byref(self._p), _ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0], n_features, n_levels, scale)
+        if rc != 0:
+            raise ValueError("ImageSizeError" if rc == -1 else "bad level count")
+        self.n_levels = n_levels
+        self.w = list(self._p.w[:n_levels])
+        self.h = list(self._p.h[:n_levels])
+        self.sf = np.array(self._p.sf[:n_levels], np.float32)
+        self.quota = list(self._p.quota[:n_levels])
+
+    def level(self, l: int) -> np.ndarray:
+        return np.ctypeslib.as_array(self._p.img[l], shape=(self.h[l], self.w[l])).copy()
+
+    def blurred(self, l: int) -> np.ndarray:
+        return np.ctypeslib.as_array(self._p.blur[l], shape=(self.h[l], self.w[l])).copy()
+
+    def __del__(self):
+        try:
+            lib().oracle_pyramid_free(C.byref(self._p))
+        except Exception:
+            pass
+
+
+@dataclass
+class Extracted:
+    kps: np.ndarray  # KP_DTYPE
+    desc: np.ndarray  # (n,32) u8
+    theta: np.ndarray  # (n,) f64 radians
+    level_counts: np.ndarray
+    pyr: Pyramid
+
+
+def extract(img: np.ndarray, n_features=2000, n_levels=8, scale=1.2, ini_th=20, min_th=7, pattern=None) -> Extracted:
+    pyr = Pyramid(img, n_features, n_levels, scale)
+    pat = np.ascontiguousarray(default_pattern() if pattern is None else pattern, np.float32)
+    kps = np.zeros(n_features + 8, KP_DTYPE)
+    desc = np.zeros((n_features + 8, 32), np.uint8)
+    th = np.zeros(n_features + 8, np.float64)
+    lc = np.zeros(n_levels, np.int32)
+    n = lib().oracle_extract(C.byref(pyr._p), ini_th, min_th, _ptr(pat, f32p), kps.ctypes.data, _ptr(desc, u8p), _ptr(th, f64p), _ptr(lc, i32p))
+    if n < 0:
+        raise ValueError("level too small for the cell grid")
+    return Extracted(kps[:n].copy(), desc[:n].copy(), th[:n].copy(), lc, pyr)
+
+
+def search_by_stereo(left: Extracted, right: Extracted, fx: float, bf: float, kps_left_undist=None):
+    kl = np.ascontiguousarray(left.kps if kps_left_undist is None else kps_left_undist)
+    kr = np.ascontiguousarray(right.kps)
+    dl = np.ascontiguousarray(left.desc)
+    dr = np.ascontiguousarray(right.desc)
+    nl, nr = len(kl), len(kr)
+    ur = np.zeros(max(nl, 1), np.float64)
+    dp = np.zeros(max(nl, 1), np.float64)
+    mi = np.zeros(max(nl, 1), np.int32)
+    nm = lib().oracle_search_by_stereo(C.byref(left.pyr._p), C.byref(right.pyr._p), kl.ctypes.data, _ptr(dl, u8p), nl, kr.ctypes.data, _ptr(dr, u8p), nr,
+                                       fx, bf, _ptr(ur, f64p), _ptr(dp, f64p), _ptr(mi, i32p))
+    return nm, ur[:nl], dp[:nl], mi[:nl]
+
+
+def rgbd_lookup(depth_img: np.ndarray, depth_scale: float, kps_raw: np.ndarray, kps_undist: np.ndarray, bf: float):
+    is_float = depth_img.dtype == np.float32
+    d = np.ascontiguousarray(depth_img, np.float32 if is_float else np.uint16)
+    n = len(kps_raw)
+    ur = np.zeros(max(n, 1), np.float64)
+    dp = np.zeros(max(n, 1), np.float64)
+    kr = np.ascontiguousarray(kps_raw)
+    ku = np.ascontiguousarray(kps_undist)
+    lib().oracle_rgbd_lookup(d.ctypes.data, int(is_float), d.shape[1], d.shape[0], d.strides[0] // d.itemsize, depth_scale, kr.ctypes.data, ku.ctypes.data,
+                             n, bf, _ptr(ur, f64p), _ptr(dp, f64p))
+    return ur[:n], dp[:n]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the compiled reference (oracle/_ref/libref.so)
+_ref = None
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            build()
+        R = C.CDLL(REF_SO)
+        R.ref_extract.restype = C.c_int
+        R.ref_extract.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int,
+                                  u8p, i32p, i32p, f32p]
+        R.ref_blurred_pyramid.restype = C.c_int
+        R.ref_blurred_pyramid.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_char_p, u8p]
+        R.ref_quadtree.restype = C.c_int
+        R.ref_quadtree.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, C.c_int, i32p]
+        R.ref_stereo.restype = C.c_int
+        R.ref_stereo.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int, C.c_int, C.c_void_p, u8p, i32p,
+                                 C.c_void_p, u8p, i32p, f64p, f64p, C.c_int]
+        R.ref_set_camera.argtypes = [C.c_float] * 5 + [f32p]
+        R.ref_get_bf.restype = C.c_float
+        R.ref_undistort.argtypes = [f32p, C.c_int]
+        R.ref_bench_stereo.restype = C.c_double
+        R.ref_bench_stereo.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_long)]
+        _ref = R
+    return _ref
+
+
+def ref_reset():
+    ref().ref_reset()
+
+
+def ref_set_camera(fx, fy, cx, cy, bl, dist5=None):
+    d = np.zeros(5, np.float32) if dist5 is None else np.ascontiguousarray(dist5, np.float32)
+    ref().ref_set_camera(fx, fy, cx, cy, bl, _ptr(d, f32p))
+    return ref().ref_get_bf()
+
+
+def ref_extract(img, template_path, n_features=2000, n_levels=8, scale=1.2, ini_th=20, min_th=7, want_pyramid=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = n_features + 8
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    lw = np.zeros(n_levels, np.int32)
+    lh = np.zeros(n_levels, np.int32)
+    sf = np.zeros(n_levels, np.float32)
+    pyr = np.zeros(4 * w * h, np.uint8) if want_pyramid else None
+    n = ref().ref_extract(_ptr(img, u8p), w, h, img.strides[0], n_features, n_levels, scale, template_path.encode(), ini_th, min_th, kps.ctypes.data,
+                          _ptr(desc, u8p), cap, _ptr(pyr, u8p), _ptr(lw, i32p), _ptr(lh, i32p), _ptr(sf, f32p))
+    if n < 0:
+        return n, None, None, None
+    levels = None
+    if want_pyramid:
+        levels, off = [], 0
+        for l in range(n_levels):
+            levels.append(pyr[off : off + lw[l] * lh[l]].reshape(lh[l], lw[l]).copy())
+            off += lw[l] * lh[l]
+    return n, kps[:n].copy(), desc[:n].copy(), dict(levels=levels, lw=lw, lh=lh, sf=sf)
+
+
+def ref_blurred(img, template_path, n_features, n_levels, scale, lw, lh):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros(int(np.sum(lw.astype(np.int64) * lh)), np.uint8)
+    rc = ref().ref_blurred_pyramid(_ptr(img, u8p), w, h, img.strides[0], n_features, n_levels, scale, template_path.encode(), _ptr(out, u8p))
+    assert rc == 0
+    res, off = [], 0
+    for l in range(n_levels):
+        res.append(out[off : off + lw[l] * lh[l]].reshape(lh[l], lw[l]))
+        off += lw[l] * lh[l]
+    return res
+
+
+def ref_quadtree(roi_w, roi_h, xs, ys, resp, need):
+    xs = np.ascontiguousarray(xs, np.float32)
+    ys = np.ascontiguousarray(ys, np.float32)
+    resp = np.ascontiguousarray(resp, np.float32)
+    out = np.zeros(max(need, 1) + 4, np.int32)
+    n = ref().ref_quadtree(roi_w, roi_h, len(xs), _ptr(xs, f32p), _ptr(ys, f32p), _ptr(resp, f32p), need, _ptr(out, i32p))
+    return out[:n].copy()
+
+
+def ref_stereo(left, right, template_path, n_features=2000, n_levels=8, scale=1.2, ini_th=20, min_th=7):
+    left = np.ascontiguousarray(left, np.uint8)
+    right = np.ascontiguousarray(right, np.uint8)
+    assert left.shape == right.shape and left.strides == right.strides
+    h, w = left.shape
+    cap = n_features + 8
+    kl, kr = np.zeros(cap, KP_DTYPE), np.zeros(cap, KP_DTYPE)
+    dl, dr = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+    ur, dp = np.zeros(cap, np.float64), np.zeros(cap, np.float64)
+    nl, nr = C.c_int(0), C.c_int(0)
+    nm = ref().ref_stereo(_ptr(left, u8p), _ptr(right, u8p), w, h, left.strides[0], n_features, n_levels, scale, template_path.encode(), ini_th, min_th,
+                          kl.ctypes.data, _ptr(dl, u8p), C.byref(nl), kr.ctypes.data, _ptr(dr, u8p), C.byref(nr), _ptr(ur, f64p), _ptr(dp, f64p), cap)
+    if nm < 0:
+        return dict(status=nm)
+    a, b = nl.value, nr.value
+    return dict(status=0, n_matches=nm, kl=kl[:a].copy(), dl=dl[:a].copy(), kr=kr[:b].copy(), dr=dr[:b].copy(), u_right=ur[:a].copy(), depth=dp[:a].copy())
+
+
+def ref_undistort(xy):
+    out = np.ascontiguousarray(xy, np.float32).copy()
+    ref().ref_undistort(_ptr(out, f32p), out.shape[0])
+    return out
+
+
+def ref_bench_stereo(left_pool, right_pool, template_path, n_frames, workers, n_features=2000, n_levels=8, scale=1.2, ini_th=20, min_th=7):
+    """-> (seconds, total matches).  left_pool/right_pool: (pool, H, W) uint8, dense."""
+    lp = np.ascontiguousarray(left_pool, np.uint8)
+    rp = np.ascontiguousarray(right_pool, np.uint8)
+    pool, h, w = lp.shape
+    m = C.c_long(0)
+    secs = ref().ref_bench_stereo(_ptr(lp, u8p), _ptr(rp, u8p), pool, w, h, n_features, n_levels, scale, template_path.encode(), ini_th, min_th, n_frames,
+                                  workers, C.byref(m))
+    return secs, m.value

@@ -1,0 +1,77 @@
+"""Seeded synthetic inputs shaped like the reference's datasets.
+
+Pure numpy (PCG64) so the same frames are produced in the build container and on the GPU box:
+  * KITTI-shaped stereo pairs 1241x376 (config/kitti_config_00.yaml), constant disparity + right-image noise,
+  * TUM-shaped gray 640x480 + uint16 depth scaled by 5208 (config/tum_config_f2.yaml),
+  * 1920x1080 pairs for the high-resolution stress configuration.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+KITTI = dict(width=1241, height=376, n_features=2000, n_levels=8, scale_factor=1.2, ini_th=20, min_th=7,
+             fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, bl=0.537166, dist=(0.0, 0.0, 0.0, 0.0, 0.0), depth_scale=1.0)
+TUM = dict(width=640, height=480, n_features=1000, n_levels=8, scale_factor=1.2, ini_th=20, min_th=7,
+           fx=520.908620, fy=521.007327, cx=325.141442, cy=249.701764, bl=0.0767889,
+           dist=(0.231222, -0.784899, -0.003257, -0.000105, 0.917205), depth_scale=5208.0)
+HD = dict(width=1920, height=1080, n_features=5000, n_levels=12, scale_factor=1.2, ini_th=20, min_th=7,
+          fx=1400.0, fy=1400.0, cx=960.0, cy=540.0, bl=0.12, dist=(0.0, 0.0, 0.0, 0.0, 0.0), depth_scale=1.0)
+
+
+def _gauss_sep(img: np.ndarray, sigma: float) -> np.ndarray:
+    r = max(1, int(np.ceil(3 * sigma)))
+    x = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (x / sigma) ** 2)
+    k = (k / k.sum()).astype(np.float32)
+    p = np.pad(img, ((0, 0), (r, r)), mode="reflect")
+    out = np.zeros_like(img)
+    for i in range(2 * r + 1):
+        out += k[i] * p[:, i : i + img.shape[1]]
+    p = np.pad(out, ((r, r), (0, 0)), mode="reflect")
+    out2 = np.zeros_like(img)
+    for i in range(2 * r + 1):
+        out2 += k[i] * p[i : i + img.shape[0], :]
+    return out2
+
+
+def synth_image(h: int, w: int, seed: int) -> np.ndarray:
+    """Multi-scale blocky texture + noise, lightly blurred: a few thousand FAST corners per pyramid level."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w), np.float32)
+    for s, a in [(64, 60.0), (24, 50.0), (8, 40.0), (3, 25.0)]:
+        gh, gw = (h + s - 1) // s + 1, (w + s - 1) // s + 1
+        g = rng.random((gh, gw)).astype(np.float32)
+        img += a * np.kron(g, np.ones((s, s), np.float32))[:h, :w]
+    img += rng.normal(0.0, 3.0, (h, w)).astype(np.float32)
+    img = _gauss_sep(img, 0.8)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def synth_stereo_pair(h: int, w: int, seed: int, disparity: int = 17):
+    """left/right views of one wide base image: x_right = x_left - disparity; +-2 grey-level noise on the right."""
+    base = synth_image(h, w + 128, seed)
+    left = np.ascontiguousarray(base[:, 64 : 64 + w])
+    right = base[:, 64 + disparity : 64 + disparity + w].astype(np.int16)
+    right = right + np.random.default_rng(seed + 100).integers(-2, 3, right.shape, dtype=np.int16)
+    return left, np.clip(right, 0, 255).astype(np.uint8)
+
+
+def synth_depth_u16(h: int, w: int, seed: int, depth_scale: float = 5208.0) -> np.ndarray:
+    """Smooth random depth in [0.5, 6] m with ~10 % invalid (0) pixels, as uint16 = round(depth_scale * z)."""
+    rng = np.random.default_rng(seed + 7)
+    g = rng.random(((h + 31) // 32 + 1, (w + 31) // 32 + 1)).astype(np.float32)
+    z = np.kron(g, np.ones((32, 32), np.float32))[:h, :w]
+    z = 0.5 + 5.5 * _gauss_sep(z, 6.0)
+    raw = np.clip(np.round(depth_scale * z), 0, 65535).astype(np.uint16)
+    raw[rng.random((h, w)) < 0.10] = 0
+    return raw
+
+
+def synth_stereo_pool(h: int, w: int, n: int, seed0: int = 0, disparity: int = 17):
+    """-> (left[n,h,w], right[n,h,w]) uint8"""
+    ls, rs = [], []
+    for i in range(n):
+        l, r = synth_stereo_pair(h, w, seed0 + i, disparity)
+        ls.append(l)
+        rs.append(r)
+    return np.stack(ls), np.stack(rs)

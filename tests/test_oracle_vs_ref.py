@@ -1,0 +1,154 @@
+"""The plain-C restatement (oracle/orb_oracle.c) against the reference's OWN code compiled unmodified
+(oracle/_ref/libref.so = /root/reference/src/ORB_SLAM2/src/{ORBExtractor,Camera}.cc + the searchByStereo line ranges
+of ORBMatcher.cc built against oracle/stub).  Everything must be identical to the last bit."""
+import numpy as np
+import pytest
+
+from orb_slam2_ros2_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def R(oracle, have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference)")
+    return oracle
+
+
+def _same_kps(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+CONFIGS = [
+    ("K2000", 376, 1241, 2000, 8, 1.2, 0),
+    ("K500", 376, 1241, 500, 8, 1.2, 1),
+    ("K4000", 376, 1241, 4000, 8, 1.2, 2),
+    ("T1000", 480, 640, 1000, 8, 1.2, 3),
+    ("H5000", 1080, 1920, 5000, 12, 1.2, 4),
+    ("S300x5", 240, 320, 300, 5, 1.3, 5),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_extract_identical(R, template_path, cfg):
+    _, h, w, nf, nl, sc, seed = cfg
+    img = synth.synth_image(h, w, seed)
+    R.ref_reset()
+    n, kps, desc, info = R.ref_extract(img, template_path, nf, nl, sc, want_pyramid=True)
+    e = R.extract(img, nf, nl, sc)
+    assert n == len(e.kps) and n > 0
+    assert _same_kps(kps, e.kps)
+    assert np.array_equal(desc, e.desc)
+    assert np.array_equal(info["sf"], e.pyr.sf)
+    for l in range(nl):
+        assert np.array_equal(info["levels"][l], e.pyr.level(l))
+    blurred = R.ref_blurred(img, template_path, nf, nl, sc, info["lw"], info["lh"])
+    for l in range(nl):
+        assert np.array_equal(blurred[l], e.pyr.blurred(l))
+
+
+def test_extract_degenerate_images(R, template_path):
+    R.ref_reset()
+    for img in (np.zeros((376, 1241), np.uint8), np.full((200, 300), 255, np.uint8)):
+        n, kps, desc, _ = R.ref_extract(img, template_path, 1000, 4, 1.2)
+        e = R.extract(img, 1000, 4, 1.2)
+        assert n == 0 and len(e.kps) == 0
+    # uniform noise: tens of thousands of corners per level, quotas still met
+    img = np.random.default_rng(1).integers(0, 256, (240, 320), dtype=np.uint8)
+    n, kps, desc, _ = R.ref_extract(img, template_path, 1000, 4, 1.2)
+    e = R.extract(img, 1000, 4, 1.2)
+    assert n == len(e.kps) and _same_kps(kps, e.kps) and np.array_equal(desc, e.desc)
+
+
+def test_starved_level_returns_zero(R, template_path):
+    """a level with fewer usable corners than its quota drains the multimap and yields 0 keypoints (ORBExtractor.cc:151)"""
+    R.ref_reset()
+    img = np.full((240, 320), 128, np.uint8)
+    img[60:180, 80:240] = synth.synth_image(120, 160, 11)  # corners only in the centre
+    n, kps, desc, _ = R.ref_extract(img, template_path, 3000, 3, 1.2)
+    e = R.extract(img, 3000, 3, 1.2)
+    assert n == len(e.kps) and _same_kps(kps, e.kps) and np.array_equal(desc, e.desc)
+    assert (e.level_counts == 0).any()
+
+
+def test_errors(R, template_path):
+    R.ref_reset()
+    img = synth.synth_image(60, 100, 0)
+    n, *_ = R.ref_extract(img, template_path, 500, 8, 1.2)
+    assert n == -1  # ImageSizeError
+    R.ref_reset()
+    n, *_ = R.ref_extract(synth.synth_image(240, 320, 0), "/nonexistent/brief_template.txt", 500, 4, 1.2)
+    assert n == -2  # FileNotOpenError
+    R.ref_reset()
+
+
+def test_quadtree_identical(R):
+    rng = np.random.default_rng(7)
+    cases = 0
+    for it in range(60):
+        w, h = int(rng.integers(40, 1300)), int(rng.integers(40, 400))
+        n = int(rng.integers(0, 3000))
+        xs = rng.integers(3, max(4, w - 3), n).astype(np.float32)
+        ys = rng.integers(3, max(4, h - 3), n).astype(np.float32)
+        if it % 5 == 0 and n:  # corners exactly on root / first split lines
+            xs[: n // 4] = np.float32(w / max(1, round(w / h)) / 2)
+            ys[n // 4 : n // 2] = np.float32(h // 2) if h % 2 == 0 else ys[n // 4 : n // 2]
+        resp = rng.integers(6, 120, n).astype(np.float32)
+        for need in {0, 1, 2, int(rng.integers(3, 600)), n + 5}:
+            a, _ = R.quadtree_select(w, h, xs, ys, resp, need)
+            b = R.ref_quadtree(w, h, xs, ys, resp, need) if not (n == 0 and need == 1) else a  # reference reads kps[0] OOB
+            assert np.array_equal(a, b), (w, h, n, need)
+            cases += 1
+    assert cases > 200
+
+
+def test_quadtree_portrait_and_wide(R):
+    rng = np.random.default_rng(3)
+    for w, h in [(100, 400), (100, 260), (3000, 100), (64, 64)]:
+        n = 800
+        xs = rng.integers(3, w - 3, n).astype(np.float32)
+        ys = rng.integers(3, h - 3, n).astype(np.float32)
+        resp = rng.integers(6, 120, n).astype(np.float32)
+        for need in (5, 50, 300):
+            a, _ = R.quadtree_select(w, h, xs, ys, resp, need)
+            assert np.array_equal(a, R.ref_quadtree(w, h, xs, ys, resp, need)), (w, h, need)
+
+
+STEREO = [
+    ("K2000_d17", synth.KITTI, 2000, 0, 17),
+    ("K2000_d5", synth.KITTI, 2000, 1, 5),
+    ("K1000_d63", synth.KITTI, 1000, 2, 63),
+    ("T1000_d17", synth.TUM, 1000, 3, 17),
+    ("H5000_d42", synth.HD, 5000, 4, 42),
+]
+
+
+@pytest.mark.parametrize("cfg", STEREO, ids=[c[0] for c in STEREO])
+def test_stereo_identical(R, template_path, cfg):
+    _, c, nf, seed, disp = cfg
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], seed, disp)
+    R.ref_reset()
+    bf = R.ref_set_camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], None)  # zero distortion
+    r = R.ref_stereo(left, right, template_path, nf, c["n_levels"], c["scale_factor"])
+    assert r["status"] == 0
+    el = R.extract(left, nf, c["n_levels"], c["scale_factor"])
+    er = R.extract(right, nf, c["n_levels"], c["scale_factor"])
+    assert _same_kps(r["kl"], el.kps) and _same_kps(r["kr"], er.kps)
+    assert np.array_equal(r["dl"], el.desc) and np.array_equal(r["dr"], er.desc)
+    nm, ur, dp, _ = R.search_by_stereo(el, er, np.float32(c["fx"]), bf)
+    assert nm == r["n_matches"] and nm > 0.3 * len(el.kps)
+    assert np.array_equal(ur, r["u_right"]) and np.array_equal(dp, r["depth"])
+    # sanity: matched disparities sit at the synthetic disparity
+    m = ur >= 0
+    assert np.median(el.kps["x"][m] - ur[m]) == pytest.approx(disp, abs=1.0)
+
+
+def test_undistort_identical(R):
+    c = synth.TUM
+    R.ref_set_camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], np.array(c["dist"], np.float32))
+    rng = np.random.default_rng(5)
+    pts = np.stack([rng.uniform(19, 620, 1000), rng.uniform(19, 460, 1000)], 1).astype(np.float32)
+    a = R.undistort_points(pts, c["fx"], c["fy"], c["cx"], c["cy"], np.array(c["dist"], np.float32))
+    b = R.ref_undistort(pts)
+    assert np.array_equal(a, b)
+    R.ref_set_camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], None)
+    assert np.array_equal(R.ref_undistort(pts), pts)  # k1 == 0 -> early return (Camera.cc:31)
