@@ -1,0 +1,163 @@
+/*
+ * orbx.h -- C ABI of the B200-native ORB front-end (liborbx.so).
+ *
+ * Drop-in boundary for the per-frame feature path of sunshanlu/ORB_SLAM2_ROS2.  Every entry point names the
+ * reference interface it replaces (paths relative to /root/reference/src/ORB_SLAM2/).  Plain pointers and sizes
+ * only; the library owns all device memory and runs hand-written sm_100a kernels.  There is NO CPU fallback:
+ * orbx_create() fails with ORBX_ERR_NO_DEVICE / ORBX_ERR_CUDA when no usable CUDA device exists.
+ *
+ * Threading: a context is not re-entrant; independent contexts may be used from different host threads
+ * (the reference runs two ORBExtractor::extract() calls on two std::threads, src/Frame.cc:100-105 -- here the left
+ * and right images of a pair are processed by the same launches, so one call covers both).
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_VERSION 100
+
+/* status codes (0 = success).  The C++ shim (include/orbx/orb_slam2_shim.hpp) rethrows them as the reference's
+ * exception types from include/ORB_SLAM2/Error.h. */
+#define ORBX_OK 0
+#define ORBX_ERR_INVALID_ARG (-1)
+#define ORBX_ERR_IMAGE_SIZE (-2)    /* ImageSizeError: a pyramid level is smaller than 2*19 px (src/ORBExtractor.cc:310-314),
+                                       or too small for one 30-px FAST cell (the reference divides by zero, :340-343) */
+#define ORBX_ERR_FILE_NOT_OPEN (-3) /* FileNotOpenError: BRIEF template file (src/ORBExtractor.cc:247-250) */
+#define ORBX_ERR_CUDA (-4)
+#define ORBX_ERR_NO_DEVICE (-5)
+#define ORBX_ERR_CAPACITY (-6)      /* more frames than orbx_config.max_batch */
+#define ORBX_ERR_STATE (-7)         /* e.g. orbx_get_pyramid before any frame was processed */
+
+/* memory layout of cv::KeyPoint (28 bytes) so that results can be memcpy'd into std::vector<cv::KeyPoint> */
+typedef struct orbx_keypoint {
+  float x, y;      /* pt, level coordinates multiplied by the level scale factor (src/ORBExtractor.cc:408-409) */
+  float size;      /* 7 (cv::FAST) */
+  float angle;     /* degrees in (-180, 180]  (src/ORBExtractor.cc:407) */
+  float response;  /* FAST score */
+  int32_t octave;  /* pyramid level */
+  int32_t class_id;/* -1 */
+} orbx_keypoint;
+
+#define ORBX_DESC_BYTES 32
+#define ORBX_DEPTH_U16 0
+#define ORBX_DEPTH_F32 1
+
+/* Everything the reference reads from its YAML for this path (src/System.cc:27-73): ORBExtractor.* and Camera.* */
+typedef struct orbx_config {
+  int32_t width, height;   /* input image size (8-bit, single channel) */
+  int32_t n_features;      /* ORBExtractor.nFeatures */
+  int32_t n_levels;        /* ORBExtractor.nLevels */
+  float scale_factor;      /* ORBExtractor.scaleFactor (> 1) */
+  int32_t ini_th_fast;     /* ORBExtractor.iniThFAST */
+  int32_t min_th_fast;     /* ORBExtractor.minThFAST */
+  float fx, fy, cx, cy;    /* Camera.fx .. Camera.cy */
+  float bf;                /* Camera::mfBf = fx * Camera.bl (src/System.cc:60) */
+  float dist[5];           /* k1 k2 p1 p2 k3; undistortion is skipped when k1 == 0 (src/Camera.cc:31) */
+  float depth_scale;       /* Camera.DepthScale (RGB-D) */
+  int32_t max_batch;       /* frames one batch call may carry (>= 1) */
+  int32_t device;          /* CUDA device ordinal, -1 = current device */
+  const float *pattern;    /* 256 x (x1,y1,x2,y2) BRIEF test pairs, or NULL for the built-in bit_pattern_31_ */
+} orbx_config;
+
+typedef struct orbx_ctx orbx_ctx;
+
+/* ---- life cycle ---------------------------------------------------------------------------------------- */
+/* fills *cfg with the KITTI defaults of config/kitti_config_00.yaml */
+void orbx_default_config(orbx_config *cfg);
+/* replaces: ORBExtractor::ORBExtractor's table setup (initPyramid :283-317, initBriefTemplate, initMaxU) -- done once
+ * per context instead of once per process/frame */
+int orbx_create(const orbx_config *cfg, orbx_ctx **out);
+void orbx_destroy(orbx_ctx *ctx);
+const char *orbx_status_string(int status);
+/* text of the last CUDA / argument error seen by this context ("" if none) */
+const char *orbx_last_error(const orbx_ctx *ctx);
+/* replaces: ORBExtractor::initBriefTemplate (src/ORBExtractor.cc:242-267): header line + 256 rows "x1 y1 x2 y2" */
+int orbx_load_brief_template(const char *path, float *pattern_out /* [1024] */);
+/* launch on this CUDA stream (cudaStream_t) instead of the context's own; NULL restores the default */
+int orbx_set_stream(orbx_ctx *ctx, void *cuda_stream);
+
+/* ---- per-config tables ---------------------------------------------------------------------------------- */
+/* replaces: ORBExtractor::getScaledFactors() (include/ORB_SLAM2/ORBExtractor.h:116), ORBExtractor::mnLevels,
+ * mvnFeatures (:155) and the level sizes of getPyramid() */
+int orbx_num_levels(const orbx_ctx *ctx);
+int orbx_level_info(const orbx_ctx *ctx, int level, int32_t *width, int32_t *height, float *scale, int32_t *quota);
+
+/* ---- single frame, host buffers (the reference's call surface) ---------------------------------------- */
+/* replaces: ORBExtractor(image, ...) + ORBExtractor::extract(keyPoints, descriptors)
+ * (include/ORB_SLAM2/ORBExtractor.h:107,110; src/ORBExtractor.cc:205-214,499-508).
+ * kps: capacity n_features; desc: n_features x 32 bytes (row i is the reference's descriptors[i], a 1x32 CV_8U Mat). */
+int orbx_extract(orbx_ctx *ctx, const uint8_t *image, size_t stride, orbx_keypoint *kps, uint8_t *desc, int32_t *n);
+
+/* replaces: ORBExtractor::getPyramid() (include/ORB_SLAM2/ORBExtractor.h:113), Frame::getLeftPyramid/getRightPyramid
+ * (include/ORB_SLAM2/Frame.h:346-347) for the most recent single-frame call.  side: 0 = left / mono, 1 = right.
+ * blurred != 0 returns the Gaussian-blurred level (the private mvBriefMat, :152). */
+int orbx_get_pyramid(orbx_ctx *ctx, int side, int level, int blurred, uint8_t *dst, size_t dst_stride);
+
+/* replaces: Frame::createStereo (include/ORB_SLAM2/Frame.h:313-322) = Frame::Frame stereo ctor (src/Frame.cc:85-111:
+ * two extractors, Camera::undistortPoints on the left keypoints) + ORBMatcher::searchByStereo (src/ORBMatcher.cc:18-81).
+ * kps_left are the undistorted left keypoints (mvFeatsLeft), u_right / depth = mvFeatsRightU / mvDepths (-1 = none),
+ * *n_matches = Frame::mnN.  Any output pointer may be NULL. */
+int orbx_stereo_frame(orbx_ctx *ctx, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
+                      orbx_keypoint *kps_left, uint8_t *desc_left, int32_t *n_left, orbx_keypoint *kps_right,
+                      uint8_t *desc_right, int32_t *n_right, double *u_right, double *depth, int32_t *n_matches);
+
+/* replaces: Frame::createRGBD (include/ORB_SLAM2/Frame.h:325-331) = RGB-D ctor (src/Frame.cc:125-159).
+ * depth_image: raw sensor depth (uint16 or float32, row stride in BYTES), divided by depth_scale on the fly.
+ * kps_raw (optional) are the keypoints before undistortion (used for the lookup), kps the undistorted ones. */
+int orbx_rgbd_frame(orbx_ctx *ctx, const uint8_t *gray, size_t gray_stride, const void *depth_image,
+                    size_t depth_stride_bytes, int depth_type, orbx_keypoint *kps_raw, orbx_keypoint *kps,
+                    uint8_t *desc, int32_t *n, double *u_right, double *depth);
+
+/* ---- batches (offline map / vocabulary building: frames are independent) -------------------------------- */
+/* n_frames <= max_batch stereo pairs from HOST memory (pinned memory makes the copies asynchronous).
+ * left/right: frame f at base + f * frame_stride bytes, rows `stride` bytes apart.  Outputs are fixed-stride arrays:
+ * kps_*[f * n_features + i], desc_*[(f * n_features + i) * 32], u_right/depth[f * n_features + i], n_*[f].
+ * Returns after all results have landed in the output arrays. */
+int orbx_stereo_batch(orbx_ctx *ctx, int n_frames, const uint8_t *left, const uint8_t *right, size_t stride,
+                      size_t frame_stride, orbx_keypoint *kps_left, uint8_t *desc_left, int32_t *n_left,
+                      orbx_keypoint *kps_right, uint8_t *desc_right, int32_t *n_right, double *u_right, double *depth,
+                      int32_t *n_matches);
+
+/* device-resident results of the last *_device call; pointers stay valid until the next call on the context.
+ * Image index: stereo frame f -> left image 2f, right image 2f+1; mono / RGB-D frame f -> image f. */
+typedef struct orbx_device_results {
+  const orbx_keypoint *kps;     /* [n_images][n_features] raw keypoints */
+  const orbx_keypoint *kps_und; /* [n_images][n_features] undistorted keypoints (== kps when k1 == 0) */
+  const uint8_t *desc;          /* [n_images][n_features][32] */
+  const int32_t *n_kps;         /* [n_images] */
+  const double *u_right;        /* [n_frames][n_features] */
+  const double *depth;          /* [n_frames][n_features] */
+  const int32_t *n_matches;     /* [n_frames] */
+  int32_t n_images, n_frames, n_features;
+} orbx_device_results;
+
+/* same work as orbx_stereo_batch with inputs already in DEVICE memory; asynchronous on the context's stream
+ * (orbx_set_stream); no host synchronisation. */
+int orbx_stereo_batch_device(orbx_ctx *ctx, int n_frames, const uint8_t *d_left, const uint8_t *d_right, size_t stride,
+                             size_t frame_stride, orbx_device_results *out);
+/* mono extraction of n_images device-resident images (ORBExtractor only) */
+int orbx_extract_batch_device(orbx_ctx *ctx, int n_images, const uint8_t *d_images, size_t stride, size_t frame_stride,
+                              orbx_device_results *out);
+/* RGB-D frames with device-resident gray + depth images */
+int orbx_rgbd_batch_device(orbx_ctx *ctx, int n_frames, const uint8_t *d_gray, size_t gray_stride,
+                           size_t gray_frame_stride, const void *d_depth, size_t depth_stride_bytes,
+                           size_t depth_frame_stride_bytes, int depth_type, orbx_device_results *out);
+/* block until the context's stream is idle */
+int orbx_synchronize(orbx_ctx *ctx);
+
+/* ---- introspection for benchmarks / profiles ----------------------------------------------------------- */
+/* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
+int64_t orbx_launch_count(const orbx_ctx *ctx);
+/* algorithmic bytes of one stereo frame / one mono image at this configuration */
+int64_t orbx_algorithmic_bytes(const orbx_ctx *ctx, int stereo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

@@ -1,0 +1,433 @@
+"""Python host-side mirror of the reference interface, bound to liborbx.so through ctypes.
+
+The names follow the reference (include/ORB_SLAM2/ORBExtractor.h:99-161, include/ORB_SLAM2/Frame.h:303-371,
+include/ORB_SLAM2/ORBMatcher.h:39): ``ORBExtractor(image, nFeatures, pyramidLevels, scaleFactor, bfTemFp, maxThreshold,
+minThreshold).extract()``, ``Frame.createStereo(...)``, ``Frame.createRGBD(...)``.  All compute happens in the CUDA
+library; there is no CPU fallback -- loading fails loudly when liborbx.so or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liborbx.so")
+
+KP_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")]
+)
+
+ORBX_OK = 0
+ORBX_ERR_INVALID_ARG = -1
+ORBX_ERR_IMAGE_SIZE = -2
+ORBX_ERR_FILE_NOT_OPEN = -3
+ORBX_ERR_CUDA = -4
+ORBX_ERR_NO_DEVICE = -5
+ORBX_ERR_CAPACITY = -6
+ORBX_ERR_STATE = -7
+DEPTH_U16, DEPTH_F32 = 0, 1
+
+
+# the reference's exception types (include/ORB_SLAM2/Error.h:13-98)
+class ORBSlam2Error(RuntimeError):
+    pass
+
+
+class ImageSizeError(ORBSlam2Error):
+    pass
+
+
+class FileNotOpenError(ORBSlam2Error):
+    pass
+
+
+class OrbxCudaError(ORBSlam2Error):
+    pass
+
+
+class OrbxConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("n_features", C.c_int32), ("n_levels", C.c_int32), ("scale_factor", C.c_float),
+        ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("bf", C.c_float), ("dist", C.c_float * 5), ("depth_scale", C.c_float), ("max_batch", C.c_int32), ("device", C.c_int32),
+        ("pattern", C.POINTER(C.c_float)),
+    ]
+
+
+class OrbxDeviceResults(C.Structure):
+    _fields_ = [
+        ("kps", C.c_void_p), ("kps_und", C.c_void_p), ("desc", C.c_void_p), ("n_kps", C.c_void_p), ("u_right", C.c_void_p), ("depth", C.c_void_p),
+        ("n_matches", C.c_void_p), ("n_images", C.c_int32), ("n_frames", C.c_int32), ("n_features", C.c_int32),
+    ]
+
+
+EXPORTS = [
+    "orbx_default_config", "orbx_create", "orbx_destroy", "orbx_status_string", "orbx_last_error", "orbx_load_brief_template", "orbx_set_stream",
+    "orbx_num_levels", "orbx_level_info", "orbx_extract", "orbx_get_pyramid", "orbx_stereo_frame", "orbx_rgbd_frame", "orbx_stereo_batch",
+    "orbx_stereo_batch_device", "orbx_extract_batch_device", "orbx_rgbd_batch_device", "orbx_synchronize", "orbx_launch_count", "orbx_algorithmic_bytes",
+]
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen liborbx.so (building it with nvcc first when absent).  Raises if it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise OSError(f"{LIB_PATH} is missing: run `python -m orb_slam2_ros2_b200.build`")
+        from . import build as _b
+
+        _b.build()
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, i32p, f64p, sz = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t
+    L.orbx_default_config.argtypes = [C.POINTER(OrbxConfig)]
+    L.orbx_default_config.restype = None
+    L.orbx_create.argtypes = [C.POINTER(OrbxConfig), C.POINTER(vp)]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_destroy.restype = None
+    L.orbx_status_string.argtypes = [C.c_int]
+    L.orbx_status_string.restype = C.c_char_p
+    L.orbx_last_error.argtypes = [vp]
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_load_brief_template.argtypes = [C.c_char_p, C.POINTER(C.c_float)]
+    L.orbx_set_stream.argtypes = [vp, vp]
+    L.orbx_num_levels.argtypes = [vp]
+    L.orbx_level_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    L.orbx_extract.argtypes = [vp, u8p, sz, vp, u8p, i32p]
+    L.orbx_get_pyramid.argtypes = [vp, C.c_int, C.c_int, C.c_int, u8p, sz]
+    L.orbx_stereo_frame.argtypes = [vp, u8p, sz, u8p, sz, vp, u8p, i32p, vp, u8p, i32p, f64p, f64p, i32p]
+    L.orbx_rgbd_frame.argtypes = [vp, u8p, sz, vp, sz, C.c_int, vp, vp, u8p, i32p, f64p, f64p]
+    L.orbx_stereo_batch.argtypes = [vp, C.c_int, u8p, u8p, sz, sz, vp, u8p, i32p, vp, u8p, i32p, f64p, f64p, i32p]
+    L.orbx_stereo_batch_device.argtypes = [vp, C.c_int, vp, vp, sz, sz, C.POINTER(OrbxDeviceResults)]
+    L.orbx_extract_batch_device.argtypes = [vp, C.c_int, vp, sz, sz, C.POINTER(OrbxDeviceResults)]
+    L.orbx_rgbd_batch_device.argtypes = [vp, C.c_int, vp, sz, sz, vp, sz, sz, C.c_int, C.POINTER(OrbxDeviceResults)]
+    L.orbx_synchronize.argtypes = [vp]
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbx_launch_count.restype = C.c_int64
+    L.orbx_algorithmic_bytes.argtypes = [vp, C.c_int]
+    L.orbx_algorithmic_bytes.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def _check(ctx, rc: int, what: str):
+    if rc == ORBX_OK:
+        return
+    L = load_library()
+    msg = L.orbx_status_string(rc).decode()
+    detail = L.orbx_last_error(ctx).decode() if ctx else ""
+    text = f"{what}: {msg}" + (f" ({detail})" if detail else "")
+    if rc == ORBX_ERR_IMAGE_SIZE:
+        raise ImageSizeError(text)
+    if rc == ORBX_ERR_FILE_NOT_OPEN:
+        raise FileNotOpenError(text)
+    if rc in (ORBX_ERR_CUDA, ORBX_ERR_NO_DEVICE):
+        raise OrbxCudaError(text)
+    raise ValueError(text)
+
+
+def load_brief_template(path: str) -> np.ndarray:
+    """ORBExtractor::initBriefTemplate (src/ORBExtractor.cc:242-267) -> (256, 4) float32; FileNotOpenError if missing."""
+    out = np.zeros(1024, np.float32)
+    rc = load_library().orbx_load_brief_template(path.encode(), out.ctypes.data_as(C.POINTER(C.c_float)))
+    _check(None, rc, f"BRIEF template {path!r}")
+    return out.reshape(256, 4)
+
+
+@dataclass
+class Camera:
+    """ORB_SLAM2_ROS2::Camera statics (include/ORB_SLAM2/Camera.h:23-32) as set by System::setSetting (src/System.cc:27-73)."""
+
+    fx: float = 718.856
+    fy: float = 718.856
+    cx: float = 607.1928
+    cy: float = 185.2157
+    bl: float = 0.537166
+    dist: tuple = (0.0, 0.0, 0.0, 0.0, 0.0)
+    depth_scale: float = 1.0
+
+    @property
+    def bf(self) -> np.float32:
+        return np.float32(self.fx) * np.float32(self.bl)  # Camera::mfBf = mfFx * mfBl in float (src/System.cc:60)
+
+
+class Context:
+    """One configured front-end (owns all device memory).  Thin wrapper over orbx_create / orbx_destroy."""
+
+    def __init__(self, width, height, n_features=2000, n_levels=8, scale_factor=1.2, ini_th=20, min_th=7, camera: Camera | None = None, max_batch=1,
+                 device=-1, pattern: np.ndarray | None = None):
+        L = load_library()
+        cam = camera or Camera()
+        cfg = OrbxConfig()
+        L.orbx_default_config(C.byref(cfg))
+        cfg.width, cfg.height, cfg.n_features, cfg.n_levels = int(width), int(height), int(n_features), int(n_levels)
+        cfg.scale_factor, cfg.ini_th_fast, cfg.min_th_fast = float(scale_factor), int(ini_th), int(min_th)
+        cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.bf = cam.fx, cam.fy, cam.cx, cam.cy, float(cam.bf)
+        for i in range(5):
+            cfg.dist[i] = float(cam.dist[i]) if i < len(cam.dist) else 0.0
+        cfg.depth_scale, cfg.max_batch, cfg.device = float(cam.depth_scale), int(max_batch), int(device)
+        self._pattern = None
+        if pattern is not None:
+            self._pattern = np.ascontiguousarray(pattern, np.float32).reshape(-1)
+            cfg.pattern = self._pattern.ctypes.data_as(C.POINTER(C.c_float))
+        self._h = C.c_void_p()
+        self.width, self.height, self.n_features, self.n_levels, self.max_batch = int(width), int(height), int(n_features), int(n_levels), int(max_batch)
+        self.camera = cam
+        rc = L.orbx_create(C.byref(cfg), C.byref(self._h))
+        if rc != ORBX_OK:
+            self._h = C.c_void_p()
+        _check(None, rc, "orbx_create")
+        self._L = L
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.orbx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables -------------------------------------------------------------------------------------------
+    def level_info(self, level: int):
+        w, h, q, s = C.c_int32(), C.c_int32(), C.c_int32(), C.c_float()
+        _check(self._h, self._L.orbx_level_info(self._h, level, C.byref(w), C.byref(h), C.byref(s), C.byref(q)), "orbx_level_info")
+        return w.value, h.value, np.float32(s.value), q.value
+
+    def scaled_factors(self) -> np.ndarray:
+        return np.array([self.level_info(l)[2] for l in range(self.n_levels)], np.float32)
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        _check(self._h, self._L.orbx_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "orbx_set_stream")
+
+    def synchronize(self):
+        _check(self._h, self._L.orbx_synchronize(self._h), "orbx_synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.orbx_launch_count(self._h))
+
+    def algorithmic_bytes(self, stereo: bool = True) -> int:
+        return int(self._L.orbx_algorithmic_bytes(self._h, 1 if stereo else 0))
+
+    # ---- single frame, host buffers -----------------------------------------------------------------------------
+    def extract(self, image: np.ndarray):
+        img = _as_u8(image, self.height, self.width)
+        N = self.n_features
+        kps, desc, n = np.zeros(N, KP_DTYPE), np.zeros((N, 32), np.uint8), C.c_int32(0)
+        rc = self._L.orbx_extract(self._h, img.ctypes.data, img.strides[0], kps.ctypes.data, desc.ctypes.data, C.addressof(n))
+        _check(self._h, rc, "orbx_extract")
+        return kps[: n.value], desc[: n.value]
+
+    def get_pyramid(self, side: int = 0, blurred: bool = False):
+        out = []
+        for l in range(self.n_levels):
+            w, h, _, _ = self.level_info(l)
+            a = np.zeros((h, w), np.uint8)
+            _check(self._h, self._L.orbx_get_pyramid(self._h, side, l, int(blurred), a.ctypes.data, a.strides[0]), "orbx_get_pyramid")
+            out.append(a)
+        return out
+
+    def stereo_frame(self, left: np.ndarray, right: np.ndarray):
+        l, r = _as_u8(left, self.height, self.width), _as_u8(right, self.height, self.width)
+        N = self.n_features
+        kl, kr = np.zeros(N, KP_DTYPE), np.zeros(N, KP_DTYPE)
+        dl, dr = np.zeros((N, 32), np.uint8), np.zeros((N, 32), np.uint8)
+        ur, dp = np.zeros(N, np.float64), np.zeros(N, np.float64)
+        nl, nr, nm = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        rc = self._L.orbx_stereo_frame(self._h, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0], kl.ctypes.data, dl.ctypes.data, C.addressof(nl),
+                                       kr.ctypes.data, dr.ctypes.data, C.addressof(nr), ur.ctypes.data, dp.ctypes.data, C.addressof(nm))
+        _check(self._h, rc, "orbx_stereo_frame")
+        a, b = nl.value, nr.value
+        return StereoResult(kl[:a], dl[:a], kr[:b], dr[:b], ur[:a], dp[:a], nm.value)
+
+    def rgbd_frame(self, gray: np.ndarray, depth_image: np.ndarray):
+        g = _as_u8(gray, self.height, self.width)
+        if depth_image.dtype == np.float32:
+            d, dt = np.ascontiguousarray(depth_image), DEPTH_F32
+        else:
+            d, dt = np.ascontiguousarray(depth_image, np.uint16), DEPTH_U16
+        assert d.shape == (self.height, self.width)
+        N = self.n_features
+        kraw, kund = np.zeros(N, KP_DTYPE), np.zeros(N, KP_DTYPE)
+        desc, ur, dp, n = np.zeros((N, 32), np.uint8), np.zeros(N, np.float64), np.zeros(N, np.float64), C.c_int32(0)
+        rc = self._L.orbx_rgbd_frame(self._h, g.ctypes.data, g.strides[0], d.ctypes.data, d.strides[0], dt, kraw.ctypes.data, kund.ctypes.data,
+                                     desc.ctypes.data, C.addressof(n), ur.ctypes.data, dp.ctypes.data)
+        _check(self._h, rc, "orbx_rgbd_frame")
+        k = n.value
+        return RGBDResult(kraw[:k], kund[:k], desc[:k], ur[:k], dp[:k])
+
+    # ---- batches ----------------------------------------------------------------------------------------------------
+    def stereo_batch(self, left: np.ndarray, right: np.ndarray, out: "StereoBatchBuffers | None" = None):
+        """left/right: (n, H, W) uint8 host arrays (pinned memory makes the copies asynchronous)."""
+        n = left.shape[0]
+        assert left.shape == right.shape == (n, self.height, self.width) and left.strides == right.strides and left.dtype == np.uint8
+        ob = out or StereoBatchBuffers.numpy(n, self.n_features)
+        rc = self._L.orbx_stereo_batch(self._h, n, left.ctypes.data, right.ctypes.data, left.strides[1], left.strides[0], ob.kps_left.ctypes.data,
+                                       ob.desc_left.ctypes.data, ob.n_left.ctypes.data, ob.kps_right.ctypes.data, ob.desc_right.ctypes.data,
+                                       ob.n_right.ctypes.data, ob.u_right.ctypes.data, ob.depth.ctypes.data, ob.n_matches.ctypes.data)
+        _check(self._h, rc, "orbx_stereo_batch")
+        return ob
+
+    def stereo_batch_ptr(self, n_frames, left_ptr, right_ptr, stride, frame_stride, ptrs):
+        """raw-pointer variant of stereo_batch (host pointers; ptrs = 9 output addresses or 0)."""
+        rc = self._L.orbx_stereo_batch(self._h, n_frames, left_ptr, right_ptr, stride, frame_stride, *[C.c_void_p(q or 0) for q in ptrs])
+        _check(self._h, rc, "orbx_stereo_batch")
+
+    def stereo_batch_device(self, n_frames, d_left_ptr, d_right_ptr, stride, frame_stride) -> OrbxDeviceResults:
+        res = OrbxDeviceResults()
+        rc = self._L.orbx_stereo_batch_device(self._h, n_frames, C.c_void_p(d_left_ptr), C.c_void_p(d_right_ptr), stride, frame_stride, C.byref(res))
+        _check(self._h, rc, "orbx_stereo_batch_device")
+        return res
+
+    def extract_batch_device(self, n_images, d_ptr, stride, frame_stride) -> OrbxDeviceResults:
+        res = OrbxDeviceResults()
+        rc = self._L.orbx_extract_batch_device(self._h, n_images, C.c_void_p(d_ptr), stride, frame_stride, C.byref(res))
+        _check(self._h, rc, "orbx_extract_batch_device")
+        return res
+
+    def rgbd_batch_device(self, n_frames, d_gray, gstride, gframe, d_depth, dstride, dframe, depth_type) -> OrbxDeviceResults:
+        res = OrbxDeviceResults()
+        rc = self._L.orbx_rgbd_batch_device(self._h, n_frames, C.c_void_p(d_gray), gstride, gframe, C.c_void_p(d_depth), dstride, dframe, depth_type,
+                                            C.byref(res))
+        _check(self._h, rc, "orbx_rgbd_batch_device")
+        return res
+
+
+def _as_u8(a: np.ndarray, h: int, w: int) -> np.ndarray:
+    if a.dtype != np.uint8 or a.ndim != 2 or a.shape != (h, w):
+        raise ValueError(f"expected a {h}x{w} uint8 image, got {a.shape} {a.dtype}")
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+@dataclass
+class StereoResult:
+    kps_left: np.ndarray
+    desc_left: np.ndarray
+    kps_right: np.ndarray
+    desc_right: np.ndarray
+    u_right: np.ndarray
+    depth: np.ndarray
+    n_matches: int
+
+
+@dataclass
+class RGBDResult:
+    kps_raw: np.ndarray
+    kps: np.ndarray
+    desc: np.ndarray
+    u_right: np.ndarray
+    depth: np.ndarray
+
+
+@dataclass
+class StereoBatchBuffers:
+    kps_left: np.ndarray
+    desc_left: np.ndarray
+    n_left: np.ndarray
+    kps_right: np.ndarray
+    desc_right: np.ndarray
+    n_right: np.ndarray
+    u_right: np.ndarray
+    depth: np.ndarray
+    n_matches: np.ndarray
+
+    @staticmethod
+    def numpy(n: int, n_features: int) -> "StereoBatchBuffers":
+        N = n_features
+        return StereoBatchBuffers(np.zeros((n, N), KP_DTYPE), np.zeros((n, N, 32), np.uint8), np.zeros(n, np.int32), np.zeros((n, N), KP_DTYPE),
+                                  np.zeros((n, N, 32), np.uint8), np.zeros(n, np.int32), np.zeros((n, N), np.float64), np.zeros((n, N), np.float64),
+                                  np.zeros(n, np.int32))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference-shaped classes
+# ----------------------------------------------------------------------------------------------------------------
+_ctx_cache: dict = {}
+
+
+def _context_for(h, w, n_features, n_levels, scale, ini_th, min_th, camera: Camera, pattern_key, pattern) -> Context:
+    key = (h, w, n_features, n_levels, float(scale), ini_th, min_th, camera.fx, camera.fy, camera.cx, camera.cy, camera.bl, tuple(camera.dist),
+           camera.depth_scale, pattern_key)
+    ctx = _ctx_cache.get(key)
+    if ctx is None:
+        ctx = Context(w, h, n_features, n_levels, scale, ini_th, min_th, camera, max_batch=1, pattern=pattern)
+        _ctx_cache[key] = ctx
+    return ctx
+
+
+class ORBExtractor:
+    """Mirror of ORB_SLAM2_ROS2::ORBExtractor (include/ORB_SLAM2/ORBExtractor.h:99-161).
+
+    The constructor takes the image (the reference builds the pyramid there, src/ORBExtractor.cc:205-214); ``extract()``
+    returns (keypoints, descriptors) where descriptors[i] is the reference's i-th 1x32 CV_8U Mat.
+    """
+
+    mnBorderSize = 19
+
+    def __init__(self, image: np.ndarray, nFeatures: int, pyramidLevels: int, scaleFactor: float, bfTemFp: str | None, maxThreshold: int,
+                 minThreshold: int, camera: Camera | None = None):
+        pattern = load_brief_template(bfTemFp) if bfTemFp else None  # FileNotOpenError like :247-250
+        self._image = image
+        h, w = image.shape
+        self._ctx = _context_for(h, w, nFeatures, pyramidLevels, scaleFactor, maxThreshold, minThreshold, camera or Camera(), bfTemFp, pattern)
+        self._done = False
+
+    def extract(self):
+        kps, desc = self._ctx.extract(self._image)
+        self._done = True
+        return kps, desc
+
+    def getPyramid(self):
+        if not self._done:
+            self.extract()
+        return self._ctx.get_pyramid(0)
+
+    def getScaledFactors(self) -> np.ndarray:
+        return self._ctx.scaled_factors()
+
+
+@dataclass
+class Frame:
+    """The per-frame outputs of ORB_SLAM2_ROS2::Frame that belong to the hot path (include/ORB_SLAM2/Frame.h:263-274)."""
+
+    mvFeatsLeft: np.ndarray
+    mvLeftDescriptor: np.ndarray
+    mvFeatsRight: np.ndarray | None
+    mRightDescriptor: np.ndarray | None
+    mvFeatsRightU: np.ndarray
+    mvDepths: np.ndarray
+    mnN: int
+    extra: dict = field(default_factory=dict)
+
+    @staticmethod
+    def createStereo(leftImg, rightImg, nFeatures, briefFp, maxThresh, minThresh, pVoc=None, nLevels=8, scale=1.2, camera: Camera | None = None) -> "Frame":
+        """Frame::createStereo (include/ORB_SLAM2/Frame.h:313-322)."""
+        pattern = load_brief_template(briefFp) if briefFp else None
+        h, w = leftImg.shape
+        ctx = _context_for(h, w, nFeatures, nLevels, scale, maxThresh, minThresh, camera or Camera(), briefFp, pattern)
+        r = ctx.stereo_frame(leftImg, rightImg)
+        return Frame(r.kps_left, r.desc_left, r.kps_right, r.desc_right, r.u_right, r.depth, r.n_matches, {"ctx": ctx})
+
+    @staticmethod
+    def createRGBD(colorImg, depthImg, nFeatures, briefF, maxThresh, minThresh, pVoc=None, dScale=1.0, nLevels=8, scale=1.2,
+                   camera: Camera | None = None) -> "Frame":
+        """Frame::createRGBD (include/ORB_SLAM2/Frame.h:325-331)."""
+        import dataclasses
+
+        cam = dataclasses.replace(camera or Camera(), depth_scale=float(dScale))
+        pattern = load_brief_template(briefF) if briefF else None
+        h, w = colorImg.shape
+        ctx = _context_for(h, w, nFeatures, nLevels, scale, maxThresh, minThresh, cam, briefF, pattern)
+        r = ctx.rgbd_frame(colorImg, depthImg)
+        return Frame(r.kps, r.desc, None, None, r.u_right, r.depth, int((r.depth > 0).sum()), {"ctx": ctx, "kps_raw": r.kps_raw})

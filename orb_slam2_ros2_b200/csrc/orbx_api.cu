@@ -1,0 +1,730 @@
+// orbx_api.cu -- host layer behind the C ABI of include/orbx.h: per-context tables, device buffers, launch sequences.
+//
+// The per-config tables restate ORBExtractor::initPyramid's bookkeeping (src/ORBExtractor.cc:283-317) and the FAST cell
+// grid of extractFast (:334-362) once per context -- the reference recomputes them per frame and keeps part of them in
+// process-wide statics (:511-524); here nothing is static, so contexts with different configurations can coexist.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/orbx_pattern.h"
+#include "orbx_device.cuh"
+
+using namespace orbx;
+
+struct orbx_ctx
+{
+  orbx_config cfg;
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int n_img_max = 0;
+  std::vector<Level> levels;
+  std::vector<Tile> tiles;
+  std::vector<Cell> cells;
+  Params p;            // template: geometry + base pointers
+  size_t qt_smem = 0;
+  std::string last_error;
+  int64_t launches = 0;
+  int64_t alg_bytes_image = 0, alg_bytes_stereo = 0;
+  // device allocations
+  std::vector<void *> allocs;
+  uint8_t *d_in = nullptr;      // staging for host-side calls: [n_img_max][H][in_pitch]
+  size_t in_pitch = 0;
+  uint8_t *d_depth_in = nullptr; // [max_batch][H][W] float/uint16 (sized for float)
+  int last_images = 0;          // images processed by the most recent call (for orbx_get_pyramid)
+  int last_stereo = 0;
+};
+
+namespace
+{
+
+inline int cv_round(float v) { return (int)lrintf(v); }  // cvRound: round half to even (default FP environment)
+inline int cv_round(double v) { return (int)lrint(v); }
+inline int cv_floor(float v)
+{
+  int i = (int)v;
+  return i - (i > v);
+}
+
+int fail(orbx_ctx *c, int code, const std::string &msg)
+{
+  if (c) c->last_error = msg;
+  return code;
+}
+
+#define ORBX_CUDA(ctx, expr)                                                                                         \
+  do                                                                                                                 \
+  {                                                                                                                  \
+    cudaError_t e__ = (expr);                                                                                        \
+    if (e__ != cudaSuccess) return fail((ctx), ORBX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+template <typename T> int dev_alloc(orbx_ctx *c, T **ptr, size_t count)
+{
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e != cudaSuccess) return fail(c, ORBX_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  c->allocs.push_back(q);
+  *ptr = (T *)q;
+  return ORBX_OK;
+}
+
+template <typename T> int dev_upload(orbx_ctx *c, const T **ptr, const std::vector<T> &v)
+{
+  T *d = nullptr;
+  int rc = dev_alloc(c, &d, v.size() ? v.size() : 1);
+  if (rc) return rc;
+  if (!v.empty()) ORBX_CUDA(c, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *ptr = d;
+  return ORBX_OK;
+}
+
+// cv::resize INTER_LINEAR coefficient tables (OpenCV imgproc/resize.cpp): 11-bit fixed point, computed in float
+void build_resize_axis(int src_n, int dst_n, bool zero_at_border, std::vector<int> &ofs, std::vector<short2> &coef)
+{
+  const double scale = 1.0 / ((double)dst_n / (double)src_n);
+  for (int d = 0; d < dst_n; ++d)
+  {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = cv_floor(f);
+    f -= (float)s;
+    if (zero_at_border)
+    { // columns: taps are re-weighted at the border; rows are clamped by the kernel instead
+      if (s < 0)
+      {
+        f = 0.f;
+        s = 0;
+      }
+      if (s >= src_n - 1)
+      {
+        f = 0.f;
+        s = src_n - 1;
+      }
+    }
+    int a0 = cv_round((1.f - f) * 2048.f), a1 = cv_round(f * 2048.f);
+    a0 = a0 < -32768 ? -32768 : (a0 > 32767 ? 32767 : a0);
+    a1 = a1 < -32768 ? -32768 : (a1 > 32767 ? 32767 : a1);
+    ofs.push_back(s);
+    coef.push_back(make_short2((short)a0, (short)a1));
+  }
+}
+
+int build_tables(orbx_ctx *c)
+{
+  const orbx_config &g = c->cfg;
+  const int nl = g.n_levels;
+  c->levels.assign(nl, Level());
+  std::vector<int> tab_ofs;
+  std::vector<short2> tab_coef;
+  std::vector<double> strips;
+
+  // scale factors (:283-289), per-level quotas (:291-301), level sizes (:305-317)
+  std::vector<float> sf(nl);
+  for (int l = 0; l < nl; ++l) sf[l] = (float)std::pow((double)g.scale_factor, (double)l);
+  {
+    const float scale = 1.0f / g.scale_factor;
+    int sum = 0;
+    int nfeats = cv_round((double)((float)g.n_features * (1 - scale)) / (1 - std::pow((double)scale, (double)nl)));
+    for (int l = 0; l < nl - 1; ++l)
+    {
+      c->levels[l].quota = nfeats;
+      sum += nfeats;
+      nfeats = cv_round((float)nfeats * scale);
+    }
+    c->levels[nl - 1].quota = std::max(0, g.n_features - sum);
+  }
+  size_t pyr_off = 0;
+  int cell_index = 0, sel_off = 0;
+  size_t slot_off = 0, scratch_off = 0;
+  int max_quota = 0, max_ini = 0;
+  c->tiles.clear();
+  c->cells.clear();
+  for (int l = 0; l < nl; ++l)
+  {
+    Level &L = c->levels[l];
+    L.sf = sf[l];
+    L.w = l == 0 ? g.width : cv_round((float)g.width / sf[l]);
+    L.h = l == 0 ? g.height : cv_round((float)g.height / sf[l]);
+    if (L.w < 2 * 19 || L.h < 2 * 19) return fail(c, ORBX_ERR_IMAGE_SIZE, "pyramid level smaller than 2*19 px");
+    L.pitch = (L.w + 15) & ~15;
+    L.pyr_off = (int)pyr_off;
+    pyr_off += (size_t)L.pitch * L.h;
+    pyr_off = (pyr_off + 255) & ~(size_t)255;
+    L.area2x = (l > 0 && L.w * 2 == g.width && L.h * 2 == g.height) ? 1 : 0;
+    if (l > 0)
+    {
+      L.tab_x = (int)tab_ofs.size();
+      build_resize_axis(g.width, L.w, true, tab_ofs, tab_coef);
+      L.tab_y = (int)tab_ofs.size();
+      build_resize_axis(g.height, L.h, false, tab_ofs, tab_coef);
+    }
+    for (int y0 = 0; y0 < L.h; y0 += kTileH)
+      for (int x0 = 0; x0 < L.w; x0 += kTileW) c->tiles.push_back(Tile{l, x0, y0, 0});
+
+    // FAST cell grid (:334-362)
+    const int maxBX = L.w - kEdge, maxBY = L.h - kEdge;
+    const int w = maxBX - kEdge, h = maxBY - kEdge;
+    L.roi_w = w;
+    L.roi_h = h;
+    L.n_cols = w / 30;
+    L.n_rows = h / 30;
+    if (L.n_cols <= 0 || L.n_rows <= 0) return fail(c, ORBX_ERR_IMAGE_SIZE, "pyramid level too small for one 30-px FAST cell");
+    L.w_cell = w / L.n_cols; // ceil() of an integer quotient (:342-343)
+    L.h_cell = h / L.n_rows;
+    L.cell_base = cell_index;
+    L.list_cap = 0;
+    for (int i = 0; i < L.n_rows; ++i)
+    {
+      const int iniY = kEdge + i * L.h_cell;
+      int maxY = iniY + L.h_cell + 6;
+      if (iniY >= maxBY - 6) continue;
+      if (maxY > maxBY) maxY = maxBY;
+      for (int j = 0; j < L.n_cols; ++j)
+      {
+        const int iniX = kEdge + j * L.w_cell;
+        int maxX = iniX + L.w_cell + 6;
+        if (iniX >= maxBX - 6) continue;
+        if (maxX > maxBX) maxX = maxBX;
+        Cell ce;
+        ce.level = l;
+        ce.x0 = iniX;
+        ce.y0 = iniY;
+        ce.pw = maxX - iniX;
+        ce.ph = maxY - iniY;
+        if (ce.pw > kMaxPatch || ce.ph > kMaxPatch) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cell patch exceeds 72 px");
+        const int zw = std::max(0, ce.pw - 6), zh = std::max(0, ce.ph - 6);
+        ce.cap = std::max(1, ((zw + 1) / 2) * ((zh + 1) / 2)); // strict 8-neighbour maxima cannot be denser than this
+        ce.slot = (int)slot_off;
+        ce.pad = 0;
+        slot_off += (size_t)ce.cap;
+        L.list_cap += ce.cap;
+        c->cells.push_back(ce);
+        ++cell_index;
+      }
+    }
+    L.n_level_cells = cell_index - L.cell_base;
+
+    // quadtree root fan-out (initSplit :81-96)
+    L.n_ini = (int)std::round((double)w / (double)h);
+    if (L.n_ini > kMaxStrips) return fail(c, ORBX_ERR_INVALID_ARG, "aspect ratio too extreme (more than 255 root strips)");
+    if (L.n_ini < 0) L.n_ini = 0;
+    L.strip_off = (int)strips.size();
+    {
+      const float hX = (float)((double)w / (double)L.n_ini);
+      strips.push_back(0.0);
+      for (int k = 1; k < L.n_ini; ++k) strips.push_back((double)((float)k * hX));
+      strips.push_back((double)w);
+    }
+    L.sel_off = sel_off;
+    sel_off += std::max(1, L.quota);
+    L.scratch_off = (int)scratch_off;
+    scratch_off += ((size_t)L.list_cap * 17 + 8 + 3) / 4 + 4;
+    scratch_off = (scratch_off + 3) & ~(size_t)3;
+    max_quota = std::max(max_quota, L.quota);
+    max_ini = std::max(max_ini, L.n_ini);
+  }
+  if (g.width > 4080 || g.height > 4080) return fail(c, ORBX_ERR_INVALID_ARG, "images larger than 4080 px are not supported");
+
+  Params &p = c->p;
+  std::memset(&p, 0, sizeof(p));
+  p.n_levels = nl;
+  p.n_features = g.n_features;
+  p.ini_th = g.ini_th_fast;
+  p.min_th = g.min_th_fast;
+  p.n_tiles = (int)c->tiles.size();
+  p.n_cells = (int)c->cells.size();
+  p.width = g.width;
+  p.height = g.height;
+  p.pyr_img_stride = pyr_off;
+  p.cell_entries = slot_off;
+  p.sel_entries = sel_off;
+  p.qt_scratch_img_stride = scratch_off;
+  p.qt_node_cap = max_quota + max_ini + 8;
+  if (p.qt_node_cap >= 60000) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree node pool");
+  // shared-memory budget of the quadtree kernel: node pool + as many corners as fit in ~100 KB, at most 8192
+  {
+    int cap = 4096;
+    int max_list = 0;
+    for (auto &L : c->levels) max_list = std::max(max_list, L.list_cap);
+    cap = std::min(cap, std::max(64, max_list));
+    size_t bytes = quadtree_smem_bytes(cap, p.qt_node_cap);
+    if (bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree shared-memory pool");
+    p.qt_smem_cap = cap;
+    c->qt_smem = bytes;
+  }
+  p.fx = g.fx;
+  p.fy = g.fy;
+  p.cx = g.cx;
+  p.cy = g.cy;
+  p.bf = g.bf;
+  p.depth_scale_inv = (float)(1.0 / (double)(g.depth_scale != 0.f ? g.depth_scale : 1.f)); // Mat /= s == convertTo(.., 1./s)
+  for (int i = 0; i < 5; ++i) p.dist[i] = g.dist[i];
+  p.undistort = g.dist[0] != 0.f ? 1 : 0; // Camera::undistortPoints returns early when k1 == 0 (src/Camera.cc:31)
+
+  // pattern: float pairs -> int8 (the template file holds integers, :262)
+  std::vector<char4> pat(256);
+  for (int b = 0; b < 256; ++b)
+  {
+    float v[4];
+    for (int k = 0; k < 4; ++k) v[k] = g.pattern ? g.pattern[4 * b + k] : (float)ORBX_BIT_PATTERN_31[4 * b + k];
+    for (int k = 0; k < 4; ++k)
+      if (v[k] != std::floor(v[k]) || std::fabs(v[k]) > 127.f) return fail(c, ORBX_ERR_INVALID_ARG, "BRIEF pattern entries must be integers in [-127,127]");
+    pat[b] = make_char4((signed char)v[0], (signed char)v[1], (signed char)v[2], (signed char)v[3]);
+  }
+  // the rotated pattern must stay inside the 19-px border (mnBorderSize, :523)
+  for (int b = 0; b < 256; ++b)
+  {
+    const double r1 = std::hypot((double)pat[b].x, (double)pat[b].y), r2 = std::hypot((double)pat[b].z, (double)pat[b].w);
+    if (r1 > 18.5 || r2 > 18.5) return fail(c, ORBX_ERR_INVALID_ARG, "BRIEF pattern radius exceeds the 19-px border");
+  }
+
+  int rc;
+  if ((rc = dev_upload(c, &p.levels, c->levels))) return rc;
+  if ((rc = dev_upload(c, &p.tiles, c->tiles))) return rc;
+  if ((rc = dev_upload(c, &p.cells, c->cells))) return rc;
+  if ((rc = dev_upload(c, &p.tab_ofs, tab_ofs))) return rc;
+  if ((rc = dev_upload(c, &p.tab_coef, tab_coef))) return rc;
+  if ((rc = dev_upload(c, &p.strips, strips))) return rc;
+  if ((rc = dev_upload(c, &p.pattern, pat))) return rc;
+
+  // algorithmic bytes: per image P + 60 N; stereo step 2*60 N + 352 N + 16 N
+  int64_t P = 0;
+  for (auto &L : c->levels) P += (int64_t)L.w * L.h;
+  const int64_t N = g.n_features;
+  c->alg_bytes_image = P + 60 * N;
+  c->alg_bytes_stereo = 2 * c->alg_bytes_image + 120 * N + 352 * N + 16 * N;
+  return ORBX_OK;
+}
+
+int alloc_buffers(orbx_ctx *c)
+{
+  Params &p = c->p;
+  const size_t ni = (size_t)c->n_img_max, nf = (size_t)c->cfg.max_batch, N = (size_t)c->cfg.n_features;
+  int rc;
+  if ((rc = dev_alloc(c, &p.pyr, ni * p.pyr_img_stride))) return rc;
+  if ((rc = dev_alloc(c, &p.blur, ni * p.pyr_img_stride))) return rc;
+  if ((rc = dev_alloc(c, &p.cell_list, ni * p.cell_entries))) return rc;
+  if ((rc = dev_alloc(c, &p.cell_cnt, ni * (size_t)p.n_cells))) return rc;
+  if ((rc = dev_alloc(c, &p.sel, ni * (size_t)p.sel_entries))) return rc;
+  if ((rc = dev_alloc(c, &p.sel_cnt, ni * (size_t)p.n_levels))) return rc;
+  if ((rc = dev_alloc(c, &p.qt_scratch, ni * p.qt_scratch_img_stride))) return rc;
+  if ((rc = dev_alloc(c, &p.kps, ni * N))) return rc;
+  if ((rc = dev_alloc(c, &p.kps_und, ni * N))) return rc;
+  if ((rc = dev_alloc(c, &p.desc, ni * N * 32))) return rc;
+  if ((rc = dev_alloc(c, &p.n_kps, ni))) return rc;
+  if ((rc = dev_alloc(c, &p.rtab, ni * N))) return rc;
+  if ((rc = dev_alloc(c, &p.u_right, ni * N))) return rc; // sized per image so that mono batches can use it too
+  if ((rc = dev_alloc(c, &p.depth, ni * N))) return rc;
+  if ((rc = dev_alloc(c, &p.n_matches, ni))) return rc;
+  c->in_pitch = ((size_t)c->cfg.width + 15) & ~(size_t)15;
+  if ((rc = dev_alloc(c, &c->d_in, ni * c->in_pitch * (size_t)c->cfg.height))) return rc;
+  if ((rc = dev_alloc(c, &c->d_depth_in, nf * (size_t)c->cfg.width * (size_t)c->cfg.height * 4))) return rc;
+  ORBX_CUDA(c, cudaMemset(p.n_kps, 0, ni * sizeof(int)));
+  ORBX_CUDA(c, cudaMemset(p.n_matches, 0, ni * sizeof(int)));
+  return ORBX_OK;
+}
+
+// ORBExtractor ctor + extract for n_images device-resident images
+int run_extract(orbx_ctx *c, const Params &p, int n_images)
+{
+  launch_pyramid(p, n_images, c->stream);
+  launch_fast(p, n_images, c->stream);
+  launch_quadtree(p, n_images, c->qt_smem, c->stream);
+  launch_orient_brief(p, n_images, c->stream);
+  c->launches += 4;
+  ORBX_CUDA(c, cudaGetLastError());
+  return ORBX_OK;
+}
+
+void fill_results(orbx_ctx *c, int n_images, int n_frames, orbx_device_results *out)
+{
+  if (!out) return;
+  out->kps = c->p.kps;
+  out->kps_und = c->p.kps_und;
+  out->desc = c->p.desc;
+  out->n_kps = c->p.n_kps;
+  out->u_right = c->p.u_right;
+  out->depth = c->p.depth;
+  out->n_matches = c->p.n_matches;
+  out->n_images = n_images;
+  out->n_frames = n_frames;
+  out->n_features = c->cfg.n_features;
+}
+
+} // namespace
+
+extern "C"
+{
+
+  void orbx_default_config(orbx_config *cfg)
+  {
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->width = 1241;
+    cfg->height = 376;
+    cfg->n_features = 2000;
+    cfg->n_levels = 8;
+    cfg->scale_factor = 1.2f;
+    cfg->ini_th_fast = 20;
+    cfg->min_th_fast = 7;
+    cfg->fx = 718.856f;
+    cfg->fy = 718.856f;
+    cfg->cx = 607.1928f;
+    cfg->cy = 185.2157f;
+    cfg->bf = cfg->fx * 0.537166f;
+    cfg->depth_scale = 1.f;
+    cfg->max_batch = 1;
+    cfg->device = -1;
+    cfg->pattern = nullptr;
+  }
+
+  const char *orbx_status_string(int status)
+  {
+    switch (status)
+    {
+    case ORBX_OK: return "ok";
+    case ORBX_ERR_INVALID_ARG: return "invalid argument";
+    case ORBX_ERR_IMAGE_SIZE: return "ImageSizeError: pyramid level too small";
+    case ORBX_ERR_FILE_NOT_OPEN: return "FileNotOpenError: cannot open BRIEF template";
+    case ORBX_ERR_CUDA: return "CUDA error";
+    case ORBX_ERR_NO_DEVICE: return "no CUDA device";
+    case ORBX_ERR_CAPACITY: return "batch larger than max_batch";
+    case ORBX_ERR_STATE: return "invalid state";
+    default: return "unknown status";
+    }
+  }
+
+  int orbx_load_brief_template(const char *path, float *pattern_out)
+  {
+    if (!path || !pattern_out) return ORBX_ERR_INVALID_ARG;
+    std::ifstream ifs(path);
+    if (!ifs.is_open()) return ORBX_ERR_FILE_NOT_OPEN;
+    std::string line;
+    bool header = true;
+    int n = 0;
+    while (std::getline(ifs, line))
+    {
+      if (header)
+      { // first line is a column header (:255-259)
+        header = false;
+        continue;
+      }
+      if (n >= 256) break;
+      std::istringstream iss(line);
+      float v[4] = {0, 0, 0, 0};
+      iss >> v[0] >> v[1] >> v[2] >> v[3];
+      for (int k = 0; k < 4; ++k) pattern_out[4 * n + k] = v[k];
+      ++n;
+    }
+    return n == 256 ? ORBX_OK : ORBX_ERR_INVALID_ARG;
+  }
+
+  int orbx_create(const orbx_config *cfg, orbx_ctx **out)
+  {
+    if (!cfg || !out) return ORBX_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->n_features < 1 || cfg->n_levels < 1 || cfg->n_levels > kMaxLevels || !(cfg->scale_factor > 1.f) ||
+        cfg->ini_th_fast < 0 || cfg->ini_th_fast > 255 || cfg->min_th_fast < 0 || cfg->min_th_fast > 255 || cfg->max_batch < 1)
+      return ORBX_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return ORBX_ERR_NO_DEVICE; // no CPU fallback, by design
+    orbx_ctx *c = new (std::nothrow) orbx_ctx();
+    if (!c) return ORBX_ERR_INVALID_ARG;
+    c->cfg = *cfg;
+    c->cfg.pattern = cfg->pattern;
+    int rc = ORBX_OK;
+    do
+    {
+      if (cfg->device >= 0)
+      {
+        if (cfg->device >= ndev)
+        {
+          rc = ORBX_ERR_NO_DEVICE;
+          break;
+        }
+        if (cudaSetDevice(cfg->device) != cudaSuccess)
+        {
+          rc = ORBX_ERR_CUDA;
+          break;
+        }
+      }
+      if (cudaGetDevice(&c->device) != cudaSuccess)
+      {
+        rc = ORBX_ERR_CUDA;
+        break;
+      }
+      c->n_img_max = 2 * cfg->max_batch;
+      if ((rc = build_tables(c))) break;
+      c->cfg.pattern = nullptr; // not retained
+      if ((rc = alloc_buffers(c))) break;
+      if (quadtree_configure(c->qt_smem) != 0)
+      {
+        rc = fail(c, ORBX_ERR_CUDA, "cudaFuncSetAttribute(quadtree_kernel, MaxDynamicSharedMemorySize)");
+        break;
+      }
+      if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+      {
+        rc = ORBX_ERR_CUDA;
+        break;
+      }
+      c->stream = c->own_stream;
+    } while (0);
+    if (rc != ORBX_OK)
+    {
+      if (!c->last_error.empty()) std::fprintf(stderr, "orbx_create: %s\n", c->last_error.c_str());
+      orbx_destroy(c);
+      return rc;
+    }
+    *out = c;
+    return ORBX_OK;
+  }
+
+  void orbx_destroy(orbx_ctx *c)
+  {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream)
+    {
+      cudaStreamSynchronize(c->own_stream);
+      cudaStreamDestroy(c->own_stream);
+    }
+    for (void *q : c->allocs) cudaFree(q);
+    delete c;
+  }
+
+  const char *orbx_last_error(const orbx_ctx *c) { return c ? c->last_error.c_str() : ""; }
+
+  int orbx_set_stream(orbx_ctx *c, void *cuda_stream)
+  {
+    if (!c) return ORBX_ERR_INVALID_ARG;
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return ORBX_OK;
+  }
+
+  int orbx_num_levels(const orbx_ctx *c) { return c ? c->cfg.n_levels : ORBX_ERR_INVALID_ARG; }
+
+  int orbx_level_info(const orbx_ctx *c, int level, int32_t *width, int32_t *height, float *scale, int32_t *quota)
+  {
+    if (!c || level < 0 || level >= c->cfg.n_levels) return ORBX_ERR_INVALID_ARG;
+    const Level &L = c->levels[level];
+    if (width) *width = L.w;
+    if (height) *height = L.h;
+    if (scale) *scale = L.sf;
+    if (quota) *quota = L.quota;
+    return ORBX_OK;
+  }
+
+  int orbx_synchronize(orbx_ctx *c)
+  {
+    if (!c) return ORBX_ERR_INVALID_ARG;
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
+  }
+
+  int64_t orbx_launch_count(const orbx_ctx *c) { return c ? c->launches : 0; }
+  int64_t orbx_algorithmic_bytes(const orbx_ctx *c, int stereo) { return c ? (stereo ? c->alg_bytes_stereo : c->alg_bytes_image) : 0; }
+
+  // ---------------------------------------------------------------------------------------------------------------
+  int orbx_extract_batch_device(orbx_ctx *c, int n_images, const uint8_t *d_images, size_t stride, size_t frame_stride, orbx_device_results *out)
+  {
+    if (!c || !d_images || n_images < 1) return ORBX_ERR_INVALID_ARG;
+    if (n_images > c->n_img_max) return fail(c, ORBX_ERR_CAPACITY, "n_images > 2 * max_batch");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    Params p = c->p;
+    p.stereo = 0;
+    p.in_left = d_images;
+    p.in_right = nullptr;
+    p.in_stride = stride;
+    p.in_frame_stride = frame_stride;
+    int rc = run_extract(c, p, n_images);
+    if (rc) return rc;
+    c->last_images = n_images;
+    c->last_stereo = 0;
+    fill_results(c, n_images, 0, out);
+    return ORBX_OK;
+  }
+
+  int orbx_stereo_batch_device(orbx_ctx *c, int n_frames, const uint8_t *d_left, const uint8_t *d_right, size_t stride, size_t frame_stride,
+                               orbx_device_results *out)
+  {
+    if (!c || !d_left || !d_right || n_frames < 1) return ORBX_ERR_INVALID_ARG;
+    if (n_frames > c->cfg.max_batch) return fail(c, ORBX_ERR_CAPACITY, "n_frames > max_batch");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    Params p = c->p;
+    p.stereo = 1;
+    p.in_left = d_left;
+    p.in_right = d_right;
+    p.in_stride = stride;
+    p.in_frame_stride = frame_stride;
+    int rc = run_extract(c, p, 2 * n_frames);
+    if (rc) return rc;
+    ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)n_frames * sizeof(int), c->stream));
+    launch_stereo(p, n_frames, c->stream);
+    c->launches += 1;
+    ORBX_CUDA(c, cudaGetLastError());
+    c->last_images = 2 * n_frames;
+    c->last_stereo = 1;
+    fill_results(c, 2 * n_frames, n_frames, out);
+    return ORBX_OK;
+  }
+
+  int orbx_rgbd_batch_device(orbx_ctx *c, int n_frames, const uint8_t *d_gray, size_t gray_stride, size_t gray_frame_stride, const void *d_depth,
+                             size_t depth_stride_bytes, size_t depth_frame_stride_bytes, int depth_type, orbx_device_results *out)
+  {
+    if (!c || !d_gray || !d_depth || n_frames < 1 || (depth_type != ORBX_DEPTH_U16 && depth_type != ORBX_DEPTH_F32)) return ORBX_ERR_INVALID_ARG;
+    if (n_frames > c->n_img_max) return fail(c, ORBX_ERR_CAPACITY, "n_frames > 2 * max_batch");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    Params p = c->p;
+    p.stereo = 0;
+    p.in_left = d_gray;
+    p.in_stride = gray_stride;
+    p.in_frame_stride = gray_frame_stride;
+    p.depth_img = d_depth;
+    p.depth_stride = depth_stride_bytes;
+    p.depth_frame_stride = depth_frame_stride_bytes;
+    p.depth_type = depth_type;
+    int rc = run_extract(c, p, n_frames);
+    if (rc) return rc;
+    ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)n_frames * sizeof(int), c->stream));
+    launch_rgbd(p, n_frames, c->stream);
+    c->launches += 1;
+    ORBX_CUDA(c, cudaGetLastError());
+    c->last_images = n_frames;
+    c->last_stereo = 0;
+    fill_results(c, n_frames, n_frames, out);
+    return ORBX_OK;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------------
+  int orbx_stereo_batch(orbx_ctx *c, int n_frames, const uint8_t *left, const uint8_t *right, size_t stride, size_t frame_stride, orbx_keypoint *kps_left,
+                        uint8_t *desc_left, int32_t *n_left, orbx_keypoint *kps_right, uint8_t *desc_right, int32_t *n_right, double *u_right,
+                        double *depth, int32_t *n_matches)
+  {
+    if (!c || !left || !right || n_frames < 1) return ORBX_ERR_INVALID_ARG;
+    if (n_frames > c->cfg.max_batch) return fail(c, ORBX_ERR_CAPACITY, "n_frames > max_batch");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const size_t W = (size_t)c->cfg.width, H = (size_t)c->cfg.height, N = (size_t)c->cfg.n_features;
+    const size_t fs = c->in_pitch * H;
+    uint8_t *dl = c->d_in, *dr = c->d_in + (size_t)c->cfg.max_batch * fs;
+    if (stride == c->in_pitch && frame_stride == fs)
+    {
+      ORBX_CUDA(c, cudaMemcpyAsync(dl, left, fs * n_frames, cudaMemcpyHostToDevice, c->stream));
+      ORBX_CUDA(c, cudaMemcpyAsync(dr, right, fs * n_frames, cudaMemcpyHostToDevice, c->stream));
+    }
+    else if (frame_stride == stride * H)
+    { // frames are densely stacked rows: one 2-D copy per side
+      ORBX_CUDA(c, cudaMemcpy2DAsync(dl, c->in_pitch, left, stride, W, H * n_frames, cudaMemcpyHostToDevice, c->stream));
+      ORBX_CUDA(c, cudaMemcpy2DAsync(dr, c->in_pitch, right, stride, W, H * n_frames, cudaMemcpyHostToDevice, c->stream));
+    }
+    else
+    {
+      for (int f = 0; f < n_frames; ++f)
+      {
+        ORBX_CUDA(c, cudaMemcpy2DAsync(dl + f * fs, c->in_pitch, left + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, c->stream));
+        ORBX_CUDA(c, cudaMemcpy2DAsync(dr + f * fs, c->in_pitch, right + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, c->stream));
+      }
+    }
+    int rc = orbx_stereo_batch_device(c, n_frames, dl, dr, c->in_pitch, fs, nullptr);
+    if (rc) return rc;
+    const Params &p = c->p;
+    // results: left = even images, right = odd images -> one strided 2-D copy per array
+    const size_t kb = N * sizeof(orbx_keypoint), db = N * 32;
+    if (kps_left) ORBX_CUDA(c, cudaMemcpy2DAsync(kps_left, kb, p.kps_und, 2 * kb, kb, n_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (kps_right) ORBX_CUDA(c, cudaMemcpy2DAsync(kps_right, kb, p.kps + N, 2 * kb, kb, n_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (desc_left) ORBX_CUDA(c, cudaMemcpy2DAsync(desc_left, db, p.desc, 2 * db, db, n_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (desc_right) ORBX_CUDA(c, cudaMemcpy2DAsync(desc_right, db, p.desc + db, 2 * db, db, n_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (n_left) ORBX_CUDA(c, cudaMemcpy2DAsync(n_left, 4, p.n_kps, 8, 4, n_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (n_right) ORBX_CUDA(c, cudaMemcpy2DAsync(n_right, 4, p.n_kps + 1, 8, 4, n_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (u_right) ORBX_CUDA(c, cudaMemcpyAsync(u_right, p.u_right, N * 8 * n_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (depth) ORBX_CUDA(c, cudaMemcpyAsync(depth, p.depth, N * 8 * n_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (n_matches) ORBX_CUDA(c, cudaMemcpyAsync(n_matches, p.n_matches, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
+  }
+
+  int orbx_stereo_frame(orbx_ctx *c, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride, orbx_keypoint *kps_left,
+                        uint8_t *desc_left, int32_t *n_left, orbx_keypoint *kps_right, uint8_t *desc_right, int32_t *n_right, double *u_right, double *depth,
+                        int32_t *n_matches)
+  {
+    if (!c || !left || !right) return ORBX_ERR_INVALID_ARG;
+    if (left_stride == right_stride)
+      return orbx_stereo_batch(c, 1, left, right, left_stride, left_stride * (size_t)c->cfg.height, kps_left, desc_left, n_left, kps_right, desc_right, n_right,
+                               u_right, depth, n_matches);
+    // different row strides: stage the two images separately, then run the device path
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const size_t W = (size_t)c->cfg.width, H = (size_t)c->cfg.height, N = (size_t)c->cfg.n_features;
+    const size_t fs = c->in_pitch * H;
+    uint8_t *dl = c->d_in, *dr = c->d_in + (size_t)c->cfg.max_batch * fs;
+    ORBX_CUDA(c, cudaMemcpy2DAsync(dl, c->in_pitch, left, left_stride, W, H, cudaMemcpyHostToDevice, c->stream));
+    ORBX_CUDA(c, cudaMemcpy2DAsync(dr, c->in_pitch, right, right_stride, W, H, cudaMemcpyHostToDevice, c->stream));
+    int rc = orbx_stereo_batch_device(c, 1, dl, dr, c->in_pitch, fs, nullptr);
+    if (rc) return rc;
+    const Params &p = c->p;
+    if (kps_left) ORBX_CUDA(c, cudaMemcpyAsync(kps_left, p.kps_und, N * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    if (kps_right) ORBX_CUDA(c, cudaMemcpyAsync(kps_right, p.kps + N, N * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    if (desc_left) ORBX_CUDA(c, cudaMemcpyAsync(desc_left, p.desc, N * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (desc_right) ORBX_CUDA(c, cudaMemcpyAsync(desc_right, p.desc + N * 32, N * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (n_left) ORBX_CUDA(c, cudaMemcpyAsync(n_left, p.n_kps, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (n_right) ORBX_CUDA(c, cudaMemcpyAsync(n_right, p.n_kps + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (u_right) ORBX_CUDA(c, cudaMemcpyAsync(u_right, p.u_right, N * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (depth) ORBX_CUDA(c, cudaMemcpyAsync(depth, p.depth, N * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (n_matches) ORBX_CUDA(c, cudaMemcpyAsync(n_matches, p.n_matches, 4, cudaMemcpyDeviceToHost, c->stream));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
+  }
+
+  int orbx_extract(orbx_ctx *c, const uint8_t *image, size_t stride, orbx_keypoint *kps, uint8_t *desc, int32_t *n)
+  {
+    if (!c || !image) return ORBX_ERR_INVALID_ARG;
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const size_t W = (size_t)c->cfg.width, H = (size_t)c->cfg.height, N = (size_t)c->cfg.n_features;
+    ORBX_CUDA(c, cudaMemcpy2DAsync(c->d_in, c->in_pitch, image, stride, W, H, cudaMemcpyHostToDevice, c->stream));
+    int rc = orbx_extract_batch_device(c, 1, c->d_in, c->in_pitch, c->in_pitch * H, nullptr);
+    if (rc) return rc;
+    const Params &p = c->p;
+    if (kps) ORBX_CUDA(c, cudaMemcpyAsync(kps, p.kps, N * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    if (desc) ORBX_CUDA(c, cudaMemcpyAsync(desc, p.desc, N * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (n) ORBX_CUDA(c, cudaMemcpyAsync(n, p.n_kps, 4, cudaMemcpyDeviceToHost, c->stream));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
+  }
+
+  int orbx_rgbd_frame(orbx_ctx *c, const uint8_t *gray, size_t gray_stride, const void *depth_image, size_t depth_stride_bytes, int depth_type,
+                      orbx_keypoint *kps_raw, orbx_keypoint *kps, uint8_t *desc, int32_t *n, double *u_right, double *depth)
+  {
+    if (!c || !gray || !depth_image || (depth_type != ORBX_DEPTH_U16 && depth_type != ORBX_DEPTH_F32)) return ORBX_ERR_INVALID_ARG;
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const size_t W = (size_t)c->cfg.width, H = (size_t)c->cfg.height, N = (size_t)c->cfg.n_features;
+    const size_t esz = depth_type == ORBX_DEPTH_F32 ? 4 : 2;
+    ORBX_CUDA(c, cudaMemcpy2DAsync(c->d_in, c->in_pitch, gray, gray_stride, W, H, cudaMemcpyHostToDevice, c->stream));
+    ORBX_CUDA(c, cudaMemcpy2DAsync(c->d_depth_in, W * esz, depth_image, depth_stride_bytes, W * esz, H, cudaMemcpyHostToDevice, c->stream));
+    int rc = orbx_rgbd_batch_device(c, 1, c->d_in, c->in_pitch, c->in_pitch * H, c->d_depth_in, W * esz, W * H * esz, depth_type, nullptr);
+    if (rc) return rc;
+    const Params &p = c->p;
+    if (kps_raw) ORBX_CUDA(c, cudaMemcpyAsync(kps_raw, p.kps, N * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    if (kps) ORBX_CUDA(c, cudaMemcpyAsync(kps, p.kps_und, N * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    if (desc) ORBX_CUDA(c, cudaMemcpyAsync(desc, p.desc, N * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (n) ORBX_CUDA(c, cudaMemcpyAsync(n, p.n_kps, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (u_right) ORBX_CUDA(c, cudaMemcpyAsync(u_right, p.u_right, N * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (depth) ORBX_CUDA(c, cudaMemcpyAsync(depth, p.depth, N * 8, cudaMemcpyDeviceToHost, c->stream));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
+  }
+
+  int orbx_get_pyramid(orbx_ctx *c, int side, int level, int blurred, uint8_t *dst, size_t dst_stride)
+  {
+    if (!c || !dst || level < 0 || level >= c->cfg.n_levels || side < 0) return ORBX_ERR_INVALID_ARG;
+    if (side >= c->last_images) return fail(c, ORBX_ERR_STATE, "no image with that index has been processed");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const Level &L = c->levels[level];
+    const uint8_t *src = (blurred ? c->p.blur : c->p.pyr) + (size_t)side * c->p.pyr_img_stride + L.pyr_off;
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    ORBX_CUDA(c, cudaMemcpy2D(dst, dst_stride, src, (size_t)L.pitch, (size_t)L.w, (size_t)L.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+  }
+
+} // extern "C"

@@ -1,0 +1,131 @@
+// orbx_device.cuh -- device-side data layout shared by the kernels (orbx_kernels.cu) and the host layer (orbx_api.cu).
+//
+// HBM layout (all buffers are per context, sized for n_img_max = 2 * max_batch images):
+//   pyr / blur     [image][pyr_img_stride]   every level stored with a 16-byte aligned pitch at Level::pyr_off
+//   cell_list      [image][cell_entries]     one fixed-capacity slot per FAST cell, entries packed x:12 | y:12 | score:8
+//   cell_cnt       [image][n_cells]
+//   sel / sel_cnt  [image][sel_entries] / [image][n_levels]   quadtree survivors per level (ascending detection index)
+//   kps, kps_und   [image][n_features]       cv::KeyPoint layout (28 B)
+//   desc           [image][n_features][32]
+//   rtab           [image][n_features]       {x, minRow, maxRow} row-band table for the stereo search
+//   u_right, depth [frame][n_features]       doubles, -1 = no match
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orbx.h"
+
+namespace orbx
+{
+
+constexpr int kMaxLevels = 32;
+constexpr int kEdge = 16;       // FAST ROI margin: mnBorderSize - 3 (src/ORBExtractor.cc:334-337)
+constexpr int kTileW = 64;      // pyramid/blur output tile
+constexpr int kTileH = 32;
+constexpr int kHalo = 3;        // 7x7 Gaussian
+constexpr int kPyrThreads = 256;
+constexpr int kFastThreads = 128;
+constexpr int kQtThreads = 128;
+constexpr int kMaxPatch = 72;   // largest FAST cell patch edge (cell < 60 px + 6), padded
+constexpr int kMaxStrips = 255; // root split fan-out: round(w/h) vertical strips
+constexpr uint32_t kNil = 0xFFFFu;
+
+struct Level
+{
+  int w, h, pitch;  // level image size and row pitch (bytes)
+  int pyr_off;      // byte offset of the level inside one image's pyramid buffer
+  float sf;         // mvfScaledFactors[level]
+  int quota;        // mvnFeatures[level]
+  int tab_x, tab_y; // offsets into the resize tables (unused for level 0)
+  int area2x;       // exact 2x2 decimation: cv::resize re-routes INTER_LINEAR to INTER_AREA
+  // FAST cell grid (src/ORBExtractor.cc:334-343)
+  int n_cols, n_rows, w_cell, h_cell;
+  int cell_base;    // index of this level's first cell in the cell table
+  int n_level_cells;
+  // quadtree (src/ORBExtractor.cc:81-96,144-173)
+  int roi_w, roi_h, n_ini;
+  int strip_off;    // offset into Params::strips (n_ini + 1 column bounds)
+  int list_cap;     // worst-case number of corners on this level
+  int scratch_off;  // entry offset of this level inside one image's quadtree scratch (global-memory path)
+  int sel_off;      // entry offset of this level inside one image's sel buffer
+};
+
+struct Tile
+{
+  int level, x0, y0, pad;
+};
+
+struct Cell
+{
+  int level;
+  int x0, y0;   // patch origin in level coordinates (iniX, iniY)
+  int pw, ph;   // patch size (maxX - iniX, maxY - iniY)
+  int slot;     // entry offset of the cell's slot inside one image's cell_list
+  int cap;      // slot capacity
+  int pad;
+};
+
+struct RTab
+{
+  float x;
+  short min_row, max_row;
+};
+
+struct Params
+{
+  int n_levels, n_features, ini_th, min_th;
+  int n_tiles, n_cells;
+  int width, height;
+  int stereo; // images are interleaved left/right pairs
+  const Level *levels;
+  const Tile *tiles;
+  const Cell *cells;
+  const int *tab_ofs;     // resize source index per destination index
+  const short2 *tab_coef; // resize 11-bit coefficients
+  const double *strips;
+  const char4 *pattern;   // 256 x (x1, y1, x2, y2)
+  // inputs
+  const uint8_t *in_left, *in_right;
+  size_t in_stride, in_frame_stride;
+  const void *depth_img;
+  size_t depth_stride, depth_frame_stride;
+  int depth_type;
+  // per-image buffers
+  uint8_t *pyr, *blur;
+  size_t pyr_img_stride;
+  uint32_t *cell_list;
+  size_t cell_entries;
+  int *cell_cnt;
+  uint32_t *sel;
+  int sel_entries;
+  int *sel_cnt;
+  // quadtree scratch (global-memory path for levels whose corner count exceeds the shared-memory capacity)
+  uint32_t *qt_scratch;
+  size_t qt_scratch_img_stride; // in uint32 entries
+  int qt_smem_cap;              // corners that fit the shared-memory path
+  int qt_node_cap;              // node pool capacity (max quota + 8)
+  // results
+  orbx_keypoint *kps, *kps_und;
+  uint8_t *desc;
+  int *n_kps;
+  RTab *rtab;
+  double *u_right, *depth;
+  int *n_matches;
+  // camera
+  float fx, fy, cx, cy, bf, depth_scale_inv;
+  float dist[5];
+  int undistort;
+};
+
+// launchers (orbx_kernels.cu); every call enqueues exactly one kernel on `s`
+void launch_pyramid(const Params &p, int n_images, cudaStream_t s);
+void launch_fast(const Params &p, int n_images, cudaStream_t s);
+void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
+void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
+void launch_stereo(const Params &p, int n_frames, cudaStream_t s);
+void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
+size_t quadtree_smem_bytes(int list_cap, int node_cap);
+int quadtree_configure(size_t smem_bytes); // opt in to large dynamic shared memory
+
+} // namespace orbx

@@ -1,0 +1,1083 @@
+// orbx_kernels.cu -- hand-written sm_100a kernels of the ORB front-end.
+//
+// One kernel per stage of the reference's CPU path (citations relative to /root/reference/src/ORB_SLAM2/):
+//   pyramid_blur_kernel  ORBExtractor::initPyramid            src/ORBExtractor.cc:304-319  (cv::resize + cv::GaussianBlur)
+//   fast_cells_kernel    ORBExtractor::extractFast, FAST part  src/ORBExtractor.cc:346-375  (cv::FAST + threshold fallback)
+//   quadtree_kernel      Quadtree::split / nodes2kpoints       src/ORBExtractor.cc:19-192,376-386
+//   orient_brief_kernel  getGrayCentroid + computeBRIEF        src/ORBExtractor.cc:397-487,534-540
+//   stereo_kernel        ORBMatcher::searchByStereo            src/ORBMatcher.cc:18-81,841-1011
+//   rgbd_kernel          Frame::Frame (RGB-D)                  src/Frame.cc:125-159
+// All arithmetic that decides a result bit is integer, or IEEE float/double with explicit round-to-nearest
+// intrinsics (no FMA contraction), so results equal the CPU path bit for bit.
+#include "orbx_device.cuh"
+
+namespace orbx
+{
+
+// ------------------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int refl101(int i, int n)
+{
+  // BORDER_REFLECT_101 for an overshoot of at most 3 pixels on images of at least 4 pixels
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__device__ __forceinline__ const uint8_t *input_image(const Params &p, int img)
+{
+  if (p.stereo) return ((img & 1) ? p.in_right : p.in_left) + (size_t)(img >> 1) * p.in_frame_stride;
+  return p.in_left + (size_t)img * p.in_frame_stride;
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// exclusive scan of one int per thread over a block of NT threads (NT multiple of 32, <= 1024); returns the block total
+template <int NT> __device__ __forceinline__ int block_exclusive_scan(int v, int &total, int *s_warp /* [NT/32] */)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w)
+  {
+    int t = s_warp[w];
+    if (w < wid) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  total = tot;
+  return base + inc - v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1: pyramid level (resize from level 0) fused with the 7x7 Gaussian blur.  One CTA per 64x32 output tile.
+//   cv::resize INTER_LINEAR 8UC1: 11-bit coefficient tables (built on the host exactly like OpenCV does), int32 maths.
+//   cv::GaussianBlur 7x7 sigma 2: 8.8 fixed-point kernel {18,34,48,56,48,34,18}, u16 rows, (v + 32768) >> 16.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kSrcW = kTileW + 2 * kHalo;      // 70
+constexpr int kSrcH = kTileH + 2 * kHalo;      // 38
+constexpr int kSrcPitch = 72;
+
+__global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params p)
+{
+  __shared__ __align__(16) uint8_t s_src[kSrcH * kSrcPitch];
+  __shared__ __align__(16) uint16_t s_h[kSrcH * kTileW];
+
+  const Tile t = p.tiles[blockIdx.x];
+  const int img = blockIdx.y;
+  const Level &L = p.levels[t.level];
+  const int lw = L.w, lh = L.h, pitch = L.pitch;
+  const uint8_t *__restrict__ src = input_image(p, img);
+  const size_t sstride = p.in_stride;
+  const int W = p.width, H = p.height;
+  const int *__restrict__ xofs = p.tab_ofs + L.tab_x;
+  const int *__restrict__ yofs = p.tab_ofs + L.tab_y;
+  const short2 *__restrict__ xco = p.tab_coef + L.tab_x;
+  const short2 *__restrict__ yco = p.tab_coef + L.tab_y;
+  const int level = t.level, area2x = L.area2x;
+
+  // stage A: the tile plus a 3-pixel halo of the (resized) level image, REFLECT_101 at the level's borders
+  for (int i = threadIdx.x; i < kSrcH * kSrcW; i += kPyrThreads)
+  {
+    const int ty = i / kSrcW, tx = i - ty * kSrcW;
+    const int rx = t.x0 + tx - kHalo, ry = t.y0 + ty - kHalo;
+    int v = 0;
+    if (rx < lw + kHalo && ry < lh + kHalo)
+    {
+      const int gx = refl101(rx, lw), gy = refl101(ry, lh);
+      if (level == 0)
+      {
+        v = src[(size_t)gy * sstride + gx];
+      }
+      else if (area2x)
+      {
+        const uint8_t *s0 = src + (size_t)(2 * gy) * sstride + 2 * gx;
+        v = (s0[0] + s0[1] + s0[sstride] + s0[sstride + 1] + 2) >> 2;
+      }
+      else
+      {
+        const int sx = xofs[gx], sy = yofs[gy];
+        const short2 a = xco[gx], b = yco[gy];
+        const int sx1 = min(sx + 1, W - 1);
+        const int sy0 = min(max(sy, 0), H - 1), sy1 = min(max(sy + 1, 0), H - 1);
+        const uint8_t *r0 = src + (size_t)sy0 * sstride, *r1 = src + (size_t)sy1 * sstride;
+        const int h0 = r0[sx] * a.x + r0[sx1] * a.y;
+        const int h1 = r1[sx] * a.x + r1[sx1] * a.y;
+        v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+      }
+    }
+    s_src[ty * kSrcPitch + tx] = (uint8_t)v;
+  }
+  __syncthreads();
+
+  uint8_t *__restrict__ pyr = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
+  uint8_t *__restrict__ blr = p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off;
+
+  // the level image itself (getPyramid(); FAST, orientation and the stereo SAD read it): 4 pixels per store
+  for (int i = threadIdx.x; i < kTileH * (kTileW / 4); i += kPyrThreads)
+  {
+    const int ty = i / (kTileW / 4), tx = (i - ty * (kTileW / 4)) * 4;
+    const int gx = t.x0 + tx, gy = t.y0 + ty;
+    if (gy < lh && gx < pitch)
+    {
+      const uint8_t *s = &s_src[(ty + kHalo) * kSrcPitch + tx + kHalo];
+      const uint32_t w = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+      *reinterpret_cast<uint32_t *>(pyr + (size_t)gy * pitch + gx) = w;
+    }
+  }
+
+  // stage B: horizontal pass (fits u16: 255 * 256)
+  for (int i = threadIdx.x; i < kSrcH * kTileW; i += kPyrThreads)
+  {
+    const int ty = i / kTileW, tx = i - ty * kTileW;
+    const uint8_t *s = &s_src[ty * kSrcPitch + tx];
+    const int acc = 18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3];
+    s_h[i] = (uint16_t)acc;
+  }
+  __syncthreads();
+
+  // stage C: vertical pass + rounding, 4 pixels per store
+  for (int i = threadIdx.x; i < kTileH * (kTileW / 4); i += kPyrThreads)
+  {
+    const int ty = i / (kTileW / 4), tx = (i - ty * (kTileW / 4)) * 4;
+    const int gx = t.x0 + tx, gy = t.y0 + ty;
+    if (gy < lh && gx < pitch)
+    {
+      uint32_t w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        const uint16_t *c = &s_h[ty * kTileW + tx + k];
+        const uint32_t acc = 18u * (c[0] + c[6 * kTileW]) + 34u * (c[kTileW] + c[5 * kTileW]) + 48u * (c[2 * kTileW] + c[4 * kTileW]) +
+                             56u * c[3 * kTileW];
+        w |= ((acc + 32768u) >> 16) << (8 * k);
+      }
+      *reinterpret_cast<uint32_t *>(blr + (size_t)gy * pitch + gx) = w;
+    }
+  }
+}
+
+void launch_pyramid(const Params &p, int n_images, cudaStream_t s)
+{
+  dim3 grid(p.n_tiles, n_images);
+  pyramid_blur_kernel<<<grid, kPyrThreads, 0, s>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2: FAST-9/16 with non-max suppression per 30-px cell and the iniTh -> minTh fallback.  One CTA per cell.
+//   arc value m(p) = max over the 16 arcs of 9 contiguous ring pixels of min(+-(I(p) - I(ring)));
+//   corner at threshold t  <=>  m > t;  cv score = m - 1;  keep iff score > all 8 neighbours' scores (strict), where a
+//   neighbour that is not a corner at t, or lies outside the cell's detection zone, scores 0.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kPatPitch = kMaxPatch;          // 72
+constexpr int kZoneMax = kMaxPatch - 6;       // 66
+constexpr int kMapPitch = kZoneMax + 2;       // 68
+
+__device__ __forceinline__ int fast_arc_value(const uint8_t *c)
+{
+  constexpr int P = kPatPitch;
+  const int v = c[0];
+  int d[16];
+  d[0] = v - c[3 * P];
+  d[1] = v - c[3 * P + 1];
+  d[2] = v - c[2 * P + 2];
+  d[3] = v - c[P + 3];
+  d[4] = v - c[3];
+  d[5] = v - c[-P + 3];
+  d[6] = v - c[-2 * P + 2];
+  d[7] = v - c[-3 * P + 1];
+  d[8] = v - c[-3 * P];
+  d[9] = v - c[-3 * P - 1];
+  d[10] = v - c[-2 * P - 2];
+  d[11] = v - c[-P - 3];
+  d[12] = v - c[-3];
+  d[13] = v - c[P - 3];
+  d[14] = v - c[2 * P - 2];
+  d[15] = v - c[3 * P - 1];
+  int mn2[16], mx2[16], mn4[16], mx4[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+  {
+    mn2[k] = min(d[k], d[(k + 1) & 15]);
+    mx2[k] = max(d[k], d[(k + 1) & 15]);
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+  {
+    mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
+    mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+  }
+  int best = -256;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+  {
+    const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+    const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+    best = max(best, max(mn9, -mx9));
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p)
+{
+  __shared__ __align__(16) uint8_t s_pat[kMaxPatch * kPatPitch];
+  __shared__ uint8_t s_map[(kZoneMax + 2) * kMapPitch];
+  __shared__ uint16_t s_cand[kZoneMax * kZoneMax];
+  __shared__ int s_ncand;
+  __shared__ int s_warp[kFastThreads / 32];
+
+  const Cell c = p.cells[blockIdx.x];
+  const int img = blockIdx.y;
+  const Level &L = p.levels[c.level];
+  const uint8_t *__restrict__ lvl = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
+  const int pitch = L.pitch;
+  const int pw = c.pw, ph = c.ph;
+  const int zw = pw - 6, zh = ph - 6; // detection zone: FAST looks at [3, w-3) x [3, h-3) of the patch
+  const int tid = threadIdx.x;
+  int *cnt_out = p.cell_cnt + (size_t)img * p.n_cells + blockIdx.x;
+  if (zw <= 0 || zh <= 0)
+  {
+    if (tid == 0) *cnt_out = 0;
+    return;
+  }
+  const int zn = zw * zh;
+  const int tq = min(p.ini_th, p.min_th);
+
+  if (tid == 0) s_ncand = 0;
+  for (int i = tid; i < (zh + 2) * kMapPitch; i += kFastThreads) s_map[i] = 0;
+  for (int i = tid; i < ph * pw; i += kFastThreads)
+  {
+    const int y = i / pw, x = i - y * pw;
+    s_pat[y * kPatPitch + x] = lvl[(size_t)(c.y0 + y) * pitch + c.x0 + x];
+  }
+  __syncthreads();
+
+  // quick reject: every arc of 9 holds at least 2 of the 4 compass pixels
+  for (int i = tid; i < zn; i += kFastThreads)
+  {
+    const int zy = i / zw, zx = i - zy * zw;
+    const uint8_t *q = &s_pat[(zy + 3) * kPatPitch + zx + 3];
+    const int v = q[0], hi = v + tq, lo = v - tq;
+    const int a = q[3 * kPatPitch], b = q[3], cc = q[-3 * kPatPitch], dd = q[-3];
+    const int nb = (a > hi) + (b > hi) + (cc > hi) + (dd > hi);
+    const int nd = (a < lo) + (b < lo) + (cc < lo) + (dd < lo);
+    if (nb >= 2 || nd >= 2) s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)i;
+  }
+  __syncthreads();
+  const int ncand = s_ncand;
+  for (int k = tid; k < ncand; k += kFastThreads)
+  {
+    const int i = s_cand[k];
+    const int zy = i / zw, zx = i - zy * zw;
+    const int m = fast_arc_value(&s_pat[(zy + 3) * kPatPitch + zx + 3]);
+    if (m > tq) s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)m;
+  }
+  __syncthreads();
+
+  // non-max suppression for both thresholds; each thread owns a contiguous run of zone pixels (row-major)
+  const int per = (zn + kFastThreads - 1) / kFastThreads; // <= 35
+  const int i0 = tid * per, i1 = min(i0 + per, zn);
+  unsigned long long keep_ini = 0, keep_min = 0;
+  const int t_ini = p.ini_th, t_min = p.min_th;
+  for (int i = i0; i < i1; ++i)
+  {
+    const int zy = i / zw, zx = i - zy * zw;
+    const uint8_t *mp = &s_map[(zy + 1) * kMapPitch + zx + 1];
+    const int m = mp[0];
+    if (m == 0) continue;
+    int nb[8] = {mp[-1], mp[1], mp[-kMapPitch - 1], mp[-kMapPitch], mp[-kMapPitch + 1], mp[kMapPitch - 1], mp[kMapPitch], mp[kMapPitch + 1]};
+    bool k_ini = m > t_ini, k_min = m > t_min;
+    const int s = m - 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+      const int q = nb[j];
+      k_ini = k_ini && (s > (q > t_ini ? q - 1 : 0));
+      k_min = k_min && (s > (q > t_min ? q - 1 : 0));
+    }
+    if (k_ini) keep_ini |= 1ull << (i - i0);
+    if (k_min) keep_min |= 1ull << (i - i0);
+  }
+  const int any_ini = __syncthreads_or(keep_ini != 0ull);
+  const unsigned long long keep = any_ini ? keep_ini : keep_min; // fallback iff the post-NMS list is empty (:366-367)
+  const int mine = __popcll(keep);
+  int total;
+  int off = block_exclusive_scan<kFastThreads>(mine, total, s_warp);
+  uint32_t *slot = p.cell_list + (size_t)img * p.cell_entries + c.slot;
+  for (int i = i0; i < i1; ++i)
+  {
+    if (!((keep >> (i - i0)) & 1ull)) continue;
+    const int zy = i / zw, zx = i - zy * zw;
+    const uint32_t score = (uint32_t)s_map[(zy + 1) * kMapPitch + zx + 1] - 1u;
+    const uint32_t x = (uint32_t)(c.x0 - kEdge + 3 + zx), y = (uint32_t)(c.y0 - kEdge + 3 + zy); // ROI coordinates (:368-372)
+    if (off < c.cap) slot[off] = x | (y << 12) | (score << 24);
+    ++off;
+  }
+  if (tid == 0) *cnt_out = min(total, c.cap);
+}
+
+void launch_fast(const Params &p, int n_images, cudaStream_t s)
+{
+  dim3 grid(p.n_cells, n_images);
+  fast_cells_kernel<<<grid, kFastThreads, 0, s>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3: quadtree keypoint distribution.  One CTA per (level, image).
+//   Phase A/B  concatenate the level's cell lists in cell-row-major order (the reference's levelKps order)
+//   Phase C    warp 0 replays Quadtree::split(): the multimap<count, node, greater> becomes FIFO buckets indexed by
+//              count with a descending cursor (a child never holds more corners than its parent, so the pop key is
+//              monotone); a node's corner list is a range of an index array, split by a stable warp partition.
+//   Phase D    nodes2kpoints(): best response per surviving node, ascending index order, shift by the 16-px margin.
+// ------------------------------------------------------------------------------------------------------------------
+struct QtNodePool
+{
+  double *r0, *r1, *c0, *c1;
+  uint32_t *lo, *cnt;
+  uint16_t *next, *prev, *free_ids;
+  uint8_t *buf, *state; // state: 0 dead, 1 live, 2 live but beyond the first `need` entries
+};
+
+size_t quadtree_smem_bytes(int list_cap, int node_cap)
+{
+  size_t b = 0;
+  b += (size_t)node_cap * (4 * 8 + 2 * 4 + 3 * 2 + 2); // node pool
+  b = (b + 15) & ~(size_t)15;
+  b += (size_t)list_cap * (3 * 4 + 1) + (size_t)(list_cap + 1) * 2 * 2; // kp, ia, ib, dig, bucket head/tail
+  b = (b + 15) & ~(size_t)15;
+  return b + 64;
+}
+
+__device__ __forceinline__ void qt_push(const QtNodePool &np, uint16_t *bhead, uint16_t *btail, uint32_t id, uint32_t count)
+{
+  const uint32_t t = btail[count];
+  np.next[id] = (uint16_t)kNil;
+  np.prev[id] = (uint16_t)t;
+  if (t == kNil)
+    bhead[count] = (uint16_t)id;
+  else
+    np.next[t] = (uint16_t)id;
+  btail[count] = (uint16_t)id;
+  np.state[id] = 1;
+}
+
+__global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_warp[kQtThreads / 32];
+  __shared__ int s_n, s_live, s_take;
+
+  const int level = blockIdx.x, img = blockIdx.y;
+  const Level &L = p.levels[level];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int need = L.quota;
+  const int ncell = L.n_level_cells;
+  const int *ccnt = p.cell_cnt + (size_t)img * p.n_cells + L.cell_base;
+  const Cell *cells = p.cells + L.cell_base;
+  int *sel_cnt = p.sel_cnt + (size_t)img * p.n_levels + level;
+  uint32_t *sel_out = p.sel + (size_t)img * p.sel_entries + L.sel_off;
+
+  // ---- Phase A: total number of corners on the level
+  int mysum = 0;
+  const int per_c = (ncell + kQtThreads - 1) / kQtThreads;
+  const int c0i = tid * per_c, c1i = min(c0i + per_c, ncell);
+  for (int c = c0i; c < c1i; ++c) mysum += ccnt[c];
+  int n;
+  int mybase = block_exclusive_scan<kQtThreads>(mysum, n, s_warp);
+
+  // carve the working arrays out of shared memory, or out of the global scratch for very dense levels
+  const int node_cap = p.qt_node_cap;
+  QtNodePool np;
+  {
+    uint8_t *q = smem;
+    np.r0 = (double *)q;
+    np.r1 = np.r0 + node_cap;
+    np.c0 = np.r1 + node_cap;
+    np.c1 = np.c0 + node_cap;
+    q = (uint8_t *)(np.c1 + node_cap);
+    np.lo = (uint32_t *)q;
+    np.cnt = np.lo + node_cap;
+    q = (uint8_t *)(np.cnt + node_cap);
+    np.next = (uint16_t *)q;
+    np.prev = np.next + node_cap;
+    np.free_ids = np.prev + node_cap;
+    q = (uint8_t *)(np.free_ids + node_cap);
+    np.buf = q;
+    np.state = q + node_cap;
+  }
+  uint32_t *kp, *ia, *ib;
+  uint16_t *bhead, *btail;
+  uint8_t *dig;
+  {
+    size_t pool = (size_t)node_cap * (4 * 8 + 2 * 4 + 3 * 2 + 2);
+    pool = (pool + 15) & ~(size_t)15;
+    uint8_t *q;
+    int cap;
+    if (n <= p.qt_smem_cap)
+    {
+      q = smem + pool;
+      cap = p.qt_smem_cap;
+    }
+    else
+    {
+      q = (uint8_t *)(p.qt_scratch + (size_t)img * p.qt_scratch_img_stride + L.scratch_off);
+      cap = L.list_cap;
+    }
+    kp = (uint32_t *)q;
+    ia = kp + cap;
+    ib = ia + cap;
+    bhead = (uint16_t *)(ib + cap);
+    btail = bhead + (cap + 1);
+    dig = (uint8_t *)(btail + (cap + 1));
+  }
+
+  // ---- Phase B: gather the cell lists (cell-row-major, row-major inside a cell == the reference's detection order)
+  {
+    const uint32_t *cl = p.cell_list + (size_t)img * p.cell_entries;
+    int off = mybase;
+    for (int c = c0i; c < c1i; ++c)
+    {
+      const int k = ccnt[c];
+      const uint32_t *src = cl + cells[c].slot;
+      for (int j = 0; j < k; ++j) kp[off + j] = src[j];
+      off += k;
+    }
+  }
+  for (int i = tid; i < n; i += kQtThreads) ia[i] = (uint32_t)i; // root holds every corner (:26-27)
+  for (int i = tid; i <= n; i += kQtThreads)
+  {
+    bhead[i] = (uint16_t)kNil;
+    btail[i] = (uint16_t)kNil;
+  }
+  for (int i = tid; i < node_cap; i += kQtThreads) np.state[i] = 0;
+  __syncthreads();
+
+  // ---- Phase C: the priority loop, warp 0 only
+  if (wid == 0)
+  {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int n_alloc = 1, n_free = 0;
+    if (lane == 0)
+    {
+      np.r0[0] = 0.0;
+      np.r1[0] = (double)L.roi_h;
+      np.c0[0] = 0.0;
+      np.c1[0] = (double)L.roi_w;
+      np.lo[0] = 0;
+      np.cnt[0] = (uint32_t)n;
+      np.buf[0] = 0;
+      qt_push(np, bhead, btail, 0, (uint32_t)n);
+    }
+    __syncwarp();
+    int n_nodes = 1, live = 1, cursor = n;
+    bool root_pending = true;
+    while (n_nodes < need && live > 0)
+    {
+      // highest non-empty bucket at or below the cursor
+      for (;;)
+      {
+        const int b = cursor - lane;
+        const bool hit = (b >= 0) && (bhead[b] != (uint16_t)kNil);
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (m)
+        {
+          cursor -= __ffs(m) - 1;
+          break;
+        }
+        cursor -= 32;
+        if (cursor < 0) break;
+      }
+      if (cursor < 0) break; // cannot happen while live > 0
+      if (cursor == 1 && !root_pending)
+      {
+        // Every live node holds exactly one corner and we are still short of `need`: a one-corner node yields at most one
+        // one-corner child, so the node count can never grow again and the reference keeps splitting until each corner
+        // lands exactly on a midline and vanishes -- the multimap drains and the level returns no keypoints (:151).
+        for (int i = lane; i < node_cap; i += 32) np.state[i] = 0;
+        live = 0;
+        break;
+      }
+      const uint32_t id = bhead[cursor];
+      const uint32_t lo = np.lo[id], cnt = np.cnt[id];
+      const int buf = np.buf[id];
+      const double r0 = np.r0[id], r1 = np.r1[id], c0 = np.c0[id], c1 = np.c1[id];
+      __syncwarp();
+      if (lane == 0)
+      {
+        const uint32_t nx = np.next[id];
+        bhead[cursor] = (uint16_t)nx;
+        if (nx == kNil)
+          btail[cursor] = (uint16_t)kNil;
+        else
+          np.prev[nx] = (uint16_t)kNil;
+        np.state[id] = 0;
+      }
+      --live;
+      --n_nodes;
+      const uint32_t *src = buf ? ib : ia;
+      uint32_t *dst = buf ? ia : ib;
+
+      if (root_pending)
+      {
+        // initSplit (:81-96): n_ini vertical strips with float-rounded column bounds
+        root_pending = false;
+        const int K = L.n_ini;
+        const double *cols = p.strips + L.strip_off;
+        for (uint32_t i = lane; i < cnt; i += 32)
+        {
+          const uint32_t e = kp[src[lo + i]];
+          const double x = (double)(float)(e & 0xfffu), y = (double)(float)((e >> 12) & 0xfffu);
+          int d = 255;
+          if (y > r0 && y < r1)
+            for (int k = 0; k < K; ++k)
+              if (x > cols[k] && x < cols[k + 1])
+              {
+                d = k;
+                break;
+              }
+          dig[lo + i] = (uint8_t)d;
+        }
+        __syncwarp();
+        uint32_t base = lo;
+        for (int k = 0; k < K; ++k)
+        {
+          uint32_t run = 0;
+          for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
+          {
+            const uint32_t i = i0 + lane;
+            const bool f = (i < cnt) && (dig[lo + i] == k);
+            const unsigned m = __ballot_sync(FULL, f);
+            if (f) dst[base + run + __popc(m & lt_mask)] = src[lo + i];
+            run += __popc(m);
+          }
+          if (run > 0)
+          {
+            uint32_t cid;
+            if (n_free > 0)
+              cid = np.free_ids[--n_free];
+            else
+              cid = n_alloc++;
+            if (lane == 0)
+            {
+              np.r0[cid] = r0;
+              np.r1[cid] = r1;
+              np.c0[cid] = cols[k];
+              np.c1[cid] = cols[k + 1];
+              np.lo[cid] = base;
+              np.cnt[cid] = run;
+              np.buf[cid] = (uint8_t)(buf ^ 1);
+              qt_push(np, bhead, btail, cid, run);
+            }
+            ++n_nodes;
+            ++live;
+            base += run;
+          }
+          __syncwarp();
+        }
+      }
+      else
+      {
+        // split (:60-72): midlines in double, children (row0,col0) (row0,col1) (row1,col0) (row1,col1); corners on a
+        // midline belong to no child (strict isIn, ORBExtractor.h:55-62)
+        const double mr = __dmul_rn(__dadd_rn(r0, r1), 0.5), mc = __dmul_rn(__dadd_rn(c0, c1), 0.5);
+        uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
+        {
+          const uint32_t i = i0 + lane;
+          int d = 255;
+          if (i < cnt)
+          {
+            const uint32_t e = kp[src[lo + i]];
+            const double x = (double)(e & 0xfffu), y = (double)((e >> 12) & 0xfffu);
+            const int jx = x < mc ? 0 : (x > mc ? 1 : -1);
+            const int iy = y < mr ? 0 : (y > mr ? 1 : -1);
+            if (jx >= 0 && iy >= 0) d = iy * 2 + jx;
+            dig[lo + i] = (uint8_t)d;
+          }
+          t0 += __popc(__ballot_sync(FULL, d == 0));
+          t1 += __popc(__ballot_sync(FULL, d == 1));
+          t2 += __popc(__ballot_sync(FULL, d == 2));
+          t3 += __popc(__ballot_sync(FULL, d == 3));
+        }
+        __syncwarp();
+        const uint32_t b0 = lo, b1 = b0 + t0, b2 = b1 + t1, b3 = b2 + t2;
+        uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
+        {
+          const uint32_t i = i0 + lane;
+          int d = 255;
+          uint32_t idx = 0;
+          if (i < cnt)
+          {
+            d = dig[lo + i];
+            idx = src[lo + i];
+          }
+          const unsigned m0 = __ballot_sync(FULL, d == 0), m1 = __ballot_sync(FULL, d == 1);
+          const unsigned m2 = __ballot_sync(FULL, d == 2), m3 = __ballot_sync(FULL, d == 3);
+          if (d == 0) dst[b0 + q0 + __popc(m0 & lt_mask)] = idx;
+          if (d == 1) dst[b1 + q1 + __popc(m1 & lt_mask)] = idx;
+          if (d == 2) dst[b2 + q2 + __popc(m2 & lt_mask)] = idx;
+          if (d == 3) dst[b3 + q3 + __popc(m3 & lt_mask)] = idx;
+          q0 += __popc(m0);
+          q1 += __popc(m1);
+          q2 += __popc(m2);
+          q3 += __popc(m3);
+        }
+        const uint32_t tc[4] = {t0, t1, t2, t3};
+        const uint32_t bs[4] = {b0, b1, b2, b3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          if (tc[k] == 0) continue;
+          uint32_t cid;
+          if (n_free > 0)
+            cid = np.free_ids[--n_free];
+          else
+            cid = n_alloc++;
+          if (lane == 0)
+          {
+            np.r0[cid] = (k & 2) ? mr : r0;
+            np.r1[cid] = (k & 2) ? r1 : mr;
+            np.c0[cid] = (k & 1) ? mc : c0;
+            np.c1[cid] = (k & 1) ? c1 : mc;
+            np.lo[cid] = bs[k];
+            np.cnt[cid] = tc[k];
+            np.buf[cid] = (uint8_t)(buf ^ 1);
+            qt_push(np, bhead, btail, cid, tc[k]);
+          }
+          ++n_nodes;
+          ++live;
+          __syncwarp();
+        }
+      }
+      // the popped node's slot can be reused
+      if (lane == 0) np.free_ids[n_free] = (uint16_t)id;
+      ++n_free;
+      __syncwarp();
+    }
+
+    // nodes2kpoints (:182-192): only the first min(need, |M|) entries in (count desc, FIFO) order are used; the surplus
+    // (at most 3 nodes) sits at the tails of the lowest buckets
+    int take = min(need, live), excl = live - take;
+    if (excl > 0)
+    {
+      int b = 0;
+      while (excl > 0 && b <= n)
+      {
+        const uint32_t t = btail[b];
+        if (t == kNil)
+        {
+          ++b;
+          continue;
+        }
+        __syncwarp();
+        if (lane == 0)
+        {
+          np.state[t] = 2;
+          const uint32_t pv = np.prev[t];
+          btail[b] = (uint16_t)pv;
+          if (pv == kNil) bhead[b] = (uint16_t)kNil;
+        }
+        --excl;
+        __syncwarp();
+      }
+    }
+    if (lane == 0)
+    {
+      s_n = n_alloc; // node slots ever used
+      s_take = take;
+      s_live = live;
+    }
+  }
+  // dig doubles as the "selected" flag array from here on
+  __syncthreads();
+  for (int i = tid; i < n; i += kQtThreads) dig[i] = 0;
+  __syncthreads();
+
+  // ---- Phase D: best response per surviving node (getFeature :103-117: strict '>', first wins, default index 0)
+  const int n_slots = s_n;
+  if (s_take > 0)
+  {
+    for (int s = tid; s < n_slots; s += kQtThreads)
+    {
+      if (np.state[s] != 1) continue;
+      const uint32_t *arr = np.buf[s] ? ib : ia;
+      const uint32_t lo = np.lo[s], cnt = np.cnt[s];
+      uint32_t best = 0, best_i = 0;
+      for (uint32_t i = 0; i < cnt; ++i)
+      {
+        const uint32_t idx = arr[lo + i];
+        const uint32_t r = kp[idx] >> 24;
+        if (r > best)
+        {
+          best = r;
+          best_i = idx;
+        }
+      }
+      if ((int)best_i < n) dig[best_i] = 1;
+    }
+  }
+  __syncthreads();
+  {
+    const int per = (n + kQtThreads - 1) / kQtThreads;
+    const int i0 = tid * per, i1 = min(i0 + per, n);
+    int mine = 0;
+    for (int i = i0; i < i1; ++i) mine += dig[i];
+    int total;
+    int off = block_exclusive_scan<kQtThreads>(mine, total, s_warp);
+    for (int i = i0; i < i1; ++i)
+      if (dig[i])
+      {
+        const uint32_t e = kp[i];
+        // back to level coordinates (:382-383)
+        if (off < need) sel_out[off] = ((e & 0xfffu) + kEdge) | ((((e >> 12) & 0xfffu) + kEdge) << 12) | (e & 0xff000000u);
+        ++off;
+      }
+    if (tid == 0) *sel_cnt = min(total, need);
+  }
+}
+
+int quadtree_configure(size_t smem_bytes)
+{
+  return (int)cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+
+void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s)
+{
+  dim3 grid(p.n_levels, n_images);
+  quadtree_kernel<<<grid, kQtThreads, smem_bytes, s>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K4: intensity-centroid orientation + rotated BRIEF.  One warp per keypoint.
+// ------------------------------------------------------------------------------------------------------------------
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3}; // initMaxU (:217-236), radius 15
+
+constexpr int kBriefWarps = 8;
+
+__device__ __forceinline__ void undistort_point(const Params &p, float u, float v, float &uo, float &vo)
+{
+  // cv::undistortPoints(pts, pts, K, D, noArray(), K) (src/Camera.cc:36): 5 fixed-point iterations in double
+  const double fx = p.fx, fy = p.fy, cx = p.cx, cy = p.cy;
+  const double k1 = p.dist[0], k2 = p.dist[1], p1 = p.dist[2], p2 = p.dist[3], k3 = p.dist[4];
+  const double ifx = __ddiv_rn(1.0, fx), ify = __ddiv_rn(1.0, fy);
+  double x = __dmul_rn(__dsub_rn((double)u, cx), ifx), y = __dmul_rn(__dsub_rn((double)v, cy), ify);
+  const double x0 = x, y0 = y;
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it)
+  {
+    const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y);
+    const double r2 = __dadd_rn(xx, yy);
+    double poly = __dadd_rn(__dmul_rn(k3, r2), k2);
+    poly = __dadd_rn(__dmul_rn(poly, r2), k1);
+    poly = __dadd_rn(1.0, __dmul_rn(poly, r2));
+    const double icdist = __ddiv_rn(1.0, poly);
+    const double dx = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p1), x), y), __dmul_rn(p2, __dadd_rn(r2, __dmul_rn(2.0, xx))));
+    const double dy = __dadd_rn(__dmul_rn(p1, __dadd_rn(r2, __dmul_rn(2.0, yy))), __dmul_rn(__dmul_rn(__dmul_rn(2.0, p2), x), y));
+    x = __dmul_rn(__dsub_rn(x0, dx), icdist);
+    y = __dmul_rn(__dsub_rn(y0, dy), icdist);
+  }
+  uo = __double2float_rn(__dadd_rn(__dmul_rn(x, fx), cx));
+  vo = __double2float_rn(__dadd_rn(__dmul_rn(y, fy), cy));
+}
+
+__global__ void __launch_bounds__(kBriefWarps * 32) orient_brief_kernel(const Params p)
+{
+  const int img = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * kBriefWarps + (threadIdx.x >> 5);
+  const unsigned FULL = 0xffffffffu;
+
+  // which level does this output slot belong to? (level-major concatenation, src/ORBExtractor.cc:501-506)
+  const int *sel_cnt = p.sel_cnt + (size_t)img * p.n_levels;
+  const int my = lane < p.n_levels ? sel_cnt[lane] : 0;
+  int inc = my;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    int t = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const int total = __shfl_sync(FULL, inc, 31);
+  if (slot == 0 && lane == 0) p.n_kps[img] = total;
+  if (slot >= total) return;
+  const unsigned above = __ballot_sync(FULL, inc > slot); // first lane whose inclusive sum exceeds the slot
+  const int level = __ffs(above) - 1;
+  const int level_start = __shfl_sync(FULL, inc - my, level);
+  const Level &L = p.levels[level];
+  const uint32_t e = p.sel[(size_t)img * p.sel_entries + L.sel_off + (slot - level_start)];
+  const int x = (int)(e & 0xfffu), y = (int)((e >> 12) & 0xfffu), score = (int)(e >> 24);
+  const int pitch = L.pitch;
+  const uint8_t *__restrict__ lvl = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
+  const uint8_t *__restrict__ blr = p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off;
+
+  // getGrayCentroid (:465-487): moments over the radius-15 disc of the un-blurred level; lane <-> column offset
+  int m10 = 0, m01 = 0;
+  if (lane < 31)
+  {
+    const int dx = lane - 15, adx = abs(dx);
+    const uint8_t *c = lvl + (size_t)y * pitch + x + dx;
+#pragma unroll 1
+    for (int dy = -15; dy <= 15; ++dy)
+    {
+      if (adx <= c_umax[abs(dy)])
+      {
+        const int v = c[dy * pitch];
+        m10 += dx * v;
+        m01 += dy * v;
+      }
+    }
+  }
+  m10 = warp_sum(m10);
+  m01 = warp_sum(m01);
+  const double theta = atan2((double)m01, (double)m10);
+  double sn, cs;
+  sincos(theta, &sn, &cs);
+
+  // computeBRIEF (:427-456) with rotateTemplate (:534-540): double products, float result, float add, round-half-even
+  const float fx = (float)x, fy = (float)y;
+  uint32_t byte = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+  {
+    const char4 t = p.pattern[lane * 8 + k]; // bit b = lane * 8 + k lands in byte b >> 3 == lane, position b & 7 == k
+    const double x1 = (double)t.x, y1 = (double)t.y, x2 = (double)t.z, y2 = (double)t.w;
+    const float p1x = __double2float_rn(__dsub_rn(__dmul_rn(x1, cs), __dmul_rn(y1, sn)));
+    const float p1y = __double2float_rn(__dadd_rn(__dmul_rn(x1, sn), __dmul_rn(y1, cs)));
+    const float p2x = __double2float_rn(__dsub_rn(__dmul_rn(x2, cs), __dmul_rn(y2, sn)));
+    const float p2y = __double2float_rn(__dadd_rn(__dmul_rn(x2, sn), __dmul_rn(y2, cs)));
+    const int v1 = blr[(size_t)__float2int_rn(__fadd_rn(fy, p1y)) * pitch + __float2int_rn(__fadd_rn(fx, p1x))];
+    const int v2 = blr[(size_t)__float2int_rn(__fadd_rn(fy, p2y)) * pitch + __float2int_rn(__fadd_rn(fx, p2x))];
+    byte |= (uint32_t)(v1 < v2) << k;
+  }
+  const size_t o = (size_t)img * p.n_features + slot;
+  p.desc[o * 32 + lane] = (uint8_t)byte;
+
+  // keypoint record (:407-409) + the row band used by the stereo search (createRowIndexDB, src/ORBMatcher.cc:915-932)
+  const float sf = L.sf;
+  const float kx = __fmul_rn(fx, sf), ky = __fmul_rn(fy, sf);
+  const float angle = __double2float_rn(__dmul_rn(__ddiv_rn(theta, 3.14159265358979323846), 180.0));
+  if (lane == 0)
+  {
+    orbx_keypoint kpt;
+    kpt.x = kx;
+    kpt.y = ky;
+    kpt.size = 7.f;
+    kpt.angle = angle;
+    kpt.response = (float)score;
+    kpt.octave = level;
+    kpt.class_id = -1;
+    p.kps[o] = kpt;
+    if (p.undistort) undistort_point(p, kx, ky, kpt.x, kpt.y); // Camera::undistortPoints (src/Camera.cc:29-39)
+    p.kps_und[o] = kpt;
+    const float r = __double2float_rn(__dmul_rn(2.0, (double)sf));
+    const unsigned row = (unsigned)__float2int_rn(ky);
+    RTab rt;
+    rt.x = kx;
+    rt.max_row = (short)min(p.height, __float2int_rn(__fadd_rn(__fadd_rn((float)row, r), 1.0f)));
+    rt.min_row = (short)max(0, __float2int_rn(__fsub_rn((float)row, r)));
+    p.rtab[o] = rt;
+  }
+}
+
+void launch_orient_brief(const Params &p, int n_images, cudaStream_t s)
+{
+  dim3 grid((p.n_features + kBriefWarps - 1) / kBriefWarps, n_images);
+  orient_brief_kernel<<<grid, kBriefWarps * 32, 0, s>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K5: stereo association.  One warp per left keypoint: row-band + x-range scan over the right keypoints, Hamming argmin
+// (first minimum == lexicographic min of (distance, index)), 11 SADs over an 11x11 window, parabola refinement.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kStereoWarps = 8;
+
+__global__ void __launch_bounds__(kStereoWarps * 32) stereo_kernel(const Params p)
+{
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int li = blockIdx.x * kStereoWarps + (threadIdx.x >> 5);
+  const unsigned FULL = 0xffffffffu;
+  const int imgL = 2 * frame, imgR = 2 * frame + 1;
+  const int nL = p.n_kps[imgL], nR = p.n_kps[imgR];
+  if (li >= p.n_features) return;
+  const size_t oL = (size_t)imgL * p.n_features, oR = (size_t)imgR * p.n_features;
+  double *ur_out = p.u_right + (size_t)frame * p.n_features + li;
+  double *dp_out = p.depth + (size_t)frame * p.n_features + li;
+  if (lane == 0)
+  {
+    *ur_out = -1.0; // :22-25
+    *dp_out = -1.0;
+  }
+  if (li >= nL) return;
+
+  const orbx_keypoint lk = p.kps_und[oL + li]; // the left keypoints are undistorted before matching (src/Frame.cc:106)
+  const float maxU = lk.x;
+  const float minU = fmaxf(0.f, __fsub_rn(lk.x, p.fx));
+  const int row = __float2int_rn(lk.y);
+  const uint4 *dl4 = reinterpret_cast<const uint4 *>(p.desc + (oL + li) * 32);
+  const uint4 a0 = dl4[0], a1 = dl4[1];
+
+  // getBestMatch over rowIdxDB[row] filtered by minU < x < maxU (:38-52, :967-990)
+  unsigned best = 0xffffffffu;
+  const RTab *rt = p.rtab + oR;
+  for (int j = lane; j < nR; j += 32)
+  {
+    const RTab t = rt[j];
+    if (row >= t.min_row && row < t.max_row && t.x < maxU && t.x > minU)
+    {
+      const uint4 *dr4 = reinterpret_cast<const uint4 *>(p.desc + (oR + j) * 32);
+      const uint4 b0 = dr4[0], b1 = dr4[1];
+      const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+                    __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+      best = min(best, ((unsigned)d << 20) | (unsigned)j);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
+  if (best == 0xffffffffu) return;          // no candidates (:49-50)
+  if ((int)(best >> 20) > 75) return;       // mnMeanThreshold (:53)
+  const int rj = (int)(best & 0xfffffu);
+  const orbx_keypoint rk = p.kps[oR + rj];
+  if (lk.octave > rk.octave + 1 || lk.octave < rk.octave - 1) return; // :57
+
+  // pixelSADMatch (:841-881) on the un-blurred pyramid levels of each keypoint's own octave
+  const Level &LL = p.levels[lk.octave];
+  const Level &LR = p.levels[rk.octave];
+  const uint8_t *il = p.pyr + (size_t)imgL * p.pyr_img_stride + LL.pyr_off;
+  const uint8_t *ir = p.pyr + (size_t)imgR * p.pyr_img_stride + LR.pyr_off;
+  const int lx = __float2int_rd(__fdiv_rn(lk.x, LL.sf)), ly = __float2int_rd(__fdiv_rn(lk.y, LL.sf)); // getPitch (:1002-1011)
+  const int rx = __float2int_rd(__fdiv_rn(rk.x, LR.sf)), ry = __float2int_rd(__fdiv_rn(rk.y, LR.sf));
+  // Out-of-image windows can only arise with undistorted left coordinates; the reference would throw cv::Exception there.
+  if (lx - 5 < 0 || ly - 5 < 0 || lx + 5 >= LL.w || ly + 5 >= LL.h || rx - 10 < 0 || ry - 5 < 0 || rx + 10 >= LR.w || ry + 5 >= LR.h) return;
+
+  int acc[11];
+#pragma unroll
+  for (int s = 0; s < 11; ++s) acc[s] = 0;
+  const int lc = il[(size_t)ly * LL.pitch + lx];
+  int rc[11];
+  {
+    const int v = lane < 21 ? ir[(size_t)ry * LR.pitch + rx - 10 + lane] : 0;
+#pragma unroll
+    for (int s = 0; s < 11; ++s) rc[s] = __shfl_sync(FULL, v, 5 + s);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 11; ++r)
+  {
+    const int lv = lane < 11 ? (int)il[(size_t)(ly - 5 + r) * LL.pitch + lx - 5 + lane] - lc : 0;
+    const int rv = lane < 21 ? (int)ir[(size_t)(ry - 5 + r) * LR.pitch + rx - 10 + lane] : 0;
+#pragma unroll
+    for (int s = 0; s < 11; ++s)
+    {
+      const int b = __shfl_sync(FULL, rv, (lane + s) & 31) - rc[s];
+      if (lane < 11) acc[s] += abs(lv - b);
+    }
+  }
+  int sad[11];
+#pragma unroll
+  for (int s = 0; s < 11; ++s)
+  {
+    int v = acc[s];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); // lanes 0..15 (11..15 hold zeros)
+    sad[s] = __shfl_sync(FULL, v, 0);
+  }
+  if (lane != 0) return;
+  int bi = 0;
+#pragma unroll
+  for (int s = 1; s < 11; ++s)
+    if (sad[s] < sad[bi]) bi = s; // first minimum (:862-866)
+  float delta = 0.f;
+  if (bi > 0 && bi < 10)
+  {
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int s = 1; s < 10; ++s)
+      if (s == bi)
+      {
+        s1 = (float)sad[s - 1];
+        s2 = (float)sad[s];
+        s3 = (float)sad[s + 1];
+      }
+    const float num = __fsub_rn(s1, s3);
+    const float den = __fsub_rn(__fadd_rn(s1, s3), __fmul_rn(2.f, s2));
+    delta = __double2float_rn(__ddiv_rn(__dmul_rn(0.5, (double)num), (double)den));
+    if (delta < 1.f && delta > -1.f)
+      delta = __fmul_rn(delta, LR.sf);
+    else
+      delta = 0.f;
+  }
+  float uR = __fadd_rn(rk.x, delta);
+  uR = fmaxf(0.f, uR);
+  uR = fminf(uR, __fsub_rn((float)p.width, 1.f));
+  float disp = __fsub_rn(lk.x, uR);
+  if (disp <= 0.f)
+  {
+    uR = rk.x;
+    disp = __fsub_rn(lk.x, uR);
+    if (disp <= 0.f) return;
+  }
+  *ur_out = (double)uR;
+  *dp_out = (double)__fdiv_rn(p.bf, __fsub_rn(lk.x, uR));
+  atomicAdd(p.n_matches + frame, 1);
+}
+
+void launch_stereo(const Params &p, int n_frames, cudaStream_t s)
+{
+  dim3 grid((p.n_features + kStereoWarps - 1) / kStereoWarps, n_frames);
+  stereo_kernel<<<grid, kStereoWarps * 32, 0, s>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K6: RGB-D depth association (src/Frame.cc:125-159): d = depth(int(y), int(x)) on the RAW keypoint, uRight from the
+// undistorted x.  The whole-image convertTo / divide of the reference is folded into the per-keypoint gather.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void rgbd_kernel(const Params p)
+{
+  const int frame = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_features) return;
+  const size_t o = (size_t)frame * p.n_features + i;
+  double ur = -1.0, dp = -1.0;
+  if (i < p.n_kps[frame])
+  {
+    const orbx_keypoint k = p.kps[o];
+    const int yy = (int)k.y, xx = (int)k.x; // Mat::at<float>(float, float): truncation
+    const uint8_t *base = (const uint8_t *)p.depth_img + (size_t)frame * p.depth_frame_stride + (size_t)yy * p.depth_stride;
+    const float raw = p.depth_type == ORBX_DEPTH_F32 ? ((const float *)base)[xx] : (float)((const uint16_t *)base)[xx];
+    const float d = __fmul_rn(raw, p.depth_scale_inv);
+    if (d > 0.f)
+    {
+      dp = (double)d;
+      ur = (double)__fsub_rn(p.kps_und[o].x, __fdiv_rn(p.bf, d));
+      atomicAdd(p.n_matches + frame, 1);
+    }
+  }
+  p.u_right[o] = ur;
+  p.depth[o] = dp;
+}
+
+void launch_rgbd(const Params &p, int n_frames, cudaStream_t s)
+{
+  dim3 grid((p.n_features + 127) / 128, n_frames);
+  rgbd_kernel<<<grid, 128, 0, s>>>(p);
+}
+
+} // namespace orbx

@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): pyramid pixels, keypoint sets, octaves, responses and descriptors bit-exact; angles
+within 1e-4 rad; uRight / depth within 1e-3 px.  Descriptor bit flips may only come from last-ulp libm differences
+(CUDA vs glibc atan2/sin/cos) landing on a rounding tie; they are counted and bounded.
+"""
+import numpy as np
+import pytest
+
+from orb_slam2_ros2_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = np.degrees(1e-4)
+
+
+def _camera(c):
+    return api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], tuple(c["dist"]), c["depth_scale"])
+
+
+def _cmp_kps(got, exp, got_desc, exp_desc, what=""):
+    assert len(got) == len(exp), f"{what}: {len(got)} vs {len(exp)} keypoints"
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(got[f], exp[f]), f"{what}: field {f}"
+    dang = np.abs(got["angle"] - exp["angle"])
+    dang = np.minimum(dang, 360.0 - dang)
+    assert dang.max(initial=0.0) <= ANGLE_TOL_DEG, f"{what}: max angle error {dang.max()} deg"
+    flips = int(np.unpackbits(got_desc ^ exp_desc).sum())
+    # a flip needs a 1-ulp libm difference to cross a float rounding boundary or a .5 tie: expect none, tolerate a trace
+    assert flips <= 2, f"{what}: {flips} descriptor bit flips"
+    return flips, int((got["angle"] != exp["angle"]).sum())
+
+
+CONFIGS = [
+    ("K2000", 376, 1241, 2000, 8, 1.2, 0),
+    ("K500", 376, 1241, 500, 8, 1.2, 1),
+    ("K4000", 376, 1241, 4000, 8, 1.2, 2),
+    ("T1000", 480, 640, 1000, 8, 1.2, 3),
+    ("H5000", 1080, 1920, 5000, 12, 1.2, 4),
+    ("S300x5", 240, 320, 300, 5, 1.3, 5),
+    ("odd", 333, 517, 700, 6, 1.25, 6),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_extract_matches_oracle(oracle, cfg):
+    name, h, w, nf, nl, sc, seed = cfg
+    img = synth.synth_image(h, w, seed)
+    ctx = api.Context(w, h, nf, nl, sc)
+    kps, desc = ctx.extract(img)
+    e = oracle.extract(img, nf, nl, sc)
+    # pyramid and blurred pyramid: every pixel
+    for blurred in (False, True):
+        levels = ctx.get_pyramid(0, blurred)
+        for l in range(nl):
+            exp = e.pyr.blurred(l) if blurred else e.pyr.level(l)
+            assert np.array_equal(levels[l], exp), f"{name} level {l} blurred={blurred}"
+    for l in range(nl):
+        lw, lh, sf, q = ctx.level_info(l)
+        assert (lw, lh, q) == (e.pyr.w[l], e.pyr.h[l], e.pyr.quota[l]) and sf == e.pyr.sf[l]
+    flips, inexact = _cmp_kps(kps, e.kps, desc, e.desc, name)
+    print(f"{name}: {len(kps)} kps, {flips} bit flips, {inexact} angles differing in the last float ulp")
+    ctx.close()
+
+
+def test_degenerate_images(oracle):
+    ctx = api.Context(320, 240, 1000, 4, 1.2)
+    kps, desc = ctx.extract(np.zeros((240, 320), np.uint8))
+    assert len(kps) == 0
+    kps, desc = ctx.extract(np.full((240, 320), 255, np.uint8))
+    assert len(kps) == 0
+    # uniform noise: tens of thousands of corners per level
+    img = np.random.default_rng(1).integers(0, 256, (240, 320), dtype=np.uint8)
+    kps, desc = ctx.extract(img)
+    e = oracle.extract(img, 1000, 4, 1.2)
+    _cmp_kps(kps, e.kps, desc, e.desc, "noise")
+    ctx.close()
+
+
+def test_dense_level_uses_global_quadtree_path(oracle):
+    """more corners on a level than the shared-memory list holds (4096) -> the global-scratch path of the quadtree"""
+    img = np.random.default_rng(2).integers(0, 256, (376, 1241), dtype=np.uint8)
+    ctx = api.Context(1241, 376, 2000, 8, 1.2)
+    kps, desc = ctx.extract(img)
+    e = oracle.extract(img, 2000, 8, 1.2)
+    fc, _ = oracle.fast_cells(e.pyr.level(0))
+    assert len(fc) > 4096
+    _cmp_kps(kps, e.kps, desc, e.desc, "dense")
+    ctx.close()
+
+
+def test_starved_level_returns_zero(oracle):
+    img = np.full((240, 320), 128, np.uint8)
+    img[60:180, 80:240] = synth.synth_image(120, 160, 11)
+    ctx = api.Context(320, 240, 3000, 3, 1.2)
+    kps, desc = ctx.extract(img)
+    e = oracle.extract(img, 3000, 3, 1.2)
+    assert (e.level_counts == 0).any()
+    _cmp_kps(kps, e.kps, desc, e.desc, "starved")
+    ctx.close()
+
+
+def test_fallback_threshold_cells(oracle):
+    """low-contrast image: most cells only produce corners at minThFAST"""
+    img = (synth.synth_image(240, 320, 21).astype(np.float32) * 0.25 + 90).astype(np.uint8)
+    _, nfb = oracle.fast_cells(img)
+    assert nfb > 10
+    ctx = api.Context(320, 240, 500, 3, 1.2)
+    kps, desc = ctx.extract(img)
+    e = oracle.extract(img, 500, 3, 1.2)
+    _cmp_kps(kps, e.kps, desc, e.desc, "fallback")
+    ctx.close()
+
+
+def test_errors():
+    with pytest.raises(api.ImageSizeError):
+        api.Context(100, 60, 500, 8, 1.2)
+    with pytest.raises(api.ImageSizeError):
+        api.Context(60, 60, 100, 1, 1.2)  # one level, but no room for a 30-px FAST cell
+    with pytest.raises(api.FileNotOpenError):
+        api.ORBExtractor(np.zeros((240, 320), np.uint8), 500, 4, 1.2, "/nonexistent/brief_template.txt", 20, 7)
+    ctx = api.Context(320, 240, 500, 4, 1.2, max_batch=2)
+    with pytest.raises(ValueError):
+        ctx.stereo_batch(np.zeros((3, 240, 320), np.uint8), np.zeros((3, 240, 320), np.uint8))
+    ctx.close()
+
+
+STEREO = [
+    ("K2000_d17", synth.KITTI, 2000, 0, 17),
+    ("K2000_d5", synth.KITTI, 2000, 1, 5),
+    ("K1000_d63", synth.KITTI, 1000, 2, 63),
+    ("T1000_d17", synth.TUM, 1000, 3, 17),
+    ("H5000_d42", synth.HD, 5000, 4, 42),
+]
+
+
+@pytest.mark.parametrize("cfg", STEREO, ids=[c[0] for c in STEREO])
+def test_stereo_matches_oracle(oracle, cfg):
+    name, c, nf, seed, disp = cfg
+    cam = api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"])  # zero distortion
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], seed, disp)
+    ctx = api.Context(c["width"], c["height"], nf, c["n_levels"], c["scale_factor"], camera=cam)
+    r = ctx.stereo_frame(left, right)
+    el = oracle.extract(left, nf, c["n_levels"], c["scale_factor"])
+    er = oracle.extract(right, nf, c["n_levels"], c["scale_factor"])
+    _cmp_kps(r.kps_left, el.kps, r.desc_left, el.desc, name + " left")
+    _cmp_kps(r.kps_right, er.kps, r.desc_right, er.desc, name + " right")
+    nm, ur, dp, _ = oracle.search_by_stereo(el, er, np.float32(c["fx"]), cam.bf)
+    assert r.n_matches == nm and nm > 0.3 * len(el.kps)
+    assert np.array_equal(r.u_right >= 0, ur >= 0)
+    assert np.abs(r.u_right - ur).max() <= 1e-3 and np.abs(r.depth - dp).max() <= 1e-3 * np.abs(dp).max()
+    print(f"{name}: {nm} matches, exact uRight {np.array_equal(r.u_right, ur)}, exact depth {np.array_equal(r.depth, dp)}")
+    # right pyramid is retrievable too (Frame::getRightPyramid)
+    assert np.array_equal(ctx.get_pyramid(1)[1], er.pyr.level(1))
+    ctx.close()
+
+
+def test_stereo_with_distortion_uses_undistorted_left(oracle):
+    """Frame.cc:106 undistorts the left keypoints before searchByStereo; mild distortion keeps SAD windows inside"""
+    c = synth.KITTI
+    dist = (0.02, -0.01, 0.0005, -0.0003, 0.0)
+    cam = api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], dist)
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], 8, 17)
+    ctx = api.Context(c["width"], c["height"], 1000, 8, 1.2, camera=cam)
+    r = ctx.stereo_frame(left, right)
+    el, er = oracle.extract(left, 1000), oracle.extract(right, 1000)
+    kl_u = el.kps.copy()
+    xy = oracle.undistort_points(np.stack([el.kps["x"], el.kps["y"]], 1), c["fx"], c["fy"], c["cx"], c["cy"], np.array(dist[:4], np.float32))
+    kl_u["x"], kl_u["y"] = xy[:, 0], xy[:, 1]
+    assert np.abs(r.kps_left["x"] - kl_u["x"]).max() <= 1e-3 and np.abs(r.kps_left["y"] - kl_u["y"]).max() <= 1e-3
+    # feed the oracle the device's undistorted coordinates so the comparison isolates the matcher
+    nm, ur, dp, _ = oracle.search_by_stereo(el, er, np.float32(c["fx"]), cam.bf, kps_left_undist=r.kps_left)
+    assert r.n_matches == nm
+    assert np.abs(r.u_right - ur).max() <= 1e-3
+    ctx.close()
+
+
+@pytest.mark.parametrize("use_dist", [False, True], ids=["nodist", "tumdist"])
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32], ids=["u16", "f32"])
+def test_rgbd_matches_oracle(oracle, use_dist, dtype):
+    c = synth.TUM
+    dist = tuple(c["dist"]) if use_dist else (0.0,) * 5
+    cam = api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], dist, c["depth_scale"])
+    gray = synth.synth_image(c["height"], c["width"], 12)
+    depth = synth.synth_depth_u16(c["height"], c["width"], 12, c["depth_scale"])
+    if dtype == np.float32:
+        depth = depth.astype(np.float32)
+    ctx = api.Context(c["width"], c["height"], 1000, 8, 1.2, camera=cam)
+    r = ctx.rgbd_frame(gray, depth)
+    e = oracle.extract(gray, 1000, 8, 1.2)
+    _cmp_kps(r.kps_raw, e.kps, r.desc, e.desc, "rgbd")
+    ku = e.kps.copy()
+    if use_dist:
+        xy = oracle.undistort_points(np.stack([e.kps["x"], e.kps["y"]], 1), c["fx"], c["fy"], c["cx"], c["cy"], np.array(dist, np.float32))
+        ku["x"], ku["y"] = xy[:, 0], xy[:, 1]
+        assert np.abs(r.kps["x"] - ku["x"]).max() > 0.5  # distortion is not a no-op
+    assert np.abs(r.kps["x"] - ku["x"]).max() <= 1e-3 and np.abs(r.kps["y"] - ku["y"]).max() <= 1e-3
+    ur, dp = oracle.rgbd_lookup(depth, c["depth_scale"], e.kps, ku, cam.bf)
+    assert np.array_equal(r.depth, dp)
+    assert np.abs(r.u_right - ur).max() <= 1e-3
+    assert 0.05 < (dp < 0).mean() < 0.2  # ~10 % invalid depth pixels
+    ctx.close()
+
+
+def test_batch_equals_single_frames(oracle):
+    c = synth.KITTI
+    cam = _camera(c)
+    n = 5
+    lefts, rights = synth.synth_stereo_pool(c["height"], c["width"], n, seed0=30)
+    ctx = api.Context(c["width"], c["height"], 1000, 8, 1.2, camera=cam, max_batch=8)
+    ob = ctx.stereo_batch(lefts, rights)
+    one = api.Context(c["width"], c["height"], 1000, 8, 1.2, camera=cam, max_batch=1)
+    for f in range(n):
+        r = one.stereo_frame(lefts[f], rights[f])
+        a, b = ob.n_left[f], ob.n_right[f]
+        assert (a, b, ob.n_matches[f]) == (len(r.kps_left), len(r.kps_right), r.n_matches)
+        assert np.array_equal(ob.kps_left[f, :a].view(np.uint8), r.kps_left.view(np.uint8))
+        assert np.array_equal(ob.kps_right[f, :b].view(np.uint8), r.kps_right.view(np.uint8))
+        assert np.array_equal(ob.desc_left[f, :a], r.desc_left) and np.array_equal(ob.desc_right[f, :b], r.desc_right)
+        assert np.array_equal(ob.u_right[f, :a], r.u_right) and np.array_equal(ob.depth[f, :a], r.depth)
+    # and one frame against the oracle
+    el, er = oracle.extract(lefts[2], 1000), oracle.extract(rights[2], 1000)
+    _cmp_kps(ob.kps_left[2, : ob.n_left[2]], el.kps, ob.desc_left[2, : ob.n_left[2]], el.desc, "batch left")
+    ctx.close()
+    one.close()
+
+
+def test_device_batch_and_launch_count():
+    import torch
+
+    c = synth.KITTI
+    n = 4
+    lefts, rights = synth.synth_stereo_pool(c["height"], c["width"], n, seed0=50)
+    ctx = api.Context(c["width"], c["height"], 2000, 8, 1.2, camera=_camera(c), max_batch=n)
+    host = ctx.stereo_batch(lefts, rights)
+    dl, dr = torch.from_numpy(lefts).cuda(), torch.from_numpy(rights).cuda()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    before = ctx.launch_count
+    res = ctx.stereo_batch_device(n, dl.data_ptr(), dr.data_ptr(), c["width"], c["width"] * c["height"])
+    assert ctx.launch_count - before == 5  # pyramid+blur, FAST, quadtree, orientation+BRIEF, stereo
+    torch.cuda.synchronize()
+    import ctypes as C
+
+    nm = np.zeros(n, np.int32)
+    torch.cuda.synchronize()
+    cudart = torch.cuda.cudart()
+    assert int(cudart.cudaMemcpy(nm.ctypes.data, res.n_matches, 4 * n, 2)) == 0
+    assert np.array_equal(nm, host.n_matches) and (nm > 500).all()
+    ctx.set_stream(None)
+    ctx.close()
+
+
+def test_reference_shaped_classes(oracle, template_path):
+    c = synth.KITTI
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], 0, 17)
+    ex = api.ORBExtractor(left, 2000, 8, 1.2, template_path, 20, 7)
+    kps, desc = ex.extract()
+    e = oracle.extract(left)
+    _cmp_kps(kps, e.kps, desc, e.desc, "ORBExtractor")
+    assert np.array_equal(ex.getScaledFactors(), e.pyr.sf)
+    assert np.array_equal(ex.getPyramid()[3], e.pyr.level(3))
+    f = api.Frame.createStereo(left, right, 2000, template_path, 20, 7, None, 8, 1.2, camera=_camera(c))
+    assert f.mnN == int((f.mvDepths > 0).sum()) and f.mnN > 1000
