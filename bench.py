@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/s of the ORB front-end (extract L+R + stereo match, 2000 features) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--pool P] [--impl reference]
+
+A "step" is one pass of the hot path (pyramid+blur, FAST, quadtree, orientation+BRIEF, stereo match) over one batch of
+B synthetic KITTI-shaped stereo pairs.  `value` is whole-job frames/s with the inputs resident in HBM (CUDA events on
+the launching stream, max over ranks); `e2e` is the same metric through the host-buffer C-ABI call (pinned host images
+in, results out, copies inside the timed region).  Frames shard by rank with no data-path exchange; at N>1 the left
+descriptors of every step are all-gathered with NCCL (north_star: "only the descriptor gather is collected").
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref: the reference's ORBExtractor.cc and the
+searchByStereo lines of ORBMatcher.cc compiled unmodified) on the host cores of the same box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from orb_slam2_ros2_b200 import synth  # noqa: E402
+
+METRIC = "stereo frames/s (extract+stereo match, 2000 feats)"
+UNIT = "frames/s"
+CFG = synth.KITTI
+
+
+def workload_config(batch, pool):
+    return {
+        "workload": "synthetic KITTI-shaped stereo pairs 1241x376, 2000 features, 8 levels x1.2, ORB extraction (L+R) + stereo matching",
+        "frames_per_step": batch,
+        "pool_pairs": pool,
+        "l2_policy": f"inputs larger than L2: {pool} distinct pairs ({pool * 2 * CFG['width'] * CFG['height'] / 1e6:.0f} MB) cycled, "
+                     f"plus ~{batch * 2 * 2 * 1.45:.0f} MB of pyramid/blur intermediates rewritten every step",
+        "parallelism": "frames sharded by rank, no data-path collective; NCCL all-gather of left descriptors per step when N>1",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [q.strip() for q in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_frames: int, workers: int, pool_pairs: int = 4):
+    """times oracle/_ref (the compiled reference) on `n_frames` stereo frames; returns (fps, cores, kind, sample)"""
+    from oracle import oracle_py as O  # the CPU baseline leg is one of the places allowed to execute oracle/
+
+    lefts, rights = synth.synth_stereo_pool(CFG["height"], CFG["width"], pool_pairs, seed0=1000)
+    with tempfile.TemporaryDirectory() as td:
+        tp = O.write_template_file(os.path.join(td, "brief_template.txt"))
+        if O.have_ref():
+            O.ref_set_camera(CFG["fx"], CFG["fy"], CFG["cx"], CFG["cy"], CFG["bl"], None)
+            secs, _ = O.ref_bench_stereo(lefts, rights, tp, n_frames, workers, CFG["n_features"], CFG["n_levels"], CFG["scale_factor"])
+            kind = "reference"
+            cores = min(os.cpu_count() or 1, 2 * workers)
+        else:  # the reference could not be compiled where this tree was built: time the scalar C port instead
+            t0 = time.perf_counter()
+            for i in range(n_frames):
+                el = O.extract(lefts[i % pool_pairs])
+                er = O.extract(rights[i % pool_pairs])
+                O.search_by_stereo(el, er, np.float32(CFG["fx"]), np.float32(CFG["fx"]) * np.float32(CFG["bl"]))
+            secs = time.perf_counter() - t0
+            kind, cores = "port", 1
+    sample = f"{n_frames} KITTI-shaped stereo frames ({pool_pairs} distinct pairs), {workers} frames in flight x 2 extractor threads (Frame.cc:100-105)"
+    return n_frames / secs, cores, kind, sample
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncpu = os.cpu_count() or 1
+    workers = max(1, ncpu // 2)
+    per_step = max(2, workers)
+    for _ in range(args.warmup):
+        cpu_reference_run(per_step, workers)
+    t0 = time.perf_counter()
+    fps_list = []
+    kind = cores = sample = None
+    for _ in range(args.steps):
+        fps, cores, kind, sample = cpu_reference_run(per_step, workers)
+        fps_list.append(fps)
+    wall = time.perf_counter() - t0
+    value = float(args.steps * per_step / sum(per_step / f for f in fps_list))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(per_step, 4),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + f", per step; {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class CudaArray:
+    """expose a raw device pointer to torch through __cuda_array_interface__"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from orb_slam2_ros2_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    H, W, N = CFG["height"], CFG["width"], CFG["n_features"]
+    B, P = args.batch, args.pool
+    cam = api.Camera(CFG["fx"], CFG["fy"], CFG["cx"], CFG["cy"], CFG["bl"])
+    ctx = api.Context(W, H, N, CFG["n_levels"], CFG["scale_factor"], CFG["ini_th"], CFG["min_th"], camera=cam, max_batch=B, device=local_rank)
+
+    # synthetic pool (distinct seeds per rank), resident in HBM for `value`, in pinned host memory for `e2e`
+    lefts, rights = synth.synth_stereo_pool(H, W, P, seed0=10_000 * rank)
+    h_left, h_right = torch.from_numpy(lefts).pin_memory(), torch.from_numpy(rights).pin_memory()
+    d_left, d_right = h_left.cuda(non_blocking=True), h_right.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    fsz = W * H
+    n_chunks = P // B
+    assert n_chunks >= 1, "pool must hold at least one batch"
+
+    gathered = torch.empty((world, B, N, 32), dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def device_step(i):
+        c = i % n_chunks
+        res = ctx.stereo_batch_device(B, d_left.data_ptr() + c * B * fsz, d_right.data_ptr() + c * B * fsz, W, fsz)
+        if world > 1:
+            # left descriptors = even images of the interleaved [2B][N][32] result array
+            desc = torch.as_tensor(CudaArray(res.desc, (B, 2, N, 32), "|u1"), device="cuda")[:, 0]
+            dist.all_gather_into_tensor(gathered, desc.contiguous())
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ------------------------------------------------------------------
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        device_step(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps * B / (ms_max * 1e-3)
+
+    # sanity: the timed work produced real results
+    res = device_step(0)
+    nm = ctx.read_device(res.n_matches, (B,), np.int32)
+    nk = ctx.read_device(res.n_kps, (2 * B,), np.int32)
+
+    # ---- per-stage device times -> roofline of the dominant kernel --------------------------------------------
+    stage_ms = {}
+    reps = 5
+    for r in range(reps):
+        c = r % n_chunks
+        sm = ctx.profile_stereo_batch_device(B, d_left.data_ptr() + c * B * fsz, d_right.data_ptr() + c * B * fsz, W, fsz)
+        if r == 0:
+            continue
+        for k, v in sm.items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v / (reps - 1)
+    dominant = max(stage_ms, key=stage_ms.get)
+    peak, peak_src = measured_peaks()
+    alg_frame = ctx.algorithmic_bytes(True)
+    dom_ms = stage_ms[dominant]
+    achieved = alg_frame * B / (dom_ms * 1e-3) / 1e9
+    step_total = sum(stage_ms.values())
+    roofline = {
+        "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_frame": alg_frame, "frames_per_launch": B, "kernel_ms": dom_ms,
+        "kernel_share_of_step": dom_ms / step_total, "stage_ms": stage_ms,
+        "whole_step": {"achieved": alg_frame * value / world / 1e9, "frac": alg_frame * value / world / 1e9 / peak},
+    }
+
+    # ---- end to end through the host-buffer C-ABI call (`e2e`) -------------------------------------------------
+    ctx.set_stream(None)  # the library's own stream; the call synchronises internally
+    out = {
+        "kl": torch.empty((B, N, 28), dtype=torch.uint8).pin_memory(), "dl": torch.empty((B, N, 32), dtype=torch.uint8).pin_memory(),
+        "nl": torch.empty(B, dtype=torch.int32).pin_memory(), "kr": torch.empty((B, N, 28), dtype=torch.uint8).pin_memory(),
+        "dr": torch.empty((B, N, 32), dtype=torch.uint8).pin_memory(), "nr": torch.empty(B, dtype=torch.int32).pin_memory(),
+        "ur": torch.empty((B, N), dtype=torch.float64).pin_memory(), "dp": torch.empty((B, N), dtype=torch.float64).pin_memory(),
+        "nm": torch.empty(B, dtype=torch.int32).pin_memory(),
+    }
+    ptrs = [out[k].data_ptr() for k in ("kl", "dl", "nl", "kr", "dr", "nr", "ur", "dp", "nm")]
+    h2d = 2 * B * fsz
+    d2h = sum(v.numel() * v.element_size() for v in out.values())
+
+    def host_step(i):
+        c = i % n_chunks
+        ctx.stereo_batch_ptr(B, h_left.data_ptr() + c * B * fsz, h_right.data_ptr() + c * B * fsz, W, fsz, ptrs)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(3):
+        host_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        host_step(3 + i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * B / float(t.item())
+    e2e_matches = int(out["nm"].sum())
+
+    # ---- single-frame latency (p50), one GPU ---------------------------------------------------------------------
+    latency = None
+    if rank == 0:
+        one = api.Context(W, H, N, CFG["n_levels"], CFG["scale_factor"], CFG["ini_th"], CFG["min_th"], camera=cam, max_batch=1, device=local_rank)
+        one.set_stream(stream.cuda_stream)
+        dev_ms, host_ms = [], []
+        for i in range(60):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            one.stereo_batch_device(1, d_left.data_ptr() + (i % P) * fsz, d_right.data_ptr() + (i % P) * fsz, W, fsz)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if i >= 10:
+                dev_ms.append(a.elapsed_time(b))
+        one.set_stream(None)
+        p1 = [q for q in ptrs]
+        for i in range(60):
+            t0 = time.perf_counter()
+            one.stereo_batch_ptr(1, h_left.data_ptr() + (i % P) * fsz, h_right.data_ptr() + (i % P) * fsz, W, fsz, p1)
+            if i >= 10:
+                host_ms.append(1e3 * (time.perf_counter() - t0))
+        latency = {"p50_ms_device": float(np.median(dev_ms)), "p50_ms_host_to_host": float(np.median(host_ms)), "frames": 50,
+                   "note": "one stereo pair per call; device = inputs and results in HBM, host_to_host = pinned host images in, results out"}
+        one.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ncpu = os.cpu_count() or 1
+        workers = max(1, ncpu // 2)
+        n_frames = max(8, 6 * workers)
+        fps, cores, kind, sample = cpu_reference_run(n_frames, workers)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(B, P), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "matches_last_step": e2e_matches},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
+            "check": {"mean_keypoints_per_image": float(nk.mean()), "mean_matches_per_frame": float(nm.mean())},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="stereo frames per step (per GPU)")
+    ap.add_argument("--pool", type=int, default=256, help="distinct synthetic pairs per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,12 +150,31 @@ int orbx_rgbd_batch_device(orbx_ctx *ctx, int n_frames, const uint8_t *d_gray, s
                            size_t depth_frame_stride_bytes, int depth_type, orbx_device_results *out);
 /* block until the context's stream is idle */
 int orbx_synchronize(orbx_ctx *ctx);
+/* synchronous device-to-host copy of `bytes` bytes of a device result array (after draining the context's stream) */
+int orbx_read_device(orbx_ctx *ctx, const void *device_ptr, void *host_dst, size_t bytes);
 
 /* ---- introspection for benchmarks / profiles ----------------------------------------------------------- */
+#define ORBX_N_STAGES 5
+/* Same work as orbx_stereo_batch_device, with a CUDA event recorded on the stream after every kernel; blocks until
+ * done and returns the device time of each stage in milliseconds:
+ * [0] pyramid+blur  [1] FAST cells  [2] quadtree  [3] orientation+BRIEF  [4] stereo match */
+int orbx_profile_stereo_batch_device(orbx_ctx *ctx, int n_frames, const uint8_t *d_left, const uint8_t *d_right,
+                                     size_t stride, size_t frame_stride, float *stage_ms /* [ORBX_N_STAGES] */);
+/* name of stage i of the list above */
+const char *orbx_stage_name(int stage);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
 int64_t orbx_launch_count(const orbx_ctx *ctx);
 /* algorithmic bytes of one stereo frame / one mono image at this configuration */
 int64_t orbx_algorithmic_bytes(const orbx_ctx *ctx, int stereo);
+
+/* ---- stage-level read-back for parity tests (results of the most recent call; synchronises the stream) ---- */
+/* FAST corners of one level in the reference's detection order (cell-row-major, row-major inside a cell), in ROI
+ * coordinates as in src/ORBExtractor.cc:368-372, i.e. the `levelKps` handed to the Quadtree (:376) */
+int orbx_debug_level_corners(orbx_ctx *ctx, int image, int level, int32_t *xs, int32_t *ys, int32_t *scores, int cap,
+                             int32_t *n);
+/* quadtree survivors of one level (level coordinates, ascending detection index): Quadtree::getFeatIdxs (:378-386) */
+int orbx_debug_level_selected(orbx_ctx *ctx, int image, int level, int32_t *xs, int32_t *ys, int32_t *scores, int cap,
+                              int32_t *n);
 
 #ifdef __cplusplus
 }

@@ -210,7 +210,12 @@ int oracle_fast9_nms(const uint8_t *img, int w, int h, size_t stride, int thresh
   uint8_t *sc = (uint8_t *)calloc((size_t)w * (size_t)h, 1);
   for (int y = 3; y < h - 3; ++y)
     for (int x = 3; x < w - 3; ++x) {
-      int m = oracle_fast9_arc_value(img + (size_t)y * stride + x, stride);
+      const uint8_t *p = img + (size_t)y * stride + x;
+      /* cheap exact pre-test (as cv::FAST does): any arc of 9 contains at least 2 of the 4 compass pixels */
+      int v = p[0], hi = v + threshold, lo = v - threshold;
+      int a = p[3 * (ptrdiff_t)stride], b = p[3], c = p[-3 * (ptrdiff_t)stride], d = p[-3];
+      if ((a > hi) + (b > hi) + (c > hi) + (d > hi) < 2 && (a < lo) + (b < lo) + (c < lo) + (d < lo) < 2) continue;
+      int m = oracle_fast9_arc_value(p, stride);
       if (m > threshold) sc[(size_t)y * w + x] = (uint8_t)(m - 1);
     }
   int n = 0;

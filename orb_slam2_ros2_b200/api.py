@@ -68,6 +68,7 @@ EXPORTS = [
     "orbx_default_config", "orbx_create", "orbx_destroy", "orbx_status_string", "orbx_last_error", "orbx_load_brief_template", "orbx_set_stream",
     "orbx_num_levels", "orbx_level_info", "orbx_extract", "orbx_get_pyramid", "orbx_stereo_frame", "orbx_rgbd_frame", "orbx_stereo_batch",
     "orbx_stereo_batch_device", "orbx_extract_batch_device", "orbx_rgbd_batch_device", "orbx_synchronize", "orbx_launch_count", "orbx_algorithmic_bytes",
+    "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name",
 ]
 
 _lib = None
@@ -108,10 +109,16 @@ def load_library(build_if_missing: bool = True):
     L.orbx_extract_batch_device.argtypes = [vp, C.c_int, vp, sz, sz, C.POINTER(OrbxDeviceResults)]
     L.orbx_rgbd_batch_device.argtypes = [vp, C.c_int, vp, sz, sz, vp, sz, sz, C.c_int, C.POINTER(OrbxDeviceResults)]
     L.orbx_synchronize.argtypes = [vp]
+    L.orbx_read_device.argtypes = [vp, vp, vp, sz]
+    L.orbx_profile_stereo_batch_device.argtypes = [vp, C.c_int, vp, vp, sz, sz, C.POINTER(C.c_float)]
+    L.orbx_stage_name.argtypes = [C.c_int]
+    L.orbx_stage_name.restype = C.c_char_p
     L.orbx_launch_count.argtypes = [vp]
     L.orbx_launch_count.restype = C.c_int64
     L.orbx_algorithmic_bytes.argtypes = [vp, C.c_int]
     L.orbx_algorithmic_bytes.restype = C.c_int64
+    L.orbx_debug_level_corners.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+    L.orbx_debug_level_selected.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
     _lib = L
     return L
 
@@ -211,6 +218,12 @@ class Context:
     def synchronize(self):
         _check(self._h, self._L.orbx_synchronize(self._h), "orbx_synchronize")
 
+    def read_device(self, device_ptr: int, shape, dtype) -> np.ndarray:
+        """copy a device result array (a pointer from OrbxDeviceResults) to a new numpy array"""
+        out = np.zeros(shape, dtype)
+        _check(self._h, self._L.orbx_read_device(self._h, C.c_void_p(device_ptr), out.ctypes.data, out.nbytes), "orbx_read_device")
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(self._L.orbx_launch_count(self._h))
@@ -265,6 +278,22 @@ class Context:
         k = n.value
         return RGBDResult(kraw[:k], kund[:k], desc[:k], ur[:k], dp[:k])
 
+    # ---- stage-level read-back (parity tests) --------------------------------------------------------------------
+    def _debug_list(self, fn, image, level, cap):
+        xs, ys, sc, n = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), C.c_int32(0)
+        _check(self._h, fn(self._h, image, level, xs.ctypes.data, ys.ctypes.data, sc.ctypes.data, cap, C.addressof(n)), "orbx_debug")
+        k = min(n.value, cap)
+        return np.stack([xs[:k], ys[:k], sc[:k]], 1)
+
+    def level_corners(self, image: int, level: int) -> np.ndarray:
+        """(n,3) int32 (x_roi, y_roi, score): the level's FAST corners in the reference's detection order"""
+        w, h, _, _ = self.level_info(level)
+        return self._debug_list(self._L.orbx_debug_level_corners, image, level, w * h // 4 + 16)
+
+    def level_selected(self, image: int, level: int) -> np.ndarray:
+        """(n,3) int32 (x, y, score) in level coordinates: the quadtree survivors of the level"""
+        return self._debug_list(self._L.orbx_debug_level_selected, image, level, self.n_features + 8)
+
     # ---- batches ----------------------------------------------------------------------------------------------------
     def stereo_batch(self, left: np.ndarray, right: np.ndarray, out: "StereoBatchBuffers | None" = None):
         """left/right: (n, H, W) uint8 host arrays (pinned memory makes the copies asynchronous)."""
@@ -287,6 +316,13 @@ class Context:
         rc = self._L.orbx_stereo_batch_device(self._h, n_frames, C.c_void_p(d_left_ptr), C.c_void_p(d_right_ptr), stride, frame_stride, C.byref(res))
         _check(self._h, rc, "orbx_stereo_batch_device")
         return res
+
+    def profile_stereo_batch_device(self, n_frames, d_left_ptr, d_right_ptr, stride, frame_stride) -> dict:
+        """device milliseconds per stage (events between the kernels; blocks)"""
+        ms = (C.c_float * 5)()
+        rc = self._L.orbx_profile_stereo_batch_device(self._h, n_frames, C.c_void_p(d_left_ptr), C.c_void_p(d_right_ptr), stride, frame_stride, ms)
+        _check(self._h, rc, "orbx_profile_stereo_batch_device")
+        return {self._L.orbx_stage_name(i).decode(): float(ms[i]) for i in range(5)}
 
     def extract_batch_device(self, n_images, d_ptr, stride, frame_stride) -> OrbxDeviceResults:
         res = OrbxDeviceResults()

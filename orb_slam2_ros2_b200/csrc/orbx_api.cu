@@ -525,6 +525,15 @@ extern "C"
     return ORBX_OK;
   }
 
+  int orbx_read_device(orbx_ctx *c, const void *device_ptr, void *host_dst, size_t bytes)
+  {
+    if (!c || !device_ptr || !host_dst) return ORBX_ERR_INVALID_ARG;
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    ORBX_CUDA(c, cudaMemcpy(host_dst, device_ptr, bytes, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+  }
+
   int64_t orbx_launch_count(const orbx_ctx *c) { return c ? c->launches : 0; }
   int64_t orbx_algorithmic_bytes(const orbx_ctx *c, int stereo) { return c ? (stereo ? c->alg_bytes_stereo : c->alg_bytes_image) : 0; }
 
@@ -569,6 +578,49 @@ extern "C"
     c->last_images = 2 * n_frames;
     c->last_stereo = 1;
     fill_results(c, 2 * n_frames, n_frames, out);
+    return ORBX_OK;
+  }
+
+  const char *orbx_stage_name(int stage)
+  {
+    static const char *names[ORBX_N_STAGES] = {"pyramid_blur", "fast_cells", "quadtree", "orient_brief", "stereo_match"};
+    return (stage >= 0 && stage < ORBX_N_STAGES) ? names[stage] : "";
+  }
+
+  int orbx_profile_stereo_batch_device(orbx_ctx *c, int n_frames, const uint8_t *d_left, const uint8_t *d_right, size_t stride, size_t frame_stride,
+                                       float *stage_ms)
+  {
+    if (!c || !d_left || !d_right || n_frames < 1 || !stage_ms) return ORBX_ERR_INVALID_ARG;
+    if (n_frames > c->cfg.max_batch) return fail(c, ORBX_ERR_CAPACITY, "n_frames > max_batch");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    Params p = c->p;
+    p.stereo = 1;
+    p.in_left = d_left;
+    p.in_right = d_right;
+    p.in_stride = stride;
+    p.in_frame_stride = frame_stride;
+    cudaEvent_t ev[ORBX_N_STAGES + 1];
+    for (auto &e : ev) ORBX_CUDA(c, cudaEventCreate(&e));
+    const int ni = 2 * n_frames;
+    ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)n_frames * sizeof(int), c->stream));
+    ORBX_CUDA(c, cudaEventRecord(ev[0], c->stream));
+    launch_pyramid(p, ni, c->stream);
+    ORBX_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    launch_fast(p, ni, c->stream);
+    ORBX_CUDA(c, cudaEventRecord(ev[2], c->stream));
+    launch_quadtree(p, ni, c->qt_smem, c->stream);
+    ORBX_CUDA(c, cudaEventRecord(ev[3], c->stream));
+    launch_orient_brief(p, ni, c->stream);
+    ORBX_CUDA(c, cudaEventRecord(ev[4], c->stream));
+    launch_stereo(p, n_frames, c->stream);
+    ORBX_CUDA(c, cudaEventRecord(ev[5], c->stream));
+    c->launches += 5;
+    ORBX_CUDA(c, cudaGetLastError());
+    ORBX_CUDA(c, cudaEventSynchronize(ev[5]));
+    for (int i = 0; i < ORBX_N_STAGES; ++i) ORBX_CUDA(c, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    c->last_images = ni;
+    c->last_stereo = 1;
     return ORBX_OK;
   }
 
@@ -724,6 +776,57 @@ extern "C"
     const uint8_t *src = (blurred ? c->p.blur : c->p.pyr) + (size_t)side * c->p.pyr_img_stride + L.pyr_off;
     ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     ORBX_CUDA(c, cudaMemcpy2D(dst, dst_stride, src, (size_t)L.pitch, (size_t)L.w, (size_t)L.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+  }
+
+  int orbx_debug_level_corners(orbx_ctx *c, int image, int level, int32_t *xs, int32_t *ys, int32_t *scores, int cap, int32_t *n)
+  {
+    if (!c || !n || level < 0 || level >= c->cfg.n_levels || image < 0) return ORBX_ERR_INVALID_ARG;
+    if (image >= c->last_images) return fail(c, ORBX_ERR_STATE, "no image with that index has been processed");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    const Level &L = c->levels[level];
+    std::vector<int> cnt(L.n_level_cells);
+    ORBX_CUDA(c, cudaMemcpy(cnt.data(), c->p.cell_cnt + (size_t)image * c->p.n_cells + L.cell_base, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    int k = 0;
+    std::vector<uint32_t> buf;
+    for (int ci = 0; ci < L.n_level_cells; ++ci)
+    {
+      const Cell &ce = c->cells[L.cell_base + ci];
+      buf.resize(cnt[ci]);
+      if (cnt[ci])
+        ORBX_CUDA(c, cudaMemcpy(buf.data(), c->p.cell_list + (size_t)image * c->p.cell_entries + ce.slot, cnt[ci] * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost));
+      for (int j = 0; j < cnt[ci]; ++j, ++k)
+        if (k < cap)
+        {
+          if (xs) xs[k] = (int)(buf[j] & 0xfffu);
+          if (ys) ys[k] = (int)((buf[j] >> 12) & 0xfffu);
+          if (scores) scores[k] = (int)(buf[j] >> 24);
+        }
+    }
+    *n = k;
+    return ORBX_OK;
+  }
+
+  int orbx_debug_level_selected(orbx_ctx *c, int image, int level, int32_t *xs, int32_t *ys, int32_t *scores, int cap, int32_t *n)
+  {
+    if (!c || !n || level < 0 || level >= c->cfg.n_levels || image < 0) return ORBX_ERR_INVALID_ARG;
+    if (image >= c->last_images) return fail(c, ORBX_ERR_STATE, "no image with that index has been processed");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    const Level &L = c->levels[level];
+    int cnt = 0;
+    ORBX_CUDA(c, cudaMemcpy(&cnt, c->p.sel_cnt + (size_t)image * c->p.n_levels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> buf(cnt > 0 ? cnt : 1);
+    if (cnt) ORBX_CUDA(c, cudaMemcpy(buf.data(), c->p.sel + (size_t)image * c->p.sel_entries + L.sel_off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < cnt && k < cap; ++k)
+    {
+      if (xs) xs[k] = (int)(buf[k] & 0xfffu);
+      if (ys) ys[k] = (int)((buf[k] >> 12) & 0xfffu);
+      if (scores) scores[k] = (int)(buf[k] >> 24);
+    }
+    *n = cnt;
     return ORBX_OK;
   }
 

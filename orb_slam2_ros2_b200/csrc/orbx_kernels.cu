@@ -10,6 +10,7 @@
 // All arithmetic that decides a result bit is integer, or IEEE float/double with explicit round-to-nearest
 // intrinsics (no FMA contraction), so results equal the CPU path bit for bit.
 #include "orbx_device.cuh"
+#include <cstdio>
 
 namespace orbx
 {
@@ -210,26 +211,32 @@ __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
   d[13] = v - c[P - 3];
   d[14] = v - c[2 * P - 2];
   d[15] = v - c[3 * P - 1];
-  int mn2[16], mx2[16], mn4[16], mx4[16];
+  // Sliding minimum over 9 of 16 by doubling (2, 4, 8, +1), once for d (ring darker than the centre) and once for
+  // e = -d (ring brighter).  NB: written with two explicit min-chains instead of "-max(d...)": nvcc 12.9 for sm_100a
+  // folds the negated 3-input max (VIMNMX3) incorrectly and drops the negation.
+  int e[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) e[k] = -d[k];
+  int a2[16], b2[16], a4[16], b4[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k)
   {
-    mn2[k] = min(d[k], d[(k + 1) & 15]);
-    mx2[k] = max(d[k], d[(k + 1) & 15]);
+    a2[k] = min(d[k], d[(k + 1) & 15]);
+    b2[k] = min(e[k], e[(k + 1) & 15]);
   }
 #pragma unroll
   for (int k = 0; k < 16; ++k)
   {
-    mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
-    mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+    a4[k] = min(a2[k], a2[(k + 2) & 15]);
+    b4[k] = min(b2[k], b2[(k + 2) & 15]);
   }
   int best = -256;
 #pragma unroll
   for (int k = 0; k < 16; ++k)
   {
-    const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-    const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-    best = max(best, max(mn9, -mx9));
+    const int a9 = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);
+    const int b9 = min(min(b4[k], b4[(k + 4) & 15]), e[(k + 8) & 15]);
+    best = max(best, max(a9, b9));
   }
   return best;
 }
@@ -286,6 +293,14 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
     const int i = s_cand[k];
     const int zy = i / zw, zx = i - zy * zw;
     const int m = fast_arc_value(&s_pat[(zy + 3) * kPatPitch + zx + 3]);
+#ifdef ORBX_DEBUG_FAST
+    if (c.level == 7 && c.x0 == 16 && c.y0 == 16 && zy == 1 && zx == 24)
+    {
+      const uint8_t *q = &s_pat[(zy + 3) * kPatPitch + zx + 3];
+      printf("DBG cell pw=%d ph=%d pitch=%d v=%d m=%d ring: %d %d %d %d | %d %d %d %d | row: %d %d %d %d %d %d %d\n", pw, ph, pitch, q[0], m, q[3 * kPatPitch], q[3], q[-3 * kPatPitch], q[-3],
+             q[3 * kPatPitch + 1], q[2 * kPatPitch + 2], q[kPatPitch + 3], q[-kPatPitch + 3], q[-3], q[-2], q[-1], q[0], q[1], q[2], q[3]);
+    }
+#endif
     if (m > tq) s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)m;
   }
   __syncthreads();
