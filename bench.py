@@ -190,7 +190,8 @@ def run_gpu_arm(args):
     h_left, h_right = torch.from_numpy(lefts).pin_memory(), torch.from_numpy(rights).pin_memory()
     d_left, d_right = h_left.cuda(non_blocking=True), h_right.cuda(non_blocking=True)
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # the stream every kernel of the timed region is launched on
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     fsz = W * H
     n_chunks = P // B

@@ -79,7 +79,8 @@ const char *orbx_status_string(int status);
 const char *orbx_last_error(const orbx_ctx *ctx);
 /* replaces: ORBExtractor::initBriefTemplate (src/ORBExtractor.cc:242-267): header line + 256 rows "x1 y1 x2 y2" */
 int orbx_load_brief_template(const char *path, float *pattern_out /* [1024] */);
-/* launch on this CUDA stream (cudaStream_t) instead of the context's own; NULL restores the default */
+/* launch on this CUDA stream (cudaStream_t) instead of the context's own non-blocking stream; NULL restores the
+ * context's own stream (pass cudaStreamLegacy / cudaStreamPerThread explicitly to use a default stream) */
 int orbx_set_stream(orbx_ctx *ctx, void *cuda_stream);
 
 /* ---- per-config tables ---------------------------------------------------------------------------------- */

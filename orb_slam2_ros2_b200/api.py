@@ -213,7 +213,12 @@ class Context:
         return np.array([self.level_info(l)[2] for l in range(self.n_levels)], np.float32)
 
     def set_stream(self, cuda_stream_ptr: int | None):
-        _check(self._h, self._L.orbx_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "orbx_set_stream")
+        """None restores the context's own stream; 0 (torch's legacy default stream) is passed as cudaStreamLegacy"""
+        if cuda_stream_ptr is None:
+            ptr = 0
+        else:
+            ptr = int(cuda_stream_ptr) or 1  # cudaStreamLegacy == (cudaStream_t)0x1
+        _check(self._h, self._L.orbx_set_stream(self._h, C.c_void_p(ptr)), "orbx_set_stream")
 
     def synchronize(self):
         _check(self._h, self._L.orbx_synchronize(self._h), "orbx_synchronize")
