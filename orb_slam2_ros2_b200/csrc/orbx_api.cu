@@ -196,7 +196,7 @@ int build_tables(orbx_ctx *c)
         ce.y0 = iniY;
         ce.pw = maxX - iniX;
         ce.ph = maxY - iniY;
-        if (ce.pw > kMaxPatch || ce.ph > kMaxPatch) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cell patch exceeds 72 px");
+        if (ce.pw > kMaxPatch || ce.ph > kMaxPatch) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cell patch exceeds 70 px");
         const int zw = std::max(0, ce.pw - 6), zh = std::max(0, ce.ph - 6);
         ce.cap = std::max(1, ((zw + 1) / 2) * ((zh + 1) / 2)); // strict 8-neighbour maxima cannot be denser than this
         ce.slot = (int)slot_off;

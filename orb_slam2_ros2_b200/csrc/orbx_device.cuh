@@ -27,7 +27,7 @@ constexpr int kHalo = 3;        // 7x7 Gaussian
 constexpr int kPyrThreads = 256;
 constexpr int kFastThreads = 128;
 constexpr int kQtThreads = 128;
-constexpr int kMaxPatch = 72;   // largest FAST cell patch edge (cell < 60 px + 6), padded
+constexpr int kMaxPatch = 70;   // largest FAST cell patch edge: a cell is < 60 px wide, + 6 px apron; zone <= 64
 constexpr int kMaxStrips = 255; // root split fan-out: round(w/h) vertical strips
 constexpr uint32_t kNil = 0xFFFFu;
 

@@ -69,15 +69,21 @@ template <int NT> __device__ __forceinline__ int block_exclusive_scan(int v, int
 // K1: pyramid level (resize from level 0) fused with the 7x7 Gaussian blur.  One CTA per 64x32 output tile.
 //   cv::resize INTER_LINEAR 8UC1: 11-bit coefficient tables (built on the host exactly like OpenCV does), int32 maths.
 //   cv::GaussianBlur 7x7 sigma 2: 8.8 fixed-point kernel {18,34,48,56,48,34,18}, u16 rows, (v + 32768) >> 16.
+//   Stage A  thread <-> tile column (coefficients in registers), loop over rows: 4 byte gathers from level 0 per pixel
+//   Stage B  horizontal pass on packed bytes: 3 aligned LDS.32 + funnel shifts + 8 DP4A per 4 pixels -> u16
+//   Stage C  vertical pass: one thread per 4 columns x 2 rows, LDS.64 of packed u16, exact integer MACs
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kSrcW = kTileW + 2 * kHalo;      // 70
 constexpr int kSrcH = kTileH + 2 * kHalo;      // 38
-constexpr int kSrcPitch = 72;
+constexpr int kSrcPitch = 72;                  // bytes, word aligned
+constexpr int kColGroups = kPyrThreads / kSrcPitch; // 3 row-interleaved groups of 72 column threads
 
 __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params p)
 {
   __shared__ __align__(16) uint8_t s_src[kSrcH * kSrcPitch];
   __shared__ __align__(16) uint16_t s_h[kSrcH * kTileW];
+  __shared__ int s_ys[kSrcH];      // source row (or kOutside: beyond the level + halo, never read)
+  __shared__ short2 s_yc[kSrcH];   // vertical coefficients
 
   const Tile t = p.tiles[blockIdx.x];
   const int img = blockIdx.y;
@@ -86,44 +92,84 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
   const uint8_t *__restrict__ src = input_image(p, img);
   const size_t sstride = p.in_stride;
   const int W = p.width, H = p.height;
-  const int *__restrict__ xofs = p.tab_ofs + L.tab_x;
-  const int *__restrict__ yofs = p.tab_ofs + L.tab_y;
-  const short2 *__restrict__ xco = p.tab_coef + L.tab_x;
-  const short2 *__restrict__ yco = p.tab_coef + L.tab_y;
   const int level = t.level, area2x = L.area2x;
+  const int tid = threadIdx.x;
+
+  constexpr int kOutside = -(1 << 30);
+  if (tid < kSrcH)
+  {
+    const int ry = t.y0 + tid - kHalo;
+    int sy = kOutside;
+    short2 b = make_short2(0, 0);
+    if (ry < lh + kHalo)
+    {
+      const int gy = refl101(ry, lh);
+      if (level == 0 || area2x)
+        sy = gy;
+      else
+      {
+        sy = p.tab_ofs[L.tab_y + gy];
+        b = p.tab_coef[L.tab_y + gy];
+      }
+    }
+    s_ys[tid] = sy;
+    s_yc[tid] = b;
+  }
+  __syncthreads();
 
   // stage A: the tile plus a 3-pixel halo of the (resized) level image, REFLECT_101 at the level's borders
-  for (int i = threadIdx.x; i < kSrcH * kSrcW; i += kPyrThreads)
   {
-    const int ty = i / kSrcW, tx = i - ty * kSrcW;
-    const int rx = t.x0 + tx - kHalo, ry = t.y0 + ty - kHalo;
-    int v = 0;
-    if (rx < lw + kHalo && ry < lh + kHalo)
+    const int col = tid % kSrcPitch, grp = tid / kSrcPitch;
+    const int rx = t.x0 + col - kHalo;
+    if (grp < kColGroups && col < kSrcW)
     {
-      const int gx = refl101(rx, lw), gy = refl101(ry, lh);
+      const bool col_ok = rx < lw + kHalo;
+      const int gx = col_ok ? refl101(rx, lw) : 0;
       if (level == 0)
       {
-        v = src[(size_t)gy * sstride + gx];
+        for (int ty = grp; ty < kSrcH; ty += kColGroups)
+        {
+          const int sy = s_ys[ty];
+          s_src[ty * kSrcPitch + col] = (col_ok && sy != kOutside) ? src[(size_t)sy * sstride + gx] : (uint8_t)0;
+        }
       }
       else if (area2x)
       {
-        const uint8_t *s0 = src + (size_t)(2 * gy) * sstride + 2 * gx;
-        v = (s0[0] + s0[1] + s0[sstride] + s0[sstride + 1] + 2) >> 2;
+        for (int ty = grp; ty < kSrcH; ty += kColGroups)
+        {
+          const int sy = s_ys[ty];
+          int v = 0;
+          if (col_ok && sy != kOutside)
+          {
+            const uint8_t *s0 = src + (size_t)(2 * sy) * sstride + 2 * gx;
+            v = (s0[0] + s0[1] + s0[sstride] + s0[sstride + 1] + 2) >> 2;
+          }
+          s_src[ty * kSrcPitch + col] = (uint8_t)v;
+        }
       }
       else
       {
-        const int sx = xofs[gx], sy = yofs[gy];
-        const short2 a = xco[gx], b = yco[gy];
+        const int sx = col_ok ? p.tab_ofs[L.tab_x + gx] : 0;
+        const short2 a = col_ok ? p.tab_coef[L.tab_x + gx] : make_short2(0, 0);
         const int sx1 = min(sx + 1, W - 1);
-        const int sy0 = min(max(sy, 0), H - 1), sy1 = min(max(sy + 1, 0), H - 1);
-        const uint8_t *r0 = src + (size_t)sy0 * sstride, *r1 = src + (size_t)sy1 * sstride;
-        const int h0 = r0[sx] * a.x + r0[sx1] * a.y;
-        const int h1 = r1[sx] * a.x + r1[sx1] * a.y;
-        v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
-        v = min(max(v, 0), 255);
+        for (int ty = grp; ty < kSrcH; ty += kColGroups)
+        {
+          const int sy = s_ys[ty];
+          int v = 0;
+          if (col_ok && sy != kOutside)
+          {
+            const short2 b = s_yc[ty];
+            const int sy0 = min(max(sy, 0), H - 1), sy1 = min(max(sy + 1, 0), H - 1);
+            const uint8_t *r0 = src + (size_t)sy0 * sstride, *r1 = src + (size_t)sy1 * sstride;
+            const int h0 = r0[sx] * a.x + r0[sx1] * a.y;
+            const int h1 = r1[sx] * a.x + r1[sx1] * a.y;
+            v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+          }
+          s_src[ty * kSrcPitch + col] = (uint8_t)v;
+        }
       }
     }
-    s_src[ty * kSrcPitch + tx] = (uint8_t)v;
   }
   __syncthreads();
 
@@ -131,9 +177,9 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
   uint8_t *__restrict__ blr = p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off;
 
   // the level image itself (getPyramid(); FAST, orientation and the stereo SAD read it): 4 pixels per store
-  for (int i = threadIdx.x; i < kTileH * (kTileW / 4); i += kPyrThreads)
+  for (int i = tid; i < kTileH * (kTileW / 4); i += kPyrThreads)
   {
-    const int ty = i / (kTileW / 4), tx = (i - ty * (kTileW / 4)) * 4;
+    const int ty = i >> 4, tx = (i & 15) * 4;
     const int gx = t.x0 + tx, gy = t.y0 + ty;
     if (gy < lh && gx < pitch)
     {
@@ -143,33 +189,56 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
     }
   }
 
-  // stage B: horizontal pass (fits u16: 255 * 256)
-  for (int i = threadIdx.x; i < kSrcH * kTileW; i += kPyrThreads)
+  // stage B: horizontal pass, 4 outputs per item from 3 aligned words (bytes 4g .. 4g+11); sums fit u16 (255 * 256)
   {
-    const int ty = i / kTileW, tx = i - ty * kTileW;
-    const uint8_t *s = &s_src[ty * kSrcPitch + tx];
-    const int acc = 18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3];
-    s_h[i] = (uint16_t)acc;
+    constexpr uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24); // taps 0..3
+    constexpr uint32_t K1 = 48u | (34u << 8) | (18u << 16);               // taps 4..6
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s_src);
+    uint2 *h2 = reinterpret_cast<uint2 *>(s_h);
+    for (int i = tid; i < kSrcH * (kTileW / 4); i += kPyrThreads)
+    {
+      const int ty = i >> 4, g = i & 15;
+      const uint32_t *row = s32 + ty * (kSrcPitch / 4) + g;
+      const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+      const uint32_t o0 = __dp4a(w0, K0, __dp4a(w1, K1, 0u));
+      const uint32_t o1 = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
+      const uint32_t o2 = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
+      const uint32_t o3 = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
+      h2[i] = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+    }
   }
   __syncthreads();
 
-  // stage C: vertical pass + rounding, 4 pixels per store
-  for (int i = threadIdx.x; i < kTileH * (kTileW / 4); i += kPyrThreads)
+  // stage C: vertical pass + rounding; one thread per 4 columns x 2 output rows
   {
-    const int ty = i / (kTileW / 4), tx = (i - ty * (kTileW / 4)) * 4;
-    const int gx = t.x0 + tx, gy = t.y0 + ty;
+    const int g = tid & 15, ry = (tid >> 4) * 2; // 16 column groups x 16 row pairs == 256 threads
+    const int gx = t.x0 + g * 4, gy = t.y0 + ry;
     if (gy < lh && gx < pitch)
     {
-      uint32_t w = 0;
+      const uint2 *h2 = reinterpret_cast<const uint2 *>(s_h);
+      uint32_t c[8][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int r = 0; r < 8; ++r)
       {
-        const uint16_t *c = &s_h[ty * kTileW + tx + k];
-        const uint32_t acc = 18u * (c[0] + c[6 * kTileW]) + 34u * (c[kTileW] + c[5 * kTileW]) + 48u * (c[2 * kTileW] + c[4 * kTileW]) +
-                             56u * c[3 * kTileW];
-        w |= ((acc + 32768u) >> 16) << (8 * k);
+        const uint2 v = h2[(ry + r) * (kTileW / 4) + g];
+        c[r][0] = v.x & 0xffffu;
+        c[r][1] = v.x >> 16;
+        c[r][2] = v.y & 0xffffu;
+        c[r][3] = v.y >> 16;
       }
-      *reinterpret_cast<uint32_t *>(blr + (size_t)gy * pitch + gx) = w;
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+      {
+        if (gy + o >= lh) break;
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          const uint32_t acc = 18u * (c[o][k] + c[o + 6][k]) + 34u * (c[o + 1][k] + c[o + 5][k]) + 48u * (c[o + 2][k] + c[o + 4][k]) + 56u * c[o + 3][k];
+          w |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(blr + (size_t)(gy + o) * pitch + gx) = w;
+      }
     }
   }
 }
@@ -186,9 +255,9 @@ void launch_pyramid(const Params &p, int n_images, cudaStream_t s)
 //   corner at threshold t  <=>  m > t;  cv score = m - 1;  keep iff score > all 8 neighbours' scores (strict), where a
 //   neighbour that is not a corner at t, or lies outside the cell's detection zone, scores 0.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kPatPitch = kMaxPatch;          // 72
-constexpr int kZoneMax = kMaxPatch - 6;       // 66
-constexpr int kMapPitch = kZoneMax + 2;       // 68
+constexpr int kPatPitch = 80;                 // bytes: patch rows keep the level image's 4-byte alignment (x0 & 3)
+constexpr int kZoneMax = 64;                  // detection zone edge (patch edge - 6); one 64-bit mask per zone row
+constexpr int kMapPitch = kZoneMax + 4;       // 68
 
 __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
 {
@@ -241,13 +310,24 @@ __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
   return best;
 }
 
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kCandSeg = (kZoneMax / kFastWarps) * kZoneMax; // candidates one warp can produce (its rows x 64)
+
+// at least 4 circularly consecutive bits set in an 8-bit ring mask
+__device__ __forceinline__ bool ring8_has_run4(unsigned m)
+{
+  m |= m << 8;
+  return ((m & (m >> 1) & (m >> 2) & (m >> 3)) & 0xffu) != 0u;
+}
+
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p)
 {
-  __shared__ __align__(16) uint8_t s_pat[kMaxPatch * kPatPitch];
-  __shared__ uint8_t s_map[(kZoneMax + 2) * kMapPitch];
-  __shared__ uint16_t s_cand[kZoneMax * kZoneMax];
-  __shared__ int s_ncand;
-  __shared__ int s_warp[kFastThreads / 32];
+  __shared__ __align__(16) uint8_t s_pat[(kZoneMax + 6) * kPatPitch];
+  __shared__ __align__(16) uint8_t s_map[(kZoneMax + 2) * kMapPitch + 16]; // + 16: zeroed with 16-byte stores
+  __shared__ uint16_t s_cand[kFastWarps * kCandSeg];
+  __shared__ unsigned long long s_keep_ini[kZoneMax], s_keep_min[kZoneMax];
+  __shared__ int s_wcnt[kFastWarps];
+  __shared__ int s_warp[kFastWarps];
 
   const Cell c = p.cells[blockIdx.x];
   const int img = blockIdx.y;
@@ -256,91 +336,118 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
   const int pitch = L.pitch;
   const int pw = c.pw, ph = c.ph;
   const int zw = pw - 6, zh = ph - 6; // detection zone: FAST looks at [3, w-3) x [3, h-3) of the patch
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned FULL = 0xffffffffu;
   int *cnt_out = p.cell_cnt + (size_t)img * p.n_cells + blockIdx.x;
   if (zw <= 0 || zh <= 0)
   {
     if (tid == 0) *cnt_out = 0;
     return;
   }
-  const int zn = zw * zh;
   const int tq = min(p.ini_th, p.min_th);
 
-  if (tid == 0) s_ncand = 0;
-  for (int i = tid; i < (zh + 2) * kMapPitch; i += kFastThreads) s_map[i] = 0;
-  for (int i = tid; i < ph * pw; i += kFastThreads)
+  // patch rows as aligned 32-bit words (one warp per row); zero the arc-value map and the keep masks
+  const int xoff = c.x0 & 3;
   {
-    const int y = i / pw, x = i - y * pw;
-    s_pat[y * kPatPitch + x] = lvl[(size_t)(c.y0 + y) * pitch + c.x0 + x];
+    const int nw = (xoff + pw + 3) >> 2; // <= 19 words
+    const uint8_t *g = lvl + (size_t)c.y0 * pitch + (c.x0 - xoff);
+    uint32_t *s32 = reinterpret_cast<uint32_t *>(s_pat);
+    for (int y = wid; y < ph; y += kFastWarps)
+      if (lane < nw) s32[y * (kPatPitch / 4) + lane] = *reinterpret_cast<const uint32_t *>(g + (size_t)y * pitch + 4 * lane);
+    uint4 *m128 = reinterpret_cast<uint4 *>(s_map);
+    for (int i = tid; i < ((zh + 2) * kMapPitch + 15) / 16; i += kFastThreads) m128[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < kZoneMax)
+    {
+      s_keep_ini[tid] = 0ull;
+      s_keep_min[tid] = 0ull;
+    }
   }
   __syncthreads();
 
-  // quick reject: every arc of 9 holds at least 2 of the 4 compass pixels
-  for (int i = tid; i < zn; i += kFastThreads)
+  // Pre-tests at the lower threshold (both are necessary conditions for a 9-arc):
+  //   (1) at least 2 of the 4 compass ring pixels are brighter (darker) than the centre by more than t
+  //   (2) at least 4 consecutive of the 8 even ring pixels are
+  // Survivors go to a per-warp candidate segment (warp-local counter, no atomics).
+  const uint8_t *pat0 = s_pat + 3 * kPatPitch + 3 + xoff; // zone pixel (0,0)
+  int wcnt = 0;
+  uint16_t *my_cand = s_cand + wid * kCandSeg;
+  for (int zy = wid; zy < zh; zy += kFastWarps)
   {
-    const int zy = i / zw, zx = i - zy * zw;
-    const uint8_t *q = &s_pat[(zy + 3) * kPatPitch + zx + 3];
-    const int v = q[0], hi = v + tq, lo = v - tq;
-    const int a = q[3 * kPatPitch], b = q[3], cc = q[-3 * kPatPitch], dd = q[-3];
-    const int nb = (a > hi) + (b > hi) + (cc > hi) + (dd > hi);
-    const int nd = (a < lo) + (b < lo) + (cc < lo) + (dd < lo);
-    if (nb >= 2 || nd >= 2) s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)i;
+    for (int zx0 = 0; zx0 < zw; zx0 += 32)
+    {
+      const int zx = zx0 + lane;
+      bool cand = false;
+      if (zx < zw)
+      {
+        const uint8_t *q = pat0 + zy * kPatPitch + zx;
+        const int v = q[0], hi = v + tq, lo = v - tq;
+        const int r0 = q[3 * kPatPitch], r4 = q[3], r8 = q[-3 * kPatPitch], r12 = q[-3];
+        const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
+        const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
+        if (nb >= 2 || nd >= 2)
+        {
+          const int r2 = q[2 * kPatPitch + 2], r6 = q[-2 * kPatPitch + 2], r10 = q[-2 * kPatPitch - 2], r14 = q[2 * kPatPitch - 2];
+          const unsigned mb = (unsigned)(r0 > hi) | ((unsigned)(r2 > hi) << 1) | ((unsigned)(r4 > hi) << 2) | ((unsigned)(r6 > hi) << 3) |
+                              ((unsigned)(r8 > hi) << 4) | ((unsigned)(r10 > hi) << 5) | ((unsigned)(r12 > hi) << 6) | ((unsigned)(r14 > hi) << 7);
+          const unsigned md = (unsigned)(r0 < lo) | ((unsigned)(r2 < lo) << 1) | ((unsigned)(r4 < lo) << 2) | ((unsigned)(r6 < lo) << 3) |
+                              ((unsigned)(r8 < lo) << 4) | ((unsigned)(r10 < lo) << 5) | ((unsigned)(r12 < lo) << 6) | ((unsigned)(r14 < lo) << 7);
+          cand = ring8_has_run4(mb) || ring8_has_run4(md);
+        }
+      }
+      const unsigned m = __ballot_sync(FULL, cand);
+      if (cand) my_cand[wcnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(zy * kZoneMax + zx);
+      wcnt += __popc(m);
+    }
   }
+  if (lane == 0) s_wcnt[wid] = wcnt;
   __syncthreads();
-  const int ncand = s_ncand;
+  const int n0 = s_wcnt[0], n1 = n0 + s_wcnt[1], n2 = n1 + s_wcnt[2], ncand = n2 + s_wcnt[3];
+  static_assert(kFastWarps == 4, "candidate segment lookup assumes 4 warps");
+  auto cand_at = [&](int k) -> int {
+    const int seg = (k >= n0) + (k >= n1) + (k >= n2);
+    const int base = seg == 0 ? 0 : (seg == 1 ? n0 : (seg == 2 ? n1 : n2));
+    return s_cand[seg * kCandSeg + (k - base)];
+  };
   for (int k = tid; k < ncand; k += kFastThreads)
   {
-    const int i = s_cand[k];
-    const int zy = i / zw, zx = i - zy * zw;
-    const int m = fast_arc_value(&s_pat[(zy + 3) * kPatPitch + zx + 3]);
-#ifdef ORBX_DEBUG_FAST
-    if (c.level == 7 && c.x0 == 16 && c.y0 == 16 && zy == 1 && zx == 24)
-    {
-      const uint8_t *q = &s_pat[(zy + 3) * kPatPitch + zx + 3];
-      printf("DBG cell pw=%d ph=%d pitch=%d v=%d m=%d ring: %d %d %d %d | %d %d %d %d | row: %d %d %d %d %d %d %d\n", pw, ph, pitch, q[0], m, q[3 * kPatPitch], q[3], q[-3 * kPatPitch], q[-3],
-             q[3 * kPatPitch + 1], q[2 * kPatPitch + 2], q[kPatPitch + 3], q[-kPatPitch + 3], q[-3], q[-2], q[-1], q[0], q[1], q[2], q[3]);
-    }
-#endif
+    const int i = cand_at(k);
+    const int zy = i >> 6, zx = i & (kZoneMax - 1);
+    const int m = fast_arc_value(pat0 + zy * kPatPitch + zx);
     if (m > tq) s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)m;
   }
   __syncthreads();
 
-  // non-max suppression for both thresholds; each thread owns a contiguous run of zone pixels (row-major)
-  const int per = (zn + kFastThreads - 1) / kFastThreads; // <= 35
-  const int i0 = tid * per, i1 = min(i0 + per, zn);
-  unsigned long long keep_ini = 0, keep_min = 0;
+  // Non-max suppression at both thresholds.  keep at t  <=>  m > t  and  m - 1 > max over the 8 neighbours of
+  // (q > t ? q - 1 : 0); that map is monotone in q, so only the largest neighbour matters.
   const int t_ini = p.ini_th, t_min = p.min_th;
-  for (int i = i0; i < i1; ++i)
+  for (int k = tid; k < ncand; k += kFastThreads)
   {
-    const int zy = i / zw, zx = i - zy * zw;
+    const int i = cand_at(k);
+    const int zy = i >> 6, zx = i & (kZoneMax - 1);
     const uint8_t *mp = &s_map[(zy + 1) * kMapPitch + zx + 1];
     const int m = mp[0];
     if (m == 0) continue;
-    int nb[8] = {mp[-1], mp[1], mp[-kMapPitch - 1], mp[-kMapPitch], mp[-kMapPitch + 1], mp[kMapPitch - 1], mp[kMapPitch], mp[kMapPitch + 1]};
-    bool k_ini = m > t_ini, k_min = m > t_min;
+    const int q = max(max(max((int)mp[-1], (int)mp[1]), max((int)mp[-kMapPitch - 1], (int)mp[-kMapPitch])),
+                      max(max((int)mp[-kMapPitch + 1], (int)mp[kMapPitch - 1]), max((int)mp[kMapPitch], (int)mp[kMapPitch + 1])));
     const int s = m - 1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-    {
-      const int q = nb[j];
-      k_ini = k_ini && (s > (q > t_ini ? q - 1 : 0));
-      k_min = k_min && (s > (q > t_min ? q - 1 : 0));
-    }
-    if (k_ini) keep_ini |= 1ull << (i - i0);
-    if (k_min) keep_min |= 1ull << (i - i0);
+    if (m > t_ini && s > (q > t_ini ? q - 1 : 0)) atomicOr(&s_keep_ini[zy], 1ull << zx);
+    if (m > t_min && s > (q > t_min ? q - 1 : 0)) atomicOr(&s_keep_min[zy], 1ull << zx);
   }
-  const int any_ini = __syncthreads_or(keep_ini != 0ull);
-  const unsigned long long keep = any_ini ? keep_ini : keep_min; // fallback iff the post-NMS list is empty (:366-367)
-  const int mine = __popcll(keep);
+  __syncthreads();
+  const unsigned long long row_ini = tid < zh ? s_keep_ini[tid] : 0ull;
+  const int any_ini = __syncthreads_or(row_ini != 0ull);
+  // fallback to minThFAST iff the post-NMS list at iniThFAST is empty (:366-367)
+  unsigned long long keep = any_ini ? row_ini : (tid < zh ? s_keep_min[tid] : 0ull);
   int total;
-  int off = block_exclusive_scan<kFastThreads>(mine, total, s_warp);
+  int off = block_exclusive_scan<kFastThreads>(__popcll(keep), total, s_warp); // thread <-> zone row: row-major output order
   uint32_t *slot = p.cell_list + (size_t)img * p.cell_entries + c.slot;
-  for (int i = i0; i < i1; ++i)
+  const uint32_t y = (uint32_t)(c.y0 - kEdge + 3 + tid); // ROI coordinates (:368-372)
+  while (keep)
   {
-    if (!((keep >> (i - i0)) & 1ull)) continue;
-    const int zy = i / zw, zx = i - zy * zw;
-    const uint32_t score = (uint32_t)s_map[(zy + 1) * kMapPitch + zx + 1] - 1u;
-    const uint32_t x = (uint32_t)(c.x0 - kEdge + 3 + zx), y = (uint32_t)(c.y0 - kEdge + 3 + zy); // ROI coordinates (:368-372)
+    const int zx = __ffsll((long long)keep) - 1;
+    keep &= keep - 1;
+    const uint32_t score = (uint32_t)s_map[(tid + 1) * kMapPitch + zx + 1] - 1u;
+    const uint32_t x = (uint32_t)(c.x0 - kEdge + 3 + zx);
     if (off < c.cap) slot[off] = x | (y << 12) | (score << 24);
     ++off;
   }
