@@ -3,6 +3,7 @@
 // The per-config tables restate ORBExtractor::initPyramid's bookkeeping (src/ORBExtractor.cc:283-317) and the FAST cell
 // grid of extractFast (:334-362) once per context -- the reference recomputes them per frame and keeps part of them in
 // process-wide statics (:511-524); here nothing is static, so contexts with different configurations can coexist.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -38,6 +39,12 @@ struct orbx_ctx
   uint8_t *d_depth_in = nullptr; // [max_batch][H][W] float/uint16 (sized for float)
   int last_images = 0;          // images processed by the most recent call (for orbx_get_pyramid)
   int last_stereo = 0;
+  // host-batch pipeline: chunks of frames round-robin over kPipe streams so that H2D, kernels and D2H overlap
+  static constexpr int kPipe = 4;
+  static constexpr int kChunk = 8; // frames per chunk
+  cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr;
+  cudaEvent_t join_ev[kPipe] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace
@@ -329,6 +336,49 @@ int alloc_buffers(orbx_ctx *c)
   return ORBX_OK;
 }
 
+// Params whose per-image buffers start at image `img0` (and per-frame buffers at frame `frame0`)
+Params params_at(const orbx_ctx *c, int img0, int frame0)
+{
+  Params p = c->p;
+  const size_t N = (size_t)c->cfg.n_features, i = (size_t)img0, f = (size_t)frame0;
+  p.pyr += i * p.pyr_img_stride;
+  p.blur += i * p.pyr_img_stride;
+  p.cell_list += i * p.cell_entries;
+  p.cell_cnt += i * (size_t)p.n_cells;
+  p.sel += i * (size_t)p.sel_entries;
+  p.sel_cnt += i * (size_t)p.n_levels;
+  p.qt_scratch += i * p.qt_scratch_img_stride;
+  p.kps += i * N;
+  p.kps_und += i * N;
+  p.desc += i * N * 32;
+  p.n_kps += i;
+  p.rtab += i * N;
+  p.u_right += f * N;
+  p.depth += f * N;
+  p.n_matches += f;
+  return p;
+}
+
+// the five kernels of a stereo batch for frames [frame0, frame0 + nf) on stream s
+int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint8_t *d_left, const uint8_t *d_right, size_t stride, size_t frame_stride)
+{
+  Params p = params_at(c, 2 * frame0, frame0);
+  p.stereo = 1;
+  p.in_left = d_left + (size_t)frame0 * frame_stride;
+  p.in_right = d_right + (size_t)frame0 * frame_stride;
+  p.in_stride = stride;
+  p.in_frame_stride = frame_stride;
+  ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)nf * sizeof(int), s));
+  launch_pyramid(p, 2 * nf, s);
+  launch_fast(p, 2 * nf, s);
+  launch_quadtree(p, 2 * nf, c->qt_smem, s);
+  launch_orient_brief(p, 2 * nf, s);
+  launch_stereo(p, nf, s);
+  c->launches += 5;
+  ORBX_CUDA(c, cudaGetLastError());
+  return ORBX_OK;
+}
+
 // ORBExtractor ctor + extract for n_images device-resident images
 int run_extract(orbx_ctx *c, const Params &p, int n_images)
 {
@@ -472,6 +522,11 @@ extern "C"
         break;
       }
       c->stream = c->own_stream;
+      for (auto &ps : c->pipe)
+        if (cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking) != cudaSuccess) rc = ORBX_ERR_CUDA;
+      if (cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) != cudaSuccess) rc = ORBX_ERR_CUDA;
+      for (auto &je : c->join_ev)
+        if (cudaEventCreateWithFlags(&je, cudaEventDisableTiming) != cudaSuccess) rc = ORBX_ERR_CUDA;
     } while (0);
     if (rc != ORBX_OK)
     {
@@ -492,6 +547,15 @@ extern "C"
       cudaStreamSynchronize(c->own_stream);
       cudaStreamDestroy(c->own_stream);
     }
+    for (auto &ps : c->pipe)
+      if (ps)
+      {
+        cudaStreamSynchronize(ps);
+        cudaStreamDestroy(ps);
+      }
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    for (auto &je : c->join_ev)
+      if (je) cudaEventDestroy(je);
     for (void *q : c->allocs) cudaFree(q);
     delete c;
   }
@@ -563,18 +627,29 @@ extern "C"
     if (!c || !d_left || !d_right || n_frames < 1) return ORBX_ERR_INVALID_ARG;
     if (n_frames > c->cfg.max_batch) return fail(c, ORBX_ERR_CAPACITY, "n_frames > max_batch");
     ORBX_CUDA(c, cudaSetDevice(c->device));
-    Params p = c->p;
-    p.stereo = 1;
-    p.in_left = d_left;
-    p.in_right = d_right;
-    p.in_stride = stride;
-    p.in_frame_stride = frame_stride;
-    int rc = run_extract(c, p, 2 * n_frames);
-    if (rc) return rc;
-    ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)n_frames * sizeof(int), c->stream));
-    launch_stereo(p, n_frames, c->stream);
-    c->launches += 1;
-    ORBX_CUDA(c, cudaGetLastError());
+    if (n_frames <= orbx_ctx::kChunk)
+    {
+      int rc = run_stereo_range(c, c->stream, 0, n_frames, d_left, d_right, stride, frame_stride);
+      if (rc) return rc;
+    }
+    else
+    {
+      // Fork the batch into chunks on the pipeline streams and join back into the caller's stream: the latency-bound
+      // quadtree launches of one chunk then overlap the issue-bound FAST / pyramid launches of the others.
+      ORBX_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
+      for (auto &ps : c->pipe) ORBX_CUDA(c, cudaStreamWaitEvent(ps, c->fork_ev, 0));
+      int k = 0;
+      for (int f0 = 0; f0 < n_frames; f0 += orbx_ctx::kChunk, ++k)
+      {
+        int rc = run_stereo_range(c, c->pipe[k % orbx_ctx::kPipe], f0, std::min(orbx_ctx::kChunk, n_frames - f0), d_left, d_right, stride, frame_stride);
+        if (rc) return rc;
+      }
+      for (int i = 0; i < orbx_ctx::kPipe; ++i)
+      {
+        ORBX_CUDA(c, cudaEventRecord(c->join_ev[i], c->pipe[i]));
+        ORBX_CUDA(c, cudaStreamWaitEvent(c->stream, c->join_ev[i], 0));
+      }
+    }
     c->last_images = 2 * n_frames;
     c->last_stereo = 1;
     fill_results(c, 2 * n_frames, n_frames, out);
@@ -662,39 +737,54 @@ extern "C"
     const size_t W = (size_t)c->cfg.width, H = (size_t)c->cfg.height, N = (size_t)c->cfg.n_features;
     const size_t fs = c->in_pitch * H;
     uint8_t *dl = c->d_in, *dr = c->d_in + (size_t)c->cfg.max_batch * fs;
-    if (stride == c->in_pitch && frame_stride == fs)
-    {
-      ORBX_CUDA(c, cudaMemcpyAsync(dl, left, fs * n_frames, cudaMemcpyHostToDevice, c->stream));
-      ORBX_CUDA(c, cudaMemcpyAsync(dr, right, fs * n_frames, cudaMemcpyHostToDevice, c->stream));
-    }
-    else if (frame_stride == stride * H)
-    { // frames are densely stacked rows: one 2-D copy per side
-      ORBX_CUDA(c, cudaMemcpy2DAsync(dl, c->in_pitch, left, stride, W, H * n_frames, cudaMemcpyHostToDevice, c->stream));
-      ORBX_CUDA(c, cudaMemcpy2DAsync(dr, c->in_pitch, right, stride, W, H * n_frames, cudaMemcpyHostToDevice, c->stream));
-    }
-    else
-    {
-      for (int f = 0; f < n_frames; ++f)
-      {
-        ORBX_CUDA(c, cudaMemcpy2DAsync(dl + f * fs, c->in_pitch, left + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, c->stream));
-        ORBX_CUDA(c, cudaMemcpy2DAsync(dr + f * fs, c->in_pitch, right + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, c->stream));
-      }
-    }
-    int rc = orbx_stereo_batch_device(c, n_frames, dl, dr, c->in_pitch, fs, nullptr);
-    if (rc) return rc;
     const Params &p = c->p;
-    // results: left = even images, right = odd images -> one strided 2-D copy per array
     const size_t kb = N * sizeof(orbx_keypoint), db = N * 32;
-    if (kps_left) ORBX_CUDA(c, cudaMemcpy2DAsync(kps_left, kb, p.kps_und, 2 * kb, kb, n_frames, cudaMemcpyDeviceToHost, c->stream));
-    if (kps_right) ORBX_CUDA(c, cudaMemcpy2DAsync(kps_right, kb, p.kps + N, 2 * kb, kb, n_frames, cudaMemcpyDeviceToHost, c->stream));
-    if (desc_left) ORBX_CUDA(c, cudaMemcpy2DAsync(desc_left, db, p.desc, 2 * db, db, n_frames, cudaMemcpyDeviceToHost, c->stream));
-    if (desc_right) ORBX_CUDA(c, cudaMemcpy2DAsync(desc_right, db, p.desc + db, 2 * db, db, n_frames, cudaMemcpyDeviceToHost, c->stream));
-    if (n_left) ORBX_CUDA(c, cudaMemcpy2DAsync(n_left, 4, p.n_kps, 8, 4, n_frames, cudaMemcpyDeviceToHost, c->stream));
-    if (n_right) ORBX_CUDA(c, cudaMemcpy2DAsync(n_right, 4, p.n_kps + 1, 8, 4, n_frames, cudaMemcpyDeviceToHost, c->stream));
-    if (u_right) ORBX_CUDA(c, cudaMemcpyAsync(u_right, p.u_right, N * 8 * n_frames, cudaMemcpyDeviceToHost, c->stream));
-    if (depth) ORBX_CUDA(c, cudaMemcpyAsync(depth, p.depth, N * 8 * n_frames, cudaMemcpyDeviceToHost, c->stream));
-    if (n_matches) ORBX_CUDA(c, cudaMemcpyAsync(n_matches, p.n_matches, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
-    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    // Chunks of kChunk frames round-robin over the pipeline streams: the H2D copy of chunk k+1 and the D2H copy of chunk
+    // k-1 overlap the kernels of chunk k.  A single chunk runs on the context's stream (single-frame latency path).
+    const bool piped = n_frames > orbx_ctx::kChunk;
+    if (piped)
+    {
+      ORBX_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
+      for (auto &ps : c->pipe) ORBX_CUDA(c, cudaStreamWaitEvent(ps, c->fork_ev, 0));
+    }
+    int k = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += orbx_ctx::kChunk, ++k)
+    {
+      const int nf = std::min(orbx_ctx::kChunk, n_frames - f0);
+      cudaStream_t s = piped ? c->pipe[k % orbx_ctx::kPipe] : c->stream;
+      if (frame_stride == stride * H)
+      { // frames are densely stacked rows: one 2-D copy per side
+        ORBX_CUDA(c, cudaMemcpy2DAsync(dl + f0 * fs, c->in_pitch, left + f0 * frame_stride, stride, W, H * nf, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(c, cudaMemcpy2DAsync(dr + f0 * fs, c->in_pitch, right + f0 * frame_stride, stride, W, H * nf, cudaMemcpyHostToDevice, s));
+      }
+      else
+      {
+        for (int f = f0; f < f0 + nf; ++f)
+        {
+          ORBX_CUDA(c, cudaMemcpy2DAsync(dl + f * fs, c->in_pitch, left + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, s));
+          ORBX_CUDA(c, cudaMemcpy2DAsync(dr + f * fs, c->in_pitch, right + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, s));
+        }
+      }
+      int rc = run_stereo_range(c, s, f0, nf, dl, dr, c->in_pitch, fs);
+      if (rc) return rc;
+      // results: left = even images, right = odd images -> one strided 2-D copy per array
+      const size_t i0 = 2 * (size_t)f0;
+      if (kps_left) ORBX_CUDA(c, cudaMemcpy2DAsync(kps_left + f0 * N, kb, p.kps_und + i0 * N, 2 * kb, kb, nf, cudaMemcpyDeviceToHost, s));
+      if (kps_right) ORBX_CUDA(c, cudaMemcpy2DAsync(kps_right + f0 * N, kb, p.kps + (i0 + 1) * N, 2 * kb, kb, nf, cudaMemcpyDeviceToHost, s));
+      if (desc_left) ORBX_CUDA(c, cudaMemcpy2DAsync(desc_left + f0 * db, db, p.desc + i0 * db, 2 * db, db, nf, cudaMemcpyDeviceToHost, s));
+      if (desc_right) ORBX_CUDA(c, cudaMemcpy2DAsync(desc_right + f0 * db, db, p.desc + (i0 + 1) * db, 2 * db, db, nf, cudaMemcpyDeviceToHost, s));
+      if (n_left) ORBX_CUDA(c, cudaMemcpy2DAsync(n_left + f0, 4, p.n_kps + i0, 8, 4, nf, cudaMemcpyDeviceToHost, s));
+      if (n_right) ORBX_CUDA(c, cudaMemcpy2DAsync(n_right + f0, 4, p.n_kps + i0 + 1, 8, 4, nf, cudaMemcpyDeviceToHost, s));
+      if (u_right) ORBX_CUDA(c, cudaMemcpyAsync(u_right + f0 * N, p.u_right + f0 * N, N * 8 * nf, cudaMemcpyDeviceToHost, s));
+      if (depth) ORBX_CUDA(c, cudaMemcpyAsync(depth + f0 * N, p.depth + f0 * N, N * 8 * nf, cudaMemcpyDeviceToHost, s));
+      if (n_matches) ORBX_CUDA(c, cudaMemcpyAsync(n_matches + f0, p.n_matches + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s));
+    }
+    if (piped)
+      for (auto &ps : c->pipe) ORBX_CUDA(c, cudaStreamSynchronize(ps));
+    else
+      ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->last_images = 2 * n_frames;
+    c->last_stereo = 1;
     return ORBX_OK;
   }
 
