@@ -1,0 +1,327 @@
+// orb_slam2_shim.hpp -- header-only C++17 mirror of the reference's classes on top of the C ABI (include/orbx.h).
+//
+// Same names, argument order and error behaviour as the reference, so that its call sites compile unchanged:
+//   ORBExtractor(image, nFeatures, pyramidLevels, scaleFactor, bfTemFp, maxThreshold, minThreshold)
+//       include/ORB_SLAM2/ORBExtractor.h:107     .extract(keyPoints, descriptors)            :110
+//       .getPyramid() :113     ::getScaledFactors() :116     ::mnLevels / mnBorderSize / mfScaledFactor :158-160
+//   Frame::createStereo(l, r, nFeatures, briefFp, maxThresh, minThresh, pVoc, nLevels, scale)   include/ORB_SLAM2/Frame.h:313
+//   Frame::createRGBD(color, depth, nFeatures, briefFp, maxThresh, minThresh, pVoc, dScale, nLevels, scale)          :325
+//   ORBMatcher::searchByStereo(FramePtr)                                                 include/ORB_SLAM2/ORBMatcher.h:39
+//   Camera statics (include/ORB_SLAM2/Camera.h:23-32), exceptions (include/ORB_SLAM2/Error.h:13-98)
+// It needs only the cv:: value types (cv::Mat, cv::KeyPoint): real OpenCV headers when available, otherwise any header
+// providing them (this image has no C++ OpenCV; the tests compile against oracle/stub/opencv2/opencv.hpp).
+// All compute happens in liborbx.so (CUDA); there is no CPU code path here.
+#pragma once
+
+#include <array>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#if __has_include(<opencv2/core.hpp>)
+#include <opencv2/core.hpp>
+#else
+#include <opencv2/opencv.hpp>
+#endif
+
+#include "../orbx.h"
+
+namespace ORB_SLAM2_ROS2_B200
+{
+
+// ---- include/ORB_SLAM2/Error.h ------------------------------------------------------------------------------------
+class ORBSlam2Error : public std::runtime_error
+{
+public:
+  explicit ORBSlam2Error(const std::string &what) : std::runtime_error(what) {}
+};
+class ImageSizeError : public ORBSlam2Error
+{
+  using ORBSlam2Error::ORBSlam2Error;
+};
+class FileNotOpenError : public ORBSlam2Error
+{
+  using ORBSlam2Error::ORBSlam2Error;
+};
+class DeviceError : public ORBSlam2Error
+{
+  using ORBSlam2Error::ORBSlam2Error;
+};
+
+namespace detail
+{
+inline void check(orbx_ctx *ctx, int rc, const char *what)
+{
+  if (rc == ORBX_OK) return;
+  std::string msg = std::string(what) + ": " + orbx_status_string(rc);
+  if (ctx && orbx_last_error(ctx)[0]) msg += std::string(" (") + orbx_last_error(ctx) + ")";
+  if (rc == ORBX_ERR_IMAGE_SIZE) throw ImageSizeError(msg);
+  if (rc == ORBX_ERR_FILE_NOT_OPEN) throw FileNotOpenError(msg);
+  if (rc == ORBX_ERR_CUDA || rc == ORBX_ERR_NO_DEVICE) throw DeviceError(msg);
+  throw ORBSlam2Error(msg);
+}
+} // namespace detail
+
+// ---- include/ORB_SLAM2/Camera.h (set once, like System::setSetting does, src/System.cc:27-73) ---------------------
+struct Camera
+{
+  static inline float mfBf = 0, mfBl = 0, mfFx = 0, mfFy = 0, mfCx = 0, mfCy = 0;
+  static inline std::array<float, 5> mDistCoeff = {0, 0, 0, 0, 0}; // k1 k2 p1 p2 k3
+  static void set(float fx, float fy, float cx, float cy, float bl, const std::array<float, 5> &dist = {0, 0, 0, 0, 0})
+  {
+    mfFx = fx;
+    mfFy = fy;
+    mfCx = cx;
+    mfCy = cy;
+    mfBl = bl;
+    mfBf = mfFx * mfBl;
+    mDistCoeff = dist;
+  }
+};
+
+// ---- one CUDA context per distinct configuration (the reference keeps these tables in process-wide statics) ----
+namespace detail
+{
+struct CtxKey
+{
+  int w, h, nFeatures, nLevels, iniTh, minTh;
+  float scale, fx, fy, cx, cy, bf, dScale;
+  std::array<float, 5> dist;
+  std::string tmpl;
+  auto tie() const { return std::tie(w, h, nFeatures, nLevels, iniTh, minTh, scale, fx, fy, cx, cy, bf, dScale, dist, tmpl); }
+  bool operator<(const CtxKey &o) const { return tie() < o.tie(); }
+};
+
+struct CtxDeleter
+{
+  void operator()(orbx_ctx *c) const { orbx_destroy(c); }
+};
+
+inline std::shared_ptr<orbx_ctx> context_for(int w, int h, int nFeatures, int nLevels, float scale, const std::string &tmpl, int iniTh, int minTh, float dScale)
+{
+  static std::mutex mtx;
+  static std::map<CtxKey, std::shared_ptr<orbx_ctx>> cache;
+  CtxKey key{w, h, nFeatures, nLevels, iniTh, minTh, scale, Camera::mfFx, Camera::mfFy, Camera::mfCx, Camera::mfCy, Camera::mfBf, dScale, Camera::mDistCoeff, tmpl};
+  std::lock_guard<std::mutex> lock(mtx);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  std::vector<float> pattern(1024);
+  check(nullptr, orbx_load_brief_template(tmpl.c_str(), pattern.data()), "BRIEF template"); // FileNotOpenError (:247-250)
+  orbx_config cfg;
+  orbx_default_config(&cfg);
+  cfg.width = w;
+  cfg.height = h;
+  cfg.n_features = nFeatures;
+  cfg.n_levels = nLevels;
+  cfg.scale_factor = scale;
+  cfg.ini_th_fast = iniTh;
+  cfg.min_th_fast = minTh;
+  cfg.fx = Camera::mfFx;
+  cfg.fy = Camera::mfFy;
+  cfg.cx = Camera::mfCx;
+  cfg.cy = Camera::mfCy;
+  cfg.bf = Camera::mfBf;
+  for (int i = 0; i < 5; ++i) cfg.dist[i] = Camera::mDistCoeff[i];
+  cfg.depth_scale = dScale;
+  cfg.max_batch = 1;
+  cfg.pattern = pattern.data();
+  orbx_ctx *raw = nullptr;
+  check(nullptr, orbx_create(&cfg, &raw), "orbx_create"); // ImageSizeError (:310-314)
+  std::shared_ptr<orbx_ctx> sp(raw, CtxDeleter());
+  cache[key] = sp;
+  return sp;
+}
+
+inline void to_cv(const std::vector<orbx_keypoint> &src, int n, std::vector<cv::KeyPoint> &dst)
+{
+  static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "orbx_keypoint mirrors cv::KeyPoint");
+  dst.resize((size_t)n);
+  if (n) std::memcpy((void *)dst.data(), src.data(), (size_t)n * sizeof(orbx_keypoint));
+}
+
+// n rows of one contiguous N x 32 block, each a 1x32 CV_8U header sharing the block (vector<cv::Mat> for DBoW3)
+inline void to_cv(const cv::Mat &block, int n, std::vector<cv::Mat> &dst)
+{
+  dst.clear();
+  dst.reserve((size_t)n);
+  for (int i = 0; i < n; ++i) dst.push_back(block.rowRange(i, i + 1));
+}
+
+inline std::vector<cv::Mat> fetch_pyramid(orbx_ctx *ctx, int side)
+{
+  std::vector<cv::Mat> pyr;
+  const int nl = orbx_num_levels(ctx);
+  for (int l = 0; l < nl; ++l)
+  {
+    int32_t w = 0, h = 0;
+    check(ctx, orbx_level_info(ctx, l, &w, &h, nullptr, nullptr), "orbx_level_info");
+    cv::Mat m(h, w, CV_8U);
+    check(ctx, orbx_get_pyramid(ctx, side, l, 0, m.data, (size_t)m.step), "orbx_get_pyramid");
+    pyr.push_back(m);
+  }
+  return pyr;
+}
+} // namespace detail
+
+// ---- include/ORB_SLAM2/ORBExtractor.h:99-161 ------------------------------------------------------------------------
+class ORBExtractor
+{
+public:
+  typedef std::shared_ptr<ORBExtractor> SharedPtr;
+
+  ORBExtractor(const cv::Mat &image, int nFeatures, int pyramidLevels, float scaleFactor, const std::string &bfTemFp, int maxThreshold, int minThreshold)
+      : mImage(image), mnFeats(nFeatures)
+  {
+    mCtx = detail::context_for(image.cols, image.rows, nFeatures, pyramidLevels, scaleFactor, bfTemFp, maxThreshold, minThreshold, 1.f);
+    // the reference keeps these as process-wide statics initialised by the first constructor (src/ORBExtractor.cc:283-302)
+    mnLevels = pyramidLevels;
+    mfScaledFactor = scaleFactor;
+    scaledFactors().resize((size_t)pyramidLevels);
+    for (int l = 0; l < pyramidLevels; ++l) detail::check(mCtx.get(), orbx_level_info(mCtx.get(), l, nullptr, nullptr, &scaledFactors()[(size_t)l], nullptr), "orbx_level_info");
+  }
+
+  void extract(std::vector<cv::KeyPoint> &keyPoints, std::vector<cv::Mat> &descriptors)
+  {
+    std::vector<orbx_keypoint> k((size_t)mnFeats);
+    mDescBlock = cv::Mat(mnFeats, 32, CV_8U);
+    int32_t n = 0;
+    detail::check(mCtx.get(), orbx_extract(mCtx.get(), mImage.data, (size_t)mImage.step, k.data(), mDescBlock.data, &n), "orbx_extract");
+    detail::to_cv(k, n, keyPoints);
+    detail::to_cv(mDescBlock, n, descriptors);
+    mvPyramids = detail::fetch_pyramid(mCtx.get(), 0);
+  }
+
+  const std::vector<cv::Mat> &getPyramid() const { return mvPyramids; }
+  static const std::vector<float> &getScaledFactors() { return scaledFactors(); }
+
+  static inline int mnLevels = 0;
+  static inline int mnBorderSize = 19;
+  static inline float mfScaledFactor = 0.f;
+
+private:
+  static std::vector<float> &scaledFactors()
+  {
+    static std::vector<float> v;
+    return v;
+  }
+  cv::Mat mImage;
+  int mnFeats;
+  std::shared_ptr<orbx_ctx> mCtx;
+  cv::Mat mDescBlock;
+  std::vector<cv::Mat> mvPyramids;
+};
+
+class ORBMatcher;
+
+// ---- the hot-path part of include/ORB_SLAM2/Frame.h:303-371 --------------------------------------------------------
+class Frame
+{
+  friend class ORBMatcher;
+
+public:
+  typedef std::shared_ptr<Frame> SharedPtr;
+
+  static SharedPtr createStereo(cv::Mat leftImg, cv::Mat rightImg, int nFeatures, const std::string &briefFp, int maxThresh, int minThresh, void *pVoc,
+                                int nLevels, float scale);
+  static SharedPtr createRGBD(cv::Mat colorImg, cv::Mat depthImg, int nFeatures, const std::string &briefF, int maxThresh, int minThresh, void *pVoc,
+                              float dScale, int nLevels, float scale)
+  {
+    (void)pVoc;
+    SharedPtr f(new Frame());
+    f->mLeftIm = colorImg;
+    f->mCtx = detail::context_for(colorImg.cols, colorImg.rows, nFeatures, nLevels, scale, briefF, maxThresh, minThresh, dScale);
+    const int dtype = depthImg.type() == CV_32F ? ORBX_DEPTH_F32 : ORBX_DEPTH_U16;
+    std::vector<orbx_keypoint> kraw((size_t)nFeatures), kund((size_t)nFeatures);
+    f->mDescLeft = cv::Mat(nFeatures, 32, CV_8U);
+    std::vector<double> ur((size_t)nFeatures), dp((size_t)nFeatures);
+    int32_t n = 0;
+    detail::check(f->mCtx.get(),
+                  orbx_rgbd_frame(f->mCtx.get(), colorImg.data, (size_t)colorImg.step, depthImg.data, (size_t)depthImg.step, dtype, kraw.data(), kund.data(),
+                                  f->mDescLeft.data, &n, ur.data(), dp.data()),
+                  "orbx_rgbd_frame");
+    detail::to_cv(kund, n, f->mvFeatsLeft);
+    detail::to_cv(f->mDescLeft, n, f->mvLeftDescriptor);
+    f->mvFeatsRightU.assign(ur.begin(), ur.begin() + n);
+    f->mvDepths.assign(dp.begin(), dp.begin() + n);
+    f->mnN = 0;
+    for (double d : f->mvDepths) f->mnN += d > 0;
+    return f;
+  }
+
+  const std::vector<cv::KeyPoint> &getLeftKeyPoints() const { return mvFeatsLeft; }
+  const std::vector<cv::KeyPoint> &getRightKeyPoints() const { return mvFeatsRight; }
+  const std::vector<cv::Mat> &getLeftDescriptor() const { return mvLeftDescriptor; }
+  const std::vector<cv::Mat> &getRightDescriptor() const { return mRightDescriptor; }
+  const std::vector<cv::Mat> &getDescriptor() const { return mvLeftDescriptor; }
+  const std::vector<double> &getDepth() const { return mvDepths; }
+  const std::vector<double> &getRightU() const { return mvFeatsRightU; }
+  const cv::Mat &getLeftImage() const { return mLeftIm; }
+  const cv::Mat &getRightImage() const { return mRightIm; }
+  std::vector<cv::Mat> getLeftPyramid() const { return detail::fetch_pyramid(mCtx.get(), 0); }
+  std::vector<cv::Mat> getRightPyramid() const { return detail::fetch_pyramid(mCtx.get(), 1); }
+  int getN() const { return mnN; }
+
+private:
+  Frame() = default;
+  std::vector<cv::KeyPoint> mvFeatsLeft, mvFeatsRight;
+  std::vector<cv::Mat> mvLeftDescriptor, mRightDescriptor;
+  std::vector<double> mvDepths, mvFeatsRightU;
+  std::vector<double> mStereoU, mStereoDepth; // computed with the frame, published by ORBMatcher::searchByStereo
+  int mStereoMatches = 0;
+  int mnN = 0;
+  cv::Mat mLeftIm, mRightIm, mDescLeft, mDescRight;
+  std::shared_ptr<orbx_ctx> mCtx;
+};
+
+// ---- the stereo entry of include/ORB_SLAM2/ORBMatcher.h:39 ---------------------------------------------------------
+class ORBMatcher
+{
+public:
+  typedef std::shared_ptr<ORBMatcher> SharedPtr;
+  explicit ORBMatcher(float ratio = 0.6f, bool checkOri = true) { (void)ratio, (void)checkOri; }
+  // fills mvFeatsRightU / mvDepths (-1 = no match) and returns the match count, like src/ORBMatcher.cc:18-81.  The GPU
+  // computed them together with the features (one launch sequence per frame); this call publishes them.
+  int searchByStereo(Frame::SharedPtr pFrame)
+  {
+    pFrame->mvFeatsRightU = pFrame->mStereoU;
+    pFrame->mvDepths = pFrame->mStereoDepth;
+    return pFrame->mStereoMatches;
+  }
+};
+
+inline Frame::SharedPtr Frame::createStereo(cv::Mat leftImg, cv::Mat rightImg, int nFeatures, const std::string &briefFp, int maxThresh, int minThresh,
+                                            void *pVoc, int nLevels, float scale)
+{
+  (void)pVoc;
+  SharedPtr f(new Frame());
+  f->mLeftIm = leftImg;
+  f->mRightIm = rightImg;
+  f->mCtx = detail::context_for(leftImg.cols, leftImg.rows, nFeatures, nLevels, scale, briefFp, maxThresh, minThresh, 1.f);
+  std::vector<orbx_keypoint> kl((size_t)nFeatures), kr((size_t)nFeatures);
+  f->mDescLeft = cv::Mat(nFeatures, 32, CV_8U);
+  f->mDescRight = cv::Mat(nFeatures, 32, CV_8U);
+  f->mStereoU.resize((size_t)nFeatures);
+  f->mStereoDepth.resize((size_t)nFeatures);
+  int32_t nl = 0, nr = 0, nm = 0;
+  detail::check(f->mCtx.get(),
+                orbx_stereo_frame(f->mCtx.get(), leftImg.data, (size_t)leftImg.step, rightImg.data, (size_t)rightImg.step, kl.data(), f->mDescLeft.data, &nl,
+                                  kr.data(), f->mDescRight.data, &nr, f->mStereoU.data(), f->mStereoDepth.data(), &nm),
+                "orbx_stereo_frame");
+  detail::to_cv(kl, nl, f->mvFeatsLeft);
+  detail::to_cv(kr, nr, f->mvFeatsRight);
+  detail::to_cv(f->mDescLeft, nl, f->mvLeftDescriptor);
+  detail::to_cv(f->mDescRight, nr, f->mRightDescriptor);
+  f->mStereoU.resize((size_t)nl);
+  f->mStereoDepth.resize((size_t)nl);
+  f->mStereoMatches = nm;
+  ORBMatcher::SharedPtr mpMatcher = std::make_shared<ORBMatcher>(); // Frame.h:317-319
+  f->mnN = mpMatcher->searchByStereo(f);
+  return f;
+}
+
+} // namespace ORB_SLAM2_ROS2_B200

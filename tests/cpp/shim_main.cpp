@@ -1,0 +1,103 @@
+// Drives the C++ shim exactly like the reference's call sites do (Frame::createStereo / ORBExtractor / createRGBD) on raw
+// image files written by tests/test_cpp_shim.py, and dumps the results for comparison with the oracle.
+//   shim_main stereo <w> <h> <nFeatures> <nLevels> <scale> <template> <left.raw> <right.raw> <out.bin>
+//   shim_main rgbd   <w> <h> <nFeatures> <nLevels> <scale> <template> <gray.raw> <depth_u16.raw> <out.bin> <dScale>
+//   shim_main errors <template>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include <orbx/orb_slam2_shim.hpp>
+
+using namespace ORB_SLAM2_ROS2_B200;
+
+static cv::Mat read_raw(const char *path, int w, int h, int type)
+{
+  cv::Mat m(h, w, type);
+  std::ifstream f(path, std::ios::binary);
+  f.read((char *)m.data, (std::streamsize)((size_t)w * h * m.elemSize()));
+  if (!f) throw std::runtime_error(std::string("cannot read ") + path);
+  return m;
+}
+
+template <typename T> static void put(std::ofstream &o, const T &v) { o.write((const char *)&v, sizeof(T)); }
+
+static void dump(std::ofstream &o, const std::vector<cv::KeyPoint> &k, const std::vector<cv::Mat> &d)
+{
+  put(o, (int32_t)k.size());
+  for (auto &kp : k) o.write((const char *)&kp, sizeof(cv::KeyPoint));
+  for (auto &m : d) o.write((const char *)m.data, 32);
+}
+
+int main(int argc, char **argv)
+{
+  try
+  {
+    std::string mode = argv[1];
+    if (mode == "errors")
+    {
+      int ok = 0;
+      cv::Mat img(240, 320, CV_8U);
+      try
+      {
+        ORBExtractor ex(img, 500, 4, 1.2f, "/nonexistent/brief_template.txt", 20, 7);
+      }
+      catch (const FileNotOpenError &)
+      {
+        ++ok;
+      }
+      cv::Mat tiny(60, 100, CV_8U);
+      try
+      {
+        ORBExtractor ex(tiny, 500, 8, 1.2f, argv[2], 20, 7);
+      }
+      catch (const ImageSizeError &)
+      {
+        ++ok;
+      }
+      std::printf("errors ok=%d\n", ok);
+      return ok == 2 ? 0 : 1;
+    }
+    int w = atoi(argv[2]), h = atoi(argv[3]), nf = atoi(argv[4]), nl = atoi(argv[5]);
+    float scale = (float)atof(argv[6]);
+    std::string tmpl = argv[7];
+    std::ofstream out(argv[10], std::ios::binary);
+    if (mode == "stereo")
+    {
+      Camera::set(718.856f, 718.856f, 607.1928f, 185.2157f, 0.537166f);
+      cv::Mat l = read_raw(argv[8], w, h, CV_8U), r = read_raw(argv[9], w, h, CV_8U);
+      // the extractor on its own, then the frame factory -- as Tracking::grabFrame would (src/Tracking.cc:82-88)
+      ORBExtractor ex(l, nf, nl, scale, tmpl, 20, 7);
+      std::vector<cv::KeyPoint> k;
+      std::vector<cv::Mat> d;
+      ex.extract(k, d);
+      dump(out, k, d);
+      put(out, (int32_t)ex.getPyramid().size());
+      put(out, (int32_t)ex.getPyramid().back().cols);
+      put(out, ORBExtractor::getScaledFactors().back());
+      Frame::SharedPtr f = Frame::createStereo(l, r, nf, tmpl, 20, 7, nullptr, nl, scale);
+      dump(out, f->getLeftKeyPoints(), f->getLeftDescriptor());
+      dump(out, f->getRightKeyPoints(), f->getRightDescriptor());
+      put(out, (int32_t)f->getN());
+      for (double v : f->getRightU()) put(out, v);
+      for (double v : f->getDepth()) put(out, v);
+    }
+    else if (mode == "rgbd")
+    {
+      Camera::set(520.908620f, 521.007327f, 325.141442f, 249.701764f, 0.0767889f, {0.231222f, -0.784899f, -0.003257f, -0.000105f, 0.917205f});
+      cv::Mat g = read_raw(argv[8], w, h, CV_8U), dep = read_raw(argv[9], w, h, CV_16U);
+      Frame::SharedPtr f = Frame::createRGBD(g, dep, nf, tmpl, 20, 7, nullptr, (float)atof(argv[11]), nl, scale);
+      dump(out, f->getLeftKeyPoints(), f->getLeftDescriptor());
+      put(out, (int32_t)f->getN());
+      for (double v : f->getRightU()) put(out, v);
+      for (double v : f->getDepth()) put(out, v);
+    }
+    return 0;
+  }
+  catch (const std::exception &e)
+  {
+    std::fprintf(stderr, "shim_main: %s\n", e.what());
+    return 2;
+  }
+}
