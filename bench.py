@@ -63,7 +63,7 @@ class ClockSampler:
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -214,11 +214,11 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`) ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # started before the warm-up so that short timed regions still get samples under load
     for i in range(args.warmup):
         device_step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -348,7 +348,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="stereo frames per step (per GPU)")
     ap.add_argument("--pool", type=int, default=256, help="distinct synthetic pairs per GPU")

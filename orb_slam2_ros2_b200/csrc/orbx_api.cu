@@ -230,7 +230,7 @@ int build_tables(orbx_ctx *c)
     L.sel_off = sel_off;
     sel_off += std::max(1, L.quota);
     L.scratch_off = (int)scratch_off;
-    scratch_off += ((size_t)L.list_cap * 17 + 8 + 3) / 4 + 4;
+    scratch_off += (size_t)L.list_cap * 3 + ((size_t)L.list_cap + 3) / 4 + 8; // corner list + 2 index arrays (u32) + digits (u8)
     scratch_off = (scratch_off + 3) & ~(size_t)3;
     max_quota = std::max(max_quota, L.quota);
     max_ini = std::max(max_ini, L.n_ini);
@@ -253,13 +253,13 @@ int build_tables(orbx_ctx *c)
   p.qt_scratch_img_stride = scratch_off;
   p.qt_node_cap = max_quota + max_ini + 8;
   if (p.qt_node_cap >= 60000) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree node pool");
-  // shared-memory budget of the quadtree kernel: node pool + as many corners as fit in ~100 KB, at most 8192
+  // shared-memory budget of the quadtree kernel: node pool + buckets + big-node list + u16 index arrays for up to 4096 corners
   {
-    int cap = 4096;
     int max_list = 0;
     for (auto &L : c->levels) max_list = std::max(max_list, L.list_cap);
-    cap = std::min(cap, std::max(64, max_list));
-    size_t bytes = quadtree_smem_bytes(cap, p.qt_node_cap);
+    const int cap = std::min(4096, std::max(64, max_list));
+    p.qt_big_cap = max_list / 256 + kMaxStrips + 16;
+    const size_t bytes = quadtree_smem_bytes(cap, p.qt_node_cap, p.qt_big_cap);
     if (bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree shared-memory pool");
     p.qt_smem_cap = cap;
     c->qt_smem = bytes;
@@ -735,10 +735,19 @@ extern "C"
     if (n_frames > c->cfg.max_batch) return fail(c, ORBX_ERR_CAPACITY, "n_frames > max_batch");
     ORBX_CUDA(c, cudaSetDevice(c->device));
     const size_t W = (size_t)c->cfg.width, H = (size_t)c->cfg.height, N = (size_t)c->cfg.n_features;
-    const size_t fs = c->in_pitch * H;
-    uint8_t *dl = c->d_in, *dr = c->d_in + (size_t)c->cfg.max_batch * fs;
+    size_t fs = c->in_pitch * H, dstride = c->in_pitch;
+    uint8_t *dl = c->d_in, *dr = c->d_in + (size_t)c->cfg.max_batch * c->in_pitch * H;
     const Params &p = c->p;
     const size_t kb = N * sizeof(orbx_keypoint), db = N * 32;
+    // Densely stacked rows that fit the staging pitch are copied as ONE linear transfer per side and read on the device
+    // with the caller's stride (the kernels gather bytes, so rows need no alignment); 2-D pitched copies of odd-width
+    // rows run at a fraction of the PCIe rate.
+    const bool linear = frame_stride == stride * H && stride >= W && stride <= c->in_pitch;
+    if (linear)
+    {
+      fs = frame_stride;
+      dstride = stride;
+    }
     // Chunks of kChunk frames round-robin over the pipeline streams: the H2D copy of chunk k+1 and the D2H copy of chunk
     // k-1 overlap the kernels of chunk k.  A single chunk runs on the context's stream (single-frame latency path).
     const bool piped = n_frames > orbx_ctx::kChunk;
@@ -752,10 +761,10 @@ extern "C"
     {
       const int nf = std::min(orbx_ctx::kChunk, n_frames - f0);
       cudaStream_t s = piped ? c->pipe[k % orbx_ctx::kPipe] : c->stream;
-      if (frame_stride == stride * H)
-      { // frames are densely stacked rows: one 2-D copy per side
-        ORBX_CUDA(c, cudaMemcpy2DAsync(dl + f0 * fs, c->in_pitch, left + f0 * frame_stride, stride, W, H * nf, cudaMemcpyHostToDevice, s));
-        ORBX_CUDA(c, cudaMemcpy2DAsync(dr + f0 * fs, c->in_pitch, right + f0 * frame_stride, stride, W, H * nf, cudaMemcpyHostToDevice, s));
+      if (linear)
+      {
+        ORBX_CUDA(c, cudaMemcpyAsync(dl + f0 * fs, left + f0 * frame_stride, fs * nf, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(c, cudaMemcpyAsync(dr + f0 * fs, right + f0 * frame_stride, fs * nf, cudaMemcpyHostToDevice, s));
       }
       else
       {
@@ -765,7 +774,7 @@ extern "C"
           ORBX_CUDA(c, cudaMemcpy2DAsync(dr + f * fs, c->in_pitch, right + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, s));
         }
       }
-      int rc = run_stereo_range(c, s, f0, nf, dl, dr, c->in_pitch, fs);
+      int rc = run_stereo_range(c, s, f0, nf, dl, dr, dstride, fs);
       if (rc) return rc;
       // results: left = even images, right = odd images -> one strided 2-D copy per array
       const size_t i0 = 2 * (size_t)f0;

@@ -104,7 +104,8 @@ struct Params
   uint32_t *qt_scratch;
   size_t qt_scratch_img_stride; // in uint32 entries
   int qt_smem_cap;              // corners that fit the shared-memory path
-  int qt_node_cap;              // node pool capacity (max quota + 8)
+  int qt_node_cap;              // node pool capacity (max quota + max root fan-out + 8)
+  int qt_big_cap;               // capacity of the list of nodes holding >= 256 corners
   // results
   orbx_keypoint *kps, *kps_und;
   uint8_t *desc;
@@ -125,7 +126,7 @@ void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStrea
 void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
 void launch_stereo(const Params &p, int n_frames, cudaStream_t s);
 void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
-size_t quadtree_smem_bytes(int list_cap, int node_cap);
+size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap);
 int quadtree_configure(size_t smem_bytes); // opt in to large dynamic shared memory
 
 } // namespace orbx

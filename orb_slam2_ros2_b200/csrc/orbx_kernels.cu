@@ -462,161 +462,152 @@ void launch_fast(const Params &p, int n_images, cudaStream_t s)
 
 // ------------------------------------------------------------------------------------------------------------------
 // K3: quadtree keypoint distribution.  One CTA per (level, image).
-//   Phase A/B  concatenate the level's cell lists in cell-row-major order (the reference's levelKps order)
+//   Phase A/B  concatenate the level's cell lists in cell-row-major order (the reference's levelKps order) into the
+//              level's corner list (global scratch, L1/L2 resident)
 //   Phase C    warp 0 replays Quadtree::split(): the multimap<count, node, greater> becomes FIFO buckets indexed by
 //              count with a descending cursor (a child never holds more corners than its parent, so the pop key is
-//              monotone); a node's corner list is a range of an index array, split by a stable warp partition.
+//              monotone).  Counts >= 256 (a handful of early nodes) live in a small unsorted list ordered by
+//              (count, insertion sequence); counts < 256 in 256 linked FIFO buckets.  A node's corner list is a range of
+//              an index array, split by a stable 4-way warp partition (ballot + popc) between two ping-pong arrays.
 //   Phase D    nodes2kpoints(): best response per surviving node, ascending index order, shift by the 16-px margin.
+// Index arrays / digits live in shared memory (u16) when the level has at most qt_smem_cap corners, otherwise in the
+// global scratch (u32); node pool, buckets and the big-node list are always in shared memory.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kQtBuckets = 256;  // small buckets hold counts 0..255
+constexpr int kNodeBytes = 4 * 8 + 3 * 4 + 3 * 2 + 2; // r0 r1 c0 c1 | lo cnt seq | next prev free | buf state
+
 struct QtNodePool
 {
   double *r0, *r1, *c0, *c1;
-  uint32_t *lo, *cnt;
+  uint32_t *lo, *cnt, *seq;
   uint16_t *next, *prev, *free_ids;
   uint8_t *buf, *state; // state: 0 dead, 1 live, 2 live but beyond the first `need` entries
 };
 
-size_t quadtree_smem_bytes(int list_cap, int node_cap)
+__host__ __device__ inline size_t qt_align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+// shared memory: node pool | bucket heads+tails | big-node list | (smem path) ia, ib (u16), dig (u8)
+size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap)
 {
-  size_t b = 0;
-  b += (size_t)node_cap * (4 * 8 + 2 * 4 + 3 * 2 + 2); // node pool
-  b = (b + 15) & ~(size_t)15;
-  b += (size_t)list_cap * (3 * 4 + 1) + (size_t)(list_cap + 1) * 2 * 2; // kp, ia, ib, dig, bucket head/tail
-  b = (b + 15) & ~(size_t)15;
+  size_t b = qt_align16((size_t)node_cap * kNodeBytes);
+  b += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
+  b += qt_align16((size_t)big_cap * sizeof(uint16_t));
+  b += qt_align16((size_t)list_cap * (2 * sizeof(uint16_t) + 1));
   return b + 64;
 }
 
-__device__ __forceinline__ void qt_push(const QtNodePool &np, uint16_t *bhead, uint16_t *btail, uint32_t id, uint32_t count)
+struct QtState
 {
-  const uint32_t t = btail[count];
-  np.next[id] = (uint16_t)kNil;
-  np.prev[id] = (uint16_t)t;
-  if (t == kNil)
-    bhead[count] = (uint16_t)id;
-  else
-    np.next[t] = (uint16_t)id;
-  btail[count] = (uint16_t)id;
-  np.state[id] = 1;
+  QtNodePool np;
+  uint16_t *bhead, *btail, *big;
+  int nbig;
+  uint32_t seq_ctr;
+};
+
+__device__ __forceinline__ void qt_push(QtState &q, uint32_t id, uint32_t count, int lane)
+{
+  // warp-uniform call; lane 0 performs the stores
+  if (count >= (uint32_t)kQtBuckets)
+  {
+    if (lane == 0)
+    {
+      q.big[q.nbig] = (uint16_t)id;
+      q.np.seq[id] = q.seq_ctr;
+      q.np.state[id] = 1;
+    }
+    ++q.nbig;
+    ++q.seq_ctr;
+    return;
+  }
+  if (lane == 0)
+  {
+    const uint32_t t = q.btail[count];
+    q.np.next[id] = (uint16_t)kNil;
+    q.np.prev[id] = (uint16_t)t;
+    if (t == kNil)
+      q.bhead[count] = (uint16_t)id;
+    else
+      q.np.next[t] = (uint16_t)id;
+    q.btail[count] = (uint16_t)id;
+    q.np.state[id] = 1;
+  }
 }
 
-__global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
+// position in the big list of the first (want_max) or last (!want_max) node in multimap order (count desc, FIFO)
+__device__ __forceinline__ int qt_big_extreme(const QtState &q, int lane, bool want_max)
 {
-  extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ int s_warp[kQtThreads / 32];
-  __shared__ int s_n, s_live, s_take;
-
-  const int level = blockIdx.x, img = blockIdx.y;
-  const Level &L = p.levels[level];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int need = L.quota;
-  const int ncell = L.n_level_cells;
-  const int *ccnt = p.cell_cnt + (size_t)img * p.n_cells + L.cell_base;
-  const Cell *cells = p.cells + L.cell_base;
-  int *sel_cnt = p.sel_cnt + (size_t)img * p.n_levels + level;
-  uint32_t *sel_out = p.sel + (size_t)img * p.sel_entries + L.sel_off;
-
-  // ---- Phase A: total number of corners on the level
-  int mysum = 0;
-  const int per_c = (ncell + kQtThreads - 1) / kQtThreads;
-  const int c0i = tid * per_c, c1i = min(c0i + per_c, ncell);
-  for (int c = c0i; c < c1i; ++c) mysum += ccnt[c];
-  int n;
-  int mybase = block_exclusive_scan<kQtThreads>(mysum, n, s_warp);
-
-  // carve the working arrays out of shared memory, or out of the global scratch for very dense levels
-  const int node_cap = p.qt_node_cap;
-  QtNodePool np;
+  unsigned long long best = want_max ? 0ull : ~0ull;
+  int best_pos = -1;
+  for (int j = lane; j < q.nbig; j += 32)
   {
-    uint8_t *q = smem;
-    np.r0 = (double *)q;
-    np.r1 = np.r0 + node_cap;
-    np.c0 = np.r1 + node_cap;
-    np.c1 = np.c0 + node_cap;
-    q = (uint8_t *)(np.c1 + node_cap);
-    np.lo = (uint32_t *)q;
-    np.cnt = np.lo + node_cap;
-    q = (uint8_t *)(np.cnt + node_cap);
-    np.next = (uint16_t *)q;
-    np.prev = np.next + node_cap;
-    np.free_ids = np.prev + node_cap;
-    q = (uint8_t *)(np.free_ids + node_cap);
-    np.buf = q;
-    np.state = q + node_cap;
-  }
-  uint32_t *kp, *ia, *ib;
-  uint16_t *bhead, *btail;
-  uint8_t *dig;
-  {
-    size_t pool = (size_t)node_cap * (4 * 8 + 2 * 4 + 3 * 2 + 2);
-    pool = (pool + 15) & ~(size_t)15;
-    uint8_t *q;
-    int cap;
-    if (n <= p.qt_smem_cap)
+    const uint32_t id = q.big[j];
+    const unsigned long long key = ((unsigned long long)q.np.cnt[id] << 32) | (unsigned long long)(0xffffffffu - q.np.seq[id]);
+    if (want_max ? key >= best : key <= best)
     {
-      q = smem + pool;
-      cap = p.qt_smem_cap;
+      best = key;
+      best_pos = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
+    const int op = __shfl_xor_sync(0xffffffffu, best_pos, o);
+    const bool take = op >= 0 && (best_pos < 0 || (want_max ? ok > best : ok < best));
+    if (take)
+    {
+      best = ok;
+      best_pos = op;
+    }
+  }
+  return best_pos; // keys are unique (seq), so all lanes agree
+}
+
+template <typename IdxT>
+__device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const uint32_t *kp, IdxT *ia, IdxT *ib, uint8_t *dig, int n, int need, int node_cap,
+                            int lane, int &out_n_alloc, int &out_take)
+{
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  QtNodePool &np = q.np;
+  int n_alloc = 1, n_free = 0;
+  if (lane == 0)
+  {
+    np.r0[0] = 0.0;
+    np.r1[0] = (double)L.roi_h;
+    np.c0[0] = 0.0;
+    np.c1[0] = (double)L.roi_w;
+    np.lo[0] = 0;
+    np.cnt[0] = (uint32_t)n;
+    np.buf[0] = 0;
+  }
+  qt_push(q, 0, (uint32_t)n, lane);
+  __syncwarp();
+  int live = 1; // == the reference's mnNodes: every live node sits in the multimap
+  int cursor = kQtBuckets - 1;
+  bool root_pending = true;
+  while (live < need && live > 0)
+  {
+    uint32_t id;
+    if (q.nbig > 0)
+    {
+      const int pos = qt_big_extreme(q, lane, true);
+      id = q.big[pos];
+      __syncwarp();
+      if (lane == 0)
+      {
+        q.big[pos] = q.big[q.nbig - 1];
+        np.state[id] = 0;
+      }
+      --q.nbig;
     }
     else
     {
-      q = (uint8_t *)(p.qt_scratch + (size_t)img * p.qt_scratch_img_stride + L.scratch_off);
-      cap = L.list_cap;
-    }
-    kp = (uint32_t *)q;
-    ia = kp + cap;
-    ib = ia + cap;
-    bhead = (uint16_t *)(ib + cap);
-    btail = bhead + (cap + 1);
-    dig = (uint8_t *)(btail + (cap + 1));
-  }
-
-  // ---- Phase B: gather the cell lists (cell-row-major, row-major inside a cell == the reference's detection order)
-  {
-    const uint32_t *cl = p.cell_list + (size_t)img * p.cell_entries;
-    int off = mybase;
-    for (int c = c0i; c < c1i; ++c)
-    {
-      const int k = ccnt[c];
-      const uint32_t *src = cl + cells[c].slot;
-      for (int j = 0; j < k; ++j) kp[off + j] = src[j];
-      off += k;
-    }
-  }
-  for (int i = tid; i < n; i += kQtThreads) ia[i] = (uint32_t)i; // root holds every corner (:26-27)
-  for (int i = tid; i <= n; i += kQtThreads)
-  {
-    bhead[i] = (uint16_t)kNil;
-    btail[i] = (uint16_t)kNil;
-  }
-  for (int i = tid; i < node_cap; i += kQtThreads) np.state[i] = 0;
-  __syncthreads();
-
-  // ---- Phase C: the priority loop, warp 0 only
-  if (wid == 0)
-  {
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int n_alloc = 1, n_free = 0;
-    if (lane == 0)
-    {
-      np.r0[0] = 0.0;
-      np.r1[0] = (double)L.roi_h;
-      np.c0[0] = 0.0;
-      np.c1[0] = (double)L.roi_w;
-      np.lo[0] = 0;
-      np.cnt[0] = (uint32_t)n;
-      np.buf[0] = 0;
-      qt_push(np, bhead, btail, 0, (uint32_t)n);
-    }
-    __syncwarp();
-    int n_nodes = 1, live = 1, cursor = n;
-    bool root_pending = true;
-    while (n_nodes < need && live > 0)
-    {
-      // highest non-empty bucket at or below the cursor
+      // highest non-empty small bucket at or below the cursor
       for (;;)
       {
         const int b = cursor - lane;
-        const bool hit = (b >= 0) && (bhead[b] != (uint16_t)kNil);
+        const bool hit = (b >= 0) && (q.bhead[b] != (uint16_t)kNil);
         const unsigned m = __ballot_sync(FULL, hit);
         if (m)
         {
@@ -636,90 +627,115 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
         live = 0;
         break;
       }
-      const uint32_t id = bhead[cursor];
-      const uint32_t lo = np.lo[id], cnt = np.cnt[id];
-      const int buf = np.buf[id];
-      const double r0 = np.r0[id], r1 = np.r1[id], c0 = np.c0[id], c1 = np.c1[id];
+      id = q.bhead[cursor];
       __syncwarp();
       if (lane == 0)
       {
         const uint32_t nx = np.next[id];
-        bhead[cursor] = (uint16_t)nx;
+        q.bhead[cursor] = (uint16_t)nx;
         if (nx == kNil)
-          btail[cursor] = (uint16_t)kNil;
+          q.btail[cursor] = (uint16_t)kNil;
         else
           np.prev[nx] = (uint16_t)kNil;
         np.state[id] = 0;
       }
-      --live;
-      --n_nodes;
-      const uint32_t *src = buf ? ib : ia;
-      uint32_t *dst = buf ? ia : ib;
+    }
+    const uint32_t lo = np.lo[id], cnt = np.cnt[id];
+    const int buf = np.buf[id];
+    const double r0 = np.r0[id], r1 = np.r1[id], c0 = np.c0[id], c1 = np.c1[id];
+    --live;
+    const IdxT *src = buf ? ib : ia;
+    IdxT *dst = buf ? ia : ib;
 
-      if (root_pending)
+    if (root_pending)
+    {
+      // initSplit (:81-96): n_ini vertical strips with float-rounded column bounds
+      root_pending = false;
+      const int K = L.n_ini;
+      const double *cols = p.strips + L.strip_off;
+      for (uint32_t i = lane; i < cnt; i += 32)
       {
-        // initSplit (:81-96): n_ini vertical strips with float-rounded column bounds
-        root_pending = false;
-        const int K = L.n_ini;
-        const double *cols = p.strips + L.strip_off;
-        for (uint32_t i = lane; i < cnt; i += 32)
+        const uint32_t e = kp[src[lo + i]];
+        const double x = (double)(e & 0xfffu), y = (double)((e >> 12) & 0xfffu);
+        int d = 255;
+        if (y > r0 && y < r1)
+          for (int k = 0; k < K; ++k)
+            if (x > cols[k] && x < cols[k + 1])
+            {
+              d = k;
+              break;
+            }
+        dig[lo + i] = (uint8_t)d;
+      }
+      __syncwarp();
+      uint32_t base = lo;
+      for (int k = 0; k < K; ++k)
+      {
+        uint32_t run = 0;
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
         {
-          const uint32_t e = kp[src[lo + i]];
-          const double x = (double)(float)(e & 0xfffu), y = (double)(float)((e >> 12) & 0xfffu);
-          int d = 255;
-          if (y > r0 && y < r1)
-            for (int k = 0; k < K; ++k)
-              if (x > cols[k] && x < cols[k + 1])
-              {
-                d = k;
-                break;
-              }
-          dig[lo + i] = (uint8_t)d;
+          const uint32_t i = i0 + lane;
+          const bool f = (i < cnt) && (dig[lo + i] == k);
+          const unsigned m = __ballot_sync(FULL, f);
+          if (f) dst[base + run + __popc(m & lt_mask)] = src[lo + i];
+          run += __popc(m);
+        }
+        if (run > 0)
+        {
+          uint32_t cid;
+          if (n_free > 0)
+            cid = np.free_ids[--n_free];
+          else
+            cid = n_alloc++;
+          if (lane == 0)
+          {
+            np.r0[cid] = r0;
+            np.r1[cid] = r1;
+            np.c0[cid] = cols[k];
+            np.c1[cid] = cols[k + 1];
+            np.lo[cid] = base;
+            np.cnt[cid] = run;
+            np.buf[cid] = (uint8_t)(buf ^ 1);
+          }
+          qt_push(q, cid, run, lane);
+          ++live;
+          base += run;
         }
         __syncwarp();
-        uint32_t base = lo;
-        for (int k = 0; k < K; ++k)
+      }
+    }
+    else
+    {
+      // split (:60-72): midlines in double, children (row0,col0) (row0,col1) (row1,col0) (row1,col1); corners on a
+      // midline belong to no child (strict isIn, ORBExtractor.h:55-62)
+      const double mr = __dmul_rn(__dadd_rn(r0, r1), 0.5), mc = __dmul_rn(__dadd_rn(c0, c1), 0.5);
+      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      if (cnt <= 32)
+      {
+        // the common case: the whole node fits one warp pass, no digit round trip through memory
+        int d = 255;
+        uint32_t idx = 0;
+        if ((uint32_t)lane < cnt)
         {
-          uint32_t run = 0;
-          for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
-          {
-            const uint32_t i = i0 + lane;
-            const bool f = (i < cnt) && (dig[lo + i] == k);
-            const unsigned m = __ballot_sync(FULL, f);
-            if (f) dst[base + run + __popc(m & lt_mask)] = src[lo + i];
-            run += __popc(m);
-          }
-          if (run > 0)
-          {
-            uint32_t cid;
-            if (n_free > 0)
-              cid = np.free_ids[--n_free];
-            else
-              cid = n_alloc++;
-            if (lane == 0)
-            {
-              np.r0[cid] = r0;
-              np.r1[cid] = r1;
-              np.c0[cid] = cols[k];
-              np.c1[cid] = cols[k + 1];
-              np.lo[cid] = base;
-              np.cnt[cid] = run;
-              np.buf[cid] = (uint8_t)(buf ^ 1);
-              qt_push(np, bhead, btail, cid, run);
-            }
-            ++n_nodes;
-            ++live;
-            base += run;
-          }
-          __syncwarp();
+          idx = src[lo + lane];
+          const uint32_t e = kp[idx];
+          const double x = (double)(e & 0xfffu), y = (double)((e >> 12) & 0xfffu);
+          const int jx = x < mc ? 0 : (x > mc ? 1 : -1);
+          const int iy = y < mr ? 0 : (y > mr ? 1 : -1);
+          if (jx >= 0 && iy >= 0) d = iy * 2 + jx;
         }
+        const unsigned m0 = __ballot_sync(FULL, d == 0), m1 = __ballot_sync(FULL, d == 1);
+        const unsigned m2 = __ballot_sync(FULL, d == 2), m3 = __ballot_sync(FULL, d == 3);
+        t0 = __popc(m0);
+        t1 = __popc(m1);
+        t2 = __popc(m2);
+        t3 = __popc(m3);
+        const unsigned mm = d == 0 ? m0 : (d == 1 ? m1 : (d == 2 ? m2 : m3));
+        const uint32_t bb = d == 0 ? 0u : (d == 1 ? t0 : (d == 2 ? t0 + t1 : t0 + t1 + t2));
+        if (d != 255) dst[lo + bb + __popc(mm & lt_mask)] = (IdxT)idx;
       }
       else
       {
-        // split (:60-72): midlines in double, children (row0,col0) (row0,col1) (row1,col0) (row1,col1); corners on a
-        // midline belong to no child (strict isIn, ORBExtractor.h:55-62)
-        const double mr = __dmul_rn(__dadd_rn(r0, r1), 0.5), mc = __dmul_rn(__dadd_rn(c0, c1), 0.5);
-        uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
         for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
         {
           const uint32_t i = i0 + lane;
@@ -745,7 +761,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
         {
           const uint32_t i = i0 + lane;
           int d = 255;
-          uint32_t idx = 0;
+          IdxT idx = 0;
           if (i < cnt)
           {
             d = dig[lo + i];
@@ -762,70 +778,206 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
           q2 += __popc(m2);
           q3 += __popc(m3);
         }
-        const uint32_t tc[4] = {t0, t1, t2, t3};
-        const uint32_t bs[4] = {b0, b1, b2, b3};
+      }
+      // children: lane k < 4 fills the record of child k; ids come from the free stack first, then fresh slots
+      const uint32_t tc[4] = {t0, t1, t2, t3};
+      const uint32_t bs[4] = {lo, lo + t0, lo + t0 + t1, lo + t0 + t1 + t2};
+      const int ne[4] = {t0 > 0, t1 > 0, t2 > 0, t3 > 0};
+      const int rk[4] = {0, ne[0], ne[0] + ne[1], ne[0] + ne[1] + ne[2]};
+      const int n_new = rk[3] + ne[3];
+      uint32_t cid[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-        {
-          if (tc[k] == 0) continue;
-          uint32_t cid;
-          if (n_free > 0)
-            cid = np.free_ids[--n_free];
-          else
-            cid = n_alloc++;
-          if (lane == 0)
-          {
-            np.r0[cid] = (k & 2) ? mr : r0;
-            np.r1[cid] = (k & 2) ? r1 : mr;
-            np.c0[cid] = (k & 1) ? mc : c0;
-            np.c1[cid] = (k & 1) ? c1 : mc;
-            np.lo[cid] = bs[k];
-            np.cnt[cid] = tc[k];
-            np.buf[cid] = (uint8_t)(buf ^ 1);
-            qt_push(np, bhead, btail, cid, tc[k]);
-          }
-          ++n_nodes;
-          ++live;
-          __syncwarp();
-        }
-      }
-      // the popped node's slot can be reused
-      if (lane == 0) np.free_ids[n_free] = (uint16_t)id;
-      ++n_free;
-      __syncwarp();
-    }
-
-    // nodes2kpoints (:182-192): only the first min(need, |M|) entries in (count desc, FIFO) order are used; the surplus
-    // (at most 3 nodes) sits at the tails of the lowest buckets
-    int take = min(need, live), excl = live - take;
-    if (excl > 0)
-    {
-      int b = 0;
-      while (excl > 0 && b <= n)
+      for (int k = 0; k < 4; ++k) cid[k] = rk[k] < n_free ? (uint32_t)np.free_ids[n_free - 1 - rk[k]] : (uint32_t)(n_alloc + rk[k] - n_free);
       {
-        const uint32_t t = btail[b];
-        if (t == kNil)
+        const int k = lane & 3;
+        const uint32_t my_t = k == 0 ? tc[0] : (k == 1 ? tc[1] : (k == 2 ? tc[2] : tc[3]));
+        const uint32_t my_b = k == 0 ? bs[0] : (k == 1 ? bs[1] : (k == 2 ? bs[2] : bs[3]));
+        const uint32_t c = k == 0 ? cid[0] : (k == 1 ? cid[1] : (k == 2 ? cid[2] : cid[3]));
+        if (lane < 4 && my_t > 0)
         {
-          ++b;
-          continue;
+          np.r0[c] = (k & 2) ? mr : r0;
+          np.r1[c] = (k & 2) ? r1 : mr;
+          np.c0[c] = (k & 1) ? mc : c0;
+          np.c1[c] = (k & 1) ? c1 : mc;
+          np.lo[c] = my_b;
+          np.cnt[c] = my_t;
+          np.buf[c] = (uint8_t)(buf ^ 1);
         }
-        __syncwarp();
-        if (lane == 0)
+      }
+      const int from_free = min(n_free, n_new);
+      n_alloc += n_new - from_free;
+      n_free -= from_free;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (tc[k] > 0)
         {
-          np.state[t] = 2;
-          const uint32_t pv = np.prev[t];
-          btail[b] = (uint16_t)pv;
-          if (pv == kNil) bhead[b] = (uint16_t)kNil;
+          qt_push(q, cid[k], tc[k], lane); // multimap insertion order == child order
+          ++live;
         }
-        --excl;
-        __syncwarp();
+    }
+    // the popped node's slot can be reused
+    if (lane == 0) np.free_ids[n_free] = (uint16_t)id;
+    ++n_free;
+    __syncwarp();
+  }
+
+  // nodes2kpoints (:182-192): only the first min(need, |M|) entries in (count desc, FIFO) order are used; the surplus
+  // sits at the tails of the lowest buckets (and, if those run out, at the low end of the big-node list)
+  const int take = min(need, live);
+  int excl = live - take;
+  int b = 0;
+  while (excl > 0 && b < kQtBuckets)
+  {
+    const uint32_t t = q.btail[b];
+    if (t == kNil)
+    {
+      ++b;
+      continue;
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+      np.state[t] = 2;
+      const uint32_t pv = np.prev[t];
+      q.btail[b] = (uint16_t)pv;
+      if (pv == kNil) q.bhead[b] = (uint16_t)kNil;
+    }
+    --excl;
+    __syncwarp();
+  }
+  while (excl > 0 && q.nbig > 0)
+  {
+    const int pos = qt_big_extreme(q, lane, false);
+    __syncwarp();
+    if (lane == 0)
+    {
+      np.state[q.big[pos]] = 2;
+      q.big[pos] = q.big[q.nbig - 1];
+    }
+    --q.nbig;
+    --excl;
+    __syncwarp();
+  }
+  out_n_alloc = n_alloc;
+  out_take = take;
+}
+
+template <typename IdxT>
+__device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *ia, const IdxT *ib, uint8_t *flag, int n, int n_slots, int tid)
+{
+  // best response per surviving node (getFeature :103-117: strict '>', first wins, default index 0)
+  for (int s = tid; s < n_slots; s += kQtThreads)
+  {
+    if (np.state[s] != 1) continue;
+    const IdxT *arr = np.buf[s] ? ib : ia;
+    const uint32_t lo = np.lo[s], cnt = np.cnt[s];
+    uint32_t best = 0, best_i = 0;
+    for (uint32_t i = 0; i < cnt; ++i)
+    {
+      const uint32_t idx = arr[lo + i];
+      const uint32_t r = kp[idx] >> 24;
+      if (r > best)
+      {
+        best = r;
+        best_i = idx;
       }
     }
+    if ((int)best_i < n) flag[best_i] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_warp[kQtThreads / 32];
+  __shared__ int s_n, s_take;
+
+  const int level = blockIdx.x, img = blockIdx.y;
+  const Level &L = p.levels[level];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int need = L.quota;
+  const int ncell = L.n_level_cells;
+  const int *ccnt = p.cell_cnt + (size_t)img * p.n_cells + L.cell_base;
+  const Cell *cells = p.cells + L.cell_base;
+  int *sel_cnt = p.sel_cnt + (size_t)img * p.n_levels + level;
+  uint32_t *sel_out = p.sel + (size_t)img * p.sel_entries + L.sel_off;
+
+  // ---- Phase A: total number of corners on the level
+  int mysum = 0;
+  const int per_c = (ncell + kQtThreads - 1) / kQtThreads;
+  const int c0i = min(tid * per_c, ncell), c1i = min(c0i + per_c, ncell);
+  for (int c = c0i; c < c1i; ++c) mysum += ccnt[c];
+  int n;
+  const int mybase = block_exclusive_scan<kQtThreads>(mysum, n, s_warp);
+
+  // carve shared memory
+  const int node_cap = p.qt_node_cap;
+  QtState q;
+  uint8_t *lists;
+  {
+    uint8_t *w = smem;
+    q.np.r0 = (double *)w;
+    q.np.r1 = q.np.r0 + node_cap;
+    q.np.c0 = q.np.r1 + node_cap;
+    q.np.c1 = q.np.c0 + node_cap;
+    q.np.lo = (uint32_t *)(q.np.c1 + node_cap);
+    q.np.cnt = q.np.lo + node_cap;
+    q.np.seq = q.np.cnt + node_cap;
+    q.np.next = (uint16_t *)(q.np.seq + node_cap);
+    q.np.prev = q.np.next + node_cap;
+    q.np.free_ids = q.np.prev + node_cap;
+    q.np.buf = (uint8_t *)(q.np.free_ids + node_cap);
+    q.np.state = q.np.buf + node_cap;
+    w = smem + qt_align16((size_t)node_cap * kNodeBytes);
+    q.bhead = (uint16_t *)w;
+    q.btail = q.bhead + kQtBuckets;
+    w += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
+    q.big = (uint16_t *)w;
+    w += qt_align16((size_t)p.qt_big_cap * sizeof(uint16_t));
+    lists = w;
+    q.nbig = 0;
+    q.seq_ctr = 0;
+  }
+  // the level's corner list always lives in the global scratch; index arrays / digits there only for dense levels
+  uint32_t *kp = p.qt_scratch + (size_t)img * p.qt_scratch_img_stride + L.scratch_off;
+  const bool in_smem = n <= p.qt_smem_cap;
+  uint16_t *ia16 = (uint16_t *)lists, *ib16 = ia16 + p.qt_smem_cap;
+  uint32_t *ia32 = kp + L.list_cap, *ib32 = ia32 + L.list_cap;
+  uint8_t *dig = in_smem ? (uint8_t *)(ib16 + p.qt_smem_cap) : (uint8_t *)(ib32 + L.list_cap);
+
+  // ---- Phase B: gather the cell lists (cell-row-major, row-major inside a cell == the reference's detection order)
+  {
+    const uint32_t *cl = p.cell_list + (size_t)img * p.cell_entries;
+    int off = mybase;
+    for (int c = c0i; c < c1i; ++c)
+    {
+      const int k = ccnt[c];
+      const uint32_t *src = cl + cells[c].slot;
+      for (int j = 0; j < k; ++j) kp[off + j] = src[j];
+      off += k;
+    }
+  }
+  if (in_smem)
+    for (int i = tid; i < n; i += kQtThreads) ia16[i] = (uint16_t)i; // root holds every corner (:26-27)
+  else
+    for (int i = tid; i < n; i += kQtThreads) ia32[i] = (uint32_t)i;
+  for (int i = tid; i < 2 * kQtBuckets; i += kQtThreads) q.bhead[i] = (uint16_t)kNil; // heads and tails are contiguous
+  for (int i = tid; i < node_cap; i += kQtThreads) q.np.state[i] = 0;
+  __syncthreads();
+
+  // ---- Phase C: the priority loop, warp 0 only
+  if (wid == 0)
+  {
+    int n_alloc = 0, take = 0;
+    if (in_smem)
+      qt_simulate<uint16_t>(p, L, q, kp, ia16, ib16, dig, n, need, node_cap, lane, n_alloc, take);
+    else
+      qt_simulate<uint32_t>(p, L, q, kp, ia32, ib32, dig, n, need, node_cap, lane, n_alloc, take);
     if (lane == 0)
     {
       s_n = n_alloc; // node slots ever used
       s_take = take;
-      s_live = live;
     }
   }
   // dig doubles as the "selected" flag array from here on
@@ -833,33 +985,18 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   for (int i = tid; i < n; i += kQtThreads) dig[i] = 0;
   __syncthreads();
 
-  // ---- Phase D: best response per surviving node (getFeature :103-117: strict '>', first wins, default index 0)
-  const int n_slots = s_n;
+  // ---- Phase D
   if (s_take > 0)
   {
-    for (int s = tid; s < n_slots; s += kQtThreads)
-    {
-      if (np.state[s] != 1) continue;
-      const uint32_t *arr = np.buf[s] ? ib : ia;
-      const uint32_t lo = np.lo[s], cnt = np.cnt[s];
-      uint32_t best = 0, best_i = 0;
-      for (uint32_t i = 0; i < cnt; ++i)
-      {
-        const uint32_t idx = arr[lo + i];
-        const uint32_t r = kp[idx] >> 24;
-        if (r > best)
-        {
-          best = r;
-          best_i = idx;
-        }
-      }
-      if ((int)best_i < n) dig[best_i] = 1;
-    }
+    if (in_smem)
+      qt_select<uint16_t>(q.np, kp, ia16, ib16, dig, n, s_n, tid);
+    else
+      qt_select<uint32_t>(q.np, kp, ia32, ib32, dig, n, s_n, tid);
   }
   __syncthreads();
   {
     const int per = (n + kQtThreads - 1) / kQtThreads;
-    const int i0 = tid * per, i1 = min(i0 + per, n);
+    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
     int mine = 0;
     for (int i = i0; i < i1; ++i) mine += dig[i];
     int total;
