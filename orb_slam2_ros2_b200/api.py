@@ -29,6 +29,7 @@ ORBX_ERR_NO_DEVICE = -5
 ORBX_ERR_CAPACITY = -6
 ORBX_ERR_STATE = -7
 DEPTH_U16, DEPTH_F32 = 0, 1
+N_STAGES = 6  # ORBX_N_STAGES
 
 
 # the reference's exception types (include/ORB_SLAM2/Error.h:13-98)
@@ -324,10 +325,10 @@ class Context:
 
     def profile_stereo_batch_device(self, n_frames, d_left_ptr, d_right_ptr, stride, frame_stride) -> dict:
         """device milliseconds per stage (events between the kernels; blocks)"""
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * N_STAGES)()
         rc = self._L.orbx_profile_stereo_batch_device(self._h, n_frames, C.c_void_p(d_left_ptr), C.c_void_p(d_right_ptr), stride, frame_stride, ms)
         _check(self._h, rc, "orbx_profile_stereo_batch_device")
-        return {self._L.orbx_stage_name(i).decode(): float(ms[i]) for i in range(5)}
+        return {self._L.orbx_stage_name(i).decode(): float(ms[i]) for i in range(N_STAGES)}
 
     def extract_batch_device(self, n_images, d_ptr, stride, frame_stride) -> OrbxDeviceResults:
         res = OrbxDeviceResults()

@@ -325,6 +325,13 @@ int alloc_buffers(orbx_ctx *c)
   if ((rc = dev_alloc(c, &p.desc, ni * N * 32))) return rc;
   if ((rc = dev_alloc(c, &p.n_kps, ni))) return rc;
   if ((rc = dev_alloc(c, &p.rtab, ni * N))) return rc;
+  {
+    // a right keypoint covers at most 2 * (2 * sf) + 2 rows (createRowIndexDB, src/ORBMatcher.cc:924-927)
+    const float sf_max = c->levels.back().sf;
+    p.row_cap = (int)std::min<size_t>((size_t)1 << 30, N * (size_t)(4.f * sf_max + 4.f));
+    if ((rc = dev_alloc(c, &p.row_start, nf * ((size_t)c->cfg.height + 1)))) return rc;
+    if ((rc = dev_alloc(c, &p.row_entries, nf * (size_t)p.row_cap))) return rc;
+  }
   if ((rc = dev_alloc(c, &p.u_right, ni * N))) return rc; // sized per image so that mono batches can use it too
   if ((rc = dev_alloc(c, &p.depth, ni * N))) return rc;
   if ((rc = dev_alloc(c, &p.n_matches, ni))) return rc;
@@ -353,6 +360,8 @@ Params params_at(const orbx_ctx *c, int img0, int frame0)
   p.desc += i * N * 32;
   p.n_kps += i;
   p.rtab += i * N;
+  p.row_start += f * ((size_t)c->cfg.height + 1);
+  p.row_entries += f * (size_t)p.row_cap;
   p.u_right += f * N;
   p.depth += f * N;
   p.n_matches += f;
@@ -373,8 +382,9 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
   launch_fast(p, 2 * nf, s);
   launch_quadtree(p, 2 * nf, c->qt_smem, s);
   launch_orient_brief(p, 2 * nf, s);
+  launch_rowindex(p, nf, s);
   launch_stereo(p, nf, s);
-  c->launches += 5;
+  c->launches += 6;
   ORBX_CUDA(c, cudaGetLastError());
   return ORBX_OK;
 }
@@ -658,7 +668,7 @@ extern "C"
 
   const char *orbx_stage_name(int stage)
   {
-    static const char *names[ORBX_N_STAGES] = {"pyramid_blur", "fast_cells", "quadtree", "orient_brief", "stereo_match"};
+    static const char *names[ORBX_N_STAGES] = {"pyramid_blur", "fast_cells", "quadtree", "orient_brief", "row_index", "stereo_match"};
     return (stage >= 0 && stage < ORBX_N_STAGES) ? names[stage] : "";
   }
 
@@ -687,11 +697,13 @@ extern "C"
     ORBX_CUDA(c, cudaEventRecord(ev[3], c->stream));
     launch_orient_brief(p, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[4], c->stream));
-    launch_stereo(p, n_frames, c->stream);
+    launch_rowindex(p, n_frames, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[5], c->stream));
-    c->launches += 5;
+    launch_stereo(p, n_frames, c->stream);
+    ORBX_CUDA(c, cudaEventRecord(ev[6], c->stream));
+    c->launches += 6;
     ORBX_CUDA(c, cudaGetLastError());
-    ORBX_CUDA(c, cudaEventSynchronize(ev[5]));
+    ORBX_CUDA(c, cudaEventSynchronize(ev[6]));
     for (int i = 0; i < ORBX_N_STAGES; ++i) ORBX_CUDA(c, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
     for (auto &e : ev) cudaEventDestroy(e);
     c->last_images = ni;

@@ -8,6 +8,7 @@
 //   kps, kps_und   [image][n_features]       cv::KeyPoint layout (28 B)
 //   desc           [image][n_features][32]
 //   rtab           [image][n_features]       {x, minRow, maxRow} row-band table for the stereo search
+//   row_start/row_entries [frame][H+1] / [frame][row_cap]   CSR row index of the right keypoints (createRowIndexDB)
 //   u_right, depth [frame][n_features]       doubles, -1 = no match
 #pragma once
 
@@ -111,6 +112,9 @@ struct Params
   uint8_t *desc;
   int *n_kps;
   RTab *rtab;
+  int *row_start;            // [frame][height + 1]  CSR over image rows of the right keypoints whose band covers the row
+  uint16_t *row_entries;     // [frame][row_cap]     right keypoint indices
+  int row_cap;
   double *u_right, *depth;
   int *n_matches;
   // camera
@@ -124,6 +128,7 @@ void launch_pyramid(const Params &p, int n_images, cudaStream_t s);
 void launch_fast(const Params &p, int n_images, cudaStream_t s);
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
 void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
+void launch_rowindex(const Params &p, int n_frames, cudaStream_t s);
 void launch_stereo(const Params &p, int n_frames, cudaStream_t s);
 void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap);

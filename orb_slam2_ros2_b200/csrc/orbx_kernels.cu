@@ -1087,22 +1087,25 @@ __global__ void __launch_bounds__(kBriefWarps * 32) orient_brief_kernel(const Pa
   const uint8_t *__restrict__ lvl = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
   const uint8_t *__restrict__ blr = p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off;
 
-  // getGrayCentroid (:465-487): moments over the radius-15 disc of the un-blurred level; lane <-> column offset
+  // getGrayCentroid (:465-487): moments over the radius-15 disc of the un-blurred level; lane <-> column offset.
+  // Row dy belongs to the lane's column iff |dx| <= umax[|dy|]: a 31-bit row mask per lane, then a fully unrolled loop of
+  // predicated byte loads so that all 31 loads are in flight together.
   int m10 = 0, m01 = 0;
-  if (lane < 31)
   {
     const int dx = lane - 15, adx = abs(dx);
+    unsigned rows = 0u;
+#pragma unroll
+    for (int dy = -15; dy <= 15; ++dy) rows |= (unsigned)(lane < 31 && adx <= c_umax[dy < 0 ? -dy : dy]) << (dy + 15);
     const uint8_t *c = lvl + (size_t)y * pitch + x + dx;
-#pragma unroll 1
+    int colsum = 0;
+#pragma unroll
     for (int dy = -15; dy <= 15; ++dy)
     {
-      if (adx <= c_umax[abs(dy)])
-      {
-        const int v = c[dy * pitch];
-        m10 += dx * v;
-        m01 += dy * v;
-      }
+      const int v = ((rows >> (dy + 15)) & 1u) ? (int)c[dy * pitch] : 0;
+      colsum += v;
+      m01 += dy * v;
     }
+    m10 = dx * colsum;
   }
   m10 = warp_sum(m10);
   m01 = warp_sum(m01);
@@ -1163,6 +1166,64 @@ void launch_orient_brief(const Params &p, int n_images, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K5a: createRowIndexDB (src/ORBMatcher.cc:915-932) as a CSR: for every image row the right keypoints whose band
+// [minRow, maxRow) covers it.  One CTA per frame: shared-memory histogram, block scan, fill.  (Order inside a row does not
+// matter: the search takes the lexicographic minimum of (distance, index), which equals the reference's first minimum
+// over ascending indices.)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kRowThreads = 256;
+
+__global__ void __launch_bounds__(kRowThreads) rowindex_kernel(const Params p)
+{
+  extern __shared__ int s_cnt[]; // [height + 1]
+  __shared__ int s_warp[kRowThreads / 32];
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int H = p.height;
+  const int imgR = 2 * frame + 1;
+  const int nR = p.n_kps[imgR];
+  const RTab *rt = p.rtab + (size_t)imgR * p.n_features;
+  int *row_start = p.row_start + (size_t)frame * (H + 1);
+  uint16_t *entries = p.row_entries + (size_t)frame * p.row_cap;
+  for (int i = tid; i <= H; i += kRowThreads) s_cnt[i] = 0;
+  __syncthreads();
+  for (int j = tid; j < nR; j += kRowThreads)
+  {
+    const RTab t = rt[j];
+    for (int r = t.min_row; r < t.max_row; ++r) atomicAdd(&s_cnt[r], 1);
+  }
+  __syncthreads();
+  const int per = (H + kRowThreads - 1) / kRowThreads;
+  const int r0 = min(tid * per, H), r1 = min(r0 + per, H);
+  int mine = 0;
+  for (int r = r0; r < r1; ++r) mine += s_cnt[r];
+  int total;
+  int off = block_exclusive_scan<kRowThreads>(mine, total, s_warp);
+  for (int r = r0; r < r1; ++r)
+  {
+    const int c = s_cnt[r];
+    s_cnt[r] = off;
+    row_start[r] = off;
+    off += c;
+  }
+  if (tid == 0) row_start[H] = total;
+  __syncthreads();
+  for (int j = tid; j < nR; j += kRowThreads)
+  {
+    const RTab t = rt[j];
+    for (int r = t.min_row; r < t.max_row; ++r)
+    {
+      const int pos = atomicAdd(&s_cnt[r], 1);
+      if (pos < p.row_cap) entries[pos] = (uint16_t)j;
+    }
+  }
+}
+
+void launch_rowindex(const Params &p, int n_frames, cudaStream_t s)
+{
+  rowindex_kernel<<<n_frames, kRowThreads, (size_t)(p.height + 1) * sizeof(int), s>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // K5: stereo association.  One warp per left keypoint: row-band + x-range scan over the right keypoints, Hamming argmin
 // (first minimum == lexicographic min of (distance, index)), 11 SADs over an 11x11 window, parabola refinement.
 // ------------------------------------------------------------------------------------------------------------------
@@ -1175,7 +1236,7 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_kernel(const Params 
   const int li = blockIdx.x * kStereoWarps + (threadIdx.x >> 5);
   const unsigned FULL = 0xffffffffu;
   const int imgL = 2 * frame, imgR = 2 * frame + 1;
-  const int nL = p.n_kps[imgL], nR = p.n_kps[imgR];
+  const int nL = p.n_kps[imgL];
   if (li >= p.n_features) return;
   const size_t oL = (size_t)imgL * p.n_features, oR = (size_t)imgR * p.n_features;
   double *ur_out = p.u_right + (size_t)frame * p.n_features + li;
@@ -1197,16 +1258,23 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_kernel(const Params 
   // getBestMatch over rowIdxDB[row] filtered by minU < x < maxU (:38-52, :967-990)
   unsigned best = 0xffffffffu;
   const RTab *rt = p.rtab + oR;
-  for (int j = lane; j < nR; j += 32)
+  if (row >= 0 && row < p.height) // rows outside the image index the reference's rowIdxDB out of range
   {
-    const RTab t = rt[j];
-    if (row >= t.min_row && row < t.max_row && t.x < maxU && t.x > minU)
+    const int *rs = p.row_start + (size_t)frame * (p.height + 1) + row;
+    const int e0 = rs[0], e1 = min(rs[1], p.row_cap);
+    const uint16_t *entries = p.row_entries + (size_t)frame * p.row_cap;
+    for (int e = e0 + lane; e < e1; e += 32)
     {
-      const uint4 *dr4 = reinterpret_cast<const uint4 *>(p.desc + (oR + j) * 32);
-      const uint4 b0 = dr4[0], b1 = dr4[1];
-      const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
-                    __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-      best = min(best, ((unsigned)d << 20) | (unsigned)j);
+      const int j = entries[e];
+      const float xr = rt[j].x;
+      if (xr < maxU && xr > minU)
+      {
+        const uint4 *dr4 = reinterpret_cast<const uint4 *>(p.desc + (oR + j) * 32);
+        const uint4 b0 = dr4[0], b1 = dr4[1];
+        const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+                      __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+        best = min(best, ((unsigned)d << 20) | (unsigned)j);
+      }
     }
   }
 #pragma unroll
