@@ -128,7 +128,7 @@ int build_tables(orbx_ctx *c)
   c->levels.assign(nl, Level());
   std::vector<int> tab_ofs;
   std::vector<short2> tab_coef;
-  std::vector<double> strips;
+  std::vector<long long> strips; // 24.40 fixed point
 
   // scale factors (:283-289), per-level quotas (:291-301), level sizes (:305-317)
   std::vector<float> sf(nl);
@@ -222,15 +222,17 @@ int build_tables(orbx_ctx *c)
     if (L.n_ini < 0) L.n_ini = 0;
     L.strip_off = (int)strips.size();
     {
+      // cols = {0, (float)(1 * hX), (float)(2 * hX), ..., w} with hX = (float)(w / nIni) (:86-90); floats below 4096 have at
+      // most 23 fractional bits, so the 24.40 fixed-point image is exact
       const float hX = (float)((double)w / (double)L.n_ini);
-      strips.push_back(0.0);
-      for (int k = 1; k < L.n_ini; ++k) strips.push_back((double)((float)k * hX));
-      strips.push_back((double)w);
+      strips.push_back(0);
+      for (int k = 1; k < L.n_ini; ++k) strips.push_back((long long)std::llround(std::ldexp((double)((float)k * hX), 40)));
+      strips.push_back((long long)w << 40);
     }
     L.sel_off = sel_off;
     sel_off += std::max(1, L.quota);
     L.scratch_off = (int)scratch_off;
-    scratch_off += (size_t)L.list_cap * 3 + ((size_t)L.list_cap + 3) / 4 + 8; // corner list + 2 index arrays (u32) + digits (u8)
+    scratch_off += (size_t)L.list_cap * 4 + 8; // corner list + descent keys + 2 index arrays (u32 each)
     scratch_off = (scratch_off + 3) & ~(size_t)3;
     max_quota = std::max(max_quota, L.quota);
     max_ini = std::max(max_ini, L.n_ini);
@@ -253,13 +255,16 @@ int build_tables(orbx_ctx *c)
   p.qt_scratch_img_stride = scratch_off;
   p.qt_node_cap = max_quota + max_ini + 8;
   if (p.qt_node_cap >= 60000) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree node pool");
-  // shared-memory budget of the quadtree kernel: node pool + buckets + big-node list + u16 index arrays for up to 4096 corners
+  // shared-memory budget of the quadtree kernel: node pool + buckets + big-node list + keys / u16 index arrays of up to 3584 corners
   {
     int max_list = 0;
     for (auto &L : c->levels) max_list = std::max(max_list, L.list_cap);
-    const int cap = std::min(4096, std::max(64, max_list));
+    const int cap = std::min(3584, std::max(64, max_list)); // 4 CTAs per SM at the KITTI configuration
     p.qt_big_cap = max_list / 256 + kMaxStrips + 16;
-    const size_t bytes = quadtree_smem_bytes(cap, p.qt_node_cap, p.qt_big_cap);
+    int max_cells = 0;
+    for (auto &L : c->levels) max_cells = std::max(max_cells, L.n_level_cells);
+    p.qt_cell_cap = max_cells + 1;
+    const size_t bytes = quadtree_smem_bytes(cap, p.qt_node_cap, p.qt_big_cap, p.qt_cell_cap);
     if (bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree shared-memory pool");
     p.qt_smem_cap = cap;
     c->qt_smem = bytes;
@@ -296,7 +301,7 @@ int build_tables(orbx_ctx *c)
   if ((rc = dev_upload(c, &p.cells, c->cells))) return rc;
   if ((rc = dev_upload(c, &p.tab_ofs, tab_ofs))) return rc;
   if ((rc = dev_upload(c, &p.tab_coef, tab_coef))) return rc;
-  if ((rc = dev_upload(c, &p.strips, strips))) return rc;
+  if ((rc = dev_upload(c, &p.strips_fx, strips))) return rc;
   if ((rc = dev_upload(c, &p.pattern, pat))) return rc;
 
   // algorithmic bytes: per image P + 60 N; stereo step 2*60 N + 352 N + 16 N

@@ -27,7 +27,7 @@ constexpr int kTileH = 32;
 constexpr int kHalo = 3;        // 7x7 Gaussian
 constexpr int kPyrThreads = 256;
 constexpr int kFastThreads = 128;
-constexpr int kQtThreads = 128;
+constexpr int kQtThreads = 256;
 constexpr int kMaxPatch = 70;   // largest FAST cell patch edge: a cell is < 60 px wide, + 6 px apron; zone <= 64
 constexpr int kMaxStrips = 255; // root split fan-out: round(w/h) vertical strips
 constexpr uint32_t kNil = 0xFFFFu;
@@ -84,7 +84,7 @@ struct Params
   const Cell *cells;
   const int *tab_ofs;     // resize source index per destination index
   const short2 *tab_coef; // resize 11-bit coefficients
-  const double *strips;
+  const long long *strips_fx; // root strip column bounds, 24.40 fixed point (exact: they are float-rounded values)
   const char4 *pattern;   // 256 x (x1, y1, x2, y2)
   // inputs
   const uint8_t *in_left, *in_right;
@@ -107,6 +107,7 @@ struct Params
   int qt_smem_cap;              // corners that fit the shared-memory path
   int qt_node_cap;              // node pool capacity (max quota + max root fan-out + 8)
   int qt_big_cap;               // capacity of the list of nodes holding >= 256 corners
+  int qt_cell_cap;              // largest number of FAST cells on one level (+1): per-cell offsets in shared memory
   // results
   orbx_keypoint *kps, *kps_und;
   uint8_t *desc;
@@ -131,7 +132,7 @@ void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
 void launch_rowindex(const Params &p, int n_frames, cudaStream_t s);
 void launch_stereo(const Params &p, int n_frames, cudaStream_t s);
 void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
-size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap);
+size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells);
 int quadtree_configure(size_t smem_bytes); // opt in to large dynamic shared memory
 
 } // namespace orbx

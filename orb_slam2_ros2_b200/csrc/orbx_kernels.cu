@@ -463,36 +463,53 @@ void launch_fast(const Params &p, int n_images, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------------------------
 // K3: quadtree keypoint distribution.  One CTA per (level, image).
 //   Phase A/B  concatenate the level's cell lists in cell-row-major order (the reference's levelKps order) into the
-//              level's corner list (global scratch, L1/L2 resident)
+//              level's corner list (global scratch) and give every corner its DESCENT KEY: the root strip it falls in
+//              and its quadrant at each of the next 9 subdivision depths (or "on a split line").  The sequence of nodes
+//              that contain a corner is fixed by geometry alone (midlines are (a+b)/2 in double, exactly as :60-72), so
+//              the keys can be computed for all corners in parallel, before any pop order is known.
+//   Phase B'   the root split (initSplit :81-96) is done by the whole block: a stable partition of the corners by strip.
 //   Phase C    warp 0 replays Quadtree::split(): the multimap<count, node, greater> becomes FIFO buckets indexed by
 //              count with a descending cursor (a child never holds more corners than its parent, so the pop key is
 //              monotone).  Counts >= 256 (a handful of early nodes) live in a small unsorted list ordered by
 //              (count, insertion sequence); counts < 256 in 256 linked FIFO buckets.  A node's corner list is a range of
-//              an index array, split by a stable 4-way warp partition (ballot + popc) between two ping-pong arrays.
+//              an index array, split by a stable 4-way warp partition (key digit -> ballot + popc) between two
+//              ping-pong arrays; nodes deeper than the key covers fall back to the double-precision geometry test.
 //   Phase D    nodes2kpoints(): best response per surviving node, ascending index order, shift by the 16-px margin.
-// Index arrays / digits live in shared memory (u16) when the level has at most qt_smem_cap corners, otherwise in the
-// global scratch (u32); node pool, buckets and the big-node list are always in shared memory.
+// Index arrays / keys live in shared memory when the level has at most qt_smem_cap corners, otherwise in the global
+// scratch; node pool, buckets and the big-node list are always in shared memory.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kQtBuckets = 256;  // small buckets hold counts 0..255
-constexpr int kNodeBytes = 4 * 8 + 3 * 4 + 3 * 2 + 2; // r0 r1 c0 c1 | lo cnt seq | next prev free | buf state
+constexpr int kNodeBytes = 4 * 8 + 3 * 4 + 3 * 2 + 3; // r0 r1 c0 c1 | lo cnt seq | next prev free | buf state depth
+constexpr int kKeyLevels = 9;    // subdivision depths encoded in a key (3 bits each) below the 5-bit strip id
+constexpr int kKeyStripShift = 27;
+constexpr uint32_t kKeyNoStrip = 31u;
+constexpr uint32_t kDigitDrop = 7u;
+// Node bounds are dyadic rationals: the strip bounds are float-rounded values below 4096 (at most 23 fractional bits) and
+// every split halves an interval, adding one bit.  Up to depth 17 they are exact both in double ((a+b)/2 has at most
+// 12 + 23 + 17 = 52 significant bits) and in 24.40 fixed point, so the integer computation below is bit-identical to the
+// reference's double arithmetic (src/ORBExtractor.cc:60-72) -- and it keeps FP64 latency out of the single-warp loop.
+// Deeper nodes (reachable only through single-corner nodes) continue in double exactly like the reference.
+constexpr int kFixShift = 40;
+constexpr int kFixDepth = 17; // nodes up to this depth store fixed-point bounds; nodes up to depth 16 split in fixed point
 
 struct QtNodePool
 {
-  double *r0, *r1, *c0, *c1;
+  long long *r0, *r1, *c0, *c1; // bounds: 24.40 fixed point up to depth kFixDepth, IEEE double bit patterns below
   uint32_t *lo, *cnt, *seq;
   uint16_t *next, *prev, *free_ids;
-  uint8_t *buf, *state; // state: 0 dead, 1 live, 2 live but beyond the first `need` entries
+  uint8_t *buf, *state, *depth; // state: 0 dead, 1 live, 2 live but beyond the first `need` entries
 };
 
 __host__ __device__ inline size_t qt_align16(size_t b) { return (b + 15) & ~(size_t)15; }
 
-// shared memory: node pool | bucket heads+tails | big-node list | (smem path) ia, ib (u16), dig (u8)
-size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap)
+// shared memory: node pool | bucket heads+tails | big-node list | (smem path) ia, ib (u16), key (u32)
+size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells)
 {
   size_t b = qt_align16((size_t)node_cap * kNodeBytes);
+  b += qt_align16((size_t)max_level_cells * sizeof(int));
   b += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
   b += qt_align16((size_t)big_cap * sizeof(uint16_t));
-  b += qt_align16((size_t)list_cap * (2 * sizeof(uint16_t) + 1));
+  b += qt_align16((size_t)list_cap * (2 * sizeof(uint16_t) + sizeof(uint32_t)));
   return b + 64;
 }
 
@@ -563,29 +580,85 @@ __device__ __forceinline__ int qt_big_extreme(const QtState &q, int lane, bool w
   return best_pos; // keys are unique (seq), so all lanes agree
 }
 
+// quadrant of (x, y) inside a node with midlines (mr, mc): 0..3 in the reference's child order, or kDigitDrop on a midline
+template <typename T> __device__ __forceinline__ uint32_t qt_quadrant(T x, T y, T mr, T mc)
+{
+  const int jx = x < mc ? 0 : (x > mc ? 1 : -1);
+  const int iy = y < mr ? 0 : (y > mr ? 1 : -1);
+  return (jx >= 0 && iy >= 0) ? (uint32_t)(iy * 2 + jx) : kDigitDrop;
+}
+
+// Descent key of one corner (strip id + kKeyLevels quadrant digits); cols = strip bounds in 24.40 fixed point.
+// Inside a strip [c0, c0 + W) x [0, H) the depth-j nodes are the 2^j x 2^j grid of equal dyadic sub-intervals, so the
+// column of the depth-j node holding x is floor((x - c0) * 2^j / W), its low bit is the left/right choice at depth j, and x
+// lies on a depth-j midline iff (x - c0) * 2^j / W is an integer: one division per axis replaces the level-by-level descent.
+__device__ __forceinline__ uint32_t qt_make_key(uint32_t e, const long long *cols, int K, int roi_h)
+{
+  const uint32_t xi = e & 0xfffu, yi = (e >> 12) & 0xfffu;
+  const long long x = (long long)xi << kFixShift;
+  int strip = -1;
+  if (yi > 0u && yi < (uint32_t)roi_h)
+    for (int k = 0; k < K; ++k)
+      if (x > cols[k] && x < cols[k + 1])
+      {
+        strip = k;
+        break;
+      }
+  if (strip < 0) return kKeyNoStrip << kKeyStripShift;
+  const unsigned long long ux = (unsigned long long)(x - cols[strip]) << kKeyLevels, wx = (unsigned long long)(cols[strip + 1] - cols[strip]);
+  const unsigned long long qx64 = ux / wx;
+  const bool x_exact = qx64 * wx == ux;
+  const uint32_t qx = (uint32_t)qx64;
+  const uint32_t uy = yi << kKeyLevels, qy = uy / (uint32_t)roi_h;
+  const bool y_exact = qy * (uint32_t)roi_h == uy;
+  // first depth at which the corner sits on a midline (kKeyLevels + 1: none within the key)
+  const int jdx = x_exact ? kKeyLevels - (__ffs((int)qx) - 1) : kKeyLevels + 1;
+  const int jdy = y_exact ? kKeyLevels - (__ffs((int)qy) - 1) : kKeyLevels + 1;
+  const int jd = max(1, min(jdx, jdy));
+  uint32_t key = (uint32_t)strip << kKeyStripShift;
+#pragma unroll
+  for (int j = 1; j <= kKeyLevels; ++j)
+  {
+    const uint32_t d = (((qy >> (kKeyLevels - j)) & 1u) << 1) | ((qx >> (kKeyLevels - j)) & 1u);
+    key |= (j < jd ? d : (j == jd ? kDigitDrop : 0u)) << (kKeyStripShift - 3 * j);
+  }
+  return key;
+}
+
+// bounds (24.40 fixed point) of the depth-kKeyLevels node a key leads to
+__device__ __forceinline__ void qt_bounds_from_key(uint32_t key, const long long *cols, long long roi_h_fx, long long &r0, long long &r1, long long &c0, long long &c1)
+{
+  const int strip = (int)(key >> kKeyStripShift);
+  r0 = 0;
+  r1 = roi_h_fx;
+  c0 = cols[strip];
+  c1 = cols[strip + 1];
+#pragma unroll 1
+  for (int j = 1; j <= kKeyLevels; ++j)
+  {
+    const uint32_t d = (key >> (kKeyStripShift - 3 * j)) & 7u;
+    const long long mr = (r0 + r1) >> 1, mc = (c0 + c1) >> 1;
+    if (d & 2u)
+      r0 = mr;
+    else
+      r1 = mr;
+    if (d & 1u)
+      c0 = mc;
+    else
+      c1 = mc;
+  }
+}
+
 template <typename IdxT>
-__device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const uint32_t *kp, IdxT *ia, IdxT *ib, uint8_t *dig, int n, int need, int node_cap,
-                            int lane, int &out_n_alloc, int &out_take)
+__device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const uint32_t *kp, const uint32_t *keys, bool use_keys, IdxT *ia, IdxT *ib, int n,
+                            int need, int node_cap, int lane, int live, int n_alloc, bool root_pending, int &out_n_alloc, int &out_take)
 {
   const unsigned FULL = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
   QtNodePool &np = q.np;
-  int n_alloc = 1, n_free = 0;
-  if (lane == 0)
-  {
-    np.r0[0] = 0.0;
-    np.r1[0] = (double)L.roi_h;
-    np.c0[0] = 0.0;
-    np.c1[0] = (double)L.roi_w;
-    np.lo[0] = 0;
-    np.cnt[0] = (uint32_t)n;
-    np.buf[0] = 0;
-  }
-  qt_push(q, 0, (uint32_t)n, lane);
-  __syncwarp();
-  int live = 1; // == the reference's mnNodes: every live node sits in the multimap
+  int n_free = 0;
   int cursor = kQtBuckets - 1;
-  bool root_pending = true;
+  // `live` == the reference's mnNodes: every live node sits in the multimap
   while (live < need && live > 0)
   {
     uint32_t id;
@@ -641,33 +714,33 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
       }
     }
     const uint32_t lo = np.lo[id], cnt = np.cnt[id];
-    const int buf = np.buf[id];
-    const double r0 = np.r0[id], r1 = np.r1[id], c0 = np.c0[id], c1 = np.c1[id];
+    const int buf = np.buf[id], depth = np.depth[id];
     --live;
     const IdxT *src = buf ? ib : ia;
     IdxT *dst = buf ? ia : ib;
+    // Bounds are only needed where the keys end: nodes above depth kKeyLevels never store or load them, a node AT that depth
+    // rebuilds them from the key of any of its corners, deeper nodes (and key-less configurations) keep them in the pool.
+    const bool keyed = use_keys && depth < kKeyLevels && !root_pending;
+    long long r0 = 0, r1 = 0, c0 = 0, c1 = 0;
+    if (!keyed)
+    {
+      if (use_keys && depth == kKeyLevels && cnt > 0)
+        qt_bounds_from_key(keys[src[lo]], p.strips_fx + L.strip_off, (long long)L.roi_h << kFixShift, r0, r1, c0, c1);
+      else
+      {
+        r0 = np.r0[id];
+        r1 = np.r1[id];
+        c0 = np.c0[id];
+        c1 = np.c1[id];
+      }
+    }
 
     if (root_pending)
     {
-      // initSplit (:81-96): n_ini vertical strips with float-rounded column bounds
+      // initSplit (:81-96) for configurations the keys cannot express (more than 31 strips): generic K-way passes
       root_pending = false;
       const int K = L.n_ini;
-      const double *cols = p.strips + L.strip_off;
-      for (uint32_t i = lane; i < cnt; i += 32)
-      {
-        const uint32_t e = kp[src[lo + i]];
-        const double x = (double)(e & 0xfffu), y = (double)((e >> 12) & 0xfffu);
-        int d = 255;
-        if (y > r0 && y < r1)
-          for (int k = 0; k < K; ++k)
-            if (x > cols[k] && x < cols[k + 1])
-            {
-              d = k;
-              break;
-            }
-        dig[lo + i] = (uint8_t)d;
-      }
-      __syncwarp();
+      const long long *cols = p.strips_fx + L.strip_off;
       uint32_t base = lo;
       for (int k = 0; k < K; ++k)
       {
@@ -675,9 +748,17 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
         for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
         {
           const uint32_t i = i0 + lane;
-          const bool f = (i < cnt) && (dig[lo + i] == k);
+          bool f = false;
+          uint32_t idx = 0;
+          if (i < cnt)
+          {
+            idx = src[lo + i];
+            const uint32_t e = kp[idx];
+            const long long x = (long long)(e & 0xfffu) << kFixShift, y = (long long)((e >> 12) & 0xfffu) << kFixShift;
+            f = x > cols[k] && x < cols[k + 1] && y > r0 && y < r1;
+          }
           const unsigned m = __ballot_sync(FULL, f);
-          if (f) dst[base + run + __popc(m & lt_mask)] = src[lo + i];
+          if (f) dst[base + run + __popc(m & lt_mask)] = (IdxT)idx;
           run += __popc(m);
         }
         if (run > 0)
@@ -696,6 +777,7 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
             np.lo[cid] = base;
             np.cnt[cid] = run;
             np.buf[cid] = (uint8_t)(buf ^ 1);
+            np.depth[cid] = 0;
           }
           qt_push(q, cid, run, lane);
           ++live;
@@ -708,21 +790,46 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
     {
       // split (:60-72): midlines in double, children (row0,col0) (row0,col1) (row1,col0) (row1,col1); corners on a
       // midline belong to no child (strict isIn, ORBExtractor.h:55-62)
-      const double mr = __dmul_rn(__dadd_rn(r0, r1), 0.5), mc = __dmul_rn(__dadd_rn(c0, c1), 0.5);
+      const bool fixed = depth < kFixDepth; // this node splits in fixed point; its children (depth <= kFixDepth) store fixed bounds
+      long long mr = 0, mc = 0;             // midlines in the representation of the CHILDREN
+      double mr_d = 0.0, mc_d = 0.0;
+      if (!keyed)
+      {
+        if (fixed)
+        {
+          mr = (r0 + r1) >> 1;
+          mc = (c0 + c1) >> 1;
+        }
+        else
+        {
+          // depth == kFixDepth holds fixed-point bounds (exactly convertible), deeper nodes hold double bit patterns
+          const double scale = 1.0 / (double)(1ll << kFixShift);
+          const double dr0 = depth == kFixDepth ? __dmul_rn((double)r0, scale) : __longlong_as_double(r0);
+          const double dr1 = depth == kFixDepth ? __dmul_rn((double)r1, scale) : __longlong_as_double(r1);
+          const double dc0 = depth == kFixDepth ? __dmul_rn((double)c0, scale) : __longlong_as_double(c0);
+          const double dc1 = depth == kFixDepth ? __dmul_rn((double)c1, scale) : __longlong_as_double(c1);
+          mr_d = __dmul_rn(__dadd_rn(dr0, dr1), 0.5);
+          mc_d = __dmul_rn(__dadd_rn(dc0, dc1), 0.5);
+          mr = __double_as_longlong(mr_d);
+          mc = __double_as_longlong(mc_d);
+        }
+      }
+      const int shift = kKeyStripShift - 3 * (depth + 1);
       uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      auto digit_of = [&](uint32_t idx) -> uint32_t {
+        if (keyed) return (keys[idx] >> shift) & 7u;
+        const uint32_t e = kp[idx];
+        if (fixed) return qt_quadrant((long long)(e & 0xfffu) << kFixShift, (long long)((e >> 12) & 0xfffu) << kFixShift, mr, mc);
+        return qt_quadrant((double)(e & 0xfffu), (double)((e >> 12) & 0xfffu), mr_d, mc_d);
+      };
       if (cnt <= 32)
       {
-        // the common case: the whole node fits one warp pass, no digit round trip through memory
-        int d = 255;
-        uint32_t idx = 0;
+        // the common case: the whole node fits one warp pass
+        uint32_t d = kDigitDrop, idx = 0;
         if ((uint32_t)lane < cnt)
         {
           idx = src[lo + lane];
-          const uint32_t e = kp[idx];
-          const double x = (double)(e & 0xfffu), y = (double)((e >> 12) & 0xfffu);
-          const int jx = x < mc ? 0 : (x > mc ? 1 : -1);
-          const int iy = y < mr ? 0 : (y > mr ? 1 : -1);
-          if (jx >= 0 && iy >= 0) d = iy * 2 + jx;
+          d = digit_of(idx);
         }
         const unsigned m0 = __ballot_sync(FULL, d == 0), m1 = __ballot_sync(FULL, d == 1);
         const unsigned m2 = __ballot_sync(FULL, d == 2), m3 = __ballot_sync(FULL, d == 3);
@@ -732,40 +839,30 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
         t3 = __popc(m3);
         const unsigned mm = d == 0 ? m0 : (d == 1 ? m1 : (d == 2 ? m2 : m3));
         const uint32_t bb = d == 0 ? 0u : (d == 1 ? t0 : (d == 2 ? t0 + t1 : t0 + t1 + t2));
-        if (d != 255) dst[lo + bb + __popc(mm & lt_mask)] = (IdxT)idx;
+        if (d != kDigitDrop) dst[lo + bb + __popc(mm & lt_mask)] = (IdxT)idx;
       }
       else
       {
         for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
         {
           const uint32_t i = i0 + lane;
-          int d = 255;
-          if (i < cnt)
-          {
-            const uint32_t e = kp[src[lo + i]];
-            const double x = (double)(e & 0xfffu), y = (double)((e >> 12) & 0xfffu);
-            const int jx = x < mc ? 0 : (x > mc ? 1 : -1);
-            const int iy = y < mr ? 0 : (y > mr ? 1 : -1);
-            if (jx >= 0 && iy >= 0) d = iy * 2 + jx;
-            dig[lo + i] = (uint8_t)d;
-          }
+          const uint32_t d = i < cnt ? digit_of(src[lo + i]) : kDigitDrop;
           t0 += __popc(__ballot_sync(FULL, d == 0));
           t1 += __popc(__ballot_sync(FULL, d == 1));
           t2 += __popc(__ballot_sync(FULL, d == 2));
           t3 += __popc(__ballot_sync(FULL, d == 3));
         }
-        __syncwarp();
         const uint32_t b0 = lo, b1 = b0 + t0, b2 = b1 + t1, b3 = b2 + t2;
         uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
         for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
         {
           const uint32_t i = i0 + lane;
-          int d = 255;
+          uint32_t d = kDigitDrop;
           IdxT idx = 0;
           if (i < cnt)
           {
-            d = dig[lo + i];
             idx = src[lo + i];
+            d = digit_of(idx);
           }
           const unsigned m0 = __ballot_sync(FULL, d == 0), m1 = __ballot_sync(FULL, d == 1);
           const unsigned m2 = __ballot_sync(FULL, d == 2), m3 = __ballot_sync(FULL, d == 3);
@@ -795,13 +892,26 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
         const uint32_t c = k == 0 ? cid[0] : (k == 1 ? cid[1] : (k == 2 ? cid[2] : cid[3]));
         if (lane < 4 && my_t > 0)
         {
-          np.r0[c] = (k & 2) ? mr : r0;
-          np.r1[c] = (k & 2) ? r1 : mr;
-          np.c0[c] = (k & 1) ? mc : c0;
-          np.c1[c] = (k & 1) ? c1 : mc;
+          if (!keyed)
+          {
+            long long pr0 = r0, pr1 = r1, pc0 = c0, pc1 = c1; // parent bounds in the children's representation
+            if (depth == kFixDepth)
+            {
+              const double scale = 1.0 / (double)(1ll << kFixShift);
+              pr0 = __double_as_longlong(__dmul_rn((double)r0, scale));
+              pr1 = __double_as_longlong(__dmul_rn((double)r1, scale));
+              pc0 = __double_as_longlong(__dmul_rn((double)c0, scale));
+              pc1 = __double_as_longlong(__dmul_rn((double)c1, scale));
+            }
+            np.r0[c] = (k & 2) ? mr : pr0;
+            np.r1[c] = (k & 2) ? pr1 : mr;
+            np.c0[c] = (k & 1) ? mc : pc0;
+            np.c1[c] = (k & 1) ? pc1 : mc;
+          }
           np.lo[c] = my_b;
           np.cnt[c] = my_t;
           np.buf[c] = (uint8_t)(buf ^ 1);
+          np.depth[c] = (uint8_t)min(depth + 1, 255);
         }
       }
       const int from_free = min(n_free, n_new);
@@ -864,9 +974,10 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
 }
 
 template <typename IdxT>
-__device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *ia, const IdxT *ib, uint8_t *flag, int n, int n_slots, int tid)
+__device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *ia, const IdxT *ib, uint32_t *flag, int n, int n_slots, int tid)
 {
-  // best response per surviving node (getFeature :103-117: strict '>', first wins, default index 0)
+  // best response per surviving node (getFeature :103-117: strict '>' over the node's list, whose order is ascending
+  // detection index, i.e. the lowest index among the maxima wins; default index 0 when no response is positive)
   for (int s = tid; s < n_slots; s += kQtThreads)
   {
     if (np.state[s] != 1) continue;
@@ -877,13 +988,13 @@ __device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *
     {
       const uint32_t idx = arr[lo + i];
       const uint32_t r = kp[idx] >> 24;
-      if (r > best)
+      if (r > best || (r == best && r > 0 && idx < best_i))
       {
         best = r;
         best_i = idx;
       }
     }
-    if ((int)best_i < n) flag[best_i] = 1;
+    if ((int)best_i < n) flag[best_i] = 1u;
   }
 }
 
@@ -892,6 +1003,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_warp[kQtThreads / 32];
   __shared__ int s_n, s_take;
+  __shared__ int s_strip_cnt[32];
 
   const int level = blockIdx.x, img = blockIdx.y;
   const Level &L = p.levels[level];
@@ -903,13 +1015,22 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   int *sel_cnt = p.sel_cnt + (size_t)img * p.n_levels + level;
   uint32_t *sel_out = p.sel + (size_t)img * p.sel_entries + L.sel_off;
 
-  // ---- Phase A: total number of corners on the level
-  int mysum = 0;
+  // ---- Phase A: per-cell offsets (exclusive scan of the cell counts) and the total number of corners on the level
+  int *cell_off = (int *)(smem + qt_align16((size_t)p.qt_node_cap * kNodeBytes));
   const int per_c = (ncell + kQtThreads - 1) / kQtThreads;
   const int c0i = min(tid * per_c, ncell), c1i = min(c0i + per_c, ncell);
+  int mysum = 0;
   for (int c = c0i; c < c1i; ++c) mysum += ccnt[c];
   int n;
-  const int mybase = block_exclusive_scan<kQtThreads>(mysum, n, s_warp);
+  {
+    int off = block_exclusive_scan<kQtThreads>(mysum, n, s_warp);
+    for (int c = c0i; c < c1i; ++c)
+    {
+      cell_off[c] = off;
+      off += ccnt[c];
+    }
+    if (tid == 0) cell_off[ncell] = n;
+  }
 
   // carve shared memory
   const int node_cap = p.qt_node_cap;
@@ -917,7 +1038,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   uint8_t *lists;
   {
     uint8_t *w = smem;
-    q.np.r0 = (double *)w;
+    q.np.r0 = (long long *)w;
     q.np.r1 = q.np.r0 + node_cap;
     q.np.c0 = q.np.r1 + node_cap;
     q.np.c1 = q.np.c0 + node_cap;
@@ -929,7 +1050,8 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
     q.np.free_ids = q.np.prev + node_cap;
     q.np.buf = (uint8_t *)(q.np.free_ids + node_cap);
     q.np.state = q.np.buf + node_cap;
-    w = smem + qt_align16((size_t)node_cap * kNodeBytes);
+    q.np.depth = q.np.state + node_cap;
+    w = smem + qt_align16((size_t)node_cap * kNodeBytes) + qt_align16((size_t)p.qt_cell_cap * sizeof(int));
     q.bhead = (uint16_t *)w;
     q.btail = q.bhead + kQtBuckets;
     w += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
@@ -939,70 +1061,163 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
     q.nbig = 0;
     q.seq_ctr = 0;
   }
-  // the level's corner list always lives in the global scratch; index arrays / digits there only for dense levels
+  // the level's corner list always lives in the global scratch; index arrays / keys there only for dense levels
   uint32_t *kp = p.qt_scratch + (size_t)img * p.qt_scratch_img_stride + L.scratch_off;
   const bool in_smem = n <= p.qt_smem_cap;
-  uint16_t *ia16 = (uint16_t *)lists, *ib16 = ia16 + p.qt_smem_cap;
-  uint32_t *ia32 = kp + L.list_cap, *ib32 = ia32 + L.list_cap;
-  uint8_t *dig = in_smem ? (uint8_t *)(ib16 + p.qt_smem_cap) : (uint8_t *)(ib32 + L.list_cap);
+  uint32_t *keys = in_smem ? (uint32_t *)lists : kp + L.list_cap;
+  uint16_t *ia16 = (uint16_t *)(lists + (size_t)p.qt_smem_cap * sizeof(uint32_t)), *ib16 = ia16 + p.qt_smem_cap;
+  uint32_t *ia32 = kp + 2 * (size_t)L.list_cap, *ib32 = ia32 + L.list_cap;
+  const int K = L.n_ini;
+  const bool use_keys = K <= 31;
+  const long long *cols = p.strips_fx + L.strip_off;
+  const long long roi_h_fx = (long long)L.roi_h << kFixShift, roi_w_fx = (long long)L.roi_w << kFixShift;
 
-  // ---- Phase B: gather the cell lists (cell-row-major, row-major inside a cell == the reference's detection order)
+  // ---- Phase B: gather the cell lists (cell-row-major, row-major inside a cell == the reference's detection order),
+  // one thread per corner: binary search of the corner's cell in the offsets, then load + key
+  __syncthreads();
   {
     const uint32_t *cl = p.cell_list + (size_t)img * p.cell_entries;
-    int off = mybase;
-    for (int c = c0i; c < c1i; ++c)
+    for (int i = tid; i < n; i += kQtThreads)
     {
-      const int k = ccnt[c];
-      const uint32_t *src = cl + cells[c].slot;
-      for (int j = 0; j < k; ++j) kp[off + j] = src[j];
-      off += k;
+      int lo_c = 0, hi_c = ncell; // largest c with cell_off[c] <= i
+      while (hi_c - lo_c > 1)
+      {
+        const int mid = (lo_c + hi_c) >> 1;
+        if (cell_off[mid] <= i)
+          lo_c = mid;
+        else
+          hi_c = mid;
+      }
+      const uint32_t e = cl[cells[lo_c].slot + (i - cell_off[lo_c])];
+      kp[i] = e;
+      if (use_keys) keys[i] = qt_make_key(e, cols, K, L.roi_h);
     }
   }
-  if (in_smem)
-    for (int i = tid; i < n; i += kQtThreads) ia16[i] = (uint16_t)i; // root holds every corner (:26-27)
-  else
-    for (int i = tid; i < n; i += kQtThreads) ia32[i] = (uint32_t)i;
   for (int i = tid; i < 2 * kQtBuckets; i += kQtThreads) q.bhead[i] = (uint16_t)kNil; // heads and tails are contiguous
   for (int i = tid; i < node_cap; i += kQtThreads) q.np.state[i] = 0;
+  if (tid < 32) s_strip_cnt[tid] = 0;
+  __syncthreads();
+
+  // ---- Phase B': root.  With need <= 1 the reference never pops the root (:151); otherwise its first pop is the root,
+  // whose children are the strips: partition the corners by strip with the whole block (stable: K ordered scans).
+  const bool split_root_here = use_keys && need > 1;
+  if (split_root_here)
+  {
+    const int per = (n + kQtThreads - 1) / kQtThreads;
+    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+    int base = 0;
+    for (int k = 0; k < K; ++k)
+    {
+      int mine = 0;
+      for (int i = i0; i < i1; ++i) mine += (keys[i] >> kKeyStripShift) == (uint32_t)k;
+      int total;
+      int off = base + block_exclusive_scan<kQtThreads>(mine, total, s_warp);
+      for (int i = i0; i < i1; ++i)
+        if ((keys[i] >> kKeyStripShift) == (uint32_t)k)
+        {
+          if (in_smem)
+            ia16[off] = (uint16_t)i;
+          else
+            ia32[off] = (uint32_t)i;
+          ++off;
+        }
+      if (tid == 0) s_strip_cnt[k] = total;
+      base += total;
+    }
+  }
+  else
+  {
+    if (in_smem)
+      for (int i = tid; i < n; i += kQtThreads) ia16[i] = (uint16_t)i; // root holds every corner (:26-27)
+    else
+      for (int i = tid; i < n; i += kQtThreads) ia32[i] = (uint32_t)i;
+  }
   __syncthreads();
 
   // ---- Phase C: the priority loop, warp 0 only
   if (wid == 0)
   {
-    int n_alloc = 0, take = 0;
-    if (in_smem)
-      qt_simulate<uint16_t>(p, L, q, kp, ia16, ib16, dig, n, need, node_cap, lane, n_alloc, take);
+    int n_alloc = 0, live = 0, take = 0;
+    bool root_pending;
+    if (split_root_here)
+    {
+      // state right after the reference's first iteration: root popped, its non-empty strips inserted in order
+      uint32_t base = 0;
+      for (int k = 0; k < K; ++k)
+      {
+        const uint32_t cnt = (uint32_t)s_strip_cnt[k];
+        if (cnt == 0) continue;
+        const uint32_t cid = (uint32_t)n_alloc++;
+        if (lane == 0)
+        {
+          q.np.r0[cid] = 0;
+          q.np.r1[cid] = roi_h_fx;
+          q.np.c0[cid] = cols[k];
+          q.np.c1[cid] = cols[k + 1];
+          q.np.lo[cid] = base;
+          q.np.cnt[cid] = cnt;
+          q.np.buf[cid] = 0;
+          q.np.depth[cid] = 0;
+        }
+        qt_push(q, cid, cnt, lane);
+        ++live;
+        base += cnt;
+      }
+      root_pending = false;
+    }
     else
-      qt_simulate<uint32_t>(p, L, q, kp, ia32, ib32, dig, n, need, node_cap, lane, n_alloc, take);
+    {
+      if (lane == 0)
+      {
+        q.np.r0[0] = 0;
+        q.np.r1[0] = roi_h_fx;
+        q.np.c0[0] = 0;
+        q.np.c1[0] = roi_w_fx;
+        q.np.lo[0] = 0;
+        q.np.cnt[0] = (uint32_t)n;
+        q.np.buf[0] = 0;
+        q.np.depth[0] = 0;
+      }
+      qt_push(q, 0, (uint32_t)n, lane);
+      n_alloc = 1;
+      live = 1;
+      root_pending = true;
+    }
+    __syncwarp();
+    if (in_smem)
+      qt_simulate<uint16_t>(p, L, q, kp, keys, use_keys, ia16, ib16, n, need, node_cap, lane, live, n_alloc, root_pending, n_alloc, take);
+    else
+      qt_simulate<uint32_t>(p, L, q, kp, keys, use_keys, ia32, ib32, n, need, node_cap, lane, live, n_alloc, root_pending, n_alloc, take);
     if (lane == 0)
     {
       s_n = n_alloc; // node slots ever used
       s_take = take;
     }
   }
-  // dig doubles as the "selected" flag array from here on
+  // the key array doubles as the "selected" flag array from here on
   __syncthreads();
-  for (int i = tid; i < n; i += kQtThreads) dig[i] = 0;
+  uint32_t *flag = keys;
+  for (int i = tid; i < n; i += kQtThreads) flag[i] = 0u;
   __syncthreads();
 
   // ---- Phase D
   if (s_take > 0)
   {
     if (in_smem)
-      qt_select<uint16_t>(q.np, kp, ia16, ib16, dig, n, s_n, tid);
+      qt_select<uint16_t>(q.np, kp, ia16, ib16, flag, n, s_n, tid);
     else
-      qt_select<uint32_t>(q.np, kp, ia32, ib32, dig, n, s_n, tid);
+      qt_select<uint32_t>(q.np, kp, ia32, ib32, flag, n, s_n, tid);
   }
   __syncthreads();
   {
     const int per = (n + kQtThreads - 1) / kQtThreads;
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
     int mine = 0;
-    for (int i = i0; i < i1; ++i) mine += dig[i];
+    for (int i = i0; i < i1; ++i) mine += (int)flag[i];
     int total;
     int off = block_exclusive_scan<kQtThreads>(mine, total, s_warp);
     for (int i = i0; i < i1; ++i)
-      if (dig[i])
+      if (flag[i])
       {
         const uint32_t e = kp[i];
         // back to level coordinates (:382-383)
