@@ -257,8 +257,14 @@ def run_gpu_arm(args):
     dom_ms = stage_ms[dominant]
     achieved = alg_frame * B / (dom_ms * 1e-3) / 1e9
     step_total = sum(stage_ms.values())
+    traffic = None
+    try:  # dram__bytes_read+write of the same kernel from the committed ncu --set full capture (per 64-frame launch)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[dominant]
+        traffic = tj["dram_bytes_per_launch"] * B / tj["frames_per_launch"]
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "algorithmic_bytes_per_frame": alg_frame, "frames_per_launch": B, "kernel_ms": dom_ms,
         "kernel_share_of_step": dom_ms / step_total, "stage_ms": stage_ms,
         "whole_step": {"achieved": alg_frame * value / world / 1e9, "frac": alg_frame * value / world / 1e9 / peak},

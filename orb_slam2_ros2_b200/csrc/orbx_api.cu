@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <new>
@@ -40,11 +41,12 @@ struct orbx_ctx
   int last_images = 0;          // images processed by the most recent call (for orbx_get_pyramid)
   int last_stereo = 0;
   // host-batch pipeline: chunks of frames round-robin over kPipe streams so that H2D, kernels and D2H overlap
-  static constexpr int kPipe = 4;
-  static constexpr int kChunk = 8; // frames per chunk
-  cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kPipeMax = 8;
+  int kPipe = 8;  // streams (tunable for experiments: ORBX_PIPE); 8 x 8 frames measured best on B200
+  int kChunk = 8; // frames per chunk (ORBX_CHUNK)
+  cudaStream_t pipe[kPipeMax] = {};
   cudaEvent_t fork_ev = nullptr;
-  cudaEvent_t join_ev[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t join_ev[kPipeMax] = {};
 };
 
 namespace
@@ -537,11 +539,13 @@ extern "C"
         break;
       }
       c->stream = c->own_stream;
-      for (auto &ps : c->pipe)
-        if (cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking) != cudaSuccess) rc = ORBX_ERR_CUDA;
+      if (const char *e = std::getenv("ORBX_PIPE")) c->kPipe = std::max(1, std::min(orbx_ctx::kPipeMax, std::atoi(e)));
+      if (const char *e = std::getenv("ORBX_CHUNK")) c->kChunk = std::max(1, std::atoi(e));
+      for (int i = 0; i < c->kPipe; ++i)
+        if (cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking) != cudaSuccess) rc = ORBX_ERR_CUDA;
       if (cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) != cudaSuccess) rc = ORBX_ERR_CUDA;
-      for (auto &je : c->join_ev)
-        if (cudaEventCreateWithFlags(&je, cudaEventDisableTiming) != cudaSuccess) rc = ORBX_ERR_CUDA;
+      for (int i = 0; i < c->kPipe; ++i)
+        if (cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = ORBX_ERR_CUDA;
     } while (0);
     if (rc != ORBX_OK)
     {
@@ -642,7 +646,7 @@ extern "C"
     if (!c || !d_left || !d_right || n_frames < 1) return ORBX_ERR_INVALID_ARG;
     if (n_frames > c->cfg.max_batch) return fail(c, ORBX_ERR_CAPACITY, "n_frames > max_batch");
     ORBX_CUDA(c, cudaSetDevice(c->device));
-    if (n_frames <= orbx_ctx::kChunk)
+    if (n_frames <= c->kChunk)
     {
       int rc = run_stereo_range(c, c->stream, 0, n_frames, d_left, d_right, stride, frame_stride);
       if (rc) return rc;
@@ -652,14 +656,14 @@ extern "C"
       // Fork the batch into chunks on the pipeline streams and join back into the caller's stream: the latency-bound
       // quadtree launches of one chunk then overlap the issue-bound FAST / pyramid launches of the others.
       ORBX_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
-      for (auto &ps : c->pipe) ORBX_CUDA(c, cudaStreamWaitEvent(ps, c->fork_ev, 0));
+      for (int i = 0; i < c->kPipe; ++i) ORBX_CUDA(c, cudaStreamWaitEvent(c->pipe[i], c->fork_ev, 0));
       int k = 0;
-      for (int f0 = 0; f0 < n_frames; f0 += orbx_ctx::kChunk, ++k)
+      for (int f0 = 0; f0 < n_frames; f0 += c->kChunk, ++k)
       {
-        int rc = run_stereo_range(c, c->pipe[k % orbx_ctx::kPipe], f0, std::min(orbx_ctx::kChunk, n_frames - f0), d_left, d_right, stride, frame_stride);
+        int rc = run_stereo_range(c, c->pipe[k % c->kPipe], f0, std::min(c->kChunk, n_frames - f0), d_left, d_right, stride, frame_stride);
         if (rc) return rc;
       }
-      for (int i = 0; i < orbx_ctx::kPipe; ++i)
+      for (int i = 0; i < c->kPipe; ++i)
       {
         ORBX_CUDA(c, cudaEventRecord(c->join_ev[i], c->pipe[i]));
         ORBX_CUDA(c, cudaStreamWaitEvent(c->stream, c->join_ev[i], 0));
@@ -767,17 +771,17 @@ extern "C"
     }
     // Chunks of kChunk frames round-robin over the pipeline streams: the H2D copy of chunk k+1 and the D2H copy of chunk
     // k-1 overlap the kernels of chunk k.  A single chunk runs on the context's stream (single-frame latency path).
-    const bool piped = n_frames > orbx_ctx::kChunk;
+    const bool piped = n_frames > c->kChunk;
     if (piped)
     {
       ORBX_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
-      for (auto &ps : c->pipe) ORBX_CUDA(c, cudaStreamWaitEvent(ps, c->fork_ev, 0));
+      for (int i = 0; i < c->kPipe; ++i) ORBX_CUDA(c, cudaStreamWaitEvent(c->pipe[i], c->fork_ev, 0));
     }
     int k = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += orbx_ctx::kChunk, ++k)
+    for (int f0 = 0; f0 < n_frames; f0 += c->kChunk, ++k)
     {
-      const int nf = std::min(orbx_ctx::kChunk, n_frames - f0);
-      cudaStream_t s = piped ? c->pipe[k % orbx_ctx::kPipe] : c->stream;
+      const int nf = std::min(c->kChunk, n_frames - f0);
+      cudaStream_t s = piped ? c->pipe[k % c->kPipe] : c->stream;
       if (linear)
       {
         ORBX_CUDA(c, cudaMemcpyAsync(dl + f0 * fs, left + f0 * frame_stride, fs * nf, cudaMemcpyHostToDevice, s));
@@ -806,7 +810,7 @@ extern "C"
       if (n_matches) ORBX_CUDA(c, cudaMemcpyAsync(n_matches + f0, p.n_matches + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s));
     }
     if (piped)
-      for (auto &ps : c->pipe) ORBX_CUDA(c, cudaStreamSynchronize(ps));
+      for (int i = 0; i < c->kPipe; ++i) ORBX_CUDA(c, cudaStreamSynchronize(c->pipe[i]));
     else
       ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     c->last_images = 2 * n_frames;

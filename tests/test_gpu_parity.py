@@ -129,6 +129,8 @@ STEREO = [
     ("K2000_d17", synth.KITTI, 2000, 0, 17),
     ("K2000_d5", synth.KITTI, 2000, 1, 5),
     ("K1000_d63", synth.KITTI, 1000, 2, 63),
+    ("K500_d42", synth.KITTI, 500, 5, 42),    # BASELINE.json configs[3]: 500/1000/2000/4000 features
+    ("K4000_d17", synth.KITTI, 4000, 6, 17),
     ("T1000_d17", synth.TUM, 1000, 3, 17),
     ("H5000_d42", synth.HD, 5000, 4, 42),
 ]
@@ -199,6 +201,34 @@ def test_rgbd_matches_oracle(oracle, use_dist, dtype):
     assert np.array_equal(r.depth, dp)
     assert np.abs(r.u_right - ur).max() <= 1e-3
     assert 0.05 < (dp < 0).mean() < 0.2  # ~10 % invalid depth pixels
+    ctx.close()
+
+
+def test_sequence_sharded_batches_equal_oracle(oracle):
+    """BASELINE.json configs[2] in miniature: a frame sequence split into per-rank blocks (shard.frame_range), each block
+    run through the batch call; every frame's descriptors must equal the oracle's regardless of its position in a batch"""
+    from orb_slam2_ros2_b200 import shard
+
+    c = synth.KITTI
+    F, R, B = 11, 2, 4
+    lefts, rights = synth.synth_stereo_pool(c["height"], c["width"], F, seed0=70)
+    ctx = api.Context(c["width"], c["height"], 500, 8, 1.2, camera=_camera(c), max_batch=B)
+    got_desc = np.zeros((F, 500, 32), np.uint8)
+    got_n = np.zeros(F, np.int32)
+    got_nm = np.zeros(F, np.int32)
+    for rank in range(R):
+        frames = list(shard.frame_range(F, rank, R))
+        for i in range(0, len(frames), B):
+            blk = frames[i : i + B]
+            ob = ctx.stereo_batch(lefts[blk[0] : blk[-1] + 1], rights[blk[0] : blk[-1] + 1])
+            got_desc[blk] = ob.desc_left
+            got_n[blk] = ob.n_left
+            got_nm[blk] = ob.n_matches
+    for f in (0, 5, 10):
+        el, er = oracle.extract(lefts[f], 500), oracle.extract(rights[f], 500)
+        assert got_n[f] == len(el.kps) and np.array_equal(got_desc[f, : got_n[f]], el.desc)
+        nm, _, _, _ = oracle.search_by_stereo(el, er, np.float32(c["fx"]), _camera(c).bf)
+        assert got_nm[f] == nm
     ctx.close()
 
 
