@@ -261,11 +261,20 @@ int build_tables(orbx_ctx *c)
   {
     int max_list = 0;
     for (auto &L : c->levels) max_list = std::max(max_list, L.list_cap);
-    const int cap = std::min(3584, std::max(64, max_list)); // 4 CTAs per SM at the KITTI configuration
     p.qt_big_cap = max_list / 256 + kMaxStrips + 16;
     int max_cells = 0;
     for (auto &L : c->levels) max_cells = std::max(max_cells, L.n_level_cells);
     p.qt_cell_cap = max_cells + 1;
+    // Corners kept in shared memory: 3584 (4 CTAs per SM at the KITTI configuration) for images up to ~1 MP; larger images
+    // produce proportionally more corners per level (~1 per 140-200 px on textured input), so they trade occupancy for a
+    // list that fits: up to 160 KB per CTA.  Denser levels still work, through the global-scratch path.
+    int cap = std::min(3584, std::max(64, max_list));
+    if ((long long)g.width * g.height / 140 > 3584)
+    {
+      const size_t fixed = quadtree_smem_bytes(0, p.qt_node_cap, p.qt_big_cap, p.qt_cell_cap);
+      const size_t budget = 160 * 1024;
+      if (budget > fixed + 8 * 3584) cap = std::min(max_list, (int)((budget - fixed) / 8) & ~255);
+    }
     const size_t bytes = quadtree_smem_bytes(cap, p.qt_node_cap, p.qt_big_cap, p.qt_cell_cap);
     if (bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree shared-memory pool");
     p.qt_smem_cap = cap;
