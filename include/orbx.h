@@ -176,6 +176,11 @@ int orbx_debug_level_corners(orbx_ctx *ctx, int image, int level, int32_t *xs, i
 /* quadtree survivors of one level (level coordinates, ascending detection index): Quadtree::getFeatIdxs (:378-386) */
 int orbx_debug_level_selected(orbx_ctx *ctx, int image, int level, int32_t *xs, int32_t *ys, int32_t *scores, int cap,
                               int32_t *n);
+/* Runs ONLY the quadtree kernel (Quadtree::split + nodes2kpoints, src/ORBExtractor.cc:126-192) of image 0 on a caller-
+ * supplied corner list for `level` (ROI coordinates, detection order; the other levels get no corners), so that the
+ * kernel can be checked against the reference on arbitrary inputs: corners on split lines, starved levels, deep nodes.
+ * Read the result with orbx_debug_level_selected(ctx, 0, level, ...). */
+int orbx_debug_run_quadtree(orbx_ctx *ctx, int level, const int32_t *xs, const int32_t *ys, const int32_t *scores, int n);
 
 #ifdef __cplusplus
 }

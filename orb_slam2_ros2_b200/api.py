@@ -69,7 +69,7 @@ EXPORTS = [
     "orbx_default_config", "orbx_create", "orbx_destroy", "orbx_status_string", "orbx_last_error", "orbx_load_brief_template", "orbx_set_stream",
     "orbx_num_levels", "orbx_level_info", "orbx_extract", "orbx_get_pyramid", "orbx_stereo_frame", "orbx_rgbd_frame", "orbx_stereo_batch",
     "orbx_stereo_batch_device", "orbx_extract_batch_device", "orbx_rgbd_batch_device", "orbx_synchronize", "orbx_launch_count", "orbx_algorithmic_bytes",
-    "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name",
+    "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name", "orbx_debug_run_quadtree",
 ]
 
 _lib = None
@@ -120,6 +120,7 @@ def load_library(build_if_missing: bool = True):
     L.orbx_algorithmic_bytes.restype = C.c_int64
     L.orbx_debug_level_corners.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
     L.orbx_debug_level_selected.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+    L.orbx_debug_run_quadtree.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int]
     _lib = L
     return L
 
@@ -299,6 +300,14 @@ class Context:
     def level_selected(self, image: int, level: int) -> np.ndarray:
         """(n,3) int32 (x, y, score) in level coordinates: the quadtree survivors of the level"""
         return self._debug_list(self._L.orbx_debug_level_selected, image, level, self.n_features + 8)
+
+    def run_quadtree(self, level: int, xs, ys, scores) -> np.ndarray:
+        """run only the quadtree kernel on a corner list (ROI coords, detection order) -> (m,3) survivors in ROI coords"""
+        xs, ys, sc = (np.ascontiguousarray(a, np.int32) for a in (xs, ys, scores))
+        _check(self._h, self._L.orbx_debug_run_quadtree(self._h, level, xs.ctypes.data, ys.ctypes.data, sc.ctypes.data, len(xs)), "orbx_debug_run_quadtree")
+        sel = self.level_selected(0, level)
+        sel[:, :2] -= 16
+        return sel
 
     # ---- batches ----------------------------------------------------------------------------------------------------
     def stereo_batch(self, left: np.ndarray, right: np.ndarray, out: "StereoBatchBuffers | None" = None):

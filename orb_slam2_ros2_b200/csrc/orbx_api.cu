@@ -959,4 +959,37 @@ extern "C"
     return ORBX_OK;
   }
 
+  int orbx_debug_run_quadtree(orbx_ctx *c, int level, const int32_t *xs, const int32_t *ys, const int32_t *scores, int n)
+  {
+    if (!c || level < 0 || level >= c->cfg.n_levels || n < 0 || (n > 0 && (!xs || !ys || !scores))) return ORBX_ERR_INVALID_ARG;
+    const Level &L = c->levels[level];
+    if (n > L.list_cap) return fail(c, ORBX_ERR_CAPACITY, "more corners than the level's cell slots can hold");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    // spread the list over the level's cell slots in order: the kernel concatenates them back in the same order
+    std::vector<int> cnt(c->p.n_cells, 0);
+    ORBX_CUDA(c, cudaMemcpy(c->p.cell_cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    int k = 0;
+    for (int ci = 0; ci < L.n_level_cells && k < n; ++ci)
+    {
+      const Cell &ce = c->cells[L.cell_base + ci];
+      const int m = std::min(ce.cap, n - k);
+      std::vector<uint32_t> buf(m);
+      for (int j = 0; j < m; ++j, ++k)
+      {
+        if (xs[k] < 0 || xs[k] > 4095 || ys[k] < 0 || ys[k] > 4095 || scores[k] < 0 || scores[k] > 255) return ORBX_ERR_INVALID_ARG;
+        buf[j] = (uint32_t)xs[k] | ((uint32_t)ys[k] << 12) | ((uint32_t)scores[k] << 24);
+      }
+      cnt[L.cell_base + ci] = m;
+      ORBX_CUDA(c, cudaMemcpy(c->p.cell_list + ce.slot, buf.data(), (size_t)m * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    ORBX_CUDA(c, cudaMemcpy(c->p.cell_cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    launch_quadtree(c->p, 1, c->qt_smem, c->stream);
+    c->launches += 1;
+    ORBX_CUDA(c, cudaGetLastError());
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->last_images = std::max(c->last_images, 1);
+    return ORBX_OK;
+  }
+
 } // extern "C"

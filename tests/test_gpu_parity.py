@@ -63,6 +63,29 @@ def test_extract_matches_oracle(oracle, cfg):
     ctx.close()
 
 
+@pytest.mark.parametrize("kind", ["texture", "noise", "lowcontrast"])
+def test_fast_and_quadtree_stages_match_oracle(oracle, kind):
+    """stage-level parity: the per-level FAST corner lists (detection order, scores) and the quadtree survivors"""
+    if kind == "texture":
+        img = synth.synth_image(376, 1241, 7)
+    elif kind == "noise":
+        img = np.random.default_rng(3).integers(0, 256, (376, 1241), dtype=np.uint8)
+    else:
+        img = (synth.synth_image(376, 1241, 8).astype(np.float32) * 0.3 + 80).astype(np.uint8)
+    ctx = api.Context(1241, 376, 2000, 8, 1.2)
+    ctx.extract(img)
+    e = oracle.extract(img)
+    for l in range(8):
+        got = ctx.level_corners(0, l)
+        exp, _ = oracle.fast_cells(e.pyr.level(l))
+        assert np.array_equal(got, exp), f"{kind}: FAST list of level {l}: {len(got)} vs {len(exp)}"
+        w, h, _, quota = ctx.level_info(l)
+        idx, _ = oracle.quadtree_select(w - 32, h - 32, exp[:, 0].astype(np.float32), exp[:, 1].astype(np.float32), exp[:, 2].astype(np.float32), quota)
+        sel = ctx.level_selected(0, l)
+        assert np.array_equal(sel, exp[idx] + np.array([16, 16, 0], np.int32)), f"{kind}: quadtree survivors of level {l}"
+    ctx.close()
+
+
 def test_degenerate_images(oracle):
     ctx = api.Context(320, 240, 1000, 4, 1.2)
     kps, desc = ctx.extract(np.zeros((240, 320), np.uint8))
