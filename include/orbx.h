@@ -115,6 +115,13 @@ int orbx_rgbd_frame(orbx_ctx *ctx, const uint8_t *gray, size_t gray_stride, cons
                     size_t depth_stride_bytes, int depth_type, orbx_keypoint *kps_raw, orbx_keypoint *kps,
                     uint8_t *desc, int32_t *n, double *u_right, double *depth);
 
+/* replaces: VirtualFrame::initGrid (src/Frame.cc:53-69, called by both Frame ctors) for frame `frame` of the most recent
+ * call: the 64x48-px bucket grid over the (undistorted) left keypoints, as a CSR.  rows/cols and the undistorted image
+ * bounds mfMinU/mfMinV/mfMaxU/mfMaxV (include/ORB_SLAM2/Frame.h:33-43) come from orbx_grid_info.  cell_start has
+ * rows*cols+1 entries; cell (r, c) lists entries[cell_start[r*cols+c] .. cell_start[r*cols+c+1]) in ascending order. */
+int orbx_grid_info(const orbx_ctx *ctx, int32_t *rows, int32_t *cols, float *min_u, float *min_v, float *max_u, float *max_v);
+int orbx_get_grid(orbx_ctx *ctx, int frame, int32_t *cell_start, int32_t *entries /* [n_features] */);
+
 /* ---- batches (offline map / vocabulary building: frames are independent) -------------------------------- */
 /* n_frames <= max_batch stereo pairs from HOST memory (pinned memory makes the copies asynchronous).
  * left/right: frame f at base + f * frame_stride bytes, rows `stride` bytes apart.  Outputs are fixed-stride arrays:
@@ -136,6 +143,9 @@ typedef struct orbx_device_results {
   const double *depth;          /* [n_frames][n_features] */
   const int32_t *n_matches;     /* [n_frames] */
   int32_t n_images, n_frames, n_features;
+  const int32_t *grid_start;    /* [n_frames][grid_rows * grid_cols + 1]  CSR of VirtualFrame::mGrids (src/Frame.cc:53-69) */
+  const uint16_t *grid_entries; /* [n_frames][n_features] keypoint indices, ascending inside a cell */
+  int32_t grid_rows, grid_cols;
 } orbx_device_results;
 
 /* same work as orbx_stereo_batch with inputs already in DEVICE memory; asynchronous on the context's stream

@@ -233,6 +233,7 @@ public:
   {
     (void)pVoc;
     SharedPtr f(new Frame());
+    f->mCapacity = nFeatures;
     f->mLeftIm = colorImg;
     f->mCtx = detail::context_for(colorImg.cols, colorImg.rows, nFeatures, nLevels, scale, briefF, maxThresh, minThresh, dScale);
     const int dtype = depthImg.type() == CV_32F ? ORBX_DEPTH_F32 : ORBX_DEPTH_U16;
@@ -262,12 +263,29 @@ public:
   const std::vector<double> &getRightU() const { return mvFeatsRightU; }
   const cv::Mat &getLeftImage() const { return mLeftIm; }
   const cv::Mat &getRightImage() const { return mRightIm; }
+  // VirtualFrame::mGrids (include/ORB_SLAM2/Frame.h:289, built by initGrid src/Frame.cc:53-69): [row][col] -> keypoint indices
+  typedef std::vector<std::vector<std::vector<std::size_t>>> GridsType;
+  GridsType getGrids() const
+  {
+    int32_t rows = 0, cols = 0;
+    detail::check(mCtx.get(), orbx_grid_info(mCtx.get(), &rows, &cols, nullptr, nullptr, nullptr, nullptr), "orbx_grid_info");
+    std::vector<int32_t> start((size_t)rows * cols + 1);
+    std::vector<int32_t> all((size_t)orbx_capacity());
+    detail::check(mCtx.get(), orbx_get_grid(mCtx.get(), 0, start.data(), all.data()), "orbx_get_grid");
+    GridsType g((size_t)rows, std::vector<std::vector<std::size_t>>((size_t)cols));
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c)
+        for (int i = start[(size_t)r * cols + c]; i < start[(size_t)r * cols + c + 1]; ++i) g[(size_t)r][(size_t)c].push_back((std::size_t)all[(size_t)i]);
+    return g;
+  }
   std::vector<cv::Mat> getLeftPyramid() const { return detail::fetch_pyramid(mCtx.get(), 0); }
   std::vector<cv::Mat> getRightPyramid() const { return detail::fetch_pyramid(mCtx.get(), 1); }
   int getN() const { return mnN; }
 
 private:
   Frame() = default;
+  int orbx_capacity() const { return mCapacity; }
+  int mCapacity = 0; // nFeatures of the context: size of the fixed-stride result arrays
   std::vector<cv::KeyPoint> mvFeatsLeft, mvFeatsRight;
   std::vector<cv::Mat> mvLeftDescriptor, mRightDescriptor;
   std::vector<double> mvDepths, mvFeatsRightU;
@@ -299,6 +317,7 @@ inline Frame::SharedPtr Frame::createStereo(cv::Mat leftImg, cv::Mat rightImg, i
 {
   (void)pVoc;
   SharedPtr f(new Frame());
+  f->mCapacity = nFeatures;
   f->mLeftIm = leftImg;
   f->mRightIm = rightImg;
   f->mCtx = detail::context_for(leftImg.cols, leftImg.rows, nFeatures, nLevels, scale, briefFp, maxThresh, minThresh, 1.f);

@@ -29,10 +29,8 @@ f64p = C.POINTER(C.c_double)
 
 
 def build(force: bool = False) -> None:
-    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
-    if force or not os.path.exists(ORACLE_SO) or (os.path.isdir("/root/reference") and not os.path.exists(REF_SO)):
-        subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
-    elif os.path.isdir("/root/reference"):
+    """Compile the oracle (and oracle/_ref when /root/reference is present); `make` is incremental."""
+    if force or not os.path.exists(ORACLE_SO) or os.path.isdir("/root/reference"):
         subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
 
 
@@ -284,6 +282,23 @@ def rgbd_lookup(depth_img: np.ndarray, depth_scale: float, kps_raw: np.ndarray, 
     lib().oracle_rgbd_lookup(d.ctypes.data, int(is_float), d.shape[1], d.shape[0], d.strides[0] // d.itemsize, depth_scale, kr.ctypes.data, ku.ctypes.data,
                              n, bf, _ptr(ur, f64p), _ptr(dp, f64p))
     return ur[:n], dp[:n]
+
+
+def init_grid(kps: np.ndarray, min_u, min_v, max_u, max_v):
+    """VirtualFrame::initGrid (src/Frame.cc:53-69), numpy restatement: rows = cvCeil((float)(maxV - minV) / 48), cols =
+    cvCeil((float)(maxU - minU) / 64); keypoint i goes to cell (cvFloor(pt.y / 48), cvFloor(pt.x / 64)), float division,
+    in keypoint order.  (Frame.cc cannot be compiled in isolation -- DBoW3 / KeyFrame dependencies -- so this piece is a
+    restatement only.)  -> list[rows][cols] of index arrays"""
+    f32 = np.float32
+    rows = int(np.ceil(f32(f32(max_v) - f32(min_v)) / f32(48)))
+    cols = int(np.ceil(f32(f32(max_u) - f32(min_u)) / f32(64)))
+    grid = [[[] for _ in range(cols)] for _ in range(rows)]
+    r = np.floor(kps["y"].astype(f32) / f32(48)).astype(np.int64)
+    c = np.floor(kps["x"].astype(f32) / f32(64)).astype(np.int64)
+    for i in range(len(kps)):
+        if 0 <= r[i] < rows and 0 <= c[i] < cols:  # anything else indexes mGrids out of range in the reference
+            grid[r[i]][c[i]].append(i)
+    return [[np.asarray(cell, np.int32) for cell in row] for row in grid]
 
 
 # ----------------------------------------------------------------------------------------------------------------

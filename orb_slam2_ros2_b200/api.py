@@ -62,6 +62,7 @@ class OrbxDeviceResults(C.Structure):
     _fields_ = [
         ("kps", C.c_void_p), ("kps_und", C.c_void_p), ("desc", C.c_void_p), ("n_kps", C.c_void_p), ("u_right", C.c_void_p), ("depth", C.c_void_p),
         ("n_matches", C.c_void_p), ("n_images", C.c_int32), ("n_frames", C.c_int32), ("n_features", C.c_int32),
+        ("grid_start", C.c_void_p), ("grid_entries", C.c_void_p), ("grid_rows", C.c_int32), ("grid_cols", C.c_int32),
     ]
 
 
@@ -69,7 +70,7 @@ EXPORTS = [
     "orbx_default_config", "orbx_create", "orbx_destroy", "orbx_status_string", "orbx_last_error", "orbx_load_brief_template", "orbx_set_stream",
     "orbx_num_levels", "orbx_level_info", "orbx_extract", "orbx_get_pyramid", "orbx_stereo_frame", "orbx_rgbd_frame", "orbx_stereo_batch",
     "orbx_stereo_batch_device", "orbx_extract_batch_device", "orbx_rgbd_batch_device", "orbx_synchronize", "orbx_launch_count", "orbx_algorithmic_bytes",
-    "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name", "orbx_debug_run_quadtree",
+    "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name", "orbx_debug_run_quadtree", "orbx_grid_info", "orbx_get_grid",
 ]
 
 _lib = None
@@ -121,6 +122,8 @@ def load_library(build_if_missing: bool = True):
     L.orbx_debug_level_corners.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
     L.orbx_debug_level_selected.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
     L.orbx_debug_run_quadtree.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int]
+    L.orbx_grid_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)] + [C.POINTER(C.c_float)] * 4
+    L.orbx_get_grid.argtypes = [vp, C.c_int, vp, vp]
     _lib = L
     return L
 
@@ -300,6 +303,21 @@ class Context:
     def level_selected(self, image: int, level: int) -> np.ndarray:
         """(n,3) int32 (x, y, score) in level coordinates: the quadtree survivors of the level"""
         return self._debug_list(self._L.orbx_debug_level_selected, image, level, self.n_features + 8)
+
+    def grid_info(self):
+        """(rows, cols, mfMinU, mfMinV, mfMaxU, mfMaxV) of VirtualFrame (include/ORB_SLAM2/Frame.h:33-43, src/Frame.cc:55-56)"""
+        r, c = C.c_int32(), C.c_int32()
+        b = [C.c_float() for _ in range(4)]
+        _check(self._h, self._L.orbx_grid_info(self._h, C.byref(r), C.byref(c), *[C.byref(x) for x in b]), "orbx_grid_info")
+        return (r.value, c.value, *[np.float32(x.value) for x in b])
+
+    def get_grid(self, frame: int = 0):
+        """VirtualFrame::mGrids of a frame of the last stereo / RGB-D call: list[rows][cols] of ascending keypoint indices"""
+        rows, cols = self.grid_info()[:2]
+        start = np.zeros(rows * cols + 1, np.int32)
+        ent = np.zeros(self.n_features, np.int32)
+        _check(self._h, self._L.orbx_get_grid(self._h, frame, start.ctypes.data, ent.ctypes.data), "orbx_get_grid")
+        return [[ent[start[r * cols + c] : start[r * cols + c + 1]].copy() for c in range(cols)] for r in range(rows)]
 
     def run_quadtree(self, level: int, xs, ys, scores) -> np.ndarray:
         """run only the quadtree kernel on a corner list (ROI coords, detection order) -> (m,3) survivors in ROI coords"""

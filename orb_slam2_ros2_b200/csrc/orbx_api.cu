@@ -40,6 +40,8 @@ struct orbx_ctx
   uint8_t *d_depth_in = nullptr; // [max_batch][H][W] float/uint16 (sized for float)
   int last_images = 0;          // images processed by the most recent call (for orbx_get_pyramid)
   int last_stereo = 0;
+  int last_frames = 0;
+  float min_u = 0, min_v = 0, max_u = 0, max_v = 0; // undistorted image bounds (VirtualFrame ctor, Frame.h:33-43)
   // host-batch pipeline: chunks of frames round-robin over kPipe streams so that H2D, kernels and D2H overlap
   static constexpr int kPipeMax = 8;
   int kPipe = 8;  // streams (tunable for experiments: ORBX_PIPE); 8 x 8 frames measured best on B200
@@ -288,6 +290,34 @@ int build_tables(orbx_ctx *c)
   p.depth_scale_inv = (float)(1.0 / (double)(g.depth_scale != 0.f ? g.depth_scale : 1.f)); // Mat /= s == convertTo(.., 1./s)
   for (int i = 0; i < 5; ++i) p.dist[i] = g.dist[i];
   p.undistort = g.dist[0] != 0.f ? 1 : 0; // Camera::undistortPoints returns early when k1 == 0 (src/Camera.cc:31)
+  {
+    // VirtualFrame ctor (include/ORB_SLAM2/Frame.h:33-43): undistort (0,0) and (width,height); grid size (src/Frame.cc:55-56)
+    float b[4] = {0.f, 0.f, (float)g.width, (float)g.height};
+    if (p.undistort)
+      for (int i = 0; i < 2; ++i)
+      { // cv::undistortPoints with P = K: 5 fixed-point iterations in double
+        const double fx = g.fx, fy = g.fy, cx = g.cx, cy = g.cy, k1 = g.dist[0], k2 = g.dist[1], p1 = g.dist[2], p2 = g.dist[3], k3 = g.dist[4];
+        double x = ((double)b[2 * i] - cx) * (1. / fx), y = ((double)b[2 * i + 1] - cy) * (1. / fy);
+        const double x0 = x, y0 = y;
+        for (int it = 0; it < 5; ++it)
+        {
+          const double r2 = x * x + y * y, icd = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+          const double dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x), dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+          x = (x0 - dx) * icd;
+          y = (y0 - dy) * icd;
+        }
+        b[2 * i] = (float)(x * fx + cx);
+        b[2 * i + 1] = (float)(y * fy + cy);
+      }
+    c->min_u = b[0];
+    c->min_v = b[1];
+    c->max_u = b[2];
+    c->max_v = b[3];
+    const float fr = (float)(c->max_v - c->min_v) / 48.f, fc = (float)(c->max_u - c->min_u) / 64.f;
+    p.grid_rows = std::max(1, (int)std::ceil(fr));
+    p.grid_cols = std::max(1, (int)std::ceil(fc));
+    if ((long long)p.grid_rows * p.grid_cols > 10000) return fail(c, ORBX_ERR_INVALID_ARG, "undistorted image bounds are degenerate");
+  }
 
   // pattern: float pairs -> int8 (the template file holds integers, :262)
   std::vector<char4> pat(256);
@@ -351,6 +381,8 @@ int alloc_buffers(orbx_ctx *c)
   if ((rc = dev_alloc(c, &p.u_right, ni * N))) return rc; // sized per image so that mono batches can use it too
   if ((rc = dev_alloc(c, &p.depth, ni * N))) return rc;
   if ((rc = dev_alloc(c, &p.n_matches, ni))) return rc;
+  if ((rc = dev_alloc(c, &p.grid_start, ni * ((size_t)p.grid_rows * p.grid_cols + 1)))) return rc;
+  if ((rc = dev_alloc(c, &p.grid_entries, ni * N))) return rc;
   c->in_pitch = ((size_t)c->cfg.width + 15) & ~(size_t)15;
   if ((rc = dev_alloc(c, &c->d_in, ni * c->in_pitch * (size_t)c->cfg.height))) return rc;
   if ((rc = dev_alloc(c, &c->d_depth_in, nf * (size_t)c->cfg.width * (size_t)c->cfg.height * 4))) return rc;
@@ -381,6 +413,8 @@ Params params_at(const orbx_ctx *c, int img0, int frame0)
   p.u_right += f * N;
   p.depth += f * N;
   p.n_matches += f;
+  p.grid_start += f * ((size_t)p.grid_rows * p.grid_cols + 1);
+  p.grid_entries += f * N;
   return p;
 }
 
@@ -400,7 +434,8 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
   launch_orient_brief(p, 2 * nf, s);
   launch_rowindex(p, nf, s);
   launch_stereo(p, nf, s);
-  c->launches += 6;
+  launch_grid(p, nf, 2, s);
+  c->launches += 7;
   ORBX_CUDA(c, cudaGetLastError());
   return ORBX_OK;
 }
@@ -430,6 +465,10 @@ void fill_results(orbx_ctx *c, int n_images, int n_frames, orbx_device_results *
   out->n_images = n_images;
   out->n_frames = n_frames;
   out->n_features = c->cfg.n_features;
+  out->grid_start = c->p.grid_start;
+  out->grid_entries = c->p.grid_entries;
+  out->grid_rows = c->p.grid_rows;
+  out->grid_cols = c->p.grid_cols;
 }
 
 } // namespace
@@ -680,6 +719,7 @@ extern "C"
     }
     c->last_images = 2 * n_frames;
     c->last_stereo = 1;
+    c->last_frames = n_frames;
     fill_results(c, 2 * n_frames, n_frames, out);
     return ORBX_OK;
   }
@@ -719,13 +759,15 @@ extern "C"
     ORBX_CUDA(c, cudaEventRecord(ev[5], c->stream));
     launch_stereo(p, n_frames, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[6], c->stream));
-    c->launches += 6;
+    launch_grid(p, n_frames, 2, c->stream);
+    c->launches += 7;
     ORBX_CUDA(c, cudaGetLastError());
-    ORBX_CUDA(c, cudaEventSynchronize(ev[6]));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int i = 0; i < ORBX_N_STAGES; ++i) ORBX_CUDA(c, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
     for (auto &e : ev) cudaEventDestroy(e);
     c->last_images = ni;
     c->last_stereo = 1;
+    c->last_frames = n_frames;
     return ORBX_OK;
   }
 
@@ -748,10 +790,12 @@ extern "C"
     if (rc) return rc;
     ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)n_frames * sizeof(int), c->stream));
     launch_rgbd(p, n_frames, c->stream);
-    c->launches += 1;
+    launch_grid(p, n_frames, 1, c->stream);
+    c->launches += 2;
     ORBX_CUDA(c, cudaGetLastError());
     c->last_images = n_frames;
     c->last_stereo = 0;
+    c->last_frames = n_frames;
     fill_results(c, n_frames, n_frames, out);
     return ORBX_OK;
   }
@@ -824,6 +868,7 @@ extern "C"
       ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     c->last_images = 2 * n_frames;
     c->last_stereo = 1;
+    c->last_frames = n_frames;
     return ORBX_OK;
   }
 
@@ -905,6 +950,33 @@ extern "C"
     const uint8_t *src = (blurred ? c->p.blur : c->p.pyr) + (size_t)side * c->p.pyr_img_stride + L.pyr_off;
     ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     ORBX_CUDA(c, cudaMemcpy2D(dst, dst_stride, src, (size_t)L.pitch, (size_t)L.w, (size_t)L.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+  }
+
+  int orbx_grid_info(const orbx_ctx *c, int32_t *rows, int32_t *cols, float *min_u, float *min_v, float *max_u, float *max_v)
+  {
+    if (!c) return ORBX_ERR_INVALID_ARG;
+    if (rows) *rows = c->p.grid_rows;
+    if (cols) *cols = c->p.grid_cols;
+    if (min_u) *min_u = c->min_u;
+    if (min_v) *min_v = c->min_v;
+    if (max_u) *max_u = c->max_u;
+    if (max_v) *max_v = c->max_v;
+    return ORBX_OK;
+  }
+
+  int orbx_get_grid(orbx_ctx *c, int frame, int32_t *cell_start, int32_t *entries)
+  {
+    if (!c || frame < 0 || !cell_start || !entries) return ORBX_ERR_INVALID_ARG;
+    if (frame >= c->last_frames) return fail(c, ORBX_ERR_STATE, "no frame with that index has a grid (stereo / RGB-D calls build it)");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t nc = (size_t)c->p.grid_rows * c->p.grid_cols, N = (size_t)c->cfg.n_features;
+    ORBX_CUDA(c, cudaMemcpy(cell_start, c->p.grid_start + (size_t)frame * (nc + 1), (nc + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> e16(N);
+    ORBX_CUDA(c, cudaMemcpy(e16.data(), c->p.grid_entries + (size_t)frame * N, N * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    const int total = cell_start[nc];
+    for (int i = 0; i < total && i < (int)N; ++i) entries[i] = e16[i];
     return ORBX_OK;
   }
 

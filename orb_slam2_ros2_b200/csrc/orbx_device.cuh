@@ -118,6 +118,10 @@ struct Params
   int row_cap;
   double *u_right, *depth;
   int *n_matches;
+  // VirtualFrame::initGrid (src/Frame.cc:53-69): CSR over the 64x48-px grid cells of the (undistorted) left keypoints
+  int *grid_start;        // [frame][grid_rows * grid_cols + 1]
+  uint16_t *grid_entries; // [frame][n_features], ascending keypoint index inside a cell
+  int grid_rows, grid_cols;
   // camera
   float fx, fy, cx, cy, bf, depth_scale_inv;
   float dist[5];
@@ -132,6 +136,7 @@ void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
 void launch_rowindex(const Params &p, int n_frames, cudaStream_t s);
 void launch_stereo(const Params &p, int n_frames, cudaStream_t s);
 void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
+void launch_grid(const Params &p, int n_frames, int image_stride, cudaStream_t s);
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells);
 int quadtree_configure(size_t smem_bytes); // opt in to large dynamic shared memory
 

@@ -1622,4 +1622,78 @@ void launch_rgbd(const Params &p, int n_frames, cudaStream_t s)
   rgbd_kernel<<<grid, 128, 0, s>>>(p);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K7: VirtualFrame::initGrid (src/Frame.cc:53-69): bucket the frame's (undistorted) left keypoints into 64x48-px cells,
+// rowIdx = cvFloor(pt.y / 48), colIdx = cvFloor(pt.x / 64) in float; a cell lists its keypoints in ascending index order
+// (the reference push_backs them in keypoint order).  One CTA per frame: histogram, scan, fill, per-cell sort.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGridThreads = 256;
+
+__global__ void __launch_bounds__(kGridThreads) grid_kernel(const Params p, int image_stride)
+{
+  extern __shared__ int s_cell[]; // [n_cells + 1]
+  __shared__ int s_warp[kGridThreads / 32];
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int img = frame * image_stride;
+  const int nc = p.grid_rows * p.grid_cols;
+  const int n = p.n_kps[img];
+  const orbx_keypoint *kps = p.kps_und + (size_t)img * p.n_features;
+  int *start = p.grid_start + (size_t)frame * (nc + 1);
+  uint16_t *entries = p.grid_entries + (size_t)frame * p.n_features;
+  auto cell_of = [&](int i) -> int {
+    const int r = __float2int_rd(__fdiv_rn(kps[i].y, 48.f)), c = __float2int_rd(__fdiv_rn(kps[i].x, 64.f));
+    return (r >= 0 && r < p.grid_rows && c >= 0 && c < p.grid_cols) ? r * p.grid_cols + c : -1; // outside: UB in the reference
+  };
+  for (int i = tid; i <= nc; i += kGridThreads) s_cell[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += kGridThreads)
+  {
+    const int c = cell_of(i);
+    if (c >= 0) atomicAdd(&s_cell[c], 1);
+  }
+  __syncthreads();
+  const int per = (nc + kGridThreads - 1) / kGridThreads;
+  const int c0 = min(tid * per, nc), c1 = min(c0 + per, nc);
+  int mine = 0;
+  for (int c = c0; c < c1; ++c) mine += s_cell[c];
+  int total;
+  int off = block_exclusive_scan<kGridThreads>(mine, total, s_warp);
+  for (int c = c0; c < c1; ++c)
+  {
+    const int k = s_cell[c];
+    s_cell[c] = off;
+    start[c] = off;
+    off += k;
+  }
+  if (tid == 0) start[nc] = total;
+  __syncthreads();
+  for (int i = tid; i < n; i += kGridThreads)
+  {
+    const int c = cell_of(i);
+    if (c >= 0) entries[atomicAdd(&s_cell[c], 1)] = (uint16_t)i;
+  }
+  __syncthreads();
+  // ascending index order inside every cell (insertion sort; a cell holds a few dozen keypoints at most)
+  for (int c = tid; c < nc; c += kGridThreads)
+  {
+    const int b = start[c], e = s_cell[c];
+    for (int i = b + 1; i < e; ++i)
+    {
+      const uint16_t v = entries[i];
+      int j = i - 1;
+      while (j >= b && entries[j] > v)
+      {
+        entries[j + 1] = entries[j];
+        --j;
+      }
+      entries[j + 1] = v;
+    }
+  }
+}
+
+void launch_grid(const Params &p, int n_frames, int image_stride, cudaStream_t s)
+{
+  grid_kernel<<<n_frames, kGridThreads, (size_t)(p.grid_rows * p.grid_cols + 1) * sizeof(int), s>>>(p, image_stride);
+}
+
 } // namespace orbx

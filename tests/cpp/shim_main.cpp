@@ -82,6 +82,20 @@ int main(int argc, char **argv)
       put(out, (int32_t)f->getN());
       for (double v : f->getRightU()) put(out, v);
       for (double v : f->getDepth()) put(out, v);
+      // VirtualFrame::initGrid: every keypoint sits in exactly one cell, cells are ascending
+      auto grids = f->getGrids();
+      std::size_t total = 0;
+      bool ascending = true;
+      for (auto &row : grids)
+        for (auto &cell : row)
+        {
+          total += cell.size();
+          for (std::size_t i = 1; i < cell.size(); ++i) ascending = ascending && cell[i - 1] < cell[i];
+        }
+      put(out, (int32_t)grids.size());
+      put(out, (int32_t)grids[0].size());
+      put(out, (int32_t)total);
+      put(out, (int32_t)ascending);
     }
     else if (mode == "rgbd")
     {

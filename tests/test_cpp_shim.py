@@ -92,6 +92,7 @@ def test_shim_stereo_matches_oracle(shim_binary, template_path, oracle, tmp_path
     cam = api.Camera()
     nm, our, odp, _ = oracle.search_by_stereo(el, er, np.float32(cam.fx), cam.bf)
     assert n_matches == nm and np.abs(ur - our).max() <= 1e-3 and np.abs(dp - odp).max() <= 1e-3 * np.abs(odp).max()
+    assert (rd.i32(), rd.i32(), rd.i32(), rd.i32()) == (8, 20, len(kl), 1)  # mGrids: 8 x 20 cells, all keypoints, ascending
 
 
 @pytest.mark.gpu

@@ -255,6 +255,36 @@ def test_sequence_sharded_batches_equal_oracle(oracle):
     ctx.close()
 
 
+def test_init_grid_matches_restatement(oracle):
+    """VirtualFrame::initGrid (Frame.cc:53-69) for a stereo frame (KITTI, no distortion) and an RGB-D frame (TUM distortion)"""
+    c = synth.KITTI
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], 4, 17)
+    ctx = api.Context(c["width"], c["height"], 2000, 8, 1.2, camera=_camera(c))
+    r = ctx.stereo_frame(left, right)
+    rows, cols, mnu, mnv, mxu, mxv = ctx.grid_info()
+    assert (rows, cols, mnu, mnv, mxu, mxv) == (8, 20, 0.0, 0.0, 1241.0, 376.0)
+    got, exp = ctx.get_grid(0), oracle.init_grid(r.kps_left, mnu, mnv, mxu, mxv)
+    assert sum(len(x) for row in got for x in row) == len(r.kps_left)
+    for i in range(rows):
+        for j in range(cols):
+            assert np.array_equal(got[i][j], exp[i][j]), (i, j)
+    ctx.close()
+
+    c = synth.TUM
+    cam = _camera(c)
+    ctx = api.Context(c["width"], c["height"], 1000, 8, 1.2, camera=cam)
+    rg = ctx.rgbd_frame(synth.synth_image(c["height"], c["width"], 12), synth.synth_depth_u16(c["height"], c["width"], 12, c["depth_scale"]))
+    rows, cols, mnu, mnv, mxu, mxv = ctx.grid_info()
+    b = oracle.undistort_points(np.array([[0, 0], [c["width"], c["height"]]], np.float32), c["fx"], c["fy"], c["cx"], c["cy"], np.array(c["dist"], np.float32))
+    assert np.abs(np.array([mnu, mnv, mxu, mxv]) - b.reshape(-1)).max() <= 1e-3
+    got, exp = ctx.get_grid(0), oracle.init_grid(rg.kps, mnu, mnv, mxu, mxv)
+    assert len(got) == len(exp) and len(got[0]) == len(exp[0])
+    for i in range(rows):
+        for j in range(cols):
+            assert np.array_equal(got[i][j], exp[i][j]), (i, j)
+    ctx.close()
+
+
 def test_batch_equals_single_frames(oracle):
     c = synth.KITTI
     cam = _camera(c)
@@ -290,7 +320,7 @@ def test_device_batch_and_launch_count():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     before = ctx.launch_count
     res = ctx.stereo_batch_device(n, dl.data_ptr(), dr.data_ptr(), c["width"], c["width"] * c["height"])
-    assert ctx.launch_count - before == 6  # pyramid+blur, FAST, quadtree, orientation+BRIEF, row index, stereo (one chunk: n <= 8)
+    assert ctx.launch_count - before == 7  # pyramid+blur, FAST, quadtree, orientation+BRIEF, row index, stereo, grid (one chunk: n <= 8)
     nm = ctx.read_device(res.n_matches, (n,), np.int32)
     assert np.array_equal(nm, host.n_matches) and (nm > 500).all()
     desc = ctx.read_device(res.desc, (2 * n, 2000, 32), np.uint8)
