@@ -82,87 +82,93 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
 {
   __shared__ __align__(16) uint8_t s_src[kSrcH * kSrcPitch];
   __shared__ __align__(16) uint16_t s_h[kSrcH * kTileW];
-  __shared__ int s_ys[kSrcH];      // source row (or kOutside: beyond the level + halo, never read)
-  __shared__ short2 s_yc[kSrcH];   // vertical coefficients
+  __shared__ uint32_t s_r0[kSrcH], s_r1[kSrcH]; // byte offsets of the two source rows (kOutside: beyond the level + halo, never read)
+  __shared__ short2 s_yc[kSrcH];               // vertical coefficients
 
   const Tile t = p.tiles[blockIdx.x];
   const int img = blockIdx.y;
   const Level &L = p.levels[t.level];
   const int lw = L.w, lh = L.h, pitch = L.pitch;
   const uint8_t *__restrict__ src = input_image(p, img);
-  const size_t sstride = p.in_stride;
+  const uint32_t sstride = (uint32_t)p.in_stride;
   const int W = p.width, H = p.height;
   const int level = t.level, area2x = L.area2x;
   const int tid = threadIdx.x;
 
-  constexpr int kOutside = -(1 << 30);
+  constexpr uint32_t kOutside = 0xffffffffu;
   if (tid < kSrcH)
   {
     const int ry = t.y0 + tid - kHalo;
-    int sy = kOutside;
+    uint32_t o0 = kOutside, o1 = kOutside;
     short2 b = make_short2(0, 0);
     if (ry < lh + kHalo)
     {
       const int gy = refl101(ry, lh);
-      if (level == 0 || area2x)
-        sy = gy;
+      if (level == 0)
+        o0 = o1 = (uint32_t)gy * sstride;
+      else if (area2x)
+      {
+        o0 = (uint32_t)(2 * gy) * sstride;
+        o1 = o0 + sstride;
+      }
       else
       {
-        sy = p.tab_ofs[L.tab_y + gy];
+        const int sy = p.tab_ofs[L.tab_y + gy];
         b = p.tab_coef[L.tab_y + gy];
+        o0 = (uint32_t)min(max(sy, 0), H - 1) * sstride; // rows are clamped, not re-weighted (cv::resize)
+        o1 = (uint32_t)min(max(sy + 1, 0), H - 1) * sstride;
       }
     }
-    s_ys[tid] = sy;
+    s_r0[tid] = o0;
+    s_r1[tid] = o1;
     s_yc[tid] = b;
   }
   __syncthreads();
 
-  // stage A: the tile plus a 3-pixel halo of the (resized) level image, REFLECT_101 at the level's borders
+  // stage A: the tile plus a 3-pixel halo of the (resized) level image, REFLECT_101 at the level's borders.
+  // src is CTA-uniform and all offsets are 32-bit, so the loads use uniform-base + 32-bit-offset addressing.
   {
     const int col = tid % kSrcPitch, grp = tid / kSrcPitch;
     const int rx = t.x0 + col - kHalo;
     if (grp < kColGroups && col < kSrcW)
     {
       const bool col_ok = rx < lw + kHalo;
-      const int gx = col_ok ? refl101(rx, lw) : 0;
+      const uint32_t gx = col_ok ? (uint32_t)refl101(rx, lw) : 0u;
       if (level == 0)
       {
+#pragma unroll 4
         for (int ty = grp; ty < kSrcH; ty += kColGroups)
         {
-          const int sy = s_ys[ty];
-          s_src[ty * kSrcPitch + col] = (col_ok && sy != kOutside) ? src[(size_t)sy * sstride + gx] : (uint8_t)0;
+          const uint32_t o0 = s_r0[ty];
+          s_src[ty * kSrcPitch + col] = (col_ok && o0 != kOutside) ? src[o0 + gx] : (uint8_t)0;
         }
       }
       else if (area2x)
       {
         for (int ty = grp; ty < kSrcH; ty += kColGroups)
         {
-          const int sy = s_ys[ty];
+          const uint32_t o0 = s_r0[ty], o1 = s_r1[ty];
           int v = 0;
-          if (col_ok && sy != kOutside)
-          {
-            const uint8_t *s0 = src + (size_t)(2 * sy) * sstride + 2 * gx;
-            v = (s0[0] + s0[1] + s0[sstride] + s0[sstride + 1] + 2) >> 2;
-          }
+          if (col_ok && o0 != kOutside) v = (src[o0 + 2 * gx] + src[o0 + 2 * gx + 1] + src[o1 + 2 * gx] + src[o1 + 2 * gx + 1] + 2) >> 2;
           s_src[ty * kSrcPitch + col] = (uint8_t)v;
         }
       }
       else
       {
-        const int sx = col_ok ? p.tab_ofs[L.tab_x + gx] : 0;
+        const uint32_t sx = col_ok ? (uint32_t)p.tab_ofs[L.tab_x + gx] : 0u;
         const short2 a = col_ok ? p.tab_coef[L.tab_x + gx] : make_short2(0, 0);
-        const int sx1 = min(sx + 1, W - 1);
+        const uint32_t sx1 = min(sx + 1u, (uint32_t)(W - 1));
+        const int ax = a.x, ay = a.y;
+#pragma unroll 4
         for (int ty = grp; ty < kSrcH; ty += kColGroups)
         {
-          const int sy = s_ys[ty];
+          const uint32_t o0 = s_r0[ty], o1 = s_r1[ty];
           int v = 0;
-          if (col_ok && sy != kOutside)
+          if (col_ok && o0 != kOutside)
           {
             const short2 b = s_yc[ty];
-            const int sy0 = min(max(sy, 0), H - 1), sy1 = min(max(sy + 1, 0), H - 1);
-            const uint8_t *r0 = src + (size_t)sy0 * sstride, *r1 = src + (size_t)sy1 * sstride;
-            const int h0 = r0[sx] * a.x + r0[sx1] * a.y;
-            const int h1 = r1[sx] * a.x + r1[sx1] * a.y;
+            const int h0 = src[o0 + sx] * ax + src[o0 + sx1] * ay;
+            const int h1 = src[o1 + sx] * ax + src[o1 + sx1] * ay;
             v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
             v = min(max(v, 0), 255);
           }
@@ -326,7 +332,6 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
   __shared__ __align__(16) uint8_t s_map[(kZoneMax + 2) * kMapPitch + 16]; // + 16: zeroed with 16-byte stores
   __shared__ uint16_t s_cand[kFastWarps * kCandSeg];
   __shared__ unsigned long long s_keep_ini[kZoneMax], s_keep_min[kZoneMax];
-  __shared__ int s_wcnt[kFastWarps];
   __shared__ int s_warp[kFastWarps];
 
   const Cell c = p.cells[blockIdx.x];
@@ -399,18 +404,11 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
       wcnt += __popc(m);
     }
   }
-  if (lane == 0) s_wcnt[wid] = wcnt;
-  __syncthreads();
-  const int n0 = s_wcnt[0], n1 = n0 + s_wcnt[1], n2 = n1 + s_wcnt[2], ncand = n2 + s_wcnt[3];
-  static_assert(kFastWarps == 4, "candidate segment lookup assumes 4 warps");
-  auto cand_at = [&](int k) -> int {
-    const int seg = (k >= n0) + (k >= n1) + (k >= n2);
-    const int base = seg == 0 ? 0 : (seg == 1 ? n0 : (seg == 2 ? n1 : n2));
-    return s_cand[seg * kCandSeg + (k - base)];
-  };
-  for (int k = tid; k < ncand; k += kFastThreads)
+  // each warp evaluates the arc value of its own candidates (its segment is private, the patch is read-only)
+  __syncwarp();
+  for (int k = lane; k < wcnt; k += 32)
   {
-    const int i = cand_at(k);
+    const int i = my_cand[k];
     const int zy = i >> 6, zx = i & (kZoneMax - 1);
     const int m = fast_arc_value(pat0 + zy * kPatPitch + zx);
     if (m > tq) s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)m;
@@ -420,9 +418,9 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
   // Non-max suppression at both thresholds.  keep at t  <=>  m > t  and  m - 1 > max over the 8 neighbours of
   // (q > t ? q - 1 : 0); that map is monotone in q, so only the largest neighbour matters.
   const int t_ini = p.ini_th, t_min = p.min_th;
-  for (int k = tid; k < ncand; k += kFastThreads)
+  for (int k = lane; k < wcnt; k += 32)
   {
-    const int i = cand_at(k);
+    const int i = my_cand[k];
     const int zy = i >> 6, zx = i & (kZoneMax - 1);
     const uint8_t *mp = &s_map[(zy + 1) * kMapPitch + zx + 1];
     const int m = mp[0];
