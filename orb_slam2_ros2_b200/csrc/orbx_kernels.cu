@@ -319,19 +319,12 @@ __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kCandSeg = (kZoneMax / kFastWarps) * kZoneMax; // candidates one warp can produce (its rows x 64)
 
-// at least 4 circularly consecutive bits set in an 8-bit ring mask
-__device__ __forceinline__ bool ring8_has_run4(unsigned m)
-{
-  m |= m << 8;
-  return ((m & (m >> 1) & (m >> 2) & (m >> 3)) & 0xffu) != 0u;
-}
-
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p)
 {
   __shared__ __align__(16) uint8_t s_pat[(kZoneMax + 6) * kPatPitch];
   __shared__ __align__(16) uint8_t s_map[(kZoneMax + 2) * kMapPitch + 16]; // + 16: zeroed with 16-byte stores
   __shared__ uint16_t s_cand[kFastWarps * kCandSeg];
-  __shared__ unsigned long long s_keep_ini[kZoneMax], s_keep_min[kZoneMax];
+  __shared__ unsigned long long s_keep[kZoneMax];
   __shared__ int s_warp[kFastWarps];
 
   const Cell c = p.cells[blockIdx.x];
@@ -349,9 +342,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
     if (tid == 0) *cnt_out = 0;
     return;
   }
-  const int tq = min(p.ini_th, p.min_th);
 
-  // patch rows as aligned 32-bit words (one warp per row); zero the arc-value map and the keep masks
+  // patch rows as aligned 32-bit words (one warp per row)
   const int xoff = c.x0 & 3;
   {
     const int nw = (xoff + pw + 3) >> 2; // <= 19 words
@@ -359,83 +351,115 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
     uint32_t *s32 = reinterpret_cast<uint32_t *>(s_pat);
     for (int y = wid; y < ph; y += kFastWarps)
       if (lane < nw) s32[y * (kPatPitch / 4) + lane] = *reinterpret_cast<const uint32_t *>(g + (size_t)y * pitch + 4 * lane);
-    uint4 *m128 = reinterpret_cast<uint4 *>(s_map);
-    for (int i = tid; i < ((zh + 2) * kMapPitch + 15) / 16; i += kFastThreads) m128[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid < kZoneMax)
-    {
-      s_keep_ini[tid] = 0ull;
-      s_keep_min[tid] = 0ull;
-    }
   }
-  __syncthreads();
-
-  // Pre-tests at the lower threshold (both are necessary conditions for a 9-arc):
-  //   (1) at least 2 of the 4 compass ring pixels are brighter (darker) than the centre by more than t
-  //   (2) at least 4 consecutive of the 8 even ring pixels are
-  // Survivors go to a per-warp candidate segment (warp-local counter, no atomics).
   const uint8_t *pat0 = s_pat + 3 * kPatPitch + 3 + xoff; // zone pixel (0,0)
-  int wcnt = 0;
   uint16_t *my_cand = s_cand + wid * kCandSeg;
-  for (int zy = wid; zy < zh; zy += kFastWarps)
-  {
-    for (int zx0 = 0; zx0 < zw; zx0 += 32)
-    {
-      const int zx = zx0 + lane;
-      bool cand = false;
-      if (zx < zw)
-      {
-        const uint8_t *q = pat0 + zy * kPatPitch + zx;
-        const int v = q[0], hi = v + tq, lo = v - tq;
-        const int r0 = q[3 * kPatPitch], r4 = q[3], r8 = q[-3 * kPatPitch], r12 = q[-3];
-        const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
-        const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
-        if (nb >= 2 || nd >= 2)
-        {
-          const int r2 = q[2 * kPatPitch + 2], r6 = q[-2 * kPatPitch + 2], r10 = q[-2 * kPatPitch - 2], r14 = q[2 * kPatPitch - 2];
-          const unsigned mb = (unsigned)(r0 > hi) | ((unsigned)(r2 > hi) << 1) | ((unsigned)(r4 > hi) << 2) | ((unsigned)(r6 > hi) << 3) |
-                              ((unsigned)(r8 > hi) << 4) | ((unsigned)(r10 > hi) << 5) | ((unsigned)(r12 > hi) << 6) | ((unsigned)(r14 > hi) << 7);
-          const unsigned md = (unsigned)(r0 < lo) | ((unsigned)(r2 < lo) << 1) | ((unsigned)(r4 < lo) << 2) | ((unsigned)(r6 < lo) << 3) |
-                              ((unsigned)(r8 < lo) << 4) | ((unsigned)(r10 < lo) << 5) | ((unsigned)(r12 < lo) << 6) | ((unsigned)(r14 < lo) << 7);
-          cand = ring8_has_run4(mb) || ring8_has_run4(md);
-        }
-      }
-      const unsigned m = __ballot_sync(FULL, cand);
-      if (cand) my_cand[wcnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(zy * kZoneMax + zx);
-      wcnt += __popc(m);
-    }
-  }
-  // each warp evaluates the arc value of its own candidates (its segment is private, the patch is read-only)
-  __syncwarp();
-  for (int k = lane; k < wcnt; k += 32)
-  {
-    const int i = my_cand[k];
-    const int zy = i >> 6, zx = i & (kZoneMax - 1);
-    const int m = fast_arc_value(pat0 + zy * kPatPitch + zx);
-    if (m > tq) s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)m;
-  }
-  __syncthreads();
+  unsigned long long keep = 0ull;
 
-  // Non-max suppression at both thresholds.  keep at t  <=>  m > t  and  m - 1 > max over the 8 neighbours of
-  // (q > t ? q - 1 : 0); that map is monotone in q, so only the largest neighbour matters.
-  const int t_ini = p.ini_th, t_min = p.min_th;
-  for (int k = lane; k < wcnt; k += 32)
+  // cv::FAST(cell, iniThFAST); only if its post-NMS list is empty, cv::FAST(cell, minThFAST) (src/ORBExtractor.cc:365-367).
+  // Running the thresholds one after the other (instead of computing everything at the lower one) keeps the second,
+  // far more expensive pass to the few cells that need it.
+  for (int pass = 0; pass < 2; ++pass)
   {
-    const int i = my_cand[k];
-    const int zy = i >> 6, zx = i & (kZoneMax - 1);
-    const uint8_t *mp = &s_map[(zy + 1) * kMapPitch + zx + 1];
-    const int m = mp[0];
-    if (m == 0) continue;
-    const int q = max(max(max((int)mp[-1], (int)mp[1]), max((int)mp[-kMapPitch - 1], (int)mp[-kMapPitch])),
-                      max(max((int)mp[-kMapPitch + 1], (int)mp[kMapPitch - 1]), max((int)mp[kMapPitch], (int)mp[kMapPitch + 1])));
-    const int s = m - 1;
-    if (m > t_ini && s > (q > t_ini ? q - 1 : 0)) atomicOr(&s_keep_ini[zy], 1ull << zx);
-    if (m > t_min && s > (q > t_min ? q - 1 : 0)) atomicOr(&s_keep_min[zy], 1ull << zx);
+    const int t = pass == 0 ? p.ini_th : p.min_th;
+    {
+      uint4 *m128 = reinterpret_cast<uint4 *>(s_map);
+      for (int i = tid; i < ((zh + 2) * kMapPitch + 15) / 16; i += kFastThreads) m128[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (tid < kZoneMax) s_keep[tid] = 0ull;
+    }
+    __syncthreads();
+
+    // Stage 1 (every zone pixel): at least 2 of the 4 compass ring pixels are brighter (darker) than the centre by more
+    // than t -- a necessary condition for a 9-arc.  Survivors go to a per-warp candidate segment (warp-local counter, no
+    // atomics), so that the later stages run on dense lanes.
+    int wcnt = 0;
+    for (int zy = wid; zy < zh; zy += kFastWarps)
+    {
+      for (int zx0 = 0; zx0 < zw; zx0 += 32)
+      {
+        const int zx = zx0 + lane;
+        bool cand = false;
+        if (zx < zw)
+        {
+          const uint8_t *q = pat0 + zy * kPatPitch + zx;
+          const int v = q[0], hi = v + t, lo = v - t;
+          const int r0 = q[3 * kPatPitch], r4 = q[3], r8 = q[-3 * kPatPitch], r12 = q[-3];
+          const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
+          const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
+          cand = nb >= 2 || nd >= 2;
+        }
+        const unsigned m = __ballot_sync(FULL, cand);
+        if (cand) my_cand[wcnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(zy * kZoneMax + zx);
+        wcnt += __popc(m);
+      }
+    }
+    __syncwarp();
+
+    // Stage 2 (stage-1 survivors, dense lanes): the exact corner test.  One bit per ring pixel (sign of hi - r / r - lo
+    // shifted in with a funnel shift), then "9 circularly consecutive bits" by and-doubling.  The segment is compacted
+    // in place to the true corners (every chunk is read before it is overwritten).
+    int ccnt = 0;
+    for (int k0 = 0; k0 < wcnt; k0 += 32)
+    {
+      const int k = k0 + lane;
+      bool corner = false;
+      int i = 0;
+      if (k < wcnt)
+      {
+        i = my_cand[k];
+        const uint8_t *q = pat0 + (i >> 6) * kPatPitch + (i & (kZoneMax - 1));
+        const int v = q[0], hi = v + t, lo = v - t;
+        constexpr int P = kPatPitch;
+        const int ro[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1, -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
+        unsigned mb = 0u, md = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+        {
+          const int r = q[ro[j]];
+          mb = __funnelshift_l((unsigned)(hi - r), mb, 1); // shifts in 1 iff r > v + t
+          md = __funnelshift_l((unsigned)(r - lo), md, 1); // shifts in 1 iff r < v - t
+        }
+        auto run9 = [](unsigned m16) -> bool {
+          const unsigned m = m16 | (m16 << 16);
+          const unsigned a = m & (m >> 1), b = a & (a >> 2), cc = b & (b >> 4);
+          return ((cc & (m >> 8)) & 0xffffu) != 0u;
+        };
+        corner = run9(mb) || run9(md);
+      }
+      __syncwarp();
+      const unsigned m = __ballot_sync(FULL, corner);
+      if (corner) my_cand[ccnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+      ccnt += __popc(m);
+    }
+    __syncwarp();
+
+    // Stage 3 (true corners only): the arc value m, needed for the scores and the non-max suppression
+    for (int k = lane; k < ccnt; k += 32)
+    {
+      const int i = my_cand[k];
+      const int zy = i >> 6, zx = i & (kZoneMax - 1);
+      s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)fast_arc_value(pat0 + zy * kPatPitch + zx); // > t by stage 2
+    }
+    __syncthreads();
+
+    // Non-max suppression: keep  <=>  score m - 1 > the scores of all 8 neighbours (strict), where a neighbour that is not
+    // a corner at this threshold (map 0) scores 0; the map q -> (q ? q - 1 : 0) is monotone, so only the largest neighbour
+    // matters.
+    for (int k = lane; k < ccnt; k += 32)
+    {
+      const int i = my_cand[k];
+      const int zy = i >> 6, zx = i & (kZoneMax - 1);
+      const uint8_t *mp = &s_map[(zy + 1) * kMapPitch + zx + 1];
+      const int m = mp[0];
+      const int q = max(max(max((int)mp[-1], (int)mp[1]), max((int)mp[-kMapPitch - 1], (int)mp[-kMapPitch])),
+                        max(max((int)mp[-kMapPitch + 1], (int)mp[kMapPitch - 1]), max((int)mp[kMapPitch], (int)mp[kMapPitch + 1])));
+      if (m - 1 > (q ? q - 1 : 0)) atomicOr(&s_keep[zy], 1ull << zx);
+    }
+    __syncthreads();
+    keep = tid < zh ? s_keep[tid] : 0ull;
+    if (__syncthreads_or(keep != 0ull)) break; // fallback iff the post-NMS list is empty (:366)
   }
-  __syncthreads();
-  const unsigned long long row_ini = tid < zh ? s_keep_ini[tid] : 0ull;
-  const int any_ini = __syncthreads_or(row_ini != 0ull);
-  // fallback to minThFAST iff the post-NMS list at iniThFAST is empty (:366-367)
-  unsigned long long keep = any_ini ? row_ini : (tid < zh ? s_keep_min[tid] : 0ull);
+
   int total;
   int off = block_exclusive_scan<kFastThreads>(__popcll(keep), total, s_warp); // thread <-> zone row: row-major output order
   uint32_t *slot = p.cell_list + (size_t)img * p.cell_entries + c.slot;
