@@ -384,13 +384,17 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
           const uint8_t *q = pat0 + zy * kPatPitch + zx;
           const int v = q[0], hi = v + t, lo = v - t;
           const int r0 = q[3 * kPatPitch], r4 = q[3], r8 = q[-3 * kPatPitch], r12 = q[-3];
-          const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
-          const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
-          cand = nb >= 2 || nd >= 2;
+          // "at least two of the four exceed hi" <=> the second largest does; likewise the second smallest below lo
+          const int mx1 = max(r0, r4), mn1 = min(r0, r4), mx2 = max(r8, r12), mn2 = min(r8, r12);
+          const int a = min(mx1, mx2), b = max(mn1, mn2);
+          cand = max(a, b) > hi || min(a, b) < lo;
         }
         const unsigned m = __ballot_sync(FULL, cand);
-        if (cand) my_cand[wcnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(zy * kZoneMax + zx);
-        wcnt += __popc(m);
+        if (m)
+        {
+          if (cand) my_cand[wcnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(zy * kZoneMax + zx);
+          wcnt += __popc(m);
+        }
       }
     }
     __syncwarp();
