@@ -68,6 +68,17 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi needs a moment to attach; block until it has written its first line"""
+        t0 = time.time()
+        while self.proc and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.02)
+
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -216,6 +227,7 @@ def run_gpu_arm(args):
     # ---- device-resident throughput (`value`) ------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()  # started before the warm-up so that short timed regions still get samples under load
+    sampler.wait_first_sample()
     for i in range(args.warmup):
         device_step(i)
     barrier()

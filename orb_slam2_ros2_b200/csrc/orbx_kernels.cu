@@ -319,7 +319,7 @@ __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kCandSeg = (kZoneMax / kFastWarps) * kZoneMax; // candidates one warp can produce (its rows x 64)
 
-__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p)
+__global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Params p)
 {
   __shared__ __align__(16) uint8_t s_pat[(kZoneMax + 6) * kPatPitch];
   __shared__ __align__(16) uint8_t s_map[(kZoneMax + 2) * kMapPitch + 16]; // + 16: zeroed with 16-byte stores
@@ -1298,7 +1298,7 @@ __device__ __forceinline__ void undistort_point(const Params &p, float u, float 
   vo = __double2float_rn(__dadd_rn(__dmul_rn(y, fy), cy));
 }
 
-__global__ void __launch_bounds__(kBriefWarps * 32) orient_brief_kernel(const Params p)
+__global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const Params p)
 {
   const int img = blockIdx.y;
   const int lane = threadIdx.x & 31;
@@ -1470,7 +1470,7 @@ void launch_rowindex(const Params &p, int n_frames, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kStereoWarps = 8;
 
-__global__ void __launch_bounds__(kStereoWarps * 32) stereo_kernel(const Params p)
+__global__ void __launch_bounds__(kStereoWarps * 32, 5) stereo_kernel(const Params p)
 {
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31;
