@@ -1337,12 +1337,13 @@ __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const
     unsigned rows = 0u;
 #pragma unroll
     for (int dy = -15; dy <= 15; ++dy) rows |= (unsigned)(lane < 31 && adx <= c_umax[dy < 0 ? -dy : dy]) << (dy + 15);
-    const uint8_t *c = lvl + (size_t)y * pitch + x + dx;
+    const uint8_t *c = lvl + (size_t)(y - 15) * pitch + x + dx; // row -15 of the lane's column; walks down one pitch per row
     int colsum = 0;
 #pragma unroll
     for (int dy = -15; dy <= 15; ++dy)
     {
-      const int v = ((rows >> (dy + 15)) & 1u) ? (int)c[dy * pitch] : 0;
+      const int v = ((rows >> (dy + 15)) & 1u) ? (int)*c : 0;
+      c += pitch;
       colsum += v;
       m01 += dy * v;
     }
