@@ -373,26 +373,27 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
     // than t -- a necessary condition for a 9-arc.  Survivors go to a per-warp candidate segment (warp-local counter, no
     // atomics), so that the later stages run on dense lanes.
     int wcnt = 0;
-    for (int zy = wid; zy < zh; zy += kFastWarps)
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int zx0 = 0; zx0 < zw; zx0 += 32) // one chunk for every cell narrower than 33 px (the usual 30-32)
     {
-      for (int zx0 = 0; zx0 < zw; zx0 += 32)
+      const int zx = zx0 + lane;
+      const bool valid = zx < zw;
+      // lanes beyond the zone read inside the patch buffer (pitch 80 > 3 + 64 + 3) and are masked out of the vote
+      const uint8_t *q = pat0 + wid * kPatPitch + min(zx, kZoneMax - 1);
+      int code = wid * kZoneMax + zx;
+#pragma unroll 2
+      for (int zy = wid; zy < zh; zy += kFastWarps, q += kFastWarps * kPatPitch, code += kFastWarps * kZoneMax)
       {
-        const int zx = zx0 + lane;
-        bool cand = false;
-        if (zx < zw)
-        {
-          const uint8_t *q = pat0 + zy * kPatPitch + zx;
-          const int v = q[0], hi = v + t, lo = v - t;
-          const int r0 = q[3 * kPatPitch], r4 = q[3], r8 = q[-3 * kPatPitch], r12 = q[-3];
-          // "at least two of the four exceed hi" <=> the second largest does; likewise the second smallest below lo
-          const int mx1 = max(r0, r4), mn1 = min(r0, r4), mx2 = max(r8, r12), mn2 = min(r8, r12);
-          const int a = min(mx1, mx2), b = max(mn1, mn2);
-          cand = max(a, b) > hi || min(a, b) < lo;
-        }
+        const int v = q[0], hi = v + t, lo = v - t;
+        const int r0 = q[3 * kPatPitch], r4 = q[3], r8 = q[-3 * kPatPitch], r12 = q[-3];
+        // "at least two of the four exceed hi" <=> the second largest does; likewise the second smallest below lo
+        const int mx1 = max(r0, r4), mn1 = min(r0, r4), mx2 = max(r8, r12), mn2 = min(r8, r12);
+        const int a = min(mx1, mx2), b = max(mn1, mn2);
+        const bool cand = valid && (max(a, b) > hi || min(a, b) < lo);
         const unsigned m = __ballot_sync(FULL, cand);
         if (m)
         {
-          if (cand) my_cand[wcnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(zy * kZoneMax + zx);
+          if (cand) my_cand[wcnt + __popc(m & lt_mask)] = (uint16_t)code;
           wcnt += __popc(m);
         }
       }

@@ -86,6 +86,35 @@ def test_fast_and_quadtree_stages_match_oracle(oracle, kind):
     ctx.close()
 
 
+def test_random_configurations(oracle):
+    """seeded sweep over image sizes (not multiples of any tile), level counts, scale factors, quotas and thresholds"""
+    rng = np.random.default_rng(2024)
+    done = 0
+    for trial in range(60):
+        w, h = int(rng.integers(80, 900)), int(rng.integers(80, 700))
+        nl = int(rng.integers(1, 9))
+        sc = float(np.float32(rng.uniform(1.1, 1.6)))
+        nf = int(rng.integers(20, 3000))
+        ini, mn = int(rng.integers(8, 40)), int(rng.integers(2, 12))
+        rc, lw, lh = oracle.level_sizes(w, h, sc, nl)
+        if rc != 0 or min(lw[-1], lh[-1]) < 62:
+            with pytest.raises(api.ImageSizeError):
+                api.Context(w, h, nf, nl, sc, ini, mn)
+            continue
+        img = synth.synth_image(h, w, 1000 + trial)
+        if trial % 4 == 0:
+            img = np.ascontiguousarray(np.pad(img, ((0, 0), (0, 13)))[:, :w + 13])[:, :w]  # non-contiguous rows (stride != width)
+        ctx = api.Context(w, h, nf, nl, sc, ini, mn)
+        kps, desc = ctx.extract(img)
+        e = oracle.extract(img, nf, nl, sc, ini, mn)
+        _cmp_kps(kps, e.kps, desc, e.desc, f"trial {trial}: {w}x{h} L{nl} s{sc:.3f} N{nf} th{ini}/{mn}")
+        lv = ctx.get_pyramid(0, True)
+        assert np.array_equal(lv[-1], e.pyr.blurred(nl - 1))
+        ctx.close()
+        done += 1
+    assert done >= 30
+
+
 def test_degenerate_images(oracle):
     ctx = api.Context(320, 240, 1000, 4, 1.2)
     kps, desc = ctx.extract(np.zeros((240, 320), np.uint8))
