@@ -347,10 +347,14 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
   const int xoff = c.x0 & 3;
   {
     const int nw = (xoff + pw + 3) >> 2; // <= 19 words
-    const uint8_t *g = lvl + (size_t)c.y0 * pitch + (c.x0 - xoff);
-    uint32_t *s32 = reinterpret_cast<uint32_t *>(s_pat);
-    for (int y = wid; y < ph; y += kFastWarps)
-      if (lane < nw) s32[y * (kPatPitch / 4) + lane] = *reinterpret_cast<const uint32_t *>(g + (size_t)y * pitch + 4 * lane);
+    if (lane < nw)
+    {
+      const uint32_t *g = reinterpret_cast<const uint32_t *>(lvl + (size_t)(c.y0 + wid) * pitch + (c.x0 - xoff)) + lane;
+      uint32_t *d = reinterpret_cast<uint32_t *>(s_pat) + wid * (kPatPitch / 4) + lane;
+      const int gstep = kFastWarps * (pitch >> 2); // pitch is a multiple of 16
+#pragma unroll 4
+      for (int y = wid; y < ph; y += kFastWarps, g += gstep, d += kFastWarps * (kPatPitch / 4)) *d = *g;
+    }
   }
   const uint8_t *pat0 = s_pat + 3 * kPatPitch + 3 + xoff; // zone pixel (0,0)
   uint16_t *my_cand = s_cand + wid * kCandSeg;
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
         // "at least two of the four exceed hi" <=> the second largest does; likewise the second smallest below lo
         const int mx1 = max(r0, r4), mn1 = min(r0, r4), mx2 = max(r8, r12), mn2 = min(r8, r12);
         const int a = min(mx1, mx2), b = max(mn1, mn2);
-        const bool cand = valid && (max(a, b) > hi || min(a, b) < lo);
+        const bool cand = valid & ((max(a, b) > hi) | (min(a, b) < lo));
         const unsigned m = __ballot_sync(FULL, cand);
         if (m)
         {
