@@ -237,6 +237,7 @@ int build_tables(orbx_ctx *c)
     sel_off += std::max(1, L.quota);
     L.scratch_off = (int)scratch_off;
     scratch_off += (size_t)L.list_cap * 4 + 8; // corner list + descent keys + 2 index arrays (u32 each)
+    scratch_off += ((size_t)g.n_features + kMaxStrips + 8) * 8; // node bounds (4 x int64 per node, node_cap <= nFeatures + strips + 8)
     scratch_off = (scratch_off + 3) & ~(size_t)3;
     max_quota = std::max(max_quota, L.quota);
     max_ini = std::max(max_ini, L.n_ini);

@@ -510,7 +510,8 @@ void launch_fast(const Params &p, int n_images, cudaStream_t s)
 // scratch; node pool, buckets and the big-node list are always in shared memory.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kQtBuckets = 256;  // small buckets hold counts 0..255
-constexpr int kNodeBytes = 4 * 8 + 3 * 4 + 3 * 2 + 3; // r0 r1 c0 c1 | lo cnt seq | next prev free | buf state depth
+constexpr int kNodeBytes = 3 * 4 + 3 * 2 + 3;  // shared memory per node: lo cnt seq | next prev free | buf state depth
+constexpr int kNodeBoundWords = 4 * 2;          // global scratch per node (uint32 words): r0 r1 c0 c1, touched only below the key depth
 constexpr int kKeyLevels = 9;    // subdivision depths encoded in a key (3 bits each) below the 5-bit strip id
 constexpr int kKeyStripShift = 27;
 constexpr uint32_t kKeyNoStrip = 31u;
@@ -1036,7 +1037,9 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   __shared__ int s_n, s_take;
   __shared__ int s_strip_cnt[32];
 
-  const int level = blockIdx.x, img = blockIdx.y;
+  // grid = (images, levels): CTAs are dispatched x-fastest, so every image's level 0 (the longest chain) starts first
+  // and the short high levels fill the tail
+  const int level = blockIdx.y, img = blockIdx.x;
   const Level &L = p.levels[level];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int need = L.quota;
@@ -1069,11 +1072,12 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   uint8_t *lists;
   {
     uint8_t *w = smem;
-    q.np.r0 = (long long *)w;
+    // node bounds: global scratch behind the level's lists (only nodes below the key depth ever read or write them)
+    q.np.r0 = (long long *)(p.qt_scratch + (size_t)img * p.qt_scratch_img_stride + L.scratch_off + 4 * (size_t)L.list_cap + 8);
     q.np.r1 = q.np.r0 + node_cap;
     q.np.c0 = q.np.r1 + node_cap;
     q.np.c1 = q.np.c0 + node_cap;
-    q.np.lo = (uint32_t *)(q.np.c1 + node_cap);
+    q.np.lo = (uint32_t *)w;
     q.np.cnt = q.np.lo + node_cap;
     q.np.seq = q.np.cnt + node_cap;
     q.np.next = (uint16_t *)(q.np.seq + node_cap);
@@ -1266,7 +1270,7 @@ int quadtree_configure(size_t smem_bytes)
 
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s)
 {
-  dim3 grid(p.n_levels, n_images);
+  dim3 grid(n_images, p.n_levels);
   quadtree_kernel<<<grid, kQtThreads, smem_bytes, s>>>(p);
 }
 
