@@ -510,7 +510,7 @@ void launch_fast(const Params &p, int n_images, cudaStream_t s)
 // scratch; node pool, buckets and the big-node list are always in shared memory.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kQtBuckets = 256;  // small buckets hold counts 0..255
-constexpr int kNodeBytes = 3 * 4 + 3 * 2 + 3;  // shared memory per node: lo cnt seq | next prev free | buf state depth
+constexpr int kNodeBytes = 8 + 4 + 3 * 2 + 1;  // shared memory per node: rec {lo, cnt|depth|buf} | seq | next prev free | state
 constexpr int kNodeBoundWords = 4 * 2;          // global scratch per node (uint32 words): r0 r1 c0 c1, touched only below the key depth
 constexpr int kKeyLevels = 9;    // subdivision depths encoded in a key (3 bits each) below the 5-bit strip id
 constexpr int kKeyStripShift = 27;
@@ -527,10 +527,19 @@ constexpr int kFixDepth = 17; // nodes up to this depth store fixed-point bounds
 struct QtNodePool
 {
   long long *r0, *r1, *c0, *c1; // bounds: 24.40 fixed point up to depth kFixDepth, IEEE double bit patterns below
-  uint32_t *lo, *cnt, *seq;
+  uint2 *rec;    // x = first index of the node's range, y = count (24 bits) | depth << 24 (7 bits, saturating) | buffer << 31
+  uint32_t *seq;
   uint16_t *next, *prev, *free_ids;
-  uint8_t *buf, *state, *depth; // state: 0 dead, 1 live, 2 live but beyond the first `need` entries
+  uint8_t *state; // 0 dead, 1 live, 2 live but beyond the first `need` entries
 };
+
+__device__ __forceinline__ uint2 qt_rec(uint32_t lo, uint32_t cnt, int depth, int buf)
+{
+  return make_uint2(lo, cnt | ((uint32_t)min(depth, 127) << 24) | ((uint32_t)buf << 31));
+}
+__device__ __forceinline__ uint32_t qt_rec_cnt(uint2 r) { return r.y & 0xffffffu; }
+__device__ __forceinline__ int qt_rec_depth(uint2 r) { return (int)((r.y >> 24) & 127u); }
+__device__ __forceinline__ int qt_rec_buf(uint2 r) { return (int)(r.y >> 31); }
 
 __host__ __device__ inline size_t qt_align16(size_t b) { return (b + 15) & ~(size_t)15; }
 
@@ -590,7 +599,7 @@ __device__ __forceinline__ int qt_big_extreme(const QtState &q, int lane, bool w
   for (int j = lane; j < q.nbig; j += 32)
   {
     const uint32_t id = q.big[j];
-    const unsigned long long key = ((unsigned long long)q.np.cnt[id] << 32) | (unsigned long long)(0xffffffffu - q.np.seq[id]);
+    const unsigned long long key = ((unsigned long long)qt_rec_cnt(q.np.rec[id]) << 32) | (unsigned long long)(0xffffffffu - q.np.seq[id]);
     if (want_max ? key >= best : key <= best)
     {
       best = key;
@@ -745,8 +754,9 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
         np.state[id] = 0;
       }
     }
-    const uint32_t lo = np.lo[id], cnt = np.cnt[id];
-    const int buf = np.buf[id], depth = np.depth[id];
+    const uint2 rec = np.rec[id];
+    const uint32_t lo = rec.x, cnt = qt_rec_cnt(rec);
+    const int buf = qt_rec_buf(rec), depth = qt_rec_depth(rec);
     --live;
     const IdxT *src = buf ? ib : ia;
     IdxT *dst = buf ? ia : ib;
@@ -806,10 +816,7 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
             np.r1[cid] = r1;
             np.c0[cid] = cols[k];
             np.c1[cid] = cols[k + 1];
-            np.lo[cid] = base;
-            np.cnt[cid] = run;
-            np.buf[cid] = (uint8_t)(buf ^ 1);
-            np.depth[cid] = 0;
+            np.rec[cid] = qt_rec(base, run, 0, buf ^ 1);
           }
           qt_push(q, cid, run, lane);
           ++live;
@@ -875,37 +882,58 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
       }
       else
       {
-        for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
+        // four chunks of 32 per iteration: the (index -> key) load chains of the chunks are independent, which is what
+        // hides the shared-memory latency on this single warp
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 128)
         {
-          const uint32_t i = i0 + lane;
-          const uint32_t d = i < cnt ? digit_of(src[lo + i]) : kDigitDrop;
-          t0 += __popc(__ballot_sync(FULL, d == 0));
-          t1 += __popc(__ballot_sync(FULL, d == 1));
-          t2 += __popc(__ballot_sync(FULL, d == 2));
-          t3 += __popc(__ballot_sync(FULL, d == 3));
+          uint32_t d[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            const uint32_t i = i0 + 32 * u + lane;
+            d[u] = i < cnt ? digit_of(src[lo + i]) : kDigitDrop;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            t0 += __popc(__ballot_sync(FULL, d[u] == 0));
+            t1 += __popc(__ballot_sync(FULL, d[u] == 1));
+            t2 += __popc(__ballot_sync(FULL, d[u] == 2));
+            t3 += __popc(__ballot_sync(FULL, d[u] == 3));
+          }
         }
         const uint32_t b0 = lo, b1 = b0 + t0, b2 = b1 + t1, b3 = b2 + t2;
         uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-        for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 128)
         {
-          const uint32_t i = i0 + lane;
-          uint32_t d = kDigitDrop;
-          IdxT idx = 0;
-          if (i < cnt)
+          uint32_t d[4];
+          IdxT idx[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
           {
-            idx = src[lo + i];
-            d = digit_of(idx);
+            const uint32_t i = i0 + 32 * u + lane;
+            d[u] = kDigitDrop;
+            idx[u] = 0;
+            if (i < cnt)
+            {
+              idx[u] = src[lo + i];
+              d[u] = digit_of(idx[u]);
+            }
           }
-          const unsigned m0 = __ballot_sync(FULL, d == 0), m1 = __ballot_sync(FULL, d == 1);
-          const unsigned m2 = __ballot_sync(FULL, d == 2), m3 = __ballot_sync(FULL, d == 3);
-          if (d == 0) dst[b0 + q0 + __popc(m0 & lt_mask)] = idx;
-          if (d == 1) dst[b1 + q1 + __popc(m1 & lt_mask)] = idx;
-          if (d == 2) dst[b2 + q2 + __popc(m2 & lt_mask)] = idx;
-          if (d == 3) dst[b3 + q3 + __popc(m3 & lt_mask)] = idx;
-          q0 += __popc(m0);
-          q1 += __popc(m1);
-          q2 += __popc(m2);
-          q3 += __popc(m3);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            const unsigned m0 = __ballot_sync(FULL, d[u] == 0), m1 = __ballot_sync(FULL, d[u] == 1);
+            const unsigned m2 = __ballot_sync(FULL, d[u] == 2), m3 = __ballot_sync(FULL, d[u] == 3);
+            if (d[u] == 0) dst[b0 + q0 + __popc(m0 & lt_mask)] = idx[u];
+            if (d[u] == 1) dst[b1 + q1 + __popc(m1 & lt_mask)] = idx[u];
+            if (d[u] == 2) dst[b2 + q2 + __popc(m2 & lt_mask)] = idx[u];
+            if (d[u] == 3) dst[b3 + q3 + __popc(m3 & lt_mask)] = idx[u];
+            q0 += __popc(m0);
+            q1 += __popc(m1);
+            q2 += __popc(m2);
+            q3 += __popc(m3);
+          }
         }
       }
       // children: lane k < 4 fills the record of child k; ids come from the free stack first, then fresh slots
@@ -940,23 +968,47 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
             np.c0[c] = (k & 1) ? mc : pc0;
             np.c1[c] = (k & 1) ? pc1 : mc;
           }
-          np.lo[c] = my_b;
-          np.cnt[c] = my_t;
-          np.buf[c] = (uint8_t)(buf ^ 1);
-          np.depth[c] = (uint8_t)min(depth + 1, 255);
+          np.rec[c] = qt_rec(my_b, my_t, depth + 1, buf ^ 1);
         }
       }
       const int from_free = min(n_free, n_new);
       n_alloc += n_new - from_free;
       n_free -= from_free;
       __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (tc[k] > 0)
+      // multimap insertion order == child order; it only matters between children of EQUAL count (same bucket), so when
+      // the non-empty children have pairwise distinct counts below 256 the four pushes go to four different buckets and
+      // lanes 0..3 do them concurrently
+      const bool distinct = (t0 != t1 || t0 == 0) && (t0 != t2 || t0 == 0) && (t0 != t3 || t0 == 0) && (t1 != t2 || t1 == 0) && (t1 != t3 || t1 == 0) &&
+                            (t2 != t3 || t2 == 0) && max(max(t0, t1), max(t2, t3)) < (uint32_t)kQtBuckets;
+      if (distinct)
+      {
+        const int k = lane & 3;
+        const uint32_t my_t = k == 0 ? t0 : (k == 1 ? t1 : (k == 2 ? t2 : t3));
+        const uint32_t c = k == 0 ? cid[0] : (k == 1 ? cid[1] : (k == 2 ? cid[2] : cid[3]));
+        if (lane < 4 && my_t > 0)
         {
-          qt_push(q, cid[k], tc[k], lane); // multimap insertion order == child order
-          ++live;
+          const uint32_t tl = q.btail[my_t];
+          np.next[c] = (uint16_t)kNil;
+          np.prev[c] = (uint16_t)tl;
+          if (tl == kNil)
+            q.bhead[my_t] = (uint16_t)c;
+          else
+            np.next[tl] = (uint16_t)c;
+          q.btail[my_t] = (uint16_t)c;
+          np.state[c] = 1;
         }
+        live += n_new;
+      }
+      else
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (tc[k] > 0)
+          {
+            qt_push(q, cid[k], tc[k], lane);
+            ++live;
+          }
+      }
     }
     // the popped node's slot can be reused
     if (lane == 0) np.free_ids[n_free] = (uint16_t)id;
@@ -1013,8 +1065,9 @@ __device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *
   for (int s = tid; s < n_slots; s += kQtThreads)
   {
     if (np.state[s] != 1) continue;
-    const IdxT *arr = np.buf[s] ? ib : ia;
-    const uint32_t lo = np.lo[s], cnt = np.cnt[s];
+    const uint2 rec = np.rec[s];
+    const IdxT *arr = qt_rec_buf(rec) ? ib : ia;
+    const uint32_t lo = rec.x, cnt = qt_rec_cnt(rec);
     uint32_t best = 0, best_i = 0;
     for (uint32_t i = 0; i < cnt; ++i)
     {
@@ -1077,15 +1130,12 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
     q.np.r1 = q.np.r0 + node_cap;
     q.np.c0 = q.np.r1 + node_cap;
     q.np.c1 = q.np.c0 + node_cap;
-    q.np.lo = (uint32_t *)w;
-    q.np.cnt = q.np.lo + node_cap;
-    q.np.seq = q.np.cnt + node_cap;
+    q.np.rec = (uint2 *)w;
+    q.np.seq = (uint32_t *)(q.np.rec + node_cap);
     q.np.next = (uint16_t *)(q.np.seq + node_cap);
     q.np.prev = q.np.next + node_cap;
     q.np.free_ids = q.np.prev + node_cap;
-    q.np.buf = (uint8_t *)(q.np.free_ids + node_cap);
-    q.np.state = q.np.buf + node_cap;
-    q.np.depth = q.np.state + node_cap;
+    q.np.state = (uint8_t *)(q.np.free_ids + node_cap);
     w = smem + qt_align16((size_t)node_cap * kNodeBytes) + qt_align16((size_t)p.qt_cell_cap * sizeof(int));
     q.bhead = (uint16_t *)w;
     q.btail = q.bhead + kQtBuckets;
@@ -1189,10 +1239,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
           q.np.r1[cid] = roi_h_fx;
           q.np.c0[cid] = cols[k];
           q.np.c1[cid] = cols[k + 1];
-          q.np.lo[cid] = base;
-          q.np.cnt[cid] = cnt;
-          q.np.buf[cid] = 0;
-          q.np.depth[cid] = 0;
+          q.np.rec[cid] = qt_rec(base, cnt, 0, 0);
         }
         qt_push(q, cid, cnt, lane);
         ++live;
@@ -1208,10 +1255,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
         q.np.r1[0] = roi_h_fx;
         q.np.c0[0] = 0;
         q.np.c1[0] = roi_w_fx;
-        q.np.lo[0] = 0;
-        q.np.cnt[0] = (uint32_t)n;
-        q.np.buf[0] = 0;
-        q.np.depth[0] = 0;
+        q.np.rec[0] = qt_rec(0, (uint32_t)n, 0, 0);
       }
       qt_push(q, 0, (uint32_t)n, lane);
       n_alloc = 1;
