@@ -510,6 +510,7 @@ void launch_fast(const Params &p, int n_images, cudaStream_t s)
 // scratch; node pool, buckets and the big-node list are always in shared memory.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kQtBuckets = 256;  // small buckets hold counts 0..255
+constexpr int kQtMaxBinStrips = 8; // up to this many root strips the block pre-sorts two subdivision depths
 constexpr int kNodeBytes = 8 + 4 + 3 * 2 + 1;  // shared memory per node: rec {lo, cnt|depth|buf} | seq | next prev free | state
 constexpr int kNodeBoundWords = 4 * 2;          // global scratch per node (uint32 words): r0 r1 c0 c1, touched only below the key depth
 constexpr int kKeyLevels = 9;    // subdivision depths encoded in a key (3 bits each) below the 5-bit strip id
@@ -691,8 +692,9 @@ __device__ __forceinline__ void qt_bounds_from_key(uint32_t key, const long long
 }
 
 template <typename IdxT>
-__device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const uint32_t *kp, const uint32_t *keys, bool use_keys, IdxT *ia, IdxT *ib, int n,
-                            int need, int node_cap, int lane, int live, int n_alloc, bool root_pending, int &out_n_alloc, int &out_take)
+__device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const uint32_t *kp, const uint32_t *keys, bool use_keys, const int *bin_start,
+                            IdxT *ia, IdxT *ib, int n, int need, int node_cap, int lane, int live, int n_alloc, bool root_pending, int &out_n_alloc,
+                            int &out_take)
 {
   const unsigned FULL = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -861,7 +863,31 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
         if (fixed) return qt_quadrant((long long)(e & 0xfffu) << kFixShift, (long long)((e >> 12) & 0xfffu) << kFixShift, mr, mc);
         return qt_quadrant((double)(e & 0xfffu), (double)((e >> 12) & 0xfffu), mr_d, mc_d);
       };
-      if (cnt <= 32)
+      // The block sorted the corners by (strip, depth-1 digit, depth-2 digit) up front: the children of strip and depth-1
+      // nodes are contiguous sub-ranges of the parent's range, their sizes come from the bin table, nothing moves.
+      const bool presorted = bin_start != nullptr && keyed && depth <= 1;
+      if (presorted)
+      {
+        const uint32_t key0 = keys[src[lo]];
+        const int sidx = (int)(key0 >> kKeyStripShift);
+        if (depth == 0)
+        {
+          const int b = sidx * 25;
+          t0 = (uint32_t)(bin_start[b + 5] - bin_start[b]);
+          t1 = (uint32_t)(bin_start[b + 10] - bin_start[b + 5]);
+          t2 = (uint32_t)(bin_start[b + 15] - bin_start[b + 10]);
+          t3 = (uint32_t)(bin_start[b + 20] - bin_start[b + 15]);
+        }
+        else
+        {
+          const int b = (sidx * 5 + (int)((key0 >> (kKeyStripShift - 3)) & 7u)) * 5;
+          t0 = (uint32_t)(bin_start[b + 1] - bin_start[b]);
+          t1 = (uint32_t)(bin_start[b + 2] - bin_start[b + 1]);
+          t2 = (uint32_t)(bin_start[b + 3] - bin_start[b + 2]);
+          t3 = (uint32_t)(bin_start[b + 4] - bin_start[b + 3]);
+        }
+      }
+      else if (cnt <= 32)
       {
         // the common case: the whole node fits one warp pass
         uint32_t d = kDigitDrop, idx = 0;
@@ -968,7 +994,7 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
             np.c0[c] = (k & 1) ? mc : pc0;
             np.c1[c] = (k & 1) ? pc1 : mc;
           }
-          np.rec[c] = qt_rec(my_b, my_t, depth + 1, buf ^ 1);
+          np.rec[c] = qt_rec(my_b, my_t, depth + 1, presorted ? buf : buf ^ 1);
         }
       }
       const int from_free = min(n_free, n_new);
@@ -1089,6 +1115,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   __shared__ int s_warp[kQtThreads / 32];
   __shared__ int s_n, s_take;
   __shared__ int s_strip_cnt[32];
+  __shared__ int s_bin_start[kQtMaxBinStrips * 25 + 1], s_bin_cur[kQtMaxBinStrips * 25];
 
   // grid = (images, levels): CTAs are dispatched x-fastest, so every image's level 0 (the longest chain) starts first
   // and the short high levels fill the tail
@@ -1186,7 +1213,53 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   // ---- Phase B': root.  With need <= 1 the reference never pops the root (:151); otherwise its first pop is the root,
   // whose children are the strips: partition the corners by strip with the whole block (stable: K ordered scans).
   const bool split_root_here = use_keys && need > 1;
-  if (split_root_here)
+  const bool presort = split_root_here && K <= kQtMaxBinStrips;
+  if (presort)
+  {
+    // counting sort by (strip, depth-1 digit, depth-2 digit), "on a split line" (7) last; order inside a bin is arbitrary
+    // (nothing downstream depends on the order of a node's list: the best-response pick breaks ties by lowest index)
+    const int nb = K * 25;
+    auto bin_of = [&](uint32_t key) -> int {
+      const uint32_t sidx = key >> kKeyStripShift;
+      if (sidx == kKeyNoStrip) return -1;
+      const uint32_t d1 = (key >> (kKeyStripShift - 3)) & 7u, d2 = (key >> (kKeyStripShift - 6)) & 7u;
+      return (int)((sidx * 5u + min(d1, 4u)) * 5u + min(d2, 4u));
+    };
+    for (int i = tid; i <= nb; i += kQtThreads) s_bin_start[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kQtThreads)
+    {
+      const int b = bin_of(keys[i]);
+      if (b >= 0) atomicAdd(&s_bin_start[b + 1], 1);
+    }
+    __syncthreads();
+    {
+      const int v = tid < nb ? s_bin_start[tid + 1] : 0; // nb <= 200 < kQtThreads
+      int total;
+      const int off = block_exclusive_scan<kQtThreads>(v, total, s_warp);
+      if (tid < nb)
+      {
+        s_bin_start[tid] = off;
+        s_bin_cur[tid] = off;
+      }
+      if (tid == 0) s_bin_start[nb] = total;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kQtThreads)
+    {
+      const int b = bin_of(keys[i]);
+      if (b >= 0)
+      {
+        const int pos = atomicAdd(&s_bin_cur[b], 1);
+        if (in_smem)
+          ia16[pos] = (uint16_t)i;
+        else
+          ia32[pos] = (uint32_t)i;
+      }
+    }
+    if (tid < K) s_strip_cnt[tid] = s_bin_start[(tid + 1) * 25] - s_bin_start[tid * 25];
+  }
+  else if (split_root_here)
   {
     const int per = (n + kQtThreads - 1) / kQtThreads;
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
@@ -1264,9 +1337,11 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
     }
     __syncwarp();
     if (in_smem)
-      qt_simulate<uint16_t>(p, L, q, kp, keys, use_keys, ia16, ib16, n, need, node_cap, lane, live, n_alloc, root_pending, n_alloc, take);
+      qt_simulate<uint16_t>(p, L, q, kp, keys, use_keys, presort ? s_bin_start : nullptr, ia16, ib16, n, need, node_cap, lane, live, n_alloc, root_pending,
+                            n_alloc, take);
     else
-      qt_simulate<uint32_t>(p, L, q, kp, keys, use_keys, ia32, ib32, n, need, node_cap, lane, live, n_alloc, root_pending, n_alloc, take);
+      qt_simulate<uint32_t>(p, L, q, kp, keys, use_keys, presort ? s_bin_start : nullptr, ia32, ib32, n, need, node_cap, lane, live, n_alloc, root_pending,
+                            n_alloc, take);
     if (lane == 0)
     {
       s_n = n_alloc; // node slots ever used
