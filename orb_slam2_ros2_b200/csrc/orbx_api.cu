@@ -271,7 +271,7 @@ int build_tables(orbx_ctx *c)
     // Corners kept in shared memory: 3584 (4 CTAs per SM at the KITTI configuration) for images up to ~1 MP; larger images
     // produce proportionally more corners per level (~1 per 140-200 px on textured input), so they trade occupancy for a
     // list that fits: up to 160 KB per CTA.  Denser levels still work, through the global-scratch path.
-    int cap = std::min(3584, std::max(64, max_list));
+    int cap = std::min(3584, std::max(2048, max_list)); // >= 2048: the second u16 index array doubles as up to 1000 int scatter cursors
     if ((long long)g.width * g.height / 140 > 3584)
     {
       const size_t fixed = quadtree_smem_bytes(0, p.qt_node_cap, p.qt_big_cap, p.qt_cell_cap);

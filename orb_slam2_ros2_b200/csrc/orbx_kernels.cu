@@ -510,7 +510,9 @@ void launch_fast(const Params &p, int n_images, cudaStream_t s)
 // scratch; node pool, buckets and the big-node list are always in shared memory.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kQtBuckets = 256;  // small buckets hold counts 0..255
-constexpr int kQtMaxBinStrips = 8; // up to this many root strips the block pre-sorts two subdivision depths
+constexpr int kQtMaxBinStrips = 8; // up to this many root strips the block pre-sorts kQtPresort subdivision depths
+constexpr int kQtPresort = 3;      // depths 1..3 (5 slots each: quadrants 0-3, "on a split line")
+constexpr int kQtBinsPerStrip = 125;
 constexpr int kNodeBytes = 8 + 4 + 3 * 2 + 1;  // shared memory per node: rec {lo, cnt|depth|buf} | seq | next prev free | state
 constexpr int kNodeBoundWords = 4 * 2;          // global scratch per node (uint32 words): r0 r1 c0 c1, touched only below the key depth
 constexpr int kKeyLevels = 9;    // subdivision depths encoded in a key (3 bits each) below the 5-bit strip id
@@ -863,29 +865,22 @@ __device__ void qt_simulate(const Params &p, const Level &L, QtState &q, const u
         if (fixed) return qt_quadrant((long long)(e & 0xfffu) << kFixShift, (long long)((e >> 12) & 0xfffu) << kFixShift, mr, mc);
         return qt_quadrant((double)(e & 0xfffu), (double)((e >> 12) & 0xfffu), mr_d, mc_d);
       };
-      // The block sorted the corners by (strip, depth-1 digit, depth-2 digit) up front: the children of strip and depth-1
-      // nodes are contiguous sub-ranges of the parent's range, their sizes come from the bin table, nothing moves.
-      const bool presorted = bin_start != nullptr && keyed && depth <= 1;
+      // The block sorted the corners by (strip, digits of depths 1..3) up front: the children of nodes above depth 3 are
+      // contiguous sub-ranges of the parent's range, their sizes come from the bin table, nothing moves.
+      const bool presorted = bin_start != nullptr && keyed && depth < kQtPresort;
       if (presorted)
       {
+        // base-5 prefix of the node (strip, digits 1..depth) from the key of any of its corners
         const uint32_t key0 = keys[src[lo]];
-        const int sidx = (int)(key0 >> kKeyStripShift);
-        if (depth == 0)
-        {
-          const int b = sidx * 25;
-          t0 = (uint32_t)(bin_start[b + 5] - bin_start[b]);
-          t1 = (uint32_t)(bin_start[b + 10] - bin_start[b + 5]);
-          t2 = (uint32_t)(bin_start[b + 15] - bin_start[b + 10]);
-          t3 = (uint32_t)(bin_start[b + 20] - bin_start[b + 15]);
-        }
-        else
-        {
-          const int b = (sidx * 5 + (int)((key0 >> (kKeyStripShift - 3)) & 7u)) * 5;
-          t0 = (uint32_t)(bin_start[b + 1] - bin_start[b]);
-          t1 = (uint32_t)(bin_start[b + 2] - bin_start[b + 1]);
-          t2 = (uint32_t)(bin_start[b + 3] - bin_start[b + 2]);
-          t3 = (uint32_t)(bin_start[b + 4] - bin_start[b + 3]);
-        }
+        int prefix = (int)(key0 >> kKeyStripShift);
+        for (int j = 1; j <= depth; ++j) prefix = prefix * 5 + (int)((key0 >> (kKeyStripShift - 3 * j)) & 7u);
+        int span = 1; // bins below one child: 5^(kQtPresort - 1 - depth)
+        for (int j = depth + 1; j < kQtPresort; ++j) span *= 5;
+        const int b = prefix * 5 * span;
+        t0 = (uint32_t)(bin_start[b + span] - bin_start[b]);
+        t1 = (uint32_t)(bin_start[b + 2 * span] - bin_start[b + span]);
+        t2 = (uint32_t)(bin_start[b + 3 * span] - bin_start[b + 2 * span]);
+        t3 = (uint32_t)(bin_start[b + 4 * span] - bin_start[b + 3 * span]);
       }
       else if (cnt <= 32)
       {
@@ -1109,13 +1104,13 @@ __device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *
   }
 }
 
-__global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
+__global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_warp[kQtThreads / 32];
   __shared__ int s_n, s_take;
   __shared__ int s_strip_cnt[32];
-  __shared__ int s_bin_start[kQtMaxBinStrips * 25 + 1], s_bin_cur[kQtMaxBinStrips * 25];
+  __shared__ int s_bin_start[kQtMaxBinStrips * kQtBinsPerStrip + 1];
 
   // grid = (images, levels): CTAs are dispatched x-fastest, so every image's level 0 (the longest chain) starts first
   // and the short high levels fill the tail
@@ -1218,12 +1213,15 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
   {
     // counting sort by (strip, depth-1 digit, depth-2 digit), "on a split line" (7) last; order inside a bin is arbitrary
     // (nothing downstream depends on the order of a node's list: the best-response pick breaks ties by lowest index)
-    const int nb = K * 25;
+    const int nb = K * kQtBinsPerStrip;
+    int *s_bin_cur = in_smem ? (int *)ib16 : (int *)ib32; // scatter cursors: the second index array is still unused here
     auto bin_of = [&](uint32_t key) -> int {
       const uint32_t sidx = key >> kKeyStripShift;
       if (sidx == kKeyNoStrip) return -1;
-      const uint32_t d1 = (key >> (kKeyStripShift - 3)) & 7u, d2 = (key >> (kKeyStripShift - 6)) & 7u;
-      return (int)((sidx * 5u + min(d1, 4u)) * 5u + min(d2, 4u));
+      uint32_t b = sidx;
+#pragma unroll
+      for (int j = 1; j <= kQtPresort; ++j) b = b * 5u + min((key >> (kKeyStripShift - 3 * j)) & 7u, 4u);
+      return (int)b;
     };
     for (int i = tid; i <= nb; i += kQtThreads) s_bin_start[i] = 0;
     __syncthreads();
@@ -1234,14 +1232,21 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
     }
     __syncthreads();
     {
-      const int v = tid < nb ? s_bin_start[tid + 1] : 0; // nb <= 200 < kQtThreads
+      // exclusive scan over the bins: a contiguous run of bins per thread
+      const int per = (nb + kQtThreads - 1) / kQtThreads;
+      const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
+      int mine = 0;
+      for (int b = b0; b < b1; ++b) mine += s_bin_start[b + 1];
       int total;
-      const int off = block_exclusive_scan<kQtThreads>(v, total, s_warp);
-      if (tid < nb)
+      int off = block_exclusive_scan<kQtThreads>(mine, total, s_warp);
+      for (int b = b0; b < b1; ++b)
       {
-        s_bin_start[tid] = off;
-        s_bin_cur[tid] = off;
+        const int c = s_bin_start[b + 1];
+        s_bin_cur[b] = off;
+        off += c;
       }
+      __syncthreads();
+      for (int b = b0; b < b1; ++b) s_bin_start[b] = s_bin_cur[b];
       if (tid == 0) s_bin_start[nb] = total;
     }
     __syncthreads();
@@ -1257,7 +1262,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const Params p)
           ia32[pos] = (uint32_t)i;
       }
     }
-    if (tid < K) s_strip_cnt[tid] = s_bin_start[(tid + 1) * 25] - s_bin_start[tid * 25];
+    if (tid < K) s_strip_cnt[tid] = s_bin_start[(tid + 1) * kQtBinsPerStrip] - s_bin_start[tid * kQtBinsPerStrip];
   }
   else if (split_root_here)
   {
