@@ -283,36 +283,38 @@ def run_gpu_arm(args):
     }
 
     # ---- end to end through the host-buffer C-ABI call (`e2e`) -------------------------------------------------
-    ctx.set_stream(None)  # the library's own stream; the call synchronises internally
+    ctx.set_stream(None)  # the library's own streams; the call synchronises internally
+    # One call = one sequence of S frames from the pinned pool (the call streams it through the context's device slots);
+    # an e2e "step" is still B frames, so K steps are K * B frames = K * B / S calls.
+    S = n_chunks * B
     out = {
-        "kl": torch.empty((B, N, 28), dtype=torch.uint8).pin_memory(), "dl": torch.empty((B, N, 32), dtype=torch.uint8).pin_memory(),
-        "nl": torch.empty(B, dtype=torch.int32).pin_memory(), "kr": torch.empty((B, N, 28), dtype=torch.uint8).pin_memory(),
-        "dr": torch.empty((B, N, 32), dtype=torch.uint8).pin_memory(), "nr": torch.empty(B, dtype=torch.int32).pin_memory(),
-        "ur": torch.empty((B, N), dtype=torch.float64).pin_memory(), "dp": torch.empty((B, N), dtype=torch.float64).pin_memory(),
-        "nm": torch.empty(B, dtype=torch.int32).pin_memory(),
+        "kl": torch.empty((S, N, 28), dtype=torch.uint8).pin_memory(), "dl": torch.empty((S, N, 32), dtype=torch.uint8).pin_memory(),
+        "nl": torch.empty(S, dtype=torch.int32).pin_memory(), "kr": torch.empty((S, N, 28), dtype=torch.uint8).pin_memory(),
+        "dr": torch.empty((S, N, 32), dtype=torch.uint8).pin_memory(), "nr": torch.empty(S, dtype=torch.int32).pin_memory(),
+        "ur": torch.empty((S, N), dtype=torch.float64).pin_memory(), "dp": torch.empty((S, N), dtype=torch.float64).pin_memory(),
+        "nm": torch.empty(S, dtype=torch.int32).pin_memory(),
     }
     ptrs = [out[k].data_ptr() for k in ("kl", "dl", "nl", "kr", "dr", "nr", "ur", "dp", "nm")]
     h2d = 2 * B * fsz
-    d2h = sum(v.numel() * v.element_size() for v in out.values())
+    d2h = sum(v.numel() * v.element_size() for v in out.values()) * B // S
 
-    def host_step(i):
-        c = i % n_chunks
-        ctx.stereo_batch_ptr(B, h_left.data_ptr() + c * B * fsz, h_right.data_ptr() + c * B * fsz, W, fsz, ptrs)
+    def host_sequence():
+        ctx.stereo_batch_ptr(S, h_left.data_ptr(), h_right.data_ptr(), W, fsz, ptrs)
 
-    e2e_steps = max(3, min(args.steps, 20))
-    for i in range(3):
-        host_step(i)
+    e2e_calls = max(2, -(-max(3, min(args.steps, 40)) * B // S))
+    host_sequence()
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        host_step(3 + i)
+    for i in range(e2e_calls):
+        host_sequence()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * B / float(t.item())
-    e2e_matches = int(out["nm"].sum())
+    e2e_steps = e2e_calls * S // B
+    e2e_value = world * e2e_calls * S / float(t.item())
+    e2e_matches = int(out["nm"][:B].sum())
 
     # ---- single-frame latency (p50), one GPU ---------------------------------------------------------------------
     latency = None
@@ -329,7 +331,7 @@ def run_gpu_arm(args):
             if i >= 10:
                 dev_ms.append(a.elapsed_time(b))
         one.set_stream(None)
-        p1 = [q for q in ptrs]
+        p1 = [q for q in ptrs]  # the first frame's slice of the pinned output arrays
         for i in range(60):
             t0 = time.perf_counter()
             one.stereo_batch_ptr(1, h_left.data_ptr() + (i % P) * fsz, h_right.data_ptr() + (i % P) * fsz, W, fsz, p1)
@@ -353,7 +355,7 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(B, P), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "matches_last_step": e2e_matches},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "frames_per_call": S, "matches_first_step": e2e_matches},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
             "check": {"mean_keypoints_per_image": float(nk.mean()), "mean_matches_per_frame": float(nm.mean())},
         }

@@ -123,7 +123,9 @@ int orbx_grid_info(const orbx_ctx *ctx, int32_t *rows, int32_t *cols, float *min
 int orbx_get_grid(orbx_ctx *ctx, int frame, int32_t *cell_start, int32_t *entries /* [n_features] */);
 
 /* ---- batches (offline map / vocabulary building: frames are independent) -------------------------------- */
-/* n_frames <= max_batch stereo pairs from HOST memory (pinned memory makes the copies asynchronous).
+/* A sequence of n_frames stereo pairs (ANY length) from HOST memory; pinned memory makes the copies asynchronous.  The
+ * frames stream through the context's max_batch device slots in chunks, so that the H2D copy of one chunk, the kernels of
+ * another and the D2H copy of a third overlap.
  * left/right: frame f at base + f * frame_stride bytes, rows `stride` bytes apart.  Outputs are fixed-stride arrays:
  * kps_*[f * n_features + i], desc_*[(f * n_features + i) * 32], u_right/depth[f * n_features + i], n_*[f].
  * Returns after all results have landed in the output arrays. */

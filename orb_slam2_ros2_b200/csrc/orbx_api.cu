@@ -807,7 +807,6 @@ extern "C"
                         double *depth, int32_t *n_matches)
   {
     if (!c || !left || !right || n_frames < 1) return ORBX_ERR_INVALID_ARG;
-    if (n_frames > c->cfg.max_batch) return fail(c, ORBX_ERR_CAPACITY, "n_frames > max_batch");
     ORBX_CUDA(c, cudaSetDevice(c->device));
     const size_t W = (size_t)c->cfg.width, H = (size_t)c->cfg.height, N = (size_t)c->cfg.n_features;
     size_t fs = c->in_pitch * H, dstride = c->in_pitch;
@@ -823,53 +822,60 @@ extern "C"
       fs = frame_stride;
       dstride = stride;
     }
-    // Chunks of kChunk frames round-robin over the pipeline streams: the H2D copy of chunk k+1 and the D2H copy of chunk
-    // k-1 overlap the kernels of chunk k.  A single chunk runs on the context's stream (single-frame latency path).
-    const bool piped = n_frames > c->kChunk;
+    // The sequence streams through the context's max_batch device slots in chunks: chunk k lives in slot k % n_slots, and a
+    // slot is always driven by the same pipeline stream, so reusing it is ordered by that stream while the H2D copy of one
+    // chunk, the kernels of another and the D2H copy of a third overlap across streams.  A sequence that fits one chunk runs
+    // on the context's stream (single-frame latency path).
+    const int chunk = std::min(c->kChunk, c->cfg.max_batch);
+    const int n_slots = std::max(1, c->cfg.max_batch / chunk);
+    const bool piped = n_frames > chunk;
     if (piped)
     {
       ORBX_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
       for (int i = 0; i < c->kPipe; ++i) ORBX_CUDA(c, cudaStreamWaitEvent(c->pipe[i], c->fork_ev, 0));
     }
     int k = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += c->kChunk, ++k)
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++k)
     {
-      const int nf = std::min(c->kChunk, n_frames - f0);
-      cudaStream_t s = piped ? c->pipe[k % c->kPipe] : c->stream;
+      const int nf = std::min(chunk, n_frames - f0);
+      const int slot = k % n_slots;
+      const size_t d0 = (size_t)slot * chunk; // first device frame of the slot
+      cudaStream_t s = piped ? c->pipe[slot % c->kPipe] : c->stream;
       if (linear)
       {
-        ORBX_CUDA(c, cudaMemcpyAsync(dl + f0 * fs, left + f0 * frame_stride, fs * nf, cudaMemcpyHostToDevice, s));
-        ORBX_CUDA(c, cudaMemcpyAsync(dr + f0 * fs, right + f0 * frame_stride, fs * nf, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(c, cudaMemcpyAsync(dl + d0 * fs, left + f0 * frame_stride, fs * nf, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(c, cudaMemcpyAsync(dr + d0 * fs, right + f0 * frame_stride, fs * nf, cudaMemcpyHostToDevice, s));
       }
       else
       {
-        for (int f = f0; f < f0 + nf; ++f)
+        for (int f = 0; f < nf; ++f)
         {
-          ORBX_CUDA(c, cudaMemcpy2DAsync(dl + f * fs, c->in_pitch, left + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, s));
-          ORBX_CUDA(c, cudaMemcpy2DAsync(dr + f * fs, c->in_pitch, right + f * frame_stride, stride, W, H, cudaMemcpyHostToDevice, s));
+          ORBX_CUDA(c, cudaMemcpy2DAsync(dl + (d0 + f) * fs, c->in_pitch, left + (f0 + f) * frame_stride, stride, W, H, cudaMemcpyHostToDevice, s));
+          ORBX_CUDA(c, cudaMemcpy2DAsync(dr + (d0 + f) * fs, c->in_pitch, right + (f0 + f) * frame_stride, stride, W, H, cudaMemcpyHostToDevice, s));
         }
       }
-      int rc = run_stereo_range(c, s, f0, nf, dl, dr, dstride, fs);
+      int rc = run_stereo_range(c, s, (int)d0, nf, dl, dr, dstride, fs);
       if (rc) return rc;
       // results: left = even images, right = odd images -> one strided 2-D copy per array
-      const size_t i0 = 2 * (size_t)f0;
+      const size_t i0 = 2 * d0;
       if (kps_left) ORBX_CUDA(c, cudaMemcpy2DAsync(kps_left + f0 * N, kb, p.kps_und + i0 * N, 2 * kb, kb, nf, cudaMemcpyDeviceToHost, s));
       if (kps_right) ORBX_CUDA(c, cudaMemcpy2DAsync(kps_right + f0 * N, kb, p.kps + (i0 + 1) * N, 2 * kb, kb, nf, cudaMemcpyDeviceToHost, s));
       if (desc_left) ORBX_CUDA(c, cudaMemcpy2DAsync(desc_left + f0 * db, db, p.desc + i0 * db, 2 * db, db, nf, cudaMemcpyDeviceToHost, s));
       if (desc_right) ORBX_CUDA(c, cudaMemcpy2DAsync(desc_right + f0 * db, db, p.desc + (i0 + 1) * db, 2 * db, db, nf, cudaMemcpyDeviceToHost, s));
       if (n_left) ORBX_CUDA(c, cudaMemcpy2DAsync(n_left + f0, 4, p.n_kps + i0, 8, 4, nf, cudaMemcpyDeviceToHost, s));
       if (n_right) ORBX_CUDA(c, cudaMemcpy2DAsync(n_right + f0, 4, p.n_kps + i0 + 1, 8, 4, nf, cudaMemcpyDeviceToHost, s));
-      if (u_right) ORBX_CUDA(c, cudaMemcpyAsync(u_right + f0 * N, p.u_right + f0 * N, N * 8 * nf, cudaMemcpyDeviceToHost, s));
-      if (depth) ORBX_CUDA(c, cudaMemcpyAsync(depth + f0 * N, p.depth + f0 * N, N * 8 * nf, cudaMemcpyDeviceToHost, s));
-      if (n_matches) ORBX_CUDA(c, cudaMemcpyAsync(n_matches + f0, p.n_matches + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s));
+      if (u_right) ORBX_CUDA(c, cudaMemcpyAsync(u_right + f0 * N, p.u_right + d0 * N, N * 8 * nf, cudaMemcpyDeviceToHost, s));
+      if (depth) ORBX_CUDA(c, cudaMemcpyAsync(depth + f0 * N, p.depth + d0 * N, N * 8 * nf, cudaMemcpyDeviceToHost, s));
+      if (n_matches) ORBX_CUDA(c, cudaMemcpyAsync(n_matches + f0, p.n_matches + d0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, s));
     }
     if (piped)
       for (int i = 0; i < c->kPipe; ++i) ORBX_CUDA(c, cudaStreamSynchronize(c->pipe[i]));
     else
       ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->last_images = 2 * n_frames;
+    // introspection (get_pyramid / get_grid) refers to the device slots, i.e. to the frames of the last pass over them
+    c->last_frames = std::min(n_frames, n_slots * chunk);
+    c->last_images = 2 * c->last_frames;
     c->last_stereo = 1;
-    c->last_frames = n_frames;
     return ORBX_OK;
   }
 

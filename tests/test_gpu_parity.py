@@ -172,8 +172,11 @@ def test_errors():
     with pytest.raises(api.FileNotOpenError):
         api.ORBExtractor(np.zeros((240, 320), np.uint8), 500, 4, 1.2, "/nonexistent/brief_template.txt", 20, 7)
     ctx = api.Context(320, 240, 500, 4, 1.2, max_batch=2)
-    with pytest.raises(ValueError):
-        ctx.stereo_batch(np.zeros((3, 240, 320), np.uint8), np.zeros((3, 240, 320), np.uint8))
+    import torch
+
+    d = torch.zeros((3, 240, 320), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):  # device-resident batches are limited by max_batch (host sequences are not)
+        ctx.stereo_batch_device(3, d.data_ptr(), d.data_ptr(), 320, 320 * 240)
     ctx.close()
 
 
@@ -312,6 +315,29 @@ def test_init_grid_matches_restatement(oracle):
         for j in range(cols):
             assert np.array_equal(got[i][j], exp[i][j]), (i, j)
     ctx.close()
+
+
+def test_long_sequence_streams_through_the_slots(oracle):
+    """a host sequence longer than max_batch: every frame's results equal the single-frame results"""
+    c = synth.KITTI
+    cam = _camera(c)
+    n = 37
+    base_l, base_r = synth.synth_stereo_pool(c["height"], c["width"], 5, seed0=90)
+    order = np.arange(n) % 5
+    lefts, rights = np.ascontiguousarray(base_l[order]), np.ascontiguousarray(base_r[order])
+    ctx = api.Context(c["width"], c["height"], 800, 8, 1.2, camera=cam, max_batch=16)  # 2 slots of 8 frames
+    ob = ctx.stereo_batch(lefts, rights)
+    one = api.Context(c["width"], c["height"], 800, 8, 1.2, camera=cam, max_batch=1)
+    ref = [one.stereo_frame(base_l[i], base_r[i]) for i in range(5)]
+    for f in range(n):
+        r = ref[order[f]]
+        a = ob.n_left[f]
+        assert (a, ob.n_right[f], ob.n_matches[f]) == (len(r.kps_left), len(r.kps_right), r.n_matches), f
+        assert np.array_equal(ob.kps_left[f, :a].view(np.uint8), r.kps_left.view(np.uint8))
+        assert np.array_equal(ob.desc_left[f, :a], r.desc_left) and np.array_equal(ob.desc_right[f, : ob.n_right[f]], r.desc_right)
+        assert np.array_equal(ob.u_right[f, :a], r.u_right) and np.array_equal(ob.depth[f, :a], r.depth)
+    ctx.close()
+    one.close()
 
 
 def test_batch_equals_single_frames(oracle):
