@@ -52,7 +52,7 @@ typedef struct orbx_keypoint {
 typedef struct orbx_config {
   int32_t width, height;   /* input image size (8-bit, single channel) */
   int32_t n_features;      /* ORBExtractor.nFeatures */
-  int32_t n_levels;        /* ORBExtractor.nLevels */
+  int32_t n_levels;        /* ORBExtractor.nLevels (1..16) */
   float scale_factor;      /* ORBExtractor.scaleFactor (> 1) */
   int32_t ini_th_fast;     /* ORBExtractor.iniThFAST */
   int32_t min_th_fast;     /* ORBExtractor.minThFAST */

@@ -41,6 +41,7 @@ struct orbx_ctx
   int last_images = 0;          // images processed by the most recent call (for orbx_get_pyramid)
   int last_stereo = 0;
   int last_frames = 0;
+  LevelMaps maps; // TMA descriptors of the pyramid levels (kernel parameter, __grid_constant__)
   float min_u = 0, min_v = 0, max_u = 0, max_v = 0; // undistorted image bounds (VirtualFrame ctor, Frame.h:33-43)
   // host-batch pipeline: chunks of frames round-robin over kPipe streams so that H2D, kernels and D2H overlap
   static constexpr int kPipeMax = 8;
@@ -207,7 +208,7 @@ int build_tables(orbx_ctx *c)
         ce.y0 = iniY;
         ce.pw = maxX - iniX;
         ce.ph = maxY - iniY;
-        if (ce.pw > kMaxPatch || ce.ph > kMaxPatch) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cell patch exceeds 70 px");
+        if (ce.pw > kMaxPatch || ce.ph > kMaxPatch) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cell patch exceeds 65 px");
         const int zw = std::max(0, ce.pw - 6), zh = std::max(0, ce.ph - 6);
         ce.cap = std::max(1, ((zw + 1) / 2) * ((zh + 1) / 2)); // strict 8-neighbour maxima cannot be denser than this
         ce.slot = (int)slot_off;
@@ -219,6 +220,8 @@ int build_tables(orbx_ctx *c)
       }
     }
     L.n_level_cells = cell_index - L.cell_base;
+    L.fast_box_h = 1;
+    for (int ci = L.cell_base; ci < cell_index; ++ci) L.fast_box_h = std::max(L.fast_box_h, c->cells[ci].ph);
 
     // quadtree root fan-out (initSplit :81-96)
     L.n_ini = (int)std::round((double)w / (double)h);
@@ -396,6 +399,7 @@ int alloc_buffers(orbx_ctx *c)
 Params params_at(const orbx_ctx *c, int img0, int frame0)
 {
   Params p = c->p;
+  p.img0 = img0;
   const size_t N = (size_t)c->cfg.n_features, i = (size_t)img0, f = (size_t)frame0;
   p.pyr += i * p.pyr_img_stride;
   p.blur += i * p.pyr_img_stride;
@@ -430,7 +434,7 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
   p.in_frame_stride = frame_stride;
   ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)nf * sizeof(int), s));
   launch_pyramid(p, 2 * nf, s);
-  launch_fast(p, 2 * nf, s);
+  launch_fast(p, c->maps, 2 * nf, s);
   launch_quadtree(p, 2 * nf, c->qt_smem, s);
   launch_orient_brief(p, 2 * nf, s);
   launch_rowindex(p, nf, s);
@@ -441,11 +445,39 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
   return ORBX_OK;
 }
 
+// TMA descriptors: one 3-D byte tensor {pitch, rows, images} per pyramid level over the context's pyr buffer, box = the
+// level's largest FAST patch (80 bytes wide = the shared-memory patch pitch).  cuTensorMapEncodeTiled is a driver entry point.
+int build_level_maps(orbx_ctx *c)
+{
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  ORBX_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  std::vector<CUtensorMap> maps(c->levels.size());
+  for (size_t l = 0; l < c->levels.size(); ++l)
+  {
+    const Level &L = c->levels[l];
+    const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)c->n_img_max};
+    const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)c->p.pyr_img_stride};
+    const cuuint32_t box[3] = {80u, (cuuint32_t)L.fast_box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = ((EncodeFn)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->p.pyr + L.pyr_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed for level " + std::to_string(l));
+  }
+  std::memset(&c->maps, 0, sizeof(c->maps));
+  for (size_t l = 0; l < maps.size(); ++l) c->maps.m[l] = maps[l];
+  c->p.img0 = 0;
+  return ORBX_OK;
+}
+
 // ORBExtractor ctor + extract for n_images device-resident images
 int run_extract(orbx_ctx *c, const Params &p, int n_images)
 {
   launch_pyramid(p, n_images, c->stream);
-  launch_fast(p, n_images, c->stream);
+  launch_fast(p, c->maps, n_images, c->stream);
   launch_quadtree(p, n_images, c->qt_smem, c->stream);
   launch_orient_brief(p, n_images, c->stream);
   c->launches += 4;
@@ -577,6 +609,7 @@ extern "C"
       if ((rc = build_tables(c))) break;
       c->cfg.pattern = nullptr; // not retained
       if ((rc = alloc_buffers(c))) break;
+      if ((rc = build_level_maps(c))) break;
       if (quadtree_configure(c->qt_smem) != 0)
       {
         rc = fail(c, ORBX_ERR_CUDA, "cudaFuncSetAttribute(quadtree_kernel, MaxDynamicSharedMemorySize)");
@@ -750,7 +783,7 @@ extern "C"
     ORBX_CUDA(c, cudaEventRecord(ev[0], c->stream));
     launch_pyramid(p, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[1], c->stream));
-    launch_fast(p, ni, c->stream);
+    launch_fast(p, c->maps, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[2], c->stream));
     launch_quadtree(p, ni, c->qt_smem, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[3], c->stream));

@@ -12,6 +12,7 @@
 //   u_right, depth [frame][n_features]       doubles, -1 = no match
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -20,7 +21,7 @@
 namespace orbx
 {
 
-constexpr int kMaxLevels = 32;
+constexpr int kMaxLevels = 16;  // one TMA descriptor per level travels as a kernel parameter (LevelMaps)
 constexpr int kEdge = 16;       // FAST ROI margin: mnBorderSize - 3 (src/ORBExtractor.cc:334-337)
 constexpr int kTileW = 64;      // pyramid/blur output tile
 constexpr int kTileH = 32;
@@ -28,7 +29,7 @@ constexpr int kHalo = 3;        // 7x7 Gaussian
 constexpr int kPyrThreads = 256;
 constexpr int kFastThreads = 128;
 constexpr int kQtThreads = 256;
-constexpr int kMaxPatch = 70;   // largest FAST cell patch edge: a cell is < 60 px wide, + 6 px apron; zone <= 64
+constexpr int kMaxPatch = 65;   // largest FAST cell patch edge: a cell is at most 59 px wide, + 6 px apron
 constexpr int kMaxStrips = 255; // root split fan-out: round(w/h) vertical strips
 constexpr uint32_t kNil = 0xFFFFu;
 
@@ -42,6 +43,7 @@ struct Level
   int area2x;       // exact 2x2 decimation: cv::resize re-routes INTER_LINEAR to INTER_AREA
   // FAST cell grid (src/ORBExtractor.cc:334-343)
   int n_cols, n_rows, w_cell, h_cell;
+  int fast_box_h;   // rows of the TMA box that fetches one FAST patch of this level (its tallest patch)
   int cell_base;    // index of this level's first cell in the cell table
   int n_level_cells;
   // quadtree (src/ORBExtractor.cc:81-96,144-173)
@@ -73,6 +75,13 @@ struct RTab
   short min_row, max_row;
 };
 
+// TMA descriptors of the pyramid levels: 3-D {pitch, rows, images} byte tensors over `pyr`; box = 80 bytes x the level's
+// tallest FAST patch.  Passed to the kernel by value (__grid_constant__).
+struct LevelMaps
+{
+  CUtensorMap m[kMaxLevels];
+};
+
 struct Params
 {
   int n_levels, n_features, ini_th, min_th;
@@ -92,6 +101,7 @@ struct Params
   const void *depth_img;
   size_t depth_stride, depth_frame_stride;
   int depth_type;
+  int img0; // index of this launch's first image inside the context buffers (the TMA descriptors address whole buffers)
   // per-image buffers
   uint8_t *pyr, *blur;
   size_t pyr_img_stride;
@@ -130,7 +140,7 @@ struct Params
 
 // launchers (orbx_kernels.cu); every call enqueues exactly one kernel on `s`
 void launch_pyramid(const Params &p, int n_images, cudaStream_t s);
-void launch_fast(const Params &p, int n_images, cudaStream_t s);
+void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
 void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
 void launch_rowindex(const Params &p, int n_frames, cudaStream_t s);

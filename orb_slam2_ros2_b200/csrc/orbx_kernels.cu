@@ -261,7 +261,7 @@ void launch_pyramid(const Params &p, int n_images, cudaStream_t s)
 //   corner at threshold t  <=>  m > t;  cv score = m - 1;  keep iff score > all 8 neighbours' scores (strict), where a
 //   neighbour that is not a corner at t, or lies outside the cell's detection zone, scores 0.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kPatPitch = 80;                 // bytes: patch rows keep the level image's 4-byte alignment (x0 & 3)
+constexpr int kPatPitch = 80;                 // bytes = width of the TMA box: (x0 & 15) + patch width (<= 65)
 constexpr int kZoneMax = 64;                  // detection zone edge (patch edge - 6); one 64-bit mask per zone row
 constexpr int kMapPitch = kZoneMax + 4;       // 68
 
@@ -316,12 +316,50 @@ __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
   return best;
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// one 3-D box {x .. x + boxW, y .. y + boxH, z} of a byte tensor -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
+               "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+               : "memory");
+}
+
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kCandSeg = (kZoneMax / kFastWarps) * kZoneMax; // candidates one warp can produce (its rows x 64)
 
-__global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Params p)
+__global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Params p, const __grid_constant__ LevelMaps maps)
 {
-  __shared__ __align__(16) uint8_t s_pat[(kZoneMax + 6) * kPatPitch];
+  __shared__ __align__(128) uint8_t s_pat[(kZoneMax + 6) * kPatPitch];
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ __align__(16) uint8_t s_map[(kZoneMax + 2) * kMapPitch + 16]; // + 16: zeroed with 16-byte stores
   __shared__ uint16_t s_cand[kFastWarps * kCandSeg];
   __shared__ unsigned long long s_keep[kZoneMax];
@@ -343,20 +381,17 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
     return;
   }
 
-  // patch rows as aligned 32-bit words (one warp per row)
-  const int xoff = c.x0 & 3;
+  // The patch (plus whatever lies right of / below it up to the box size; out-of-range bytes are zero-filled) arrives
+  // through one TMA box load issued by thread 0; the map zeroing of the first threshold pass overlaps it.
+  if (tid == 0)
   {
-    const int nw = (xoff + pw + 3) >> 2; // <= 19 words
-    if (lane < nw)
-    {
-      const uint32_t *g = reinterpret_cast<const uint32_t *>(lvl + (size_t)(c.y0 + wid) * pitch + (c.x0 - xoff)) + lane;
-      uint32_t *d = reinterpret_cast<uint32_t *>(s_pat) + wid * (kPatPitch / 4) + lane;
-      const int gstep = kFastWarps * (pitch >> 2); // pitch is a multiple of 16
-#pragma unroll 4
-      for (int y = wid; y < ph; y += kFastWarps, g += gstep, d += kFastWarps * (kPatPitch / 4)) *d = *g;
-    }
+    mbar_init(&s_bar, 1);
+    mbar_expect_tx(&s_bar, (uint32_t)(kPatPitch * L.fast_box_h));
+    tma_load_3d(s_pat, &maps.m[c.level], c.x0 & ~15, c.y0, p.img0 + img, &s_bar); // TMA needs 16-byte aligned row starts
   }
-  const uint8_t *pat0 = s_pat + 3 * kPatPitch + 3 + xoff; // zone pixel (0,0)
+  const uint8_t *pat0 = s_pat + 3 * kPatPitch + 3 + (c.x0 & 15); // zone pixel (0,0); 15 + 65 <= the 80-byte box
+
+  bool patch_ready = false;
   uint16_t *my_cand = s_cand + wid * kCandSeg;
   unsigned long long keep = 0ull;
 
@@ -371,7 +406,12 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
       for (int i = tid; i < ((zh + 2) * kMapPitch + 15) / 16; i += kFastThreads) m128[i] = make_uint4(0u, 0u, 0u, 0u);
       if (tid < kZoneMax) s_keep[tid] = 0ull;
     }
-    __syncthreads();
+    __syncthreads(); // also orders thread 0's mbarrier init before everybody's wait
+    if (!patch_ready)
+    {
+      mbar_wait(&s_bar, 0);
+      patch_ready = true;
+    }
 
     // Stage 1 (every zone pixel): at least 2 of the 4 compass ring pixels are brighter (darker) than the centre by more
     // than t -- a necessary condition for a 9-arc.  Survivors go to a per-warp candidate segment (warp-local counter, no
@@ -485,10 +525,10 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
   if (tid == 0) *cnt_out = min(total, c.cap);
 }
 
-void launch_fast(const Params &p, int n_images, cudaStream_t s)
+void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s)
 {
   dim3 grid(p.n_cells, n_images);
-  fast_cells_kernel<<<grid, kFastThreads, 0, s>>>(p);
+  fast_cells_kernel<<<grid, kFastThreads, 0, s>>>(p, maps);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
