@@ -175,6 +175,63 @@ class CudaArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
+def bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cpu=True, th=15.0, reps=20):
+    """ORBMatcher::searchByProjection's inner step (findFeaturesInArea + exclusion + getBestMatch) for N queries per frame
+    against the B device-resident frames of one stereo batch: queries = each frame's own keypoints as "seen in the last
+    frame" (moved by N(0, 3) px, 6 descriptor bits flipped), 30 % of the frame's keypoints excluded."""
+    ctx.set_stream(stream.cuda_stream)
+    res = ctx.stereo_batch_device(B, d_left.data_ptr(), d_right.data_ptr(), W, fsz)
+    kps = ctx.read_device(res.kps_und, (2 * B, N), api.KP_DTYPE)[0::2]
+    desc = ctx.read_device(res.desc, (2 * B, N, 32), np.uint8)[0::2]
+    nk = ctx.read_device(res.n_kps, (2 * B,), np.int32)[0::2]
+    qs, qds, exs = np.zeros((B, N), api.AREA_QUERY_DTYPE), np.zeros((B, N, 32), np.uint8), np.zeros((B, N), np.uint8)
+    for f in range(B):
+        q, qd, ex, _ = synth.synth_area_queries(kps[f][: nk[f]], desc[f][: nk[f]], N, 500 + f, W, H, CFG["n_levels"], th)
+        qs[f], qds[f], exs[f, : len(ex)] = q, qd, ex
+    with torch.cuda.stream(stream):
+        t_q = torch.from_numpy(qs.view(np.uint8).reshape(B, -1)).cuda()
+        t_d, t_x = torch.from_numpy(qds).cuda(), torch.from_numpy(exs).cuda()
+        o = [torch.zeros((B, N), dtype=torch.int32, device="cuda") for _ in range(3)]
+        o_ratio = torch.zeros((B, N), dtype=torch.float32, device="cuda")
+
+        def launch():
+            ctx.search_in_area_batch_device(B, N, t_q.data_ptr(), t_d.data_ptr(), 0, t_x.data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o_ratio.data_ptr(),
+                                            o[2].data_ptr())
+
+        for _ in range(3):
+            launch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            launch()
+        e1.record(stream)
+        stream.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    n_cand = o[2].cpu().numpy()
+    accepted = int(((o[0].cpu().numpy() >= 0) & (o[1].cpu().numpy() < 50) & (o_ratio.cpu().numpy() < 0.6)).sum())
+    alg = B * N * (24 + 32 + 16) + int(n_cand.sum()) * (32 + 4 + 2)  # queries in, results out, per candidate: descriptor + octave + grid entry
+    peak, _ = measured_peaks()
+    out = {
+        "metric": "area-search queries/s (findFeaturesInArea + getBestMatch, %d queries/frame, th=%g)" % (N, th), "value": B * N / (ms * 1e-3),
+        "unit": "queries/s", "kernel": "area_match", "kernel_ms": ms, "frames_per_launch": B, "mean_candidates": float(n_cand.mean()),
+        "accepted_per_frame": accepted / B, "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg},
+    }
+    if cpu:
+        from oracle import oracle_py as O
+
+        bounds = ctx.grid_info()[2:]
+        sf = ctx.scaled_factors()
+        t0 = time.perf_counter()
+        nf = min(B, 8)
+        for f in range(nf):
+            O.search_in_area(kps[f][: nk[f]], desc[f][: nk[f]], bounds, sf, qs[f], qds[f], exs[f][: nk[f]])
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nf * N / dt, "unit": "queries/s", "cores": 1, "kind": "port", "sample": "%d frames x %d queries (incl. initGrid per frame)" % (nf, N)}
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -341,6 +398,11 @@ def run_gpu_arm(args):
                    "note": "one stereo pair per call; device = inputs and results in HBM, host_to_host = pinned host images in, results out"}
         one.close()
 
+    # ---- tracking-side matchers: a secondary line, not part of the headline metric ------------
+    matchers = None
+    if rank == 0 and not args.no_matchers:
+        matchers = bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cpu=(world == 1 and not args.no_cpu_baseline))
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -356,7 +418,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(B, P), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "frames_per_call": S, "matches_first_step": e2e_matches},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency, "matchers": matchers,
             "check": {"mean_keypoints_per_image": float(nk.mean()), "mean_matches_per_frame": float(nm.mean())},
         }
         print(json.dumps(line), flush=True)
@@ -374,6 +436,7 @@ def main():
     ap.add_argument("--pool", type=int, default=256, help="distinct synthetic pairs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-matchers", action="store_true", help="skip the secondary tracking-matcher measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -166,6 +166,42 @@ int orbx_synchronize(orbx_ctx *ctx);
 /* synchronous device-to-host copy of `bytes` bytes of a device result array (after draining the context's stream) */
 int orbx_read_device(orbx_ctx *ctx, const void *device_ptr, void *host_dst, size_t bytes);
 
+/* ---- tracking-side Hamming matchers -------------------------------------- */
+/* One query of VirtualFrame::findFeaturesInArea (src/Frame.cc:286-311): the keypoint `kp` (position in undistorted
+ * image coordinates + octave), the radius BEFORE its multiplication by getScaledFactor2(kp.octave), and the inclusive
+ * octave range of the candidates. */
+typedef struct orbx_area_query {
+  float x, y;
+  float radius;
+  int32_t octave;
+  int32_t min_level, max_level;
+} orbx_area_query; /* 24 bytes */
+
+/* replaces the inner step of both ORBMatcher::searchByProjection overloads (src/ORBMatcher.cc:296-343 constant-velocity /
+ * fuse, :575-591 local map), against frame `frame` of the most recent stereo / RGB-D call (its keypoints, descriptors and
+ * grid are resident on the device): for query i, candidates = findFeaturesInArea(kp, radius, min_level, max_level) in
+ * the reference's order, minus those with exclude[idx] != 0 (the "already has a map point" filter, :322-331; NULL = keep
+ * all), then ORBMatcher::getBestMatch (src/ORBMatcher.cc:967-990) with query_desc[i*32 .. +32).
+ * Outputs (any may be NULL): best_idx[i] = index of the best candidate among the frame's left keypoints or -1 when no
+ * candidate is left (the reference `continue`s), best_dist[i] = its Hamming distance (INT_MAX if none), ratio[i] =
+ * float(best) / float(second) exactly as the reference computes it (its "second" ignores displaced minima),
+ * n_candidates[i].  The caller applies `ratio < mfRatio && dist < mnMinThreshold`.
+ * Windows that leave the grid are clipped (the reference indexes mGrids out of range there). */
+int orbx_search_in_area(orbx_ctx *ctx, int frame, int n_queries, const orbx_area_query *queries,
+                        const uint8_t *query_desc, const uint8_t *exclude /* [n_features] */, int32_t *best_idx,
+                        int32_t *best_dist, float *ratio, int32_t *n_candidates);
+/* same, for frames 0..n_frames-1 of the most recent *_device call, everything in DEVICE memory, asynchronous on the
+ * context's stream: frame f uses d_queries[f * query_stride + i], i < d_n_queries[f] (NULL: query_stride queries each),
+ * d_exclude[f * n_features + idx] (or NULL); outputs are [n_frames][query_stride]. */
+int orbx_search_in_area_batch_device(orbx_ctx *ctx, int n_frames, int query_stride, const orbx_area_query *d_queries,
+                                     const uint8_t *d_query_desc, const int32_t *d_n_queries, const uint8_t *d_exclude,
+                                     int32_t *d_best_idx, int32_t *d_best_dist, float *d_ratio, int32_t *d_n_candidates);
+/* replaces: ORBMatcher::verifyAngle (src/ORBMatcher.cc:1013-1051): keeps the matches that fall into the three fullest
+ * of the 30 bins of angle(kps1[queryIdx]) - angle(kps2[trainIdx]); survivors are written back in place in the
+ * reference's order (ascending bin, original order inside a bin); *n_out = their number. */
+int orbx_verify_angle(orbx_ctx *ctx, int n_matches, int32_t *query_idx, int32_t *train_idx, float *distance,
+                      const orbx_keypoint *kps1, int n1, const orbx_keypoint *kps2, int n2, int32_t *n_out);
+
 /* ---- introspection for benchmarks / profiles ----------------------------------------------------------- */
 #define ORBX_N_STAGES 6
 /* Same work as orbx_stereo_batch_device, with a CUDA event recorded on the stream after every kernel; blocks until

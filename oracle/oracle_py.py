@@ -21,6 +21,8 @@ KP_DTYPE = np.dtype(
 )
 assert KP_DTYPE.itemsize == 28
 MAX_LEVELS = 32
+AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("radius", "<f4"), ("octave", "<i4"), ("min_level", "<i4"), ("max_level", "<i4")])
+assert AREA_QUERY_DTYPE.itemsize == 24
 
 u8p = C.POINTER(C.c_uint8)
 i32p = C.POINTER(C.c_int)
@@ -77,6 +79,14 @@ def lib():
         L.oracle_pyramid_free.argtypes = [C.POINTER(_Pyramid)]
         L.oracle_extract.restype = C.c_int
         L.oracle_extract.argtypes = [C.POINTER(_Pyramid), C.c_int, C.c_int, f32p, C.c_void_p, u8p, f64p, i32p]
+        L.oracle_init_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, i32p, i32p, i32p, C.c_int, i32p]
+        L.oracle_find_features_in_area.restype = C.c_int
+        L.oracle_find_features_in_area.argtypes = [C.c_void_p, i32p, i32p, C.c_int, C.c_int, f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                                   C.c_int, C.c_int, C.c_int, i32p]
+        L.oracle_search_in_area.argtypes = [C.c_void_p, u8p, C.c_int, i32p, i32p, C.c_int, C.c_int, f32p, C.c_float, C.c_float, C.c_void_p, u8p, C.c_int,
+                                            u8p, i32p, i32p, f32p, i32p]
+        L.oracle_verify_angle.restype = C.c_int
+        L.oracle_verify_angle.argtypes = [C.c_int, i32p, i32p, f32p, C.c_void_p, C.c_void_p]
         L.oracle_search_by_stereo.restype = C.c_int
         L.oracle_search_by_stereo.argtypes = [C.POINTER(_Pyramid), C.POINTER(_Pyramid), C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int,
                                               C.c_float, C.c_float, f64p, f64p, i32p]
@@ -301,6 +311,46 @@ def init_grid(kps: np.ndarray, min_u, min_v, max_u, max_v):
     return [[np.asarray(cell, np.int32) for cell in row] for row in grid]
 
 
+def grid_csr(kps, min_u, min_v, max_u, max_v):
+    """oracle_init_grid (VirtualFrame::initGrid, src/Frame.cc:53-69) -> (rows, cols, start[rows*cols+1], entries)"""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    rows, cols = C.c_int(0), C.c_int(0)
+    cap = 1 << 16
+    start = np.zeros(cap + 1, np.int32)
+    entries = np.zeros(max(len(kps), 1), np.int32)
+    lib().oracle_init_grid(kps.ctypes.data, len(kps), min_u, min_v, max_u, max_v, C.byref(rows), C.byref(cols), _ptr(start, i32p), cap, _ptr(entries, i32p))
+    nc = rows.value * cols.value
+    return rows.value, cols.value, start[: nc + 1].copy(), entries[: start[nc]].copy()
+
+
+def search_in_area(kps, desc, bounds, sf, queries, q_desc, exclude=None):
+    """oracle_search_in_area.  bounds = (min_u, min_v, max_u, max_v) -> dict(best_idx, best_dist, ratio, n_cand)"""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries, AREA_QUERY_DTYPE)
+    q_desc = np.ascontiguousarray(q_desc, np.uint8)
+    sf = np.ascontiguousarray(sf, np.float32)
+    ex = None if exclude is None else np.ascontiguousarray(exclude, np.uint8)
+    rows, cols, start, entries = grid_csr(kps, *bounds)
+    n = len(queries)
+    bi, bd, nc = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    ra = np.zeros(n, np.float32)
+    lib().oracle_search_in_area(kps.ctypes.data, _ptr(desc, u8p), len(kps), _ptr(start, i32p), _ptr(entries, i32p), rows, cols, _ptr(sf, f32p), bounds[2],
+                                bounds[3], queries.ctypes.data, _ptr(q_desc, u8p), n, _ptr(ex, u8p), _ptr(bi, i32p), _ptr(bd, i32p), _ptr(ra, f32p),
+                                _ptr(nc, i32p))
+    return dict(best_idx=bi, best_dist=bd, ratio=ra, n_cand=nc)
+
+
+def verify_angle(query_idx, train_idx, distance, kps1, kps2):
+    """oracle_verify_angle -> (query_idx, train_idx, distance) of the surviving matches"""
+    qi = np.ascontiguousarray(query_idx, np.int32).copy()
+    ti = np.ascontiguousarray(train_idx, np.int32).copy()
+    di = np.ascontiguousarray(distance, np.float32).copy()
+    k1, k2 = np.ascontiguousarray(kps1, KP_DTYPE), np.ascontiguousarray(kps2, KP_DTYPE)
+    m = lib().oracle_verify_angle(len(qi), _ptr(qi, i32p), _ptr(ti, i32p), _ptr(di, f32p), k1.ctypes.data, k2.ctypes.data)
+    return qi[:m], ti[:m], di[:m]
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # the compiled reference (oracle/_ref/libref.so)
 _ref = None
@@ -329,6 +379,12 @@ def ref():
         R.ref_set_camera.argtypes = [C.c_float] * 5 + [f32p]
         R.ref_get_bf.restype = C.c_float
         R.ref_undistort.argtypes = [f32p, C.c_int]
+        R.ref_init_grid.restype = C.c_int
+        R.ref_init_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, i32p, i32p, i32p, C.c_int, i32p]
+        R.ref_search_in_area.argtypes = [C.c_void_p, u8p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, f32p, C.c_int, C.c_void_p, u8p, C.c_int, u8p,
+                                         i32p, i32p, f32p, i32p]
+        R.ref_verify_angle.restype = C.c_int
+        R.ref_verify_angle.argtypes = [C.c_int, i32p, i32p, f32p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         R.ref_bench_stereo.restype = C.c_double
         R.ref_bench_stereo.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_long)]
@@ -413,6 +469,41 @@ def ref_undistort(xy):
     out = np.ascontiguousarray(xy, np.float32).copy()
     ref().ref_undistort(_ptr(out, f32p), out.shape[0])
     return out
+
+
+def ref_grid_csr(kps, min_u, min_v, max_u, max_v):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    rows, cols = C.c_int(0), C.c_int(0)
+    cap = 1 << 16
+    start = np.zeros(cap + 1, np.int32)
+    entries = np.zeros(max(len(kps), 1), np.int32)
+    nc = ref().ref_init_grid(kps.ctypes.data, len(kps), min_u, min_v, max_u, max_v, C.byref(rows), C.byref(cols), _ptr(start, i32p), cap, _ptr(entries, i32p))
+    assert nc >= 0
+    return rows.value, cols.value, start[: nc + 1].copy(), entries[: start[nc]].copy()
+
+
+def ref_search_in_area(kps, desc, bounds, sf, queries, q_desc, exclude=None):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries, AREA_QUERY_DTYPE)
+    q_desc = np.ascontiguousarray(q_desc, np.uint8)
+    sf = np.ascontiguousarray(sf, np.float32)
+    ex = None if exclude is None else np.ascontiguousarray(exclude, np.uint8)
+    n = len(queries)
+    bi, bd, nc = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    ra = np.zeros(n, np.float32)
+    ref().ref_search_in_area(kps.ctypes.data, _ptr(desc, u8p), len(kps), bounds[0], bounds[1], bounds[2], bounds[3], _ptr(sf, f32p), len(sf),
+                             queries.ctypes.data, _ptr(q_desc, u8p), n, _ptr(ex, u8p), _ptr(bi, i32p), _ptr(bd, i32p), _ptr(ra, f32p), _ptr(nc, i32p))
+    return dict(best_idx=bi, best_dist=bd, ratio=ra, n_cand=nc)
+
+
+def ref_verify_angle(query_idx, train_idx, distance, kps1, kps2):
+    qi = np.ascontiguousarray(query_idx, np.int32).copy()
+    ti = np.ascontiguousarray(train_idx, np.int32).copy()
+    di = np.ascontiguousarray(distance, np.float32).copy()
+    k1, k2 = np.ascontiguousarray(kps1, KP_DTYPE), np.ascontiguousarray(kps2, KP_DTYPE)
+    m = ref().ref_verify_angle(len(qi), _ptr(qi, i32p), _ptr(ti, i32p), _ptr(di, f32p), k1.ctypes.data, len(k1), k2.ctypes.data, len(k2))
+    return qi[:m], ti[:m], di[:m]
 
 
 def ref_bench_stereo(left_pool, right_pool, template_path, n_frames, workers, n_features=2000, n_levels=8, scale=1.2, ini_th=20, min_th=7):

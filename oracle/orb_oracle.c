@@ -10,6 +10,7 @@
  */
 #include "orb_oracle.h"
 
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,6 +27,10 @@ static inline int cv_floor_d(double v) {
   return i - (i > v);
 }
 static inline int cv_ceil_d(double v) {
+  int i = (int)v;
+  return i + (i < v);
+}
+static inline int cv_ceil_f(float v) {
   int i = (int)v;
   return i + (i < v);
 }
@@ -686,4 +691,165 @@ void oracle_rgbd_lookup(const void *depth_raw, int is_float, int w, int h, size_
       u_right[i] = kps_undist[i].x - bf / d;
     }
   }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tracking-side area matchers
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* VirtualFrame::initGrid, src/Frame.cc:53-69.  Keypoints whose cell lies outside the grid index mGrids out of range in
+ * the reference; they are left out here.  CSR: start[rows*cols+1], entries[n] (keypoint order inside a cell). */
+void oracle_init_grid(const oracle_keypoint *kps, int n, float min_u, float min_v, float max_u, float max_v, int *rows_out,
+                      int *cols_out, int *start, int cap_cells, int *entries) {
+  int rows = cv_ceil_f((float)(max_v - min_v) / 48u);
+  int cols = cv_ceil_f((float)(max_u - min_u) / 64u);
+  *rows_out = rows;
+  *cols_out = cols;
+  if (rows <= 0 || cols <= 0 || rows * cols > cap_cells) return;
+  int nc = rows * cols;
+  for (int c = 0; c <= nc; ++c) start[c] = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = 0; i < n; ++i) {
+      long r = cv_floor_f(kps[i].y / 48u), c = cv_floor_f(kps[i].x / 64u);
+      if (r < 0 || r >= rows || c < 0 || c >= cols) continue;
+      if (pass == 0)
+        ++start[r * cols + c + 1];
+      else
+        entries[start[r * cols + c]++] = i;
+    }
+    if (pass == 0)
+      for (int c = 0; c < nc; ++c) start[c + 1] += start[c];
+    else {
+      for (int c = nc; c > 0; --c) start[c] = start[c - 1];
+      start[0] = 0;
+    }
+  }
+}
+
+/* VirtualFrame::findFeaturesInArea, src/Frame.cc:286-311 (getScaledFactor2: include/ORB_SLAM2/Frame.h:207).
+ * A window that leaves the grid (negative maxX/maxY, or a cell index beyond the grid) is undefined behaviour in the
+ * reference (size_t loop counters over mGrids); here the cell range is clipped to the grid. */
+int oracle_find_features_in_area(const oracle_keypoint *kps, const int *start, const int *entries, int rows, int cols,
+                                 const float *sf, float max_u, float max_v, float x, float y, float radius, int octave,
+                                 int min_level, int max_level, int *out) {
+  float sf2 = (float)pow((double)sf[octave], 2);
+  radius = radius * sf2;
+  int min_x = cv_round_f(x - radius), max_x = cv_round_f(x + radius);
+  int min_y = cv_round_f(y - radius), max_y = cv_round_f(y + radius);
+  if (min_x < 0) min_x = 0;
+  if (max_x > (int)max_u) max_x = (int)max_u;
+  if (min_y < 0) min_y = 0;
+  if (max_y > (int)max_v) max_y = (int)max_v;
+  if (max_x < 0 || max_y < 0) return 0;
+  int c0 = cv_floor_f((float)min_x / 64u), c1 = cv_floor_f((float)max_x / 64u);
+  int r0 = cv_floor_f((float)min_y / 48u), r1 = cv_floor_f((float)max_y / 48u);
+  if (c1 > cols - 1) c1 = cols - 1;
+  if (r1 > rows - 1) r1 = rows - 1;
+  int n = 0;
+  for (int r = r0; r <= r1; ++r)
+    for (int c = c0; c <= c1; ++c)
+      for (int e = start[r * cols + c]; e < start[r * cols + c + 1]; ++e) {
+        int id = entries[e], o = kps[id].octave;
+        if (o <= max_level && o >= min_level) out[n++] = id;
+      }
+  return n;
+}
+
+/* ORBMatcher::getBestMatch, src/ORBMatcher.cc:967-990: the running second-best is only updated by candidates that are
+ * NOT a new minimum, and the displaced minimum is not demoted into it. */
+int oracle_best_match(const uint8_t *desc, const uint8_t *cand_desc, const int *cand_idx, int n, int *best_dist,
+                      float *ratio) {
+  int min_d = INT_MAX, second_d = INT_MAX, min_idx = 0;
+  for (int k = 0; k < n; ++k) {
+    int d = desc_distance(desc, cand_desc + 32 * (size_t)cand_idx[k]);
+    if (d < min_d) {
+      min_d = d;
+      min_idx = cand_idx[k];
+    } else if (d < second_d)
+      second_d = d;
+  }
+  *ratio = (float)min_d / (float)second_d;
+  *best_dist = min_d;
+  return min_idx;
+}
+
+/* The inner step shared by both ORBMatcher::searchByProjection overloads (src/ORBMatcher.cc:296-343 and :575-591):
+ * candidates in the area, minus the excluded keypoints (:322-331), then getBestMatch.  best_idx = -1 / n_cand = 0 when
+ * nothing is left (the reference `continue`s). */
+void oracle_search_in_area(const oracle_keypoint *kps, const uint8_t *desc, int n_kps, const int *start,
+                           const int *entries, int rows, int cols, const float *sf, float max_u, float max_v,
+                           const oracle_area_query *q, const uint8_t *q_desc, int n_q, const uint8_t *exclude,
+                           int *best_idx, int *best_dist, float *ratio, int *n_cand) {
+  int *cand = (int *)malloc(sizeof(int) * (size_t)(n_kps > 0 ? n_kps : 1));
+  for (int i = 0; i < n_q; ++i) {
+    int n = oracle_find_features_in_area(kps, start, entries, rows, cols, sf, max_u, max_v, q[i].x, q[i].y, q[i].radius,
+                                         q[i].octave, q[i].min_level, q[i].max_level, cand);
+    if (exclude) {
+      int m = 0;
+      for (int k = 0; k < n; ++k)
+        if (!exclude[cand[k]]) cand[m++] = cand[k];
+      n = m;
+    }
+    n_cand[i] = n;
+    best_idx[i] = -1;
+    best_dist[i] = INT_MAX;
+    ratio[i] = 0.f;
+    if (n == 0) continue;
+    best_idx[i] = oracle_best_match(q_desc + 32 * (size_t)i, desc, cand, n, &best_dist[i], &ratio[i]);
+  }
+  free(cand);
+}
+
+/* ORBMatcher::verifyAngle, src/ORBMatcher.cc:1013-1051 (mnBinNum = 30, mnBinChoose = 3): keeps the matches of the three
+ * fullest bins of the angle-difference histogram, emitted in ascending bin order, original order inside a bin.
+ * Arrays are rewritten in place; returns the new count. */
+int oracle_verify_angle(int n, int *query_idx, int *train_idx, float *distance, const oracle_keypoint *kps1,
+                        const oracle_keypoint *kps2) {
+  enum { kBins = 30, kChoose = 3 };
+  int *bin = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  int count[kBins] = {0};
+  for (int i = 0; i < n; ++i) {
+    float diff = kps1[query_idx[i]].angle - kps2[train_idx[i]].angle;
+    diff = diff >= 0 ? diff : 360 + diff;
+    int b = (int)(diff / (360 / kBins));
+    if (b == 30) b = 0;
+    bin[i] = b;
+    ++count[b];
+  }
+  int good[kBins] = {0};
+  for (int k = 0; k < kChoose; ++k) {
+    int max_size = 0, max_id = 0, init = 0;
+    for (int b = 0; b < kBins; ++b) {
+      if (good[b]) continue;
+      if (count[b] > max_size) {
+        max_id = b;
+        max_size = count[b];
+        init = 1;
+      }
+    }
+    if (init) good[max_id] = 1;
+  }
+  int *qi = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1)), *ti = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  float *di = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  int m = 0;
+  for (int b = 0; b < kBins; ++b) {
+    if (!good[b]) continue;
+    for (int i = 0; i < n; ++i)
+      if (bin[i] == b) {
+        qi[m] = query_idx[i];
+        ti[m] = train_idx[i];
+        di[m] = distance[i];
+        ++m;
+      }
+  }
+  for (int i = 0; i < m; ++i) {
+    query_idx[i] = qi[i];
+    train_idx[i] = ti[i];
+    distance[i] = di[i];
+  }
+  free(bin);
+  free(qi);
+  free(ti);
+  free(di);
+  return m;
 }

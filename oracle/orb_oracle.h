@@ -97,6 +97,33 @@ void oracle_rgbd_lookup(const void *depth_raw, int is_float, int w, int h, size_
                         const oracle_keypoint *kps_raw, const oracle_keypoint *kps_undist, int n, float bf,
                         double *u_right, double *depth);
 
+/* ---- tracking-side area matchers ---- */
+typedef struct oracle_area_query {
+  float x, y;     /* kp.pt */
+  float radius;   /* before the sf[octave]^2 scaling of findFeaturesInArea */
+  int32_t octave; /* kp.octave */
+  int32_t min_level, max_level;
+} oracle_area_query;
+
+/* VirtualFrame::initGrid, src/Frame.cc:53-69 -> CSR (start[rows*cols+1], entries[n]) */
+void oracle_init_grid(const oracle_keypoint *kps, int n, float min_u, float min_v, float max_u, float max_v, int *rows_out,
+                      int *cols_out, int *start, int cap_cells, int *entries);
+/* VirtualFrame::findFeaturesInArea, src/Frame.cc:286-311 */
+int oracle_find_features_in_area(const oracle_keypoint *kps, const int *start, const int *entries, int rows, int cols,
+                                 const float *sf, float max_u, float max_v, float x, float y, float radius, int octave,
+                                 int min_level, int max_level, int *out);
+/* ORBMatcher::getBestMatch, src/ORBMatcher.cc:967-990; returns the best candidate's index */
+int oracle_best_match(const uint8_t *desc, const uint8_t *cand_desc, const int *cand_idx, int n, int *best_dist,
+                      float *ratio);
+/* inner step of ORBMatcher::searchByProjection, src/ORBMatcher.cc:296-343 / :575-591 */
+void oracle_search_in_area(const oracle_keypoint *kps, const uint8_t *desc, int n_kps, const int *start,
+                           const int *entries, int rows, int cols, const float *sf, float max_u, float max_v,
+                           const oracle_area_query *q, const uint8_t *q_desc, int n_q, const uint8_t *exclude,
+                           int *best_idx, int *best_dist, float *ratio, int *n_cand);
+/* ORBMatcher::verifyAngle, src/ORBMatcher.cc:1013-1051 (in place; returns the new count) */
+int oracle_verify_angle(int n, int *query_idx, int *train_idx, float *distance, const oracle_keypoint *kps1,
+                        const oracle_keypoint *kps2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,8 @@
-// Stand-in for ORB_SLAM2_ROS2::Frame (TEST INFRASTRUCTURE ONLY): same member names / getters as the reference's
-// Frame (include/ORB_SLAM2/Frame.h:263-274,340-347) restricted to what ORBMatcher::searchByStereo touches.
+// Stand-in for ORB_SLAM2_ROS2::VirtualFrame / Frame (TEST INFRASTRUCTURE ONLY): same member names / getters as the
+// reference's classes (include/ORB_SLAM2/Frame.h:28,204-207,263-299,340-347) restricted to what the compiled line ranges
+// touch: ORBMatcher::searchByStereo, VirtualFrame::initGrid and VirtualFrame::findFeaturesInArea.  The bodies of
+// getScaledFactor / getScaledFactor2 are the reference's own lines (Frame.h:204,207), extracted with sed at build time
+// into ref_frame_h_ranges.inc (never stored in this repo).
 #pragma once
 #include "ORB_SLAM2/ORBExtractor.h"
 
@@ -7,12 +10,26 @@ namespace ORB_SLAM2_ROS2
 {
 class VirtualFrame
 {
+public:
+  typedef std::vector<std::vector<std::vector<std::size_t>>> GridsType;
+  std::vector<cv::KeyPoint> mvFeatsLeft;
+  float mfMaxU = 0, mfMaxV = 0, mfMinU = 0, mfMinV = 0;
+  GridsType mGrids;
+  static std::vector<float> mvfScaledFactors;
+  static bool mbScaled;
+  static std::size_t mnNextID;
+  static unsigned mnGridHeight;
+  static unsigned mnGridWidth;
+
+  void initGrid();
+  std::vector<std::size_t> findFeaturesInArea(const cv::KeyPoint &kp, float radius, int minNLevel, int maxNLevel);
+#include "ref_frame_h_ranges.inc"
 };
 class Frame : public VirtualFrame
 {
 public:
   typedef std::shared_ptr<Frame> SharedPtr;
-  std::vector<cv::KeyPoint> mvFeatsLeft, mvFeatsRight;
+  std::vector<cv::KeyPoint> mvFeatsRight;
   std::vector<cv::Mat> mvLeftDescriptor, mRightDescriptor;
   std::vector<double> mvDepths, mvFeatsRightU;
   cv::Mat mLeftIm, mRightIm;

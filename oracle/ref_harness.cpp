@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <limits>
 #include <memory>
 #include <sstream>
 #include <thread>
@@ -32,6 +33,12 @@
 #include "ref_frame_standin.h"
 
 using namespace ORB_SLAM2_ROS2;
+
+namespace ref_private // ref_stereo_tu.cpp: wrappers around ORBMatcher's private statics
+{
+std::pair<std::size_t, int> best_match(const cv::Mat &desc, const std::vector<cv::Mat> &all, const std::vector<std::size_t> &cand, float &ratio);
+void verify_angle(std::vector<cv::DMatch> &m, const std::vector<cv::KeyPoint> &k1, const std::vector<cv::KeyPoint> &k2);
+} // namespace ref_private
 
 namespace
 {
@@ -240,6 +247,97 @@ extern "C"
       xy[2 * i] = kps[i].pt.x;
       xy[2 * i + 1] = kps[i].pt.y;
     }
+  }
+
+  // VirtualFrame::initGrid (src/Frame.cc:53-69) on the given keypoints -> CSR; returns rows * cols, or -1 if cap is small
+  int ref_init_grid(const oracle_keypoint *kps, int n, float min_u, float min_v, float max_u, float max_v, int *rows, int *cols, int *start, int cap_cells,
+                    int *entries)
+  {
+    VirtualFrame f;
+    f.mvFeatsLeft.resize(n);
+    for (int i = 0; i < n; ++i) std::memcpy(&f.mvFeatsLeft[i], &kps[i], sizeof(oracle_keypoint));
+    f.mfMinU = min_u, f.mfMinV = min_v, f.mfMaxU = max_u, f.mfMaxV = max_v;
+    f.initGrid();
+    *rows = (int)f.mGrids.size();
+    *cols = *rows ? (int)f.mGrids[0].size() : 0;
+    if (*rows * *cols > cap_cells) return -1;
+    int k = 0, c = 0;
+    for (auto &row : f.mGrids)
+      for (auto &cell : row)
+      {
+        start[c++] = k;
+        for (auto id : cell) entries[k++] = (int)id;
+      }
+    start[c] = k;
+    return c;
+  }
+
+  // The inner step of both ORBMatcher::searchByProjection overloads, composed from the reference's own compiled
+  // functions: VirtualFrame::initGrid + findFeaturesInArea (src/Frame.cc:53-69,286-311), the exclusion filter of
+  // src/ORBMatcher.cc:322-331 (a plain copy_if here) and ORBMatcher::getBestMatch (:967-990).
+  void ref_search_in_area(const oracle_keypoint *kps, const uint8_t *desc, int n_kps, float min_u, float min_v, float max_u, float max_v, const float *sf,
+                          int n_levels, const oracle_area_query *q, const uint8_t *q_desc, int n_q, const uint8_t *exclude, int *best_idx, int *best_dist,
+                          float *ratio, int *n_cand)
+  {
+    VirtualFrame f;
+    f.mvFeatsLeft.resize(n_kps);
+    std::vector<cv::Mat> descs(n_kps);
+    for (int i = 0; i < n_kps; ++i)
+    {
+      std::memcpy(&f.mvFeatsLeft[i], &kps[i], sizeof(oracle_keypoint));
+      descs[i] = cv::Mat(1, 32, CV_8U, (void *)(desc + 32 * (size_t)i), 32);
+    }
+    f.mfMinU = min_u, f.mfMinV = min_v, f.mfMaxU = max_u, f.mfMaxV = max_v;
+    VirtualFrame::mvfScaledFactors.assign(sf, sf + n_levels);
+    f.initGrid();
+    // findFeaturesInArea reads cell floor(mfMaxU / 64) / row floor(mfMaxV / 48), which lies one past the grid whenever the
+    // bound is a multiple of the cell size (320x240, 640x480 ...): out-of-range vector reads in the reference.  One empty
+    // guard row and column turn them into reads of empty cells (= the clipping the oracle and the CUDA path apply).
+    for (auto &row : f.mGrids) row.emplace_back();
+    f.mGrids.emplace_back(f.mGrids.empty() ? 1 : f.mGrids[0].size());
+    for (int i = 0; i < n_q; ++i)
+    {
+      cv::KeyPoint kp;
+      kp.pt = cv::Point2f(q[i].x, q[i].y);
+      kp.octave = q[i].octave;
+      std::vector<std::size_t> cand = f.findFeaturesInArea(kp, q[i].radius, q[i].min_level, q[i].max_level), kept;
+      for (auto id : cand)
+        if (!exclude || !exclude[id]) kept.push_back(id);
+      n_cand[i] = (int)kept.size();
+      best_idx[i] = -1;
+      best_dist[i] = std::numeric_limits<int>::max();
+      ratio[i] = 0.f;
+      if (kept.empty()) continue;
+      cv::Mat d(1, 32, CV_8U, (void *)(q_desc + 32 * (size_t)i), 32);
+      float r = 0.f;
+      auto best = ref_private::best_match(d, descs, kept, r);
+      best_idx[i] = (int)best.first;
+      best_dist[i] = best.second;
+      ratio[i] = r;
+    }
+  }
+
+  // ORBMatcher::verifyAngle (src/ORBMatcher.cc:1013-1051), in place; returns the new count
+  int ref_verify_angle(int n, int *query_idx, int *train_idx, float *distance, const oracle_keypoint *kps1, int n1, const oracle_keypoint *kps2, int n2)
+  {
+    std::vector<cv::KeyPoint> k1(n1), k2(n2);
+    for (int i = 0; i < n1; ++i) std::memcpy(&k1[i], &kps1[i], sizeof(oracle_keypoint));
+    for (int i = 0; i < n2; ++i) std::memcpy(&k2[i], &kps2[i], sizeof(oracle_keypoint));
+    std::vector<cv::DMatch> m(n);
+    for (int i = 0; i < n; ++i)
+    {
+      m[i].queryIdx = query_idx[i];
+      m[i].trainIdx = train_idx[i];
+      m[i].distance = distance[i];
+    }
+    ref_private::verify_angle(m, k1, k2);
+    for (size_t i = 0; i < m.size(); ++i)
+    {
+      query_idx[i] = m[i].queryIdx;
+      train_idx[i] = m[i].trainIdx;
+      distance[i] = m[i].distance;
+    }
+    return (int)m.size();
   }
 
   // CPU baseline: process `n_frames` stereo frames drawn round-robin from a pool of `pool` pairs (each w x h, dense),

@@ -1,17 +1,39 @@
-// Translation unit that compiles the reference's stereo matcher VERBATIM (TEST INFRASTRUCTURE ONLY).
+// Translation unit that compiles the reference's matcher / frame-grid functions VERBATIM (TEST INFRASTRUCTURE ONLY).
 //
-// ORBMatcher.cc as a whole needs Frame/KeyFrame/MapPoint/DBoW3/g2o; its stereo functions do not.  The Makefile
-// extracts lines 18-81 (searchByStereo), 841-1011 (pixelSADMatch, SAD, createRowIndexDB, descDistance, getBestMatch,
-// getPitch) and 1086-1093 (static constants) of /root/reference/src/ORB_SLAM2/src/ORBMatcher.cc with sed into a
-// temporary file (REF_STEREO_INC, never stored in this repo) that is #included below, after the reference's REAL
-// ORBMatcher.h / Camera.h and a stand-in Frame exposing exactly the members those lines touch
-// (include/ORB_SLAM2/Frame.h:263-274,340-347).
+// ORBMatcher.cc and Frame.cc as a whole need KeyFrame/MapPoint/DBoW3/g2o; the functions below do not.  The Makefile
+// extracts with sed, into temporary files that are never stored in this repo:
+//   ref_orbmatcher_ranges.inc  ORBMatcher.cc 18-81 (searchByStereo), 841-1051 (pixelSADMatch, SAD, createRowIndexDB,
+//                              descDistance, getBestMatch, getPitch, verifyAngle), 1086-1093 (static constants)
+//   ref_frame_cc_ranges.inc    Frame.cc 53-69 (VirtualFrame::initGrid), 286-311 (VirtualFrame::findFeaturesInArea),
+//                              355-359 (static members)
+//   ref_frame_h_ranges.inc     Frame.h 204, 207 (getScaledFactor, getScaledFactor2; included by ref_frame_standin.h)
+// They are #included below after the reference's REAL ORBMatcher.h / Camera.h and a stand-in VirtualFrame/Frame exposing
+// exactly the members those lines touch.  getBestMatch / verifyAngle are private statics of ORBMatcher: the
+// access-specifier override applies to this TU only and the C wrappers at the bottom expose them to the harness.
+#include <limits>
+
 #include "ORB_SLAM2/Camera.h"
+#include "ORB_SLAM2/ORBExtractor.h"
+#define private public
 #include "ORB_SLAM2/ORBMatcher.h"
+#undef private
 
 #include "ref_frame_standin.h"
 
 namespace ORB_SLAM2_ROS2
 {
-#include REF_STEREO_INC
+#include "ref_orbmatcher_ranges.inc"
+#include "ref_frame_cc_ranges.inc"
 } // namespace ORB_SLAM2_ROS2
+
+namespace ref_private
+{
+std::pair<std::size_t, int> best_match(const cv::Mat &desc, const std::vector<cv::Mat> &all, const std::vector<std::size_t> &cand, float &ratio)
+{
+  return ORB_SLAM2_ROS2::ORBMatcher::getBestMatch(desc, all, cand, ratio);
+}
+void verify_angle(std::vector<cv::DMatch> &m, const std::vector<cv::KeyPoint> &k1, const std::vector<cv::KeyPoint> &k2)
+{
+  ORB_SLAM2_ROS2::ORBMatcher::verifyAngle(m, k1, k2);
+}
+} // namespace ref_private

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, "liborbx.so")
 KP_DTYPE = np.dtype(
     [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")]
 )
+AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("radius", "<f4"), ("octave", "<i4"), ("min_level", "<i4"), ("max_level", "<i4")])
 
 ORBX_OK = 0
 ORBX_ERR_INVALID_ARG = -1
@@ -71,6 +72,7 @@ EXPORTS = [
     "orbx_num_levels", "orbx_level_info", "orbx_extract", "orbx_get_pyramid", "orbx_stereo_frame", "orbx_rgbd_frame", "orbx_stereo_batch",
     "orbx_stereo_batch_device", "orbx_extract_batch_device", "orbx_rgbd_batch_device", "orbx_synchronize", "orbx_launch_count", "orbx_algorithmic_bytes",
     "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name", "orbx_debug_run_quadtree", "orbx_grid_info", "orbx_get_grid",
+    "orbx_search_in_area", "orbx_search_in_area_batch_device", "orbx_verify_angle",
 ]
 
 _lib = None
@@ -124,6 +126,9 @@ def load_library(build_if_missing: bool = True):
     L.orbx_debug_run_quadtree.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int]
     L.orbx_grid_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)] + [C.POINTER(C.c_float)] * 4
     L.orbx_get_grid.argtypes = [vp, C.c_int, vp, vp]
+    L.orbx_search_in_area.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_search_in_area_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_verify_angle.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int32)]
     _lib = L
     return L
 
@@ -327,6 +332,44 @@ class Context:
         sel[:, :2] -= 16
         return sel
 
+    # ---- tracking-side matchers ----------------------------------------------------------
+    def search_in_area(self, queries: np.ndarray, query_desc: np.ndarray, exclude: np.ndarray | None = None, frame: int = 0) -> dict:
+        """findFeaturesInArea (src/Frame.cc:286-311) + exclusion (src/ORBMatcher.cc:322-331) + getBestMatch (:967-990) for
+        every query against frame `frame` of the last stereo / RGB-D call -> dict(best_idx, best_dist, ratio, n_cand)"""
+        q = np.ascontiguousarray(queries, AREA_QUERY_DTYPE)
+        d = np.ascontiguousarray(query_desc, np.uint8)
+        n = len(q)
+        assert d.shape == (n, 32)
+        ex = None
+        if exclude is not None:
+            ex = np.zeros(self.n_features, np.uint8)
+            ex[: len(exclude)] = np.asarray(exclude).astype(bool)
+        bi, bd, nc = np.full(n, -1, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ra = np.zeros(n, np.float32)
+        rc = self._L.orbx_search_in_area(self._h, frame, n, q.ctypes.data, d.ctypes.data, ex.ctypes.data if ex is not None else None, bi.ctypes.data,
+                                         bd.ctypes.data, ra.ctypes.data, nc.ctypes.data)
+        _check(self._h, rc, "orbx_search_in_area")
+        return dict(best_idx=bi, best_dist=bd, ratio=ra, n_cand=nc)
+
+    def search_in_area_batch_device(self, n_frames, query_stride, d_queries, d_query_desc, d_n_queries, d_exclude, d_best_idx, d_best_dist, d_ratio,
+                                    d_n_cand):
+        """device-pointer variant over the frames of the last *_device call (asynchronous on the context's stream)"""
+        rc = self._L.orbx_search_in_area_batch_device(self._h, n_frames, query_stride, *[C.c_void_p(x or 0) for x in (
+            d_queries, d_query_desc, d_n_queries, d_exclude, d_best_idx, d_best_dist, d_ratio, d_n_cand)])
+        _check(self._h, rc, "orbx_search_in_area_batch_device")
+
+    def verify_angle(self, query_idx, train_idx, distance, kps1: np.ndarray, kps2: np.ndarray):
+        """ORBMatcher::verifyAngle (src/ORBMatcher.cc:1013-1051) -> (query_idx, train_idx, distance) of the survivors"""
+        qi = np.ascontiguousarray(query_idx, np.int32).copy()
+        ti = np.ascontiguousarray(train_idx, np.int32).copy()
+        di = np.ascontiguousarray(distance, np.float32).copy()
+        k1, k2 = np.ascontiguousarray(kps1, KP_DTYPE), np.ascontiguousarray(kps2, KP_DTYPE)
+        m = C.c_int32(0)
+        rc = self._L.orbx_verify_angle(self._h, len(qi), qi.ctypes.data, ti.ctypes.data, di.ctypes.data, k1.ctypes.data, len(k1), k2.ctypes.data, len(k2),
+                                       C.byref(m))
+        _check(self._h, rc, "orbx_verify_angle")
+        return qi[: m.value], ti[: m.value], di[: m.value]
+
     # ---- batches ----------------------------------------------------------------------------------------------------
     def stereo_batch(self, left: np.ndarray, right: np.ndarray, out: "StereoBatchBuffers | None" = None):
         """left/right: (n, H, W) uint8 host arrays (pinned memory makes the copies asynchronous)."""
@@ -500,3 +543,73 @@ class Frame:
         ctx = _context_for(h, w, nFeatures, nLevels, scale, maxThresh, minThresh, cam, briefF, pattern)
         r = ctx.rgbd_frame(colorImg, depthImg)
         return Frame(r.kps, r.desc, None, None, r.u_right, r.depth, int((r.depth > 0).sum()), {"ctx": ctx, "kps_raw": r.kps_raw})
+
+
+class ORBMatcher:
+    """Host mirror of the tracking-side entry points of ORB_SLAM2_ROS2::ORBMatcher (include/ORB_SLAM2/ORBMatcher.h:17-124)
+    whose inner loops run on the device (Context.search_in_area / verify_angle).  Map points are not modelled: the callers
+    pass the per-keypoint "has a usable map point" masks the reference derives from them."""
+
+    mnMaxThreshold, mnMinThreshold, mnMeanThreshold = 100, 50, 75  # src/ORBMatcher.cc:1086-1088
+    mnBinNum, mnBinChoose = 30, 3                                   # :1091-1092
+
+    def __init__(self, ratio: float = 0.6, checkOri: bool = True):
+        self.mfRatio = np.float32(ratio)
+        self.mbCheckOri = checkOri
+
+    def searchByProjection(self, pFrame1: "Frame", kps2: np.ndarray, desc2: np.ndarray, valid2: np.ndarray, hasMp1: np.ndarray | None, th: float,
+                           tlc_z: float = 0.0, baseline: float = 0.0, bFuse: bool = False) -> np.ndarray:
+        """searchByProjection(pFrame1, pFrame2, matches, th, bFuse) (src/ORBMatcher.cc:265-347).  kps2/desc2 = pFrame2's
+        left keypoints/descriptors, valid2[idx] = "mps2[idx] is a good map point" (and, for bFuse, in view of pFrame1),
+        hasMp1[i] = "pFrame1 keypoint i already has a good map point" (dropped from the candidates unless bFuse),
+        tlc_z = z of pFrame1's camera centre in pFrame2's camera frame (:275-281).  -> (m, 3) int32 rows (queryIdx =
+        pFrame1 keypoint, trainIdx = idx, distance), ascending idx."""
+        ctx: Context = pFrame1.extra["ctx"]
+        idx = np.nonzero(np.asarray(valid2).astype(bool))[0]
+        q = np.zeros(len(idx), AREA_QUERY_DTYPE)
+        q["x"], q["y"], q["octave"], q["radius"] = kps2["x"][idx], kps2["y"][idx], kps2["octave"][idx], np.float32(th)
+        up = abs(np.float32(tlc_z)) > np.float32(baseline) and tlc_z > 0
+        down = abs(np.float32(tlc_z)) > np.float32(baseline) and not tlc_z > 0
+        if up:
+            q["min_level"], q["max_level"] = q["octave"], 7
+        elif down:
+            q["min_level"], q["max_level"] = 0, q["octave"]
+        else:
+            q["min_level"], q["max_level"] = np.maximum(0, q["octave"] - 1), np.minimum(q["octave"] + 1, 7)
+        r = ctx.search_in_area(q, desc2[idx], None if bFuse else hasMp1, frame=pFrame1.extra.get("frame", 0))
+        ok = (r["n_cand"] > 0) & (r["ratio"] < self.mfRatio) & (r["best_dist"] < self.mnMinThreshold)
+        return np.stack([r["best_idx"][ok], idx[ok].astype(np.int32), r["best_dist"][ok]], axis=1).astype(np.int32)
+
+    def searchByProjectionMapPoints(self, pframe: "Frame", uv: np.ndarray, octave: np.ndarray, cosTheta: np.ndarray, mp_desc: np.ndarray, th: float,
+                                    hasMp: np.ndarray, bFuse: bool = False, nLevels: int = 8):
+        """searchByProjection(pframe, mapPoints, th, matches, bFuse) (src/ORBMatcher.cc:561-621) for the map points that
+        passed isInVision: uv = projections, octave = predictLevel(distance), cosTheta = viewing-angle cosine, mp_desc =
+        their descriptors, hasMp[i] = "pframe keypoint i has a good map point".
+        -> (nMatches, matches): matches = (m, 3) int32 rows (keypoint idx, map point idx, distance); for bFuse = False these
+        are the map points newly assigned (first map point to claim a free keypoint wins, :594-601)."""
+        ctx: Context = pframe.extra["ctx"]
+        n = len(uv)
+        q = np.zeros(n, AREA_QUERY_DTYPE)
+        q["x"], q["y"], q["octave"] = uv[:, 0], uv[:, 1], octave
+        q["radius"] = np.where(np.asarray(cosTheta, np.float32) > np.float32(0.998), np.float32(2.5), np.float32(4.0)) * np.float32(th)
+        q["min_level"], q["max_level"] = np.maximum(0, q["octave"] - 1), np.minimum(nLevels - 1, q["octave"] + 1)
+        r = ctx.search_in_area(q, mp_desc, None, frame=pframe.extra.get("frame", 0))
+        ok = (r["n_cand"] > 0) & (r["best_dist"] < self.mnMinThreshold) & (r["ratio"] < self.mfRatio)
+        taken = np.asarray(hasMp).astype(bool).copy()
+        n_matches = 0 if bFuse else int(taken.sum())
+        out = []
+        for i in np.nonzero(ok)[0]:
+            k = int(r["best_idx"][i])
+            if bFuse:
+                out.append((k, i, r["best_dist"][i]))
+                n_matches += 1
+            elif not taken[k]:
+                taken[k] = True
+                out.append((k, i, r["best_dist"][i]))
+                n_matches += 1
+        return n_matches, np.asarray(out, np.int32).reshape(-1, 3)
+
+    def verifyAngle(self, ctx: Context, matches: np.ndarray, keyPoints1: np.ndarray, keyPoints2: np.ndarray) -> np.ndarray:
+        """ORBMatcher::verifyAngle (src/ORBMatcher.cc:1013-1051) on (m, 3) rows (queryIdx, trainIdx, distance)"""
+        qi, ti, di = ctx.verify_angle(matches[:, 0], matches[:, 1], matches[:, 2].astype(np.float32), keyPoints1, keyPoints2)
+        return np.stack([qi, ti, di.astype(np.int32)], axis=1).astype(np.int32).reshape(-1, 3)

@@ -50,6 +50,9 @@ struct orbx_ctx
   cudaStream_t pipe[kPipeMax] = {};
   cudaEvent_t fork_ev = nullptr;
   cudaEvent_t join_ev[kPipeMax] = {};
+  // staging for the host-side matcher calls (orbx_search_in_area / orbx_verify_angle), grown on demand
+  uint8_t *match_scratch = nullptr;
+  size_t match_scratch_bytes = 0;
 };
 
 namespace
@@ -658,6 +661,7 @@ extern "C"
     for (auto &je : c->join_ev)
       if (je) cudaEventDestroy(je);
     for (void *q : c->allocs) cudaFree(q);
+    if (c->match_scratch) cudaFree(c->match_scratch);
     delete c;
   }
 
@@ -1017,6 +1021,129 @@ extern "C"
     ORBX_CUDA(c, cudaMemcpy(e16.data(), c->p.grid_entries + (size_t)frame * N, N * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     const int total = cell_start[nc];
     for (int i = 0; i < total && i < (int)N; ++i) entries[i] = e16[i];
+    return ORBX_OK;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------------
+  // tracking-side matchers
+  static int match_scratch(orbx_ctx *c, size_t bytes, uint8_t **out)
+  {
+    if (bytes > c->match_scratch_bytes)
+    {
+      ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (c->match_scratch) cudaFree(c->match_scratch);
+      c->match_scratch = nullptr;
+      c->match_scratch_bytes = 0;
+      const size_t want = bytes + bytes / 2 + 4096;
+      ORBX_CUDA(c, cudaMalloc((void **)&c->match_scratch, want));
+      c->match_scratch_bytes = want;
+    }
+    *out = c->match_scratch;
+    return ORBX_OK;
+  }
+
+  static inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+  int orbx_search_in_area_batch_device(orbx_ctx *c, int n_frames, int query_stride, const orbx_area_query *d_queries, const uint8_t *d_query_desc,
+                                       const int32_t *d_n_queries, const uint8_t *d_exclude, int32_t *d_best_idx, int32_t *d_best_dist, float *d_ratio,
+                                       int32_t *d_n_candidates)
+  {
+    if (!c || n_frames < 1 || query_stride < 1 || !d_queries || !d_query_desc || !d_best_idx || !d_best_dist || !d_ratio || !d_n_candidates)
+      return ORBX_ERR_INVALID_ARG;
+    if (n_frames > c->last_frames) return fail(c, ORBX_ERR_STATE, "more frames than the last stereo / RGB-D call processed (they own the grids)");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    AreaArgs a{};
+    a.q = d_queries, a.q_desc = d_query_desc, a.n_q = d_n_queries, a.n_q_all = query_stride, a.q_stride = query_stride;
+    a.exclude = d_exclude;
+    a.best_idx = d_best_idx, a.best_dist = d_best_dist, a.ratio = d_ratio, a.n_cand = d_n_candidates;
+    a.image_stride = c->last_stereo ? 2 : 1;
+    a.max_u = c->max_u, a.max_v = c->max_v;
+    launch_area_match(c->p, a, n_frames, c->stream);
+    ++c->launches;
+    ORBX_CUDA(c, cudaGetLastError());
+    return ORBX_OK;
+  }
+
+  int orbx_search_in_area(orbx_ctx *c, int frame, int n_queries, const orbx_area_query *queries, const uint8_t *query_desc, const uint8_t *exclude,
+                          int32_t *best_idx, int32_t *best_dist, float *ratio, int32_t *n_candidates)
+  {
+    if (!c || frame < 0 || n_queries < 0 || (n_queries && (!queries || !query_desc))) return ORBX_ERR_INVALID_ARG;
+    if (frame >= c->last_frames) return fail(c, ORBX_ERR_STATE, "no frame with that index has a grid (stereo / RGB-D calls build it)");
+    if (n_queries == 0) return ORBX_OK;
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)n_queries, N = (size_t)c->cfg.n_features;
+    const size_t o_q = 0, o_d = o_q + up256(n * sizeof(orbx_area_query)), o_x = o_d + up256(n * 32), o_out = o_x + up256(N), total = o_out + up256(n * 16);
+    uint8_t *base = nullptr;
+    int rc = match_scratch(c, total, &base);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    ORBX_CUDA(c, cudaMemcpyAsync(base + o_q, queries, n * sizeof(orbx_area_query), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(c, cudaMemcpyAsync(base + o_d, query_desc, n * 32, cudaMemcpyHostToDevice, s));
+    if (exclude) ORBX_CUDA(c, cudaMemcpyAsync(base + o_x, exclude, N, cudaMemcpyHostToDevice, s));
+    int32_t *d_idx = (int32_t *)(base + o_out), *d_dist = d_idx + n, *d_nc = d_dist + n;
+    float *d_ratio = (float *)(d_nc + n);
+    AreaArgs a{};
+    a.q = (const orbx_area_query *)(base + o_q), a.q_desc = base + o_d, a.n_q = nullptr, a.n_q_all = n_queries, a.q_stride = n_queries;
+    a.exclude = exclude ? base + o_x : nullptr;
+    a.best_idx = d_idx, a.best_dist = d_dist, a.ratio = d_ratio, a.n_cand = d_nc;
+    a.image_stride = c->last_stereo ? 2 : 1;
+    a.max_u = c->max_u, a.max_v = c->max_v;
+    const Params p = params_at(c, frame * a.image_stride, frame);
+    launch_area_match(p, a, 1, s);
+    ++c->launches;
+    ORBX_CUDA(c, cudaGetLastError());
+    if (best_idx) ORBX_CUDA(c, cudaMemcpyAsync(best_idx, d_idx, n * 4, cudaMemcpyDeviceToHost, s));
+    if (best_dist) ORBX_CUDA(c, cudaMemcpyAsync(best_dist, d_dist, n * 4, cudaMemcpyDeviceToHost, s));
+    if (n_candidates) ORBX_CUDA(c, cudaMemcpyAsync(n_candidates, d_nc, n * 4, cudaMemcpyDeviceToHost, s));
+    if (ratio) ORBX_CUDA(c, cudaMemcpyAsync(ratio, d_ratio, n * 4, cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(c, cudaStreamSynchronize(s));
+    return ORBX_OK;
+  }
+
+  int orbx_verify_angle(orbx_ctx *c, int n_matches, int32_t *query_idx, int32_t *train_idx, float *distance, const orbx_keypoint *kps1, int n1,
+                        const orbx_keypoint *kps2, int n2, int32_t *n_out)
+  {
+    if (!c || n_matches < 0 || !n_out || n1 < 0 || n2 < 0) return ORBX_ERR_INVALID_ARG;
+    *n_out = 0;
+    if (n_matches == 0) return ORBX_OK;
+    if (!query_idx || !train_idx || !distance || !kps1 || !kps2) return ORBX_ERR_INVALID_ARG;
+    for (int i = 0; i < n_matches; ++i)
+      if (query_idx[i] < 0 || query_idx[i] >= n1 || train_idx[i] < 0 || train_idx[i] >= n2)
+        return fail(c, ORBX_ERR_INVALID_ARG, "match index outside the keypoint arrays");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)n_matches;
+    const size_t o_in = 0, o_k1 = o_in + up256(n * 12), o_k2 = o_k1 + up256((size_t)n1 * sizeof(orbx_keypoint)),
+                 o_out = o_k2 + up256((size_t)n2 * sizeof(orbx_keypoint)), total = o_out + up256(n * 12 + 4);
+    uint8_t *base = nullptr;
+    int rc = match_scratch(c, total, &base);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    int32_t *d_q = (int32_t *)(base + o_in), *d_t = d_q + n;
+    float *d_d = (float *)(d_t + n);
+    int32_t *d_oq = (int32_t *)(base + o_out), *d_ot = d_oq + n;
+    float *d_od = (float *)(d_ot + n);
+    int32_t *d_n = (int32_t *)(d_od + n);
+    ORBX_CUDA(c, cudaMemcpyAsync(d_q, query_idx, n * 4, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(c, cudaMemcpyAsync(d_t, train_idx, n * 4, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(c, cudaMemcpyAsync(d_d, distance, n * 4, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(c, cudaMemcpyAsync(base + o_k1, kps1, (size_t)n1 * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(c, cudaMemcpyAsync(base + o_k2, kps2, (size_t)n2 * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, s));
+    VerifyArgs a{};
+    a.n = n_matches, a.query_idx = d_q, a.train_idx = d_t, a.distance = d_d;
+    a.kps1 = (const orbx_keypoint *)(base + o_k1), a.kps2 = (const orbx_keypoint *)(base + o_k2);
+    a.out_query = d_oq, a.out_train = d_ot, a.out_dist = d_od, a.n_out = d_n;
+    launch_verify_angle(a, s);
+    ++c->launches;
+    ORBX_CUDA(c, cudaGetLastError());
+    ORBX_CUDA(c, cudaMemcpyAsync(n_out, d_n, 4, cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(c, cudaStreamSynchronize(s));
+    const size_t m = (size_t)*n_out;
+    if (m)
+    {
+      ORBX_CUDA(c, cudaMemcpy(query_idx, d_oq, m * 4, cudaMemcpyDeviceToHost));
+      ORBX_CUDA(c, cudaMemcpy(train_idx, d_ot, m * 4, cudaMemcpyDeviceToHost));
+      ORBX_CUDA(c, cudaMemcpy(distance, d_od, m * 4, cudaMemcpyDeviceToHost));
+    }
     return ORBX_OK;
   }
 

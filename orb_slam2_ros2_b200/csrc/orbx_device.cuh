@@ -138,7 +138,32 @@ struct Params
   int undistort;
 };
 
-// launchers (orbx_kernels.cu); every call enqueues exactly one kernel on `s`
+// tracking-side matchers (orbx_match.cu)
+struct AreaArgs
+{
+  const orbx_area_query *q; // [frame][q_stride]
+  const uint8_t *q_desc;    // [frame][q_stride][32]
+  const int *n_q;           // [frame] or null (then n_q_all queries for every frame)
+  int n_q_all, q_stride;
+  const uint8_t *exclude;   // [frame][n_features] or null
+  int *best_idx, *best_dist, *n_cand; // [frame][q_stride]
+  float *ratio;
+  int image_stride;         // frame f's (left) image is image f * image_stride
+  float max_u, max_v;       // mfMaxU / mfMaxV
+};
+
+struct VerifyArgs
+{
+  int n;
+  const int *query_idx, *train_idx;
+  const float *distance;
+  const orbx_keypoint *kps1, *kps2;
+  int *out_query, *out_train;
+  float *out_dist;
+  int *n_out;
+};
+
+// launchers (orbx_kernels.cu / orbx_match.cu); every call enqueues exactly one kernel on `s`
 void launch_pyramid(const Params &p, int n_images, cudaStream_t s);
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
@@ -147,6 +172,8 @@ void launch_rowindex(const Params &p, int n_frames, cudaStream_t s);
 void launch_stereo(const Params &p, int n_frames, cudaStream_t s);
 void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
 void launch_grid(const Params &p, int n_frames, int image_stride, cudaStream_t s);
+void launch_area_match(const Params &p, const AreaArgs &a, int n_frames, cudaStream_t s);
+void launch_verify_angle(const VerifyArgs &a, cudaStream_t s);
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells);
 int quadtree_configure(size_t smem_bytes); // opt in to large dynamic shared memory
 

@@ -368,8 +368,6 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
   const Cell c = p.cells[blockIdx.x];
   const int img = blockIdx.y;
   const Level &L = p.levels[c.level];
-  const uint8_t *__restrict__ lvl = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
-  const int pitch = L.pitch;
   const int pw = c.pw, ph = c.ph;
   const int zw = pw - 6, zh = ph - 6; // detection zone: FAST looks at [3, w-3) x [3, h-3) of the patch
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -554,7 +552,6 @@ constexpr int kQtMaxBinStrips = 8; // up to this many root strips the block pre-
 constexpr int kQtPresort = 3;      // depths 1..3 (5 slots each: quadrants 0-3, "on a split line")
 constexpr int kQtBinsPerStrip = 125;
 constexpr int kNodeBytes = 8 + 4 + 3 * 2 + 1;  // shared memory per node: rec {lo, cnt|depth|buf} | seq | next prev free | state
-constexpr int kNodeBoundWords = 4 * 2;          // global scratch per node (uint32 words): r0 r1 c0 c1, touched only below the key depth
 constexpr int kKeyLevels = 9;    // subdivision depths encoded in a key (3 bits each) below the 5-bit strip id
 constexpr int kKeyStripShift = 27;
 constexpr uint32_t kKeyNoStrip = 31u;

@@ -75,3 +75,45 @@ def synth_stereo_pool(h: int, w: int, n: int, seed0: int = 0, disparity: int = 1
         ls.append(l)
         rs.append(r)
     return np.stack(ls), np.stack(rs)
+
+
+AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("radius", "<f4"), ("octave", "<i4"), ("min_level", "<i4"), ("max_level", "<i4")])
+
+
+def synth_area_queries(kps: np.ndarray, desc: np.ndarray, n: int, seed: int, width: int, height: int, n_levels: int = 8, th: float = 15.0,
+                       jitter: float = 3.0, flip_bits: int = 6, mode: str = "window"):
+    """Queries shaped like the tracker's searchByProjection calls (src/ORBMatcher.cc:296-314, :575-583) against a frame
+    with keypoints `kps` / descriptors `desc`: n keypoints drawn from the frame ("the same point seen in the last frame"),
+    moved by N(0, jitter) px, `flip_bits` random descriptor bits flipped, octave window per `mode`:
+      "window"  [octave-1, octave+1] clamped      "up"  [octave, n_levels-1]      "down"  [0, octave]
+    Every 16th query is sent outside the image or given a huge radius (window clipping), and ~30 % of the frame's
+    keypoints are marked excluded ("already has a map point").  -> (queries, query_desc, exclude, source_idx)"""
+    rng = np.random.default_rng(seed)
+    m = len(kps)
+    src = rng.integers(0, max(m, 1), n)
+    q = np.zeros(n, AREA_QUERY_DTYPE)
+    if m == 0:
+        return q, np.zeros((n, 32), np.uint8), np.zeros(0, np.uint8), src
+    q["x"] = (kps["x"][src] + rng.normal(0, jitter, n)).astype(np.float32)
+    q["y"] = (kps["y"][src] + rng.normal(0, jitter, n)).astype(np.float32)
+    q["x"] = np.clip(q["x"], 0, width - 1)
+    q["y"] = np.clip(q["y"], 0, height - 1)
+    q["octave"] = kps["octave"][src]
+    q["radius"] = np.float32(th)
+    if mode == "up":
+        q["min_level"], q["max_level"] = q["octave"], n_levels - 1
+    elif mode == "down":
+        q["min_level"], q["max_level"] = 0, q["octave"]
+    else:
+        q["min_level"], q["max_level"] = np.maximum(0, q["octave"] - 1), np.minimum(n_levels - 1, q["octave"] + 1)
+    far = np.arange(n) % 16 == 5
+    q["x"][far] += np.float32(width)  # right of the image: empty window
+    big = np.arange(n) % 16 == 11
+    q["radius"][big] = np.float32(400.0)  # covers the whole image after the sf^2 scaling
+    q["min_level"][big], q["max_level"][big] = 0, n_levels - 1
+    qd = desc[src].copy()
+    bits = rng.integers(0, 256, (n, flip_bits))
+    for k in range(flip_bits):
+        qd[np.arange(n), bits[:, k] // 8] ^= (1 << (bits[:, k] % 8)).astype(np.uint8)
+    exclude = (rng.random(m) < 0.3).astype(np.uint8)
+    return q, qd, exclude, src

@@ -47,6 +47,21 @@ def main():
         r = O.ref_stereo(left, right, tp, 500, 4, 1.2)
         np.savez_compressed(os.path.join(OUT, "small_stereo_seed0_d9.npz"), seed=0, disparity=9, left_sha=sha(left), right_sha=sha(right),
                             kl=r["kl"], dl=r["dl"], kr=r["kr"], dr=r["dr"], u_right=r["u_right"], depth=r["depth"], n_matches=r["n_matches"])
+        # 2b. tracking-side matchers on the small frame: findFeaturesInArea + getBestMatch (+ exclusion) and verifyAngle
+        kl, dl = r["kl"], r["dl"]
+        sf = np.array([np.float32(np.float64(np.float32(1.2)) ** l) for l in range(4)], np.float32)
+        q, qd, ex, src = synth.synth_area_queries(kl, dl, 400, 5, 320, 240, n_levels=4, th=15.0)
+        bounds = (0.0, 0.0, 320.0, 240.0)
+        a = O.ref_search_in_area(kl, dl, bounds, sf, q, qd, None)
+        b = O.ref_search_in_area(kl, dl, bounds, sf, q, qd, ex)
+        ok = a["best_idx"] >= 0
+        k2 = np.zeros(len(q), O.KP_DTYPE)
+        k2["angle"] = (kl["angle"][src] + np.random.default_rng(6).normal(0, 25, len(q))).astype(np.float32)
+        qi, ti, di = a["best_idx"][ok], np.nonzero(ok)[0].astype(np.int32), a["best_dist"][ok].astype(np.float32)
+        vq, vt, vd = O.ref_verify_angle(qi, ti, di, kl, k2)
+        np.savez_compressed(os.path.join(OUT, "small_area_match_seed5.npz"), seed=5, n=400, q_sha=sha(q), qd_sha=sha(qd), k2_angle=k2["angle"],
+                            best_idx=a["best_idx"], best_dist=a["best_dist"], ratio=a["ratio"], n_cand=a["n_cand"], x_best_idx=b["best_idx"],
+                            x_best_dist=b["best_dist"], x_ratio=b["ratio"], x_n_cand=b["n_cand"], va_query=vq, va_train=vt, va_dist=vd)
         # 3. TUM-shaped mono extraction, 1000 features (the extractor part of configs[1]; the RGB-D ctor itself cannot be compiled in isolation)
         c = synth.TUM
         gray = synth.synth_image(c["height"], c["width"], 12)

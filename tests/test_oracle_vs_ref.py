@@ -152,3 +152,67 @@ def test_undistort_identical(R):
     assert np.array_equal(a, b)
     R.ref_set_camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], None)
     assert np.array_equal(R.ref_undistort(pts), pts)  # k1 == 0 -> early return (Camera.cc:31)
+
+
+# ---- tracking-side matchers: Frame.cc:53-69,286-311 and ORBMatcher.cc:967-990,1013-1051 ----
+def _frame(R, template_path, h, w, nf, nl, seed):
+    R.ref_reset()
+    n, kps, desc, info = R.ref_extract(synth.synth_image(h, w, seed), template_path, nf, nl, 1.2)
+    return kps, desc, info["sf"]
+
+
+@pytest.mark.parametrize("shape", [(376, 1241, 2000, 8), (480, 640, 1000, 8), (240, 320, 300, 4)], ids=["K", "T", "S"])
+def test_init_grid_identical(R, template_path, shape):
+    h, w, nf, nl = shape
+    kps, _, _ = _frame(R, template_path, h, w, nf, nl, 21)
+    for bounds in [(0.0, 0.0, float(w), float(h)), (-7.25, -3.5, w + 11.75, h + 6.5)]:
+        a, b = R.grid_csr(kps, *bounds), R.ref_grid_csr(kps, *bounds)
+        assert a[:2] == b[:2] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+        flat = [c for row in R.init_grid(kps, *bounds) for c in row]
+        assert np.array_equal(np.concatenate(flat), a[3])
+
+
+@pytest.mark.parametrize("mode", ["window", "up", "down"])
+@pytest.mark.parametrize("shape", [(376, 1241, 2000, 8), (480, 640, 1000, 8)], ids=["K", "T"])
+def test_search_in_area_identical(R, template_path, shape, mode):
+    h, w, nf, nl = shape
+    kps, desc, sf = _frame(R, template_path, h, w, nf, nl, 22)
+    bounds = (0.0, 0.0, float(w), float(h))
+    for th, seed in [(15.0, 1), (30.0, 2), (3.0, 3)]:
+        q, qd, ex, _ = synth.synth_area_queries(kps, desc, 700, seed, w, h, nl, th, mode=mode)
+        for e in (None, ex):
+            a, b = R.search_in_area(kps, desc, bounds, sf, q, qd, e), R.ref_search_in_area(kps, desc, bounds, sf, q, qd, e)
+            for k in a:
+                assert np.array_equal(a[k], b[k], equal_nan=True), (k, th, e is None)
+            assert (a["n_cand"] > 0).sum() > 300
+
+
+def test_best_match_second_best_rule_and_ties(R, template_path):
+    """getBestMatch keeps the FIRST minimum and its `second` ignores displaced minima: duplicated descriptors, zero
+    distances (ratio 0/0 = NaN) and strictly descending distance sequences (second stays INT_MAX) must all agree."""
+    kps, desc, sf = _frame(R, template_path, 240, 320, 300, 4, 23)
+    rng = np.random.default_rng(3)
+    desc = desc.copy()
+    desc[rng.integers(0, len(desc), 80)] = desc[rng.integers(0, len(desc), 80)]  # duplicates -> ties
+    q, qd, ex, src = synth.synth_area_queries(kps, desc, 500, 4, 320, 240, 4, 60.0, flip_bits=0)  # exact copies: distance 0
+    a = R.search_in_area(kps, desc, (0.0, 0.0, 320.0, 240.0), sf, q, qd, None)
+    b = R.ref_search_in_area(kps, desc, (0.0, 0.0, 320.0, 240.0), sf, q, qd, None)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    assert np.isnan(a["ratio"]).any() and (a["best_dist"] == 0).sum() > 100
+
+
+def test_verify_angle_identical(R, template_path):
+    kps, desc, sf = _frame(R, template_path, 376, 1241, 2000, 8, 24)
+    rng = np.random.default_rng(5)
+    for n, spread in [(1500, 25.0), (40, 200.0), (3, 1.0), (0, 1.0)]:
+        qi = rng.integers(0, len(kps), n).astype(np.int32)
+        ti = np.arange(n, dtype=np.int32)
+        k2 = np.zeros(max(n, 1), R.KP_DTYPE)
+        ang = kps["angle"][qi].astype(np.float64) + rng.normal(0, spread, n)
+        k2["angle"][:n] = (180.0 - np.mod(180.0 - ang, 360.0)).astype(np.float32)  # back into (-180, 180] like IC angles (:449)
+        k2["angle"][: n // 7] = kps["angle"][qi[: n // 7]]  # zero differences and exact wrap-arounds
+        di = rng.integers(0, 50, n).astype(np.float32)
+        a, b = R.verify_angle(qi, ti, di, kps, k2), R.ref_verify_angle(qi, ti, di, kps, k2)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), n
+        assert len(a[0]) <= n
