@@ -296,12 +296,12 @@ private:
   std::shared_ptr<orbx_ctx> mCtx;
 };
 
-// ---- the stereo entry of include/ORB_SLAM2/ORBMatcher.h:39 ---------------------------------------------------------
+// ---- the stereo entry (include/ORB_SLAM2/ORBMatcher.h:39) and the projection matchers (:50-53) ---------------------------------------------------------
 class ORBMatcher
 {
 public:
   typedef std::shared_ptr<ORBMatcher> SharedPtr;
-  explicit ORBMatcher(float ratio = 0.6f, bool checkOri = true) { (void)ratio, (void)checkOri; }
+  explicit ORBMatcher(float ratio = 0.6f, bool checkOri = true) : mfRatio(ratio), mbCheckOri(checkOri) { (void)mbCheckOri; }
   // fills mvFeatsRightU / mvDepths (-1 = no match) and returns the match count, like src/ORBMatcher.cc:18-81.  The GPU
   // computed them together with the features (one launch sequence per frame); this call publishes them.
   int searchByStereo(Frame::SharedPtr pFrame)
@@ -310,6 +310,105 @@ public:
     pFrame->mvDepths = pFrame->mStereoDepth;
     return pFrame->mStereoMatches;
   }
+
+  // ---- tracking-side matchers (include/ORB_SLAM2/ORBMatcher.h:50-53,105) -------------------------------------------
+  // The reference walks MapPoint objects; here the caller passes what it derives from them as per-keypoint masks.  The
+  // frame searched must be the one most recently created on its context (its keypoints, descriptors and grid are still
+  // resident on the device).
+  struct AreaMatch
+  {
+    int idx = -1;   // best candidate among the frame's left keypoints, -1 = no candidate
+    int distance = 0;
+    float ratio = 0.f;
+    int nCandidates = 0;
+  };
+
+  // findFeaturesInArea + exclusion + getBestMatch for every query (src/Frame.cc:286-311, src/ORBMatcher.cc:322-331,967-990):
+  // kps[i].pt / kps[i].octave, radius[i] (before the sf^2 scaling), candidate octaves in [minLevel[i], maxLevel[i]]
+  static std::vector<AreaMatch> searchInArea(Frame::SharedPtr pFrame, const std::vector<cv::KeyPoint> &kps, const std::vector<float> &radius,
+                                             const std::vector<int> &minLevel, const std::vector<int> &maxLevel, const std::vector<cv::Mat> &descs,
+                                             const std::vector<bool> *exclude = nullptr)
+  {
+    const std::size_t n = kps.size();
+    std::vector<orbx_area_query> q(n);
+    std::vector<uint8_t> qd(n * 32), ex;
+    for (std::size_t i = 0; i < n; ++i)
+    {
+      q[i] = orbx_area_query{kps[i].pt.x, kps[i].pt.y, radius[i], kps[i].octave, minLevel[i], maxLevel[i]};
+      std::memcpy(&qd[32 * i], descs[i].data, 32);
+    }
+    if (exclude)
+    {
+      ex.assign((std::size_t)pFrame->orbx_capacity(), 0);
+      for (std::size_t i = 0; i < exclude->size() && i < ex.size(); ++i) ex[i] = (*exclude)[i] ? 1 : 0;
+    }
+    std::vector<int32_t> idx(n), dist(n), nc(n);
+    std::vector<float> ratio(n);
+    detail::check(pFrame->mCtx.get(),
+                  orbx_search_in_area(pFrame->mCtx.get(), 0, (int)n, q.data(), qd.data(), exclude ? ex.data() : nullptr, idx.data(), dist.data(), ratio.data(),
+                                      nc.data()),
+                  "orbx_search_in_area");
+    std::vector<AreaMatch> out(n);
+    for (std::size_t i = 0; i < n; ++i) out[i] = AreaMatch{idx[i], dist[i], ratio[i], nc[i]};
+    return out;
+  }
+
+  // searchByProjection(pFrame1, pFrame2, matches, th, bFuse) (src/ORBMatcher.cc:265-347).  kps2 / desc2 = pFrame2's left
+  // keypoints and descriptors; valid2[idx] = mps2[idx] is a good map point (and, for bFuse, in view of pFrame1);
+  // hasMp1[i] = pFrame1's keypoint i already has a good map point; tlcZ = z of pFrame1's camera centre in pFrame2's
+  // camera frame (:275-281, compared with Camera::mfBl).
+  int searchByProjection(Frame::SharedPtr pFrame1, const std::vector<cv::KeyPoint> &kps2, const std::vector<cv::Mat> &desc2, const std::vector<bool> &valid2,
+                         const std::vector<bool> &hasMp1, std::vector<cv::DMatch> &matches, float th, float tlcZ = 0.f, bool bFuse = false)
+  {
+    matches.clear();
+    bool up = false, down = false;
+    if (std::abs(tlcZ) > Camera::mfBl) tlcZ > 0 ? up = true : down = true;
+    std::vector<cv::KeyPoint> q;
+    std::vector<cv::Mat> qd;
+    std::vector<float> radius;
+    std::vector<int> lo, hi, src;
+    for (std::size_t idx = 0; idx < kps2.size(); ++idx)
+    {
+      if (!valid2[idx]) continue;
+      const int o = kps2[idx].octave;
+      q.push_back(kps2[idx]);
+      qd.push_back(desc2[idx]);
+      radius.push_back(th);
+      lo.push_back(up ? o : down ? 0 : std::max(0, o - 1));
+      hi.push_back(up ? 7 : down ? o : std::min(o + 1, 7));
+      src.push_back((int)idx);
+    }
+    std::vector<AreaMatch> r = searchInArea(pFrame1, q, radius, lo, hi, qd, bFuse ? nullptr : &hasMp1);
+    for (std::size_t i = 0; i < r.size(); ++i)
+      if (r[i].nCandidates > 0 && r[i].ratio < mfRatio && r[i].distance < mnMinThreshold) matches.emplace_back(r[i].idx, src[i], (float)r[i].distance);
+    return (int)matches.size();
+  }
+
+  // ORBMatcher::verifyAngle (src/ORBMatcher.cc:1013-1051); `owner` provides the device context
+  static void verifyAngle(Frame::SharedPtr owner, std::vector<cv::DMatch> &matches, const std::vector<cv::KeyPoint> &keyPoints1,
+                          const std::vector<cv::KeyPoint> &keyPoints2)
+  {
+    const std::size_t n = matches.size();
+    std::vector<int32_t> qi(n), ti(n);
+    std::vector<float> di(n);
+    for (std::size_t i = 0; i < n; ++i) qi[i] = matches[i].queryIdx, ti[i] = matches[i].trainIdx, di[i] = matches[i].distance;
+    std::vector<orbx_keypoint> k1(keyPoints1.size()), k2(keyPoints2.size());
+    if (!k1.empty()) std::memcpy(k1.data(), keyPoints1.data(), k1.size() * sizeof(orbx_keypoint));
+    if (!k2.empty()) std::memcpy(k2.data(), keyPoints2.data(), k2.size() * sizeof(orbx_keypoint));
+    int32_t m = 0;
+    detail::check(owner->mCtx.get(),
+                  orbx_verify_angle(owner->mCtx.get(), (int)n, qi.data(), ti.data(), di.data(), k1.data(), (int)k1.size(), k2.data(), (int)k2.size(), &m),
+                  "orbx_verify_angle");
+    matches.resize((std::size_t)m);
+    for (int i = 0; i < m; ++i) matches[(std::size_t)i] = cv::DMatch(qi[(std::size_t)i], ti[(std::size_t)i], di[(std::size_t)i]);
+  }
+
+  static inline int mnMaxThreshold = 100, mnMinThreshold = 50, mnMeanThreshold = 75; // src/ORBMatcher.cc:1086-1088
+  static inline int mnBinNum = 30, mnBinChoose = 3;                                  // :1091-1092
+
+private:
+  float mfRatio = 0.6f;
+  bool mbCheckOri = true;
 };
 
 inline Frame::SharedPtr Frame::createStereo(cv::Mat leftImg, cv::Mat rightImg, int nFeatures, const std::string &briefFp, int maxThresh, int minThresh,

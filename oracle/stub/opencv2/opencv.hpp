@@ -92,6 +92,7 @@ struct DMatch
   int queryIdx, trainIdx, imgIdx;
   float distance;
   DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(std::numeric_limits<float>::max()) {}
+  DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
 };
 
 enum

@@ -96,6 +96,19 @@ int main(int argc, char **argv)
       put(out, (int32_t)grids[0].size());
       put(out, (int32_t)total);
       put(out, (int32_t)ascending);
+      // constant-velocity matching of the frame against itself shifted by (+2, -1) px, every 3rd keypoint of "frame 1" taken
+      std::vector<cv::KeyPoint> k2 = f->getLeftKeyPoints();
+      for (auto &kp : k2) kp.pt.x += 2.f, kp.pt.y -= 1.f;
+      std::vector<bool> valid2(k2.size(), true), hasMp1(k2.size(), false);
+      for (std::size_t i = 0; i < hasMp1.size(); i += 3) hasMp1[i] = true;
+      ORBMatcher matcher(0.6f);
+      std::vector<cv::DMatch> matches;
+      int nm = matcher.searchByProjection(f, k2, f->getLeftDescriptor(), valid2, hasMp1, matches, 15.f);
+      put(out, (int32_t)nm);
+      for (auto &m : matches) put(out, (int32_t)m.queryIdx), put(out, (int32_t)m.trainIdx), put(out, m.distance);
+      ORBMatcher::verifyAngle(f, matches, f->getLeftKeyPoints(), k2);
+      put(out, (int32_t)matches.size());
+      for (auto &m : matches) put(out, (int32_t)m.queryIdx), put(out, (int32_t)m.trainIdx), put(out, m.distance);
     }
     else if (mode == "rgbd")
     {

@@ -93,6 +93,23 @@ def test_shim_stereo_matches_oracle(shim_binary, template_path, oracle, tmp_path
     nm, our, odp, _ = oracle.search_by_stereo(el, er, np.float32(cam.fx), cam.bf)
     assert n_matches == nm and np.abs(ur - our).max() <= 1e-3 and np.abs(dp - odp).max() <= 1e-3 * np.abs(odp).max()
     assert (rd.i32(), rd.i32(), rd.i32(), rd.i32()) == (8, 20, len(kl), 1)  # mGrids: 8 x 20 cells, all keypoints, ascending
+    # ORBMatcher::searchByProjection (constant-velocity form) + verifyAngle against the oracle's composition of the same steps
+    nm = rd.i32()
+    got = rd.arr(np.dtype([("q", "<i4"), ("t", "<i4"), ("d", "<f4")]), nm)
+    q = np.zeros(len(kl), oracle.AREA_QUERY_DTYPE)
+    q["x"], q["y"], q["octave"], q["radius"] = kl["x"] + np.float32(2), kl["y"] - np.float32(1), kl["octave"], 15
+    q["min_level"], q["max_level"] = np.maximum(0, kl["octave"] - 1), np.minimum(kl["octave"] + 1, 7)
+    has1 = np.zeros(len(kl), np.uint8)
+    has1[::3] = 1
+    e = oracle.search_in_area(kl, dl, (0.0, 0.0, float(c["width"]), float(c["height"])), el.pyr.sf, q, dl, has1)
+    ok = (e["n_cand"] > 0) & (e["ratio"] < np.float32(0.6)) & (e["best_dist"] < 50)
+    assert nm == int(ok.sum()) and nm > 500
+    assert np.array_equal(got["q"], e["best_idx"][ok]) and np.array_equal(got["t"], np.nonzero(ok)[0]) and np.array_equal(got["d"], e["best_dist"][ok])
+    k2 = kl.copy()
+    vq, vt, vd = oracle.verify_angle(got["q"], got["t"], got["d"], kl, k2)
+    nv = rd.i32()
+    gv = rd.arr(np.dtype([("q", "<i4"), ("t", "<i4"), ("d", "<f4")]), nv)
+    assert nv == len(vq) and np.array_equal(gv["q"], vq) and np.array_equal(gv["t"], vt) and np.array_equal(gv["d"], vd)
 
 
 @pytest.mark.gpu
