@@ -24,7 +24,7 @@ namespace orbx
 constexpr int kMaxLevels = 16;  // one TMA descriptor per level travels as a kernel parameter (LevelMaps)
 constexpr int kEdge = 16;       // FAST ROI margin: mnBorderSize - 3 (src/ORBExtractor.cc:334-337)
 constexpr int kTileW = 64;      // pyramid/blur output tile
-constexpr int kTileH = 32;
+constexpr int kTileH = 64;
 constexpr int kHalo = 3;        // 7x7 Gaussian
 constexpr int kPyrThreads = 256;
 constexpr int kFastThreads = 128;

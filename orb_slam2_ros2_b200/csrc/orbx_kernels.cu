@@ -66,24 +66,29 @@ template <int NT> __device__ __forceinline__ int block_exclusive_scan(int v, int
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K1: pyramid level (resize from level 0) fused with the 7x7 Gaussian blur.  One CTA per 64x32 output tile.
+// K1: pyramid level (resize from level 0) fused with the 7x7 Gaussian blur.  One CTA per kTileW x kTileH output tile.
 //   cv::resize INTER_LINEAR 8UC1: 11-bit coefficient tables (built on the host exactly like OpenCV does), int32 maths.
 //   cv::GaussianBlur 7x7 sigma 2: 8.8 fixed-point kernel {18,34,48,56,48,34,18}, u16 rows, (v + 32768) >> 16.
 //   Stage A  thread <-> tile column (coefficients in registers), loop over rows: 4 byte gathers from level 0 per pixel
+//            (second tap at an immediate +1, vertical weights by multiply-high, no clamp: the weights sum to 2048)
 //   Stage B  horizontal pass on packed bytes: 3 aligned LDS.32 + funnel shifts + 8 DP4A per 4 pixels -> u16
-//   Stage C  vertical pass: one thread per 4 columns x 2 rows, LDS.64 of packed u16, exact integer MACs
+//   Stage C  vertical pass: one item per 4 columns x 2 rows, LDS.64 of packed u16, exact integer MACs
+//   The tile is stored with pixel 0 at byte 16 of a 96-byte row, so the level image leaves as LDS.128 / STG.128.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kSrcW = kTileW + 2 * kHalo;      // 70
-constexpr int kSrcH = kTileH + 2 * kHalo;      // 38
-constexpr int kSrcPitch = 72;                  // bytes, word aligned
-constexpr int kColGroups = kPyrThreads / kSrcPitch; // 3 row-interleaved groups of 72 column threads
+constexpr int kSrcH = kTileH + 2 * kHalo;      // tile rows + halo
+constexpr int kSrcPitch = 96;                  // bytes, 16-byte multiple
+constexpr int kSrcCol0 = 13;                   // byte of source column 0 inside a row: tile pixel 0 sits at byte 16 (LDS.128 rows)
+constexpr int kColStride = 72;                 // stage A: thread <-> source column, kColGroups row-interleaved groups
+constexpr int kColGroups = kPyrThreads / kColStride;
 
 __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params p)
 {
   __shared__ __align__(16) uint8_t s_src[kSrcH * kSrcPitch];
   __shared__ __align__(16) uint16_t s_h[kSrcH * kTileW];
-  __shared__ uint32_t s_r0[kSrcH], s_r1[kSrcH]; // byte offsets of the two source rows (kOutside: beyond the level + halo, never read)
-  __shared__ short2 s_yc[kSrcH];               // vertical coefficients
+  // per source row: byte offsets of the two level-0 rows (kOutside: beyond the level + halo, never read) and the
+  // vertical coefficients pre-shifted by 16 so that (b * (h >> 4)) >> 16 is one multiply-high
+  __shared__ __align__(16) uint4 s_row[kSrcH];
 
   const Tile t = p.tiles[blockIdx.x];
   const int img = blockIdx.y;
@@ -119,60 +124,71 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
         o1 = (uint32_t)min(max(sy + 1, 0), H - 1) * sstride;
       }
     }
-    s_r0[tid] = o0;
-    s_r1[tid] = o1;
-    s_yc[tid] = b;
+    s_row[tid] = make_uint4(o0, o1, (uint32_t)b.x << 16, (uint32_t)b.y << 16); // coefficients are in [0, 2048]
   }
   __syncthreads();
 
   // stage A: the tile plus a 3-pixel halo of the (resized) level image, REFLECT_101 at the level's borders.
   // src is CTA-uniform and all offsets are 32-bit, so the loads use uniform-base + 32-bit-offset addressing.
   {
-    const int col = tid % kSrcPitch, grp = tid / kSrcPitch;
+    const int col = tid % kColStride, grp = tid / kColStride;
     const int rx = t.x0 + col - kHalo;
     if (grp < kColGroups && col < kSrcW)
     {
       const bool col_ok = rx < lw + kHalo;
       const uint32_t gx = col_ok ? (uint32_t)refl101(rx, lw) : 0u;
-      if (level == 0)
+      uint8_t *dst = s_src + kSrcCol0 + col;
+      if (!col_ok)
+      {
+        for (int ty = grp; ty < kSrcH; ty += kColGroups) dst[ty * kSrcPitch] = 0;
+      }
+      else if (level == 0)
       {
 #pragma unroll 4
         for (int ty = grp; ty < kSrcH; ty += kColGroups)
         {
-          const uint32_t o0 = s_r0[ty];
-          s_src[ty * kSrcPitch + col] = (col_ok && o0 != kOutside) ? src[o0 + gx] : (uint8_t)0;
+          const uint32_t o0 = s_row[ty].x;
+          dst[ty * kSrcPitch] = (o0 != kOutside) ? src[o0 + gx] : (uint8_t)0;
         }
       }
       else if (area2x)
       {
         for (int ty = grp; ty < kSrcH; ty += kColGroups)
         {
-          const uint32_t o0 = s_r0[ty], o1 = s_r1[ty];
+          const uint4 r = s_row[ty];
           int v = 0;
-          if (col_ok && o0 != kOutside) v = (src[o0 + 2 * gx] + src[o0 + 2 * gx + 1] + src[o1 + 2 * gx] + src[o1 + 2 * gx + 1] + 2) >> 2;
-          s_src[ty * kSrcPitch + col] = (uint8_t)v;
+          if (r.x != kOutside) v = (src[r.x + 2 * gx] + src[r.x + 2 * gx + 1] + src[r.y + 2 * gx] + src[r.y + 2 * gx + 1] + 2) >> 2;
+          dst[ty * kSrcPitch] = (uint8_t)v;
         }
       }
       else
       {
-        const uint32_t sx = col_ok ? (uint32_t)p.tab_ofs[L.tab_x + gx] : 0u;
-        const short2 a = col_ok ? p.tab_coef[L.tab_x + gx] : make_short2(0, 0);
-        const uint32_t sx1 = min(sx + 1u, (uint32_t)(W - 1));
-        const int ax = a.x, ay = a.y;
+        // value = src[sx] * ax + src[min(sx + 1, W - 1)] * ay.  The second tap is always read at +1 (an immediate): in the
+        // last column (sx == W - 1, where the table has ay == 0) the pair is moved one pixel left with the weights swapped.
+        uint32_t sx = (uint32_t)p.tab_ofs[L.tab_x + gx];
+        const short2 a = p.tab_coef[L.tab_x + gx];
+        uint32_t ax = (uint32_t)a.x, ay = (uint32_t)a.y;
+        if (sx + 1u > (uint32_t)(W - 1))
+        {
+          sx = (uint32_t)(W - 2);
+          ay = ax + ay;
+          ax = 0;
+        }
+        const uint8_t *__restrict__ col_src = src + sx;
 #pragma unroll 4
         for (int ty = grp; ty < kSrcH; ty += kColGroups)
         {
-          const uint32_t o0 = s_r0[ty], o1 = s_r1[ty];
-          int v = 0;
-          if (col_ok && o0 != kOutside)
+          const uint4 r = s_row[ty];
+          uint32_t v = 0;
+          if (r.x != kOutside)
           {
-            const short2 b = s_yc[ty];
-            const int h0 = src[o0 + sx] * ax + src[o0 + sx1] * ay;
-            const int h1 = src[o1 + sx] * ax + src[o1 + sx1] * ay;
-            v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
+            const uint8_t *q0 = col_src + (size_t)r.x, *q1 = col_src + (size_t)r.y; // 64-bit: the +1 folds into the load's immediate
+            const uint32_t h0 = q0[0] * ax + q0[1] * ay;
+            const uint32_t h1 = q1[0] * ax + q1[1] * ay;
+            // (((bx * (h0 >> 4)) >> 16) + ((by * (h1 >> 4)) >> 16) + 2) >> 2; at most 255 because bx + by == 2048
+            v = (__umulhi(r.z, h0 >> 4) + __umulhi(r.w, h1 >> 4) + 2u) >> 2;
           }
-          s_src[ty * kSrcPitch + col] = (uint8_t)v;
+          dst[ty * kSrcPitch] = (uint8_t)v;
         }
       }
     }
@@ -182,20 +198,17 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
   uint8_t *__restrict__ pyr = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
   uint8_t *__restrict__ blr = p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off;
 
-  // the level image itself (getPyramid(); FAST, orientation and the stereo SAD read it): 4 pixels per store
-  for (int i = tid; i < kTileH * (kTileW / 4); i += kPyrThreads)
+  // the level image itself (getPyramid(); FAST, orientation and the stereo SAD read it): 16 pixels per load/store
+  for (int i = tid; i < kTileH * (kTileW / 16); i += kPyrThreads)
   {
-    const int ty = i >> 4, tx = (i & 15) * 4;
+    const int ty = i >> 2, tx = (i & 3) * 16;
     const int gx = t.x0 + tx, gy = t.y0 + ty;
     if (gy < lh && gx < pitch)
-    {
-      const uint8_t *s = &s_src[(ty + kHalo) * kSrcPitch + tx + kHalo];
-      const uint32_t w = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
-      *reinterpret_cast<uint32_t *>(pyr + (size_t)gy * pitch + gx) = w;
-    }
+      *reinterpret_cast<uint4 *>(pyr + (size_t)gy * pitch + gx) = *reinterpret_cast<const uint4 *>(&s_src[(ty + kHalo) * kSrcPitch + 16 + tx]);
   }
 
-  // stage B: horizontal pass, 4 outputs per item from 3 aligned words (bytes 4g .. 4g+11); sums fit u16 (255 * 256)
+  // stage B: horizontal pass, 4 outputs per item from 3 aligned words; output pixel 4g + k needs source bytes
+  // 4g + 13 + k .. + 6 of the row = words 3 + g .. 5 + g shifted by 8 (k + 1) bits; sums fit u16 (255 * 256)
   {
     constexpr uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24); // taps 0..3
     constexpr uint32_t K1 = 48u | (34u << 8) | (18u << 16);               // taps 4..6
@@ -204,20 +217,21 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
     for (int i = tid; i < kSrcH * (kTileW / 4); i += kPyrThreads)
     {
       const int ty = i >> 4, g = i & 15;
-      const uint32_t *row = s32 + ty * (kSrcPitch / 4) + g;
+      const uint32_t *row = s32 + ty * (kSrcPitch / 4) + 3 + g;
       const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
-      const uint32_t o0 = __dp4a(w0, K0, __dp4a(w1, K1, 0u));
-      const uint32_t o1 = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
-      const uint32_t o2 = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
-      const uint32_t o3 = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
+      const uint32_t o0 = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
+      const uint32_t o1 = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
+      const uint32_t o2 = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
+      const uint32_t o3 = __dp4a(w1, K0, __dp4a(w2, K1, 0u));
       h2[i] = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
     }
   }
   __syncthreads();
 
-  // stage C: vertical pass + rounding; one thread per 4 columns x 2 output rows
+  // stage C: vertical pass + rounding; one item per 4 columns x 2 output rows
+  for (int i = tid; i < (kTileH / 2) * (kTileW / 4); i += kPyrThreads)
   {
-    const int g = tid & 15, ry = (tid >> 4) * 2; // 16 column groups x 16 row pairs == 256 threads
+    const int g = i & 15, ry = (i >> 4) * 2;
     const int gx = t.x0 + g * 4, gy = t.y0 + ry;
     if (gy < lh && gx < pitch)
     {
