@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
 {
   __shared__ __align__(16) uint8_t s_src[kSrcH * kSrcPitch];
   __shared__ __align__(16) uint16_t s_h[kSrcH * kTileW];
-  // per source row: byte offsets of the two level-0 rows (kOutside: beyond the level + halo, never read) and the
-  // vertical coefficients pre-shifted by 16 so that (b * (h >> 4)) >> 16 is one multiply-high
+  // per source row: byte offsets of the two level-0 rows and the vertical coefficients pre-shifted by 16, so that
+  // (b * (h >> 4)) >> 16 is one multiply-high (level 0 / exact 2x decimation: .z = 0xff keep-mask instead)
   __shared__ __align__(16) uint4 s_row[kSrcH];
 
   const Tile t = p.tiles[blockIdx.x];
@@ -100,36 +100,40 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
   const int level = t.level, area2x = L.area2x;
   const int tid = threadIdx.x;
 
-  constexpr uint32_t kOutside = 0xffffffffu;
+  // Rows beyond the level + halo are never used; they read row 0 with zero weights / a zero mask so that stage A has no
+  // per-row branch and the loads of several rows are in flight together.
   if (tid < kSrcH)
   {
     const int ry = t.y0 + tid - kHalo;
-    uint32_t o0 = kOutside, o1 = kOutside;
-    short2 b = make_short2(0, 0);
+    uint32_t o0 = 0, o1 = 0, z = 0, w = 0;
     if (ry < lh + kHalo)
     {
       const int gy = refl101(ry, lh);
       if (level == 0)
+      {
         o0 = o1 = (uint32_t)gy * sstride;
+        z = 0xffu;
+      }
       else if (area2x)
       {
         o0 = (uint32_t)(2 * gy) * sstride;
         o1 = o0 + sstride;
+        z = 0xffu;
       }
       else
       {
         const int sy = p.tab_ofs[L.tab_y + gy];
-        b = p.tab_coef[L.tab_y + gy];
+        const short2 b = p.tab_coef[L.tab_y + gy];
         o0 = (uint32_t)min(max(sy, 0), H - 1) * sstride; // rows are clamped, not re-weighted (cv::resize)
         o1 = (uint32_t)min(max(sy + 1, 0), H - 1) * sstride;
+        z = (uint32_t)b.x << 16, w = (uint32_t)b.y << 16; // coefficients are in [0, 2048]
       }
     }
-    s_row[tid] = make_uint4(o0, o1, (uint32_t)b.x << 16, (uint32_t)b.y << 16); // coefficients are in [0, 2048]
+    s_row[tid] = make_uint4(o0, o1, z, w);
   }
   __syncthreads();
 
   // stage A: the tile plus a 3-pixel halo of the (resized) level image, REFLECT_101 at the level's borders.
-  // src is CTA-uniform and all offsets are 32-bit, so the loads use uniform-base + 32-bit-offset addressing.
   {
     const int col = tid % kColStride, grp = tid / kColStride;
     const int rx = t.x0 + col - kHalo;
@@ -144,21 +148,31 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
       }
       else if (level == 0)
       {
-#pragma unroll 4
-        for (int ty = grp; ty < kSrcH; ty += kColGroups)
+        const uint8_t *__restrict__ col_src = src + gx;
+        constexpr int U = 8; // rows per batch: all loads of a batch are issued before the first use
+        for (int ty0 = grp; ty0 < kSrcH; ty0 += U * kColGroups)
         {
-          const uint32_t o0 = s_row[ty].x;
-          dst[ty * kSrcPitch] = (o0 != kOutside) ? src[o0 + gx] : (uint8_t)0;
+          uint32_t v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+          {
+            const uint4 r = s_row[min(ty0 + u * kColGroups, kSrcH - 1)];
+            v[u] = col_src[(size_t)r.x] & r.z;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (ty0 + u * kColGroups < kSrcH) dst[(ty0 + u * kColGroups) * kSrcPitch] = (uint8_t)v[u];
         }
       }
       else if (area2x)
       {
+        const uint8_t *__restrict__ col_src = src + 2 * gx;
+#pragma unroll 2
         for (int ty = grp; ty < kSrcH; ty += kColGroups)
         {
           const uint4 r = s_row[ty];
-          int v = 0;
-          if (r.x != kOutside) v = (src[r.x + 2 * gx] + src[r.x + 2 * gx + 1] + src[r.y + 2 * gx] + src[r.y + 2 * gx + 1] + 2) >> 2;
-          dst[ty * kSrcPitch] = (uint8_t)v;
+          const uint8_t *q0 = col_src + (size_t)r.x, *q1 = col_src + (size_t)r.y;
+          dst[ty * kSrcPitch] = (uint8_t)(((q0[0] + q0[1] + q1[0] + q1[1] + 2) >> 2) & r.z);
         }
       }
       else
@@ -175,20 +189,27 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
           ax = 0;
         }
         const uint8_t *__restrict__ col_src = src + sx;
-#pragma unroll 4
-        for (int ty = grp; ty < kSrcH; ty += kColGroups)
+        constexpr int U = 4; // rows per batch: 16 byte loads in flight per thread
+        for (int ty0 = grp; ty0 < kSrcH; ty0 += U * kColGroups)
         {
-          const uint4 r = s_row[ty];
-          uint32_t v = 0;
-          if (r.x != kOutside)
+          uint32_t p00[U], p01[U], p10[U], p11[U], bz[U], bw[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
           {
+            const uint4 r = s_row[min(ty0 + u * kColGroups, kSrcH - 1)];
             const uint8_t *q0 = col_src + (size_t)r.x, *q1 = col_src + (size_t)r.y; // 64-bit: the +1 folds into the load's immediate
-            const uint32_t h0 = q0[0] * ax + q0[1] * ay;
-            const uint32_t h1 = q1[0] * ax + q1[1] * ay;
-            // (((bx * (h0 >> 4)) >> 16) + ((by * (h1 >> 4)) >> 16) + 2) >> 2; at most 255 because bx + by == 2048
-            v = (__umulhi(r.z, h0 >> 4) + __umulhi(r.w, h1 >> 4) + 2u) >> 2;
+            p00[u] = q0[0], p01[u] = q0[1], p10[u] = q1[0], p11[u] = q1[1];
+            bz[u] = r.z, bw[u] = r.w;
           }
-          dst[ty * kSrcPitch] = (uint8_t)v;
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+          {
+            const uint32_t h0 = p00[u] * ax + p01[u] * ay;
+            const uint32_t h1 = p10[u] * ax + p11[u] * ay;
+            // (((bx * (h0 >> 4)) >> 16) + ((by * (h1 >> 4)) >> 16) + 2) >> 2; at most 255 because bx + by == 2048
+            const uint32_t v = (__umulhi(bz[u], h0 >> 4) + __umulhi(bw[u], h1 >> 4) + 2u) >> 2;
+            if (ty0 + u * kColGroups < kSrcH) dst[(ty0 + u * kColGroups) * kSrcPitch] = (uint8_t)v;
+          }
         }
       }
     }
