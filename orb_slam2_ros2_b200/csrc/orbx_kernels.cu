@@ -1676,8 +1676,11 @@ void launch_rowindex(const Params &p, int n_frames, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kStereoWarps = 8;
 
+constexpr int kWinPitch = 24;
+
 __global__ void __launch_bounds__(kStereoWarps * 32, 5) stereo_kernel(const Params p)
 {
+  __shared__ uint8_t s_win[kStereoWarps][11 * kWinPitch];
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int li = blockIdx.x * kStereoWarps + (threadIdx.x >> 5);
@@ -1742,37 +1745,55 @@ __global__ void __launch_bounds__(kStereoWarps * 32, 5) stereo_kernel(const Para
   // Out-of-image windows can only arise with undistorted left coordinates; the reference would throw cv::Exception there.
   if (lx - 5 < 0 || ly - 5 < 0 || lx + 5 >= LL.w || ly + 5 >= LL.h || rx - 10 < 0 || ry - 5 < 0 || rx + 10 >= LR.w || ry + 5 >= LR.h) return;
 
-  int acc[11];
-#pragma unroll
-  for (int s = 0; s < 11; ++s) acc[s] = 0;
-  const int lc = il[(size_t)ly * LL.pitch + lx];
-  int rc[11];
+  // 11 SADs of 11x11 centre-subtracted patches (:841-881).  The right window (11 rows x 21 columns) is staged in shared
+  // memory; lane i handles the left-patch positions i, i + 32, i + 64, i + 96 (< 121) for all 11 shifts:
+  // |(L - lc) - (R - rc_s)| = |(L - lc + rc_s) - R| is one add and one sad per term, and the 11 sums leave through REDUX.
+  uint8_t *win = s_win[threadIdx.x >> 5];
   {
-    const int v = lane < 21 ? ir[(size_t)ry * LR.pitch + rx - 10 + lane] : 0;
+    uint8_t tmp[8];
 #pragma unroll
-    for (int s = 0; s < 11; ++s) rc[s] = __shfl_sync(FULL, v, 5 + s);
-  }
-#pragma unroll 1
-  for (int r = 0; r < 11; ++r)
-  {
-    const int lv = lane < 11 ? (int)il[(size_t)(ly - 5 + r) * LL.pitch + lx - 5 + lane] - lc : 0;
-    const int rv = lane < 21 ? (int)ir[(size_t)(ry - 5 + r) * LR.pitch + rx - 10 + lane] : 0;
-#pragma unroll
-    for (int s = 0; s < 11; ++s)
+    for (int k = 0; k < 8; ++k)
     {
-      const int b = __shfl_sync(FULL, rv, (lane + s) & 31) - rc[s];
-      if (lane < 11) acc[s] += abs(lv - b);
+      const int i = min(lane + 32 * k, 230), r = i / 21, c = i - 21 * r;
+      tmp[k] = ir[(size_t)(ry - 5 + r) * LR.pitch + rx - 10 + c];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      const int i = lane + 32 * k, r = i / 21, c = i - 21 * r;
+      if (i < 231) win[r * kWinPitch + c] = tmp[k];
+    }
+  }
+  const int lc = il[(size_t)ly * LL.pitch + lx];
+  int lv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+  {
+    const int i = min(lane + 32 * k, 120), r = i / 11, c = i - 11 * r;
+    lv[k] = (int)il[(size_t)(ly - 5 + r) * LL.pitch + lx - 5 + c] - lc;
+  }
+  __syncwarp();
+  int rc[11], acc[11];
+#pragma unroll
+  for (int s = 0; s < 11; ++s)
+  {
+    rc[s] = win[5 * kWinPitch + 5 + s];
+    acc[s] = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+  {
+    const int i = lane + 32 * k, r = min(i, 120) / 11, c = min(i, 120) - 11 * r;
+    if (i < 121)
+    {
+      const uint8_t *w = win + r * kWinPitch + c;
+#pragma unroll
+      for (int s = 0; s < 11; ++s) acc[s] = __sad(lv[k] + rc[s], (int)w[s], acc[s]);
     }
   }
   int sad[11];
 #pragma unroll
-  for (int s = 0; s < 11; ++s)
-  {
-    int v = acc[s];
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); // lanes 0..15 (11..15 hold zeros)
-    sad[s] = __shfl_sync(FULL, v, 0);
-  }
+  for (int s = 0; s < 11; ++s) sad[s] = __reduce_add_sync(FULL, acc[s]);
   if (lane != 0) return;
   int bi = 0;
 #pragma unroll
