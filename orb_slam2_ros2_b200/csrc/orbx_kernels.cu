@@ -1503,8 +1503,39 @@ __device__ __forceinline__ void undistort_point(const Params &p, float u, float 
   vo = __double2float_rn(__dadd_rn(__dmul_rn(y, fy), cy));
 }
 
+// cvRound of a float in (-2^22, 2^22) without the conversion unit: adding 1.5 * 2^23 leaves the integer, rounded half to
+// even by the adder, in the low mantissa bits.
+__device__ __forceinline__ int round_half_even_small(float v) { return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000; }
+
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a_u8x4, uint32_t b_s8x4, int c)
+{
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+  return d;
+}
+
 __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const Params p)
 {
+  // byte masks of the radius-15 disc: row |dy| covers columns |dx| <= umax[|dy|]; [|dy|][word k] selects bytes 4k..4k+3 of
+  // the 32-byte row that starts at dx = -15 (byte 31 is never part of the disc)
+  __shared__ __align__(16) uint32_t s_disc[16][8];
+  {
+    const int t = threadIdx.x;
+    if (t < 128)
+    {
+      const int ady = t >> 3, k = t & 7;
+      uint32_t m = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+      {
+        const int dx = 4 * k + b - 15;
+        if (dx <= 15 && abs(dx) <= c_umax[ady]) m |= 0xffu << (8 * b);
+      }
+      s_disc[ady][k] = m;
+    }
+  }
+  __syncthreads();
+
   const int img = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kBriefWarps + (threadIdx.x >> 5);
@@ -1533,29 +1564,41 @@ __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const
   const uint8_t *__restrict__ lvl = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
   const uint8_t *__restrict__ blr = p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off;
 
-  // getGrayCentroid (:465-487): moments over the radius-15 disc of the un-blurred level; lane <-> column offset.
-  // Row dy belongs to the lane's column iff |dx| <= umax[|dy|]: a 31-bit row mask per lane, then a fully unrolled loop of
-  // predicated byte loads so that all 31 loads are in flight together.
+  // getGrayCentroid (:465-487): moments over the radius-15 disc of the un-blurred level.  The disc's 31 rows are fetched
+  // as aligned words, 3 rows x 9 words per warp request (3 cache lines); a lane takes its word and the next one (from the
+  // neighbour lane), shifts them to the row start and takes both row sums with DP4A: sum(I) against the row's byte mask
+  // and sum(dx * I) against the masked signed weights dx = 4k - 15 .. 4k - 12.  Every level pitch is a multiple of 4, so
+  // the shift is the same for all rows.
   int m10 = 0, m01 = 0;
   {
-    const int dx = lane - 15, adx = abs(dx);
-    unsigned rows = 0u;
+    const int rg = lane / 9, wk = lane - 9 * rg; // lanes 27..31: rg == 3, idle
+    const uint8_t *row0 = lvl + (size_t)(y - 15) * pitch + (x - 15);
+    const uint32_t sh = ((uint32_t)(size_t)row0 & 3u) * 8u;
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>((size_t)row0 & ~(size_t)3) + wk;
+    const int pitch4 = pitch >> 2;
+    uint32_t a[11];
 #pragma unroll
-    for (int dy = -15; dy <= 15; ++dy) rows |= (unsigned)(lane < 31 && adx <= c_umax[dy < 0 ? -dy : dy]) << (dy + 15);
-    const uint8_t *c = lvl + (size_t)(y - 15) * pitch + x + dx; // row -15 of the lane's column; walks down one pitch per row
-    int colsum = 0;
-#pragma unroll
-    for (int dy = -15; dy <= 15; ++dy)
+    for (int j = 0; j < 11; ++j)
     {
-      const int v = ((rows >> (dy + 15)) & 1u) ? (int)*c : 0;
-      c += pitch;
-      colsum += v;
-      m01 += dy * v;
+      const int r = 3 * j + rg;
+      a[j] = (rg < 3 && r < 31) ? w0[(size_t)r * pitch4] : 0u;
     }
-    m10 = dx * colsum;
+    const int k = min(wk, 7);
+    const uint32_t wdx = ((uint32_t)((4 * k - 15) & 0xff)) | ((uint32_t)((4 * k - 14) & 0xff) << 8) | ((uint32_t)((4 * k - 13) & 0xff) << 16) |
+                         ((uint32_t)((4 * k - 12) & 0xff) << 24);
+#pragma unroll
+    for (int j = 0; j < 11; ++j)
+    {
+      const int r = min(3 * j + rg, 30), dy = r - 15;
+      const uint32_t nxt = __shfl_down_sync(FULL, a[j], 1);
+      const uint32_t v = __funnelshift_r(a[j], nxt, sh);
+      const uint32_t msk = (rg < 3 && wk < 8 && 3 * j + rg < 31) ? s_disc[abs(dy)][k] : 0u;
+      m10 = dp4a_u8_s8(v, wdx & msk, m10);
+      m01 += dy * (int)__dp4a(v, msk & 0x01010101u, 0u);
+    }
   }
-  m10 = warp_sum(m10);
-  m01 = warp_sum(m01);
+  m10 = __reduce_add_sync(FULL, m10);
+  m01 = __reduce_add_sync(FULL, m01);
   const double theta = atan2((double)m01, (double)m10);
   double sn, cs;
   sincos(theta, &sn, &cs);
@@ -1566,14 +1609,15 @@ __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const
 #pragma unroll
   for (int k = 0; k < 8; ++k)
   {
-    const char4 t = p.pattern[lane * 8 + k]; // bit b = lane * 8 + k lands in byte b >> 3 == lane, position b & 7 == k
-    const double x1 = (double)t.x, y1 = (double)t.y, x2 = (double)t.z, y2 = (double)t.w;
+    // bit b = lane * 8 + k lands in byte b >> 3 == lane, position b & 7 == k
+    const double2 t1 = __ldg(p.pattern_d + k * 32 + lane), t2 = __ldg(p.pattern_d + (8 + k) * 32 + lane);
+    const double x1 = t1.x, y1 = t1.y, x2 = t2.x, y2 = t2.y;
     const float p1x = __double2float_rn(__dsub_rn(__dmul_rn(x1, cs), __dmul_rn(y1, sn)));
     const float p1y = __double2float_rn(__dadd_rn(__dmul_rn(x1, sn), __dmul_rn(y1, cs)));
     const float p2x = __double2float_rn(__dsub_rn(__dmul_rn(x2, cs), __dmul_rn(y2, sn)));
     const float p2y = __double2float_rn(__dadd_rn(__dmul_rn(x2, sn), __dmul_rn(y2, cs)));
-    const int v1 = blr[(size_t)__float2int_rn(__fadd_rn(fy, p1y)) * pitch + __float2int_rn(__fadd_rn(fx, p1x))];
-    const int v2 = blr[(size_t)__float2int_rn(__fadd_rn(fy, p2y)) * pitch + __float2int_rn(__fadd_rn(fx, p2x))];
+    const int v1 = blr[round_half_even_small(__fadd_rn(fy, p1y)) * pitch + round_half_even_small(__fadd_rn(fx, p1x))];
+    const int v2 = blr[round_half_even_small(__fadd_rn(fy, p2y)) * pitch + round_half_even_small(__fadd_rn(fx, p2x))];
     byte |= (uint32_t)(v1 < v2) << k;
   }
   const size_t o = (size_t)img * p.n_features + slot;
