@@ -1503,10 +1503,6 @@ __device__ __forceinline__ void undistort_point(const Params &p, float u, float 
   vo = __double2float_rn(__dadd_rn(__dmul_rn(y, fy), cy));
 }
 
-// cvRound of a float in (-2^22, 2^22) without the conversion unit: adding 1.5 * 2^23 leaves the integer, rounded half to
-// even by the adder, in the low mantissa bits.
-__device__ __forceinline__ int round_half_even_small(float v) { return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000; }
-
 __device__ __forceinline__ int dp4a_u8_s8(uint32_t a_u8x4, uint32_t b_s8x4, int c)
 {
   int d;
@@ -1605,6 +1601,10 @@ __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const
 
   // computeBRIEF (:427-456) with rotateTemplate (:534-540): double products, float result, float add, round-half-even
   const float fx = (float)x, fy = (float)y;
+  const uint32_t upitch = (uint32_t)pitch;
+  size_t magic_off = (size_t)0x4B400000u * ((size_t)upitch + 1u);
+  asm volatile("" : "+l"(magic_off)); // opaque: keeps the constant folded into the base instead of re-subtracted per access
+  const uint8_t *__restrict__ blr_m = blr - magic_off;
   uint32_t byte = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k)
@@ -1616,8 +1616,12 @@ __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const
     const float p1y = __double2float_rn(__dadd_rn(__dmul_rn(x1, sn), __dmul_rn(y1, cs)));
     const float p2x = __double2float_rn(__dsub_rn(__dmul_rn(x2, cs), __dmul_rn(y2, sn)));
     const float p2y = __double2float_rn(__dadd_rn(__dmul_rn(x2, sn), __dmul_rn(y2, cs)));
-    const int v1 = blr[round_half_even_small(__fadd_rn(fy, p1y)) * pitch + round_half_even_small(__fadd_rn(fx, p1x))];
-    const int v2 = blr[round_half_even_small(__fadd_rn(fy, p2y)) * pitch + round_half_even_small(__fadd_rn(fx, p2x))];
+    // cvRound without the conversion unit: float_as_uint(v + 1.5 * 2^23) == 0x4B400000 + round_half_even(v) for 0 <= v < 2^22;
+    // the constant is folded into the base pointer, the row product is one 64-bit multiply-add
+    const uint32_t r1y = __float_as_uint(__fadd_rn(__fadd_rn(fy, p1y), 12582912.f)), r1x = __float_as_uint(__fadd_rn(__fadd_rn(fx, p1x), 12582912.f));
+    const uint32_t r2y = __float_as_uint(__fadd_rn(__fadd_rn(fy, p2y), 12582912.f)), r2x = __float_as_uint(__fadd_rn(__fadd_rn(fx, p2x), 12582912.f));
+    const int v1 = blr_m[(size_t)r1y * upitch + r1x];
+    const int v2 = blr_m[(size_t)r2y * upitch + r2x];
     byte |= (uint32_t)(v1 < v2) << k;
   }
   const size_t o = (size_t)img * p.n_features + slot;
