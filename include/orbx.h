@@ -202,6 +202,23 @@ int orbx_search_in_area_batch_device(orbx_ctx *ctx, int n_frames, int query_stri
 int orbx_verify_angle(orbx_ctx *ctx, int n_matches, int32_t *query_idx, int32_t *train_idx, float *distance,
                       const orbx_keypoint *kps1, int n1, const orbx_keypoint *kps2, int n2, int32_t *n_out);
 
+/* ---- result serialisation ------------------------------------------------- */
+/* replaces: KeyFrame::serializeToProtobuf (src/KeyFrame.cc:553-647) for a keyframe made from frame `frame` of the most
+ * recent stereo / RGB-D call: the orbslam2.KeyFrameData record (proto3 wire format, proto/Keyframe.proto:45-64) with
+ * id, the undistorted image bounds, keypoints (x, y, octave, angle), right_u / depths narrowed to float, descriptors,
+ * present-but-empty bow_vector / feature_vector, pose Tcw = pose_rt (R row-major [9] then t [3]; NULL = identity as in
+ * the VirtualFrame ctor, include/ORB_SLAM2/Frame.h:44-45) and, if with_map_points, -1 for every keypoint's map point.
+ * The record is assembled on the device; only its bytes are copied out.  *n_bytes is set even when cap is too small
+ * (ORBX_ERR_CAPACITY).  A KeyFrameList (proto/Keyframe.proto:66-70) is these records as length-delimited field 3. */
+int64_t orbx_serialized_capacity(const orbx_ctx *ctx); /* upper bound of one record for this context (multiple of 16) */
+int orbx_serialize_keyframe(orbx_ctx *ctx, int frame, uint64_t id, const float *pose_rt /* [12] or NULL */,
+                            int with_map_points, uint8_t *out, size_t cap, int64_t *n_bytes);
+/* frames 0..n_frames-1 of the most recent *_device call into DEVICE memory, asynchronous on the context's stream: record f
+ * (id = id0 + f, pose d_pose_rt[f * 12 ..] or identity) at d_out + f * frame_stride (>= orbx_serialized_capacity, both
+ * 4-byte aligned), its size in d_sizes[f]. */
+int orbx_serialize_keyframes_device(orbx_ctx *ctx, int n_frames, uint64_t id0, const float *d_pose_rt,
+                                    int with_map_points, uint8_t *d_out, size_t frame_stride, int64_t *d_sizes);
+
 /* ---- introspection for benchmarks / profiles ----------------------------------------------------------- */
 #define ORBX_N_STAGES 6
 /* Same work as orbx_stereo_batch_device, with a CUDA event recorded on the stream after every kernel; blocks until

@@ -278,6 +278,17 @@ public:
         for (int i = start[(size_t)r * cols + c]; i < start[(size_t)r * cols + c + 1]; ++i) g[(size_t)r][(size_t)c].push_back((std::size_t)all[(size_t)i]);
     return g;
   }
+  // orbslam2.KeyFrameData bytes for a keyframe made from this frame (KeyFrame::serializeToProtobuf, src/KeyFrame.cc:553-647;
+  // proto/Keyframe.proto:45-64), assembled on the device.  The frame must be the context's most recent one.
+  std::string serializeKeyFrameData(uint64_t id, const float *poseRt /* R row-major [9] + t [3], or nullptr */ = nullptr, bool withMapPoints = true) const
+  {
+    std::string out((size_t)orbx_serialized_capacity(mCtx.get()), '\0');
+    int64_t n = 0;
+    detail::check(mCtx.get(), orbx_serialize_keyframe(mCtx.get(), 0, id, poseRt, withMapPoints ? 1 : 0, (uint8_t *)&out[0], out.size(), &n),
+                  "orbx_serialize_keyframe");
+    out.resize((size_t)n);
+    return out;
+  }
   std::vector<cv::Mat> getLeftPyramid() const { return detail::fetch_pyramid(mCtx.get(), 0); }
   std::vector<cv::Mat> getRightPyramid() const { return detail::fetch_pyramid(mCtx.get(), 1); }
   int getN() const { return mnN; }

@@ -87,6 +87,9 @@ def lib():
                                             u8p, i32p, i32p, f32p, i32p]
         L.oracle_verify_angle.restype = C.c_int
         L.oracle_verify_angle.argtypes = [C.c_int, i32p, i32p, f32p, C.c_void_p, C.c_void_p]
+        L.oracle_serialize_keyframe.restype = C.c_size_t
+        L.oracle_serialize_keyframe.argtypes = [C.c_void_p, u8p, f64p, f64p, C.c_int, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float, f32p, C.c_int,
+                                                u8p, C.c_size_t]
         L.oracle_search_by_stereo.restype = C.c_int
         L.oracle_search_by_stereo.argtypes = [C.POINTER(_Pyramid), C.POINTER(_Pyramid), C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int,
                                               C.c_float, C.c_float, f64p, f64p, i32p]
@@ -349,6 +352,21 @@ def verify_angle(query_idx, train_idx, distance, kps1, kps2):
     k1, k2 = np.ascontiguousarray(kps1, KP_DTYPE), np.ascontiguousarray(kps2, KP_DTYPE)
     m = lib().oracle_verify_angle(len(qi), _ptr(qi, i32p), _ptr(ti, i32p), _ptr(di, f32p), k1.ctypes.data, k2.ctypes.data)
     return qi[:m], ti[:m], di[:m]
+
+
+def serialize_keyframe(kps, desc, u_right, depth, kf_id, bounds, pose_rt=None, with_map_points=True) -> bytes:
+    """oracle_serialize_keyframe: orbslam2.KeyFrameData bytes (proto/Keyframe.proto:45-64, writer src/KeyFrame.cc:553-647).
+    bounds = (min_u, min_v, max_u, max_v) as returned by grid_info"""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    ur, dp = np.ascontiguousarray(u_right, np.float64), np.ascontiguousarray(depth, np.float64)
+    n = len(kps)
+    pose = None if pose_rt is None else np.ascontiguousarray(pose_rt, np.float32)
+    out = np.zeros(256 + 96 * n, np.uint8)
+    m = lib().oracle_serialize_keyframe(kps.ctypes.data, _ptr(desc, u8p), _ptr(ur, f64p), _ptr(dp, f64p), n, kf_id, bounds[2], bounds[3], bounds[0], bounds[1],
+                                        _ptr(pose, f32p), int(with_map_points), _ptr(out, u8p), out.size)
+    assert m > 0
+    return out[:m].tobytes()
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -853,3 +853,113 @@ int oracle_verify_angle(int n, int *query_idx, int *train_idx, float *distance, 
   free(di);
   return m;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Result serialisation: orbslam2.KeyFrameData, proto3 wire format
+ * (proto/Keyframe.proto:7-17,45-64), the bytes KeyFrame::serializeToProtobuf (src/KeyFrame.cc:553-647) produces for
+ * a keyframe made from a fresh frame: no BoW yet (empty but present messages 10, 11), pose Tcw, no connections,
+ * children or loop edges, and -1 for every keypoint's map point.
+ * --------------------------------------------------------------------------------------------------------------- */
+static size_t pb_varint(uint8_t *o, uint64_t v) {
+  size_t n = 0;
+  while (v >= 0x80) {
+    o[n++] = (uint8_t)(v | 0x80);
+    v >>= 7;
+  }
+  o[n++] = (uint8_t)v;
+  return n;
+}
+static size_t pb_f32(uint8_t *o, float f) {
+  memcpy(o, &f, 4);
+  return 4;
+}
+static uint32_t f32_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
+size_t oracle_serialize_keyframe(const oracle_keypoint *kps, const uint8_t *desc, const double *u_right,
+                                 const double *depth, int n, uint64_t id, float max_u, float max_v, float min_u,
+                                 float min_v, const float *pose_rt /*[12] R row-major + t, NULL = identity*/,
+                                 int with_map_points, uint8_t *out, size_t cap) {
+  size_t need = 128 + (size_t)n * (28 + 4 + 4 + 36 + 10); /* a KeyPoint entry is at most 2 + 5 + 5 + 11 + 5 bytes */
+  if (cap < need) return 0;
+  uint8_t *o = out;
+  if (id) { /* proto3: scalar fields equal to zero are not written */
+    *o++ = 0x08;
+    o += pb_varint(o, id);
+  }
+  const float b[4] = {max_u, max_v, min_u, min_v};
+  for (int k = 0; k < 4; ++k)
+    if (f32_bits(b[k])) {
+      *o++ = (uint8_t)(((2 + k) << 3) | 5);
+      o += pb_f32(o, b[k]);
+    }
+  for (int i = 0; i < n; ++i) { /* repeated KeyPoint keypoints = 6 */
+    uint8_t m[32];
+    size_t l = 0;
+    if (f32_bits(kps[i].x)) {
+      m[l++] = 0x0D;
+      l += pb_f32(m + l, kps[i].x);
+    }
+    if (f32_bits(kps[i].y)) {
+      m[l++] = 0x15;
+      l += pb_f32(m + l, kps[i].y);
+    }
+    if (kps[i].octave) {
+      m[l++] = 0x18;
+      l += pb_varint(m + l, (uint64_t)(int64_t)kps[i].octave); /* int32: negative values sign-extend to 10 bytes */
+    }
+    if (f32_bits(kps[i].angle)) {
+      m[l++] = 0x25;
+      l += pb_f32(m + l, kps[i].angle);
+    }
+    *o++ = 0x32;
+    o += pb_varint(o, l);
+    memcpy(o, m, l);
+    o += l;
+  }
+  if (n) { /* repeated float right_u = 7, depths = 8: packed; the writer narrows the doubles to float (:575-576) */
+    *o++ = 0x3A;
+    o += pb_varint(o, 4u * (uint64_t)n);
+    for (int i = 0; i < n; ++i) o += pb_f32(o, (float)u_right[i]);
+    *o++ = 0x42;
+    o += pb_varint(o, 4u * (uint64_t)n);
+    for (int i = 0; i < n; ++i) o += pb_f32(o, (float)depth[i]);
+  }
+  for (int i = 0; i < n; ++i) { /* repeated Descriptor descriptors = 9 { bytes data = 1 } */
+    *o++ = 0x4A;
+    *o++ = 34;
+    *o++ = 0x0A;
+    *o++ = 32;
+    memcpy(o, desc + 32 * (size_t)i, 32);
+    o += 32;
+  }
+  *o++ = 0x52; /* bow_vector = 10: mutable_bow_vector() makes the empty message present (:586) */
+  *o++ = 0;
+  *o++ = 0x5A; /* feature_vector = 11 (:593) */
+  *o++ = 0;
+  {            /* Pose pose = 12 { repeated float rotation = 1 [9]; repeated float translation = 2 [3] } (:602-608) */
+    static const float eye[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    const float *rt = pose_rt ? pose_rt : eye;
+    *o++ = 0x62;
+    *o++ = 52;
+    *o++ = 0x0A;
+    *o++ = 36;
+    for (int k = 0; k < 9; ++k) o += pb_f32(o, rt[k]);
+    *o++ = 0x12;
+    *o++ = 12;
+    for (int k = 0; k < 3; ++k) o += pb_f32(o, rt[9 + k]);
+  }
+  if (with_map_points && n) { /* repeated int64 map_points = 16: -1 per keypoint without a map point (:641-646) */
+    o += pb_varint(o, (16u << 3) | 2u);
+    o += pb_varint(o, 10u * (uint64_t)n);
+    for (int i = 0; i < n; ++i) {
+      memset(o, 0xFF, 9);
+      o[9] = 0x01;
+      o += 10;
+    }
+  }
+  return (size_t)(o - out);
+}

@@ -124,6 +124,13 @@ void oracle_search_in_area(const oracle_keypoint *kps, const uint8_t *desc, int 
 int oracle_verify_angle(int n, int *query_idx, int *train_idx, float *distance, const oracle_keypoint *kps1,
                         const oracle_keypoint *kps2);
 
+/* ---- result serialisation ---- */
+/* orbslam2.KeyFrameData bytes (proto/Keyframe.proto:45-64) as written by KeyFrame::serializeToProtobuf
+ * (src/KeyFrame.cc:553-647) for a keyframe made from a fresh frame.  Returns the size, 0 if cap is too small. */
+size_t oracle_serialize_keyframe(const oracle_keypoint *kps, const uint8_t *desc, const double *u_right,
+                                 const double *depth, int n, uint64_t id, float max_u, float max_v, float min_u,
+                                 float min_v, const float *pose_rt, int with_map_points, uint8_t *out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

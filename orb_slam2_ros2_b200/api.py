@@ -73,6 +73,7 @@ EXPORTS = [
     "orbx_stereo_batch_device", "orbx_extract_batch_device", "orbx_rgbd_batch_device", "orbx_synchronize", "orbx_launch_count", "orbx_algorithmic_bytes",
     "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name", "orbx_debug_run_quadtree", "orbx_grid_info", "orbx_get_grid",
     "orbx_search_in_area", "orbx_search_in_area_batch_device", "orbx_verify_angle",
+    "orbx_serialized_capacity", "orbx_serialize_keyframe", "orbx_serialize_keyframes_device",
 ]
 
 _lib = None
@@ -129,6 +130,10 @@ def load_library(build_if_missing: bool = True):
     L.orbx_search_in_area.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_search_in_area_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_verify_angle.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int32)]
+    L.orbx_serialized_capacity.argtypes = [vp]
+    L.orbx_serialized_capacity.restype = C.c_int64
+    L.orbx_serialize_keyframe.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, vp, sz, C.POINTER(C.c_int64)]
+    L.orbx_serialize_keyframes_device.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, vp, sz, vp]
     _lib = L
     return L
 
@@ -369,6 +374,27 @@ class Context:
                                        C.byref(m))
         _check(self._h, rc, "orbx_verify_angle")
         return qi[: m.value], ti[: m.value], di[: m.value]
+
+    # ---- result serialisation ------------------------------------------------------------
+    def serialized_capacity(self) -> int:
+        return int(self._L.orbx_serialized_capacity(self._h))
+
+    def serialize_keyframe(self, kf_id: int, pose_rt=None, with_map_points: bool = True, frame: int = 0) -> bytes:
+        """orbslam2.KeyFrameData bytes (proto/Keyframe.proto:45-64; writer src/KeyFrame.cc:553-647) of a frame of the last call"""
+        cap = self.serialized_capacity()
+        out = np.zeros(cap, np.uint8)
+        pose = None if pose_rt is None else np.ascontiguousarray(pose_rt, np.float32)
+        assert pose is None or pose.size == 12
+        n = C.c_int64(0)
+        rc = self._L.orbx_serialize_keyframe(self._h, frame, kf_id, pose.ctypes.data if pose is not None else None, int(with_map_points), out.ctypes.data, cap,
+                                             C.byref(n))
+        _check(self._h, rc, "orbx_serialize_keyframe")
+        return out[: n.value].tobytes()
+
+    def serialize_keyframes_device(self, n_frames, id0, d_out, frame_stride, d_sizes, d_pose_rt=0, with_map_points=True):
+        rc = self._L.orbx_serialize_keyframes_device(self._h, n_frames, id0, C.c_void_p(d_pose_rt or 0), int(with_map_points), C.c_void_p(d_out), frame_stride,
+                                                     C.c_void_p(d_sizes))
+        _check(self._h, rc, "orbx_serialize_keyframes_device")
 
     # ---- batches ----------------------------------------------------------------------------------------------------
     def stereo_batch(self, left: np.ndarray, right: np.ndarray, out: "StereoBatchBuffers | None" = None):

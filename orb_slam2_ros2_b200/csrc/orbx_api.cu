@@ -1157,6 +1157,64 @@ extern "C"
     return ORBX_OK;
   }
 
+  // ---------------------------------------------------------------------------------------------------------------
+  // result serialisation
+  int64_t orbx_serialized_capacity(const orbx_ctx *c)
+  {
+    if (!c) return 0;
+    // head <= 31, tail 58, packed-field headers <= 16; per keypoint: entry <= 28, right_u 4, depth 4, descriptor 36, map point 10
+    return (int64_t)((128 + (size_t)c->cfg.n_features * (28 + 4 + 4 + 36 + 10) + 15) & ~(size_t)15);
+  }
+
+  int orbx_serialize_keyframes_device(orbx_ctx *c, int n_frames, uint64_t id0, const float *d_pose_rt, int with_map_points, uint8_t *d_out,
+                                      size_t frame_stride, int64_t *d_sizes)
+  {
+    if (!c || n_frames < 1 || !d_out || !d_sizes) return ORBX_ERR_INVALID_ARG;
+    if (((size_t)d_out & 3) || (frame_stride & 3)) return fail(c, ORBX_ERR_INVALID_ARG, "output buffer and stride must be 4-byte aligned");
+    if ((int64_t)frame_stride < orbx_serialized_capacity(c)) return fail(c, ORBX_ERR_CAPACITY, "frame_stride is smaller than orbx_serialized_capacity()");
+    if (n_frames > c->last_frames) return fail(c, ORBX_ERR_STATE, "more frames than the last stereo / RGB-D call processed");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    SerArgs a{};
+    a.out = d_out, a.stride = frame_stride, a.sizes = (long long *)d_sizes, a.id0 = id0, a.pose = d_pose_rt, a.with_map_points = with_map_points;
+    a.image_stride = c->last_stereo ? 2 : 1;
+    a.max_u = c->max_u, a.max_v = c->max_v, a.min_u = c->min_u, a.min_v = c->min_v;
+    launch_serialize(c->p, a, n_frames, c->stream);
+    ++c->launches;
+    ORBX_CUDA(c, cudaGetLastError());
+    return ORBX_OK;
+  }
+
+  int orbx_serialize_keyframe(orbx_ctx *c, int frame, uint64_t id, const float *pose_rt, int with_map_points, uint8_t *out, size_t cap, int64_t *n_bytes)
+  {
+    if (!c || frame < 0 || !out || !n_bytes) return ORBX_ERR_INVALID_ARG;
+    if (frame >= c->last_frames) return fail(c, ORBX_ERR_STATE, "no frame with that index has been processed by a stereo / RGB-D call");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const size_t rec = (size_t)orbx_serialized_capacity(c);
+    uint8_t *base = nullptr;
+    int rc = match_scratch(c, rec + 256, &base);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    float *d_pose = (float *)(base + rec);
+    int64_t *d_size = (int64_t *)(base + rec + 64);
+    if (pose_rt) ORBX_CUDA(c, cudaMemcpyAsync(d_pose, pose_rt, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    SerArgs a{};
+    a.out = base, a.stride = rec, a.sizes = (long long *)d_size, a.id0 = id, a.pose = pose_rt ? d_pose : nullptr;
+    a.with_map_points = with_map_points;
+    a.image_stride = c->last_stereo ? 2 : 1;
+    a.max_u = c->max_u, a.max_v = c->max_v, a.min_u = c->min_u, a.min_v = c->min_v;
+    const Params p = params_at(c, frame * a.image_stride, frame); // the single CTA (block 0) works on `frame`
+    launch_serialize(p, a, 1, s);
+    ++c->launches;
+    ORBX_CUDA(c, cudaGetLastError());
+    int64_t sz = 0;
+    ORBX_CUDA(c, cudaMemcpyAsync(&sz, d_size, sizeof(sz), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(c, cudaStreamSynchronize(s));
+    *n_bytes = sz;
+    if ((size_t)sz > cap) return fail(c, ORBX_ERR_CAPACITY, "output buffer too small for the record (see *n_bytes)");
+    ORBX_CUDA(c, cudaMemcpy(out, base, (size_t)sz, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+  }
+
   int orbx_debug_level_corners(orbx_ctx *c, int image, int level, int32_t *xs, int32_t *ys, int32_t *scores, int cap, int32_t *n)
   {
     if (!c || !n || level < 0 || level >= c->cfg.n_levels || image < 0) return ORBX_ERR_INVALID_ARG;

@@ -164,7 +164,20 @@ struct VerifyArgs
   int *n_out;
 };
 
-// launchers (orbx_kernels.cu / orbx_match.cu); every call enqueues exactly one kernel on `s`
+// result serialisation (orbx_serialize.cu)
+struct SerArgs
+{
+  uint8_t *out;          // [frame][stride], 4-byte aligned
+  size_t stride;
+  long long *sizes;      // [frame] bytes written
+  unsigned long long id0; // record of frame f carries id0 + f
+  const float *pose;     // [frame][12] R (row-major) | t, or null = identity
+  int with_map_points;
+  int image_stride;
+  float max_u, max_v, min_u, min_v;
+};
+
+// launchers (orbx_kernels.cu / orbx_match.cu / orbx_serialize.cu); every call enqueues exactly one kernel on `s`
 void launch_pyramid(const Params &p, int n_images, cudaStream_t s);
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
@@ -175,6 +188,7 @@ void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
 void launch_grid(const Params &p, int n_frames, int image_stride, cudaStream_t s);
 void launch_area_match(const Params &p, const AreaArgs &a, int n_frames, cudaStream_t s);
 void launch_verify_angle(const VerifyArgs &a, cudaStream_t s);
+void launch_serialize(const Params &p, const SerArgs &a, int n_frames, cudaStream_t s);
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells);
 int quadtree_configure(size_t smem_bytes); // opt in to large dynamic shared memory
 

@@ -109,6 +109,10 @@ int main(int argc, char **argv)
       ORBMatcher::verifyAngle(f, matches, f->getLeftKeyPoints(), k2);
       put(out, (int32_t)matches.size());
       for (auto &m : matches) put(out, (int32_t)m.queryIdx), put(out, (int32_t)m.trainIdx), put(out, m.distance);
+      // KeyFrame::serializeToProtobuf for a keyframe made from this frame
+      std::string rec = f->serializeKeyFrameData(42);
+      put(out, (int32_t)rec.size());
+      out.write(rec.data(), (std::streamsize)rec.size());
     }
     else if (mode == "rgbd")
     {

@@ -110,6 +110,9 @@ def test_shim_stereo_matches_oracle(shim_binary, template_path, oracle, tmp_path
     nv = rd.i32()
     gv = rd.arr(np.dtype([("q", "<i4"), ("t", "<i4"), ("d", "<f4")]), nv)
     assert nv == len(vq) and np.array_equal(gv["q"], vq) and np.array_equal(gv["t"], vt) and np.array_equal(gv["d"], vd)
+    # Frame::serializeKeyFrameData == the oracle's KeyFrameData bytes for the same frame
+    rec = bytes(rd.arr(np.uint8, rd.i32()))
+    assert rec == oracle.serialize_keyframe(kl, dl, ur, dp, 42, (0.0, 0.0, float(c["width"]), float(c["height"])), None, True)
 
 
 @pytest.mark.gpu
