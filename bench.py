@@ -218,9 +218,37 @@ def bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cp
         "accepted_per_frame": accepted / B, "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg},
     }
+    # result serialisation: one KeyFrameData record per frame, assembled on the device
+    cap = ctx.serialized_capacity()
+    with torch.cuda.stream(stream):
+        rec = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+        rec_sizes = torch.zeros(B, dtype=torch.int64, device="cuda")
+        for _ in range(3):
+            ctx.serialize_keyframes_device(B, 1, rec.data_ptr(), cap, rec_sizes.data_ptr())
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream.synchronize()
+        s0.record(stream)
+        for _ in range(reps):
+            ctx.serialize_keyframes_device(B, 1, rec.data_ptr(), cap, rec_sizes.data_ptr())
+        s1.record(stream)
+        stream.synchronize()
+    ser_ms = s0.elapsed_time(s1) / reps
+    ser_bytes = int(rec_sizes.sum().item())
+    out["serialize"] = {"metric": "KeyFrameData records/s (proto3 wire format, %d keypoints each)" % N, "value": B / (ser_ms * 1e-3), "unit": "records/s",
+                        "kernel": "serialize", "kernel_ms": ser_ms, "bytes_per_record": ser_bytes / B,
+                        "roofline": {"bound": "hbm", "achieved": (ser_bytes + B * N * (28 + 32 + 16)) / (ser_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": (ser_bytes + B * N * (28 + 32 + 16)) / (ser_ms * 1e-3) / 1e9 / peak}}
     if cpu:
         from oracle import oracle_py as O
 
+        t0 = time.perf_counter()
+        ur = ctx.read_device(res.u_right, (B, N), np.float64)
+        dpt = ctx.read_device(res.depth, (B, N), np.float64)
+        t0 = time.perf_counter()
+        for f in range(min(B, 16)):
+            O.serialize_keyframe(kps[f][: nk[f]], desc[f][: nk[f]], ur[f][: nk[f]], dpt[f][: nk[f]], 1 + f, ctx.grid_info()[2:], None, True)
+        out["serialize"]["cpu_baseline"] = {"value": min(B, 16) / (time.perf_counter() - t0), "unit": "records/s", "cores": 1, "kind": "port",
+                                            "sample": "%d records" % min(B, 16)}
         bounds = ctx.grid_info()[2:]
         sf = ctx.scaled_factors()
         t0 = time.perf_counter()
