@@ -427,9 +427,10 @@ def run_gpu_arm(args):
         one.close()
 
     # ---- tracking-side matchers: a secondary line, not part of the headline metric ------------
-    matchers = None
+    matchers = serialize = None
     if rank == 0 and not args.no_matchers:
         matchers = bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cpu=(world == 1 and not args.no_cpu_baseline))
+        serialize = matchers.pop("serialize", None)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
     cpu = None
@@ -446,7 +447,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(B, P), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "frames_per_call": S, "matches_first_step": e2e_matches},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency, "matchers": matchers,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency, "matchers": matchers, "serialize": serialize,
             "check": {"mean_keypoints_per_image": float(nk.mean()), "mean_matches_per_frame": float(nm.mean())},
         }
         print(json.dumps(line), flush=True)
