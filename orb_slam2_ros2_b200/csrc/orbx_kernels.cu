@@ -72,7 +72,7 @@ template <int NT> __device__ __forceinline__ int block_exclusive_scan(int v, int
 //   Stage A  thread <-> tile column (coefficients in registers), loop over rows: 4 byte gathers from level 0 per pixel
 //            (second tap at an immediate +1, vertical weights by multiply-high, no clamp: the weights sum to 2048)
 //   Stage B  horizontal pass on packed bytes: 3 aligned LDS.32 + funnel shifts + 8 DP4A per 4 pixels -> u16
-//   Stage C  vertical pass: one item per 4 columns x 2 rows, LDS.64 of packed u16, exact integer MACs
+//   Stage C  vertical pass: one item per 4 columns x 2 rows, LDS.128 of vertically paired u16, DP2A (exact integers)
 //   The tile is stored with pixel 0 at byte 16 of a 96-byte row, so the level image leaves as LDS.128 / STG.128.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kSrcW = kTileW + 2 * kHalo;      // 70
@@ -228,58 +228,58 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
       *reinterpret_cast<uint4 *>(pyr + (size_t)gy * pitch + gx) = *reinterpret_cast<const uint4 *>(&s_src[(ty + kHalo) * kSrcPitch + 16 + tx]);
   }
 
-  // stage B: horizontal pass, 4 outputs per item from 3 aligned words; output pixel 4g + k needs source bytes
-  // 4g + 13 + k .. + 6 of the row = words 3 + g .. 5 + g shifted by 8 (k + 1) bits; sums fit u16 (255 * 256)
+  // stage B: horizontal pass, 2 rows x 4 outputs per item from 3 aligned words per row; output pixel 4g + k needs source
+  // bytes 4g + 13 + k .. + 6 of the row = words 3 + g .. 5 + g shifted by 8 (k + 1) bits; sums fit u16 (255 * 256).
+  // The two rows of a pair share a word (row 2j low, row 2j + 1 high) so that the vertical pass can use DP2A.
   {
     constexpr uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24); // taps 0..3
     constexpr uint32_t K1 = 48u | (34u << 8) | (18u << 16);               // taps 4..6
     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s_src);
-    uint2 *h2 = reinterpret_cast<uint2 *>(s_h);
-    for (int i = tid; i < kSrcH * (kTileW / 4); i += kPyrThreads)
+    uint4 *h4 = reinterpret_cast<uint4 *>(s_h);
+    for (int i = tid; i < (kSrcH / 2) * (kTileW / 4); i += kPyrThreads)
     {
-      const int ty = i >> 4, g = i & 15;
-      const uint32_t *row = s32 + ty * (kSrcPitch / 4) + 3 + g;
-      const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
-      const uint32_t o0 = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
-      const uint32_t o1 = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
-      const uint32_t o2 = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
-      const uint32_t o3 = __dp4a(w1, K0, __dp4a(w2, K1, 0u));
-      h2[i] = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+      const int j = i >> 4, g = i & 15;
+      const uint32_t *row = s32 + (2 * j) * (kSrcPitch / 4) + 3 + g;
+      uint32_t o[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+      {
+        const uint32_t w0 = row[r * (kSrcPitch / 4)], w1 = row[r * (kSrcPitch / 4) + 1], w2 = row[r * (kSrcPitch / 4) + 2];
+        o[r][0] = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
+        o[r][1] = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
+        o[r][2] = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
+        o[r][3] = __dp4a(w1, K0, __dp4a(w2, K1, 0u));
+      }
+      h4[i] = make_uint4(o[0][0] | (o[1][0] << 16), o[0][1] | (o[1][1] << 16), o[0][2] | (o[1][2] << 16), o[0][3] | (o[1][3] << 16));
     }
   }
   __syncthreads();
 
-  // stage C: vertical pass + rounding; one item per 4 columns x 2 output rows
+  // stage C: vertical pass + rounding; one item per 4 columns x 2 output rows (2y, 2y + 1).  Both rows read the same four
+  // row pairs y .. y + 3: the even row weighs them (18,34) (48,56) (48,34) (18,0), the odd row (0,18) (34,48) (56,48)
+  // (34,18) -- low / high byte pairs of the same weight registers (DP2A.LO / DP2A.HI).
   for (int i = tid; i < (kTileH / 2) * (kTileW / 4); i += kPyrThreads)
   {
-    const int g = i & 15, ry = (i >> 4) * 2;
-    const int gx = t.x0 + g * 4, gy = t.y0 + ry;
+    const int g = i & 15, yp = i >> 4;
+    const int gx = t.x0 + g * 4, gy = t.y0 + 2 * yp;
     if (gy < lh && gx < pitch)
     {
-      const uint2 *h2 = reinterpret_cast<const uint2 *>(s_h);
-      uint32_t c[8][4];
+      constexpr uint32_t W0 = 18u | (34u << 8) | (0u << 16) | (18u << 24), W1 = 48u | (56u << 8) | (34u << 16) | (48u << 24);
+      constexpr uint32_t W2 = 48u | (34u << 8) | (56u << 16) | (48u << 24), W3 = 18u | (0u << 8) | (34u << 16) | (18u << 24);
+      const uint4 *h4 = reinterpret_cast<const uint4 *>(s_h);
+      const uint4 p0 = h4[yp * 16 + g], p1 = h4[(yp + 1) * 16 + g], p2 = h4[(yp + 2) * 16 + g], p3 = h4[(yp + 3) * 16 + g];
+      const uint32_t c0[4] = {p0.x, p0.y, p0.z, p0.w}, c1[4] = {p1.x, p1.y, p1.z, p1.w}, c2[4] = {p2.x, p2.y, p2.z, p2.w}, c3[4] = {p3.x, p3.y, p3.z, p3.w};
+      uint32_t we = 0, wo = 0;
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int k = 0; k < 4; ++k)
       {
-        const uint2 v = h2[(ry + r) * (kTileW / 4) + g];
-        c[r][0] = v.x & 0xffffu;
-        c[r][1] = v.x >> 16;
-        c[r][2] = v.y & 0xffffu;
-        c[r][3] = v.y >> 16;
+        const uint32_t e = __dp2a_lo(c3[k], W3, __dp2a_lo(c2[k], W2, __dp2a_lo(c1[k], W1, __dp2a_lo(c0[k], W0, 32768u))));
+        const uint32_t o = __dp2a_hi(c3[k], W3, __dp2a_hi(c2[k], W2, __dp2a_hi(c1[k], W1, __dp2a_hi(c0[k], W0, 32768u))));
+        we |= (e >> 16) << (8 * k);
+        wo |= (o >> 16) << (8 * k);
       }
-#pragma unroll
-      for (int o = 0; o < 2; ++o)
-      {
-        if (gy + o >= lh) break;
-        uint32_t w = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-        {
-          const uint32_t acc = 18u * (c[o][k] + c[o + 6][k]) + 34u * (c[o + 1][k] + c[o + 5][k]) + 48u * (c[o + 2][k] + c[o + 4][k]) + 56u * c[o + 3][k];
-          w |= ((acc + 32768u) >> 16) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t *>(blr + (size_t)(gy + o) * pitch + gx) = w;
-      }
+      *reinterpret_cast<uint32_t *>(blr + (size_t)gy * pitch + gx) = we;
+      if (gy + 1 < lh) *reinterpret_cast<uint32_t *>(blr + (size_t)(gy + 1) * pitch + gx) = wo;
     }
   }
 }
