@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
   __shared__ __align__(16) uint8_t s_map[(kZoneMax + 2) * kMapPitch + 16]; // + 16: zeroed with 16-byte stores
   __shared__ uint16_t s_cand[kFastWarps * kCandSeg];
   __shared__ unsigned long long s_keep[kZoneMax];
-  __shared__ int s_warp[kFastWarps];
+  __shared__ int s_warp[kFastWarps], s_ccnt[kFastWarps];
 
   const Cell c = p.cells[blockIdx.x];
   const int img = blockIdx.y;
@@ -515,10 +515,22 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
     }
     __syncwarp();
 
+    // Stages 3 and 4 run over the block-wide corner list (the four warp segments back to back) so that the lanes stay
+    // dense even when a warp found only a handful of corners: corner k lives in segment w at k - first[w].
+    static_assert(kFastWarps == 4, "corner_at assumes four warp segments");
+    if (lane == 0) s_ccnt[wid] = ccnt;
+    __syncthreads();
+    const int f1 = s_ccnt[0], f2 = f1 + s_ccnt[1], f3 = f2 + s_ccnt[2], n_corners = f3 + s_ccnt[3];
+    auto corner_at = [&](int k) -> int {
+      const int w = (k >= f1) + (k >= f2) + (k >= f3);
+      const int first = w == 0 ? 0 : (w == 1 ? f1 : (w == 2 ? f2 : f3));
+      return s_cand[w * kCandSeg + (k - first)];
+    };
+
     // Stage 3 (true corners only): the arc value m, needed for the scores and the non-max suppression
-    for (int k = lane; k < ccnt; k += 32)
+    for (int k = tid; k < n_corners; k += kFastThreads)
     {
-      const int i = my_cand[k];
+      const int i = corner_at(k);
       const int zy = i >> 6, zx = i & (kZoneMax - 1);
       s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)fast_arc_value(pat0 + zy * kPatPitch + zx); // > t by stage 2
     }
@@ -527,9 +539,9 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
     // Non-max suppression: keep  <=>  score m - 1 > the scores of all 8 neighbours (strict), where a neighbour that is not
     // a corner at this threshold (map 0) scores 0; the map q -> (q ? q - 1 : 0) is monotone, so only the largest neighbour
     // matters.
-    for (int k = lane; k < ccnt; k += 32)
+    for (int k = tid; k < n_corners; k += kFastThreads)
     {
-      const int i = my_cand[k];
+      const int i = corner_at(k);
       const int zy = i >> 6, zx = i & (kZoneMax - 1);
       const uint8_t *mp = &s_map[(zy + 1) * kMapPitch + zx + 1];
       const int m = mp[0];
