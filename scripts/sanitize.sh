@@ -1,0 +1,30 @@
+#!/bin/bash
+# compute-sanitizer passes over a small end-to-end run (smoke-sized inputs keep the 10-50x slowdown affordable)
+set -u
+mkdir -p gpurun_out
+cat > /tmp/san_driver.py <<'PY'
+import sys; sys.path.insert(0, '.')
+import numpy as np
+from orb_slam2_ros2_b200 import api, synth
+l, r = synth.synth_stereo_pair(240, 320, 0, 9)
+ctx = api.Context(320, 240, 500, 4, 1.2, camera=api.Camera(300.0, 300.0, 160.0, 120.0, 0.1), max_batch=2)
+res = ctx.stereo_frame(l, r)
+q, qd, ex, src = synth.synth_area_queries(res.kps_left, res.desc_left, 300, 5, 320, 240, n_levels=4, th=15.0)
+m = ctx.search_in_area(q, qd, ex)
+ok = m["best_idx"] >= 0
+k2 = np.zeros(len(q), api.KP_DTYPE)
+ctx.verify_angle(m["best_idx"][ok], np.nonzero(ok)[0], m["best_dist"][ok].astype(np.float32), res.kps_left, k2)
+rec = ctx.serialize_keyframe(3)
+b = ctx.stereo_batch(np.stack([l, l]), np.stack([r, r]))
+noise = np.random.default_rng(1).integers(0, 256, (240, 320), dtype=np.uint8)
+ctx.stereo_frame(noise, noise)
+ctx.stereo_frame(np.zeros((240, 320), np.uint8), np.zeros((240, 320), np.uint8))
+g = ctx.rgbd_frame(l, synth.synth_depth_u16(240, 320, 1, 5000.0)) if False else None
+print("driver ok", res.n_matches, len(rec), int(b.n_matches.sum()))
+ctx.close()
+PY
+for tool in memcheck racecheck initcheck synccheck; do
+  echo "== $tool"
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 77 python /tmp/san_driver.py > gpurun_out/san_$tool.log 2>&1
+  echo "exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|driver ok|Error|hazard" gpurun_out/san_$tool.log | head -8
+done
