@@ -43,7 +43,7 @@ def workload_config(batch, pool):
         "pool_pairs": pool,
         "l2_policy": f"inputs larger than L2: {pool} distinct pairs ({pool * 2 * CFG['width'] * CFG['height'] / 1e6:.0f} MB) cycled, "
                      f"plus ~{batch * 2 * 2 * 1.45:.0f} MB of pyramid/blur intermediates rewritten every step",
-        "parallelism": "frames sharded by rank, no data-path collective; NCCL all-gather of left descriptors per step when N>1",
+        "parallelism": "frames sharded by rank, no data-path collective; NCCL all-gather of left descriptors per step when N>1 (asynchronous, overlapping the next step)",
     }
 
 
@@ -274,7 +274,20 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the first communicator is created; the contract is ONE JSON line there,
+        # so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     H, W, N = CFG["height"], CFG["width"], CFG["n_features"]
     B, P = args.batch, args.pool
@@ -300,12 +313,19 @@ def run_gpu_arm(args):
         res = ctx.stereo_batch_device(B, d_left.data_ptr() + c * B * fsz, d_right.data_ptr() + c * B * fsz, W, fsz)
         if world > 1:
             # left descriptors = even images of the interleaved [2B][N][32] result array
+            # (copied out on the compute stream, so the next step may overwrite the context's buffers); the gather itself runs
+            # on NCCL's stream and overlaps the next step's kernels -- barrier() below waits for the last one
             desc = torch.as_tensor(CudaArray(res.desc, (B, 2, N, 32), "|u1"), device="cuda")[:, 0]
-            dist.all_gather_into_tensor(gathered, desc.contiguous())
+            pending[0] = dist.all_gather_into_tensor(gathered, desc.contiguous(), async_op=True)
         return res
+
+    pending = [None]
 
     def barrier():
         if world > 1:
+            if pending[0] is not None:
+                pending[0].wait()  # makes the current (compute) stream wait for the gather
+                pending[0] = None
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -322,6 +342,9 @@ def run_gpu_arm(args):
     e0.record(stream)
     for i in range(args.steps):
         device_step(args.warmup + i)
+    if pending[0] is not None:
+        pending[0].wait()  # the timed region ends after the last descriptor gather
+        pending[0] = None
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
