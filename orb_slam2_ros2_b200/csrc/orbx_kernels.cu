@@ -1522,7 +1522,9 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a_u8x4, uint32_t b_s8x4, int 
   return d;
 }
 
-__global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const Params p)
+// kBriefGroup keypoints per warp: lane j < kBriefGroup evaluates atan2 / sincos of keypoint j (once, not 32 times).  Large
+// batches use 8 (throughput), a handful of images 2 (shorter warps: single-frame latency).
+template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const Params p)
 {
   // byte masks of the radius-15 disc: row |dy| covers columns |dx| <= umax[|dy|]; [|dy|][word k] selects bytes 4k..4k+3 of
   // the 32-byte row that starts at dx = -15 (byte 31 is never part of the disc)
@@ -1546,10 +1548,10 @@ __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const
 
   const int img = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * kBriefWarps + (threadIdx.x >> 5);
+  const int slot0 = (blockIdx.x * kBriefWarps + (threadIdx.x >> 5)) * kBriefGroup;
   const unsigned FULL = 0xffffffffu;
 
-  // which level does this output slot belong to? (level-major concatenation, src/ORBExtractor.cc:501-506)
+  // which level does an output slot belong to? (level-major concatenation, src/ORBExtractor.cc:501-506)
   const int *sel_cnt = p.sel_cnt + (size_t)img * p.n_levels;
   const int my = lane < p.n_levels ? sel_cnt[lane] : 0;
   int inc = my;
@@ -1560,98 +1562,118 @@ __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const
     if (lane >= o) inc += t;
   }
   const int total = __shfl_sync(FULL, inc, 31);
-  if (slot == 0 && lane == 0) p.n_kps[img] = total;
-  if (slot >= total) return;
-  const unsigned above = __ballot_sync(FULL, inc > slot); // first lane whose inclusive sum exceeds the slot
-  const int level = __ffs(above) - 1;
-  const int level_start = __shfl_sync(FULL, inc - my, level);
-  const Level &L = p.levels[level];
-  const uint32_t e = p.sel[(size_t)img * p.sel_entries + L.sel_off + (slot - level_start)];
-  const int x = (int)(e & 0xfffu), y = (int)((e >> 12) & 0xfffu), score = (int)(e >> 24);
-  const int pitch = L.pitch;
-  const uint8_t *__restrict__ lvl = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
-  const uint8_t *__restrict__ blr = p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off;
+  if (slot0 == 0 && lane == 0) p.n_kps[img] = total;
+  if (slot0 >= total) return;
+  const int n_here = min(kBriefGroup, total - slot0);
+  const uint8_t *__restrict__ pyr_img = p.pyr + (size_t)img * p.pyr_img_stride;
+  const uint8_t *__restrict__ blr_img = p.blur + (size_t)img * p.pyr_img_stride;
 
-  // getGrayCentroid (:465-487): moments over the radius-15 disc of the un-blurred level.  The disc's 31 rows are fetched
-  // as aligned words, 3 rows x 9 words per warp request (3 cache lines); a lane takes its word and the next one (from the
-  // neighbour lane), shifts them to the row start and takes both row sums with DP4A: sum(I) against the row's byte mask
-  // and sum(dx * I) against the masked signed weights dx = 4k - 15 .. 4k - 12.  Every level pitch is a multiple of 4, so
-  // the shift is the same for all rows.
-  int m10 = 0, m01 = 0;
+  // Pass 1, keypoint by keypoint: getGrayCentroid (:465-487), moments over the radius-15 disc of the un-blurred level.
+  // The disc's 31 rows are fetched as aligned words, 3 rows x 9 words per warp request (3 cache lines); a lane takes its
+  // word and the next one (from the neighbour lane), shifts them to the row start and takes both row sums with DP4A:
+  // sum(I) against the row's byte mask and sum(dx * I) against the masked signed weights dx = 4k - 15 .. 4k - 12.  Every
+  // level pitch is a multiple of 4, so the shift is the same for all rows.  Lane j keeps keypoint j's entry and moments.
+  uint32_t my_e = 0;
+  int my_level = 0, my_m10 = 0, my_m01 = 0;
+  const int rg = lane / 9, wk = lane - 9 * rg; // lanes 27..31: rg == 3, idle
+  const int kw = min(wk, 7);
+  const uint32_t wdx = ((uint32_t)((4 * kw - 15) & 0xff)) | ((uint32_t)((4 * kw - 14) & 0xff) << 8) | ((uint32_t)((4 * kw - 13) & 0xff) << 16) |
+                       ((uint32_t)((4 * kw - 12) & 0xff) << 24);
+#pragma unroll 1
+  for (int j = 0; j < n_here; ++j)
   {
-    const int rg = lane / 9, wk = lane - 9 * rg; // lanes 27..31: rg == 3, idle
-    const uint8_t *row0 = lvl + (size_t)(y - 15) * pitch + (x - 15);
+    const int slot = slot0 + j;
+    const unsigned above = __ballot_sync(FULL, inc > slot); // first lane whose inclusive sum exceeds the slot
+    const int level = __ffs(above) - 1;
+    const int level_start = __shfl_sync(FULL, inc - my, level);
+    const Level &L = p.levels[level];
+    const uint32_t e = p.sel[(size_t)img * p.sel_entries + L.sel_off + (slot - level_start)];
+    const int x = (int)(e & 0xfffu), y = (int)((e >> 12) & 0xfffu);
+    const int pitch = L.pitch;
+    const uint8_t *row0 = pyr_img + L.pyr_off + (size_t)(y - 15) * pitch + (x - 15);
     const uint32_t sh = ((uint32_t)(size_t)row0 & 3u) * 8u;
     const uint32_t *w0 = reinterpret_cast<const uint32_t *>((size_t)row0 & ~(size_t)3) + wk;
     const int pitch4 = pitch >> 2;
     uint32_t a[11];
 #pragma unroll
-    for (int j = 0; j < 11; ++j)
+    for (int i = 0; i < 11; ++i)
     {
-      const int r = 3 * j + rg;
-      a[j] = (rg < 3 && r < 31) ? w0[(size_t)r * pitch4] : 0u;
+      const int r = 3 * i + rg;
+      a[i] = (rg < 3 && r < 31) ? w0[(size_t)r * pitch4] : 0u;
     }
-    const int k = min(wk, 7);
-    const uint32_t wdx = ((uint32_t)((4 * k - 15) & 0xff)) | ((uint32_t)((4 * k - 14) & 0xff) << 8) | ((uint32_t)((4 * k - 13) & 0xff) << 16) |
-                         ((uint32_t)((4 * k - 12) & 0xff) << 24);
+    int m10 = 0, m01 = 0;
 #pragma unroll
-    for (int j = 0; j < 11; ++j)
+    for (int i = 0; i < 11; ++i)
     {
-      const int r = min(3 * j + rg, 30), dy = r - 15;
-      const uint32_t nxt = __shfl_down_sync(FULL, a[j], 1);
-      const uint32_t v = __funnelshift_r(a[j], nxt, sh);
-      const uint32_t msk = (rg < 3 && wk < 8 && 3 * j + rg < 31) ? s_disc[abs(dy)][k] : 0u;
+      const int r = min(3 * i + rg, 30), dy = r - 15;
+      const uint32_t nxt = __shfl_down_sync(FULL, a[i], 1);
+      const uint32_t v = __funnelshift_r(a[i], nxt, sh);
+      const uint32_t msk = (rg < 3 && wk < 8 && 3 * i + rg < 31) ? s_disc[abs(dy)][kw] : 0u;
       m10 = dp4a_u8_s8(v, wdx & msk, m10);
       m01 += dy * (int)__dp4a(v, msk & 0x01010101u, 0u);
     }
+    m10 = __reduce_add_sync(FULL, m10);
+    m01 = __reduce_add_sync(FULL, m01);
+    if (lane == j) my_e = e, my_level = level, my_m10 = m10, my_m01 = m01;
   }
-  m10 = __reduce_add_sync(FULL, m10);
-  m01 = __reduce_add_sync(FULL, m01);
-  const double theta = atan2((double)m01, (double)m10);
+
+  // orientation of keypoint `lane` (lanes >= n_here compute on zeros and are ignored)
+  const double theta = atan2((double)my_m01, (double)my_m10);
   double sn, cs;
   sincos(theta, &sn, &cs);
 
-  // computeBRIEF (:427-456) with rotateTemplate (:534-540): double products, float result, float add, round-half-even
-  const float fx = (float)x, fy = (float)y;
-  const uint32_t upitch = (uint32_t)pitch;
-  size_t magic_off = (size_t)0x4B400000u * ((size_t)upitch + 1u);
-  asm volatile("" : "+l"(magic_off)); // opaque: keeps the constant folded into the base instead of re-subtracted per access
-  const uint8_t *__restrict__ blr_m = blr - magic_off;
-  uint32_t byte = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
+  // Pass 2, keypoint by keypoint: computeBRIEF (:427-456) with rotateTemplate (:534-540): double products, float result,
+  // float add, round-half-even; lane <-> descriptor byte
+#pragma unroll 1
+  for (int j = 0; j < n_here; ++j)
   {
-    // bit b = lane * 8 + k lands in byte b >> 3 == lane, position b & 7 == k
-    const double2 t1 = __ldg(p.pattern_d + k * 32 + lane), t2 = __ldg(p.pattern_d + (8 + k) * 32 + lane);
-    const double x1 = t1.x, y1 = t1.y, x2 = t2.x, y2 = t2.y;
-    const float p1x = __double2float_rn(__dsub_rn(__dmul_rn(x1, cs), __dmul_rn(y1, sn)));
-    const float p1y = __double2float_rn(__dadd_rn(__dmul_rn(x1, sn), __dmul_rn(y1, cs)));
-    const float p2x = __double2float_rn(__dsub_rn(__dmul_rn(x2, cs), __dmul_rn(y2, sn)));
-    const float p2y = __double2float_rn(__dadd_rn(__dmul_rn(x2, sn), __dmul_rn(y2, cs)));
-    // cvRound without the conversion unit: float_as_uint(v + 1.5 * 2^23) == 0x4B400000 + round_half_even(v) for 0 <= v < 2^22;
-    // the constant is folded into the base pointer, the row product is one 64-bit multiply-add
-    const uint32_t r1y = __float_as_uint(__fadd_rn(__fadd_rn(fy, p1y), 12582912.f)), r1x = __float_as_uint(__fadd_rn(__fadd_rn(fx, p1x), 12582912.f));
-    const uint32_t r2y = __float_as_uint(__fadd_rn(__fadd_rn(fy, p2y), 12582912.f)), r2x = __float_as_uint(__fadd_rn(__fadd_rn(fx, p2x), 12582912.f));
-    const int v1 = blr_m[(size_t)r1y * upitch + r1x];
-    const int v2 = blr_m[(size_t)r2y * upitch + r2x];
-    byte |= (uint32_t)(v1 < v2) << k;
+    const uint32_t e = __shfl_sync(FULL, my_e, j);
+    const int level = __shfl_sync(FULL, my_level, j);
+    const double sj = __shfl_sync(FULL, sn, j), cj = __shfl_sync(FULL, cs, j);
+    const Level &L = p.levels[level];
+    const float fx = (float)(e & 0xfffu), fy = (float)((e >> 12) & 0xfffu);
+    const uint32_t upitch = (uint32_t)L.pitch;
+    size_t magic_off = (size_t)0x4B400000u * ((size_t)upitch + 1u);
+    asm volatile("" : "+l"(magic_off)); // opaque: keeps the constant folded into the base instead of re-subtracted per access
+    const uint8_t *__restrict__ blr_m = blr_img + L.pyr_off - magic_off;
+    const double2 *pat = p.pattern_d + lane;
+    asm volatile("" : "+l"(pat)); // opaque: the 32 pattern doubles are re-read (L1) per keypoint instead of pinned in 64 registers
+    uint32_t byte = 0;
+#pragma unroll 4
+    for (int k = 0; k < 8; ++k)
+    {
+      // bit b = lane * 8 + k lands in byte b >> 3 == lane, position b & 7 == k
+      const double2 t1 = __ldg(pat + k * 32), t2 = __ldg(pat + (8 + k) * 32);
+      const double x1 = t1.x, y1 = t1.y, x2 = t2.x, y2 = t2.y;
+      const float p1x = __double2float_rn(__dsub_rn(__dmul_rn(x1, cj), __dmul_rn(y1, sj)));
+      const float p1y = __double2float_rn(__dadd_rn(__dmul_rn(x1, sj), __dmul_rn(y1, cj)));
+      const float p2x = __double2float_rn(__dsub_rn(__dmul_rn(x2, cj), __dmul_rn(y2, sj)));
+      const float p2y = __double2float_rn(__dadd_rn(__dmul_rn(x2, sj), __dmul_rn(y2, cj)));
+      // cvRound without the conversion unit: float_as_uint(v + 1.5 * 2^23) == 0x4B400000 + round_half_even(v) for 0 <= v < 2^22;
+      // the constant is folded into the base pointer, the row product is one 64-bit multiply-add
+      const uint32_t r1y = __float_as_uint(__fadd_rn(__fadd_rn(fy, p1y), 12582912.f)), r1x = __float_as_uint(__fadd_rn(__fadd_rn(fx, p1x), 12582912.f));
+      const uint32_t r2y = __float_as_uint(__fadd_rn(__fadd_rn(fy, p2y), 12582912.f)), r2x = __float_as_uint(__fadd_rn(__fadd_rn(fx, p2x), 12582912.f));
+      const int v1 = blr_m[(size_t)r1y * upitch + r1x];
+      const int v2 = blr_m[(size_t)r2y * upitch + r2x];
+      byte |= (uint32_t)(v1 < v2) << k;
+    }
+    p.desc[((size_t)img * p.n_features + slot0 + j) * 32 + lane] = (uint8_t)byte;
   }
-  const size_t o = (size_t)img * p.n_features + slot;
-  p.desc[o * 32 + lane] = (uint8_t)byte;
 
-  // keypoint record (:407-409) + the row band used by the stereo search (createRowIndexDB, src/ORBMatcher.cc:915-932)
-  const float sf = L.sf;
-  const float kx = __fmul_rn(fx, sf), ky = __fmul_rn(fy, sf);
-  const float angle = __double2float_rn(__dmul_rn(__ddiv_rn(theta, 3.14159265358979323846), 180.0));
-  if (lane == 0)
+  // keypoint record (:407-409) + the row band used by the stereo search (createRowIndexDB, src/ORBMatcher.cc:915-932):
+  // lane j writes keypoint j
+  if (lane < n_here)
   {
+    const size_t o = (size_t)img * p.n_features + slot0 + lane;
+    const float sf = p.levels[my_level].sf;
+    const float kx = __fmul_rn((float)(my_e & 0xfffu), sf), ky = __fmul_rn((float)((my_e >> 12) & 0xfffu), sf);
     orbx_keypoint kpt;
     kpt.x = kx;
     kpt.y = ky;
     kpt.size = 7.f;
-    kpt.angle = angle;
-    kpt.response = (float)score;
-    kpt.octave = level;
+    kpt.angle = __double2float_rn(__dmul_rn(__ddiv_rn(theta, 3.14159265358979323846), 180.0));
+    kpt.response = (float)(my_e >> 24);
+    kpt.octave = my_level;
     kpt.class_id = -1;
     p.kps[o] = kpt;
     if (p.undistort) undistort_point(p, kx, ky, kpt.x, kpt.y); // Camera::undistortPoints (src/Camera.cc:29-39)
@@ -1668,8 +1690,16 @@ __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const
 
 void launch_orient_brief(const Params &p, int n_images, cudaStream_t s)
 {
-  dim3 grid((p.n_features + kBriefWarps - 1) / kBriefWarps, n_images);
-  orient_brief_kernel<<<grid, kBriefWarps * 32, 0, s>>>(p);
+  if (n_images > 4)
+  {
+    dim3 grid((p.n_features + kBriefWarps * 8 - 1) / (kBriefWarps * 8), n_images);
+    orient_brief_kernel<8><<<grid, kBriefWarps * 32, 0, s>>>(p);
+  }
+  else
+  {
+    dim3 grid((p.n_features + kBriefWarps * 2 - 1) / (kBriefWarps * 2), n_images);
+    orient_brief_kernel<2><<<grid, kBriefWarps * 32, 0, s>>>(p);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
