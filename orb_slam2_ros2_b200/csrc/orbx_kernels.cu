@@ -446,8 +446,8 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
       patch_ready = true;
     }
 
-    // Stage 1 (every zone pixel): at least 2 of the 4 compass ring pixels are brighter (darker) than the centre by more
-    // than t -- a necessary condition for a 9-arc.  Survivors go to a per-warp candidate segment (warp-local counter, no
+    // Stage 1 (every zone pixel): two adjacent compass ring pixels are brighter (darker) than the centre by more than t
+    // -- a necessary condition for a 9-arc.  Survivors go to a per-warp candidate segment (warp-local counter, no
     // atomics), so that the later stages run on dense lanes.
     int wcnt = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -461,12 +461,12 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
 #pragma unroll 2
       for (int zy = wid; zy < zh; zy += kFastWarps, q += kFastWarps * kPatPitch, code += kFastWarps * kZoneMax)
       {
-        const int v = q[0], hi = v + t, lo = v - t;
+        const int v = q[0];
         const int r0 = q[3 * kPatPitch], r4 = q[3], r8 = q[-3 * kPatPitch], r12 = q[-3];
-        // "at least two of the four exceed hi" <=> the second largest does; likewise the second smallest below lo
-        const int mx1 = max(r0, r4), mn1 = min(r0, r4), mx2 = max(r8, r12), mn2 = min(r8, r12);
-        const int a = min(mx1, mx2), b = max(mn1, mn2);
-        const bool cand = valid & ((max(a, b) > hi) | (min(a, b) < lo));
+        // 9 contiguous ring pixels always contain two ADJACENT compass pixels, i.e. one of {0, 8} and one of {4, 12}:
+        // brighter arc => min(max(r0, r8), max(r4, r12)) > v + t, darker arc => max(min(r0, r8), min(r4, r12)) < v - t
+        const int hi2 = min(max(r0, r8), max(r4, r12)), lo2 = max(min(r0, r8), min(r4, r12));
+        const bool cand = valid & (max(hi2 - v, v - lo2) > t);
         const unsigned m = __ballot_sync(FULL, cand);
         if (m)
         {
