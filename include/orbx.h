@@ -219,6 +219,42 @@ int orbx_serialize_keyframe(orbx_ctx *ctx, int frame, uint64_t id, const float *
 int orbx_serialize_keyframes_device(orbx_ctx *ctx, int n_frames, uint64_t id0, const float *d_pose_rt,
                                     int with_map_points, uint8_t *d_out, size_t frame_stride, int64_t *d_sizes);
 
+/* ---- bag-of-words transform ----------------------------------------------- */
+/* A DBoW3::Vocabulary (the reference loads one in src/System.cc:93) resident on the context's device.  Records follow
+ * the ORB-SLAM2 / DBoW3 text format the reference's README prescribes: record i describes node i + 1 (node 0 is the
+ * root), `parent` precedes its children, word ids are assigned to the leaf records in order.
+ * PARITY NOTE: DBoW3 is an un-vendored dependency of the reference and no vocabulary ships with it; these entry points
+ * follow DBoW3's published algorithm (oracle/orb_oracle.c restates it) -- TF_IDF / TF weighting, L1-normalising scoring. */
+typedef struct orbx_vocab orbx_vocab;
+int orbx_vocab_create(orbx_ctx *ctx, int k, int L, int n_records, const int32_t *parent, const uint8_t *is_leaf,
+                      const uint8_t *desc /* [n_records][32] */, const double *weight, orbx_vocab **out);
+/* text file: "k L scoring weighting" then one "parent isLeaf d0 .. d31 weight" line per node (ORBvoc.txt) */
+int orbx_vocab_load_text(orbx_ctx *ctx, const char *path, orbx_vocab **out);
+void orbx_vocab_destroy(orbx_vocab *vocab);
+int orbx_vocab_info(const orbx_vocab *vocab, int32_t *k, int32_t *L, int32_t *n_nodes, int32_t *n_words);
+
+/* replaces: VirtualFrame::computeBow (include/ORB_SLAM2/Frame.h:224-231) = DBoW3::Vocabulary::transform(mvLeftDescriptor,
+ * mBowVec, mFeatVec, levelsup = 4) for frame `frame` of the most recent stereo / RGB-D call.
+ * BowVector (std::map<WordId, WordValue>): bow_ids ascending with their L1-normalised weights, *n_bow entries.
+ * FeatureVector (std::map<NodeId, std::vector<unsigned>>): fv_nodes ascending, *n_fv_nodes of them; the features of node
+ * j are fv_feats[fv_start[j] .. fv_start[j + 1]) in ascending feature index.  Arrays have n_features (+1 for fv_start)
+ * entries; any array may be NULL. */
+int orbx_bow_transform(orbx_ctx *ctx, const orbx_vocab *vocab, int frame, int levelsup, int32_t *bow_ids,
+                       double *bow_vals, int32_t *n_bow, int32_t *fv_nodes, int32_t *fv_start, int32_t *fv_feats,
+                       int32_t *n_fv_nodes);
+/* device-resident results for frames 0..n_frames-1 of the most recent *_device call (asynchronous on the context's stream) */
+typedef struct orbx_device_bow {
+  const int32_t *bow_ids;   /* [n_frames][stride] */
+  const double *bow_vals;   /* [n_frames][stride] */
+  const int32_t *n_bow;     /* [n_frames] */
+  const int32_t *fv_nodes;  /* [n_frames][stride] */
+  const int32_t *fv_start;  /* [n_frames][stride + 1] */
+  const int32_t *fv_feats;  /* [n_frames][stride] */
+  const int32_t *n_fv_nodes; /* [n_frames] */
+  int32_t stride;           /* n_features */
+} orbx_device_bow;
+int orbx_bow_transform_batch_device(orbx_ctx *ctx, const orbx_vocab *vocab, int n_frames, int levelsup, orbx_device_bow *out);
+
 /* ---- introspection for benchmarks / profiles ----------------------------------------------------------- */
 #define ORBX_N_STAGES 6
 /* Same work as orbx_stereo_batch_device, with a CUDA event recorded on the stream after every kernel; blocks until

@@ -87,6 +87,8 @@ def lib():
                                             u8p, i32p, i32p, f32p, i32p]
         L.oracle_verify_angle.restype = C.c_int
         L.oracle_verify_angle.argtypes = [C.c_int, i32p, i32p, f32p, C.c_void_p, C.c_void_p]
+        L.oracle_bow_transform.restype = C.c_int
+        L.oracle_bow_transform.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, i32p, f64p, i32p, i32p, i32p, i32p]
         L.oracle_serialize_keyframe.restype = C.c_size_t
         L.oracle_serialize_keyframe.argtypes = [C.c_void_p, u8p, f64p, f64p, C.c_int, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float, f32p, C.c_int,
                                                 u8p, C.c_size_t]
@@ -367,6 +369,48 @@ def serialize_keyframe(kps, desc, u_right, depth, kf_id, bounds, pose_rt=None, w
                                         _ptr(pose, f32p), int(with_map_points), _ptr(out, u8p), out.size)
     assert m > 0
     return out[:m].tobytes()
+
+
+class _Vocab(C.Structure):
+    _fields_ = [("k", C.c_int32), ("L", C.c_int32), ("n_nodes", C.c_int32), ("child_start", i32p), ("child_ids", i32p), ("desc", u8p), ("weight", f64p),
+                ("word_id", i32p)]
+
+
+class Vocabulary:
+    """A DBoW3 tree built from ORB-SLAM2 text-format records (record i = node i + 1; ids and word ids in record order, as
+    DBoW3's text loader assigns them) for oracle_bow_transform."""
+
+    def __init__(self, k, L, parent, is_leaf, desc, weight):
+        n = len(parent) + 1
+        self.k, self.L, self.n_nodes = int(k), int(L), n
+        par = np.concatenate([[-1], np.asarray(parent, np.int64)])
+        order = np.argsort(par[1:], kind="stable") + 1  # children grouped by parent, ascending id inside a group
+        self.child_ids = np.ascontiguousarray(order, np.int32)
+        cnt = np.bincount(par[1:], minlength=n)
+        self.child_start = np.zeros(n + 1, np.int32)
+        self.child_start[1:] = np.cumsum(cnt)
+        self.desc = np.zeros((n, 32), np.uint8)
+        self.desc[1:] = desc
+        self.weight = np.zeros(n, np.float64)
+        self.weight[1:] = weight
+        self.word_id = np.full(n, -1, np.int32)
+        leaf = np.concatenate([[0], np.asarray(is_leaf)]) > 0
+        self.word_id[leaf] = np.arange(int(leaf.sum()), dtype=np.int32)
+        self._c = _Vocab(self.k, self.L, n, _ptr(self.child_start, i32p), _ptr(self.child_ids, i32p), _ptr(self.desc, u8p), _ptr(self.weight, f64p),
+                         _ptr(self.word_id, i32p))
+
+
+def bow_transform(voc: Vocabulary, desc, levelsup: int = 4):
+    """oracle_bow_transform -> dict(bow_ids, bow_vals, fv_nodes, fv_start, fv_feats)"""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n = len(desc)
+    ids, vals = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.float64)
+    fn_, fs, ff = np.zeros(n + 1, np.int32), np.zeros(n + 2, np.int32), np.zeros(n + 1, np.int32)
+    cnt = C.c_int(0)
+    m = lib().oracle_bow_transform(C.byref(voc._c), _ptr(desc, u8p), n, levelsup, _ptr(ids, i32p), _ptr(vals, f64p), _ptr(fn_, i32p), _ptr(fs, i32p),
+                                   _ptr(ff, i32p), C.byref(cnt))
+    c = cnt.value
+    return dict(bow_ids=ids[:m].copy(), bow_vals=vals[:m].copy(), fv_nodes=fn_[:c].copy(), fv_start=fs[: c + 1].copy(), fv_feats=ff[: fs[c]].copy())
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -963,3 +963,104 @@ size_t oracle_serialize_keyframe(const oracle_keypoint *kps, const uint8_t *desc
   }
   return (size_t)(o - out);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Bag-of-words transform.  PARITY UNPINNED: DBoW3 (https://github.com/rmsalinas/DBow3,
+ * un-vendored, find_package(DBoW3) in CMakeLists.txt:15, no version pin) is not under /root/reference and the reference
+ * ships no vocabulary, so this restates DBoW3's published algorithm -- Vocabulary::transform(features, BowVector&,
+ * FeatureVector&, levelsup) and the per-feature descent, BowVector::addWeight / normalize(L1), FeatureVector::addFeature
+ * -- anchored on the reference's call site include/ORB_SLAM2/Frame.h:224-231 (levelsup = 4) and on the vocabulary text
+ * format the reference's README prescribes (ORB-SLAM2's ORBvoc.txt: "k L scoring weighting", then one node per line
+ * "parent isLeaf d0..d31 weight"; node ids and word ids are assigned in line order).
+ * Supported: TF_IDF / TF weighting with a scoring that normalises L1 (ORBvoc.txt: TF_IDF, L1_NORM).
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* Descent of one descriptor: at every level the child with the smallest Hamming distance, the first one among equals
+ * (strict <, children in id order).  nid = the node reached at level L - levelsup (root if that is <= 0). */
+void oracle_bow_descend(const oracle_vocab *v, const uint8_t *desc, int levelsup, int32_t *word_id, double *weight,
+                        int32_t *nid) {
+  const int nid_level = v->L - levelsup;
+  int32_t node = 0, at = 0;
+  int level = 0;
+  do {
+    ++level;
+    const int c0 = v->child_start[node], c1 = v->child_start[node + 1];
+    double best = 1.7976931348623157e308;
+    for (int c = c0; c < c1; ++c) {
+      const int32_t id = v->child_ids[c];
+      const double d = (double)desc_distance(desc, v->desc + 32 * (size_t)id);
+      if (d < best) {
+        best = d;
+        node = id;
+      }
+    }
+    if (level == nid_level) at = node;
+  } while (v->child_start[node] != v->child_start[node + 1]);
+  *word_id = v->word_id[node];
+  *weight = v->weight[node];
+  *nid = nid_level <= 0 ? 0 : at;
+}
+
+/* Vocabulary::transform for n descriptors.  Outputs: the BowVector as (ids ascending, values) and the FeatureVector as
+ * a CSR (node ids ascending, start[m+1], feature indices in insertion order).  Returns the BowVector size. */
+int oracle_bow_transform(const oracle_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *bow_ids,
+                         double *bow_vals, int32_t *fv_nodes, int32_t *fv_start, int32_t *fv_feats, int *fv_count) {
+  int m = 0;
+  int32_t *f_node = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+  int *f_ok = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; ++i) {
+    int32_t id, nid;
+    double w;
+    oracle_bow_descend(v, desc + 32 * (size_t)i, levelsup, &id, &w, &nid);
+    f_node[i] = nid;
+    f_ok[i] = w > 0;
+    if (!(w > 0)) continue; /* stopped word */
+    /* BowVector::addWeight: std::map lower_bound, += if present, insert otherwise */
+    int lo = 0, hi = m;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (bow_ids[mid] < id) lo = mid + 1; else hi = mid;
+    }
+    if (lo < m && bow_ids[lo] == id)
+      bow_vals[lo] += w;
+    else {
+      memmove(bow_ids + lo + 1, bow_ids + lo, sizeof(int32_t) * (size_t)(m - lo));
+      memmove(bow_vals + lo + 1, bow_vals + lo, sizeof(double) * (size_t)(m - lo));
+      bow_ids[lo] = id;
+      bow_vals[lo] = w;
+      ++m;
+    }
+  }
+  /* BowVector::normalize(L1): the sum runs over the map in key order */
+  double norm = 0.0;
+  for (int k = 0; k < m; ++k) norm += fabs(bow_vals[k]);
+  if (norm > 0.0)
+    for (int k = 0; k < m; ++k) bow_vals[k] /= norm;
+  /* FeatureVector (std::map<NodeId, std::vector<unsigned>>): node ids ascending, features in insertion order */
+  int nn = 0, total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!f_ok[i]) continue;
+    int seen = 0;
+    for (int k = 0; k < nn; ++k) seen |= fv_nodes[k] == f_node[i];
+    if (!seen) fv_nodes[nn++] = f_node[i];
+  }
+  for (int a = 1; a < nn; ++a) { /* insertion sort of the distinct node ids */
+    int32_t x = fv_nodes[a];
+    int b = a - 1;
+    while (b >= 0 && fv_nodes[b] > x) {
+      fv_nodes[b + 1] = fv_nodes[b];
+      --b;
+    }
+    fv_nodes[b + 1] = x;
+  }
+  for (int k = 0; k < nn; ++k) {
+    fv_start[k] = total;
+    for (int i = 0; i < n; ++i)
+      if (f_ok[i] && f_node[i] == fv_nodes[k]) fv_feats[total++] = i;
+  }
+  fv_start[nn] = total;
+  *fv_count = nn;
+  free(f_node);
+  free(f_ok);
+  return m;
+}

@@ -131,6 +131,23 @@ size_t oracle_serialize_keyframe(const oracle_keypoint *kps, const uint8_t *desc
                                  const double *depth, int n, uint64_t id, float max_u, float max_v, float min_u,
                                  float min_v, const float *pose_rt, int with_map_points, uint8_t *out, size_t cap);
 
+/* ---- bag-of-words transform (PARITY UNPINNED, see orb_oracle.c) ---- */
+/* A DBoW3 vocabulary tree: node 0 is the root; the children of node i are child_ids[child_start[i] .. child_start[i+1])
+ * in id order; leaves carry a word id (internal nodes -1) and a weight. */
+typedef struct oracle_vocab {
+  int32_t k, L, n_nodes;
+  const int32_t *child_start; /* [n_nodes + 1] */
+  const int32_t *child_ids;   /* [n_nodes - 1] */
+  const uint8_t *desc;        /* [n_nodes][32] */
+  const double *weight;       /* [n_nodes] */
+  const int32_t *word_id;     /* [n_nodes] */
+} oracle_vocab;
+
+void oracle_bow_descend(const oracle_vocab *v, const uint8_t *desc, int levelsup, int32_t *word_id, double *weight,
+                        int32_t *nid);
+int oracle_bow_transform(const oracle_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *bow_ids,
+                         double *bow_vals, int32_t *fv_nodes, int32_t *fv_start, int32_t *fv_feats, int *fv_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,7 +74,13 @@ EXPORTS = [
     "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name", "orbx_debug_run_quadtree", "orbx_grid_info", "orbx_get_grid",
     "orbx_search_in_area", "orbx_search_in_area_batch_device", "orbx_verify_angle",
     "orbx_serialized_capacity", "orbx_serialize_keyframe", "orbx_serialize_keyframes_device",
+    "orbx_vocab_create", "orbx_vocab_load_text", "orbx_vocab_destroy", "orbx_vocab_info", "orbx_bow_transform", "orbx_bow_transform_batch_device",
 ]
+
+class OrbxDeviceBow(C.Structure):
+    _fields_ = [("bow_ids", C.c_void_p), ("bow_vals", C.c_void_p), ("n_bow", C.c_void_p), ("fv_nodes", C.c_void_p), ("fv_start", C.c_void_p),
+                ("fv_feats", C.c_void_p), ("n_fv_nodes", C.c_void_p), ("stride", C.c_int32)]
+
 
 _lib = None
 
@@ -134,6 +140,13 @@ def load_library(build_if_missing: bool = True):
     L.orbx_serialized_capacity.restype = C.c_int64
     L.orbx_serialize_keyframe.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, vp, sz, C.POINTER(C.c_int64)]
     L.orbx_serialize_keyframes_device.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, vp, sz, vp]
+    L.orbx_vocab_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(vp)]
+    L.orbx_vocab_load_text.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.orbx_vocab_destroy.argtypes = [vp]
+    L.orbx_vocab_destroy.restype = None
+    L.orbx_vocab_info.argtypes = [vp] + [C.POINTER(C.c_int32)] * 4
+    L.orbx_bow_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int32), vp, vp, vp, C.POINTER(C.c_int32)]
+    L.orbx_bow_transform_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(OrbxDeviceBow)]
     _lib = L
     return L
 
@@ -396,6 +409,25 @@ class Context:
                                                      C.c_void_p(d_sizes))
         _check(self._h, rc, "orbx_serialize_keyframes_device")
 
+    # ---- bag-of-words transform ---------------------------------------------------------
+    def bow_transform(self, vocab: "Vocabulary", frame: int = 0, levelsup: int = 4) -> dict:
+        """VirtualFrame::computeBow (include/ORB_SLAM2/Frame.h:224-231) = DBoW3 Vocabulary::transform(descriptors, BowVector,
+        FeatureVector, levelsup) -> dict(bow_ids, bow_vals, fv_nodes, fv_start, fv_feats)"""
+        N = self.n_features
+        ids, vals = np.zeros(N, np.int32), np.zeros(N, np.float64)
+        fn, fs, ff = np.zeros(N, np.int32), np.zeros(N + 1, np.int32), np.zeros(N, np.int32)
+        nb, nf = C.c_int32(0), C.c_int32(0)
+        rc = self._L.orbx_bow_transform(self._h, vocab._h, frame, levelsup, ids.ctypes.data, vals.ctypes.data, C.byref(nb), fn.ctypes.data, fs.ctypes.data,
+                                        ff.ctypes.data, C.byref(nf))
+        _check(self._h, rc, "orbx_bow_transform")
+        m, k = nb.value, nf.value
+        return dict(bow_ids=ids[:m], bow_vals=vals[:m], fv_nodes=fn[:k], fv_start=fs[: k + 1], fv_feats=ff[: fs[k]])
+
+    def bow_transform_batch_device(self, vocab: "Vocabulary", n_frames: int, levelsup: int = 4) -> OrbxDeviceBow:
+        res = OrbxDeviceBow()
+        _check(self._h, self._L.orbx_bow_transform_batch_device(self._h, vocab._h, n_frames, levelsup, C.byref(res)), "orbx_bow_transform_batch_device")
+        return res
+
     # ---- batches ----------------------------------------------------------------------------------------------------
     def stereo_batch(self, left: np.ndarray, right: np.ndarray, out: "StereoBatchBuffers | None" = None):
         """left/right: (n, H, W) uint8 host arrays (pinned memory makes the copies asynchronous)."""
@@ -639,3 +671,44 @@ class ORBMatcher:
         """ORBMatcher::verifyAngle (src/ORBMatcher.cc:1013-1051) on (m, 3) rows (queryIdx, trainIdx, distance)"""
         qi, ti, di = ctx.verify_angle(matches[:, 0], matches[:, 1], matches[:, 2].astype(np.float32), keyPoints1, keyPoints2)
         return np.stack([qi, ti, di.astype(np.int32)], axis=1).astype(np.int32).reshape(-1, 3)
+
+
+class Vocabulary:
+    """DBoW3::Vocabulary resident on a context's device (the reference loads it in src/System.cc:93)."""
+
+    def __init__(self, ctx: Context, k: int, L: int, parent, is_leaf, desc, weight):
+        parent = np.ascontiguousarray(parent, np.int32)
+        is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        weight = np.ascontiguousarray(weight, np.float64)
+        assert desc.shape == (len(parent), 32) and len(is_leaf) == len(parent) == len(weight)
+        self._L = ctx._L
+        self._h = C.c_void_p()
+        rc = self._L.orbx_vocab_create(ctx._h, k, L, len(parent), parent.ctypes.data, is_leaf.ctypes.data, desc.ctypes.data, weight.ctypes.data,
+                                       C.byref(self._h))
+        _check(ctx._h, rc, "orbx_vocab_create")
+
+    @classmethod
+    def load_text(cls, ctx: Context, path: str) -> "Vocabulary":
+        """ORB-SLAM2 / DBoW3 text vocabulary (ORBvoc.txt)"""
+        self = cls.__new__(cls)
+        self._L = ctx._L
+        self._h = C.c_void_p()
+        _check(ctx._h, self._L.orbx_vocab_load_text(ctx._h, path.encode(), C.byref(self._h)), "orbx_vocab_load_text")
+        return self
+
+    def info(self):
+        v = [C.c_int32() for _ in range(4)]
+        self._L.orbx_vocab_info(self._h, *[C.byref(x) for x in v])
+        return dict(k=v[0].value, L=v[1].value, n_nodes=v[2].value, n_words=v[3].value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.orbx_vocab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -53,6 +53,19 @@ struct orbx_ctx
   // staging for the host-side matcher calls (orbx_search_in_area / orbx_verify_angle), grown on demand
   uint8_t *match_scratch = nullptr;
   size_t match_scratch_bytes = 0;
+  // bag-of-words transform: per-feature and per-frame result buffers, allocated on first use
+  BowArgs bow{};
+  bool bow_ready = false;
+};
+
+// DBoW3 vocabulary tree resident on one device
+struct orbx_vocab
+{
+  int device = 0;
+  int k = 0, L = 0, n_nodes = 0, n_words = 0;
+  int *child_start = nullptr, *child_ids = nullptr, *word = nullptr;
+  uint8_t *desc = nullptr;
+  double *weight = nullptr;
 };
 
 namespace
@@ -1212,6 +1225,185 @@ extern "C"
     *n_bytes = sz;
     if ((size_t)sz > cap) return fail(c, ORBX_ERR_CAPACITY, "output buffer too small for the record (see *n_bytes)");
     ORBX_CUDA(c, cudaMemcpy(out, base, (size_t)sz, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------------
+  // bag-of-words transform
+  void orbx_vocab_destroy(orbx_vocab *v)
+  {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaFree(v->child_start);
+    cudaFree(v->child_ids);
+    cudaFree(v->word);
+    cudaFree(v->desc);
+    cudaFree(v->weight);
+    delete v;
+  }
+
+  int orbx_vocab_create(orbx_ctx *c, int k, int L, int n_records, const int32_t *parent, const uint8_t *is_leaf, const uint8_t *desc, const double *weight,
+                        orbx_vocab **out)
+  {
+    if (!c || !out || k < 1 || L < 1 || n_records < 1 || !parent || !is_leaf || !desc || !weight) return ORBX_ERR_INVALID_ARG;
+    *out = nullptr;
+    const int n = n_records + 1;
+    // record i describes node i + 1 (ids in record order, as DBoW3's text loader assigns them); children keep record order
+    std::vector<int> cnt((size_t)n + 1, 0), start((size_t)n + 1, 0), ids((size_t)n_records), word((size_t)n, -1);
+    for (int i = 0; i < n_records; ++i)
+    {
+      if (parent[i] < 0 || parent[i] > i) return fail(c, ORBX_ERR_INVALID_ARG, "vocabulary record refers to a parent that does not precede it");
+      ++cnt[(size_t)parent[i]];
+    }
+    for (int i = 0; i < n; ++i) start[(size_t)i + 1] = start[(size_t)i] + cnt[(size_t)i];
+    std::vector<int> cur(start.begin(), start.end() - 1);
+    for (int i = 0; i < n_records; ++i) ids[(size_t)cur[(size_t)parent[i]]++] = i + 1;
+    int n_words = 0;
+    for (int i = 0; i < n_records; ++i)
+    {
+      const bool has_children = cnt[(size_t)i + 1] > 0;
+      if ((is_leaf[i] != 0) == has_children) return fail(c, ORBX_ERR_INVALID_ARG, "vocabulary leaf flags do not match the tree structure");
+      if (is_leaf[i]) word[(size_t)i + 1] = n_words++;
+    }
+    std::vector<uint8_t> d((size_t)n * 32, 0);
+    std::memcpy(d.data() + 32, desc, (size_t)n_records * 32);
+    std::vector<double> w((size_t)n, 0.0);
+    std::memcpy(w.data() + 1, weight, (size_t)n_records * sizeof(double));
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    orbx_vocab *v = new orbx_vocab();
+    v->device = c->device, v->k = k, v->L = L, v->n_nodes = n, v->n_words = n_words;
+    auto up = [&](auto **dst, const auto &src) -> cudaError_t {
+      cudaError_t e = cudaMalloc((void **)dst, src.size() * sizeof(src[0]) + 64);
+      if (e != cudaSuccess) return e;
+      return cudaMemcpy(*dst, src.data(), src.size() * sizeof(src[0]), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = up(&v->child_start, start);
+    if (e == cudaSuccess) e = up(&v->child_ids, ids);
+    if (e == cudaSuccess) e = up(&v->word, word);
+    if (e == cudaSuccess) e = up(&v->desc, d);
+    if (e == cudaSuccess) e = up(&v->weight, w);
+    if (e != cudaSuccess)
+    {
+      orbx_vocab_destroy(v);
+      return fail(c, ORBX_ERR_CUDA, std::string("vocabulary upload: ") + cudaGetErrorString(e));
+    }
+    *out = v;
+    return ORBX_OK;
+  }
+
+  int orbx_vocab_load_text(orbx_ctx *c, const char *path, orbx_vocab **out)
+  {
+    if (!c || !path || !out) return ORBX_ERR_INVALID_ARG;
+    *out = nullptr;
+    std::ifstream f(path);
+    if (!f.is_open()) return fail(c, ORBX_ERR_FILE_NOT_OPEN, std::string("cannot open vocabulary ") + path);
+    int k = 0, L = 0, scoring = 0, weighting = 0;
+    {
+      std::string line;
+      std::getline(f, line);
+      std::stringstream ss(line);
+      if (!(ss >> k >> L >> scoring >> weighting)) return fail(c, ORBX_ERR_INVALID_ARG, "vocabulary header is not 'k L scoring weighting'");
+    }
+    // DBoW3: WeightingType { TF_IDF, TF, IDF, BINARY }, ScoringType { L1_NORM, L2_NORM, CHI_SQUARE, KL, BHATTACHARYYA, DOT_PRODUCT };
+    // supported here: term-frequency weightings with a scoring whose mustNormalize() asks for the L1 norm
+    if (weighting < 0 || weighting > 1 || !(scoring == 0 || scoring == 2 || scoring == 3 || scoring == 4))
+      return fail(c, ORBX_ERR_INVALID_ARG, "only TF_IDF / TF weighting with an L1-normalising scoring is supported");
+    std::vector<int32_t> parent;
+    std::vector<uint8_t> leaf, desc;
+    std::vector<double> weight;
+    std::string line;
+    while (std::getline(f, line))
+    {
+      if (line.find_first_not_of(" \t\r") == std::string::npos) continue;
+      std::stringstream ss(line);
+      int pid = 0, is_leaf = 0;
+      if (!(ss >> pid >> is_leaf)) return fail(c, ORBX_ERR_INVALID_ARG, "malformed vocabulary record");
+      for (int b = 0; b < 32; ++b)
+      {
+        int x = 0;
+        if (!(ss >> x)) return fail(c, ORBX_ERR_INVALID_ARG, "malformed vocabulary record (descriptor)");
+        desc.push_back((uint8_t)x);
+      }
+      double w = 0;
+      if (!(ss >> w)) return fail(c, ORBX_ERR_INVALID_ARG, "malformed vocabulary record (weight)");
+      parent.push_back(pid);
+      leaf.push_back(is_leaf > 0);
+      weight.push_back(w);
+    }
+    if (parent.empty()) return fail(c, ORBX_ERR_INVALID_ARG, "vocabulary holds no nodes");
+    return orbx_vocab_create(c, k, L, (int)parent.size(), parent.data(), leaf.data(), desc.data(), weight.data(), out);
+  }
+
+  int orbx_vocab_info(const orbx_vocab *v, int32_t *k, int32_t *L, int32_t *n_nodes, int32_t *n_words)
+  {
+    if (!v) return ORBX_ERR_INVALID_ARG;
+    if (k) *k = v->k;
+    if (L) *L = v->L;
+    if (n_nodes) *n_nodes = v->n_nodes;
+    if (n_words) *n_words = v->n_words;
+    return ORBX_OK;
+  }
+
+  static int bow_buffers(orbx_ctx *c)
+  {
+    if (c->bow_ready) return ORBX_OK;
+    const size_t F = (size_t)c->cfg.max_batch, N = (size_t)c->cfg.n_features;
+    if (N > 65535) return fail(c, ORBX_ERR_CAPACITY, "the bag-of-words kernels index features with 16 bits");
+    int rc;
+    BowArgs &b = c->bow;
+    if ((rc = dev_alloc(c, &b.f_word, F * N))) return rc;
+    if ((rc = dev_alloc(c, &b.f_nid, F * N))) return rc;
+    if ((rc = dev_alloc(c, &b.f_weight, F * N))) return rc;
+    if ((rc = dev_alloc(c, &b.bow_ids, F * N))) return rc;
+    if ((rc = dev_alloc(c, &b.bow_vals, F * N))) return rc;
+    if ((rc = dev_alloc(c, &b.n_bow, F))) return rc;
+    if ((rc = dev_alloc(c, &b.fv_nodes, F * N))) return rc;
+    if ((rc = dev_alloc(c, &b.fv_start, F * (N + 1)))) return rc;
+    if ((rc = dev_alloc(c, &b.fv_feats, F * N))) return rc;
+    if ((rc = dev_alloc(c, &b.n_fv, F))) return rc;
+    if (bow_configure((int)N) != 0) return fail(c, ORBX_ERR_CUDA, "cannot reserve shared memory for the bag-of-words sort");
+    c->bow_ready = true;
+    return ORBX_OK;
+  }
+
+  int orbx_bow_transform_batch_device(orbx_ctx *c, const orbx_vocab *v, int n_frames, int levelsup, orbx_device_bow *out)
+  {
+    if (!c || !v || n_frames < 1 || !out) return ORBX_ERR_INVALID_ARG;
+    if (v->device != c->device) return fail(c, ORBX_ERR_INVALID_ARG, "vocabulary lives on another device");
+    if (n_frames > c->last_frames) return fail(c, ORBX_ERR_STATE, "more frames than the last stereo / RGB-D call processed");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    int rc = bow_buffers(c);
+    if (rc) return rc;
+    BowArgs a = c->bow;
+    a.child_start = v->child_start, a.child_ids = v->child_ids, a.v_desc = v->desc, a.v_weight = v->weight, a.v_word = v->word;
+    a.L = v->L, a.levelsup = levelsup, a.image_stride = c->last_stereo ? 2 : 1;
+    launch_bow_descend(c->p, a, n_frames, c->stream);
+    launch_bow_assemble(c->p, a, n_frames, c->stream);
+    c->launches += 2;
+    ORBX_CUDA(c, cudaGetLastError());
+    out->bow_ids = a.bow_ids, out->bow_vals = a.bow_vals, out->n_bow = a.n_bow;
+    out->fv_nodes = a.fv_nodes, out->fv_start = a.fv_start, out->fv_feats = a.fv_feats, out->n_fv_nodes = a.n_fv;
+    out->stride = c->cfg.n_features;
+    return ORBX_OK;
+  }
+
+  int orbx_bow_transform(orbx_ctx *c, const orbx_vocab *v, int frame, int levelsup, int32_t *bow_ids, double *bow_vals, int32_t *n_bow, int32_t *fv_nodes,
+                         int32_t *fv_start, int32_t *fv_feats, int32_t *n_fv_nodes)
+  {
+    if (!c || !v || frame < 0 || !n_bow || !n_fv_nodes) return ORBX_ERR_INVALID_ARG;
+    if (frame >= c->last_frames) return fail(c, ORBX_ERR_STATE, "no frame with that index has been processed by a stereo / RGB-D call");
+    orbx_device_bow d{};
+    const int rc = orbx_bow_transform_batch_device(c, v, frame + 1, levelsup, &d); // frames 0..frame (single-frame calls: frame == 0)
+    if (rc) return rc;
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t N = (size_t)c->cfg.n_features, f = (size_t)frame;
+    ORBX_CUDA(c, cudaMemcpy(n_bow, d.n_bow + f, 4, cudaMemcpyDeviceToHost));
+    ORBX_CUDA(c, cudaMemcpy(n_fv_nodes, d.n_fv_nodes + f, 4, cudaMemcpyDeviceToHost));
+    if (bow_ids) ORBX_CUDA(c, cudaMemcpy(bow_ids, d.bow_ids + f * N, (size_t)*n_bow * 4, cudaMemcpyDeviceToHost));
+    if (bow_vals) ORBX_CUDA(c, cudaMemcpy(bow_vals, d.bow_vals + f * N, (size_t)*n_bow * 8, cudaMemcpyDeviceToHost));
+    if (fv_nodes) ORBX_CUDA(c, cudaMemcpy(fv_nodes, d.fv_nodes + f * N, (size_t)*n_fv_nodes * 4, cudaMemcpyDeviceToHost));
+    if (fv_start) ORBX_CUDA(c, cudaMemcpy(fv_start, d.fv_start + f * (N + 1), ((size_t)*n_fv_nodes + 1) * 4, cudaMemcpyDeviceToHost));
+    if (fv_feats) ORBX_CUDA(c, cudaMemcpy(fv_feats, d.fv_feats + f * N, N * 4, cudaMemcpyDeviceToHost));
     return ORBX_OK;
   }
 

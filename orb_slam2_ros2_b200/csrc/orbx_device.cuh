@@ -177,7 +177,25 @@ struct SerArgs
   float max_u, max_v, min_u, min_v;
 };
 
-// launchers (orbx_kernels.cu / orbx_match.cu / orbx_serialize.cu); every call enqueues exactly one kernel on `s`
+// bag-of-words transform (orbx_bow.cu)
+struct BowArgs
+{
+  // vocabulary tree: node 0 = root; children of node i = child_ids[child_start[i] .. child_start[i + 1]) in id order
+  const int *child_start, *child_ids;
+  const uint8_t *v_desc;  // [n_nodes][32]
+  const double *v_weight; // [n_nodes]
+  const int *v_word;      // [n_nodes] word id of a leaf
+  int L, levelsup, image_stride;
+  // per feature: [frame][n_features]
+  int *f_word, *f_nid;
+  double *f_weight;
+  // per frame results: BowVector [frame][n_features] + count, FeatureVector CSR
+  int *bow_ids, *n_bow;
+  double *bow_vals;
+  int *fv_nodes, *fv_start /* [frame][n_features + 1] */, *fv_feats, *n_fv;
+};
+
+// launchers (orbx_kernels.cu / orbx_match.cu / orbx_serialize.cu / orbx_bow.cu); every call enqueues exactly one kernel on `s`
 void launch_pyramid(const Params &p, int n_images, cudaStream_t s);
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
@@ -189,6 +207,9 @@ void launch_grid(const Params &p, int n_frames, int image_stride, cudaStream_t s
 void launch_area_match(const Params &p, const AreaArgs &a, int n_frames, cudaStream_t s);
 void launch_verify_angle(const VerifyArgs &a, cudaStream_t s);
 void launch_serialize(const Params &p, const SerArgs &a, int n_frames, cudaStream_t s);
+void launch_bow_descend(const Params &p, const BowArgs &a, int n_frames, cudaStream_t s);
+void launch_bow_assemble(const Params &p, const BowArgs &a, int n_frames, cudaStream_t s);
+int bow_configure(int n_features); // opt in to the dynamic shared memory of the assemble kernel
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells);
 int quadtree_configure(size_t smem_bytes); // opt in to large dynamic shared memory
 

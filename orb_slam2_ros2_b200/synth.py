@@ -117,3 +117,48 @@ def synth_area_queries(kps: np.ndarray, desc: np.ndarray, n: int, seed: int, wid
         qd[np.arange(n), bits[:, k] // 8] ^= (1 << (bits[:, k] % 8)).astype(np.uint8)
     exclude = (rng.random(m) < 0.3).astype(np.uint8)
     return q, qd, exclude, src
+
+
+def synth_vocabulary(k: int, L: int, seed: int, early_leaf: float = 0.03, stop_fraction: float = 0.02, flip_bits: int = 24):
+    """A DBoW3-shaped vocabulary tree in the node order of ORB-SLAM2's text format (one record per non-root node, parents
+    before children, the k children of a node consecutive): -> dict(k, L, parent[int32 n], is_leaf[uint8 n], desc[uint8 n,32],
+    weight[float64 n]) where record i describes node i + 1.  Children are their parent's descriptor with `flip_bits`
+    random bits flipped (so that descriptors near a leaf descend to it), a few nodes stop early (k-means ran out of
+    points), leaf weights are idf-like positive doubles and a fraction is exactly 0 (stopped words)."""
+    rng = np.random.default_rng(seed)
+    parents, leaves, descs = [], [], []
+    level_ids = np.array([0], np.int64)
+    level_desc = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    next_id = 1
+    for depth in range(1, L + 1):
+        n_par = len(level_ids)
+        par = np.repeat(level_ids, k)
+        d = np.repeat(level_desc, k, axis=0)
+        bits = rng.integers(0, 256, (n_par * k, flip_bits))
+        for b in range(flip_bits):
+            d[np.arange(n_par * k), bits[:, b] // 8] ^= (1 << (bits[:, b] % 8)).astype(np.uint8)
+        leaf = np.ones(n_par * k, np.uint8) if depth == L else (rng.random(n_par * k) < early_leaf).astype(np.uint8)
+        ids = next_id + np.arange(n_par * k, dtype=np.int64)
+        next_id += n_par * k
+        parents.append(par)
+        leaves.append(leaf)
+        descs.append(d)
+        keep = leaf == 0
+        level_ids, level_desc = ids[keep], d[keep]
+    parent = np.concatenate(parents).astype(np.int32)
+    is_leaf = np.concatenate(leaves)
+    desc = np.concatenate(descs)
+    n = len(parent)
+    weight = np.where(is_leaf > 0, np.log(1.0 + 50.0 * rng.random(n)) + 0.01, 0.0)
+    weight[(is_leaf > 0) & (rng.random(n) < stop_fraction)] = 0.0
+    return dict(k=k, L=L, parent=parent, is_leaf=is_leaf, desc=desc, weight=weight.astype(np.float64))
+
+
+def write_vocabulary_text(path: str, voc: dict, scoring: int = 0, weighting: int = 0) -> str:
+    """ORB-SLAM2 / DBoW3 text vocabulary: 'k L scoring weighting', then 'parent isLeaf d0 .. d31 weight' per node
+    (scoring 0 = L1_NORM, weighting 0 = TF_IDF)."""
+    with open(path, "w") as f:
+        f.write(f"{voc['k']} {voc['L']} {scoring} {weighting}\n")
+        for p, l, d, w in zip(voc["parent"], voc["is_leaf"], voc["desc"], voc["weight"]):
+            f.write(f"{int(p)} {int(l)} " + " ".join(str(int(x)) for x in d) + f" {float(w)!r}\n")
+    return path

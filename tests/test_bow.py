@@ -1,0 +1,152 @@
+"""Bag-of-words transform: DBoW3 Vocabulary::transform as the reference calls it
+(include/ORB_SLAM2/Frame.h:224-231, levelsup = 4).
+
+PARITY UNPINNED: DBoW3 is un-vendored and the reference ships no vocabulary.  CPU: the plain-C restatement of DBoW3's
+published algorithm equals an independent, literal python restatement (dict = std::map) on synthetic vocabularies.
+GPU: the CUDA kernels equal the oracle bit for bit (ids, double weights, feature lists)."""
+import numpy as np
+import pytest
+
+from orb_slam2_ros2_b200 import api, synth
+
+
+def _features(V, n, seed, flip=8):
+    """descriptors near random leaves of the tree (so the descent is meaningful), plus a few random ones"""
+    rng = np.random.default_rng(seed)
+    leaves = np.nonzero(V.word_id >= 0)[0]
+    d = V.desc[rng.choice(leaves, n)].copy()
+    bits = rng.integers(0, 256, (n, flip))
+    for b in range(flip):
+        d[np.arange(n), bits[:, b] // 8] ^= (1 << (bits[:, b] % 8)).astype(np.uint8)
+    d[:: 17] = rng.integers(0, 256, (len(d[::17]), 32), dtype=np.uint8)
+    return d
+
+
+def _py_transform(V, desc, levelsup):
+    """literal DBoW3: per-feature descent (first minimum), BowVector::addWeight, normalize(L1), FeatureVector::addFeature"""
+    bow, fv = {}, {}
+    nid_level = V.L - levelsup
+    for i, f in enumerate(desc):
+        node, level, at = 0, 0, 0
+        while True:
+            level += 1
+            ch = V.child_ids[V.child_start[node] : V.child_start[node + 1]]
+            dist = np.unpackbits(V.desc[ch] ^ f, axis=1).sum(1)
+            node = int(ch[int(np.argmin(dist))])  # argmin returns the first minimum
+            if level == nid_level:
+                at = node
+            if V.child_start[node] == V.child_start[node + 1]:
+                break
+        w = float(V.weight[node])
+        if w > 0:
+            wid = int(V.word_id[node])
+            bow[wid] = bow[wid] + w if wid in bow else w
+            fv.setdefault(0 if nid_level <= 0 else at, []).append(i)
+    ids = sorted(bow)
+    vals = np.array([bow[k] for k in ids], np.float64)
+    norm = 0.0
+    for x in vals:
+        norm += abs(x)
+    if norm > 0:
+        vals = vals / norm
+    return ids, vals, fv
+
+
+VOCS = [(10, 3, 1), (6, 4, 2), (3, 6, 3), (40, 2, 4)]
+
+
+@pytest.mark.parametrize("kLs", VOCS, ids=[f"k{k}L{L}" for k, L, _ in VOCS])
+def test_oracle_equals_literal_restatement(oracle, kLs):
+    k, L, seed = kLs
+    V = oracle.Vocabulary(**synth.synth_vocabulary(k, L, seed))
+    assert (V.weight[V.word_id >= 0] == 0).any()  # stopped words present
+    d = _features(V, 400, seed)
+    for levelsup in (4, 2, 0, L, L + 3):
+        r = oracle.bow_transform(V, d, levelsup)
+        ids, vals, fv = _py_transform(V, d, levelsup)
+        assert ids == list(r["bow_ids"]) and np.array_equal(vals, r["bow_vals"])
+        assert sorted(fv) == list(r["fv_nodes"])
+        for j, node in enumerate(sorted(fv)):
+            assert fv[node] == list(r["fv_feats"][r["fv_start"][j] : r["fv_start"][j + 1]])
+        assert abs(r["bow_vals"].sum() - 1.0) < 1e-12
+    r = oracle.bow_transform(V, d[:0], 4)
+    assert len(r["bow_ids"]) == 0 and len(r["fv_nodes"]) == 0
+
+
+def _same(got, exp, what):
+    for key in ("bow_ids", "bow_vals", "fv_nodes", "fv_start", "fv_feats"):
+        assert np.array_equal(got[key], exp[key]), f"{what}: {key}"
+
+
+@pytest.mark.gpu
+def test_cuda_bow_equals_oracle(oracle, tmp_path):
+    c = synth.KITTI
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], 6, 17)
+    ctx = api.Context(c["width"], c["height"], 2000, 8, 1.2, camera=api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"]))
+    r = ctx.stereo_frame(left, right)
+    for k, L, seed in VOCS:
+        voc = synth.synth_vocabulary(k, L, seed)
+        # make the frame's descriptors meaningful for this tree: half of the leaves' descriptors become frame descriptors
+        O = oracle.Vocabulary(**voc)
+        leaves = np.nonzero(O.word_id >= 0)[0]
+        rng = np.random.default_rng(seed)
+        take = rng.choice(len(r.desc_left), min(len(leaves), 1200), replace=False)
+        voc["desc"][leaves[: len(take)] - 1] = r.desc_left[take]
+        O = oracle.Vocabulary(**voc)
+        V = api.Vocabulary(ctx, **voc)
+        assert V.info() == dict(k=k, L=L, n_nodes=O.n_nodes, n_words=int((O.word_id >= 0).sum()))
+        for levelsup in (4, 2, 0, L + 1):
+            _same(ctx.bow_transform(V, levelsup=levelsup), oracle.bow_transform(O, r.desc_left, levelsup), f"k{k} L{L} up{levelsup}")
+        got = ctx.bow_transform(V)
+        assert len(got["bow_ids"]) > 100 and abs(got["bow_vals"].sum() - 1.0) < 1e-12
+        # the text format round trip (DBoW3 / ORB-SLAM2 ORBvoc.txt layout)
+        if O.n_nodes < 3000:
+            path = synth.write_vocabulary_text(str(tmp_path / f"voc_{k}_{L}.txt"), voc)
+            V2 = api.Vocabulary.load_text(ctx, path)
+            assert V2.info() == V.info()
+            _same(ctx.bow_transform(V2), got, "text loader")
+            V2.close()
+        V.close()
+    with pytest.raises(api.FileNotOpenError):
+        api.Vocabulary.load_text(ctx, str(tmp_path / "missing.txt"))
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_bow_batch_device_rgbd_and_empty(oracle):
+    import torch
+
+    c = synth.KITTI
+    n = 3
+    lefts, rights = synth.synth_stereo_pool(c["height"], c["width"], n, seed0=120)
+    ctx = api.Context(c["width"], c["height"], 2000, 8, 1.2, camera=api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"]), max_batch=n)
+    host = ctx.stereo_batch(lefts, rights)
+    voc = synth.synth_vocabulary(10, 4, 9)
+    O, V = oracle.Vocabulary(**voc), api.Vocabulary(ctx, **voc)
+    dl, dr = torch.from_numpy(lefts).cuda(), torch.from_numpy(rights).cuda()
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.stereo_batch_device(n, dl.data_ptr(), dr.data_ptr(), c["width"], c["width"] * c["height"])
+    before = ctx.launch_count
+    d = ctx.bow_transform_batch_device(V, n, 4)
+    assert ctx.launch_count - before == 2
+    N = d.stride
+    nb = ctx.read_device(d.n_bow, (n,), np.int32)
+    nf = ctx.read_device(d.n_fv_nodes, (n,), np.int32)
+    ids = ctx.read_device(d.bow_ids, (n, N), np.int32)
+    vals = ctx.read_device(d.bow_vals, (n, N), np.float64)
+    fnodes = ctx.read_device(d.fv_nodes, (n, N), np.int32)
+    fstart = ctx.read_device(d.fv_start, (n, N + 1), np.int32)
+    ffeats = ctx.read_device(d.fv_feats, (n, N), np.int32)
+    for f in range(n):
+        e = oracle.bow_transform(O, host.desc_left[f][: host.n_left[f]], 4)
+        got = dict(bow_ids=ids[f, : nb[f]], bow_vals=vals[f, : nb[f]], fv_nodes=fnodes[f, : nf[f]], fv_start=fstart[f, : nf[f] + 1],
+                   fv_feats=ffeats[f, : fstart[f, nf[f]]])
+        _same(got, e, f"frame {f}")
+    ctx.set_stream(None)
+    # a frame without keypoints: empty vectors
+    ctx.stereo_frame(np.full((c["height"], c["width"]), 80, np.uint8), np.full((c["height"], c["width"]), 80, np.uint8))
+    got = ctx.bow_transform(V)
+    assert len(got["bow_ids"]) == 0 and len(got["fv_nodes"]) == 0 and len(got["fv_feats"]) == 0
+    V.close()
+    ctx.close()
