@@ -238,9 +238,38 @@ def bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cp
                         "kernel": "serialize", "kernel_ms": ser_ms, "bytes_per_record": ser_bytes / B,
                         "roofline": {"bound": "hbm", "achieved": (ser_bytes + B * N * (28 + 32 + 16)) / (ser_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": (ser_bytes + B * N * (28 + 32 + 16)) / (ser_ms * 1e-3) / 1e9 / peak}}
+    # bag-of-words transform with a synthetic vocabulary of ORBvoc.txt's shape (k = 10, L = 6, ~1 M nodes)
+    voc = synth.synth_vocabulary(10, 6, 0)
+    V = api.Vocabulary(ctx, **voc)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            ctx.bow_transform_batch_device(V, B, 4)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream.synchronize()
+        b0.record(stream)
+        for _ in range(reps):
+            dbow = ctx.bow_transform_batch_device(V, B, 4)
+        b1.record(stream)
+        stream.synchronize()
+    bow_ms = b0.elapsed_time(b1) / reps
+    n_words = ctx.read_device(dbow.n_bow, (B,), np.int32)
+    vi = V.info()
+    # per descriptor: its 32 bytes + L levels x k children x 32-byte node descriptors; per frame: 16 B per BowVector entry + 8 B per feature
+    bow_alg = B * N * (32 + 6 * 10 * 32) + int(n_words.sum()) * 12 + B * N * 8
+    out["bow"] = {"metric": "frames/s of DBoW3 transform (k=10, L=6 synthetic vocabulary, %d descriptors per frame, levelsup 4)" % N,
+                  "value": B / (bow_ms * 1e-3), "unit": "frames/s", "kernels": ["bow_descend", "bow_assemble"], "ms_per_launch_pair": bow_ms,
+                  "frames_per_launch": B, "vocabulary_nodes": vi["n_nodes"], "mean_words_per_frame": float(n_words.mean()),
+                  "roofline": {"bound": "hbm", "achieved": bow_alg / (bow_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": bow_alg / (bow_ms * 1e-3) / 1e9 / peak}, "parity": "unpinned (DBoW3 is un-vendored; oracle = restated published algorithm)"}
     if cpu:
         from oracle import oracle_py as O
 
+        OV = O.Vocabulary(**voc)
+        t0 = time.perf_counter()
+        for f in range(min(B, 8)):
+            O.bow_transform(OV, desc[f][: nk[f]], 4)
+        out["bow"]["cpu_baseline"] = {"value": min(B, 8) / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+                                      "sample": "%d frames" % min(B, 8)}
         t0 = time.perf_counter()
         ur = ctx.read_device(res.u_right, (B, N), np.float64)
         dpt = ctx.read_device(res.depth, (B, N), np.float64)
@@ -450,10 +479,11 @@ def run_gpu_arm(args):
         one.close()
 
     # ---- tracking-side matchers: a secondary line, not part of the headline metric ------------
-    matchers = serialize = None
+    matchers = serialize = bow = None
     if rank == 0 and not args.no_matchers:
         matchers = bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cpu=(world == 1 and not args.no_cpu_baseline))
         serialize = matchers.pop("serialize", None)
+        bow = matchers.pop("bow", None)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------------------
     cpu = None
@@ -470,7 +500,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(B, P), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "frames_per_call": S, "matches_first_step": e2e_matches},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency, "matchers": matchers, "serialize": serialize,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency, "matchers": matchers, "serialize": serialize, "bow": bow,
             "check": {"mean_keypoints_per_image": float(nk.mean()), "mean_matches_per_frame": float(nm.mean())},
         }
         print(json.dumps(line), flush=True)

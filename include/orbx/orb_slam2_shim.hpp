@@ -218,6 +218,33 @@ private:
 
 class ORBMatcher;
 
+// ---- DBoW3::Vocabulary as the reference uses it (src/System.cc:93, include/ORB_SLAM2/Frame.h:224-231) ----------------
+typedef std::map<unsigned, double> BowVector;                    // DBoW3::BowVector: WordId -> WordValue
+typedef std::map<unsigned, std::vector<unsigned>> FeatureVector; // DBoW3::FeatureVector: NodeId -> feature indices
+class Vocabulary
+{
+public:
+  // text vocabulary (ORB-SLAM2's ORBvoc.txt layout); the tree lives on the device of the context for (width, height, ...)
+  Vocabulary(const std::string &filename, std::shared_ptr<orbx_ctx> ctx) : mCtx(std::move(ctx))
+  {
+    detail::check(mCtx.get(), orbx_vocab_load_text(mCtx.get(), filename.c_str(), &mVoc), "orbx_vocab_load_text");
+  }
+  ~Vocabulary() { orbx_vocab_destroy(mVoc); }
+  Vocabulary(const Vocabulary &) = delete;
+  Vocabulary &operator=(const Vocabulary &) = delete;
+  unsigned size() const
+  {
+    int32_t words = 0;
+    orbx_vocab_info(mVoc, nullptr, nullptr, nullptr, &words);
+    return (unsigned)words;
+  }
+  const orbx_vocab *handle() const { return mVoc; }
+
+private:
+  std::shared_ptr<orbx_ctx> mCtx;
+  orbx_vocab *mVoc = nullptr;
+};
+
 // ---- the hot-path part of include/ORB_SLAM2/Frame.h:303-371 --------------------------------------------------------
 class Frame
 {
@@ -289,6 +316,24 @@ public:
     out.resize((size_t)n);
     return out;
   }
+  // VirtualFrame::computeBow (include/ORB_SLAM2/Frame.h:224-231): mpVoc->transform(mvLeftDescriptor, mBowVec, mFeatVec, 4)
+  void computeBow(const Vocabulary &voc, BowVector &bowVec, FeatureVector &featVec, int levelsup = 4) const
+  {
+    const std::size_t N = (std::size_t)orbx_capacity();
+    std::vector<int32_t> ids(N), nodes(N), start(N + 1), feats(N);
+    std::vector<double> vals(N);
+    int32_t nb = 0, nf = 0;
+    detail::check(mCtx.get(),
+                  orbx_bow_transform(mCtx.get(), voc.handle(), 0, levelsup, ids.data(), vals.data(), &nb, nodes.data(), start.data(), feats.data(), &nf),
+                  "orbx_bow_transform");
+    bowVec.clear();
+    featVec.clear();
+    for (int i = 0; i < nb; ++i) bowVec.emplace_hint(bowVec.end(), (unsigned)ids[(std::size_t)i], vals[(std::size_t)i]);
+    for (int j = 0; j < nf; ++j)
+      featVec.emplace_hint(featVec.end(), (unsigned)nodes[(std::size_t)j],
+                           std::vector<unsigned>(feats.begin() + start[(std::size_t)j], feats.begin() + start[(std::size_t)j + 1]));
+  }
+  std::shared_ptr<orbx_ctx> context() const { return mCtx; }
   std::vector<cv::Mat> getLeftPyramid() const { return detail::fetch_pyramid(mCtx.get(), 0); }
   std::vector<cv::Mat> getRightPyramid() const { return detail::fetch_pyramid(mCtx.get(), 1); }
   int getN() const { return mnN; }

@@ -113,6 +113,24 @@ int main(int argc, char **argv)
       std::string rec = f->serializeKeyFrameData(42);
       put(out, (int32_t)rec.size());
       out.write(rec.data(), (std::streamsize)rec.size());
+      // VirtualFrame::computeBow with a text vocabulary (optional 11th argument)
+      if (argc > 11)
+      {
+        Vocabulary voc(argv[11], f->context());
+        BowVector bv;
+        FeatureVector fv;
+        f->computeBow(voc, bv, fv);
+        put(out, (int32_t)voc.size());
+        put(out, (int32_t)bv.size());
+        for (auto &kv : bv) put(out, (int32_t)kv.first), put(out, kv.second);
+        put(out, (int32_t)fv.size());
+        for (auto &kv : fv)
+        {
+          put(out, (int32_t)kv.first);
+          put(out, (int32_t)kv.second.size());
+          for (unsigned i : kv.second) put(out, (int32_t)i);
+        }
+      }
     }
     else if (mode == "rgbd")
     {

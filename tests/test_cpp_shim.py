@@ -75,8 +75,10 @@ def test_shim_stereo_matches_oracle(shim_binary, template_path, oracle, tmp_path
     left.tofile(tmp_path / "l.raw")
     right.tofile(tmp_path / "r.raw")
     out = tmp_path / "out.bin"
+    voc = synth.synth_vocabulary(8, 3, 5)
+    voc_path = synth.write_vocabulary_text(str(tmp_path / "voc.txt"), voc)
     r = subprocess.run([shim_binary, "stereo", str(c["width"]), str(c["height"]), "2000", "8", "1.2", template_path, str(tmp_path / "l.raw"),
-                        str(tmp_path / "r.raw"), str(out)], capture_output=True, text=True)
+                        str(tmp_path / "r.raw"), str(out), voc_path], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     rd = _Reader(out)
     el, er = oracle.extract(left), oracle.extract(right)
@@ -113,6 +115,19 @@ def test_shim_stereo_matches_oracle(shim_binary, template_path, oracle, tmp_path
     # Frame::serializeKeyFrameData == the oracle's KeyFrameData bytes for the same frame
     rec = bytes(rd.arr(np.uint8, rd.i32()))
     assert rec == oracle.serialize_keyframe(kl, dl, ur, dp, 42, (0.0, 0.0, float(c["width"]), float(c["height"])), None, True)
+    # Frame::computeBow == the oracle's DBoW3 restatement
+    OV = oracle.Vocabulary(**voc)
+    e = oracle.bow_transform(OV, dl, 4)
+    assert rd.i32() == int((OV.word_id >= 0).sum())
+    nb = rd.i32()
+    bv = rd.arr(np.dtype([("id", "<i4"), ("v", "<f8")]), nb)
+    assert np.array_equal(bv["id"], e["bow_ids"]) and np.array_equal(bv["v"], e["bow_vals"])
+    nf = rd.i32()
+    assert nf == len(e["fv_nodes"])
+    for j in range(nf):
+        assert rd.i32() == e["fv_nodes"][j]
+        m = rd.i32()
+        assert np.array_equal(rd.arr(np.int32, m), e["fv_feats"][e["fv_start"][j] : e["fv_start"][j + 1]])
 
 
 @pytest.mark.gpu
