@@ -1403,7 +1403,12 @@ extern "C"
     if (bow_vals) ORBX_CUDA(c, cudaMemcpy(bow_vals, d.bow_vals + f * N, (size_t)*n_bow * 8, cudaMemcpyDeviceToHost));
     if (fv_nodes) ORBX_CUDA(c, cudaMemcpy(fv_nodes, d.fv_nodes + f * N, (size_t)*n_fv_nodes * 4, cudaMemcpyDeviceToHost));
     if (fv_start) ORBX_CUDA(c, cudaMemcpy(fv_start, d.fv_start + f * (N + 1), ((size_t)*n_fv_nodes + 1) * 4, cudaMemcpyDeviceToHost));
-    if (fv_feats) ORBX_CUDA(c, cudaMemcpy(fv_feats, d.fv_feats + f * N, N * 4, cudaMemcpyDeviceToHost));
+    if (fv_feats)
+    {
+      int32_t n_listed = 0; // == fv_start[n_fv_nodes]: only that many entries were written
+      ORBX_CUDA(c, cudaMemcpy(&n_listed, d.fv_start + f * (N + 1) + (size_t)*n_fv_nodes, 4, cudaMemcpyDeviceToHost));
+      if (n_listed > 0) ORBX_CUDA(c, cudaMemcpy(fv_feats, d.fv_feats + f * N, (size_t)n_listed * 4, cudaMemcpyDeviceToHost));
+    }
     return ORBX_OK;
   }
 

@@ -15,12 +15,20 @@ ok = m["best_idx"] >= 0
 k2 = np.zeros(len(q), api.KP_DTYPE)
 ctx.verify_angle(m["best_idx"][ok], np.nonzero(ok)[0], m["best_dist"][ok].astype(np.float32), res.kps_left, k2)
 rec = ctx.serialize_keyframe(3)
+voc = synth.synth_vocabulary(6, 3, 1)
+V = api.Vocabulary(ctx, **voc)
+bow = ctx.bow_transform(V)
+V.close()
 b = ctx.stereo_batch(np.stack([l, l]), np.stack([r, r]))
+ctx4 = api.Context(320, 240, 500, 4, 1.2, camera=api.Camera(300.0, 300.0, 160.0, 120.0, 0.1), max_batch=4)
+b4 = ctx4.stereo_batch(np.stack([l, l, l, l]), np.stack([r, r, r, r]))
+assert int(b4.n_matches[3]) == res.n_matches
+ctx4.close()
 noise = np.random.default_rng(1).integers(0, 256, (240, 320), dtype=np.uint8)
 ctx.stereo_frame(noise, noise)
 ctx.stereo_frame(np.zeros((240, 320), np.uint8), np.zeros((240, 320), np.uint8))
 g = ctx.rgbd_frame(l, synth.synth_depth_u16(240, 320, 1, 5000.0)) if False else None
-print("driver ok", res.n_matches, len(rec), int(b.n_matches.sum()))
+print("driver ok", res.n_matches, len(rec), int(b.n_matches.sum()), len(bow["bow_ids"]))
 ctx.close()
 PY
 for tool in memcheck racecheck initcheck synccheck; do
