@@ -115,6 +115,24 @@ def test_random_configurations(oracle):
     assert done >= 30
 
 
+@pytest.mark.parametrize("cfg", [(640, 480, 3, 2.0), (642, 481, 3, 2.0), (900, 600, 3, 3.0), (400, 300, 8, 1.05), (1280, 720, 4, 2.0)],
+                         ids=["2x-even", "2x-odd", "3x", "1.05x", "2x-720p"])
+def test_exact_decimation_and_extreme_scale_factors(oracle, cfg):
+    """scale 2 on even sizes takes cv::resize's INTER_AREA re-route for level 1 (exact 2x2 means) while level 2 (4x) stays
+    bilinear; odd sizes and other factors stay bilinear throughout"""
+    w, h, nl, sc = cfg
+    img = synth.synth_image(h, w, 77)
+    ctx = api.Context(w, h, 800, nl, sc)
+    kps, desc = ctx.extract(img)
+    e = oracle.extract(img, 800, nl, sc)
+    _cmp_kps(kps, e.kps, desc, e.desc, str(cfg))
+    for l, (a, b) in enumerate(zip(ctx.get_pyramid(0), [e.pyr.level(i) for i in range(nl)])):
+        assert np.array_equal(a, b), f"level {l}"
+    for l, (a, b) in enumerate(zip(ctx.get_pyramid(0, True), [e.pyr.blurred(i) for i in range(nl)])):
+        assert np.array_equal(a, b), f"blurred level {l}"
+    ctx.close()
+
+
 def test_degenerate_images(oracle):
     ctx = api.Context(320, 240, 1000, 4, 1.2)
     kps, desc = ctx.extract(np.zeros((240, 320), np.uint8))
