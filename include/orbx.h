@@ -255,6 +255,20 @@ typedef struct orbx_device_bow {
 } orbx_device_bow;
 int orbx_bow_transform_batch_device(orbx_ctx *ctx, const orbx_vocab *vocab, int n_frames, int levelsup, orbx_device_bow *out);
 
+/* replaces the matching loop of ORBMatcher::searchByBow (src/ORBMatcher.cc:170-255) between frame `frame` of the most recent
+ * call (whose FeatureVector must be resident: call orbx_bow_transform* for it first) and a keyframe given by its
+ * FeatureVector (CSR: kf_fv_nodes ascending, kf_fv_start[n_kf_nodes + 1], kf_fv_feats) and descriptors kf_desc[n_kf][32].
+ * kf_query_ok[pkId] != 0: this keyframe feature takes part (the MapPoint conditions of :195-212; NULL = all);
+ * frame_cand_ok[pId] != 0: this frame feature may be matched (:216-233; NULL = all; n_features entries).
+ * Outputs have one entry per kf_fv_feats entry e (the reference's visiting order): candidates = the frame's features under
+ * the same vocabulary node that pass the mask, then ORBMatcher::getBestMatch (:238).  n_candidates[e] == 0 (best_idx -1)
+ * when the node is not shared, the feature is masked or no candidate is left (the reference `continue`s).  The caller keeps
+ * the rows with dist <= mnMinThreshold && !(ratio > mfRatio) (:240) and runs orbx_verify_angle (:248-249). */
+int orbx_search_by_bow(orbx_ctx *ctx, int frame, int n_kf_nodes, const int32_t *kf_fv_nodes, const int32_t *kf_fv_start,
+                       const int32_t *kf_fv_feats, const uint8_t *kf_desc, int n_kf, const uint8_t *kf_query_ok,
+                       const uint8_t *frame_cand_ok, int32_t *best_idx, int32_t *best_dist, float *ratio,
+                       int32_t *n_candidates);
+
 /* ---- introspection for benchmarks / profiles ----------------------------------------------------------- */
 #define ORBX_N_STAGES 6
 /* Same work as orbx_stereo_batch_device, with a CUDA event recorded on the stream after every kernel; blocks until

@@ -89,6 +89,8 @@ def lib():
         L.oracle_verify_angle.argtypes = [C.c_int, i32p, i32p, f32p, C.c_void_p, C.c_void_p]
         L.oracle_bow_transform.restype = C.c_int
         L.oracle_bow_transform.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, i32p, f64p, i32p, i32p, i32p, i32p]
+        L.oracle_search_by_bow.restype = C.c_int
+        L.oracle_search_by_bow.argtypes = [i32p, i32p, i32p, C.c_int, u8p, u8p, i32p, i32p, i32p, C.c_int, u8p, u8p, i32p, i32p, i32p, f32p, i32p]
         L.oracle_serialize_keyframe.restype = C.c_size_t
         L.oracle_serialize_keyframe.argtypes = [C.c_void_p, u8p, f64p, f64p, C.c_int, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float, f32p, C.c_int,
                                                 u8p, C.c_size_t]
@@ -411,6 +413,23 @@ def bow_transform(voc: Vocabulary, desc, levelsup: int = 4):
                                    _ptr(ff, i32p), C.byref(cnt))
     c = cnt.value
     return dict(bow_ids=ids[:m].copy(), bow_vals=vals[:m].copy(), fv_nodes=fn_[:c].copy(), fv_start=fs[: c + 1].copy(), fv_feats=ff[: fs[c]].copy())
+
+
+def search_by_bow(f_bow: dict, f_desc, k_bow: dict, k_desc, frame_cand_ok=None, kf_query_ok=None):
+    """oracle_search_by_bow on two bow_transform() results -> dict(kf_idx, best_idx, best_dist, ratio, n_cand), one row per
+    visited keyframe feature with candidates"""
+    fd, kd = np.ascontiguousarray(f_desc, np.uint8), np.ascontiguousarray(k_desc, np.uint8)
+    fn, fs, ff = (np.ascontiguousarray(f_bow[k], np.int32) for k in ("fv_nodes", "fv_start", "fv_feats"))
+    kn, ks, kf = (np.ascontiguousarray(k_bow[k], np.int32) for k in ("fv_nodes", "fv_start", "fv_feats"))
+    fm = None if frame_cand_ok is None else np.ascontiguousarray(frame_cand_ok, np.uint8)
+    km = None if kf_query_ok is None else np.ascontiguousarray(kf_query_ok, np.uint8)
+    cap = max(len(kf), 1)
+    ki, bi, bd, nc = (np.zeros(cap, np.int32) for _ in range(4))
+    ra = np.zeros(cap, np.float32)
+    n = lib().oracle_search_by_bow(_ptr(fn, i32p), _ptr(fs, i32p), _ptr(ff, i32p), len(fn), _ptr(fd, u8p), _ptr(fm, u8p), _ptr(kn, i32p), _ptr(ks, i32p),
+                                   _ptr(kf, i32p), len(kn), _ptr(kd, u8p), _ptr(km, u8p), _ptr(ki, i32p), _ptr(bi, i32p), _ptr(bd, i32p), _ptr(ra, f32p),
+                                   _ptr(nc, i32p))
+    return dict(kf_idx=ki[:n].copy(), best_idx=bi[:n].copy(), best_dist=bd[:n].copy(), ratio=ra[:n].copy(), n_cand=nc[:n].copy())
 
 
 # ----------------------------------------------------------------------------------------------------------------

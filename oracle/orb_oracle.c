@@ -1064,3 +1064,45 @@ int oracle_bow_transform(const oracle_vocab *v, const uint8_t *desc, int n, int 
   free(f_ok);
   return m;
 }
+
+/* The matching loop of ORBMatcher::searchByBow, src/ORBMatcher.cc:170-255, without the MapPoint objects: the caller
+ * passes what the loop derives from them -- kf_query_ok[pkId] ("this keyframe feature takes part", :195-212) and
+ * frame_cand_ok[pId] ("this frame feature may be matched", :216-233).  Merge-join of the two FeatureVectors (:181-186);
+ * for every keyframe feature of a common node, in the keyframe's list order: candidates = the frame's features of the
+ * node that pass the mask, then getBestMatch (:238).  One output row per visited keyframe feature that has candidates
+ * (the reference's ++nMatch, :239): kf_idx, best_idx, best_dist, ratio.  The caller thresholds (:240-245: rejected iff
+ * dist > mnMinThreshold || ratio > mfRatio -- a NaN ratio is accepted) and runs verifyAngle.  Returns the row count. */
+int oracle_search_by_bow(const int32_t *f_nodes, const int32_t *f_start, const int32_t *f_feats, int f_n_nodes,
+                         const uint8_t *f_desc, const uint8_t *frame_cand_ok, const int32_t *k_nodes,
+                         const int32_t *k_start, const int32_t *k_feats, int k_n_nodes, const uint8_t *k_desc,
+                         const uint8_t *kf_query_ok, int32_t *kf_idx, int32_t *best_idx, int32_t *best_dist,
+                         float *ratio, int32_t *n_cand) {
+  int rows = 0, fi = 0, ki = 0;
+  int cap = 0;
+  for (int j = 0; j < f_n_nodes; ++j) cap = imax(cap, f_start[j + 1] - f_start[j]);
+  int *cand = (int *)malloc(sizeof(int) * (size_t)(cap > 0 ? cap : 1));
+  while (fi < f_n_nodes && ki < k_n_nodes) {
+    if (f_nodes[fi] > k_nodes[ki])
+      ++ki;
+    else if (f_nodes[fi] < k_nodes[ki])
+      ++fi;
+    else {
+      for (int e = k_start[ki]; e < k_start[ki + 1]; ++e) {
+        const int pk = k_feats[e];
+        if (kf_query_ok && !kf_query_ok[pk]) continue;
+        int n = 0;
+        for (int t = f_start[fi]; t < f_start[fi + 1]; ++t)
+          if (!frame_cand_ok || frame_cand_ok[f_feats[t]]) cand[n++] = f_feats[t];
+        if (n == 0) continue;
+        kf_idx[rows] = pk;
+        n_cand[rows] = n;
+        best_idx[rows] = oracle_best_match(k_desc + 32 * (size_t)pk, f_desc, cand, n, &best_dist[rows], &ratio[rows]);
+        ++rows;
+      }
+      ++fi;
+      ++ki;
+    }
+  }
+  free(cand);
+  return rows;
+}

@@ -148,6 +148,14 @@ void oracle_bow_descend(const oracle_vocab *v, const uint8_t *desc, int levelsup
 int oracle_bow_transform(const oracle_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *bow_ids,
                          double *bow_vals, int32_t *fv_nodes, int32_t *fv_start, int32_t *fv_feats, int *fv_count);
 
+/* matching loop of ORBMatcher::searchByBow, src/ORBMatcher.cc:170-255 (masks instead of MapPoint objects); FeatureVectors
+ * as CSRs (nodes ascending, start[n+1], feature indices).  Returns the number of output rows. */
+int oracle_search_by_bow(const int32_t *f_nodes, const int32_t *f_start, const int32_t *f_feats, int f_n_nodes,
+                         const uint8_t *f_desc, const uint8_t *frame_cand_ok, const int32_t *k_nodes,
+                         const int32_t *k_start, const int32_t *k_feats, int k_n_nodes, const uint8_t *k_desc,
+                         const uint8_t *kf_query_ok, int32_t *kf_idx, int32_t *best_idx, int32_t *best_dist,
+                         float *ratio, int32_t *n_cand);
+
 #ifdef __cplusplus
 }
 #endif

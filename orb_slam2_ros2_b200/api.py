@@ -75,6 +75,7 @@ EXPORTS = [
     "orbx_search_in_area", "orbx_search_in_area_batch_device", "orbx_verify_angle",
     "orbx_serialized_capacity", "orbx_serialize_keyframe", "orbx_serialize_keyframes_device",
     "orbx_vocab_create", "orbx_vocab_load_text", "orbx_vocab_destroy", "orbx_vocab_info", "orbx_bow_transform", "orbx_bow_transform_batch_device",
+    "orbx_search_by_bow",
 ]
 
 class OrbxDeviceBow(C.Structure):
@@ -147,6 +148,7 @@ def load_library(build_if_missing: bool = True):
     L.orbx_vocab_info.argtypes = [vp] + [C.POINTER(C.c_int32)] * 4
     L.orbx_bow_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int32), vp, vp, vp, C.POINTER(C.c_int32)]
     L.orbx_bow_transform_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(OrbxDeviceBow)]
+    L.orbx_search_by_bow.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -428,6 +430,27 @@ class Context:
         _check(self._h, self._L.orbx_bow_transform_batch_device(self._h, vocab._h, n_frames, levelsup, C.byref(res)), "orbx_bow_transform_batch_device")
         return res
 
+    def search_by_bow(self, kf_bow: dict, kf_desc: np.ndarray, kf_query_ok=None, frame_cand_ok=None, frame: int = 0) -> dict:
+        """matching loop of ORBMatcher::searchByBow (src/ORBMatcher.cc:170-255) against a frame whose bow_transform() was just
+        computed; kf_bow = a bow_transform() result of the keyframe.  -> dict(kf_idx, best_idx, best_dist, ratio, n_cand) with
+        one row per visited keyframe feature that had candidates (the reference's ++nMatch)"""
+        kn, ks, kf = (np.ascontiguousarray(kf_bow[k], np.int32) for k in ("fv_nodes", "fv_start", "fv_feats"))
+        kd = np.ascontiguousarray(kf_desc, np.uint8)
+        qm = None if kf_query_ok is None else np.ascontiguousarray(kf_query_ok, np.uint8)
+        cm = None
+        if frame_cand_ok is not None:
+            cm = np.zeros(self.n_features, np.uint8)
+            cm[: len(frame_cand_ok)] = np.asarray(frame_cand_ok).astype(bool)
+        n = len(kf)
+        bi, bd, nc = np.full(n, -1, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ra = np.zeros(n, np.float32)
+        rc = self._L.orbx_search_by_bow(self._h, frame, len(kn), kn.ctypes.data, ks.ctypes.data, kf.ctypes.data, kd.ctypes.data, len(kd),
+                                        qm.ctypes.data if qm is not None else None, cm.ctypes.data if cm is not None else None, bi.ctypes.data, bd.ctypes.data,
+                                        ra.ctypes.data, nc.ctypes.data)
+        _check(self._h, rc, "orbx_search_by_bow")
+        ok = nc > 0
+        return dict(kf_idx=kf[ok], best_idx=bi[ok], best_dist=bd[ok], ratio=ra[ok], n_cand=nc[ok])
+
     # ---- batches ----------------------------------------------------------------------------------------------------
     def stereo_batch(self, left: np.ndarray, right: np.ndarray, out: "StereoBatchBuffers | None" = None):
         """left/right: (n, H, W) uint8 host arrays (pinned memory makes the copies asynchronous)."""
@@ -666,6 +689,27 @@ class ORBMatcher:
                 out.append((k, i, r["best_dist"][i]))
                 n_matches += 1
         return n_matches, np.asarray(out, np.int32).reshape(-1, 3)
+
+    def searchByBow(self, pFrame: "Frame", vocab: "Vocabulary", kf_kps: np.ndarray, kf_desc: np.ndarray, kf_bow: dict, kfGood: np.ndarray,
+                    frameGood: np.ndarray, bAddMPs: bool = False, bLoop: bool = False, levelsup: int = 4) -> np.ndarray:
+        """searchByBow(pFrame, pKframe, matches, bAddMPs, bLoop) (src/ORBMatcher.cc:170-255).  kfGood[i] / frameGood[i] = "the
+        feature has a good map point" (for bAddMPs: "... that is in the map").  -> (m, 3) int32 rows (queryIdx = frame
+        feature, trainIdx = keyframe feature, distance) after verifyAngle when mbCheckOri."""
+        ctx: Context = pFrame.extra["ctx"]
+        ctx.bow_transform(vocab, frame=pFrame.extra.get("frame", 0), levelsup=levelsup)  # pFrame->computeBow() (levelsup 4, Frame.h:229)
+        kg, fg = np.asarray(kfGood).astype(bool), np.asarray(frameGood).astype(bool)
+        if bAddMPs:
+            q_ok, c_ok = ~kg, ~fg          # both sides without a map point (:198-201, :221-225)
+        elif bLoop:
+            q_ok, c_ok = np.ones_like(kg), np.ones_like(fg)
+        else:
+            q_ok, c_ok = kg, ~fg           # keyframe side has one, frame side does not (:207-211, :230-233)
+        r = ctx.search_by_bow(kf_bow, kf_desc, q_ok, c_ok, frame=pFrame.extra.get("frame", 0))
+        keep = ~((r["best_dist"] > self.mnMinThreshold) | (r["ratio"] > self.mfRatio))
+        m = np.stack([r["best_idx"][keep], r["kf_idx"][keep], r["best_dist"][keep]], axis=1).astype(np.int32).reshape(-1, 3)
+        if self.mbCheckOri and len(m):
+            m = self.verifyAngle(ctx, m, pFrame.mvFeatsLeft, kf_kps)
+        return m
 
     def verifyAngle(self, ctx: Context, matches: np.ndarray, keyPoints1: np.ndarray, keyPoints2: np.ndarray) -> np.ndarray:
         """ORBMatcher::verifyAngle (src/ORBMatcher.cc:1013-1051) on (m, 3) rows (queryIdx, trainIdx, distance)"""

@@ -56,6 +56,9 @@ struct orbx_ctx
   // bag-of-words transform: per-feature and per-frame result buffers, allocated on first use
   BowArgs bow{};
   bool bow_ready = false;
+  uint64_t frame_epoch = 0;   // bumped by every call that produces frames
+  uint64_t bow_epoch = ~0ull; // frame_epoch at the last bag-of-words call
+  int bow_frames = 0;         // frames covered by that call
 };
 
 // DBoW3 vocabulary tree resident on one device
@@ -744,6 +747,7 @@ extern "C"
     int rc = run_extract(c, p, n_images);
     if (rc) return rc;
     c->last_images = n_images;
+    ++c->frame_epoch;
     c->last_stereo = 0;
     fill_results(c, n_images, 0, out);
     return ORBX_OK;
@@ -779,6 +783,7 @@ extern "C"
       }
     }
     c->last_images = 2 * n_frames;
+    ++c->frame_epoch;
     c->last_stereo = 1;
     c->last_frames = n_frames;
     fill_results(c, 2 * n_frames, n_frames, out);
@@ -827,6 +832,7 @@ extern "C"
     for (int i = 0; i < ORBX_N_STAGES; ++i) ORBX_CUDA(c, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
     for (auto &e : ev) cudaEventDestroy(e);
     c->last_images = ni;
+    ++c->frame_epoch;
     c->last_stereo = 1;
     c->last_frames = n_frames;
     return ORBX_OK;
@@ -855,6 +861,7 @@ extern "C"
     c->launches += 2;
     ORBX_CUDA(c, cudaGetLastError());
     c->last_images = n_frames;
+    ++c->frame_epoch;
     c->last_stereo = 0;
     c->last_frames = n_frames;
     fill_results(c, n_frames, n_frames, out);
@@ -935,6 +942,7 @@ extern "C"
     // introspection (get_pyramid / get_grid) refers to the device slots, i.e. to the frames of the last pass over them
     c->last_frames = std::min(n_frames, n_slots * chunk);
     c->last_images = 2 * c->last_frames;
+    ++c->frame_epoch;
     c->last_stereo = 1;
     return ORBX_OK;
   }
@@ -1380,6 +1388,8 @@ extern "C"
     launch_bow_descend(c->p, a, n_frames, c->stream);
     launch_bow_assemble(c->p, a, n_frames, c->stream);
     c->launches += 2;
+    c->bow_epoch = c->frame_epoch;
+    c->bow_frames = n_frames;
     ORBX_CUDA(c, cudaGetLastError());
     out->bow_ids = a.bow_ids, out->bow_vals = a.bow_vals, out->n_bow = a.n_bow;
     out->fv_nodes = a.fv_nodes, out->fv_start = a.fv_start, out->fv_feats = a.fv_feats, out->n_fv_nodes = a.n_fv;
@@ -1409,6 +1419,55 @@ extern "C"
       ORBX_CUDA(c, cudaMemcpy(&n_listed, d.fv_start + f * (N + 1) + (size_t)*n_fv_nodes, 4, cudaMemcpyDeviceToHost));
       if (n_listed > 0) ORBX_CUDA(c, cudaMemcpy(fv_feats, d.fv_feats + f * N, (size_t)n_listed * 4, cudaMemcpyDeviceToHost));
     }
+    return ORBX_OK;
+  }
+
+  int orbx_search_by_bow(orbx_ctx *c, int frame, int n_kf_nodes, const int32_t *kf_fv_nodes, const int32_t *kf_fv_start, const int32_t *kf_fv_feats,
+                         const uint8_t *kf_desc, int n_kf, const uint8_t *kf_query_ok, const uint8_t *frame_cand_ok, int32_t *best_idx, int32_t *best_dist,
+                         float *ratio, int32_t *n_candidates)
+  {
+    if (!c || frame < 0 || n_kf_nodes < 0 || n_kf < 0) return ORBX_ERR_INVALID_ARG;
+    if (n_kf_nodes == 0) return ORBX_OK;
+    if (!kf_fv_nodes || !kf_fv_start || !kf_fv_feats || !kf_desc) return ORBX_ERR_INVALID_ARG;
+    if (c->bow_epoch != c->frame_epoch || frame >= c->bow_frames)
+      return fail(c, ORBX_ERR_STATE, "call orbx_bow_transform for this frame first (its FeatureVector must be resident)");
+    const int n_listed = kf_fv_start[n_kf_nodes];
+    if (n_listed <= 0) return ORBX_OK;
+    for (int i = 0; i < n_listed; ++i)
+      if (kf_fv_feats[i] < 0 || kf_fv_feats[i] >= n_kf) return fail(c, ORBX_ERR_INVALID_ARG, "keyframe FeatureVector refers to a feature outside kf_desc");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)c->cfg.n_features, nl = (size_t)n_listed, nn = (size_t)n_kf_nodes;
+    const size_t o_nodes = 0, o_start = o_nodes + up256(nn * 4), o_feats = o_start + up256((nn + 1) * 4), o_desc = o_feats + up256(nl * 4),
+                 o_qok = o_desc + up256((size_t)n_kf * 32), o_cok = o_qok + up256((size_t)n_kf), o_out = o_cok + up256(N), total = o_out + up256(nl * 16);
+    uint8_t *base = nullptr;
+    int rc = match_scratch(c, total, &base);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    ORBX_CUDA(c, cudaMemcpyAsync(base + o_nodes, kf_fv_nodes, nn * 4, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(c, cudaMemcpyAsync(base + o_start, kf_fv_start, (nn + 1) * 4, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(c, cudaMemcpyAsync(base + o_feats, kf_fv_feats, nl * 4, cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(c, cudaMemcpyAsync(base + o_desc, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, s));
+    if (kf_query_ok) ORBX_CUDA(c, cudaMemcpyAsync(base + o_qok, kf_query_ok, (size_t)n_kf, cudaMemcpyHostToDevice, s));
+    if (frame_cand_ok) ORBX_CUDA(c, cudaMemcpyAsync(base + o_cok, frame_cand_ok, N, cudaMemcpyHostToDevice, s));
+    const size_t f = (size_t)frame;
+    const int img = frame * (c->last_stereo ? 2 : 1);
+    BowMatchArgs a{};
+    a.f_nodes = c->bow.fv_nodes + f * N, a.f_start = c->bow.fv_start + f * (N + 1), a.f_feats = c->bow.fv_feats + f * N, a.f_n_nodes = c->bow.n_fv + f;
+    a.f_desc = c->p.desc + (size_t)img * N * 32, a.frame_cand_ok = frame_cand_ok ? base + o_cok : nullptr;
+    a.k_nodes = (const int *)(base + o_nodes), a.k_start = (const int *)(base + o_start), a.k_feats = (const int *)(base + o_feats);
+    a.k_n_nodes = n_kf_nodes, a.k_n_listed = n_listed;
+    a.k_desc = base + o_desc, a.kf_query_ok = kf_query_ok ? base + o_qok : nullptr;
+    int32_t *d_idx = (int32_t *)(base + o_out), *d_dist = d_idx + nl, *d_nc = d_dist + nl;
+    float *d_ratio = (float *)(d_nc + nl);
+    a.best_idx = d_idx, a.best_dist = d_dist, a.n_cand = d_nc, a.ratio = d_ratio;
+    launch_bow_match(a, s);
+    ++c->launches;
+    ORBX_CUDA(c, cudaGetLastError());
+    if (best_idx) ORBX_CUDA(c, cudaMemcpyAsync(best_idx, d_idx, nl * 4, cudaMemcpyDeviceToHost, s));
+    if (best_dist) ORBX_CUDA(c, cudaMemcpyAsync(best_dist, d_dist, nl * 4, cudaMemcpyDeviceToHost, s));
+    if (n_candidates) ORBX_CUDA(c, cudaMemcpyAsync(n_candidates, d_nc, nl * 4, cudaMemcpyDeviceToHost, s));
+    if (ratio) ORBX_CUDA(c, cudaMemcpyAsync(ratio, d_ratio, nl * 4, cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(c, cudaStreamSynchronize(s));
     return ORBX_OK;
   }
 
@@ -1493,6 +1552,7 @@ extern "C"
     ORBX_CUDA(c, cudaGetLastError());
     ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     c->last_images = std::max(c->last_images, 1);
+    ++c->frame_epoch;
     return ORBX_OK;
   }
 

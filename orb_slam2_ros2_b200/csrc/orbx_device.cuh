@@ -153,6 +153,19 @@ struct AreaArgs
   float max_u, max_v;       // mfMaxU / mfMaxV
 };
 
+struct BowMatchArgs
+{
+  // the frame's FeatureVector (device results of the last bag-of-words call) and descriptors
+  const int *f_nodes, *f_start, *f_feats, *f_n_nodes;
+  const uint8_t *f_desc, *frame_cand_ok;
+  // the keyframe's FeatureVector, descriptors and mask (uploaded by the caller)
+  const int *k_nodes, *k_start, *k_feats;
+  int k_n_nodes, k_n_listed;
+  const uint8_t *k_desc, *kf_query_ok;
+  int *best_idx, *best_dist, *n_cand; // [k_n_listed]
+  float *ratio;
+};
+
 struct VerifyArgs
 {
   int n;
@@ -206,6 +219,7 @@ void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
 void launch_grid(const Params &p, int n_frames, int image_stride, cudaStream_t s);
 void launch_area_match(const Params &p, const AreaArgs &a, int n_frames, cudaStream_t s);
 void launch_verify_angle(const VerifyArgs &a, cudaStream_t s);
+void launch_bow_match(const BowMatchArgs &a, cudaStream_t s);
 void launch_serialize(const Params &p, const SerArgs &a, int n_frames, cudaStream_t s);
 void launch_bow_descend(const Params &p, const BowArgs &a, int n_frames, cudaStream_t s);
 void launch_bow_assemble(const Params &p, const BowArgs &a, int n_frames, cudaStream_t s);

@@ -3,6 +3,8 @@
 //   area_match_kernel    VirtualFrame::findFeaturesInArea (src/Frame.cc:286-311) + the exclusion filter of
 //                        ORBMatcher::searchByProjection (src/ORBMatcher.cc:322-331) + ORBMatcher::getBestMatch
 //                        (src/ORBMatcher.cc:967-990), one warp per query, over the frame's device-resident CSR grid
+//   bow_match_kernel     the matching loop of ORBMatcher::searchByBow (src/ORBMatcher.cc:170-255), one warp per keyframe
+//                        feature, candidates = the frame's features under the same vocabulary node
 //   verify_angle_kernel  ORBMatcher::verifyAngle (src/ORBMatcher.cc:1013-1051), one CTA per match list
 //
 // Both reproduce the reference's candidate ORDER (grid cells row-major, ascending keypoint index inside a cell), which
@@ -22,6 +24,41 @@ __device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, cons
 {
   return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) +
          __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// One chunk of up to 32 candidates (lane order == the reference's candidate order; id < 0: no candidate on this lane) of
+// ORBMatcher::getBestMatch (src/ORBMatcher.cc:967-990).  The sequential rule
+//   if (d < min) { min = d; idx = i; } else if (d < second) second = d;
+// is evaluated with an exclusive prefix-minimum over the lanes: a candidate is a "new minimum" iff its distance is below
+// every earlier one (the running minimum included); `second` is the minimum over all the others.
+__device__ __forceinline__ void best_match_chunk(int id, int d, int lane, int &n_cand, int &min_d, int &second_d, int &min_idx)
+{
+  const unsigned valid = __ballot_sync(kFull, id >= 0);
+  if (!valid) return;
+  n_cand += __popc(valid);
+  int pm = d; // exclusive prefix minimum over the lanes, seeded with the running minimum
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1)
+  {
+    const int t = __shfl_up_sync(kFull, pm, s);
+    if (lane >= s) pm = min(pm, t);
+  }
+  int ex = __shfl_up_sync(kFull, pm, 1);
+  if (lane == 0) ex = 0x7fffffff;
+  ex = min(ex, min_d);
+  const bool is_new = id >= 0 && d < ex;
+  int sec = (id >= 0 && !is_new) ? d : 0x7fffffff;
+#pragma unroll
+  for (int s = 16; s; s >>= 1) sec = min(sec, __shfl_xor_sync(kFull, sec, s));
+  second_d = min(second_d, sec);
+  // the last "new minimum" lane of the chunk holds the chunk's minimum at its first occurrence
+  const unsigned news = __ballot_sync(kFull, is_new);
+  if (news)
+  {
+    const int src = 31 - __clz(news);
+    min_d = __shfl_sync(kFull, d, src);
+    min_idx = __shfl_sync(kFull, id, src);
+  }
 }
 
 // One warp per query.  Candidates are visited 32 at a time in the reference's order; getBestMatch's sequential rule
@@ -75,33 +112,7 @@ __global__ void __launch_bounds__(kAreaWarps * 32) area_match_kernel(const Param
           if (o > q.max_level || o < q.min_level || (excl && excl[id])) id = -1;
         }
         if (id >= 0) d = hamming256(q0, q1, __ldg(desc + 2 * id), __ldg(desc + 2 * id + 1));
-        const unsigned valid = __ballot_sync(kFull, id >= 0);
-        if (!valid) continue;
-        n_cand += __popc(valid);
-        // exclusive prefix minimum over the lanes, seeded with the running minimum
-        int pm = d;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1)
-        {
-          const int t = __shfl_up_sync(kFull, pm, s);
-          if (lane >= s) pm = min(pm, t);
-        }
-        int ex = __shfl_up_sync(kFull, pm, 1);
-        if (lane == 0) ex = 0x7fffffff;
-        ex = min(ex, min_d);
-        const bool is_new = id >= 0 && d < ex;
-        int sec = (id >= 0 && !is_new) ? d : 0x7fffffff;
-#pragma unroll
-        for (int s = 16; s; s >>= 1) sec = min(sec, __shfl_xor_sync(kFull, sec, s));
-        second_d = min(second_d, sec);
-        // the last "new minimum" lane of the chunk holds the chunk's minimum at its first occurrence
-        const unsigned news = __ballot_sync(kFull, is_new);
-        if (news)
-        {
-          const int src = 31 - __clz(news);
-          min_d = __shfl_sync(kFull, d, src);
-          min_idx = __shfl_sync(kFull, id, src);
-        }
+        best_match_chunk(id, d, lane, n_cand, min_d, second_d, min_idx);
       }
     }
   }
@@ -111,6 +122,66 @@ __global__ void __launch_bounds__(kAreaWarps * 32) area_match_kernel(const Param
     a.best_idx[qo] = n_cand ? min_idx : -1;
     a.best_dist[qo] = min_d;
     a.ratio[qo] = n_cand ? __fdiv_rn((float)min_d, (float)second_d) : 0.f; // :988
+  }
+}
+
+// The matching loop of ORBMatcher::searchByBow (src/ORBMatcher.cc:170-255): one warp per entry of the keyframe's
+// FeatureVector.  The entry's vocabulary node is looked up in the frame's FeatureVector (both sorted by node id: binary
+// searches replace the reference's merge-join); candidates = the frame's features of that node that pass the mask.
+__global__ void __launch_bounds__(kAreaWarps * 32) bow_match_kernel(const BowMatchArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * kAreaWarps + (threadIdx.x >> 5);
+  if (e >= a.k_n_listed) return;
+  int n_cand = 0, min_d = 0x7fffffff, second_d = 0x7fffffff, min_idx = -1;
+  const int pk = a.k_feats[e];
+  if (!a.kf_query_ok || a.kf_query_ok[pk])
+  {
+    // keyframe node segment containing entry e: last j with k_start[j] <= e
+    int lo = 0, hi = a.k_n_nodes;
+    while (hi - lo > 1)
+    {
+      const int mid = (lo + hi) >> 1;
+      if (a.k_start[mid] <= e) lo = mid; else hi = mid;
+    }
+    const int node = a.k_nodes[lo];
+    const int f_n = *a.f_n_nodes;
+    int l2 = 0, h2 = f_n; // first frame node >= node
+    while (l2 < h2)
+    {
+      const int mid = (l2 + h2) >> 1;
+      if (a.f_nodes[mid] < node) l2 = mid + 1; else h2 = mid;
+    }
+    if (l2 < f_n && a.f_nodes[l2] == node)
+    {
+      const uint4 *qd = reinterpret_cast<const uint4 *>(a.k_desc + (size_t)pk * 32);
+      const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
+      const uint4 *fd = reinterpret_cast<const uint4 *>(a.f_desc);
+      const int t0 = a.f_start[l2], t1 = a.f_start[l2 + 1];
+      for (int t = t0; t < t1; t += 32)
+      {
+        int id = -1, d = 0x7fffffff;
+        if (t + lane < t1)
+        {
+          id = a.f_feats[t + lane];
+          if (a.frame_cand_ok && !a.frame_cand_ok[id]) id = -1;
+        }
+        if (id >= 0)
+        {
+          const uint4 b0 = __ldg(fd + 2 * id), b1 = __ldg(fd + 2 * id + 1);
+          d = __popc(q0.x ^ b0.x) + __popc(q0.y ^ b0.y) + __popc(q0.z ^ b0.z) + __popc(q0.w ^ b0.w) + __popc(q1.x ^ b1.x) + __popc(q1.y ^ b1.y) +
+              __popc(q1.z ^ b1.z) + __popc(q1.w ^ b1.w);
+        }
+        best_match_chunk(id, d, lane, n_cand, min_d, second_d, min_idx);
+      }
+    }
+  }
+  if (lane == 0)
+  {
+    a.n_cand[e] = n_cand;
+    a.best_idx[e] = n_cand ? min_idx : -1;
+    a.best_dist[e] = min_d;
+    a.ratio[e] = n_cand ? __fdiv_rn((float)min_d, (float)second_d) : 0.f;
   }
 }
 
@@ -197,5 +268,10 @@ void launch_area_match(const Params &p, const AreaArgs &a, int n_frames, cudaStr
 }
 
 void launch_verify_angle(const VerifyArgs &a, cudaStream_t s) { verify_angle_kernel<<<1, kVaThreads, 0, s>>>(a); }
+
+void launch_bow_match(const BowMatchArgs &a, cudaStream_t s)
+{
+  bow_match_kernel<<<(a.k_n_listed + kAreaWarps - 1) / kAreaWarps, kAreaWarps * 32, 0, s>>>(a);
+}
 
 } // namespace orbx

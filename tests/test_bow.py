@@ -150,3 +150,111 @@ def test_cuda_bow_batch_device_rgbd_and_empty(oracle):
     assert len(got["bow_ids"]) == 0 and len(got["fv_nodes"]) == 0 and len(got["fv_feats"]) == 0
     V.close()
     ctx.close()
+
+
+# ---- ORBMatcher::searchByBow (src/ORBMatcher.cc:170-255) on top of the FeatureVectors ----------------------------------
+def _py_search_by_bow(oracle, f_bow, f_desc, k_bow, k_desc, cand_ok, query_ok):
+    """literal merge-join of the two FeatureVectors with the reference's getBestMatch (sequential min / second rule)"""
+    rows = []
+    fi = ki = 0
+    fn, fs, ff = f_bow["fv_nodes"], f_bow["fv_start"], f_bow["fv_feats"]
+    kn, ks, kf = k_bow["fv_nodes"], k_bow["fv_start"], k_bow["fv_feats"]
+    while fi < len(fn) and ki < len(kn):
+        if fn[fi] > kn[ki]:
+            ki += 1
+        elif fn[fi] < kn[ki]:
+            fi += 1
+        else:
+            for pk in kf[ks[ki] : ks[ki + 1]]:
+                if query_ok is not None and not query_ok[pk]:
+                    continue
+                cand = [p for p in ff[fs[fi] : fs[fi + 1]] if cand_ok is None or cand_ok[p]]
+                if not cand:
+                    continue
+                mn, sec, idx = 2**31 - 1, 2**31 - 1, 0
+                for p in cand:
+                    d = int(np.unpackbits(k_desc[pk] ^ f_desc[p]).sum())
+                    if d < mn:
+                        mn, idx = d, p
+                    elif d < sec:
+                        sec = d
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    rows.append((pk, idx, mn, np.float32(mn) / np.float32(sec), len(cand)))
+            fi += 1
+            ki += 1
+    return rows
+
+
+def _frames_for_bow(oracle, seed):
+    """two descriptor sets sharing most features (a frame and a keyframe of the same place) + a vocabulary built around them"""
+    rng = np.random.default_rng(seed)
+    voc = synth.synth_vocabulary(8, 3, seed)
+    V = oracle.Vocabulary(**voc)
+    leaves = np.nonzero(V.word_id >= 0)[0]
+    base = V.desc[rng.choice(leaves, 700)].copy()
+
+    def noisy(d, flips):
+        d = d.copy()
+        bits = rng.integers(0, 256, (len(d), flips))
+        for b in range(flips):
+            d[np.arange(len(d)), bits[:, b] // 8] ^= (1 << (bits[:, b] % 8)).astype(np.uint8)
+        return d
+
+    f_desc = noisy(base[rng.permutation(700)[:600]], 5)
+    k_desc = noisy(base[rng.permutation(700)[:650]], 5)
+    k_desc[:40] = f_desc[:40]  # exact copies: distance 0, NaN ratios when the runner-up is 0 too
+    return voc, V, f_desc, k_desc, rng
+
+
+def test_oracle_search_by_bow_equals_literal_merge_join(oracle):
+    for seed in (1, 2):
+        voc, V, f_desc, k_desc, rng = _frames_for_bow(oracle, seed)
+        fb, kb = oracle.bow_transform(V, f_desc, 2), oracle.bow_transform(V, k_desc, 2)
+        for cand_ok, query_ok in [(None, None), ((rng.random(len(f_desc)) < 0.6).astype(np.uint8), (rng.random(len(k_desc)) < 0.7).astype(np.uint8))]:
+            r = oracle.search_by_bow(fb, f_desc, kb, k_desc, cand_ok, query_ok)
+            exp = _py_search_by_bow(oracle, fb, f_desc, kb, k_desc, cand_ok, query_ok)
+            assert len(exp) == len(r["kf_idx"]) and len(exp) > 200
+            assert [e[0] for e in exp] == list(r["kf_idx"]) and [e[1] for e in exp] == list(r["best_idx"])
+            assert [e[2] for e in exp] == list(r["best_dist"]) and [e[4] for e in exp] == list(r["n_cand"])
+            assert np.array_equal(np.array([e[3] for e in exp], np.float32), r["ratio"], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_cuda_search_by_bow_equals_oracle(oracle):
+    c = synth.KITTI
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], 8, 17)
+    l2, r2 = synth.synth_stereo_pair(c["height"], c["width"] + 6, 8, 17)  # the "keyframe": the same scene shifted by 6 px
+    cam = api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"])
+    ctx = api.Context(c["width"], c["height"], 2000, 8, 1.2, camera=cam)
+    kfr = ctx.stereo_frame(np.ascontiguousarray(l2[:, 6:]), np.ascontiguousarray(r2[:, 6:]))
+    k_kps, k_desc = kfr.kps_left.copy(), kfr.desc_left.copy()
+    voc = synth.synth_vocabulary(10, 3, 3)
+    rng = np.random.default_rng(4)
+    O0 = oracle.Vocabulary(**voc)
+    leaves = np.nonzero(O0.word_id >= 0)[0]
+    voc["desc"][leaves[:900] - 1] = k_desc[rng.choice(len(k_desc), 900, replace=False)]  # leaves that resemble the scene's descriptors
+    O, V = oracle.Vocabulary(**voc), api.Vocabulary(ctx, **voc)
+    k_bow = ctx.bow_transform(V, levelsup=2)
+    fr = ctx.stereo_frame(left, right)
+    with pytest.raises(ValueError):
+        ctx.search_by_bow(k_bow, k_desc)  # the new frame's FeatureVector is not resident yet
+    f_bow = ctx.bow_transform(V, levelsup=2)
+    e_f, e_k = oracle.bow_transform(O, fr.desc_left, 2), oracle.bow_transform(O, k_desc, 2)
+    kf_ok = (rng.random(len(k_desc)) < 0.7).astype(np.uint8)
+    fr_ok = (rng.random(2000) < 0.6).astype(np.uint8)
+    for qm, cm in [(None, None), (kf_ok, fr_ok)]:
+        got = ctx.search_by_bow(k_bow, k_desc, qm, cm)
+        exp = oracle.search_by_bow(e_f, fr.desc_left, e_k, k_desc, cm, qm)
+        for key in exp:
+            assert np.array_equal(got[key], exp[key], equal_nan=True), key
+        assert len(got["kf_idx"]) > 300
+    # the reference-shaped entry point: thresholds + verifyAngle, composed from the oracle
+    frame = api.Frame(fr.kps_left, fr.desc_left, None, None, fr.u_right, fr.depth, fr.n_matches, {"ctx": ctx})
+    m = api.ORBMatcher(0.6, True)
+    got = m.searchByBow(frame, V, k_kps, k_desc, k_bow, kf_ok.astype(bool), ~fr_ok.astype(bool), levelsup=2)
+    e = oracle.search_by_bow(e_f, fr.desc_left, e_k, k_desc, fr_ok, kf_ok)
+    keep = ~((e["best_dist"] > 50) | (e["ratio"] > np.float32(0.6)))
+    vq, vt, vd = oracle.verify_angle(e["best_idx"][keep], e["kf_idx"][keep], e["best_dist"][keep].astype(np.float32), fr.kps_left, k_kps)
+    assert np.array_equal(got[:, 0], vq) and np.array_equal(got[:, 1], vt) and np.array_equal(got[:, 2], vd.astype(np.int32)) and len(got) > 50
+    V.close()
+    ctx.close()
