@@ -14,7 +14,7 @@ names = {"pyramid_blur": "pyramid_blur", "fast_cells": "fast_cells", "quadtree":
 out = {}
 for blk in txt.split("## ")[1:]:
     name = blk.split("(")[0].strip().replace("_kernel", "")
-    name = re.sub(r"<.*>", "", name.split("::")[-1])
+    name = re.sub(r"<.*>", "", name.split("::")[-1]).replace("void ", "").strip()
     m = re.search(r"traffic = dram read \+ write\s+([\d.]+) (\w+)", blk)
     t = re.search(r"gpu__time_duration.sum\s+([\d.]+) (\w+)", blk)
     i = re.search(r"smsp__issue_active.avg.pct_of_peak_sustained_active\s+([\d.]+)", blk)
