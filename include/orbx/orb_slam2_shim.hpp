@@ -357,7 +357,7 @@ class ORBMatcher
 {
 public:
   typedef std::shared_ptr<ORBMatcher> SharedPtr;
-  explicit ORBMatcher(float ratio = 0.6f, bool checkOri = true) : mfRatio(ratio), mbCheckOri(checkOri) { (void)mbCheckOri; }
+  explicit ORBMatcher(float ratio = 0.6f, bool checkOri = true) : mfRatio(ratio), mbCheckOri(checkOri) {}
   // fills mvFeatsRightU / mvDepths (-1 = no match) and returns the match count, like src/ORBMatcher.cc:18-81.  The GPU
   // computed them together with the features (one launch sequence per frame); this call publishes them.
   int searchByStereo(Frame::SharedPtr pFrame)
@@ -437,6 +437,50 @@ public:
     std::vector<AreaMatch> r = searchInArea(pFrame1, q, radius, lo, hi, qd, bFuse ? nullptr : &hasMp1);
     for (std::size_t i = 0; i < r.size(); ++i)
       if (r[i].nCandidates > 0 && r[i].ratio < mfRatio && r[i].distance < mnMinThreshold) matches.emplace_back(r[i].idx, src[i], (float)r[i].distance);
+    return (int)matches.size();
+  }
+
+  // searchByBow(pFrame, pKframe, matches, bAddMPs, bLoop) (src/ORBMatcher.cc:170-255).  The keyframe is given by its left
+  // keypoints / descriptors and its FeatureVector (from Frame::computeBow when it was the current frame); kfGood[i] /
+  // frameGood[i] = "the feature has a good map point" (for bAddMPs: "... that is in the map").  pFrame must be the
+  // context's most recent frame; its BoW is computed here like pFrame->computeBow() (:172).
+  int searchByBow(Frame::SharedPtr pFrame, const Vocabulary &voc, const std::vector<cv::KeyPoint> &kfKeyPoints, const std::vector<cv::Mat> &kfDescriptors,
+                  const FeatureVector &kfFeatVec, const std::vector<bool> &kfGood, const std::vector<bool> &frameGood, std::vector<cv::DMatch> &matches,
+                  bool bAddMPs = false, bool bLoop = false, int levelsup = 4)
+  {
+    matches.clear();
+    BowVector bv;
+    FeatureVector fv;
+    pFrame->computeBow(voc, bv, fv, levelsup);
+    std::vector<int32_t> nodes, start(1, 0), feats;
+    for (auto &kv : kfFeatVec)
+    {
+      nodes.push_back((int32_t)kv.first);
+      for (unsigned i : kv.second) feats.push_back((int32_t)i);
+      start.push_back((int32_t)feats.size());
+    }
+    const std::size_t nk = kfDescriptors.size(), N = (std::size_t)pFrame->orbx_capacity(), nl = feats.size();
+    std::vector<uint8_t> kd(nk * 32), qok(nk, 0), cok(N, 0);
+    for (std::size_t i = 0; i < nk; ++i)
+    {
+      std::memcpy(&kd[32 * i], kfDescriptors[i].data, 32);
+      const bool g = i < kfGood.size() && kfGood[i];
+      qok[i] = bAddMPs ? !g : (bLoop ? 1 : g); // :195-212
+    }
+    for (std::size_t i = 0; i < N; ++i)
+    {
+      const bool g = i < frameGood.size() && frameGood[i];
+      cok[i] = bLoop ? 1 : !g; // :216-233 (bAddMPs and the default mode both want frame features without a map point)
+    }
+    std::vector<int32_t> idx(nl), dist(nl), nc(nl);
+    std::vector<float> ratio(nl);
+    detail::check(pFrame->mCtx.get(),
+                  orbx_search_by_bow(pFrame->mCtx.get(), 0, (int)nodes.size(), nodes.data(), start.data(), feats.data(), kd.data(), (int)nk, qok.data(),
+                                     cok.data(), idx.data(), dist.data(), ratio.data(), nc.data()),
+                  "orbx_search_by_bow");
+    for (std::size_t e = 0; e < nl; ++e)
+      if (nc[e] > 0 && !(dist[e] > mnMinThreshold || ratio[e] > mfRatio)) matches.emplace_back(idx[e], feats[e], (float)dist[e]); // :240-245
+    if (mbCheckOri) verifyAngle(pFrame, matches, pFrame->getLeftKeyPoints(), kfKeyPoints);
     return (int)matches.size();
   }
 

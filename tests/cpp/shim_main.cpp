@@ -130,6 +130,12 @@ int main(int argc, char **argv)
           put(out, (int32_t)kv.second.size());
           for (unsigned i : kv.second) put(out, (int32_t)i);
         }
+        // ORBMatcher::searchByBow of the frame against itself as the "keyframe" (loop mode: no map-point masks)
+        std::vector<cv::DMatch> bm;
+        ORBMatcher bowMatcher(0.6f, true);
+        int nbm = bowMatcher.searchByBow(f, voc, f->getLeftKeyPoints(), f->getLeftDescriptor(), fv, {}, {}, bm, false, true);
+        put(out, (int32_t)nbm);
+        for (auto &m : bm) put(out, (int32_t)m.queryIdx), put(out, (int32_t)m.trainIdx), put(out, m.distance);
       }
     }
     else if (mode == "rgbd")

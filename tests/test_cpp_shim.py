@@ -128,6 +128,13 @@ def test_shim_stereo_matches_oracle(shim_binary, template_path, oracle, tmp_path
         assert rd.i32() == e["fv_nodes"][j]
         m = rd.i32()
         assert np.array_equal(rd.arr(np.int32, m), e["fv_feats"][e["fv_start"][j] : e["fv_start"][j + 1]])
+    # ORBMatcher::searchByBow (frame against itself, loop mode) == the oracle's composition + verifyAngle
+    sb = oracle.search_by_bow(e, dl, e, dl)
+    keep = ~((sb["best_dist"] > 50) | (sb["ratio"] > np.float32(0.6)))
+    vq, vt, vd = oracle.verify_angle(sb["best_idx"][keep], sb["kf_idx"][keep], sb["best_dist"][keep].astype(np.float32), kl, kl)
+    nbm = rd.i32()
+    gm = rd.arr(np.dtype([("q", "<i4"), ("t", "<i4"), ("d", "<f4")]), nbm)
+    assert nbm == len(vq) and nbm > 100 and np.array_equal(gm["q"], vq) and np.array_equal(gm["t"], vt) and np.array_equal(gm["d"], vd)
 
 
 @pytest.mark.gpu
