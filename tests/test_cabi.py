@@ -71,3 +71,34 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("a CUDA device is present")
     with pytest.raises(api.OrbxCudaError):
         api.Context(1241, 376)
+
+
+def test_header_is_valid_c99_and_links_against_the_library(tmp_path):
+    """include/orbx.h is a plain C header (the boundary a cgo / JNI / ctypes binding would consume): compile a C99 client
+    with -pedantic and link it against liborbx.so; running it without a GPU must fail loudly with ORBX_ERR_NO_DEVICE."""
+    import subprocess
+
+    api.load_library()
+    src = tmp_path / "client.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "orbx.h"\n'
+        "int main(void) {\n"
+        "  orbx_config cfg; orbx_ctx *ctx = 0; orbx_default_config(&cfg);\n"
+        "  cfg.width = 320; cfg.height = 240; cfg.max_batch = 1;\n"
+        "  int rc = orbx_create(&cfg, &ctx);\n"
+        '  printf("%d %s %d\\n", rc, orbx_status_string(rc), (int)sizeof(orbx_area_query));\n'
+        "  if (ctx) orbx_destroy(ctx);\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "client"
+    libdir = os.path.join(ROOT, "orb_slam2_ros2_b200")
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lorbx", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()
+    import torch
+
+    assert int(out[-1]) == 24
+    if not torch.cuda.is_available():
+        assert int(out[0]) == api.ORBX_ERR_NO_DEVICE
+    else:
+        assert int(out[0]) == 0
