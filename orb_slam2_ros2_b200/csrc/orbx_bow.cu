@@ -230,7 +230,8 @@ int bow_configure(int n_features)
 {
   const size_t bytes = (size_t)bow_sort_size(n_features) * sizeof(unsigned long long);
   if (bytes <= 48 * 1024) return 0;
-  return cudaFuncSetAttribute(bow_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : -1;
+  static SmemOptIn state;
+  return raise_dynamic_smem(bow_assemble_kernel, state, bytes);
 }
 
 } // namespace orbx

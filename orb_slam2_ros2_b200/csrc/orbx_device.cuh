@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/orbx.h"
 
 namespace orbx
@@ -226,5 +228,24 @@ void launch_bow_assemble(const Params &p, const BowArgs &a, int n_frames, cudaSt
 int bow_configure(int n_features); // opt in to the dynamic shared memory of the assemble kernel
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells);
 int quadtree_configure(size_t smem_bytes); // opt in to large dynamic shared memory
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel (per device), not to a context: it is only ever RAISED, so a
+// second context with a smaller configuration cannot shrink the limit under a live one (launches of the larger context would
+// fail with "invalid argument").  `state` = the caller's per-kernel high-water marks, one per device.
+struct SmemOptIn
+{
+  std::mutex mu;
+  int high[64] = {};
+};
+template <class Kernel> int raise_dynamic_smem(Kernel kernel, SmemOptIn &state, size_t bytes)
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  std::lock_guard<std::mutex> lock(state.mu);
+  if ((size_t)state.high[dev] >= bytes) return 0;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+  state.high[dev] = (int)bytes;
+  return 0;
+}
 
 } // namespace orbx

@@ -1473,7 +1473,8 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
 
 int quadtree_configure(size_t smem_bytes)
 {
-  return (int)cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  static SmemOptIn state;
+  return raise_dynamic_smem(quadtree_kernel, state, smem_bytes);
 }
 
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s)

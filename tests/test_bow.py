@@ -143,7 +143,21 @@ def test_cuda_bow_batch_device_rgbd_and_empty(oracle):
         got = dict(bow_ids=ids[f, : nb[f]], bow_vals=vals[f, : nb[f]], fv_nodes=fnodes[f, : nf[f]], fv_start=fstart[f, : nf[f] + 1],
                    fv_feats=ffeats[f, : fstart[f, nf[f]]])
         _same(got, e, f"frame {f}")
+    # searchByBow against a frame of the batch other than frame 0 (frame 2 vs frame 0's features as the "keyframe")
+    e2, e0 = oracle.bow_transform(O, host.desc_left[2][: host.n_left[2]], 4), oracle.bow_transform(O, host.desc_left[0][: host.n_left[0]], 4)
+    got = ctx.search_by_bow(e0, host.desc_left[0][: host.n_left[0]], frame=2)
+    exp = oracle.search_by_bow(e2, host.desc_left[2][: host.n_left[2]], e0, host.desc_left[0][: host.n_left[0]])
+    for key in exp:
+        assert np.array_equal(got[key], exp[key], equal_nan=True), key
     ctx.set_stream(None)
+    # RGB-D frames (one image per frame): same transform
+    t = synth.TUM
+    rg = api.Context(t["width"], t["height"], 1000, 8, 1.2, camera=api.Camera(t["fx"], t["fy"], t["cx"], t["cy"], t["bl"], (0.0,) * 5, t["depth_scale"]))
+    fr = rg.rgbd_frame(synth.synth_image(t["height"], t["width"], 3), synth.synth_depth_u16(t["height"], t["width"], 3, t["depth_scale"]))
+    Vr = api.Vocabulary(rg, **voc)
+    _same(rg.bow_transform(Vr), oracle.bow_transform(O, fr.desc, 4), "rgbd")
+    Vr.close()
+    rg.close()
     # a frame without keypoints: empty vectors
     ctx.stereo_frame(np.full((c["height"], c["width"]), 80, np.uint8), np.full((c["height"], c["width"]), 80, np.uint8))
     got = ctx.bow_transform(V)
