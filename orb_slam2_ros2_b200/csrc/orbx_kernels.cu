@@ -302,53 +302,54 @@ constexpr int kMapPitch = kZoneMax + 4;       // 68
 
 __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
 {
+  // m = max over the 16 arcs of 9 contiguous ring pixels of min(v - r) ("ring darker") and of min(r - v) ("ring brighter").
+  // Both chains run in ONE register per ring pixel, as two signed 16-bit halves on the packed min/max unit
+  // (VIMNMX(3).S16x2).  With G = 2 (r - v) + 1 (odd, so its sign is never ambiguous) one multiply-add packs
+  //   x = G * 0xFFFF = (G << 16) - G :  low half = -G = 2 (v - r) - 1,  high half = G - [G > 0]   (borrow of the low half)
+  // and both halves are strictly monotone in v - r / r - v, so min / max commute with the packing; the two transforms
+  // are undone once, on the result.  (Plain int chains: twice the instructions, and nvcc 12.9 for sm_100a mis-folds
+  // "max(best, max(mn9, -mx9))" into a 3-input VIMNMX3 that drops the negation.)
   constexpr int P = kPatPitch;
-  const int v = c[0];
-  int d[16];
-  d[0] = v - c[3 * P];
-  d[1] = v - c[3 * P + 1];
-  d[2] = v - c[2 * P + 2];
-  d[3] = v - c[P + 3];
-  d[4] = v - c[3];
-  d[5] = v - c[-P + 3];
-  d[6] = v - c[-2 * P + 2];
-  d[7] = v - c[-3 * P + 1];
-  d[8] = v - c[-3 * P];
-  d[9] = v - c[-3 * P - 1];
-  d[10] = v - c[-2 * P - 2];
-  d[11] = v - c[-P - 3];
-  d[12] = v - c[-3];
-  d[13] = v - c[P - 3];
-  d[14] = v - c[2 * P - 2];
-  d[15] = v - c[3 * P - 1];
-  // Sliding minimum over 9 of 16 by doubling (2, 4, 8, +1), once for d (ring darker than the centre) and once for
-  // e = -d (ring brighter).  NB: written with two explicit min-chains instead of "-max(d...)": nvcc 12.9 for sm_100a
-  // folds the negated 3-input max (VIMNMX3) incorrectly and drops the negation.
-  int e[16];
+  const unsigned C = (unsigned)(1 - 2 * (int)c[0]) * 0xFFFFu;
+  unsigned x[16];
+  x[0] = c[3 * P] * 0x1FFFEu + C;
+  x[1] = c[3 * P + 1] * 0x1FFFEu + C;
+  x[2] = c[2 * P + 2] * 0x1FFFEu + C;
+  x[3] = c[P + 3] * 0x1FFFEu + C;
+  x[4] = c[3] * 0x1FFFEu + C;
+  x[5] = c[-P + 3] * 0x1FFFEu + C;
+  x[6] = c[-2 * P + 2] * 0x1FFFEu + C;
+  x[7] = c[-3 * P + 1] * 0x1FFFEu + C;
+  x[8] = c[-3 * P] * 0x1FFFEu + C;
+  x[9] = c[-3 * P - 1] * 0x1FFFEu + C;
+  x[10] = c[-2 * P - 2] * 0x1FFFEu + C;
+  x[11] = c[-P - 3] * 0x1FFFEu + C;
+  x[12] = c[-3] * 0x1FFFEu + C;
+  x[13] = c[P - 3] * 0x1FFFEu + C;
+  x[14] = c[2 * P - 2] * 0x1FFFEu + C;
+  x[15] = c[3 * P - 1] * 0x1FFFEu + C;
+  unsigned a3[16]; // min over ring pixels k .. k + 2
 #pragma unroll
-  for (int k = 0; k < 16; ++k) e[k] = -d[k];
-  int a2[16], b2[16], a4[16], b4[16];
+  for (int k = 0; k < 16; ++k) a3[k] = __vmins2(__vmins2(x[k], x[(k + 1) & 15]), x[(k + 2) & 15]);
+  unsigned best = 0x80008000u;
 #pragma unroll
-  for (int k = 0; k < 16; ++k)
-  {
-    a2[k] = min(d[k], d[(k + 1) & 15]);
-    b2[k] = min(e[k], e[(k + 1) & 15]);
-  }
-#pragma unroll
-  for (int k = 0; k < 16; ++k)
-  {
-    a4[k] = min(a2[k], a2[(k + 2) & 15]);
-    b4[k] = min(b2[k], b2[(k + 2) & 15]);
-  }
-  int best = -256;
-#pragma unroll
-  for (int k = 0; k < 16; ++k)
-  {
-    const int a9 = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);
-    const int b9 = min(min(b4[k], b4[(k + 4) & 15]), e[(k + 8) & 15]);
-    best = max(best, max(a9, b9));
-  }
-  return best;
+  for (int k = 0; k < 16; ++k) best = __vmaxs2(best, __vmins2(__vmins2(a3[k], a3[(k + 3) & 15]), a3[(k + 6) & 15])); // k .. k + 8
+  const int lo = (int)(short)(best & 0xffffu), hi = (int)best >> 16;
+  const int darker = (lo + 1) >> 1;                      // lo = 2 m - 1
+  const int brighter = (hi + (hi >= 0 ? 1 : 0) - 1) >> 1; // hi = G - [G > 0], G = 2 m + 1
+  return max(darker, brighter);
+}
+
+// shared-memory accesses of the compaction lists by 32-bit shared address: one LDS / STS each, no generic-pointer arithmetic
+__device__ __forceinline__ void sts_u16_if(uint32_t addr, uint32_t v, bool pred)
+{
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p st.shared.u16 [%0], %1;\n}" ::"r"(addr), "h"((unsigned short)v), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
 }
 
 // ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -------------------------------------------------------------
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
   const uint8_t *pat0 = s_pat + 3 * kPatPitch + 3 + (c.x0 & 15); // zone pixel (0,0); 15 + 65 <= the 80-byte box
 
   bool patch_ready = false;
-  uint16_t *my_cand = s_cand + wid * kCandSeg;
+  const uint32_t cand0_u32 = smem_u32(s_cand), cand_u32 = cand0_u32 + 2u * (uint32_t)(wid * kCandSeg); // this warp's segment
   unsigned long long keep = 0ull;
 
   // cv::FAST(cell, iniThFAST); only if its post-NMS list is empty, cv::FAST(cell, minThFAST) (src/ORBExtractor.cc:365-367).
@@ -447,17 +448,16 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
     }
 
     // Stage 1 (every zone pixel): two adjacent compass ring pixels are brighter (darker) than the centre by more than t
-    // -- a necessary condition for a 9-arc.  Survivors go to a per-warp candidate segment (warp-local counter, no
-    // atomics), so that the later stages run on dense lanes.
-    int wcnt = 0;
+    // -- a necessary condition for a 9-arc.  Survivors go to a per-warp candidate segment (warp-local end address, no
+    // atomics), so that the next stage runs on dense lanes.
     const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t wend = cand_u32; // shared address one past the warp's last candidate
     for (int zx0 = 0; zx0 < zw; zx0 += 32) // one chunk for every cell narrower than 33 px (the usual 30-32)
     {
       const int zx = zx0 + lane;
-      const bool valid = zx < zw;
-      // lanes beyond the zone read inside the patch buffer (pitch 80 > 3 + 64 + 3) and are masked out of the vote
+      const int tl = zx < zw ? t : 0x10000; // lanes beyond the zone read inside the patch buffer (pitch 80 > 3 + 64 + 3) and can never pass
       const uint8_t *q = pat0 + wid * kPatPitch + min(zx, kZoneMax - 1);
-      int code = wid * kZoneMax + zx;
+      uint32_t code = wid * kZoneMax + zx;
 #pragma unroll 2
       for (int zy = wid; zy < zh; zy += kFastWarps, q += kFastWarps * kPatPitch, code += kFastWarps * kZoneMax)
       {
@@ -466,75 +466,48 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
         // 9 contiguous ring pixels always contain two ADJACENT compass pixels, i.e. one of {0, 8} and one of {4, 12}:
         // brighter arc => min(max(r0, r8), max(r4, r12)) > v + t, darker arc => max(min(r0, r8), min(r4, r12)) < v - t
         const int hi2 = min(max(r0, r8), max(r4, r12)), lo2 = max(min(r0, r8), min(r4, r12));
-        const bool cand = valid & (max(hi2 - v, v - lo2) > t);
+        const bool cand = max(hi2 - v, v - lo2) > tl;
         const unsigned m = __ballot_sync(FULL, cand);
-        if (m)
-        {
-          if (cand) my_cand[wcnt + __popc(m & lt_mask)] = (uint16_t)code;
-          wcnt += __popc(m);
-        }
+        sts_u16_if(wend + 2u * __popc(m & lt_mask), code, cand);
+        wend += 2u * __popc(m);
       }
     }
+    const int wcnt = (int)(wend - cand_u32) >> 1;
     __syncwarp();
 
-    // Stage 2 (stage-1 survivors, dense lanes): the exact corner test.  One bit per ring pixel (sign of hi - r / r - lo
-    // shifted in with a funnel shift), then "9 circularly consecutive bits" by and-doubling.  The segment is compacted
-    // in place to the true corners (every chunk is read before it is overwritten).
-    int ccnt = 0;
+    // Stage 2 (stage-1 survivors, dense lanes): the arc value m decides (corner at t <=> m > t) and is the score the
+    // non-max suppression needs, so it goes straight into the map.  The segment is compacted in place to the corners
+    // (every chunk is read before it is overwritten).
+    uint32_t cend = cand_u32;
     for (int k0 = 0; k0 < wcnt; k0 += 32)
     {
       const int k = k0 + lane;
       bool corner = false;
-      int i = 0;
+      uint32_t i = 0;
       if (k < wcnt)
       {
-        i = my_cand[k];
-        const uint8_t *q = pat0 + (i >> 6) * kPatPitch + (i & (kZoneMax - 1));
-        const int v = q[0], hi = v + t, lo = v - t;
-        constexpr int P = kPatPitch;
-        const int ro[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1, -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
-        unsigned mb = 0u, md = 0u;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-        {
-          const int r = q[ro[j]];
-          mb = __funnelshift_l((unsigned)(hi - r), mb, 1); // shifts in 1 iff r > v + t
-          md = __funnelshift_l((unsigned)(r - lo), md, 1); // shifts in 1 iff r < v - t
-        }
-        auto run9 = [](unsigned m16) -> bool {
-          const unsigned m = m16 | (m16 << 16);
-          const unsigned a = m & (m >> 1), b = a & (a >> 2), cc = b & (b >> 4);
-          return ((cc & (m >> 8)) & 0xffffu) != 0u;
-        };
-        corner = run9(mb) || run9(md);
+        i = lds_u16(cand_u32 + 2u * k);
+        const int zy = i >> 6, zx = i & (kZoneMax - 1);
+        const int m = fast_arc_value(pat0 + zy * kPatPitch + zx);
+        corner = m > t;
+        if (corner) s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)m;
       }
       __syncwarp();
       const unsigned m = __ballot_sync(FULL, corner);
-      if (corner) my_cand[ccnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
-      ccnt += __popc(m);
+      sts_u16_if(cend + 2u * __popc(m & lt_mask), i, corner);
+      cend += 2u * __popc(m);
     }
-    __syncwarp();
 
-    // Stages 3 and 4 run over the block-wide corner list (the four warp segments back to back) so that the lanes stay
+    // The suppression runs over the block-wide corner list (the four warp segments back to back) so that the lanes stay
     // dense even when a warp found only a handful of corners: corner k lives in segment w at k - first[w].
     static_assert(kFastWarps == 4, "corner_at assumes four warp segments");
-    if (lane == 0) s_ccnt[wid] = ccnt;
+    if (lane == 0) s_ccnt[wid] = (int)(cend - cand_u32) >> 1;
     __syncthreads();
     const int f1 = s_ccnt[0], f2 = f1 + s_ccnt[1], f3 = f2 + s_ccnt[2], n_corners = f3 + s_ccnt[3];
     auto corner_at = [&](int k) -> int {
-      const int w = (k >= f1) + (k >= f2) + (k >= f3);
-      const int first = w == 0 ? 0 : (w == 1 ? f1 : (w == 2 ? f2 : f3));
-      return s_cand[w * kCandSeg + (k - first)];
+      const int adj = k >= f3 ? 3 * kCandSeg - f3 : (k >= f2 ? 2 * kCandSeg - f2 : (k >= f1 ? kCandSeg - f1 : 0));
+      return (int)lds_u16(cand0_u32 + 2u * (uint32_t)(k + adj));
     };
-
-    // Stage 3 (true corners only): the arc value m, needed for the scores and the non-max suppression
-    for (int k = tid; k < n_corners; k += kFastThreads)
-    {
-      const int i = corner_at(k);
-      const int zy = i >> 6, zx = i & (kZoneMax - 1);
-      s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)fast_arc_value(pat0 + zy * kPatPitch + zx); // > t by stage 2
-    }
-    __syncthreads();
 
     // Non-max suppression: keep  <=>  score m - 1 > the scores of all 8 neighbours (strict), where a neighbour that is not
     // a corner at this threshold (map 0) scores 0; the map q -> (q ? q - 1 : 0) is monotone, so only the largest neighbour
@@ -554,8 +527,23 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
     if (__syncthreads_or(keep != 0ull)) break; // fallback iff the post-NMS list is empty (:366)
   }
 
-  int total;
-  int off = block_exclusive_scan<kFastThreads>(__popcll(keep), total, s_warp); // thread <-> zone row: row-major output order
+  // thread <-> zone row (zh <= 64: warps 0 and 1), row-major output order: exclusive scan of the rows' corner counts
+  static_assert(kZoneMax <= 64, "the output scan covers two warps");
+  const int row_cnt = __popcll(keep);
+  int inc = row_cnt;
+  if (wid < 2)
+  {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int up = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += up;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+  }
+  __syncthreads();
+  const int total = s_warp[0] + s_warp[1];
+  int off = inc - row_cnt + (wid == 1 ? s_warp[0] : 0);
   uint32_t *slot = p.cell_list + (size_t)img * p.cell_entries + c.slot;
   const uint32_t y = (uint32_t)(c.y0 - kEdge + 3 + tid); // ROI coordinates (:368-372)
   while (keep)
