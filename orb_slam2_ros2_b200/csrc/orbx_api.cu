@@ -367,16 +367,6 @@ int build_tables(orbx_ctx *c)
   if ((rc = dev_upload(c, &p.tab_coef, tab_coef))) return rc;
   if ((rc = dev_upload(c, &p.strips_fx, strips))) return rc;
   if ((rc = dev_upload(c, &p.pattern, pat))) return rc;
-  // the same table as doubles (rotateTemplate multiplies in double, :534-540), laid out for the BRIEF kernel: bit b = lane * 8 + k,
-  // point pt of pair b at [(pt * 8 + k) * 32 + lane] so that the 32 lanes of a warp read consecutive 16-byte entries
-  std::vector<double2> patd(512);
-  for (int b = 0; b < 256; ++b)
-  {
-    const int lane = b >> 3, k = b & 7;
-    patd[(size_t)(0 * 8 + k) * 32 + lane] = make_double2((double)pat[b].x, (double)pat[b].y);
-    patd[(size_t)(1 * 8 + k) * 32 + lane] = make_double2((double)pat[b].z, (double)pat[b].w);
-  }
-  if ((rc = dev_upload(c, &p.pattern_d, patd))) return rc;
 
   // algorithmic bytes: per image P + 60 N; stereo step 2*60 N + 352 N + 16 N
   int64_t P = 0;

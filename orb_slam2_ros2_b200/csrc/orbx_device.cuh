@@ -97,7 +97,6 @@ struct Params
   const short2 *tab_coef; // resize 11-bit coefficients
   const long long *strips_fx; // root strip column bounds, 24.40 fixed point (exact: they are float-rounded values)
   const char4 *pattern;   // 256 x (x1, y1, x2, y2)
-  const double2 *pattern_d; // the same as doubles, [point 0/1][k = bit & 7][lane = bit >> 3] (x, y)
   // inputs
   const uint8_t *in_left, *in_right;
   size_t in_stride, in_frame_stride;

@@ -1477,6 +1477,9 @@ void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStrea
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3}; // initMaxU (:217-236), radius 15
 
 constexpr int kBriefWarps = 8;
+constexpr int kBriefReach = 18;                          // cvRound of the largest rotated pattern radius, |(13, 13)| = 18.38
+constexpr int kBriefPatchRows = 2 * kBriefReach + 1;     // 37
+constexpr uint32_t kBriefPatchPitch = 40;                // bytes: 37 + up to 3 bytes of alignment shift
 
 __device__ __forceinline__ void undistort_point(const Params &p, float u, float v, float &uo, float &vo)
 {
@@ -1515,23 +1518,32 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a_u8x4, uint32_t b_s8x4, int 
 // batches use 8 (throughput), a handful of images 2 (shorter warps: single-frame latency).
 template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const Params p)
 {
-  // byte masks of the radius-15 disc: row |dy| covers columns |dx| <= umax[|dy|]; [|dy|][word k] selects bytes 4k..4k+3 of
-  // the 32-byte row that starts at dx = -15 (byte 31 is never part of the disc)
-  __shared__ __align__(16) uint32_t s_disc[16][8];
+  // Per-lane DP4A weights of the radius-15 disc for the moment pass below (lane <-> word wk of row 3 i + rg, see there):
+  // byte b of s_wx[i][lane] = dx of that byte if it lies inside the disc (|dx| <= umax[|dy|]), else 0; s_wy: dy likewise.
+  __shared__ uint32_t s_wx[11][32], s_wy[11][32];
+  for (int t = threadIdx.x; t < 11 * 32; t += kBriefWarps * 32)
   {
-    const int t = threadIdx.x;
-    if (t < 128)
+    const int i = t >> 5, ln = t & 31, g = ln / 9, k = ln - 9 * g, r = 3 * i + g, dy = r - 15;
+    uint32_t wx = 0, wy = 0;
+    if (g < 3 && k < 8 && r < 31)
     {
-      const int ady = t >> 3, k = t & 7;
-      uint32_t m = 0;
 #pragma unroll
       for (int b = 0; b < 4; ++b)
       {
-        const int dx = 4 * k + b - 15;
-        if (dx <= 15 && abs(dx) <= c_umax[ady]) m |= 0xffu << (8 * b);
+        const int dx = 4 * k + b - 15; // byte 31 of the 32-byte row (dx = 16) is never part of the disc
+        if (dx <= 15 && abs(dx) <= c_umax[abs(dy)]) wx |= (uint32_t)(dx & 0xff) << (8 * b), wy |= (uint32_t)(dy & 0xff) << (8 * b);
       }
-      s_disc[ady][k] = m;
     }
+    s_wx[i][ln] = wx;
+    s_wy[i][ln] = wy;
+  }
+  // BRIEF pattern, one word (x1, y1, x2, y2 as signed bytes) per pair: bit b = lane * 8 + k at [k][lane]
+  __shared__ uint32_t s_pat8[8][32];
+  {
+    const int b = threadIdx.x;
+    static_assert(kBriefWarps * 32 == 256, "one thread per pattern pair");
+    const char4 q = p.pattern[b];
+    s_pat8[b & 7][b >> 3] = ((uint32_t)(uint8_t)q.x | ((uint32_t)(uint8_t)q.y << 8) | ((uint32_t)(uint8_t)q.z << 16) | ((uint32_t)(uint8_t)q.w << 24));
   }
   __syncthreads();
 
@@ -1559,15 +1571,12 @@ template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5
 
   // Pass 1, keypoint by keypoint: getGrayCentroid (:465-487), moments over the radius-15 disc of the un-blurred level.
   // The disc's 31 rows are fetched as aligned words, 3 rows x 9 words per warp request (3 cache lines); a lane takes its
-  // word and the next one (from the neighbour lane), shifts them to the row start and takes both row sums with DP4A:
-  // sum(I) against the row's byte mask and sum(dx * I) against the masked signed weights dx = 4k - 15 .. 4k - 12.  Every
-  // level pitch is a multiple of 4, so the shift is the same for all rows.  Lane j keeps keypoint j's entry and moments.
+  // word and the next one (from the neighbour lane), shifts them to the row start and takes both moments with DP4A against
+  // the lane's signed weights (dx resp. dy inside the disc, 0 outside; tables above).  Every level pitch is a multiple of
+  // 4, so the shift is the same for all rows.  Lane j keeps keypoint j's entry and moments.
   uint32_t my_e = 0;
   int my_level = 0, my_m10 = 0, my_m01 = 0;
-  const int rg = lane / 9, wk = lane - 9 * rg; // lanes 27..31: rg == 3, idle
-  const int kw = min(wk, 7);
-  const uint32_t wdx = ((uint32_t)((4 * kw - 15) & 0xff)) | ((uint32_t)((4 * kw - 14) & 0xff) << 8) | ((uint32_t)((4 * kw - 13) & 0xff) << 16) |
-                       ((uint32_t)((4 * kw - 12) & 0xff) << 24);
+  const int rg = lane / 9, wk = lane - 9 * rg; // lanes 27..31: rg == 3, idle (zero weights)
 #pragma unroll 1
   for (int j = 0; j < n_here; ++j)
   {
@@ -1580,26 +1589,22 @@ template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5
     const int x = (int)(e & 0xfffu), y = (int)((e >> 12) & 0xfffu);
     const int pitch = L.pitch;
     const uint8_t *row0 = pyr_img + L.pyr_off + (size_t)(y - 15) * pitch + (x - 15);
-    const uint32_t sh = ((uint32_t)(size_t)row0 & 3u) * 8u;
-    const uint32_t *w0 = reinterpret_cast<const uint32_t *>((size_t)row0 & ~(size_t)3) + wk;
-    const int pitch4 = pitch >> 2;
+    const uint32_t mis = (uint32_t)(size_t)row0 & 3u, sh = mis * 8u;
+    // idle lanes re-read rows 0..2
+    const uint8_t *wp = row0 - mis + 4 * wk + (size_t)min(rg, 2) * pitch;
+    const uint32_t pitch3 = 3u * (uint32_t)pitch;
     uint32_t a[11];
 #pragma unroll
-    for (int i = 0; i < 11; ++i)
-    {
-      const int r = 3 * i + rg;
-      a[i] = (rg < 3 && r < 31) ? w0[(size_t)r * pitch4] : 0u;
-    }
+    for (int i = 0; i < 10; ++i) a[i] = __ldg(reinterpret_cast<const uint32_t *>(wp + (uint64_t)pitch3 * (uint32_t)i)); // one IMAD.WIDE per address
+    a[10] = __ldg(reinterpret_cast<const uint32_t *>(row0 - mis + 4 * wk + 30 * (size_t)pitch)); // row 30: only the rg == 0 lanes carry weights
     int m10 = 0, m01 = 0;
 #pragma unroll
     for (int i = 0; i < 11; ++i)
     {
-      const int r = min(3 * i + rg, 30), dy = r - 15;
       const uint32_t nxt = __shfl_down_sync(FULL, a[i], 1);
       const uint32_t v = __funnelshift_r(a[i], nxt, sh);
-      const uint32_t msk = (rg < 3 && wk < 8 && 3 * i + rg < 31) ? s_disc[abs(dy)][kw] : 0u;
-      m10 = dp4a_u8_s8(v, wdx & msk, m10);
-      m01 += dy * (int)__dp4a(v, msk & 0x01010101u, 0u);
+      m10 = dp4a_u8_s8(v, s_wx[i][lane], m10);
+      m01 = dp4a_u8_s8(v, s_wy[i][lane], m01);
     }
     m10 = __reduce_add_sync(FULL, m10);
     m01 = __reduce_add_sync(FULL, m01);
@@ -1613,6 +1618,9 @@ template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5
 
   // Pass 2, keypoint by keypoint: computeBRIEF (:427-456) with rotateTemplate (:534-540): double products, float result,
   // float add, round-half-even; lane <-> descriptor byte
+  __shared__ uint32_t s_patch[kBriefWarps][kBriefPatchRows * (kBriefPatchPitch / 4)];
+  uint32_t *my_patch = s_patch[threadIdx.x >> 5];
+  const int srg = min(lane / 10, 2), swk = lane - 10 * (lane / 10); // staging: lane <-> word swk of row 3 i + srg (lanes 30, 31 duplicate 20, 21)
 #pragma unroll 1
   for (int j = 0; j < n_here; ++j)
   {
@@ -1621,32 +1629,54 @@ template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5
     const double sj = __shfl_sync(FULL, sn, j), cj = __shfl_sync(FULL, cs, j);
     const Level &L = p.levels[level];
     const float fx = (float)(e & 0xfffu), fy = (float)((e >> 12) & 0xfffu);
-    const uint32_t upitch = (uint32_t)L.pitch;
-    size_t magic_off = (size_t)0x4B400000u * ((size_t)upitch + 1u);
-    asm volatile("" : "+l"(magic_off)); // opaque: keeps the constant folded into the base instead of re-subtracted per access
-    const uint8_t *__restrict__ blr_m = blr_img + L.pyr_off - magic_off;
-    const double2 *pat = p.pattern_d + lane;
-    asm volatile("" : "+l"(pat)); // opaque: the 32 pattern doubles are re-read (L1) per keypoint instead of pinned in 64 registers
+    // The rotated pattern stays within 18 px of the keypoint (|(13, 13)| = 18.4): the 37 x 37 blurred patch around it is staged
+    // in shared memory with coalesced word loads (3 rows x 10 aligned words per warp request, 13 requests), so that the 512
+    // scattered byte gathers of the descriptor hit shared-memory banks instead of 512 different L1 sectors.  Keypoints keep
+    // 19 px from the border (mnBorderSize), so rows y - 18 .. y + 18 exist; the aligned 40-byte row window may start up to
+    // 3 bytes left of / end a few bytes right of the image row, which is still inside the level's pitch-padded buffer.
+    const int kx_i = (int)(e & 0xfffu), ky_i = (int)((e >> 12) & 0xfffu);
+    const size_t pitch = (size_t)L.pitch;
+    const uint8_t *src0 = blr_img + L.pyr_off + (size_t)(ky_i - kBriefReach) * pitch + (kx_i - kBriefReach);
+    const uint32_t mis = (uint32_t)(size_t)src0 & 3u;
+    {
+      const uint8_t *gp = src0 - mis + 4 * swk + (size_t)srg * pitch;
+      const uint32_t pitch3 = 3u * (uint32_t)pitch;
+      uint32_t w[13];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t *>(gp + (uint64_t)pitch3 * (uint32_t)i)); // one IMAD.WIDE per address
+      w[12] = __ldg(reinterpret_cast<const uint32_t *>(src0 - mis + 4 * swk + 36 * pitch)); // row 36 (all lanes: duplicates are benign)
+      __syncwarp(); // the previous keypoint's gathers are done
+#pragma unroll
+      for (int i = 0; i < 12; ++i) my_patch[(3 * i + srg) * (kBriefPatchPitch / 4) + swk] = w[i];
+      my_patch[36 * (kBriefPatchPitch / 4) + swk] = w[12];
+      __syncwarp();
+    }
+    // cvRound without the conversion unit (below) leaves 0x4B400000 in both coordinates; that, the patch origin and the
+    // alignment shift fold into one constant (modulo 2^32), so one 32-bit multiply-add gives the byte index into the patch
+    uint32_t kofs = mis - 0x4B400000u * (kBriefPatchPitch + 1u) - (uint32_t)(ky_i - kBriefReach) * kBriefPatchPitch - (uint32_t)(kx_i - kBriefReach);
+    asm volatile("" : "+r"(kofs)); // opaque: stays one register instead of being re-materialised per access
+    const uint8_t *patch_b = reinterpret_cast<const uint8_t *>(my_patch);
     uint32_t byte = 0;
 #pragma unroll 4
     for (int k = 0; k < 8; ++k)
     {
-      // bit b = lane * 8 + k lands in byte b >> 3 == lane, position b & 7 == k
-      const double2 t1 = __ldg(pat + k * 32), t2 = __ldg(pat + (8 + k) * 32);
-      const double x1 = t1.x, y1 = t1.y, x2 = t2.x, y2 = t2.y;
+      // bit b = lane * 8 + k lands in byte b >> 3 == lane, position b & 7 == k.  The pair's four integer coordinates come as
+      // one packed word; int8 -> double is one conversion each (I2F.F64.S8 with a byte selector), exact
+      const uint32_t w = s_pat8[k][lane];
+      const double x1 = (double)(signed char)(w & 0xffu), y1 = (double)(signed char)((w >> 8) & 0xffu);
+      const double x2 = (double)(signed char)((w >> 16) & 0xffu), y2 = (double)(signed char)(w >> 24);
       const float p1x = __double2float_rn(__dsub_rn(__dmul_rn(x1, cj), __dmul_rn(y1, sj)));
       const float p1y = __double2float_rn(__dadd_rn(__dmul_rn(x1, sj), __dmul_rn(y1, cj)));
       const float p2x = __double2float_rn(__dsub_rn(__dmul_rn(x2, cj), __dmul_rn(y2, sj)));
       const float p2y = __double2float_rn(__dadd_rn(__dmul_rn(x2, sj), __dmul_rn(y2, cj)));
-      // cvRound without the conversion unit: float_as_uint(v + 1.5 * 2^23) == 0x4B400000 + round_half_even(v) for 0 <= v < 2^22;
-      // the constant is folded into the base pointer, the row product is one 64-bit multiply-add
+      // cvRound without the conversion unit: float_as_uint(v + 1.5 * 2^23) == 0x4B400000 + round_half_even(v) for 0 <= v < 2^22
       const uint32_t r1y = __float_as_uint(__fadd_rn(__fadd_rn(fy, p1y), 12582912.f)), r1x = __float_as_uint(__fadd_rn(__fadd_rn(fx, p1x), 12582912.f));
       const uint32_t r2y = __float_as_uint(__fadd_rn(__fadd_rn(fy, p2y), 12582912.f)), r2x = __float_as_uint(__fadd_rn(__fadd_rn(fx, p2x), 12582912.f));
-      const int v1 = blr_m[(size_t)r1y * upitch + r1x];
-      const int v2 = blr_m[(size_t)r2y * upitch + r2x];
-      byte |= (uint32_t)(v1 < v2) << k;
+      const int v1 = patch_b[r1y * kBriefPatchPitch + kofs + r1x];
+      const int v2 = patch_b[r2y * kBriefPatchPitch + kofs + r2x];
+      byte = __funnelshift_l((uint32_t)(v1 - v2), byte, 1); // shifts in the sign: 1 iff v1 < v2; bit k ends at position 7 - k
     }
-    p.desc[((size_t)img * p.n_features + slot0 + j) * 32 + lane] = (uint8_t)byte;
+    p.desc[((size_t)img * p.n_features + slot0 + j) * 32 + lane] = (uint8_t)(__brev(byte) >> 24);
   }
 
   // keypoint record (:407-409) + the row band used by the stereo search (createRowIndexDB, src/ORBMatcher.cc:915-932):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-CUDA-source-line instruction counts and stall samples from an .ncu-rep captured with --import-source on.
 
-    python scripts/ncu_lines.py gpurun_out/prof.ncu-rep <kernel-regex> [top_n]
+    python scripts/ncu_lines.py gpurun_out/prof.ncu-rep <kernel-regex> [top_n] [stalls]     ("stalls": order by stall samples)
 """
 import csv
 import re
@@ -36,7 +36,8 @@ def main():
         tot_s += w
         data.append((n, w, r[li], r[si].strip()[:105]))
     print(f"total warp instructions {tot_i}, stall samples {tot_s}")
-    for n, w, l, s in sorted(data, reverse=True)[:top]:
+    by_stalls = len(sys.argv) > 4 and sys.argv[4] == "stalls"
+    for n, w, l, s in sorted(data, key=(lambda d: (d[1], d[0])) if by_stalls else None, reverse=True)[:top]:
         print(f"{n:12d} {100 * n / max(tot_i, 1):5.1f}%i {100 * w / max(tot_s, 1):5.1f}%s  L{l}: {s}")
 
 
