@@ -231,7 +231,7 @@ int build_tables(orbx_ctx *c)
         const int zw = std::max(0, ce.pw - 6), zh = std::max(0, ce.ph - 6);
         ce.cap = std::max(1, ((zw + 1) / 2) * ((zh + 1) / 2)); // strict 8-neighbour maxima cannot be denser than this
         ce.slot = (int)slot_off;
-        ce.pad = 0;
+        ce.box_h = 0;
         slot_off += (size_t)ce.cap;
         L.list_cap += ce.cap;
         c->cells.push_back(ce);
@@ -241,6 +241,7 @@ int build_tables(orbx_ctx *c)
     L.n_level_cells = cell_index - L.cell_base;
     L.fast_box_h = 1;
     for (int ci = L.cell_base; ci < cell_index; ++ci) L.fast_box_h = std::max(L.fast_box_h, c->cells[ci].ph);
+    for (int ci = L.cell_base; ci < cell_index; ++ci) c->cells[ci].box_h = L.fast_box_h; // the kernel issues its TMA load right after the cell record
 
     // quadtree root fan-out (initSplit :81-96)
     L.n_ini = (int)std::round((double)w / (double)h);

@@ -68,7 +68,7 @@ struct Cell
   int pw, ph;   // patch size (maxX - iniX, maxY - iniY)
   int slot;     // entry offset of the cell's slot inside one image's cell_list
   int cap;      // slot capacity
-  int pad;
+  int box_h;    // = Level::fast_box_h of its level (rows of the TMA box)
 };
 
 struct RTab

@@ -403,7 +403,6 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
 
   const Cell c = p.cells[blockIdx.x];
   const int img = blockIdx.y;
-  const Level &L = p.levels[c.level];
   const int pw = c.pw, ph = c.ph;
   const int zw = pw - 6, zh = ph - 6; // detection zone: FAST looks at [3, w-3) x [3, h-3) of the patch
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -420,7 +419,7 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
   if (tid == 0)
   {
     mbar_init(&s_bar, 1);
-    mbar_expect_tx(&s_bar, (uint32_t)(kPatPitch * L.fast_box_h));
+    mbar_expect_tx(&s_bar, (uint32_t)(kPatPitch * c.box_h));
     tma_load_3d(s_pat, &maps.m[c.level], c.x0 & ~15, c.y0, p.img0 + img, &s_bar); // TMA needs 16-byte aligned row starts
   }
   const uint8_t *pat0 = s_pat + 3 * kPatPitch + 3 + (c.x0 & 15); // zone pixel (0,0); 15 + 65 <= the 80-byte box
@@ -1787,7 +1786,7 @@ constexpr int kStereoWarps = 8;
 
 constexpr int kWinPitch = 24;
 
-__global__ void __launch_bounds__(kStereoWarps * 32, 5) stereo_kernel(const Params p)
+__global__ void __launch_bounds__(kStereoWarps * 32, 8) stereo_kernel(const Params p)
 {
   __shared__ uint8_t s_win[kStereoWarps][11 * kWinPitch];
   const int frame = blockIdx.y;
