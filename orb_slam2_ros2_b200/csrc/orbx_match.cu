@@ -65,7 +65,7 @@ __device__ __forceinline__ void best_match_chunk(int id, int d, int lane, int &n
 //   if (d < min) { min = d; idx = i; } else if (d < second) second = d;
 // is evaluated per chunk with an exclusive prefix-minimum over the lanes: a candidate is a "new minimum" iff its
 // distance is below every earlier one (the running minimum included); `second` is the minimum over all the others.
-__global__ void __launch_bounds__(kAreaWarps * 32) area_match_kernel(const Params p, const AreaArgs a)
+__global__ void __launch_bounds__(kAreaWarps * 32, 8) area_match_kernel(const Params p, const AreaArgs a)
 {
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31;
