@@ -407,10 +407,9 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
   const int zw = pw - 6, zh = ph - 6; // detection zone: FAST looks at [3, w-3) x [3, h-3) of the patch
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned FULL = 0xffffffffu;
-  int *cnt_out = p.cell_cnt + (size_t)img * p.n_cells + blockIdx.x;
   if (zw <= 0 || zh <= 0)
   {
-    if (tid == 0) *cnt_out = 0;
+    if (tid == 0) p.cell_cnt[(size_t)img * p.n_cells + blockIdx.x] = 0;
     return;
   }
 
@@ -554,7 +553,7 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
     if (off < c.cap) slot[off] = x | (y << 12) | (score << 24);
     ++off;
   }
-  if (tid == 0) *cnt_out = min(total, c.cap);
+  if (tid == 0) p.cell_cnt[(size_t)img * p.n_cells + blockIdx.x] = min(total, c.cap); // only thread 0 needs the address
 }
 
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s)
