@@ -1,16 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- stereo frames/s of the ORB front-end (extract L+R + stereo match, 2000 features) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--pool P] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--transport nccl|peer] [--impl reference]
 
-A "step" is one pass of the hot path (pyramid+blur, FAST, quadtree, orientation+BRIEF, stereo match) over one batch of
-B synthetic KITTI-shaped stereo pairs.  `value` is whole-job frames/s with the inputs resident in HBM (CUDA events on
-the launching stream, max over ranks); `e2e` is the same metric through the host-buffer C-ABI call (pinned host images
-in, results out, copies inside the timed region).  Frames shard by rank with no data-path exchange; at N>1 the left
-descriptors of every step are all-gathered with NCCL (north_star: "only the descriptor gather is collected").
+A "step" is one pass of the hot path (pyramid+blur, FAST, quadtree, orientation+BRIEF, stereo match) over the synthetic
+4541-frame KITTI-00-length stereo sequence (BASELINE.json configs[2]; per frame it is configs[0]), sharded by frame over the
+N GPUs in contiguous blocks through the library's own sequence entry (orbx_sequence_stereo): strong scaling.  `value` is
+whole-job frames/s with every rank's block resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` is
+the same call with the block in pinned host memory and the per-frame records landing in pinned host memory (copies inside
+the timed region).  The only exchange between ranks is the gather of the left descriptors, issued by the library (NCCL
+send/recv pieces on a side stream, or peer-memory stores fused into the record-packing kernel).  The line also carries the
+other BASELINE configurations (`configs`: TUM RGB-D, 1080p, the feature-count latency sweep), the roofline of the dominant
+kernel, the CPU baseline and a `check` block that verifies the timed work (gathered descriptors against single-frame calls,
+checksums across ranks, bit flips against the oracle).
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref: the reference's ORBExtractor.cc and the
-searchByStereo lines of ORBMatcher.cc compiled unmodified) on the host cores of the same box.
+searchByStereo lines of ORBMatcher.cc compiled unmodified) on the host cores of the same box, on a bounded sample of the
+same sequence per step.
 """
 from __future__ import annotations
 
@@ -36,14 +42,23 @@ UNIT = "frames/s"
 CFG = synth.KITTI
 
 
-def workload_config(batch, pool):
+SEQ_FRAMES = 4541  # KITTI odometry sequence 00 (BASELINE.json configs[2])
+
+
+def workload_config(args):
+    c = CFG
     return {
-        "workload": "synthetic KITTI-shaped stereo pairs 1241x376, 2000 features, 8 levels x1.2, ORB extraction (L+R) + stereo matching",
-        "frames_per_step": batch,
-        "pool_pairs": pool,
-        "l2_policy": f"inputs larger than L2: {pool} distinct pairs ({pool * 2 * CFG['width'] * CFG['height'] / 1e6:.0f} MB) cycled, "
-                     f"plus ~{batch * 2 * 2 * 1.45:.0f} MB of pyramid/blur intermediates rewritten every step",
-        "parallelism": "frames sharded by rank, no data-path collective; NCCL all-gather of left descriptors per step when N>1 (asynchronous, overlapping the next step)",
+        "workload": f"synthetic {args.frames}-frame KITTI-00-length stereo sequence 1241x376, 2000 features, 8 levels x1.2: ORB extraction (L+R) + stereo "
+                    "matching per frame, frames sharded over the GPUs in contiguous blocks of ceil(F/N) (BASELINE.json configs[2] = configs[0] per frame)",
+        "frames_per_step": args.frames,
+        "pool_pairs": args.pool,
+        "frame_source": f"frame f = synthetic pair f mod {args.pool} ({args.pool} distinct pairs, seeds fixed: every rank count sees the same sequence)",
+        "l2_policy": f"inputs larger than L2: every rank's block of the sequence is materialised ({args.frames * 2 * c['width'] * c['height'] / 1e9:.2f} GB "
+                     "over all ranks, read once per step) and ~370 MB of pyramid intermediates are rewritten per 64 frames",
+        "device_slots": args.batch,
+        "parallelism": "frame blocks per rank, no data-path collective; left descriptors (+ counts) of all frames gathered on every rank by the library "
+                       f"({args.transport}: " + ("grouped ncclSend/ncclRecv of 64-frame pieces on a side stream" if args.transport == "nccl" else
+                                                 "stores into every rank's gathered array through CUDA-IPC peer pointers from the record-packing kernel") + ")",
     }
 
 
@@ -115,11 +130,16 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(n_frames: int, workers: int, pool_pairs: int = 4):
+_ref_pool = {}
+
+
+def cpu_reference_run(n_frames: int, workers: int, pool_pairs: int = 8):
     """times oracle/_ref (the compiled reference) on `n_frames` stereo frames; returns (fps, cores, kind, sample)"""
     from oracle import oracle_py as O  # the CPU baseline leg is one of the places allowed to execute oracle/
 
-    lefts, rights = synth.synth_stereo_pool(CFG["height"], CFG["width"], pool_pairs, seed0=1000)
+    if pool_pairs not in _ref_pool:
+        _ref_pool[pool_pairs] = synth.synth_stereo_pool(CFG["height"], CFG["width"], pool_pairs, seed0=0)  # the first pairs of the sequence
+    lefts, rights = _ref_pool[pool_pairs]
     with tempfile.TemporaryDirectory() as td:
         tp = O.write_template_file(os.path.join(td, "brief_template.txt"))
         if O.have_ref():
@@ -135,7 +155,9 @@ def cpu_reference_run(n_frames: int, workers: int, pool_pairs: int = 4):
                 O.search_by_stereo(el, er, np.float32(CFG["fx"]), np.float32(CFG["fx"]) * np.float32(CFG["bl"]))
             secs = time.perf_counter() - t0
             kind, cores = "port", 1
-    sample = f"{n_frames} KITTI-shaped stereo frames ({pool_pairs} distinct pairs), {workers} frames in flight x 2 extractor threads (Frame.cc:100-105)"
+    sample = (f"{n_frames} frames of the same KITTI-shaped sequence ({pool_pairs} distinct pairs), {workers} frames in flight x the reference's 2 extractor "
+              "threads (Frame.cc:100-105); the reference's own ORBExtractor.cc / ORBMatcher.cc compiled unmodified, its three OpenCV primitives "
+              "(cv::resize, cv::GaussianBlur, cv::FAST) are scalar restatements -- no C++ OpenCV in this image; a SIMD OpenCV build is ~2x faster on them")
     return n_frames / secs, cores, kind, sample
 
 
@@ -145,9 +167,9 @@ def run_reference_arm(args):
         return
     ncpu = os.cpu_count() or 1
     workers = max(1, ncpu // 2)
-    per_step = max(2, workers)
-    for _ in range(args.warmup):
-        cpu_reference_run(per_step, workers)
+    per_step = 64  # a bounded sample of the sequence per step: 64 frames = the GPU arm's device-slot batch
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_run(max(workers, 8), workers)
     t0 = time.perf_counter()
     fps_list = []
     kind = cores = sample = None
@@ -158,10 +180,10 @@ def run_reference_arm(args):
     value = float(args.steps * per_step / sum(per_step / f for f in fps_list))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        # the same config as our arm (metric, workload); what a CPU "step" actually ran is in cpu_baseline.sample
-        "config": dict(workload_config(args.batch, args.pool), reference_sample_frames_per_step=per_step, reference_sample_pool_pairs=4),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + f", per step; {args.steps} steps"},
+        "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args),  # identical to the GPU arm's; what a CPU "step" actually ran is in cpu_baseline.sample
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample + f"; {per_step} frames per step x {args.steps} steps (ms_per_step is the time of one such sample)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
@@ -290,6 +312,174 @@ def bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cp
     return out
 
 
+def _events(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def oracle_flip_check(api, O, ctx_result_kps, ctx_result_desc, img, nf, nl, sc):
+    """descriptor bit flips / inexact angles of one image against the oracle (north_star: flips "traced ... and counted")"""
+    e = O.extract(img, nf, nl, sc)
+    n = len(e.kps)
+    same = len(ctx_result_kps) == n and all(np.array_equal(ctx_result_kps[f], e.kps[f]) for f in ("x", "y", "size", "response", "octave", "class_id"))
+    flips = int(np.unpackbits(ctx_result_desc[:n] ^ e.desc).sum()) if len(ctx_result_desc) >= n else -1
+    dang = np.abs(ctx_result_kps["angle"][:n] - e.kps["angle"]) if len(ctx_result_kps) >= n else np.array([1e9])
+    dang = np.minimum(dang, 360.0 - dang)
+    return {"keypoints": n, "keypoints_bit_exact": bool(same), "descriptor_bit_flips": flips, "inexact_angles": int((dang != 0).sum()),
+            "max_angle_error_rad": float(np.radians(dang.max(initial=0.0)))}
+
+
+def bench_other_configs(args, api, torch, stream, local_rank, with_oracle):
+    """BASELINE.json configs[1], [3], [4] on one GPU: TUM-shaped RGB-D throughput, the feature-count latency sweep and the
+    1920x1080 / 5000 features / 12 levels stress case -- each with frames/s (or p50 ms), algorithmic bytes, roofline fraction
+    and a bit-flip count against the oracle on one frame."""
+    peak, _ = measured_peaks()
+    O = None
+    if with_oracle:
+        from oracle import oracle_py as O  # checker only
+    out = {}
+
+    def timed_ms(fn, reps):
+        for _ in range(3):
+            fn()
+        e0, e1 = _events(torch)
+        stream.synchronize()
+        e0.record(stream)
+        for i in range(reps):
+            fn(i)
+        e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # configs[1]: TUM-shaped RGB-D 640x480, 1000 features, depth lookup path (Frame.cc:125-159)
+    c = synth.TUM
+    B, P = 64, 128
+    g = np.stack([synth.synth_image(c["height"], c["width"], 3000 + i) for i in range(P)])
+    d = np.stack([synth.synth_depth_u16(c["height"], c["width"], 3000 + i, c["depth_scale"]) for i in range(P)])
+    with torch.cuda.stream(stream):
+        dg, dd = torch.from_numpy(g).cuda(), torch.from_numpy(d.view(np.int16)).cuda()
+    cam = api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], tuple(c["dist"]), c["depth_scale"])
+    ctx = api.Context(c["width"], c["height"], c["n_features"], c["n_levels"], c["scale_factor"], camera=cam, max_batch=B, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    fs = c["width"] * c["height"]
+
+    def tum_step(i=0):
+        o = (i % (P // B)) * B
+        ctx.rgbd_batch_device(B, dg.data_ptr() + o * fs, c["width"], fs, dd.data_ptr() + 2 * o * fs, 2 * c["width"], 2 * fs, api.DEPTH_U16)
+
+    ms = timed_ms(tum_step, 20)
+    alg = ctx.algorithmic_bytes(False) + 18 * c["n_features"]
+    fps = B / (ms * 1e-3)
+    one = api.Context(c["width"], c["height"], c["n_features"], c["n_levels"], c["scale_factor"], camera=cam, max_batch=1, device=local_rank)
+    r = one.rgbd_frame(g[0], d[0])
+    lat = []
+    for i in range(40):
+        t0 = time.perf_counter()
+        one.rgbd_frame(g[i % P], d[i % P])
+        lat.append(1e3 * (time.perf_counter() - t0))
+    out["tum_rgbd"] = {
+        "workload": "synthetic TUM-shaped RGB-D frames 640x480, 1000 features, 8 levels, TUM distortion, uint16 depth / 5208 (BASELINE.json configs[1])",
+        "value": fps, "unit": "frames/s", "frames_per_launch": B, "pool_frames": P, "ms_per_step": ms, "algorithmic_bytes_per_frame": alg,
+        "roofline": {"bound": "hbm", "achieved": alg * fps / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * fps / 1e9 / peak},
+        "p50_ms_host_to_host": float(np.median(lat[10:])), "depth_valid_fraction": float((r.depth > 0).mean()),
+        "check": oracle_flip_check(api, O, r.kps_raw, r.desc, g[0], c["n_features"], c["n_levels"], c["scale_factor"]) if O else None,
+    }
+    ctx.close()
+    one.close()
+    del dg, dd
+
+    # configs[4]: 1920x1080 stereo, 5000 features, 12 levels
+    c = synth.HD
+    B, P = 16, 32
+    l, r_ = synth.synth_stereo_pool(c["height"], c["width"], P, seed0=4000)
+    with torch.cuda.stream(stream):
+        dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r_).cuda()
+    cam = api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"])
+    ctx = api.Context(c["width"], c["height"], c["n_features"], c["n_levels"], c["scale_factor"], camera=cam, max_batch=B, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    fs = c["width"] * c["height"]
+
+    def hd_step(i=0):
+        o = (i % (P // B)) * B
+        ctx.stereo_batch_device(B, dl.data_ptr() + o * fs, dr.data_ptr() + o * fs, c["width"], fs)
+
+    ms = timed_ms(hd_step, 20)
+    stages = ctx.profile_stereo_batch_device(B, dl.data_ptr(), dr.data_ptr(), c["width"], fs)
+    alg = ctx.algorithmic_bytes(True)
+    fps = B / (ms * 1e-3)
+    one = api.Context(c["width"], c["height"], c["n_features"], c["n_levels"], c["scale_factor"], camera=cam, max_batch=1, device=local_rank)
+    one.set_stream(stream.cuda_stream)
+    lat = []
+    for i in range(40):
+        e0, e1 = _events(torch)
+        e0.record(stream)
+        one.stereo_batch_device(1, dl.data_ptr() + (i % P) * fs, dr.data_ptr() + (i % P) * fs, c["width"], fs)
+        e1.record(stream)
+        stream.synchronize()
+        lat.append(e0.elapsed_time(e1))
+    one.set_stream(None)
+    res = one.stereo_frame(l[0], r_[0])
+    out["hd_1080p"] = {
+        "workload": "synthetic 1920x1080 stereo pairs, 5000 features, 12 levels x1.2 (BASELINE.json configs[4])",
+        "value": fps, "unit": "frames/s", "frames_per_launch": B, "pool_pairs": P, "ms_per_step": ms, "algorithmic_bytes_per_frame": alg, "stage_ms": stages,
+        "roofline": {"bound": "hbm", "achieved": alg * fps / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * fps / 1e9 / peak},
+        "p50_ms_device_single_pair": float(np.median(lat[10:])), "matches_first_pair": int(res.n_matches),
+        "check": oracle_flip_check(api, O, res.kps_left, res.desc_left, l[0], c["n_features"], c["n_levels"], c["scale_factor"]) if O else None,
+    }
+    ctx.close()
+    one.close()
+    del dl, dr
+
+    # configs[3]: per-frame latency sweep over the feature count on KITTI-shaped stereo, single GPU (left and right run in the same launches)
+    c = synth.KITTI
+    P = 16
+    l, r_ = synth.synth_stereo_pool(c["height"], c["width"], P, seed0=0)
+    with torch.cuda.stream(stream):
+        dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r_).cuda()
+    hl, hr = torch.from_numpy(l).pin_memory(), torch.from_numpy(r_).pin_memory()
+    fs = c["width"] * c["height"]
+    cam = api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"])
+    sweep = {}
+    for nf in (500, 1000, 2000, 4000):
+        one = api.Context(c["width"], c["height"], nf, c["n_levels"], c["scale_factor"], camera=cam, max_batch=1, device=local_rank)
+        row = {}
+        for graph in (True, False):
+            one.set_graph(graph)
+            one.set_stream(stream.cuda_stream)
+            dev = []
+            for i in range(60):
+                e0, e1 = _events(torch)
+                e0.record(stream)
+                one.stereo_batch_device(1, dl.data_ptr() + (i % P) * fs, dr.data_ptr() + (i % P) * fs, c["width"], fs)
+                e1.record(stream)
+                stream.synchronize()
+                dev.append(e0.elapsed_time(e1))
+            one.set_stream(None)
+            host = []
+            N_ = nf
+            kl, kr = np.zeros((N_, 28), np.uint8), np.zeros((N_, 28), np.uint8)
+            dsl, dsr = np.zeros((N_, 32), np.uint8), np.zeros((N_, 32), np.uint8)
+            ur, dp, cnt = np.zeros(N_), np.zeros(N_), np.zeros(3, np.int32)
+            ptrs = [kl.ctypes.data, dsl.ctypes.data, cnt.ctypes.data, kr.ctypes.data, dsr.ctypes.data, cnt.ctypes.data + 4, ur.ctypes.data, dp.ctypes.data,
+                    cnt.ctypes.data + 8]
+            for i in range(60):
+                t0 = time.perf_counter()
+                one.stereo_batch_ptr(1, hl.data_ptr() + (i % P) * fs, hr.data_ptr() + (i % P) * fs, c["width"], fs, ptrs)
+                host.append(1e3 * (time.perf_counter() - t0))
+            tag = "graph" if graph else "stream_launches"
+            row["p50_ms_device_" + tag] = float(np.median(dev[10:]))
+            row["p50_ms_host_to_host_" + tag] = float(np.median(host[10:]))
+        res = one.stereo_frame(l[0], r_[0])
+        row["keypoints"], row["matches"] = int(len(res.kps_left)), int(res.n_matches)
+        if O:
+            row["check"] = oracle_flip_check(api, O, res.kps_left, res.desc_left, l[0], nf, c["n_levels"], c["scale_factor"])
+        sweep[str(nf)] = row
+        one.close()
+    out["latency_sweep"] = {"workload": "single KITTI-shaped stereo pair per call, nFeatures in {500, 1000, 2000, 4000} (BASELINE.json configs[3])",
+                            "note": "device = images and results in HBM (CUDA events); host_to_host = pinned host images in, results out (wall clock); "
+                                    "graph = the call replays one captured CUDA graph, stream_launches = 8 separate launches", "n_features": sweep}
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -305,76 +495,81 @@ def run_gpu_arm(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL announces its version on stdout when the first communicator is created; the contract is ONE JSON line there,
-        # so fd 1 points at stderr until the communicator exists
+        # so fd 1 points at stderr until the communicators exist
         sys.stdout.flush()
         saved = os.dup(1)
         os.dup2(2, 1)
-        try:
+
+    H, W, N = CFG["height"], CFG["width"], CFG["n_features"]
+    B, P, F = args.batch, args.pool, args.frames
+    cam = api.Camera(CFG["fx"], CFG["fy"], CFG["cx"], CFG["cy"], CFG["bl"])
+    ctx = api.Context(W, H, N, CFG["n_levels"], CFG["scale_factor"], CFG["ini_th"], CFG["min_th"], camera=cam, max_batch=B, device=local_rank)
+    comm = None
+    try:
+        if world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
             warm = torch.zeros(1, device="cuda")
             dist.all_reduce(warm)
             torch.cuda.synchronize()
-        finally:
+            # the library's own communicator (the descriptor gather lives behind the C ABI): rank 0 makes the id, torch carries it
+            ids = [api.Communicator.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            comm = api.Communicator(ctx, rank, world, ids[0], F)
+            if args.transport == "peer":
+                handles = [None] * world
+                dist.all_gather_object(handles, comm.ipc_handle())
+                comm.open_peers(handles)
+    finally:
+        if world > 1:
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
 
-    H, W, N = CFG["height"], CFG["width"], CFG["n_features"]
-    B, P = args.batch, args.pool
-    cam = api.Camera(CFG["fx"], CFG["fy"], CFG["cx"], CFG["cy"], CFG["bl"])
-    ctx = api.Context(W, H, N, CFG["n_levels"], CFG["scale_factor"], CFG["ini_th"], CFG["min_th"], camera=cam, max_batch=B, device=local_rank)
-
-    # synthetic pool (distinct seeds per rank), resident in HBM for `value`, in pinned host memory for `e2e`
-    lefts, rights = synth.synth_stereo_pool(H, W, P, seed0=10_000 * rank)
-    h_left, h_right = torch.from_numpy(lefts).pin_memory(), torch.from_numpy(rights).pin_memory()
+    # ---- the sequence: frame f = pool pair f mod P; this rank materialises its block in pinned host memory and in HBM ----
+    pool_l, pool_r = synth.synth_stereo_pool(H, W, P, seed0=0)
+    blk = api.frame_range(F, rank, world)
+    n_local = len(blk)
+    fsz = W * H
+    h_left = torch.empty((max(n_local, 1), H, W), dtype=torch.uint8, pin_memory=True)
+    h_right = torch.empty((max(n_local, 1), H, W), dtype=torch.uint8, pin_memory=True)
+    idx = np.arange(blk.start, blk.stop) % P
+    if n_local:
+        np.take(pool_l, idx, axis=0, out=h_left.numpy()[:n_local])
+        np.take(pool_r, idx, axis=0, out=h_right.numpy()[:n_local])
     d_left, d_right = h_left.cuda(non_blocking=True), h_right.cuda(non_blocking=True)
+    rs = ctx.record_layout().record_bytes
+    d_rec = torch.empty((max(n_local, 1), rs), dtype=torch.uint8, device="cuda")
+    h_rec = torch.empty((max(n_local, 1), rs), dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
-    stream = torch.cuda.Stream()  # the stream every kernel of the timed region is launched on
+    stream = torch.cuda.Stream()  # the stream every call of the timed region is issued on
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    fsz = W * H
-    n_chunks = P // B
-    assert n_chunks >= 1, "pool must hold at least one batch"
+    last = {}
 
-    gathered = torch.empty((world, B, N, 32), dtype=torch.uint8, device="cuda") if world > 1 else None
+    def device_step():
+        last["res"] = ctx.sequence_stereo_ptr(F, d_left.data_ptr(), d_right.data_ptr(), W, fsz, comm, True, d_rec.data_ptr(), rs, True)
 
-    def device_step(i):
-        c = i % n_chunks
-        res = ctx.stereo_batch_device(B, d_left.data_ptr() + c * B * fsz, d_right.data_ptr() + c * B * fsz, W, fsz)
-        if world > 1:
-            # left descriptors = even images of the interleaved [2B][N][32] result array
-            # (copied out on the compute stream, so the next step may overwrite the context's buffers); the gather itself runs
-            # on NCCL's stream and overlaps the next step's kernels -- barrier() below waits for the last one
-            desc = torch.as_tensor(CudaArray(res.desc, (B, 2, N, 32), "|u1"), device="cuda")[:, 0]
-            pending[0] = dist.all_gather_into_tensor(gathered, desc.contiguous(), async_op=True)
-        return res
-
-    pending = [None]
+    def host_step():
+        last["res"] = ctx.sequence_stereo_ptr(F, h_left.data_ptr(), h_right.data_ptr(), W, fsz, comm, False, h_rec.data_ptr(), rs, False)
 
     def barrier():
         if world > 1:
-            if pending[0] is not None:
-                pending[0].wait()  # makes the current (compute) stream wait for the gather
-                pending[0] = None
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (`value`) ------------------------------------------------------------------
+    # ---- device-resident throughput (`value`): K passes over the sequence, images and records in HBM ---------------------
     sampler = ClockSampler(local_rank)
     sampler.start()  # started before the warm-up so that short timed regions still get samples under load
     sampler.wait_first_sample()
-    for i in range(args.warmup):
-        device_step(i)
+    for _ in range(args.warmup):
+        device_step()
     barrier()
     launches0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = _events(torch)
     barrier()
     e0.record(stream)
-    for i in range(args.steps):
-        device_step(args.warmup + i)
-    if pending[0] is not None:
-        pending[0].wait()  # the timed region ends after the last descriptor gather
-        pending[0] = None
+    for _ in range(args.steps):
+        device_step()  # returns once this rank's records and (N > 1) the gathered descriptors are complete
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -384,19 +579,94 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * args.steps * B / (ms_max * 1e-3)
+    value = args.steps * F / (ms_max * 1e-3)
+    res = last["res"]
+    cap = res.world * res.block
 
-    # sanity: the timed work produced real results
-    res = device_step(0)
-    nm = ctx.read_device(res.n_matches, (B,), np.int32)
-    nk = ctx.read_device(res.n_kps, (2 * B,), np.int32)
+    # ---- verification of the timed work: records, gathered descriptors, ranks agree ---------------------------------------
+    g_desc = torch.as_tensor(CudaArray(res.gathered_desc, (cap, N * 32), "|u1"), device="cuda")
+    g_n = torch.as_tensor(CudaArray(res.gathered_n, (cap,), "<i4"), device="cuda")
+    rec_np_dtype = ctx.record_dtype()
+    check = {}
+    # (a) frames f and f + P are the same pair, computed by different ranks / slots / chunks: their gathered rows must be identical
+    if F > P:
+        check["gathered_rows_periodic"] = bool(torch.equal(g_desc[: F - P], g_desc[P:F]) and torch.equal(g_n[: F - P], g_n[P:F]))
+    # (b) one checksum of the gathered arrays per rank; all ranks must hold the same bytes (and the same as an N = 1 run of this bench)
+    csum = int(g_desc[:F].view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF
+    csum ^= int(g_n[:F].to(torch.int64).sum().item())
+    sums = [csum]
+    if world > 1:
+        sums = [None] * world
+        dist.all_gather_object(sums, csum)
+    check["gathered_checksum"] = f"{sums[0]:016x}"
+    check["gathered_checksum_equal_on_all_ranks"] = bool(all(x == sums[0] for x in sums))
+    check["gathered_keypoints_total"] = int(g_n[:F].sum().item())
+    # (c) this rank's device records agree with its rows of the gathered array
+    if n_local:
+        lay = ctx.record_layout()
+        mine = d_rec[:n_local, lay.off_desc_left: lay.off_desc_left + N * 32]
+        ok = bool(torch.equal(mine, g_desc[blk.start:blk.stop]))
+    else:
+        ok = True
+    oks = [ok]
+    if world > 1:
+        oks = [None] * world
+        dist.all_gather_object(oks, ok)
+    check["records_equal_gathered_rows_on_all_ranks"] = bool(all(oks))
+    # (d) rank 0 recomputes sampled frames of EVERY rank's block alone (single-frame call, own context) and, for two of them, with the oracle
+    if rank == 0:
+        one = api.Context(W, H, N, CFG["n_levels"], CFG["scale_factor"], CFG["ini_th"], CFG["min_th"], camera=cam, max_batch=1, device=local_rank)
+        sample = sorted({f for r in range(world) for b in [api.frame_range(F, r, world)] if len(b) for f in (b.start, b.stop - 1)})
+        good = 0
+        for f in sample:
+            r1 = one.stereo_frame(pool_l[f % P], pool_r[f % P])
+            row = g_desc[f].cpu().numpy().reshape(N, 32)
+            n_f = int(g_n[f].item())
+            good += int(n_f == len(r1.kps_left) and np.array_equal(row[:n_f], r1.desc_left) and not row[n_f:].any())
+        check["sampled_frames_vs_single_frame_call"] = {"frames": sample, "identical": good}
+        if not args.no_cpu_baseline:
+            from oracle import oracle_py as O  # checker only
 
-    # ---- per-stage device times -> roofline of the dominant kernel --------------------------------------------
+            r1 = one.stereo_frame(pool_l[0], pool_r[0])
+            oc = oracle_flip_check(api, O, r1.kps_left, r1.desc_left, pool_l[0], N, CFG["n_levels"], CFG["scale_factor"])
+            el, er = O.extract(pool_l[0], N, CFG["n_levels"], CFG["scale_factor"]), O.extract(pool_r[0], N, CFG["n_levels"], CFG["scale_factor"])
+            nm, ur, dp, _ = O.search_by_stereo(el, er, np.float32(cam.fx), cam.bf)
+            oc["stereo_matches_equal"] = bool(nm == r1.n_matches)
+            oc["max_u_right_error_px"] = float(np.abs(r1.u_right - ur).max()) if len(ur) == len(r1.u_right) else None
+            oc["max_depth_error"] = float(np.abs(r1.depth - dp).max()) if len(dp) == len(r1.depth) else None
+            check["oracle_frame0"] = oc
+        one.close()
+    if n_local:
+        rec0 = d_rec[0].cpu().numpy().view(rec_np_dtype)[0]
+        check["first_local_frame"] = {"n_left": int(rec0["n_left"]), "n_right": int(rec0["n_right"]), "n_matches": int(rec0["n_matches"])}
+
+    # ---- end to end (`e2e`): the same call with the block in pinned HOST memory and the records landing in pinned host memory ----
+    ctx.set_stream(None)
+    e2e_steps = max(2, min(args.steps, 10))
+    host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * F / float(t.item())
+    if n_local:
+        check["host_records_equal_device_records"] = bool(torch.equal(h_rec[:n_local], d_rec[:n_local].cpu()))
+    h2d = 2 * F * fsz
+    d2h = F * rs
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- per-stage device times of one 64-frame slot batch -> roofline of the dominant kernel ------------------------------
     stage_ms = {}
     reps = 5
+    nb = max(1, min(B, n_local))
     for r in range(reps):
-        c = r % n_chunks
-        sm = ctx.profile_stereo_batch_device(B, d_left.data_ptr() + c * B * fsz, d_right.data_ptr() + c * B * fsz, W, fsz)
+        o = (r * nb) % max(1, n_local - nb + 1)
+        sm = ctx.profile_stereo_batch_device(nb, d_left.data_ptr() + o * fsz, d_right.data_ptr() + o * fsz, W, fsz)
         if r == 0:
             continue
         for k, v in sm.items():
@@ -405,84 +675,61 @@ def run_gpu_arm(args):
     peak, peak_src = measured_peaks()
     alg_frame = ctx.algorithmic_bytes(True)
     dom_ms = stage_ms[dominant]
-    achieved = alg_frame * B / (dom_ms * 1e-3) / 1e9
+    achieved = alg_frame * nb / (dom_ms * 1e-3) / 1e9
     step_total = sum(stage_ms.values())
     traffic = None
     try:  # dram__bytes_read+write of the same kernel from the committed ncu --set full capture (per 64-frame launch)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[dominant]
-        traffic = tj["dram_bytes_per_launch"] * B / tj["frames_per_launch"]
+        traffic = tj["dram_bytes_per_launch"] * nb / tj["frames_per_launch"]
     except Exception:
         pass
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": peak_src, "algorithmic_bytes_per_frame": alg_frame, "frames_per_launch": B, "kernel_ms": dom_ms,
+        "peak_source": peak_src, "algorithmic_bytes_per_frame": alg_frame, "frames_per_launch": nb, "kernel_ms": dom_ms,
         "kernel_share_of_step": dom_ms / step_total, "stage_ms": stage_ms,
-        "whole_step": {"achieved": alg_frame * value / world / 1e9, "frac": alg_frame * value / world / 1e9 / peak},
+        "whole_step": {"achieved": alg_frame * value / world / 1e9, "frac": alg_frame * value / world / 1e9 / peak,
+                       "note": "algorithmic bytes of one frame x frames/s per GPU over the measured HBM peak"},
     }
 
-    # ---- end to end through the host-buffer C-ABI call (`e2e`) -------------------------------------------------
-    ctx.set_stream(None)  # the library's own streams; the call synchronises internally
-    # One call = one sequence of S frames from the pinned pool (the call streams it through the context's device slots);
-    # an e2e "step" is still B frames, so K steps are K * B frames = K * B / S calls.
-    S = n_chunks * B
-    out = {
-        "kl": torch.empty((S, N, 28), dtype=torch.uint8).pin_memory(), "dl": torch.empty((S, N, 32), dtype=torch.uint8).pin_memory(),
-        "nl": torch.empty(S, dtype=torch.int32).pin_memory(), "kr": torch.empty((S, N, 28), dtype=torch.uint8).pin_memory(),
-        "dr": torch.empty((S, N, 32), dtype=torch.uint8).pin_memory(), "nr": torch.empty(S, dtype=torch.int32).pin_memory(),
-        "ur": torch.empty((S, N), dtype=torch.float64).pin_memory(), "dp": torch.empty((S, N), dtype=torch.float64).pin_memory(),
-        "nm": torch.empty(S, dtype=torch.int32).pin_memory(),
-    }
-    ptrs = [out[k].data_ptr() for k in ("kl", "dl", "nl", "kr", "dr", "nr", "ur", "dp", "nm")]
-    h2d = 2 * B * fsz
-    d2h = sum(v.numel() * v.element_size() for v in out.values()) * B // S
-
-    def host_sequence():
-        ctx.stereo_batch_ptr(S, h_left.data_ptr(), h_right.data_ptr(), W, fsz, ptrs)
-
-    e2e_calls = max(2, -(-max(3, min(args.steps, 40)) * B // S))
-    host_sequence()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_calls):
-        host_sequence()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_steps = e2e_calls * S // B
-    e2e_value = world * e2e_calls * S / float(t.item())
-    e2e_matches = int(out["nm"][:B].sum())
-
-    # ---- single-frame latency (p50), one GPU ---------------------------------------------------------------------
+    # ---- single-frame latency (p50), one GPU: with the CUDA graph and with plain stream launches -----------------------------
     latency = None
-    if rank == 0:
+    if rank == 0 and n_local:
         one = api.Context(W, H, N, CFG["n_levels"], CFG["scale_factor"], CFG["ini_th"], CFG["min_th"], camera=cam, max_batch=1, device=local_rank)
-        one.set_stream(stream.cuda_stream)
-        dev_ms, host_ms = [], []
-        for i in range(60):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            one.stereo_batch_device(1, d_left.data_ptr() + (i % P) * fsz, d_right.data_ptr() + (i % P) * fsz, W, fsz)
-            b.record(stream)
-            torch.cuda.synchronize()
-            if i >= 10:
-                dev_ms.append(a.elapsed_time(b))
-        one.set_stream(None)
-        p1 = [q for q in ptrs]  # the first frame's slice of the pinned output arrays
-        for i in range(60):
-            t0 = time.perf_counter()
-            one.stereo_batch_ptr(1, h_left.data_ptr() + (i % P) * fsz, h_right.data_ptr() + (i % P) * fsz, W, fsz, p1)
-            if i >= 10:
-                host_ms.append(1e3 * (time.perf_counter() - t0))
-        latency = {"p50_ms_device": float(np.median(dev_ms)), "p50_ms_host_to_host": float(np.median(host_ms)), "frames": 50,
-                   "note": "one stereo pair per call; device = inputs and results in HBM, host_to_host = pinned host images in, results out"}
+        latency = {"frames": 50, "note": "one stereo pair per call; device = inputs and results in HBM, host_to_host = pinned host images in, results out"}
+        np_ = min(n_local, P)
+        ho = {k: np.zeros(s_, dt_) for k, (s_, dt_) in {"kl": ((N, 28), np.uint8), "dl": ((N, 32), np.uint8), "kr": ((N, 28), np.uint8), "dr": ((N, 32), np.uint8),
+                                                        "ur": ((N,), np.float64), "dp": ((N,), np.float64), "c": ((3,), np.int32)}.items()}
+        p1 = [ho["kl"].ctypes.data, ho["dl"].ctypes.data, ho["c"].ctypes.data, ho["kr"].ctypes.data, ho["dr"].ctypes.data, ho["c"].ctypes.data + 4,
+              ho["ur"].ctypes.data, ho["dp"].ctypes.data, ho["c"].ctypes.data + 8]
+        for graph in (True, False):
+            one.set_graph(graph)
+            one.set_stream(stream.cuda_stream)
+            dev_ms, host_ms = [], []
+            for i in range(60):
+                a, b = _events(torch)
+                a.record(stream)
+                one.stereo_batch_device(1, d_left.data_ptr() + (i % np_) * fsz, d_right.data_ptr() + (i % np_) * fsz, W, fsz)
+                b.record(stream)
+                torch.cuda.synchronize()
+                if i >= 10:
+                    dev_ms.append(a.elapsed_time(b))
+            one.set_stream(None)
+            for i in range(60):
+                t0 = time.perf_counter()
+                one.stereo_batch_ptr(1, h_left.data_ptr() + (i % np_) * fsz, h_right.data_ptr() + (i % np_) * fsz, W, fsz, p1)
+                if i >= 10:
+                    host_ms.append(1e3 * (time.perf_counter() - t0))
+            tag = "" if graph else "_stream_launches"
+            latency["p50_ms_device" + tag] = float(np.median(dev_ms))
+            latency["p50_ms_host_to_host" + tag] = float(np.median(host_ms))
         one.close()
 
-    # ---- tracking-side matchers: a secondary line, not part of the headline metric ------------
-    matchers = serialize = bow = None
-    if rank == 0 and not args.no_matchers:
-        matchers = bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cpu=(world == 1 and not args.no_cpu_baseline))
+    # ---- the other BASELINE configurations and the SURVEY 8(f) rows: secondary lines, one GPU --------------------------------
+    configs = matchers = serialize = bow = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = bench_other_configs(args, api, torch, stream, local_rank, with_oracle=not args.no_cpu_baseline)
+    if rank == 0 and world == 1 and not args.no_matchers and n_local >= B:
+        matchers = bench_matchers(ctx, api, torch, stream, d_left, d_right, B, W, H, N, fsz, cpu=not args.no_cpu_baseline)
         serialize = matchers.pop("serialize", None)
         bow = matchers.pop("bow", None)
 
@@ -491,20 +738,26 @@ def run_gpu_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncpu = os.cpu_count() or 1
         workers = max(1, ncpu // 2)
-        n_frames = max(8, 6 * workers)
+        n_frames = max(16, 8 * workers)
+        cpu_reference_run(workers, workers)  # warm
         fps, cores, kind, sample = cpu_reference_run(n_frames, workers)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(B, P), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "frames_per_call": S, "matches_first_step": e2e_matches},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency, "matchers": matchers, "serialize": serialize, "bow": bow,
-            "check": {"mean_keypoints_per_image": float(nk.mean()), "mean_matches_per_frame": float(nm.mean())},
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "note": "the same orbx_sequence_stereo call with every rank's block in pinned host memory and its records landing in pinned host memory; "
+                            "the gathered descriptors stay in HBM (they are consumed there)"},
+            "gpu_launches": int(launches), "transport": (comm.info()["transport"] if comm else 0), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
+            "configs": configs, "matchers": matchers, "serialize": serialize, "bow": bow, "check": check,
         }
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        barrier()
+        comm.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -513,13 +766,16 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="stereo frames per step (per GPU)")
-    ap.add_argument("--pool", type=int, default=256, help="distinct synthetic pairs per GPU")
+    ap.add_argument("--frames", type=int, default=SEQ_FRAMES, help="frames of the sequence (one step = one pass over all of them, sharded over the GPUs)")
+    ap.add_argument("--batch", type=int, default=64, help="device slots per GPU (frames in flight)")
+    ap.add_argument("--pool", type=int, default=256, help="distinct synthetic pairs the sequence cycles through")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer"], help="descriptor gather at N > 1")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-matchers", action="store_true", help="skip the secondary tracking-matcher measurement")
+    ap.add_argument("--no-matchers", action="store_true", help="skip the secondary tracking-matcher / serialisation / bag-of-words measurements")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configurations (TUM RGB-D, 1080p, latency sweep)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -33,6 +33,7 @@ extern "C" {
 #define ORBX_ERR_NO_DEVICE (-5)
 #define ORBX_ERR_CAPACITY (-6)      /* more frames than orbx_config.max_batch */
 #define ORBX_ERR_STATE (-7)         /* e.g. orbx_get_pyramid before any frame was processed */
+#define ORBX_ERR_COMM (-8)          /* NCCL missing / failed, or peers cannot reach each other's memory */
 
 /* memory layout of cv::KeyPoint (28 bytes) so that results can be memcpy'd into std::vector<cv::KeyPoint> */
 typedef struct orbx_keypoint {
@@ -51,7 +52,7 @@ typedef struct orbx_keypoint {
 /* Everything the reference reads from its YAML for this path (src/System.cc:27-73): ORBExtractor.* and Camera.* */
 typedef struct orbx_config {
   int32_t width, height;   /* input image size (8-bit, single channel) */
-  int32_t n_features;      /* ORBExtractor.nFeatures */
+  int32_t n_features;      /* ORBExtractor.nFeatures (1..65535: keypoint indices travel as uint16 in the row index / grid) */
   int32_t n_levels;        /* ORBExtractor.nLevels (1..16) */
   float scale_factor;      /* ORBExtractor.scaleFactor (> 1) */
   int32_t ini_th_fast;     /* ORBExtractor.iniThFAST */
@@ -82,6 +83,11 @@ int orbx_load_brief_template(const char *path, float *pattern_out /* [1024] */);
 /* launch on this CUDA stream (cudaStream_t) instead of the context's own non-blocking stream; NULL restores the
  * context's own stream (pass cudaStreamLegacy / cudaStreamPerThread explicitly to use a default stream) */
 int orbx_set_stream(orbx_ctx *ctx, void *cuda_stream);
+
+/* Single-pair calls (orbx_stereo_frame, orbx_stereo_batch* with one frame) replay their launch sequence as ONE CUDA graph
+ * captured at the first call (on by default; the legacy default stream cannot be captured and always takes plain launches).
+ * enable = 0 restores plain stream launches (bench.py reports the p50 latency both ways).  Environment: ORBX_GRAPH=0. */
+int orbx_set_graph(orbx_ctx *ctx, int enable);
 
 /* ---- per-config tables ---------------------------------------------------------------------------------- */
 /* replaces: ORBExtractor::getScaledFactors() (include/ORB_SLAM2/ORBExtractor.h:116), ORBExtractor::mnLevels,
@@ -161,10 +167,88 @@ int orbx_extract_batch_device(orbx_ctx *ctx, int n_images, const uint8_t *d_imag
 int orbx_rgbd_batch_device(orbx_ctx *ctx, int n_frames, const uint8_t *d_gray, size_t gray_stride,
                            size_t gray_frame_stride, const void *d_depth, size_t depth_stride_bytes,
                            size_t depth_frame_stride_bytes, int depth_type, orbx_device_results *out);
+/* Every call that produces frames (extract / stereo / RGB-D / batch / sequence) bumps the context's epoch.  Frame-level
+ * queries (orbx_get_grid, orbx_get_pyramid, orbx_search_in_area, orbx_serialize_keyframe, orbx_bow_transform ...) refer to
+ * the most recent call: a caller that keeps several frames alive stores the epoch at creation and compares it before
+ * querying (the C++ shim does, include/orbx/orb_slam2_shim.hpp). */
+uint64_t orbx_frame_epoch(const orbx_ctx *ctx);
 /* block until the context's stream is idle */
 int orbx_synchronize(orbx_ctx *ctx);
 /* synchronous device-to-host copy of `bytes` bytes of a device result array (after draining the context's stream) */
 int orbx_read_device(orbx_ctx *ctx, const void *device_ptr, void *host_dst, size_t bytes);
+
+/* ---- whole sequences sharded by frame over GPUs (BASELINE config 3) -------------------------- */
+/* replaces: the dataset loop of the reference's examples (example/Stereo/KittiStereo.cc:28-37 -> Frame::createStereo,
+ * include/ORB_SLAM2/Frame.h:313-322) for offline map / vocabulary building.  Frames are independent on this path: rank r
+ * of R processes the contiguous block [r * ceil(F/R), min(F, (r + 1) * ceil(F/R))) of an F-frame sequence; the only
+ * exchange is the gather of the left descriptors (+ counts), issued by the library itself.  One process (or host thread)
+ * and one context per GPU. */
+typedef struct orbx_comm orbx_comm;
+#define ORBX_COMM_ID_BYTES 128  /* == NCCL_UNIQUE_ID_BYTES */
+#define ORBX_IPC_HANDLE_BYTES 64 /* == sizeof(cudaIpcMemHandle_t) */
+#define ORBX_TRANSPORT_NONE 0   /* single rank */
+#define ORBX_TRANSPORT_NCCL 1   /* ncclSend/ncclRecv pieces on a side stream, overlapping the kernels of later chunks */
+#define ORBX_TRANSPORT_PEER 2   /* descriptors are stored straight into every rank's gathered array (NVLink peer memory) by the
+                                   kernel that assembles the records: gather fused into the producer, no separate collective */
+
+/* the block of rank `rank` (lo inclusive, hi exclusive) */
+void orbx_frame_range(int64_t n_frames_total, int rank, int world, int64_t *lo, int64_t *hi);
+/* multi-process (one rank per process, e.g. under torchrun / mpirun): rank 0 calls orbx_comm_unique_id (ncclGetUniqueId) and
+ * ships the bytes to the other ranks by any means; then EVERY rank calls orbx_comm_create (ncclCommInitRank: collective).
+ * max_frames_total = longest sequence the communicator will carry (sizes the gathered arrays; all ranks must agree).
+ * libnccl.so.2 is resolved with dlopen at the first call: ORBX_ERR_COMM if it is missing. */
+int orbx_comm_unique_id(uint8_t *id /* [ORBX_COMM_ID_BYTES] */);
+int orbx_comm_create(orbx_ctx *ctx, int rank, int world, const uint8_t *id, int64_t max_frames_total, orbx_comm **out);
+/* optional, after orbx_comm_create: switch the data path to ORBX_TRANSPORT_PEER.  Every rank exports its gathered array
+ * (orbx_comm_ipc_handle, a cudaIpcMemHandle_t), the caller all-gathers the handles, every rank maps them
+ * (orbx_comm_open_peers: handles[r * ORBX_IPC_HANDLE_BYTES ..] = rank r's).  NCCL then only carries the closing barrier. */
+int orbx_comm_ipc_handle(orbx_comm *comm, uint8_t *handle /* [ORBX_IPC_HANDLE_BYTES] */);
+int orbx_comm_open_peers(orbx_comm *comm, const uint8_t *handles /* [world][ORBX_IPC_HANDLE_BYTES] */);
+/* single process driving `world` contexts (same or different devices; one host thread each, or one thread calling the ranks
+ * one after the other): ORBX_TRANSPORT_PEER without NCCL.  out[r] is rank r's communicator.  The gathered arrays are
+ * complete on every rank once every rank's orbx_sequence_stereo call has returned. */
+int orbx_comm_create_local(orbx_ctx *const *ctxs, int world, int64_t max_frames_total, orbx_comm **out /* [world] */);
+void orbx_comm_destroy(orbx_comm *comm);
+int orbx_comm_info(const orbx_comm *comm, int32_t *rank, int32_t *world, int32_t *transport);
+
+/* One frame's results as ONE fixed-stride record, so that a chunk of frames leaves the device in a single copy:
+ *   int32 n_left, n_right, n_matches (Frame::mnN), 0 at offset 0, then the arrays below (capacity n_features each; entries
+ *   beyond the counts are zero).  kps_left are the undistorted left keypoints (mvFeatsLeft), kps_right the right ones. */
+typedef struct orbx_record_layout {
+  int64_t record_bytes;   /* multiple of 16 */
+  int64_t off_kps_left;   /* orbx_keypoint[n_features] */
+  int64_t off_desc_left;  /* uint8[n_features][32] */
+  int64_t off_kps_right;
+  int64_t off_desc_right;
+  int64_t off_u_right;    /* double[n_features]  mvFeatsRightU */
+  int64_t off_depth;      /* double[n_features]  mvDepths */
+  int32_t n_features, reserved;
+} orbx_record_layout;
+int orbx_record_layout_get(const orbx_ctx *ctx, orbx_record_layout *out);
+
+typedef struct orbx_sequence_io {
+  const uint8_t *left, *right; /* THIS RANK'S block: local frame i (global lo + i) at base + i * frame_stride, rows `stride` apart */
+  size_t stride, frame_stride;
+  int32_t input_on_device;     /* 0: host memory (pinned makes the copies asynchronous); 1: device memory, read in place */
+  int32_t records_on_device;   /* where `records` lives */
+  void *records;               /* [n_local][record_stride] or NULL; 16-byte aligned */
+  size_t record_stride;        /* >= orbx_record_layout.record_bytes, multiple of 16 */
+  uint8_t *gathered_desc_host; /* optional host copies of the gathered arrays: [n_frames_total][n_features][32] / [n_frames_total] */
+  int32_t *gathered_n_host;
+} orbx_sequence_io;
+
+typedef struct orbx_sequence_result {
+  int64_t frame_lo, frame_hi;   /* this rank's block */
+  int64_t block;                /* ceil(F / world) */
+  const uint8_t *gathered_desc; /* DEVICE [world * block][n_features][32]: row f = left descriptors of global frame f (zero beyond its count) */
+  const int32_t *gathered_n;    /* DEVICE [world * block]: left keypoints of global frame f (0 for the padding rows f >= F) */
+  int32_t n_features, world;
+} orbx_sequence_result;
+
+/* Collective over the communicator (comm == NULL: a single rank).  Blocks until this rank's records have landed and -- NCCL /
+ * multi-process transports -- the gathered arrays are complete on this rank.  The frames stream through the context's
+ * max_batch device slots in chunks on the pipeline streams (H2D of one chunk, kernels of another, D2H of a third overlap). */
+int orbx_sequence_stereo(orbx_ctx *ctx, orbx_comm *comm, int64_t n_frames_total, const orbx_sequence_io *io, orbx_sequence_result *out);
 
 /* ---- tracking-side Hamming matchers -------------------------------------- */
 /* One query of VirtualFrame::findFeaturesInArea (src/Frame.cc:286-311): the keypoint `kp` (position in undistorted

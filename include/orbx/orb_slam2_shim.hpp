@@ -20,6 +20,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -97,18 +98,29 @@ struct CtxKey
   bool operator<(const CtxKey &o) const { return tie() < o.tie(); }
 };
 
-struct CtxDeleter
+// A context is not re-entrant (include/orbx.h): the cache hands every host thread its OWN context per configuration, so
+// the reference's pattern of two extract() calls on two std::threads (src/Frame.cc:100-105) runs on two contexts, and
+// every call into a context holds its mutex (a Frame may be queried from another thread than the one that made it).
+struct Context
 {
-  void operator()(orbx_ctx *c) const { orbx_destroy(c); }
+  orbx_ctx *raw = nullptr;
+  std::mutex mu;
+  explicit Context(orbx_ctx *c) : raw(c) {}
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  ~Context() { orbx_destroy(raw); }
 };
+typedef std::shared_ptr<Context> ContextPtr;
+typedef std::lock_guard<std::mutex> Lock;
 
-inline std::shared_ptr<orbx_ctx> context_for(int w, int h, int nFeatures, int nLevels, float scale, const std::string &tmpl, int iniTh, int minTh, float dScale)
+inline ContextPtr context_for(int w, int h, int nFeatures, int nLevels, float scale, const std::string &tmpl, int iniTh, int minTh, float dScale)
 {
   static std::mutex mtx;
-  static std::map<CtxKey, std::shared_ptr<orbx_ctx>> cache;
+  static std::map<std::pair<CtxKey, std::thread::id>, ContextPtr> cache;
   CtxKey key{w, h, nFeatures, nLevels, iniTh, minTh, scale, Camera::mfFx, Camera::mfFy, Camera::mfCx, Camera::mfCy, Camera::mfBf, dScale, Camera::mDistCoeff, tmpl};
+  const auto full = std::make_pair(key, std::this_thread::get_id());
   std::lock_guard<std::mutex> lock(mtx);
-  auto it = cache.find(key);
+  auto it = cache.find(full);
   if (it != cache.end()) return it->second;
   std::vector<float> pattern(1024);
   check(nullptr, orbx_load_brief_template(tmpl.c_str(), pattern.data()), "BRIEF template"); // FileNotOpenError (:247-250)
@@ -132,8 +144,8 @@ inline std::shared_ptr<orbx_ctx> context_for(int w, int h, int nFeatures, int nL
   cfg.pattern = pattern.data();
   orbx_ctx *raw = nullptr;
   check(nullptr, orbx_create(&cfg, &raw), "orbx_create"); // ImageSizeError (:310-314)
-  std::shared_ptr<orbx_ctx> sp(raw, CtxDeleter());
-  cache[key] = sp;
+  ContextPtr sp = std::make_shared<Context>(raw);
+  cache[full] = sp;
   return sp;
 }
 
@@ -175,28 +187,51 @@ public:
   typedef std::shared_ptr<ORBExtractor> SharedPtr;
 
   ORBExtractor(const cv::Mat &image, int nFeatures, int pyramidLevels, float scaleFactor, const std::string &bfTemFp, int maxThreshold, int minThreshold)
-      : mImage(image), mnFeats(nFeatures)
+      : mImage(image), mnFeats(nFeatures), mnPyrLevels(pyramidLevels), mfScale(scaleFactor), mTmpl(bfTemFp), mIniTh(maxThreshold), mMinTh(minThreshold)
   {
-    mCtx = detail::context_for(image.cols, image.rows, nFeatures, pyramidLevels, scaleFactor, bfTemFp, maxThreshold, minThreshold, 1.f);
+    // FileNotOpenError / ImageSizeError surface here, as in the reference's constructor (src/ORBExtractor.cc:205-214)
+    detail::ContextPtr ctx = context();
     // the reference keeps these as process-wide statics initialised by the first constructor (src/ORBExtractor.cc:283-302)
     mnLevels = pyramidLevels;
     mfScaledFactor = scaleFactor;
-    scaledFactors().resize((size_t)pyramidLevels);
-    for (int l = 0; l < pyramidLevels; ++l) detail::check(mCtx.get(), orbx_level_info(mCtx.get(), l, nullptr, nullptr, &scaledFactors()[(size_t)l], nullptr), "orbx_level_info");
+    std::vector<float> sf((size_t)pyramidLevels);
+    for (int l = 0; l < pyramidLevels; ++l) detail::check(ctx->raw, orbx_level_info(ctx->raw, l, nullptr, nullptr, &sf[(size_t)l], nullptr), "orbx_level_info");
+    static std::mutex sfm;
+    detail::Lock lock(sfm);
+    scaledFactors() = sf;
   }
 
+  // Runs on the CALLING thread's context (two extractors of one configuration may extract concurrently on two threads).
   void extract(std::vector<cv::KeyPoint> &keyPoints, std::vector<cv::Mat> &descriptors)
   {
-    std::vector<orbx_keypoint> k((size_t)mnFeats);
-    mDescBlock = cv::Mat(mnFeats, 32, CV_8U);
-    int32_t n = 0;
-    detail::check(mCtx.get(), orbx_extract(mCtx.get(), mImage.data, (size_t)mImage.step, k.data(), mDescBlock.data, &n), "orbx_extract");
-    detail::to_cv(k, n, keyPoints);
-    detail::to_cv(mDescBlock, n, descriptors);
-    mvPyramids = detail::fetch_pyramid(mCtx.get(), 0);
+    detail::Lock self(mMu);
+    run(&keyPoints, &descriptors);
+    mvPyramids.clear(); // fetched on demand (getPyramid)
   }
 
-  const std::vector<cv::Mat> &getPyramid() const { return mvPyramids; }
+  // The reference builds the pyramid in the constructor (src/ORBExtractor.cc:205-214), so it is valid from then on; here it is
+  // produced by the same launches as the keypoints and copied back only when asked for.  If the context has moved on to
+  // another image since extract() (or extract() was never called), the image is simply run again.
+  const std::vector<cv::Mat> &getPyramid() const
+  {
+    detail::Lock self(mMu);
+    if (!mvPyramids.empty()) return mvPyramids;
+    bool fresh = false;
+    if (mCtx)
+    {
+      detail::Lock lock(mCtx->mu);
+      if (orbx_frame_epoch(mCtx->raw) == mEpoch)
+      {
+        mvPyramids = detail::fetch_pyramid(mCtx->raw, 0);
+        fresh = true;
+      }
+    }
+    if (!fresh)
+    {
+      const_cast<ORBExtractor *>(this)->run(nullptr, nullptr, true);
+    }
+    return mvPyramids;
+  }
   static const std::vector<float> &getScaledFactors() { return scaledFactors(); }
 
   static inline int mnLevels = 0;
@@ -209,11 +244,30 @@ private:
     static std::vector<float> v;
     return v;
   }
+  detail::ContextPtr context() const { return detail::context_for(mImage.cols, mImage.rows, mnFeats, mnPyrLevels, mfScale, mTmpl, mIniTh, mMinTh, 1.f); }
+  void run(std::vector<cv::KeyPoint> *keyPoints, std::vector<cv::Mat> *descriptors, bool want_pyramid = false)
+  {
+    mCtx = context();
+    detail::Lock lock(mCtx->mu);
+    std::vector<orbx_keypoint> k((size_t)mnFeats);
+    mDescBlock = cv::Mat(mnFeats, 32, CV_8U);
+    int32_t n = 0;
+    detail::check(mCtx->raw, orbx_extract(mCtx->raw, mImage.data, (size_t)mImage.step, k.data(), mDescBlock.data, &n), "orbx_extract");
+    mEpoch = orbx_frame_epoch(mCtx->raw);
+    if (keyPoints) detail::to_cv(k, n, *keyPoints);
+    if (descriptors) detail::to_cv(mDescBlock, n, *descriptors);
+    if (want_pyramid) mvPyramids = detail::fetch_pyramid(mCtx->raw, 0);
+  }
   cv::Mat mImage;
-  int mnFeats;
-  std::shared_ptr<orbx_ctx> mCtx;
+  int mnFeats, mnPyrLevels;
+  float mfScale;
+  std::string mTmpl;
+  int mIniTh, mMinTh;
+  mutable std::mutex mMu;
+  mutable detail::ContextPtr mCtx; // the context the last extract() ran on
+  mutable uint64_t mEpoch = 0;     // ... and its epoch right after it
   cv::Mat mDescBlock;
-  std::vector<cv::Mat> mvPyramids;
+  mutable std::vector<cv::Mat> mvPyramids;
 };
 
 class ORBMatcher;
@@ -225,9 +279,10 @@ class Vocabulary
 {
 public:
   // text vocabulary (ORB-SLAM2's ORBvoc.txt layout); the tree lives on the device of the context for (width, height, ...)
-  Vocabulary(const std::string &filename, std::shared_ptr<orbx_ctx> ctx) : mCtx(std::move(ctx))
+  Vocabulary(const std::string &filename, detail::ContextPtr ctx) : mCtx(std::move(ctx))
   {
-    detail::check(mCtx.get(), orbx_vocab_load_text(mCtx.get(), filename.c_str(), &mVoc), "orbx_vocab_load_text");
+    detail::Lock lock(mCtx->mu);
+    detail::check(mCtx->raw, orbx_vocab_load_text(mCtx->raw, filename.c_str(), &mVoc), "orbx_vocab_load_text");
   }
   ~Vocabulary() { orbx_vocab_destroy(mVoc); }
   Vocabulary(const Vocabulary &) = delete;
@@ -241,7 +296,7 @@ public:
   const orbx_vocab *handle() const { return mVoc; }
 
 private:
-  std::shared_ptr<orbx_ctx> mCtx;
+  detail::ContextPtr mCtx;
   orbx_vocab *mVoc = nullptr;
 };
 
@@ -263,15 +318,24 @@ public:
     f->mCapacity = nFeatures;
     f->mLeftIm = colorImg;
     f->mCtx = detail::context_for(colorImg.cols, colorImg.rows, nFeatures, nLevels, scale, briefF, maxThresh, minThresh, dScale);
+    if (depthImg.rows != colorImg.rows || depthImg.cols != colorImg.cols) throw ORBSlam2Error("createRGBD: depth image size differs from the colour image");
+    if (depthImg.type() != CV_16U && depthImg.type() != CV_32F)
+    { // any other depth type goes through the reference's own conversion (depthImg.convertTo(CV_32F), src/Frame.cc:130)
+      cv::Mat asFloat;
+      depthImg.convertTo(asFloat, CV_32F);
+      depthImg = asFloat;
+    }
     const int dtype = depthImg.type() == CV_32F ? ORBX_DEPTH_F32 : ORBX_DEPTH_U16;
+    detail::Lock lock(f->mCtx->mu);
     std::vector<orbx_keypoint> kraw((size_t)nFeatures), kund((size_t)nFeatures);
     f->mDescLeft = cv::Mat(nFeatures, 32, CV_8U);
     std::vector<double> ur((size_t)nFeatures), dp((size_t)nFeatures);
     int32_t n = 0;
-    detail::check(f->mCtx.get(),
-                  orbx_rgbd_frame(f->mCtx.get(), colorImg.data, (size_t)colorImg.step, depthImg.data, (size_t)depthImg.step, dtype, kraw.data(), kund.data(),
+    detail::check(f->mCtx->raw,
+                  orbx_rgbd_frame(f->mCtx->raw, colorImg.data, (size_t)colorImg.step, depthImg.data, (size_t)depthImg.step, dtype, kraw.data(), kund.data(),
                                   f->mDescLeft.data, &n, ur.data(), dp.data()),
                   "orbx_rgbd_frame");
+    f->mEpoch = orbx_frame_epoch(f->mCtx->raw);
     detail::to_cv(kund, n, f->mvFeatsLeft);
     detail::to_cv(f->mDescLeft, n, f->mvLeftDescriptor);
     f->mvFeatsRightU.assign(ur.begin(), ur.begin() + n);
@@ -294,11 +358,12 @@ public:
   typedef std::vector<std::vector<std::vector<std::size_t>>> GridsType;
   GridsType getGrids() const
   {
+    Resident here(*this, "getGrids");
     int32_t rows = 0, cols = 0;
-    detail::check(mCtx.get(), orbx_grid_info(mCtx.get(), &rows, &cols, nullptr, nullptr, nullptr, nullptr), "orbx_grid_info");
+    detail::check(mCtx->raw, orbx_grid_info(mCtx->raw, &rows, &cols, nullptr, nullptr, nullptr, nullptr), "orbx_grid_info");
     std::vector<int32_t> start((size_t)rows * cols + 1);
     std::vector<int32_t> all((size_t)orbx_capacity());
-    detail::check(mCtx.get(), orbx_get_grid(mCtx.get(), 0, start.data(), all.data()), "orbx_get_grid");
+    detail::check(mCtx->raw, orbx_get_grid(mCtx->raw, 0, start.data(), all.data()), "orbx_get_grid");
     GridsType g((size_t)rows, std::vector<std::vector<std::size_t>>((size_t)cols));
     for (int r = 0; r < rows; ++r)
       for (int c = 0; c < cols; ++c)
@@ -309,9 +374,10 @@ public:
   // proto/Keyframe.proto:45-64), assembled on the device.  The frame must be the context's most recent one.
   std::string serializeKeyFrameData(uint64_t id, const float *poseRt /* R row-major [9] + t [3], or nullptr */ = nullptr, bool withMapPoints = true) const
   {
-    std::string out((size_t)orbx_serialized_capacity(mCtx.get()), '\0');
+    Resident here(*this, "serializeKeyFrameData");
+    std::string out((size_t)orbx_serialized_capacity(mCtx->raw), '\0');
     int64_t n = 0;
-    detail::check(mCtx.get(), orbx_serialize_keyframe(mCtx.get(), 0, id, poseRt, withMapPoints ? 1 : 0, (uint8_t *)&out[0], out.size(), &n),
+    detail::check(mCtx->raw, orbx_serialize_keyframe(mCtx->raw, 0, id, poseRt, withMapPoints ? 1 : 0, (uint8_t *)&out[0], out.size(), &n),
                   "orbx_serialize_keyframe");
     out.resize((size_t)n);
     return out;
@@ -319,12 +385,13 @@ public:
   // VirtualFrame::computeBow (include/ORB_SLAM2/Frame.h:224-231): mpVoc->transform(mvLeftDescriptor, mBowVec, mFeatVec, 4)
   void computeBow(const Vocabulary &voc, BowVector &bowVec, FeatureVector &featVec, int levelsup = 4) const
   {
+    Resident here(*this, "computeBow");
     const std::size_t N = (std::size_t)orbx_capacity();
     std::vector<int32_t> ids(N), nodes(N), start(N + 1), feats(N);
     std::vector<double> vals(N);
     int32_t nb = 0, nf = 0;
-    detail::check(mCtx.get(),
-                  orbx_bow_transform(mCtx.get(), voc.handle(), 0, levelsup, ids.data(), vals.data(), &nb, nodes.data(), start.data(), feats.data(), &nf),
+    detail::check(mCtx->raw,
+                  orbx_bow_transform(mCtx->raw, voc.handle(), 0, levelsup, ids.data(), vals.data(), &nb, nodes.data(), start.data(), feats.data(), &nf),
                   "orbx_bow_transform");
     bowVec.clear();
     featVec.clear();
@@ -333,9 +400,17 @@ public:
       featVec.emplace_hint(featVec.end(), (unsigned)nodes[(std::size_t)j],
                            std::vector<unsigned>(feats.begin() + start[(std::size_t)j], feats.begin() + start[(std::size_t)j + 1]));
   }
-  std::shared_ptr<orbx_ctx> context() const { return mCtx; }
-  std::vector<cv::Mat> getLeftPyramid() const { return detail::fetch_pyramid(mCtx.get(), 0); }
-  std::vector<cv::Mat> getRightPyramid() const { return detail::fetch_pyramid(mCtx.get(), 1); }
+  detail::ContextPtr context() const { return mCtx; }
+  std::vector<cv::Mat> getLeftPyramid() const
+  {
+    Resident here(*this, "getLeftPyramid");
+    return detail::fetch_pyramid(mCtx->raw, 0);
+  }
+  std::vector<cv::Mat> getRightPyramid() const
+  {
+    Resident here(*this, "getRightPyramid");
+    return detail::fetch_pyramid(mCtx->raw, 1);
+  }
   int getN() const { return mnN; }
 
 private:
@@ -349,7 +424,22 @@ private:
   int mStereoMatches = 0;
   int mnN = 0;
   cv::Mat mLeftIm, mRightIm, mDescLeft, mDescRight;
-  std::shared_ptr<orbx_ctx> mCtx;
+  detail::ContextPtr mCtx;
+  uint64_t mEpoch = 0; // the context's epoch right after this frame was made: device-side queries need it unchanged
+
+  // Holds the frame's context for one query and checks that the frame is still the one resident on it: the context keeps the
+  // device state (pyramids, grid, descriptors) of its MOST RECENT frame only, so a query on an older Frame must not silently
+  // answer with the newer frame's data.
+  struct Resident
+  {
+    detail::Lock lock;
+    Resident(const Frame &f, const char *what) : lock(f.mCtx->mu)
+    {
+      if (orbx_frame_epoch(f.mCtx->raw) != f.mEpoch)
+        throw ORBSlam2Error(std::string(what) + ": this Frame is no longer resident on its device context (a newer frame was created on the same thread and "
+                                                "configuration); query a frame before creating the next one");
+    }
+  };
 };
 
 // ---- the stereo entry (include/ORB_SLAM2/ORBMatcher.h:39) and the projection matchers (:50-53) ---------------------------------------------------------
@@ -400,8 +490,9 @@ public:
     }
     std::vector<int32_t> idx(n), dist(n), nc(n);
     std::vector<float> ratio(n);
-    detail::check(pFrame->mCtx.get(),
-                  orbx_search_in_area(pFrame->mCtx.get(), 0, (int)n, q.data(), qd.data(), exclude ? ex.data() : nullptr, idx.data(), dist.data(), ratio.data(),
+    Frame::Resident here(*pFrame, "searchInArea");
+    detail::check(pFrame->mCtx->raw,
+                  orbx_search_in_area(pFrame->mCtx->raw, 0, (int)n, q.data(), qd.data(), exclude ? ex.data() : nullptr, idx.data(), dist.data(), ratio.data(),
                                       nc.data()),
                   "orbx_search_in_area");
     std::vector<AreaMatch> out(n);
@@ -474,10 +565,13 @@ public:
     }
     std::vector<int32_t> idx(nl), dist(nl), nc(nl);
     std::vector<float> ratio(nl);
-    detail::check(pFrame->mCtx.get(),
-                  orbx_search_by_bow(pFrame->mCtx.get(), 0, (int)nodes.size(), nodes.data(), start.data(), feats.data(), kd.data(), (int)nk, qok.data(),
+    {
+      Frame::Resident here(*pFrame, "searchByBow");
+      detail::check(pFrame->mCtx->raw,
+                  orbx_search_by_bow(pFrame->mCtx->raw, 0, (int)nodes.size(), nodes.data(), start.data(), feats.data(), kd.data(), (int)nk, qok.data(),
                                      cok.data(), idx.data(), dist.data(), ratio.data(), nc.data()),
                   "orbx_search_by_bow");
+    }
     for (std::size_t e = 0; e < nl; ++e)
       if (nc[e] > 0 && !(dist[e] > mnMinThreshold || ratio[e] > mfRatio)) matches.emplace_back(idx[e], feats[e], (float)dist[e]); // :240-245
     if (mbCheckOri) verifyAngle(pFrame, matches, pFrame->getLeftKeyPoints(), kfKeyPoints);
@@ -496,8 +590,9 @@ public:
     if (!k1.empty()) std::memcpy(k1.data(), keyPoints1.data(), k1.size() * sizeof(orbx_keypoint));
     if (!k2.empty()) std::memcpy(k2.data(), keyPoints2.data(), k2.size() * sizeof(orbx_keypoint));
     int32_t m = 0;
-    detail::check(owner->mCtx.get(),
-                  orbx_verify_angle(owner->mCtx.get(), (int)n, qi.data(), ti.data(), di.data(), k1.data(), (int)k1.size(), k2.data(), (int)k2.size(), &m),
+    detail::Lock lock(owner->mCtx->mu);
+    detail::check(owner->mCtx->raw,
+                  orbx_verify_angle(owner->mCtx->raw, (int)n, qi.data(), ti.data(), di.data(), k1.data(), (int)k1.size(), k2.data(), (int)k2.size(), &m),
                   "orbx_verify_angle");
     matches.resize((std::size_t)m);
     for (int i = 0; i < m; ++i) matches[(std::size_t)i] = cv::DMatch(qi[(std::size_t)i], ti[(std::size_t)i], di[(std::size_t)i]);
@@ -526,10 +621,14 @@ inline Frame::SharedPtr Frame::createStereo(cv::Mat leftImg, cv::Mat rightImg, i
   f->mStereoU.resize((size_t)nFeatures);
   f->mStereoDepth.resize((size_t)nFeatures);
   int32_t nl = 0, nr = 0, nm = 0;
-  detail::check(f->mCtx.get(),
-                orbx_stereo_frame(f->mCtx.get(), leftImg.data, (size_t)leftImg.step, rightImg.data, (size_t)rightImg.step, kl.data(), f->mDescLeft.data, &nl,
+  {
+    detail::Lock lock(f->mCtx->mu);
+    detail::check(f->mCtx->raw,
+                orbx_stereo_frame(f->mCtx->raw, leftImg.data, (size_t)leftImg.step, rightImg.data, (size_t)rightImg.step, kl.data(), f->mDescLeft.data, &nl,
                                   kr.data(), f->mDescRight.data, &nr, f->mStereoU.data(), f->mStereoDepth.data(), &nm),
                 "orbx_stereo_frame");
+    f->mEpoch = orbx_frame_epoch(f->mCtx->raw);
+  }
   detail::to_cv(kl, nl, f->mvFeatsLeft);
   detail::to_cv(kr, nr, f->mvFeatsRight);
   detail::to_cv(f->mDescLeft, nl, f->mvLeftDescriptor);

@@ -29,6 +29,9 @@ ORBX_ERR_CUDA = -4
 ORBX_ERR_NO_DEVICE = -5
 ORBX_ERR_CAPACITY = -6
 ORBX_ERR_STATE = -7
+ORBX_ERR_COMM = -8
+COMM_ID_BYTES, IPC_HANDLE_BYTES = 128, 64
+TRANSPORT_NONE, TRANSPORT_NCCL, TRANSPORT_PEER = 0, 1, 2
 DEPTH_U16, DEPTH_F32 = 0, 1
 N_STAGES = 6  # ORBX_N_STAGES
 
@@ -76,7 +79,25 @@ EXPORTS = [
     "orbx_serialized_capacity", "orbx_serialize_keyframe", "orbx_serialize_keyframes_device",
     "orbx_vocab_create", "orbx_vocab_load_text", "orbx_vocab_destroy", "orbx_vocab_info", "orbx_bow_transform", "orbx_bow_transform_batch_device",
     "orbx_search_by_bow",
+    "orbx_frame_epoch", "orbx_set_graph", "orbx_frame_range", "orbx_comm_unique_id", "orbx_comm_create", "orbx_comm_ipc_handle", "orbx_comm_open_peers",
+    "orbx_comm_create_local", "orbx_comm_destroy", "orbx_comm_info", "orbx_record_layout_get", "orbx_sequence_stereo",
 ]
+
+class OrbxRecordLayout(C.Structure):
+    _fields_ = [("record_bytes", C.c_int64), ("off_kps_left", C.c_int64), ("off_desc_left", C.c_int64), ("off_kps_right", C.c_int64),
+                ("off_desc_right", C.c_int64), ("off_u_right", C.c_int64), ("off_depth", C.c_int64), ("n_features", C.c_int32), ("reserved", C.c_int32)]
+
+
+class OrbxSequenceIO(C.Structure):
+    _fields_ = [("left", C.c_void_p), ("right", C.c_void_p), ("stride", C.c_size_t), ("frame_stride", C.c_size_t), ("input_on_device", C.c_int32),
+                ("records_on_device", C.c_int32), ("records", C.c_void_p), ("record_stride", C.c_size_t), ("gathered_desc_host", C.c_void_p),
+                ("gathered_n_host", C.c_void_p)]
+
+
+class OrbxSequenceResult(C.Structure):
+    _fields_ = [("frame_lo", C.c_int64), ("frame_hi", C.c_int64), ("block", C.c_int64), ("gathered_desc", C.c_void_p), ("gathered_n", C.c_void_p),
+                ("n_features", C.c_int32), ("world", C.c_int32)]
+
 
 class OrbxDeviceBow(C.Structure):
     _fields_ = [("bow_ids", C.c_void_p), ("bow_vals", C.c_void_p), ("n_bow", C.c_void_p), ("fv_nodes", C.c_void_p), ("fv_start", C.c_void_p),
@@ -149,6 +170,21 @@ def load_library(build_if_missing: bool = True):
     L.orbx_bow_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int32), vp, vp, vp, C.POINTER(C.c_int32)]
     L.orbx_bow_transform_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(OrbxDeviceBow)]
     L.orbx_search_by_bow.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.orbx_frame_epoch.argtypes = [vp]
+    L.orbx_set_graph.argtypes = [vp, C.c_int]
+    L.orbx_frame_epoch.restype = C.c_uint64
+    L.orbx_frame_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.orbx_frame_range.restype = None
+    L.orbx_comm_unique_id.argtypes = [vp]
+    L.orbx_comm_create.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, C.POINTER(vp)]
+    L.orbx_comm_ipc_handle.argtypes = [vp, vp]
+    L.orbx_comm_open_peers.argtypes = [vp, vp]
+    L.orbx_comm_create_local.argtypes = [C.POINTER(vp), C.c_int, C.c_int64, C.POINTER(vp)]
+    L.orbx_comm_destroy.argtypes = [vp]
+    L.orbx_comm_destroy.restype = None
+    L.orbx_comm_info.argtypes = [vp] + [C.POINTER(C.c_int32)] * 3
+    L.orbx_record_layout_get.argtypes = [vp, C.POINTER(OrbxRecordLayout)]
+    L.orbx_sequence_stereo.argtypes = [vp, vp, C.c_int64, C.POINTER(OrbxSequenceIO), C.POINTER(OrbxSequenceResult)]
     _lib = L
     return L
 
@@ -164,7 +200,7 @@ def _check(ctx, rc: int, what: str):
         raise ImageSizeError(text)
     if rc == ORBX_ERR_FILE_NOT_OPEN:
         raise FileNotOpenError(text)
-    if rc in (ORBX_ERR_CUDA, ORBX_ERR_NO_DEVICE):
+    if rc in (ORBX_ERR_CUDA, ORBX_ERR_NO_DEVICE, ORBX_ERR_COMM):
         raise OrbxCudaError(text)
     raise ValueError(text)
 
@@ -249,6 +285,10 @@ class Context:
         else:
             ptr = int(cuda_stream_ptr) or 1  # cudaStreamLegacy == (cudaStream_t)0x1
         _check(self._h, self._L.orbx_set_stream(self._h, C.c_void_p(ptr)), "orbx_set_stream")
+
+    def set_graph(self, enable: bool):
+        """single-pair calls as one CUDA graph launch (default) or as plain stream launches"""
+        _check(self._h, self._L.orbx_set_graph(self._h, int(bool(enable))), "orbx_set_graph")
 
     def synchronize(self):
         _check(self._h, self._L.orbx_synchronize(self._h), "orbx_synchronize")
@@ -481,6 +521,50 @@ class Context:
         _check(self._h, rc, "orbx_profile_stereo_batch_device")
         return {self._L.orbx_stage_name(i).decode(): float(ms[i]) for i in range(N_STAGES)}
 
+    # ---- whole sequences sharded by frame --------------------------------------------------------
+    @property
+    def frame_epoch(self) -> int:
+        return int(self._L.orbx_frame_epoch(self._h))
+
+    def record_layout(self) -> OrbxRecordLayout:
+        lay = OrbxRecordLayout()
+        _check(self._h, self._L.orbx_record_layout_get(self._h, C.byref(lay)), "orbx_record_layout_get")
+        return lay
+
+    def record_dtype(self) -> np.dtype:
+        """numpy view of one frame record (orbx_record_layout): fields n_left, n_right, n_matches, kps_left, desc_left, ..."""
+        lay, N = self.record_layout(), self.n_features
+        return np.dtype({"names": ["n_left", "n_right", "n_matches", "kps_left", "desc_left", "kps_right", "desc_right", "u_right", "depth"],
+                         "formats": ["<i4", "<i4", "<i4", (KP_DTYPE, (N,)), ("u1", (N, 32)), (KP_DTYPE, (N,)), ("u1", (N, 32)), ("<f8", (N,)), ("<f8", (N,))],
+                         "offsets": [0, 4, 8, lay.off_kps_left, lay.off_desc_left, lay.off_kps_right, lay.off_desc_right, lay.off_u_right, lay.off_depth],
+                         "itemsize": lay.record_bytes})
+
+    def sequence_stereo_ptr(self, n_frames_total: int, left_ptr: int, right_ptr: int, stride: int, frame_stride: int, comm: "Communicator | None" = None,
+                            input_on_device: bool = False, records_ptr: int = 0, record_stride: int = 0, records_on_device: bool = False,
+                            gathered_desc_host_ptr: int = 0, gathered_n_host_ptr: int = 0) -> OrbxSequenceResult:
+        """orbx_sequence_stereo on raw pointers: left/right = THIS RANK'S block of the sequence"""
+        io = OrbxSequenceIO(left_ptr, right_ptr, stride, frame_stride, int(input_on_device), int(records_on_device), records_ptr or None,
+                            record_stride, gathered_desc_host_ptr or None, gathered_n_host_ptr or None)
+        res = OrbxSequenceResult()
+        rc = self._L.orbx_sequence_stereo(self._h, comm._h if comm is not None else None, n_frames_total, C.byref(io), C.byref(res))
+        _check(self._h, rc, "orbx_sequence_stereo")
+        return res
+
+    def sequence_stereo(self, left: np.ndarray, right: np.ndarray, n_frames_total: int | None = None, comm: "Communicator | None" = None,
+                        gather_to_host: bool = True):
+        """left/right: (n_local, H, W) uint8 host arrays holding this rank's block.  -> (records, gathered_desc, gathered_n):
+        records = numpy structured array (record_dtype) of the block's frames; gathered_* cover the WHOLE sequence."""
+        n = left.shape[0]
+        F = n if n_frames_total is None else int(n_frames_total)
+        assert left.shape == right.shape == (n, self.height, self.width) and left.strides == right.strides and left.dtype == np.uint8
+        rec = np.zeros(max(n, 1), self.record_dtype())
+        gd = np.zeros((F, self.n_features, 32), np.uint8) if gather_to_host else None
+        gn = np.zeros(F, np.int32) if gather_to_host else None
+        res = self.sequence_stereo_ptr(F, left.ctypes.data, right.ctypes.data, left.strides[1], left.strides[0], comm, False, rec.ctypes.data,
+                                       rec.dtype.itemsize, False, gd.ctypes.data if gather_to_host else 0, gn.ctypes.data if gather_to_host else 0)
+        assert res.frame_hi - res.frame_lo == n, "left/right must hold exactly this rank's block (orbx_frame_range)"
+        return rec[:n], gd, gn
+
     def extract_batch_device(self, n_images, d_ptr, stride, frame_stride) -> OrbxDeviceResults:
         res = OrbxDeviceResults()
         rc = self._L.orbx_extract_batch_device(self._h, n_images, C.c_void_p(d_ptr), stride, frame_stride, C.byref(res))
@@ -493,6 +577,70 @@ class Context:
                                             C.byref(res))
         _check(self._h, rc, "orbx_rgbd_batch_device")
         return res
+
+
+def frame_range(n_frames_total: int, rank: int, world: int) -> range:
+    """orbx_frame_range: the contiguous block of rank `rank`"""
+    lo, hi = C.c_int64(), C.c_int64()
+    load_library().orbx_frame_range(n_frames_total, rank, world, C.byref(lo), C.byref(hi))
+    return range(lo.value, hi.value)
+
+
+class Communicator:
+    """orbx_comm: the ranks that share one frame-sharded sequence.  Multi-process: rank 0 makes `unique_id()`, ships it to
+    the others (e.g. torch.distributed.broadcast_object_list), every rank builds Communicator(ctx, rank, world, id, F)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, unique_id: bytes, max_frames_total: int, _handle=None):
+        self._L, self.ctx = ctx._L, ctx
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+            return
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        _check(ctx._h, self._L.orbx_comm_create(ctx._h, rank, world, buf, max_frames_total, C.byref(self._h)), "orbx_comm_create")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        _check(None, load_library().orbx_comm_unique_id(buf), "orbx_comm_unique_id")
+        return bytes(buf)
+
+    @staticmethod
+    def local(ctxs, max_frames_total: int):
+        """one process driving len(ctxs) ranks (peer-memory transport, no NCCL) -> list of Communicators"""
+        L = load_library()
+        n = len(ctxs)
+        hs = (C.c_void_p * n)(*[c._h for c in ctxs])
+        out = (C.c_void_p * n)()
+        _check(ctxs[0]._h, L.orbx_comm_create_local(hs, n, max_frames_total, out), "orbx_comm_create_local")
+        return [Communicator(ctxs[r], r, n, b"", max_frames_total, _handle=C.c_void_p(out[r])) for r in range(n)]
+
+    def ipc_handle(self) -> bytes:
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        _check(self.ctx._h, self._L.orbx_comm_ipc_handle(self._h, buf), "orbx_comm_ipc_handle")
+        return bytes(buf)
+
+    def open_peers(self, handles):
+        """handles[r] = rank r's ipc_handle(); switches the data path to peer-memory stores (ORBX_TRANSPORT_PEER)"""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(self.ctx._h, self._L.orbx_comm_open_peers(self._h, buf), "orbx_comm_open_peers")
+
+    def info(self):
+        v = [C.c_int32() for _ in range(3)]
+        self._L.orbx_comm_info(self._h, *[C.byref(x) for x in v])
+        return dict(rank=v[0].value, world=v[1].value, transport=v[2].value)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.orbx_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _as_u8(a: np.ndarray, h: int, w: int) -> np.ndarray:

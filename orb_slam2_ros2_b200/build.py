@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liborbx.so")
-SOURCES = ["orbx_kernels.cu", "orbx_match.cu", "orbx_serialize.cu", "orbx_bow.cu", "orbx_api.cu"]
-HEADERS = [os.path.join(CSRC, "orbx_device.cuh"), os.path.join(HERE, "..", "include", "orbx.h"), os.path.join(HERE, "..", "include", "orbx_pattern.h")]
+SOURCES = ["orbx_kernels.cu", "orbx_match.cu", "orbx_serialize.cu", "orbx_bow.cu", "orbx_sequence.cu", "orbx_api.cu"]
+HEADERS = [os.path.join(CSRC, "orbx_device.cuh"), os.path.join(CSRC, "orbx_internal.h"), os.path.join(HERE, "..", "include", "orbx.h"), os.path.join(HERE, "..", "include", "orbx_pattern.h")]
 
 
 def nvcc_cmd(extra=()):
@@ -25,7 +25,7 @@ def nvcc_cmd(extra=()):
         "-O3", "-lineinfo", "-std=c++17",
         "-ccbin", "/usr/bin/g++",  # the image's CC/CXX=/opt/gcc links libstdc++ statically (dangling symlink)
         "-Xcompiler", "-fPIC,-O2,-Wall",
-        "-shared", "-cudart", "static", "--threads", "5",
+        "-shared", "-cudart", "static", "--threads", "6",
         *extra,
         "-o", LIB,
         *[os.path.join(CSRC, s) for s in SOURCES],

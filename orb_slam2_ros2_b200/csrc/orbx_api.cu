@@ -14,52 +14,12 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/orbx_pattern.h"
-#include "orbx_device.cuh"
+#include "orbx_internal.h"
 
 using namespace orbx;
-
-struct orbx_ctx
-{
-  orbx_config cfg;
-  int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  int n_img_max = 0;
-  std::vector<Level> levels;
-  std::vector<Tile> tiles;
-  std::vector<Cell> cells;
-  Params p;            // template: geometry + base pointers
-  size_t qt_smem = 0;
-  std::string last_error;
-  int64_t launches = 0;
-  int64_t alg_bytes_image = 0, alg_bytes_stereo = 0;
-  // device allocations
-  std::vector<void *> allocs;
-  uint8_t *d_in = nullptr;      // staging for host-side calls: [n_img_max][H][in_pitch]
-  size_t in_pitch = 0;
-  uint8_t *d_depth_in = nullptr; // [max_batch][H][W] float/uint16 (sized for float)
-  int last_images = 0;          // images processed by the most recent call (for orbx_get_pyramid)
-  int last_stereo = 0;
-  int last_frames = 0;
-  LevelMaps maps; // TMA descriptors of the pyramid levels (kernel parameter, __grid_constant__)
-  float min_u = 0, min_v = 0, max_u = 0, max_v = 0; // undistorted image bounds (VirtualFrame ctor, Frame.h:33-43)
-  // host-batch pipeline: chunks of frames round-robin over kPipe streams so that H2D, kernels and D2H overlap
-  static constexpr int kPipeMax = 8;
-  int kPipe = 8;  // streams (tunable for experiments: ORBX_PIPE); 8 x 8 frames measured best on B200
-  int kChunk = 8; // frames per chunk (ORBX_CHUNK)
-  cudaStream_t pipe[kPipeMax] = {};
-  cudaEvent_t fork_ev = nullptr;
-  cudaEvent_t join_ev[kPipeMax] = {};
-  // staging for the host-side matcher calls (orbx_search_in_area / orbx_verify_angle), grown on demand
-  uint8_t *match_scratch = nullptr;
-  size_t match_scratch_bytes = 0;
-  // bag-of-words transform: per-feature and per-frame result buffers, allocated on first use
-  BowArgs bow{};
-  bool bow_ready = false;
-  uint64_t frame_epoch = 0;   // bumped by every call that produces frames
-  uint64_t bow_epoch = ~0ull; // frame_epoch at the last bag-of-words call
-  int bow_frames = 0;         // frames covered by that call
-};
 
 // DBoW3 vocabulary tree resident on one device
 struct orbx_vocab
@@ -81,19 +41,6 @@ inline int cv_floor(float v)
   int i = (int)v;
   return i - (i > v);
 }
-
-int fail(orbx_ctx *c, int code, const std::string &msg)
-{
-  if (c) c->last_error = msg;
-  return code;
-}
-
-#define ORBX_CUDA(ctx, expr)                                                                                         \
-  do                                                                                                                 \
-  {                                                                                                                  \
-    cudaError_t e__ = (expr);                                                                                        \
-    if (e__ != cudaSuccess) return fail((ctx), ORBX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
-  } while (0)
 
 template <typename T> int dev_alloc(orbx_ctx *c, T **ptr, size_t count)
 {
@@ -415,6 +362,17 @@ int alloc_buffers(orbx_ctx *c)
   return ORBX_OK;
 }
 
+} // namespace
+
+namespace orbx
+{
+
+int fail(orbx_ctx *c, int code, const std::string &msg)
+{
+  if (c) c->last_error = msg;
+  return code;
+}
+
 // Params whose per-image buffers start at image `img0` (and per-frame buffers at frame `frame0`)
 Params params_at(const orbx_ctx *c, int img0, int frame0)
 {
@@ -443,27 +401,133 @@ Params params_at(const orbx_ctx *c, int img0, int frame0)
   return p;
 }
 
-// the five kernels of a stereo batch for frames [frame0, frame0 + nf) on stream s
+// NVTX range around the enqueue of one stage (host side; profilers correlate the launches inside it)
+struct NvtxRange
+{
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+// the kernels of a stereo batch for device slots [frame0, frame0 + nf) on stream s
 int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint8_t *d_left, const uint8_t *d_right, size_t stride, size_t frame_stride)
 {
   Params p = params_at(c, 2 * frame0, frame0);
   p.stereo = 1;
-  p.in_left = d_left + (size_t)frame0 * frame_stride;
-  p.in_right = d_right + (size_t)frame0 * frame_stride;
+  p.in_left = d_left;
+  p.in_right = d_right;
   p.in_stride = stride;
   p.in_frame_stride = frame_stride;
+  NvtxRange r("orbx:stereo_range");
   ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)nf * sizeof(int), s));
-  launch_pyramid(p, 2 * nf, s);
-  launch_fast(p, c->maps, 2 * nf, s);
-  launch_quadtree(p, 2 * nf, c->qt_smem, s);
-  launch_orient_brief(p, 2 * nf, s);
-  launch_rowindex(p, nf, s);
-  launch_stereo(p, nf, s);
-  launch_grid(p, nf, 2, s);
+  {
+    NvtxRange q("orbx:pyramid_blur");
+    launch_pyramid(p, 2 * nf, s);
+  }
+  {
+    NvtxRange q("orbx:fast_cells");
+    launch_fast(p, c->maps, 2 * nf, s);
+  }
+  {
+    NvtxRange q("orbx:quadtree");
+    launch_quadtree(p, 2 * nf, c->qt_smem, s);
+  }
+  {
+    NvtxRange q("orbx:orient_brief");
+    launch_orient_brief(p, 2 * nf, s);
+  }
+  {
+    NvtxRange q("orbx:stereo_match");
+    launch_rowindex(p, nf, s);
+    launch_stereo(p, nf, s);
+  }
+  {
+    NvtxRange q("orbx:init_grid");
+    launch_grid(p, nf, 2, s);
+  }
   c->launches += 7;
   ORBX_CUDA(c, cudaGetLastError());
   return ORBX_OK;
 }
+
+static void drop_graph(orbx_ctx *c)
+{
+  if (c->graph1_exec) cudaGraphExecDestroy(c->graph1_exec);
+  if (c->graph1) cudaGraphDestroy(c->graph1);
+  c->graph1_exec = nullptr;
+  c->graph1 = nullptr;
+  c->graph1_pyr = nullptr;
+}
+
+int run_stereo_single(orbx_ctx *c, cudaStream_t s, const uint8_t *d_left, const uint8_t *d_right, size_t stride, size_t frame_stride)
+{
+  // the legacy / per-thread default streams cannot be captured
+  const bool can = c->use_graph && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  if (!can) return run_stereo_range(c, s, 0, 1, d_left, d_right, stride, frame_stride);
+  if (!c->graph1_exec)
+  {
+    const int64_t before = c->launches;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    { // e.g. the caller is capturing this stream already: plain launches
+      (void)cudaGetLastError();
+      return run_stereo_range(c, s, 0, 1, d_left, d_right, stride, frame_stride);
+    }
+    const int rc = run_stereo_range(c, s, 0, 1, d_left, d_right, stride, frame_stride);
+    const cudaError_t e = cudaStreamEndCapture(s, &c->graph1);
+    c->graph1_kernels = (int)(c->launches - before);
+    c->launches = before;
+    if (rc != ORBX_OK || e != cudaSuccess || cudaGraphInstantiate(&c->graph1_exec, c->graph1, 0) != cudaSuccess)
+    {
+      (void)cudaGetLastError();
+      drop_graph(c);
+      c->use_graph = 0;
+      return run_stereo_range(c, s, 0, 1, d_left, d_right, stride, frame_stride);
+    }
+    size_t n = 0;
+    cudaGraphGetNodes(c->graph1, nullptr, &n);
+    std::vector<cudaGraphNode_t> nodes(n);
+    cudaGraphGetNodes(c->graph1, nodes.data(), &n);
+    for (auto nd : nodes)
+    {
+      cudaGraphNodeType t;
+      cudaKernelNodeParams kp;
+      if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel && cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess &&
+          kp.func == pyramid_kernel_symbol())
+        c->graph1_pyr = nd;
+    }
+    if (!c->graph1_pyr)
+    {
+      drop_graph(c);
+      c->use_graph = 0;
+      return run_stereo_range(c, s, 0, 1, d_left, d_right, stride, frame_stride);
+    }
+    c->graph1_left = d_left, c->graph1_right = d_right, c->graph1_stride = stride, c->graph1_fs = frame_stride;
+  }
+  else if (d_left != c->graph1_left || d_right != c->graph1_right || stride != c->graph1_stride || frame_stride != c->graph1_fs)
+  {
+    // only the pyramid kernel reads the caller's images: patch that node's Params in the instantiated graph
+    cudaKernelNodeParams kp;
+    ORBX_CUDA(c, cudaGraphKernelNodeGetParams(c->graph1_pyr, &kp));
+    Params p = params_at(c, 0, 0);
+    p.stereo = 1;
+    p.in_left = d_left;
+    p.in_right = d_right;
+    p.in_stride = stride;
+    p.in_frame_stride = frame_stride;
+    void *args[1] = {&p};
+    kp.kernelParams = args;
+    kp.extra = nullptr;
+    ORBX_CUDA(c, cudaGraphExecKernelNodeSetParams(c->graph1_exec, c->graph1_pyr, &kp));
+    c->graph1_left = d_left, c->graph1_right = d_right, c->graph1_stride = stride, c->graph1_fs = frame_stride;
+  }
+  ORBX_CUDA(c, cudaGraphLaunch(c->graph1_exec, s));
+  c->launches += c->graph1_kernels;
+  return ORBX_OK;
+}
+
+} // namespace orbx
+
+namespace
+{
 
 // TMA descriptors: one 3-D byte tensor {pitch, rows, images} per pyramid level over the context's pyr buffer, box = the
 // level's largest FAST patch (80 bytes wide = the shared-memory patch pitch).  cuTensorMapEncodeTiled is a driver entry point.
@@ -562,6 +626,7 @@ extern "C"
     case ORBX_ERR_NO_DEVICE: return "no CUDA device";
     case ORBX_ERR_CAPACITY: return "batch larger than max_batch";
     case ORBX_ERR_STATE: return "invalid state";
+    case ORBX_ERR_COMM: return "communicator error (NCCL / peer memory)";
     default: return "unknown status";
     }
   }
@@ -598,6 +663,7 @@ extern "C"
     if (cfg->width <= 0 || cfg->height <= 0 || cfg->n_features < 1 || cfg->n_levels < 1 || cfg->n_levels > kMaxLevels || !(cfg->scale_factor > 1.f) ||
         cfg->ini_th_fast < 0 || cfg->ini_th_fast > 255 || cfg->min_th_fast < 0 || cfg->min_th_fast > 255 || cfg->max_batch < 1)
       return ORBX_ERR_INVALID_ARG;
+    if (cfg->n_features > 65535) return ORBX_ERR_INVALID_ARG; // keypoint indices travel as uint16 in the row index and the grid CSR
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return ORBX_ERR_NO_DEVICE; // no CPU fallback, by design
     orbx_ctx *c = new (std::nothrow) orbx_ctx();
@@ -641,6 +707,7 @@ extern "C"
         break;
       }
       c->stream = c->own_stream;
+      if (const char *e = std::getenv("ORBX_GRAPH")) c->use_graph = std::atoi(e) != 0;
       if (const char *e = std::getenv("ORBX_PIPE")) c->kPipe = std::max(1, std::min(orbx_ctx::kPipeMax, std::atoi(e)));
       if (const char *e = std::getenv("ORBX_CHUNK")) c->kChunk = std::max(1, std::atoi(e));
       for (int i = 0; i < c->kPipe; ++i)
@@ -679,6 +746,9 @@ extern "C"
       if (je) cudaEventDestroy(je);
     for (void *q : c->allocs) cudaFree(q);
     if (c->match_scratch) cudaFree(c->match_scratch);
+    drop_graph(c);
+    destroy_self_comm(c);
+    if (c->rec_staging) cudaFree(c->rec_staging);
     delete c;
   }
 
@@ -688,6 +758,13 @@ extern "C"
   {
     if (!c) return ORBX_ERR_INVALID_ARG;
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return ORBX_OK;
+  }
+
+  int orbx_set_graph(orbx_ctx *c, int enable)
+  {
+    if (!c) return ORBX_ERR_INVALID_ARG;
+    c->use_graph = enable != 0;
     return ORBX_OK;
   }
 
@@ -721,6 +798,7 @@ extern "C"
   }
 
   int64_t orbx_launch_count(const orbx_ctx *c) { return c ? c->launches : 0; }
+  uint64_t orbx_frame_epoch(const orbx_ctx *c) { return c ? c->frame_epoch : 0; }
   int64_t orbx_algorithmic_bytes(const orbx_ctx *c, int stereo) { return c ? (stereo ? c->alg_bytes_stereo : c->alg_bytes_image) : 0; }
 
   // ---------------------------------------------------------------------------------------------------------------
@@ -740,6 +818,7 @@ extern "C"
     c->last_images = n_images;
     ++c->frame_epoch;
     c->last_stereo = 0;
+    c->last_frames = 0; // extract-only images carry no grid / uRight / depth: frame-level consumers must fail with ORBX_ERR_STATE
     fill_results(c, n_images, 0, out);
     return ORBX_OK;
   }
@@ -750,7 +829,12 @@ extern "C"
     if (!c || !d_left || !d_right || n_frames < 1) return ORBX_ERR_INVALID_ARG;
     if (n_frames > c->cfg.max_batch) return fail(c, ORBX_ERR_CAPACITY, "n_frames > max_batch");
     ORBX_CUDA(c, cudaSetDevice(c->device));
-    if (n_frames <= c->kChunk)
+    if (n_frames == 1)
+    {
+      int rc = run_stereo_single(c, c->stream, d_left, d_right, stride, frame_stride);
+      if (rc) return rc;
+    }
+    else if (n_frames <= c->kChunk)
     {
       int rc = run_stereo_range(c, c->stream, 0, n_frames, d_left, d_right, stride, frame_stride);
       if (rc) return rc;
@@ -764,7 +848,8 @@ extern "C"
       int k = 0;
       for (int f0 = 0; f0 < n_frames; f0 += c->kChunk, ++k)
       {
-        int rc = run_stereo_range(c, c->pipe[k % c->kPipe], f0, std::min(c->kChunk, n_frames - f0), d_left, d_right, stride, frame_stride);
+        int rc = run_stereo_range(c, c->pipe[k % c->kPipe], f0, std::min(c->kChunk, n_frames - f0), d_left + (size_t)f0 * frame_stride,
+                                  d_right + (size_t)f0 * frame_stride, stride, frame_stride);
         if (rc) return rc;
       }
       for (int i = 0; i < c->kPipe; ++i)
@@ -912,7 +997,7 @@ extern "C"
           ORBX_CUDA(c, cudaMemcpy2DAsync(dr + (d0 + f) * fs, c->in_pitch, right + (f0 + f) * frame_stride, stride, W, H, cudaMemcpyHostToDevice, s));
         }
       }
-      int rc = run_stereo_range(c, s, (int)d0, nf, dl, dr, dstride, fs);
+      int rc = (n_frames == 1) ? run_stereo_single(c, s, dl, dr, dstride, fs) : run_stereo_range(c, s, (int)d0, nf, dl + d0 * fs, dr + d0 * fs, dstride, fs);
       if (rc) return rc;
       // results: left = even images, right = odd images -> one strided 2-D copy per array
       const size_t i0 = 2 * d0;
@@ -1543,6 +1628,7 @@ extern "C"
     ORBX_CUDA(c, cudaGetLastError());
     ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     c->last_images = std::max(c->last_images, 1);
+    c->last_frames = 0; // image 0 was overwritten: the frame-level results of an earlier call no longer match it
     ++c->frame_epoch;
     return ORBX_OK;
   }

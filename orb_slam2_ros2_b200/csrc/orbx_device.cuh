@@ -211,6 +211,7 @@ struct BowArgs
 
 // launchers (orbx_kernels.cu / orbx_match.cu / orbx_serialize.cu / orbx_bow.cu); every call enqueues exactly one kernel on `s`
 void launch_pyramid(const Params &p, int n_images, cudaStream_t s);
+const void *pyramid_kernel_symbol(); // host handle of the pyramid kernel (to find its node in a captured graph)
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
 void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);

@@ -284,6 +284,8 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params 
   }
 }
 
+const void *pyramid_kernel_symbol() { return reinterpret_cast<const void *>(&pyramid_blur_kernel); }
+
 void launch_pyramid(const Params &p, int n_images, cudaStream_t s)
 {
   dim3 grid(p.n_tiles, n_images);

@@ -51,8 +51,11 @@ def full(path):
         for i, n in enumerate(hdr):
             if n in KEEP or ("issue_stalled" in n and n.endswith("_per_warp_active.pct")):
                 print(f"{n:85s} {r[i]:>18s} {units[i]}")
+        # ncu scales every COLUMN to its own unit (read may be in Mbyte while write is in byte): convert before adding
         dr, dw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        print(f"{'traffic = dram read + write':85s} {float(r[dr].replace(',', '')) + float(r[dw].replace(',', '')):18.3f} {units[dr]}")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = float(r[dr].replace(",", "")) * scale[units[dr]] + float(r[dw].replace(",", "")) * scale[units[dw]]
+        print(f"{'traffic = dram read + write':85s} {total / 1e6:18.3f} Mbyte")
 
 
 if __name__ == "__main__":

@@ -3,10 +3,12 @@
 //   shim_main stereo <w> <h> <nFeatures> <nLevels> <scale> <template> <left.raw> <right.raw> <out.bin>
 //   shim_main rgbd   <w> <h> <nFeatures> <nLevels> <scale> <template> <gray.raw> <depth_u16.raw> <out.bin> <dScale>
 //   shim_main errors <template>
+//   shim_main threads <w> <h> <nFeatures> <nLevels> <scale> <template> <a.raw> <b.raw> <out.bin>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <thread>
 
 #include <orbx/orb_slam2_shim.hpp>
 
@@ -137,6 +139,52 @@ int main(int argc, char **argv)
         put(out, (int32_t)nbm);
         for (auto &m : bm) put(out, (int32_t)m.queryIdx), put(out, (int32_t)m.trainIdx), put(out, m.distance);
       }
+    }
+    else if (mode == "threads")
+    {
+      // the reference's own pattern (src/Frame.cc:100-105): two ORBExtractors of ONE configuration, extract() on two
+      // std::threads at the same time, several rounds; then getPyramid() of both (their contexts have moved on since)
+      Camera::set(718.856f, 718.856f, 607.1928f, 185.2157f, 0.537166f);
+      cv::Mat a = read_raw(argv[8], w, h, CV_8U), b = read_raw(argv[9], w, h, CV_8U);
+      ORBExtractor exA(a, nf, nl, scale, tmpl, 20, 7), exB(b, nf, nl, scale, tmpl, 20, 7);
+      std::vector<cv::KeyPoint> kA, kB;
+      std::vector<cv::Mat> dA, dB;
+      for (int round = 0; round < 6; ++round)
+      {
+        std::thread tA([&]() { exA.extract(kA, dA); });
+        std::thread tB([&]() { exB.extract(kB, dB); });
+        tA.join();
+        tB.join();
+      }
+      dump(out, kA, dA);
+      dump(out, kB, dB);
+      // getPyramid() is valid without (before / long after) extract(): a third extractor that never extracted
+      ORBExtractor exC(b, nf, nl, scale, tmpl, 20, 7);
+      for (const ORBExtractor *e : {&exA, &exB, &exC})
+      {
+        const std::vector<cv::Mat> &pyr = e->getPyramid();
+        put(out, (int32_t)pyr.size());
+        const cv::Mat &top = pyr.back();
+        put(out, (int32_t)top.cols);
+        put(out, (int32_t)top.rows);
+        for (int r = 0; r < top.rows; ++r) out.write((const char *)top.ptr<uchar>(r), top.cols);
+      }
+      // a Frame that is no longer resident must refuse device-side queries instead of answering with the newer frame's data
+      Frame::SharedPtr f1 = Frame::createStereo(a, b, nf, tmpl, 20, 7, nullptr, nl, scale);
+      int32_t g1 = (int32_t)f1->getGrids().size();
+      Frame::SharedPtr f2 = Frame::createStereo(b, a, nf, tmpl, 20, 7, nullptr, nl, scale);
+      int32_t refused = 0;
+      try
+      {
+        f1->getGrids();
+      }
+      catch (const ORBSlam2Error &)
+      {
+        refused = 1;
+      }
+      put(out, g1);
+      put(out, refused);
+      put(out, (int32_t)f2->getGrids().size());
     }
     else if (mode == "rgbd")
     {

@@ -19,7 +19,7 @@ def shim_binary(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("shim") / "shim_main")
     libdir = os.path.join(ROOT, "orb_slam2_ros2_b200")
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "stub"),
-           os.path.join(ROOT, "tests", "cpp", "shim_main.cpp"), "-o", out, "-L", libdir, "-lorbx", f"-Wl,-rpath,{libdir}"]
+           os.path.join(ROOT, "tests", "cpp", "shim_main.cpp"), "-o", out, "-L", libdir, "-lorbx", f"-Wl,-rpath,{libdir}", "-pthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return out
@@ -160,3 +160,30 @@ def test_shim_rgbd_matches_oracle(shim_binary, template_path, oracle, tmp_path):
     assert np.array_equal(d, e.desc)
     our, odp = oracle.rgbd_lookup(depth, c["depth_scale"], e.kps, ku, np.float32(c["fx"]) * np.float32(c["bl"]))
     assert np.array_equal(dp, odp) and np.abs(ur - our).max() <= 1e-3 and n_depth == int((odp > 0).sum())
+
+
+@pytest.mark.gpu
+def test_shim_two_threads_same_configuration(shim_binary, template_path, oracle, tmp_path):
+    """src/Frame.cc:100-105: two extractors of one configuration extract on two std::threads; each thread gets its own
+    context from the shim's cache, results equal the oracle, getPyramid() works before / long after extract(), and a Frame
+    whose device state has been replaced refuses device-side queries."""
+    c = synth.KITTI
+    a, b = synth.synth_image(c["height"], c["width"], 21), synth.synth_image(c["height"], c["width"], 22)
+    a.tofile(tmp_path / "a.raw")
+    b.tofile(tmp_path / "b.raw")
+    out = tmp_path / "out.bin"
+    r = subprocess.run([shim_binary, "threads", str(c["width"]), str(c["height"]), "1000", "8", "1.2", template_path, str(tmp_path / "a.raw"),
+                        str(tmp_path / "b.raw"), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rd = _Reader(out)
+    ea, eb = oracle.extract(a, 1000), oracle.extract(b, 1000)
+    ka, da = rd.kps_desc()
+    kb, db = rd.kps_desc()
+    _same(ka, ea.kps, da, ea.desc)
+    _same(kb, eb.kps, db, eb.desc)
+    for e in (ea, eb, eb):
+        assert rd.i32() == 8
+        w, h = rd.i32(), rd.i32()
+        assert (w, h) == (e.pyr.w[7], e.pyr.h[7])
+        assert np.array_equal(rd.arr(np.uint8, w * h).reshape(h, w), e.pyr.level(7))
+    assert (rd.i32(), rd.i32(), rd.i32()) == (8, 1, 8)  # f1's grid, f1 refused after f2 was made, f2's grid
