@@ -316,6 +316,21 @@ def _events(torch):
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
+_pinned_keep = []
+
+
+def pinned_outputs(torch, n_features):
+    """the nine output arrays of orbx_stereo_batch for one frame, in pinned host memory -> their addresses"""
+    N = n_features
+    t = {"kl": torch.empty((N, 28), dtype=torch.uint8, pin_memory=True), "dl": torch.empty((N, 32), dtype=torch.uint8, pin_memory=True),
+         "kr": torch.empty((N, 28), dtype=torch.uint8, pin_memory=True), "dr": torch.empty((N, 32), dtype=torch.uint8, pin_memory=True),
+         "ur": torch.empty(N, dtype=torch.float64, pin_memory=True), "dp": torch.empty(N, dtype=torch.float64, pin_memory=True),
+         "c": torch.zeros(4, dtype=torch.int32, pin_memory=True)}
+    _pinned_keep.append(t)
+    c = t["c"].data_ptr()
+    return [t["kl"].data_ptr(), t["dl"].data_ptr(), c, t["kr"].data_ptr(), t["dr"].data_ptr(), c + 4, t["ur"].data_ptr(), t["dp"].data_ptr(), c + 8]
+
+
 def oracle_flip_check(api, O, ctx_result_kps, ctx_result_desc, img, nf, nl, sc):
     """descriptor bit flips / inexact angles of one image against the oracle (north_star: flips "traced ... and counted")"""
     e = O.extract(img, nf, nl, sc)
@@ -455,12 +470,7 @@ def bench_other_configs(args, api, torch, stream, local_rank, with_oracle):
                 dev.append(e0.elapsed_time(e1))
             one.set_stream(None)
             host = []
-            N_ = nf
-            kl, kr = np.zeros((N_, 28), np.uint8), np.zeros((N_, 28), np.uint8)
-            dsl, dsr = np.zeros((N_, 32), np.uint8), np.zeros((N_, 32), np.uint8)
-            ur, dp, cnt = np.zeros(N_), np.zeros(N_), np.zeros(3, np.int32)
-            ptrs = [kl.ctypes.data, dsl.ctypes.data, cnt.ctypes.data, kr.ctypes.data, dsr.ctypes.data, cnt.ctypes.data + 4, ur.ctypes.data, dp.ctypes.data,
-                    cnt.ctypes.data + 8]
+            ptrs = pinned_outputs(torch, nf)
             for i in range(60):
                 t0 = time.perf_counter()
                 one.stereo_batch_ptr(1, hl.data_ptr() + (i % P) * fs, hr.data_ptr() + (i % P) * fs, c["width"], fs, ptrs)
@@ -697,10 +707,7 @@ def run_gpu_arm(args):
         one = api.Context(W, H, N, CFG["n_levels"], CFG["scale_factor"], CFG["ini_th"], CFG["min_th"], camera=cam, max_batch=1, device=local_rank)
         latency = {"frames": 50, "note": "one stereo pair per call; device = inputs and results in HBM, host_to_host = pinned host images in, results out"}
         np_ = min(n_local, P)
-        ho = {k: np.zeros(s_, dt_) for k, (s_, dt_) in {"kl": ((N, 28), np.uint8), "dl": ((N, 32), np.uint8), "kr": ((N, 28), np.uint8), "dr": ((N, 32), np.uint8),
-                                                        "ur": ((N,), np.float64), "dp": ((N,), np.float64), "c": ((3,), np.int32)}.items()}
-        p1 = [ho["kl"].ctypes.data, ho["dl"].ctypes.data, ho["c"].ctypes.data, ho["kr"].ctypes.data, ho["dr"].ctypes.data, ho["c"].ctypes.data + 4,
-              ho["ur"].ctypes.data, ho["dp"].ctypes.data, ho["c"].ctypes.data + 8]
+        p1 = pinned_outputs(torch, N)
         for graph in (True, False):
             one.set_graph(graph)
             one.set_stream(stream.cuda_stream)

@@ -749,6 +749,7 @@ extern "C"
     drop_graph(c);
     destroy_self_comm(c);
     if (c->rec_staging) cudaFree(c->rec_staging);
+    if (c->h_rec1) cudaFreeHost(c->h_rec1);
     delete c;
   }
 
@@ -956,6 +957,51 @@ extern "C"
     uint8_t *dl = c->d_in, *dr = c->d_in + (size_t)c->cfg.max_batch * c->in_pitch * H;
     const Params &p = c->p;
     const size_t kb = N * sizeof(orbx_keypoint), db = N * 32;
+    if (n_frames == 1)
+    {
+      // Latency path (the reference's one-frame-at-a-time call): both images up, ONE graph launch, the frame's results packed
+      // into one record on the device and brought back in ONE copy (instead of nine), then handed out from pinned memory.
+      orbx_record_layout lay;
+      orbx_record_layout_get(c, &lay);
+      const size_t rs = (size_t)lay.record_bytes;
+      int rc = ensure_record_staging(c, rs);
+      if (rc) return rc;
+      if (!c->h_rec1) ORBX_CUDA(c, cudaHostAlloc((void **)&c->h_rec1, rs, cudaHostAllocDefault));
+      cudaStream_t s = c->stream;
+      const bool dense = frame_stride == stride * H && stride >= W && stride <= c->in_pitch;
+      if (dense)
+      {
+        ORBX_CUDA(c, cudaMemcpyAsync(dl, left, stride * H, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(c, cudaMemcpyAsync(dr, right, stride * H, cudaMemcpyHostToDevice, s));
+      }
+      else
+      {
+        ORBX_CUDA(c, cudaMemcpy2DAsync(dl, c->in_pitch, left, stride, W, H, cudaMemcpyHostToDevice, s));
+        ORBX_CUDA(c, cudaMemcpy2DAsync(dr, c->in_pitch, right, stride, W, H, cudaMemcpyHostToDevice, s));
+      }
+      rc = run_stereo_single(c, s, dl, dr, dense ? stride : c->in_pitch, dense ? stride * H : c->in_pitch * H);
+      if (rc) return rc;
+      rc = pack_frame_records(c, s, 0, 1, c->rec_staging, rs);
+      if (rc) return rc;
+      ORBX_CUDA(c, cudaMemcpyAsync(c->h_rec1, c->rec_staging, rs, cudaMemcpyDeviceToHost, s));
+      ORBX_CUDA(c, cudaStreamSynchronize(s));
+      const int32_t *hdr = reinterpret_cast<const int32_t *>(c->h_rec1);
+      const size_t nl = (size_t)hdr[0], nr = (size_t)hdr[1];
+      if (kps_left) std::memcpy(kps_left, c->h_rec1 + lay.off_kps_left, nl * sizeof(orbx_keypoint));
+      if (desc_left) std::memcpy(desc_left, c->h_rec1 + lay.off_desc_left, nl * 32);
+      if (n_left) *n_left = hdr[0];
+      if (kps_right) std::memcpy(kps_right, c->h_rec1 + lay.off_kps_right, nr * sizeof(orbx_keypoint));
+      if (desc_right) std::memcpy(desc_right, c->h_rec1 + lay.off_desc_right, nr * 32);
+      if (n_right) *n_right = hdr[1];
+      if (u_right) std::memcpy(u_right, c->h_rec1 + lay.off_u_right, nl * 8);
+      if (depth) std::memcpy(depth, c->h_rec1 + lay.off_depth, nl * 8);
+      if (n_matches) *n_matches = hdr[2];
+      c->last_frames = 1;
+      c->last_images = 2;
+      ++c->frame_epoch;
+      c->last_stereo = 1;
+      return ORBX_OK;
+    }
     // Densely stacked rows that fit the staging pitch are copied as ONE linear transfer per side and read on the device
     // with the caller's stride (the kernels gather bytes, so rows need no alignment); 2-D pitched copies of odd-width
     // rows run at a fraction of the PCIe rate.

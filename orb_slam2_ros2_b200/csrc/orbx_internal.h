@@ -47,6 +47,7 @@ struct orbx_ctx
   uint8_t *rec_staging = nullptr;
   size_t rec_staging_bytes = 0;
   struct orbx_comm *self_comm = nullptr;
+  uint8_t *h_rec1 = nullptr; // pinned host record of the single-frame calls (one D2H copy instead of nine)
   // single-pair latency path: the launch sequence of one stereo frame captured once as a CUDA graph (orbx_set_graph)
   int use_graph = 1;
   cudaGraph_t graph1 = nullptr;
@@ -72,6 +73,9 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
 
 // one stereo frame in device slot 0: a single graph launch when the context's graph is enabled and `s` can be captured
 int run_stereo_single(orbx_ctx *c, cudaStream_t s, const uint8_t *d_left, const uint8_t *d_right, size_t stride, size_t frame_stride);
+// per-frame records (orbx_record_layout) of device slots [d0, d0 + nf) assembled at d_rec; device staging for host outputs
+int pack_frame_records(orbx_ctx *c, cudaStream_t s, int d0, int nf, uint8_t *d_rec, size_t rec_stride);
+int ensure_record_staging(orbx_ctx *c, size_t rec_stride);
 // frees the gathered arrays a context keeps for single-rank sequence calls
 void destroy_self_comm(orbx_ctx *c);
 

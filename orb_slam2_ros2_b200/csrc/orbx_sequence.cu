@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_records_kernel(const Params
   }
 }
 
-int ensure_record_staging(orbx_ctx *c, size_t rec_stride)
+int ensure_record_staging_impl(orbx_ctx *c, size_t rec_stride)
 {
   const size_t want = (size_t)c->cfg.max_batch * rec_stride;
   if (c->rec_staging && c->rec_staging_bytes >= want) return ORBX_OK;
@@ -438,7 +438,7 @@ extern "C"
     const bool rec_dev = io->records && io->records_on_device, rec_host = io->records && !io->records_on_device;
     if (rec_host)
     {
-      int rc = ensure_record_staging(c, rs);
+      int rc = ensure_record_staging_impl(c, rs);
       if (rc) return rc;
     }
     const size_t W = (size_t)c->cfg.width, H = (size_t)c->cfg.height, N = (size_t)c->cfg.n_features;
@@ -595,6 +595,23 @@ extern "C"
 
 namespace orbx
 {
+// records of device slots [d0, d0 + nf) -> d_rec (device), no gather
+int pack_frame_records(orbx_ctx *c, cudaStream_t s, int d0, int nf, uint8_t *d_rec, size_t rec_stride)
+{
+  PackArgs pa{};
+  orbx_record_layout_get(c, &pa.lay);
+  pa.rec = d_rec;
+  pa.rec_stride = rec_stride;
+  pa.n_peers = 0;
+  const Params p = params_at(c, 2 * d0, d0);
+  pack_records_kernel<<<dim3(kPackBlocksPerFrame, nf), kPackThreads, 0, s>>>(p, pa);
+  ++c->launches;
+  ORBX_CUDA(c, cudaGetLastError());
+  return ORBX_OK;
+}
+
+int ensure_record_staging(orbx_ctx *c, size_t rec_stride) { return ensure_record_staging_impl(c, rec_stride); }
+
 void destroy_self_comm(orbx_ctx *c)
 {
   if (c && c->self_comm)

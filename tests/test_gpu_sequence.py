@@ -97,7 +97,7 @@ def test_two_local_ranks_gather_equals_single_rank(oracle, F):
         assert (res.frame_lo, res.frame_hi) == (blk.start, blk.stop) and res.world == 2 and res.block == -(-F // 2)
         recs.append(rec[: len(blk)])
         results.append(res)
-    assert np.concatenate(recs).tobytes() == rec1.tobytes()
+    assert b"".join(r.tobytes() for r in recs) == rec1.tobytes()  # (np.concatenate would drop the padding bytes of the structured dtype)
     for r in range(2):
         res = results[r]
         cap = 2 * res.block
