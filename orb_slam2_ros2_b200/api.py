@@ -79,7 +79,7 @@ EXPORTS = [
     "orbx_serialized_capacity", "orbx_serialize_keyframe", "orbx_serialize_keyframes_device",
     "orbx_vocab_create", "orbx_vocab_load_text", "orbx_vocab_destroy", "orbx_vocab_info", "orbx_bow_transform", "orbx_bow_transform_batch_device",
     "orbx_search_by_bow",
-    "orbx_frame_epoch", "orbx_set_graph", "orbx_frame_range", "orbx_comm_unique_id", "orbx_comm_create", "orbx_comm_ipc_handle", "orbx_comm_open_peers",
+    "orbx_frame_epoch", "orbx_set_graph", "orbx_debug_quadtree_stats", "orbx_frame_range", "orbx_comm_unique_id", "orbx_comm_create", "orbx_comm_ipc_handle", "orbx_comm_open_peers",
     "orbx_comm_create_local", "orbx_comm_destroy", "orbx_comm_info", "orbx_record_layout_get", "orbx_sequence_stereo",
 ]
 
@@ -171,6 +171,7 @@ def load_library(build_if_missing: bool = True):
     L.orbx_bow_transform_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(OrbxDeviceBow)]
     L.orbx_search_by_bow.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.orbx_frame_epoch.argtypes = [vp]
+    L.orbx_debug_quadtree_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.orbx_set_graph.argtypes = [vp, C.c_int]
     L.orbx_frame_epoch.restype = C.c_uint64
     L.orbx_frame_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -383,6 +384,12 @@ class Context:
         ent = np.zeros(self.n_features, np.int32)
         _check(self._h, self._L.orbx_get_grid(self._h, frame, start.ctypes.data, ent.ctypes.data), "orbx_get_grid")
         return [[ent[start[r * cols + c] : start[r * cols + c + 1]].copy() for c in range(cols)] for r in range(rows)]
+
+    def quadtree_stats(self):
+        """(loop-free, sequential) counts of the (image, level) quadtree problems solved so far"""
+        a, b = C.c_int64(), C.c_int64()
+        _check(self._h, self._L.orbx_debug_quadtree_stats(self._h, C.byref(a), C.byref(b)), "orbx_debug_quadtree_stats")
+        return a.value, b.value
 
     def run_quadtree(self, level: int, xs, ys, scores) -> np.ndarray:
         """run only the quadtree kernel on a corner list (ROI coords, detection order) -> (m,3) survivors in ROI coords"""

@@ -229,6 +229,8 @@ int build_tables(orbx_ctx *c)
   p.sel_entries = sel_off;
   p.qt_scratch_img_stride = scratch_off;
   p.qt_node_cap = max_quota + max_ini + 8;
+  p.qt_fast = 1;
+  if (const char *e = std::getenv("ORBX_QT_FAST")) p.qt_fast = std::atoi(e) != 0;
   if (p.qt_node_cap >= 60000) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree node pool");
   // shared-memory budget of the quadtree kernel: node pool + buckets + big-node list + keys / u16 index arrays of up to 3584 corners
   {
@@ -357,6 +359,8 @@ int alloc_buffers(orbx_ctx *c)
   c->in_pitch = ((size_t)c->cfg.width + 15) & ~(size_t)15;
   if ((rc = dev_alloc(c, &c->d_in, ni * c->in_pitch * (size_t)c->cfg.height))) return rc;
   if ((rc = dev_alloc(c, &c->d_depth_in, nf * (size_t)c->cfg.width * (size_t)c->cfg.height * 4))) return rc;
+  if ((rc = dev_alloc(c, &p.qt_stats, 2))) return rc;
+  ORBX_CUDA(c, cudaMemset(p.qt_stats, 0, 2 * sizeof(unsigned long long)));
   ORBX_CUDA(c, cudaMemset(p.n_kps, 0, ni * sizeof(int)));
   ORBX_CUDA(c, cudaMemset(p.n_matches, 0, ni * sizeof(int)));
   return ORBX_OK;
@@ -1641,6 +1645,18 @@ extern "C"
       if (scores) scores[k] = (int)(buf[k] >> 24);
     }
     *n = cnt;
+    return ORBX_OK;
+  }
+
+  int orbx_debug_quadtree_stats(orbx_ctx *c, int64_t *fast, int64_t *sequential)
+  {
+    if (!c) return ORBX_ERR_INVALID_ARG;
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    ORBX_CUDA(c, cudaDeviceSynchronize());
+    unsigned long long h[2] = {0, 0};
+    ORBX_CUDA(c, cudaMemcpy(h, c->p.qt_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    if (fast) *fast = (int64_t)h[0];
+    if (sequential) *sequential = (int64_t)h[1];
     return ORBX_OK;
   }
 

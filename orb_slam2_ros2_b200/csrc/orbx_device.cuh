@@ -120,6 +120,8 @@ struct Params
   int qt_node_cap;              // node pool capacity (max quota + max root fan-out + 8)
   int qt_big_cap;               // capacity of the list of nodes holding >= 256 corners
   int qt_cell_cap;              // largest number of FAST cells on one level (+1): per-cell offsets in shared memory
+  unsigned long long *qt_stats; // [2] CTAs that took the loop-free path / the sequential loop (introspection)
+  int qt_fast;                  // take the loop-free formulation of Quadtree::split() where the keys decide (default; ORBX_QT_FAST=0 disables)
   // results
   orbx_keypoint *kps, *kps_und;
   uint8_t *desc;

@@ -617,6 +617,12 @@ __device__ __forceinline__ int qt_rec_depth(uint2 r) { return (int)((r.y >> 24) 
 __device__ __forceinline__ int qt_rec_buf(uint2 r) { return (int)(r.y >> 31); }
 
 __host__ __device__ inline size_t qt_align16(size_t b) { return (b + 15) & ~(size_t)15; }
+__host__ __device__ inline int fp_hash_size(int node_cap)
+{
+  int h = 64;
+  while (h < 2 * node_cap) h <<= 1;
+  return h;
+}
 
 // shared memory: node pool | bucket heads+tails | big-node list | (smem path) ia, ib (u16), key (u32)
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells)
@@ -626,6 +632,9 @@ size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_leve
   b += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
   b += qt_align16((size_t)big_cap * sizeof(uint16_t));
   b += qt_align16((size_t)list_cap * (2 * sizeof(uint16_t) + sizeof(uint32_t)));
+  // fast path: radix histograms (8 warps x 128 bins, u16) and the (start, depth) -> record hash
+  b += qt_align16((size_t)8 * 128 * sizeof(uint16_t));
+  b += qt_align16((size_t)fp_hash_size(node_cap) * sizeof(uint32_t));
   return b + 64;
 }
 
@@ -1176,6 +1185,531 @@ __device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K3 fast path: Quadtree::split() without the loop.
+//   A child never holds more corners than its parent, so the multimap's pop sequence is the list of ALL tree nodes ordered
+//   by (count desc, pop position of the parent, child index), cut at the first prefix whose running node count reaches
+//   `need`; unrolled, two nodes of equal count compare by the counts of their ancestors (parent first, +inf for the root),
+//   then by their path.  Once the corners are SORTED by descent key every node is a contiguous run, its count is the run
+//   length and its children are sub-runs -- all known before any pop.  So the whole block computes, with no serial chain:
+//     F1  stable LSD radix sort of the corner indices by key (3 passes of three base-5 digits + 1 pass over the strips)
+//     F2  L[p] = key components shared with the predecessor, vd[p] = depth of the corner's last real node; bin table
+//     F3  every node with >= 2 corners (thread <-> run start): count, number of non-empty children -> histogram of the
+//         node-count deltas by count
+//     F4  the bucket c* in which the loop stops (running node count reaches `need`)
+//     F5  the nodes that can pop (count >= c*) -> records, hash (start, depth) -> record, parent links
+//     F6  pop rank of every record (all pairs, ancestor-count chains) -> how many nodes of bucket c* pop
+//     F7  leaves = children of popped nodes that did not pop; best response per leaf; the surplus beyond `need` (at most 3)
+//         leaves from the END of the (count desc, insertion) order
+//   It bails out (returns false, the sequential loop runs instead) exactly where the keys do not decide: a node at the key
+//   depth that would have to be split, a popped node whose corners all sit on split lines (negative delta: the running
+//   count is not monotone), c* >= 256, capacity limits.  scripts/devtests/quadtree_parallel_model.py is the CPU model of
+//   this formulation (checked against the oracle).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kFpWarps = kQtThreads / 32;
+constexpr int kFpBins = 128;            // radix bins per pass: 125 (three base-5 digits) or the strips (+1: "in no strip")
+constexpr uint32_t kFpHashEmpty = 0xffffffffu;
+constexpr uint32_t kFpRoot = 0xffffu;
+constexpr int kFpMaxS = 4095;           // record index bits in a hash entry
+constexpr int kFpKeyDepth = kKeyLevels; // 9
+
+struct QtFast
+{
+  uint32_t *keys;  // [n] descent key per corner; becomes the flag array at the end
+  uint16_t *ord;   // [n] sorted position -> corner
+  uint8_t *lvd;    // [m + 1] L | vd << 4
+  uint16_t *hist;  // [kFpWarps][kFpBins]
+  int *D;          // [256]
+  int *bin_start;  // [K * 125 + 1]
+  uint32_t *lf_I;
+  uint16_t *s_pos, *s_cnt, *s_par, *s_rank, *lf_best, *lf_cnt;
+  uint8_t *s_dc, *s_pop;
+  int8_t *s_delta;
+  uint32_t *hash;
+  uint32_t hash_mask;
+  int cap_S;
+  int m, K;
+};
+
+__device__ __forceinline__ uint32_t fp_g5(uint32_t d) { return min(d, 4u); }
+__device__ __forceinline__ int fp_bin3(uint32_t key)
+{
+  return (int)((((key >> kKeyStripShift) * 5u + fp_g5((key >> 24) & 7u)) * 5u + fp_g5((key >> 21) & 7u)) * 5u + fp_g5((key >> 18) & 7u));
+}
+__device__ __forceinline__ uint32_t fp_digit(uint32_t key, int d) // d == 0: strip
+{
+  return d == 0 ? key >> kKeyStripShift : (key >> (kKeyStripShift - 3 * d)) & 7u;
+}
+__device__ __forceinline__ int fp_L(const QtFast &f, int p) { return f.lvd[p] & 15; }
+__device__ __forceinline__ int fp_vd(const QtFast &f, int p) { return f.lvd[p] >> 4; }
+
+__device__ __forceinline__ void fp_hash_insert(const QtFast &f, int pos, int depth, int idx)
+{
+  const uint32_t k = ((uint32_t)pos << 4) | (uint32_t)depth, e = (k << 12) | (uint32_t)idx;
+  uint32_t h = (k * 2654435761u) & f.hash_mask;
+  while (atomicCAS(&f.hash[h], kFpHashEmpty, e) != kFpHashEmpty) h = (h + 1) & f.hash_mask;
+}
+__device__ __forceinline__ int fp_hash_find(const QtFast &f, int pos, int depth)
+{
+  const uint32_t k = ((uint32_t)pos << 4) | (uint32_t)depth;
+  uint32_t h = (k * 2654435761u) & f.hash_mask;
+  for (;;)
+  {
+    const uint32_t e = f.hash[h];
+    if (e == kFpHashEmpty) return -1;
+    if ((e >> 12) == k) return (int)(e & 0xfffu);
+    h = (h + 1) & f.hash_mask;
+  }
+}
+
+// the nodes (>= 2 corners) whose run starts at sorted position p: fn(depth, count, non-empty children or -1 at the key depth)
+template <class Fn> __device__ __forceinline__ void fp_nodes_at(const QtFast &f, int p, Fn fn)
+{
+  const int l0 = fp_L(f, p), l1 = fp_L(f, p + 1);
+  const int dmax = min(min(l1 - 1, fp_vd(f, p)), kFpKeyDepth);
+  if (dmax < l0) return;
+  const int b3 = fp_bin3(f.keys[f.ord[p]]);
+  for (int d = l0; d <= dmax; ++d)
+  {
+    int cnt, ne;
+    if (d <= 2)
+    {
+      const int span = d == 0 ? 125 : (d == 1 ? 25 : 5), w = span / 5;
+      const int B = (b3 / span) * span;
+      cnt = f.bin_start[B + span] - p;
+      ne = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ne += f.bin_start[B + (c + 1) * w] > f.bin_start[B + c * w];
+    }
+    else
+    {
+      int q = p + 1, groups = 1;
+      while (q < f.m)
+      {
+        const int l = fp_L(f, q);
+        if (l <= d) break;
+        groups += l == d + 1;
+        ++q;
+      }
+      cnt = q - p;
+      ne = d == kFpKeyDepth ? -1 : groups - (fp_vd(f, q - 1) == d ? 1 : 0);
+    }
+    fn(d, cnt, ne);
+  }
+}
+
+// children of the depth-d node [p, p + cnt) (d == -1: the root, children = strips): fn(digit, start, end) per non-empty child
+template <class Fn> __device__ __forceinline__ void fp_children(const QtFast &f, int p, int cnt, int d, Fn fn)
+{
+  if (d < 0)
+  {
+    for (int s = 0; s < f.K; ++s)
+    {
+      const int a = f.bin_start[s * kQtBinsPerStrip], b = f.bin_start[(s + 1) * kQtBinsPerStrip];
+      if (b > a) fn(s, a, b);
+    }
+  }
+  else if (d <= 2)
+  {
+    const int span = d == 0 ? 125 : (d == 1 ? 25 : 5), w = span / 5;
+    const int B = (fp_bin3(f.keys[f.ord[p]]) / span) * span;
+    for (int c = 0; c < 4; ++c)
+    {
+      const int a = f.bin_start[B + c * w], b = f.bin_start[B + (c + 1) * w];
+      if (b > a) fn(c, a, b);
+    }
+  }
+  else
+  {
+    const int end = p + cnt;
+    int g0 = p;
+    for (int q = p + 1; q <= end; ++q)
+      if (q == end || fp_L(f, q) == d + 1)
+      {
+        const uint32_t dg = fp_digit(f.keys[f.ord[g0]], d + 1);
+        if (dg != kDigitDrop) fn((int)dg, g0, q);
+        g0 = q;
+      }
+  }
+}
+
+// equal counts: does record u pop before record v?  (ancestor counts, parent first; the root counts as +inf; then the path)
+__device__ __forceinline__ bool fp_chain_before(const QtFast &f, uint32_t u, uint32_t v)
+{
+  uint32_t a = u, b = v;
+  for (;;)
+  {
+    const uint32_t pa = a, pb = b;
+    a = f.s_par[a];
+    b = f.s_par[b];
+    if (a == b) return (f.s_dc[pa] & 15u) < (f.s_dc[pb] & 15u);
+    const uint32_t ca = a == kFpRoot ? 0x10000u : f.s_cnt[a], cb = b == kFpRoot ? 0x10000u : f.s_cnt[b];
+    if (ca != cb) return ca > cb;
+    if (a == kFpRoot || b == kFpRoot) return a == kFpRoot; // unreachable (counts differ), keeps the loop finite
+  }
+}
+
+__device__ __noinline__ bool qt_fast_path(QtFast f, const uint32_t *kp, uint16_t *ib, int n, int need, int *s_warp)
+{
+  __shared__ int s_m, s_live0, s_dbig, s_neg, s_deep, s_cstar, s_before, s_nS, s_R0, s_k, s_nleaf, s_mode;
+  __shared__ unsigned long long s_amax;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+  const int K = f.K;
+  enum { kRun = 0, kEmpty = 1, kNoPop = 2, kBail = 3 };
+
+  // ---- F1: stable LSD radix sort of the corner indices by key.  Every warp owns a contiguous segment of the input; equal
+  // digits inside a 32-element step are ranked with __match_any_sync, so no atomics and the passes are stable.
+  {
+    uint16_t *src = f.ord, *dst = ib;
+    const int seg = (n + kFpWarps - 1) / kFpWarps, lo = min(wid * seg, n), hi = min(lo + seg, n);
+    for (int pass = 0; pass < 4; ++pass)
+    {
+      auto digit = [&](uint32_t key) -> uint32_t {
+        if (pass == 3)
+        {
+          const uint32_t s = key >> kKeyStripShift;
+          return s == kKeyNoStrip ? (uint32_t)K : s;
+        }
+        const uint32_t v = (key >> (9 * pass)) & 511u;
+        return fp_g5(v >> 6) * 25u + fp_g5((v >> 3) & 7u) * 5u + fp_g5(v & 7u);
+      };
+      for (int i = tid; i < kFpWarps * kFpBins; i += kQtThreads) f.hist[i] = 0;
+      __syncthreads();
+      for (int i0 = lo; i0 < hi; i0 += 32)
+      {
+        const int i = i0 + lane;
+        const uint32_t dg = i < hi ? digit(f.keys[src[i]]) : 0xffffu;
+        const unsigned peers = __match_any_sync(FULL, dg);
+        if (i < hi && lane == __ffs(peers) - 1) f.hist[wid * kFpBins + dg] += (uint16_t)__popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      int tot = 0;
+      if (tid < kFpBins)
+        for (int w = 0; w < kFpWarps; ++w) tot += f.hist[w * kFpBins + tid];
+      int total;
+      const int base = block_exclusive_scan<kQtThreads>(tot, total, s_warp);
+      if (tid < kFpBins)
+      {
+        int run = base;
+        for (int w = 0; w < kFpWarps; ++w)
+        {
+          const int c = f.hist[w * kFpBins + tid];
+          f.hist[w * kFpBins + tid] = (uint16_t)run;
+          run += c;
+        }
+        if (pass == 3 && tid == K) s_m = base; // corners in no strip sort behind everything
+      }
+      __syncthreads();
+      for (int i0 = lo; i0 < hi; i0 += 32)
+      {
+        const int i = i0 + lane;
+        uint32_t idx = 0, dg = 0xffffu;
+        if (i < hi)
+        {
+          idx = src[i];
+          dg = digit(f.keys[idx]);
+        }
+        const unsigned peers = __match_any_sync(FULL, dg);
+        uint32_t b = 0;
+        if (i < hi)
+        {
+          b = f.hist[wid * kFpBins + dg];
+          dst[b + __popc(peers & lt_mask)] = (uint16_t)idx;
+        }
+        __syncwarp();
+        if (i < hi && lane == __ffs(peers) - 1) f.hist[wid * kFpBins + dg] = (uint16_t)(b + __popc(peers));
+        __syncwarp();
+      }
+      __syncthreads();
+      uint16_t *t = src;
+      src = dst;
+      dst = t;
+    }
+    // four passes: the sorted order is back in f.ord, `ib` is free from here on (-> lvd)
+  }
+  const int m = s_m;
+  f.m = m;
+
+  // ---- F2: L / vd bytes, bin table (start of every (strip, d1, d2, d3) bin in the sorted order), zeroed accumulators
+  for (int p = tid; p <= m; p += kQtThreads)
+  {
+    uint32_t l = 0, v = 0;
+    if (p < m)
+    {
+      const uint32_t key = f.keys[f.ord[p]];
+      const uint32_t t7 = key & (key >> 1) & (key >> 2) & 0x01249249u; // bit 0 of every digit that equals 7
+      v = t7 ? (uint32_t)((27 - (31 - __clz((int)t7))) / 3 - 1) : (uint32_t)kFpKeyDepth;
+      if (p > 0)
+      {
+        const uint32_t x = key ^ f.keys[f.ord[p - 1]];
+        if (x == 0)
+          l = kFpKeyDepth + 1;
+        else
+        {
+          const int hb = 31 - __clz((int)x);
+          l = hb >= kKeyStripShift ? 0u : (uint32_t)((29 - hb) / 3);
+        }
+      }
+    }
+    f.lvd[p] = (uint8_t)(l | (v << 4));
+  }
+  for (int i = tid; i < 256; i += kQtThreads) f.D[i] = 0;
+  for (int i = tid; i <= (int)f.hash_mask; i += kQtThreads) f.hash[i] = kFpHashEmpty;
+  if (tid == 0)
+  {
+    s_live0 = 0, s_dbig = 0, s_neg = 0, s_deep = 0, s_cstar = 0, s_before = 0, s_nS = 0, s_R0 = 0, s_k = 0, s_nleaf = 0, s_mode = kRun;
+    s_amax = 0ull;
+  }
+  __syncthreads();
+  {
+    const int nb = K * kQtBinsPerStrip;
+    if (m == 0)
+    {
+      for (int b = tid; b <= nb; b += kQtThreads) f.bin_start[b] = 0;
+    }
+    else
+      for (int p = tid; p < m; p += kQtThreads)
+      {
+        if (p > 0 && fp_L(f, p) > 3) continue; // same bin as the predecessor
+        const int b = fp_bin3(f.keys[f.ord[p]]);
+        const int pb = p > 0 ? fp_bin3(f.keys[f.ord[p - 1]]) : -1;
+        for (int bb = pb + 1; bb <= b; ++bb) f.bin_start[bb] = p;
+      }
+  }
+  __syncthreads();
+  if (m > 0)
+  {
+    const int nb = K * kQtBinsPerStrip;
+    const int last = fp_bin3(f.keys[f.ord[m - 1]]);
+    for (int b = last + 1 + tid; b <= nb; b += kQtThreads) f.bin_start[b] = m;
+  }
+  __syncthreads();
+
+  // ---- F3: deltas of all nodes by count
+  if (tid < K) atomicAdd(&s_live0, f.bin_start[(tid + 1) * kQtBinsPerStrip] > f.bin_start[tid * kQtBinsPerStrip] ? 1 : 0);
+  for (int p = tid; p < m; p += kQtThreads)
+    fp_nodes_at(f, p, [&](int d, int cnt, int ne) {
+      if (ne < 0)
+        atomicMax(&s_deep, cnt);
+      else
+      {
+        const int delta = ne - 1;
+        if (delta < 0) atomicMax(&s_neg, cnt);
+        if (cnt < 256)
+          atomicAdd(&f.D[cnt], delta);
+        else
+          atomicAdd(&s_dbig, delta);
+      }
+    });
+  __syncthreads();
+
+  // ---- F4: where does the loop stop?
+  if (tid == 0)
+  {
+    const int live0 = s_live0, hard = max(s_neg, s_deep);
+    int mode = kRun;
+    if (live0 == 0)
+      mode = kEmpty;
+    else if (live0 >= need)
+      mode = kNoPop;
+    else
+    {
+      int run = live0 + s_dbig, cstar = 0;
+      if (run >= need)
+        mode = kBail; // the loop stops among the nodes of 256+ corners
+      else
+      {
+        for (int c = 255; c >= 2; --c)
+        {
+          const int after = run + f.D[c];
+          if (after >= need)
+          {
+            cstar = c;
+            break;
+          }
+          run = after;
+        }
+        if (cstar == 0)
+          mode = hard >= 2 ? kBail : kEmpty; // starved: the multimap drains (src/ORBExtractor.cc:151), 0 keypoints
+        else if (cstar <= hard)
+          mode = kBail;
+        s_cstar = cstar;
+        s_before = run;
+      }
+    }
+    s_mode = mode;
+  }
+  __syncthreads();
+  if (s_mode == kBail) return false;
+  const int cstar = s_cstar;
+
+  if (s_mode == kRun)
+  {
+    // ---- F5: records of the nodes that can pop
+    for (int p = tid; p < m; p += kQtThreads)
+      fp_nodes_at(f, p, [&](int d, int cnt, int ne) {
+        if (cnt < cstar) return;
+        const int idx = atomicAdd(&s_nS, 1);
+        if (cnt > cstar) atomicAdd(&s_R0, 1);
+        if (idx >= f.cap_S) return;
+        f.s_pos[idx] = (uint16_t)p;
+        f.s_cnt[idx] = (uint16_t)cnt;
+        f.s_dc[idx] = (uint8_t)((d << 4) | (int)fp_digit(f.keys[f.ord[p]], d));
+        f.s_delta[idx] = (int8_t)(ne - 1);
+        f.s_pop[idx] = 0;
+        fp_hash_insert(f, p, d, idx);
+      });
+    __syncthreads();
+    const int nS = s_nS, R0 = s_R0;
+    if (nS > f.cap_S || nS - R0 > kFpWarps * kFpBins) return false; // uniform
+    // parent links
+    for (int v = tid; v < nS; v += kQtThreads)
+    {
+      const int d = f.s_dc[v] >> 4, p = f.s_pos[v];
+      uint32_t par = kFpRoot;
+      if (d > 0)
+      {
+        int pp = p;
+        if (d - 1 < fp_L(f, p))
+        {
+          // the parent's run starts earlier: lower bound of the (strip, d1 .. d(d-1)) prefix
+          const int sh = kKeyStripShift - 3 * (d - 1);
+          const uint32_t want = f.keys[f.ord[p]] >> sh;
+          int lo = 0, hi = p;
+          while (lo < hi)
+          {
+            const int mid = (lo + hi) >> 1;
+            if ((f.keys[f.ord[mid]] >> sh) < want)
+              lo = mid + 1;
+            else
+              hi = mid;
+          }
+          pp = lo;
+        }
+        const int q = fp_hash_find(f, pp, d - 1);
+        par = q < 0 ? 0xfffeu : (uint32_t)q;
+      }
+      f.s_par[v] = (uint16_t)par;
+      if (par == 0xfffeu) s_mode = kBail; // cannot happen: a parent holds at least as many corners as its child
+    }
+    __syncthreads();
+    if (s_mode == kBail) return false;
+
+    // ---- F6: pop rank of every record
+    for (int v = tid; v < nS; v += kQtThreads)
+    {
+      const uint32_t cv = f.s_cnt[v];
+      int r = 0;
+      for (int u = 0; u < nS; ++u)
+      {
+        if (u == v) continue;
+        const uint32_t cu = f.s_cnt[u];
+        r += cu != cv ? (cu > cv) : fp_chain_before(f, (uint32_t)u, (uint32_t)v);
+      }
+      f.s_rank[v] = (uint16_t)r;
+      if ((int)cv == cstar) f.hist[r - R0] = (uint16_t)f.s_delta[v]; // deltas of bucket c* in pop order (all >= 0 here)
+    }
+    __syncthreads();
+    if (wid == 0)
+    {
+      const int mb = nS - R0;
+      int run = s_before, k = 0;
+      for (int j0 = 0; j0 < mb; j0 += 32)
+      {
+        const int j = j0 + lane;
+        const int val = j < mb ? (int)f.hist[j] : 0;
+        int inc = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const int t = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const bool pops = j < mb && run + inc - val < need; // the loop tests the node count BEFORE every pop
+        const unsigned pm = __ballot_sync(FULL, pops);
+        k += __popc(pm);
+        run += __shfl_sync(FULL, inc, 31);
+        if (pm != FULL) break;
+      }
+      if (lane == 0) s_k = k;
+    }
+    __syncthreads();
+    const int k = s_k;
+    for (int v = tid; v < nS; v += kQtThreads) f.s_pop[v] = ((int)f.s_cnt[v] > cstar || (int)f.s_rank[v] - R0 < k) ? 1 : 0;
+    __syncthreads();
+  }
+
+  // ---- F7: leaves (children of popped nodes -- and of the root -- that did not pop), best response of each
+  if (s_mode != kEmpty)
+  {
+    const int nS = s_mode == kRun ? s_nS : 0;
+    for (int item = tid; item <= nS; item += kQtThreads)
+    {
+      int p = 0, cnt = 0, d = -1;
+      uint32_t prank = 0;
+      if (item < nS)
+      {
+        if (!f.s_pop[item]) continue;
+        p = f.s_pos[item], cnt = f.s_cnt[item], d = f.s_dc[item] >> 4;
+        prank = (uint32_t)f.s_rank[item] + 1u;
+      }
+      fp_children(f, p, cnt, d, [&](int dg, int a, int b) {
+        const int ccnt = b - a;
+        if (cstar > 0 && ccnt >= cstar && ccnt >= 2)
+        {
+          const int q = fp_hash_find(f, a, d + 1);
+          if (q >= 0 && f.s_pop[q]) return; // popped itself: its children stand in for it
+        }
+        uint32_t best = 0, best_i = 0;
+        for (int pos = a; pos < b; ++pos)
+        {
+          const uint32_t idx = f.ord[pos];
+          const uint32_t r = kp[idx] >> 24;
+          if (r > best || (r == best && r > 0 && idx < best_i))
+          {
+            best = r;
+            best_i = idx;
+          }
+        }
+        const int li = atomicAdd(&s_nleaf, 1);
+        if (li < f.cap_S)
+        {
+          f.lf_best[li] = (uint16_t)best_i;
+          f.lf_cnt[li] = (uint16_t)ccnt;
+          f.lf_I[li] = (prank << 3) | (uint32_t)dg;
+        }
+      });
+    }
+  }
+  __syncthreads();
+  const int nleaf = s_nleaf;
+  if (nleaf > f.cap_S) return false; // uniform
+  // nodes2kpoints (:182-192): the first min(need, |M|) entries in (count desc, insertion order); drop the rest from the end
+  const int surplus = nleaf - min(need, nleaf);
+  for (int it = 0; it < surplus; ++it)
+  {
+    for (int li = tid; li < nleaf; li += kQtThreads)
+      if (f.lf_cnt[li] != 0xffffu) atomicMax(&s_amax, ((unsigned long long)(0xffffu - f.lf_cnt[li]) << 32) | (unsigned long long)(f.lf_I[li] + 1u));
+    __syncthreads();
+    const unsigned long long top = s_amax;
+    for (int li = tid; li < nleaf; li += kQtThreads)
+      if (f.lf_cnt[li] != 0xffffu && (((unsigned long long)(0xffffu - f.lf_cnt[li]) << 32) | (unsigned long long)(f.lf_I[li] + 1u)) == top) f.lf_cnt[li] = 0xffffu;
+    __syncthreads();
+    if (tid == 0) s_amax = 0ull;
+    __syncthreads();
+  }
+  // flags (the key array is dead from here on)
+  uint32_t *flag = f.keys;
+  for (int i = tid; i < n; i += kQtThreads) flag[i] = 0u;
+  __syncthreads();
+  for (int li = tid; li < nleaf; li += kQtThreads)
+    if (f.lf_cnt[li] != 0xffffu && (int)f.lf_best[li] < n) flag[f.lf_best[li]] = 1u;
+  __syncthreads();
+  return true;
+}
+
 __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
 {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -1254,7 +1788,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   // ---- Phase B: gather the cell lists (cell-row-major, row-major inside a cell == the reference's detection order),
   // one thread per corner: binary search of the corner's cell in the offsets, then load + key
   __syncthreads();
-  {
+  auto gather = [&](bool identity_order) {
     const uint32_t *cl = p.cell_list + (size_t)img * p.cell_entries;
     for (int i = tid; i < n; i += kQtThreads)
     {
@@ -1270,8 +1804,46 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
       const uint32_t e = cl[cells[lo_c].slot + (i - cell_off[lo_c])];
       kp[i] = e;
       if (use_keys) keys[i] = qt_make_key(e, cols, K, L.roi_h);
+      if (identity_order) ia16[i] = (uint16_t)i;
     }
+  };
+
+  // ---- fast path (see qt_fast_path): the usual case -- keys decide everything -- needs no sequential loop at all
+  bool done = false;
+  if (p.qt_fast && use_keys && K >= 1 && K <= kQtMaxBinStrips && need >= 2 && in_smem)
+  {
+    gather(true);
+    __syncthreads();
+    QtFast f;
+    const size_t nc = (size_t)node_cap;
+    f.keys = keys;
+    f.ord = ia16;
+    f.lvd = (uint8_t *)ib16;
+    f.hist = (uint16_t *)(lists + qt_align16((size_t)p.qt_smem_cap * 8));
+    f.hash = (uint32_t *)((uint8_t *)f.hist + qt_align16((size_t)8 * 128 * sizeof(uint16_t)));
+    f.hash_mask = (uint32_t)fp_hash_size(node_cap) - 1u;
+    f.D = (int *)q.bhead;
+    f.bin_start = s_bin_start;
+    f.lf_I = (uint32_t *)smem;
+    f.s_pos = (uint16_t *)(smem + 4 * nc);
+    f.s_cnt = f.s_pos + nc;
+    f.s_par = f.s_cnt + nc;
+    f.s_rank = f.s_par + nc;
+    f.lf_best = f.s_rank + nc;
+    f.lf_cnt = f.lf_best + nc;
+    f.s_dc = (uint8_t *)(f.lf_cnt + nc);
+    f.s_pop = f.s_dc + nc;
+    f.s_delta = (int8_t *)(f.s_pop + nc);
+    f.cap_S = min(node_cap, kFpMaxS);
+    f.m = 0;
+    f.K = K;
+    done = qt_fast_path(f, kp, ib16, n, need, s_warp);
   }
+  uint32_t *flag = keys; // the key array doubles as the "selected" flag array at the end
+  if (tid == 0 && p.qt_stats) atomicAdd(&p.qt_stats[done ? 0 : 1], 1ull);
+  if (!done)
+  {
+  gather(false);
   for (int i = tid; i < 2 * kQtBuckets; i += kQtThreads) q.bhead[i] = (uint16_t)kNil; // heads and tails are contiguous
   for (int i = tid; i < node_cap; i += kQtThreads) q.np.state[i] = 0;
   if (tid < 32) s_strip_cnt[tid] = 0;
@@ -1427,7 +1999,6 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   }
   // the key array doubles as the "selected" flag array from here on
   __syncthreads();
-  uint32_t *flag = keys;
   for (int i = tid; i < n; i += kQtThreads) flag[i] = 0u;
   __syncthreads();
 
@@ -1440,6 +2011,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
       qt_select<uint32_t>(q.np, kp, ia32, ib32, flag, n, s_n, tid);
   }
   __syncthreads();
+  } // !done
   {
     const int per = (n + kQtThreads - 1) / kQtThreads;
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);

@@ -36,8 +36,11 @@ def _unique_points(rng, w, h, n):
     return (flat % (w - 6) + 3).astype(np.int32), (flat // (w - 6) + 3).astype(np.int32)
 
 
-@pytest.mark.parametrize("shape", [(1209, 344), (608, 448), (314, 73), (100, 400), (64, 64)])
-def test_random_lists(oracle, shape):
+@pytest.mark.parametrize("fast", ["1", "0"], ids=["loopfree", "sequential"])
+@pytest.mark.parametrize("shape", [(1209, 344), (608, 448), (314, 73), (100, 400), (64, 64), (1888, 1048)])
+def test_random_lists(oracle, shape, fast, monkeypatch):
+    """both formulations of Quadtree::split(): the loop-free one (default) and the sequential loop (ORBX_QT_FAST=0)"""
+    monkeypatch.setenv("ORBX_QT_FAST", fast)
     w, h = shape
     rng = np.random.default_rng(w * 7 + h)
     for need in (2, 7, 60, 434):
@@ -48,6 +51,26 @@ def test_random_lists(oracle, shape):
             xs, ys = _unique_points(rng, w, h, min(n, w * h // 5))  # a level's cell slots hold about w*h/4 corners
             resp = rng.integers(6, 120, len(xs)).astype(np.int32)
             _check(oracle, ctx, w, h, xs, ys, resp, need)
+        n_fast, n_seq = ctx.quadtree_stats()
+        if fast == "0" or shape == (100, 400):  # 100 x 400: round(w / h) == 0 root strips, the keys do not apply
+            assert n_fast == 0
+        elif shape in ((1209, 344), (608, 448), (1888, 1048)):
+            assert n_fast >= 6, (n_fast, n_seq)  # non-dyadic strips: random corners never force the fallback
+        ctx.close()
+
+
+def test_loop_free_path_is_the_one_that_runs_on_images(oracle):
+    """every level of ordinary images is solved without the sequential loop -- and still equals the oracle"""
+    from orb_slam2_ros2_b200 import synth
+
+    for (h, w, nf, nl, seed) in ((376, 1241, 2000, 8, 0), (480, 640, 1000, 8, 3), (1080, 1920, 5000, 12, 4), (376, 1241, 4000, 8, 2)):
+        img = synth.synth_image(h, w, seed)
+        ctx = api.Context(w, h, nf, nl, 1.2)
+        kps, desc = ctx.extract(img)
+        e = oracle.extract(img, nf, nl, 1.2)
+        assert len(kps) == len(e.kps) and np.array_equal(kps["x"], e.kps["x"]) and np.array_equal(kps["y"], e.kps["y"])
+        assert np.array_equal(kps["octave"], e.kps["octave"]) and np.array_equal(kps["response"], e.kps["response"])
+        assert ctx.quadtree_stats() == (nl, 0)
         ctx.close()
 
 
