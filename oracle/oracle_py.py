@@ -466,6 +466,9 @@ def ref():
                                          i32p, i32p, f32p, i32p]
         R.ref_verify_angle.restype = C.c_int
         R.ref_verify_angle.argtypes = [C.c_int, i32p, i32p, f32p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        R.ref_rgbd.restype = C.c_int
+        R.ref_rgbd.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int,
+                               C.c_int, C.c_void_p, u8p, f64p, f64p, C.c_int]
         R.ref_bench_stereo.restype = C.c_double
         R.ref_bench_stereo.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_long)]
@@ -544,6 +547,22 @@ def ref_stereo(left, right, template_path, n_features=2000, n_levels=8, scale=1.
         return dict(status=nm)
     a, b = nl.value, nr.value
     return dict(status=0, n_matches=nm, kl=kl[:a].copy(), dl=dl[:a].copy(), kr=kr[:b].copy(), dr=dr[:b].copy(), u_right=ur[:a].copy(), depth=dp[:a].copy())
+
+
+def ref_rgbd(gray, depth_img, depth_scale, template_path, n_features=1000, n_levels=8, scale=1.2, ini_th=20, min_th=7):
+    """The reference's OWN RGB-D Frame ctor body (src/Frame.cc:130-158) -> (kps undistorted, desc, u_right, depth)"""
+    g = np.ascontiguousarray(gray, np.uint8)
+    is_float = depth_img.dtype == np.float32
+    d = np.ascontiguousarray(depth_img, np.float32 if is_float else np.uint16)
+    h, w = g.shape
+    cap = n_features + 8
+    kps, desc = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8)
+    ur, dp = np.zeros(cap, np.float64), np.zeros(cap, np.float64)
+    n = ref().ref_rgbd(_ptr(g, u8p), w, h, g.strides[0], d.ctypes.data, int(is_float), d.strides[0], depth_scale, n_features, n_levels, scale,
+                       template_path.encode(), ini_th, min_th, kps.ctypes.data, _ptr(desc, u8p), _ptr(ur, f64p), _ptr(dp, f64p), cap)
+    if n < 0:
+        raise RuntimeError(f"ref_rgbd failed ({n})")
+    return kps[:n], desc[:n], ur[:n], dp[:n]
 
 
 def ref_undistort(xy):

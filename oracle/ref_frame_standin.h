@@ -1,6 +1,6 @@
 // Stand-in for ORB_SLAM2_ROS2::VirtualFrame / Frame (TEST INFRASTRUCTURE ONLY): same member names / getters as the
 // reference's classes (include/ORB_SLAM2/Frame.h:28,204-207,263-299,340-347) restricted to what the compiled line ranges
-// touch: ORBMatcher::searchByStereo, VirtualFrame::initGrid and VirtualFrame::findFeaturesInArea.  The bodies of
+// touch: ORBMatcher::searchByStereo, VirtualFrame::initGrid, VirtualFrame::findFeaturesInArea and the RGB-D Frame ctor.  The bodies of
 // getScaledFactor / getScaledFactor2 are the reference's own lines (Frame.h:204,207), extracted with sed at build time
 // into ref_frame_h_ranges.inc (never stored in this repo).
 #pragma once
@@ -35,6 +35,12 @@ public:
   cv::Mat mLeftIm, mRightIm;
   ORBExtractor::SharedPtr mpExtractorLeft, mpExtractorRight;
   int mnN = 0;
+  // members the RGB-D ctor body touches (include/ORB_SLAM2/Frame.h:281,31) + the body itself (src/Frame.cc:130-158, compiled
+  // verbatim from ref_frame_rgbd_body.inc by ref_stereo_tu.cpp)
+  std::vector<void *> mvpMapPoints;
+  std::size_t mnID = 0;
+  void rgbdCtorBody(cv::Mat colorImg, cv::Mat depthImg, int nFeatures, const std::string &briefFp, int maxThresh, int minThresh, float dScale, int nLevels,
+                    float scale);
 
   const std::vector<cv::KeyPoint> &getLeftKeyPoints() const { return mvFeatsLeft; }
   const std::vector<cv::KeyPoint> &getRightKeyPoints() const { return mvFeatsRight; }

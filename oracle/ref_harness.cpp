@@ -236,6 +236,50 @@ extern "C"
     }
   }
 
+  // Frame::Frame(colorImg, depthImg, ...) (src/Frame.cc:125-159): the reference's own ctor body on a gray image and a raw depth image
+  // (uint16 or float32).  kps = mvFeatsLeft (undistorted), depth / u_right = mvDepths / mvFeatsRightU.  Returns the keypoint count.
+  int ref_rgbd(const uint8_t *gray, int w, int h, size_t stride, const void *depth, int depth_is_float, size_t depth_stride_bytes, float dScale, int nFeatures,
+               int nLevels, float scale, const char *tmpl, int iniTh, int minTh, oracle_keypoint *kps, uint8_t *desc, double *u_right, double *depth_out, int cap)
+  {
+    try
+    {
+      Frame f;
+      f.mfMinU = 0, f.mfMinV = 0, f.mfMaxU = (float)w, f.mfMaxV = (float)h; // VirtualFrame ctor (Frame.h:33-43) without distortion; the grid is not exported here
+      if (Camera::mDistCoeff.at<float>(0) != 0.f)
+      {
+        std::vector<cv::KeyPoint> c(2);
+        c[0].pt = cv::Point2f(0.f, 0.f);
+        c[1].pt = cv::Point2f((float)w, (float)h);
+        Camera::undistortPoints(c);
+        f.mfMinU = c[0].pt.x, f.mfMinV = c[0].pt.y, f.mfMaxU = c[1].pt.x, f.mfMaxV = c[1].pt.y;
+      }
+      cv::Mat g = wrap_u8(gray, w, h, stride);
+      cv::Mat d(h, w, depth_is_float ? CV_32F : CV_16U, (void *)depth, depth_stride_bytes);
+      f.rgbdCtorBody(g, d, nFeatures, tmpl, iniTh, minTh, dScale, nLevels, scale);
+      export_kps(f.mvFeatsLeft, f.mvLeftDescriptor, kps, desc, cap);
+      const int n = (int)f.mvFeatsLeft.size();
+      for (int i = 0; i < n && i < cap; ++i)
+      {
+        u_right[i] = f.mvFeatsRightU[i];
+        depth_out[i] = f.mvDepths[i];
+      }
+      return n;
+    }
+    catch (const ImageSizeError &)
+    {
+      return -1;
+    }
+    catch (const FileNotOpenError &)
+    {
+      return -2;
+    }
+    catch (const std::exception &e)
+    {
+      std::fprintf(stderr, "ref_rgbd: %s\n", e.what());
+      return -3;
+    }
+  }
+
   // Camera::undistortPoints (src/Camera.cc:29-39) on raw coordinates
   void ref_undistort(float *xy, int n)
   {

@@ -6,6 +6,8 @@
 //                              descDistance, getBestMatch, getPitch, verifyAngle), 1086-1093 (static constants)
 //   ref_frame_cc_ranges.inc    Frame.cc 53-69 (VirtualFrame::initGrid), 286-311 (VirtualFrame::findFeaturesInArea),
 //                              355-359 (static members)
+//   ref_frame_rgbd_body.inc    Frame.cc 130-158 (the body of the RGB-D Frame ctor: convertTo, /= dScale, extractor, undistortion,
+//                              initGrid, the depth lookup loop)
 //   ref_frame_h_ranges.inc     Frame.h 204, 207 (getScaledFactor, getScaledFactor2; included by ref_frame_standin.h)
 // They are #included below after the reference's REAL ORBMatcher.h / Camera.h and a stand-in VirtualFrame/Frame exposing
 // exactly the members those lines touch.  getBestMatch / verifyAngle are private statics of ORBMatcher: the
@@ -24,6 +26,15 @@ namespace ORB_SLAM2_ROS2
 {
 #include "ref_orbmatcher_ranges.inc"
 #include "ref_frame_cc_ranges.inc"
+
+// Frame::Frame(colorImg, depthImg, ...) (src/Frame.cc:125-159): the initialiser list (:127-128) sets mLeftIm and the image bounds
+// (done by the harness); the body is the reference's own lines
+void Frame::rgbdCtorBody(cv::Mat colorImg, cv::Mat depthImg, int nFeatures, const std::string &briefFp, int maxThresh, int minThresh, float dScale,
+                         int nLevels, float scale)
+{
+  mLeftIm = colorImg;
+#include "ref_frame_rgbd_body.inc"
+}
 } // namespace ORB_SLAM2_ROS2
 
 namespace ref_private

@@ -187,6 +187,16 @@ public:
       }
     dst = out;
   }
+  // Mat /= scalar on CV_32F (the RGB-D ctor's depthImg /= dScale, src/Frame.cc:131): OpenCV evaluates it as
+  // convertTo(m, -1, 1. / s), i.e. a float multiply by (float)(1. / s) (cvtScale32f)
+  Mat &operator/=(double s)
+  {
+    assert(type_ == CV_32F);
+    const float a = (float)(1.0 / s);
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) at<float>(r, c) = at<float>(r, c) * a;
+    return *this;
+  }
   static Mat ones(int r, int c, int type)
   {
     assert(type == CV_32F);

@@ -142,6 +142,32 @@ def test_stereo_identical(R, template_path, cfg):
     assert np.median(el.kps["x"][m] - ur[m]) == pytest.approx(disp, abs=1.0)
 
 
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32], ids=["u16", "f32"])
+@pytest.mark.parametrize("use_dist", [True, False], ids=["tum_distortion", "no_distortion"])
+def test_rgbd_ctor_identical(R, template_path, dtype, use_dist):
+    """the reference's own RGB-D Frame ctor body (src/Frame.cc:130-158, compiled verbatim into oracle/_ref) against the
+    restatement: extraction, undistortion, depth lookup at the RAW keypoint, uRight = x_undistorted - bf / d"""
+    c = synth.TUM
+    gray = synth.synth_image(c["height"], c["width"], 12)
+    depth = synth.synth_depth_u16(c["height"], c["width"], 12, c["depth_scale"])
+    if dtype == np.float32:
+        depth = depth.astype(np.float32)
+    dist = np.array(c["dist"], np.float32) if use_dist else None
+    R.ref_reset()
+    bf = R.ref_set_camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], dist)
+    kps, desc, ur, dp = R.ref_rgbd(gray, depth, c["depth_scale"], template_path, 1000, 8, 1.2)
+    e = R.extract(gray, 1000, 8, 1.2)
+    ku = e.kps.copy()
+    if use_dist:
+        xy = R.undistort_points(np.stack([e.kps["x"], e.kps["y"]], 1), c["fx"], c["fy"], c["cx"], c["cy"], dist)
+        ku["x"], ku["y"] = xy[:, 0], xy[:, 1]
+    assert _same_kps(kps, ku) and np.array_equal(desc, e.desc)
+    our, odp = R.rgbd_lookup(depth, c["depth_scale"], e.kps, ku, bf)
+    assert np.array_equal(dp, odp) and np.array_equal(ur, our)
+    assert 0.05 < (dp < 0).mean() < 0.2 and (dp > 0).sum() > 700
+    R.ref_set_camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], None)
+
+
 def test_undistort_identical(R):
     c = synth.TUM
     R.ref_set_camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], np.array(c["dist"], np.float32))
