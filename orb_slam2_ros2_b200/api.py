@@ -171,7 +171,7 @@ def load_library(build_if_missing: bool = True):
     L.orbx_bow_transform_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(OrbxDeviceBow)]
     L.orbx_search_by_bow.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.orbx_frame_epoch.argtypes = [vp]
-    L.orbx_debug_quadtree_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.orbx_debug_quadtree_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.orbx_set_graph.argtypes = [vp, C.c_int]
     L.orbx_frame_epoch.restype = C.c_uint64
     L.orbx_frame_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -388,8 +388,15 @@ class Context:
     def quadtree_stats(self):
         """(loop-free, sequential) counts of the (image, level) quadtree problems solved so far"""
         a, b = C.c_int64(), C.c_int64()
-        _check(self._h, self._L.orbx_debug_quadtree_stats(self._h, C.byref(a), C.byref(b)), "orbx_debug_quadtree_stats")
+        _check(self._h, self._L.orbx_debug_quadtree_stats(self._h, C.byref(a), C.byref(b), None), "orbx_debug_quadtree_stats")
         return a.value, b.value
+
+    def quadtree_phase_cycles(self):
+        """SM cycles per phase of the loop-free quadtree path, summed over the problems solved so far"""
+        a, b = C.c_int64(), C.c_int64()
+        ph = (C.c_int64 * 8)()
+        _check(self._h, self._L.orbx_debug_quadtree_stats(self._h, C.byref(a), C.byref(b), ph), "orbx_debug_quadtree_stats")
+        return a.value, list(ph)
 
     def run_quadtree(self, level: int, xs, ys, scores) -> np.ndarray:
         """run only the quadtree kernel on a corner list (ROI coords, detection order) -> (m,3) survivors in ROI coords"""

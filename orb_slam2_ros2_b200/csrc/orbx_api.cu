@@ -359,8 +359,8 @@ int alloc_buffers(orbx_ctx *c)
   c->in_pitch = ((size_t)c->cfg.width + 15) & ~(size_t)15;
   if ((rc = dev_alloc(c, &c->d_in, ni * c->in_pitch * (size_t)c->cfg.height))) return rc;
   if ((rc = dev_alloc(c, &c->d_depth_in, nf * (size_t)c->cfg.width * (size_t)c->cfg.height * 4))) return rc;
-  if ((rc = dev_alloc(c, &p.qt_stats, 2))) return rc;
-  ORBX_CUDA(c, cudaMemset(p.qt_stats, 0, 2 * sizeof(unsigned long long)));
+  if ((rc = dev_alloc(c, &p.qt_stats, 16))) return rc;
+  ORBX_CUDA(c, cudaMemset(p.qt_stats, 0, 16 * sizeof(unsigned long long)));
   ORBX_CUDA(c, cudaMemset(p.n_kps, 0, ni * sizeof(int)));
   ORBX_CUDA(c, cudaMemset(p.n_matches, 0, ni * sizeof(int)));
   return ORBX_OK;
@@ -1648,15 +1648,17 @@ extern "C"
     return ORBX_OK;
   }
 
-  int orbx_debug_quadtree_stats(orbx_ctx *c, int64_t *fast, int64_t *sequential)
+  int orbx_debug_quadtree_stats(orbx_ctx *c, int64_t *fast, int64_t *sequential, int64_t *phase_cycles)
   {
     if (!c) return ORBX_ERR_INVALID_ARG;
     ORBX_CUDA(c, cudaSetDevice(c->device));
     ORBX_CUDA(c, cudaDeviceSynchronize());
-    unsigned long long h[2] = {0, 0};
+    unsigned long long h[16] = {};
     ORBX_CUDA(c, cudaMemcpy(h, c->p.qt_stats, sizeof(h), cudaMemcpyDeviceToHost));
     if (fast) *fast = (int64_t)h[0];
     if (sequential) *sequential = (int64_t)h[1];
+    if (phase_cycles)
+      for (int i = 0; i < 8; ++i) phase_cycles[i] = (int64_t)h[2 + i];
     return ORBX_OK;
   }
 

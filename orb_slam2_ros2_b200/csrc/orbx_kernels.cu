@@ -625,9 +625,17 @@ __host__ __device__ inline int fp_hash_size(int node_cap)
 }
 
 // shared memory: node pool | bucket heads+tails | big-node list | (smem path) ia, ib (u16), key (u32)
+// node-pool region: the sequential path's node pool; the loop-free path keeps its radix histograms (8 warps x 512 bins, u16)
+// there during the sort and its records / leaves afterwards
+__host__ __device__ inline size_t qt_pool_bytes(int node_cap)
+{
+  const size_t b = qt_align16((size_t)node_cap * kNodeBytes);
+  return b > 8192 ? b : 8192;
+}
+
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells)
 {
-  size_t b = qt_align16((size_t)node_cap * kNodeBytes);
+  size_t b = qt_pool_bytes(node_cap);
   b += qt_align16((size_t)max_level_cells * sizeof(int));
   b += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
   b += qt_align16((size_t)big_cap * sizeof(uint16_t));
@@ -1207,28 +1215,43 @@ __device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *
 //   this formulation (checked against the oracle).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kFpWarps = kQtThreads / 32;
-constexpr int kFpBins = 128;            // radix bins per pass: 125 (three base-5 digits) or the strips (+1: "in no strip")
 constexpr uint32_t kFpHashEmpty = 0xffffffffu;
 constexpr uint32_t kFpRoot = 0xffffu;
 constexpr int kFpMaxS = 4095;           // record index bits in a hash entry
 constexpr int kFpKeyDepth = kKeyLevels; // 9
 
+// Views into the CTA's dynamic shared memory, derived from three numbers (a by-value table of pointers would live in local memory):
+//   node-pool region  lf_I u32[nc] | s_pos s_cnt s_par s_rank lf_best lf_cnt u16[nc] | s_dc s_pop s_delta u8[nc]   (19 B per node)
+//   lists region      keys u32[cap] | ord u16[cap] | lvd u8[cap] resp u8[cap] (the second index array of the sort) | hist | hash
 struct QtFast
 {
-  uint32_t *keys;  // [n] descent key per corner; becomes the flag array at the end
-  uint16_t *ord;   // [n] sorted position -> corner
-  uint8_t *lvd;    // [m + 1] L | vd << 4
-  uint16_t *hist;  // [kFpWarps][kFpBins]
-  int *D;          // [256]
+  uint8_t *pool;   // node-pool region
+  uint8_t *lists;  // lists region
+  int *D;          // [256] sum of deltas per node count (the bucket heads / tails of the sequential path)
   int *bin_start;  // [K * 125 + 1]
-  uint32_t *lf_I;
-  uint16_t *s_pos, *s_cnt, *s_par, *s_rank, *lf_best, *lf_cnt;
-  uint8_t *s_dc, *s_pop;
-  int8_t *s_delta;
-  uint32_t *hash;
-  uint32_t hash_mask;
-  int cap_S;
+  int cap, nc;     // list capacity (qt_smem_cap), node capacity
   int m, K;
+  uint32_t hmask;  // hash size - 1
+  __device__ __forceinline__ uint32_t *keys() const { return (uint32_t *)lists; }                       // descent key per corner; flag array at the end
+  __device__ __forceinline__ uint16_t *ord() const { return (uint16_t *)(lists + 4 * (size_t)cap); }    // sorted position -> corner
+  __device__ __forceinline__ uint16_t *ib() const { return (uint16_t *)(lists + 6 * (size_t)cap); }     // second index array of the sort
+  __device__ __forceinline__ uint8_t *lvd() const { return lists + 6 * (size_t)cap; }                   // [m + 1] L | vd << 4
+  __device__ __forceinline__ uint8_t *resp() const { return lists + 7 * (size_t)cap; }                  // [m] response by sorted position
+  __device__ __forceinline__ uint16_t *hist() const { return (uint16_t *)(lists + qt_align16(8 * (size_t)cap)); }
+  __device__ __forceinline__ uint32_t *hash() const { return (uint32_t *)(lists + qt_align16(8 * (size_t)cap) + qt_align16((size_t)8 * 128 * sizeof(uint16_t))); }
+  __device__ __forceinline__ uint32_t hash_mask() const { return hmask; }
+  __device__ __forceinline__ int cap_S() const { return min(nc, kFpMaxS); }
+  __device__ __forceinline__ uint32_t *lf_I() const { return (uint32_t *)pool; }
+  __device__ __forceinline__ uint16_t *u16(int k) const { return (uint16_t *)(pool + 4 * (size_t)nc) + (size_t)k * nc; }
+  __device__ __forceinline__ uint16_t *s_pos() const { return u16(0); }
+  __device__ __forceinline__ uint16_t *s_cnt() const { return u16(1); }
+  __device__ __forceinline__ uint16_t *s_par() const { return u16(2); }
+  __device__ __forceinline__ uint16_t *s_rank() const { return u16(3); }
+  __device__ __forceinline__ uint16_t *lf_best() const { return u16(4); }
+  __device__ __forceinline__ uint16_t *lf_cnt() const { return u16(5); }
+  __device__ __forceinline__ uint8_t *s_dc() const { return pool + 16 * (size_t)nc; }
+  __device__ __forceinline__ uint8_t *s_pop() const { return pool + 17 * (size_t)nc; }
+  __device__ __forceinline__ int8_t *s_delta() const { return (int8_t *)(pool + 18 * (size_t)nc); }
 };
 
 __device__ __forceinline__ uint32_t fp_g5(uint32_t d) { return min(d, 4u); }
@@ -1240,25 +1263,25 @@ __device__ __forceinline__ uint32_t fp_digit(uint32_t key, int d) // d == 0: str
 {
   return d == 0 ? key >> kKeyStripShift : (key >> (kKeyStripShift - 3 * d)) & 7u;
 }
-__device__ __forceinline__ int fp_L(const QtFast &f, int p) { return f.lvd[p] & 15; }
-__device__ __forceinline__ int fp_vd(const QtFast &f, int p) { return f.lvd[p] >> 4; }
+__device__ __forceinline__ int fp_L(const QtFast &f, int p) { return f.lvd()[p] & 15; }
+__device__ __forceinline__ int fp_vd(const QtFast &f, int p) { return f.lvd()[p] >> 4; }
 
 __device__ __forceinline__ void fp_hash_insert(const QtFast &f, int pos, int depth, int idx)
 {
   const uint32_t k = ((uint32_t)pos << 4) | (uint32_t)depth, e = (k << 12) | (uint32_t)idx;
-  uint32_t h = (k * 2654435761u) & f.hash_mask;
-  while (atomicCAS(&f.hash[h], kFpHashEmpty, e) != kFpHashEmpty) h = (h + 1) & f.hash_mask;
+  uint32_t h = (k * 2654435761u) & f.hash_mask();
+  while (atomicCAS(&f.hash()[h], kFpHashEmpty, e) != kFpHashEmpty) h = (h + 1) & f.hash_mask();
 }
 __device__ __forceinline__ int fp_hash_find(const QtFast &f, int pos, int depth)
 {
   const uint32_t k = ((uint32_t)pos << 4) | (uint32_t)depth;
-  uint32_t h = (k * 2654435761u) & f.hash_mask;
+  uint32_t h = (k * 2654435761u) & f.hash_mask();
   for (;;)
   {
-    const uint32_t e = f.hash[h];
+    const uint32_t e = f.hash()[h];
     if (e == kFpHashEmpty) return -1;
     if ((e >> 12) == k) return (int)(e & 0xfffu);
-    h = (h + 1) & f.hash_mask;
+    h = (h + 1) & f.hash_mask();
   }
 }
 
@@ -1268,7 +1291,7 @@ template <class Fn> __device__ __forceinline__ void fp_nodes_at(const QtFast &f,
   const int l0 = fp_L(f, p), l1 = fp_L(f, p + 1);
   const int dmax = min(min(l1 - 1, fp_vd(f, p)), kFpKeyDepth);
   if (dmax < l0) return;
-  const int b3 = fp_bin3(f.keys[f.ord[p]]);
+  const int b3 = fp_bin3(f.keys()[f.ord()[p]]);
   for (int d = l0; d <= dmax; ++d)
   {
     int cnt, ne;
@@ -1312,7 +1335,7 @@ template <class Fn> __device__ __forceinline__ void fp_children(const QtFast &f,
   else if (d <= 2)
   {
     const int span = d == 0 ? 125 : (d == 1 ? 25 : 5), w = span / 5;
-    const int B = (fp_bin3(f.keys[f.ord[p]]) / span) * span;
+    const int B = (fp_bin3(f.keys()[f.ord()[p]]) / span) * span;
     for (int c = 0; c < 4; ++c)
     {
       const int a = f.bin_start[B + c * w], b = f.bin_start[B + (c + 1) * w];
@@ -1326,7 +1349,7 @@ template <class Fn> __device__ __forceinline__ void fp_children(const QtFast &f,
     for (int q = p + 1; q <= end; ++q)
       if (q == end || fp_L(f, q) == d + 1)
       {
-        const uint32_t dg = fp_digit(f.keys[f.ord[g0]], d + 1);
+        const uint32_t dg = fp_digit(f.keys()[f.ord()[g0]], d + 1);
         if (dg != kDigitDrop) fn((int)dg, g0, q);
         g0 = q;
       }
@@ -1340,66 +1363,114 @@ __device__ __forceinline__ bool fp_chain_before(const QtFast &f, uint32_t u, uin
   for (;;)
   {
     const uint32_t pa = a, pb = b;
-    a = f.s_par[a];
-    b = f.s_par[b];
-    if (a == b) return (f.s_dc[pa] & 15u) < (f.s_dc[pb] & 15u);
-    const uint32_t ca = a == kFpRoot ? 0x10000u : f.s_cnt[a], cb = b == kFpRoot ? 0x10000u : f.s_cnt[b];
+    a = f.s_par()[a];
+    b = f.s_par()[b];
+    if (a == b) return (f.s_dc()[pa] & 15u) < (f.s_dc()[pb] & 15u);
+    const uint32_t ca = a == kFpRoot ? 0x10000u : f.s_cnt()[a], cb = b == kFpRoot ? 0x10000u : f.s_cnt()[b];
     if (ca != cb) return ca > cb;
     if (a == kFpRoot || b == kFpRoot) return a == kFpRoot; // unreachable (counts differ), keeps the loop finite
   }
 }
 
-__device__ __noinline__ bool qt_fast_path(QtFast f, const uint32_t *kp, uint16_t *ib, int n, int need, int *s_warp)
+// warp-aggregated slot allocation: the lanes that execute this together take consecutive indices with ONE shared-memory atomic
+__device__ __forceinline__ int fp_alloc(int *counter)
 {
-  __shared__ int s_m, s_live0, s_dbig, s_neg, s_deep, s_cstar, s_before, s_nS, s_R0, s_k, s_nleaf, s_mode;
+  const unsigned act = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(act) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(act));
+  base = __shfl_sync(act, base, leader);
+  return base + __popc(act & ((1u << lane) - 1u));
+}
+
+constexpr int kFpSortBins = 512;  // radix bins per pass (three raw 3-bit digits); per-warp histograms of u16 live in the node-pool region
+constexpr int kFpSmall = 8;       // node counts below this are accumulated in per-warp counters (they are the hot histogram bins)
+
+__device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *D, int *bin_start, int cap, int nc, int K_, const uint32_t *kp, int n, int need,
+                                          int *s_warp, unsigned long long *stats)
+{
+  __shared__ int s_m, s_live0, s_dbig, s_neg, s_deep, s_cstar, s_before, s_nS, s_k, s_nleaf, s_mode, s_first;
+  __shared__ int s_small[kFpWarps][kFpSmall];
   __shared__ unsigned long long s_amax;
+  QtFast f;
+  f.pool = pool, f.lists = lists, f.D = D, f.bin_start = bin_start, f.cap = cap, f.nc = nc, f.m = 0, f.K = K_;
+  f.hmask = (uint32_t)fp_hash_size(nc) - 1u;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
   const int K = f.K;
   enum { kRun = 0, kEmpty = 1, kNoPop = 2, kBail = 3 };
+  long long t_prev = clock64();
+  auto tick = [&](int phase) {
+    if (tid == 0 && stats)
+    {
+      const long long t = clock64();
+      atomicAdd(&stats[2 + phase], (unsigned long long)(t - t_prev));
+      t_prev = t;
+    }
+  };
 
-  // ---- F1: stable LSD radix sort of the corner indices by key.  Every warp owns a contiguous segment of the input; equal
-  // digits inside a 32-element step are ranked with __match_any_sync, so no atomics and the passes are stable.
+  // ---- F1: stable LSD radix sort of the corner indices by key: three raw digits (9 bits) per pass, low digits first; the last
+  // pass folds the strip in (K <= 4: strip * 125 + the three digits in base 5) or is followed by a pass over the strips.  Every
+  // warp owns a contiguous segment of the input; equal digits inside a 32-element step are ranked with __match_any_sync, so
+  // there are no atomics and every pass is stable.  The first pass reads the identity order, so no index array is initialised.
+  uint16_t *sorted;
   {
-    uint16_t *src = f.ord, *dst = ib;
+    uint16_t *hist = (uint16_t *)pool; // [kFpWarps][kFpSortBins], dead before the records are built
+    const int npass = K <= 4 ? 3 : 4;
+    uint16_t *bufA = npass == 3 ? f.ord() : f.ib(), *bufB = npass == 3 ? f.ib() : f.ord(); // the last pass lands in f.ord()
+    const uint16_t *src = nullptr;
+    uint16_t *dst = bufA;
     const int seg = (n + kFpWarps - 1) / kFpWarps, lo = min(wid * seg, n), hi = min(lo + seg, n);
-    for (int pass = 0; pass < 4; ++pass)
+    const uint32_t *keys = f.keys();
+    for (int pass = 0; pass < npass; ++pass)
     {
       auto digit = [&](uint32_t key) -> uint32_t {
-        if (pass == 3)
-        {
-          const uint32_t s = key >> kKeyStripShift;
-          return s == kKeyNoStrip ? (uint32_t)K : s;
-        }
-        const uint32_t v = (key >> (9 * pass)) & 511u;
-        return fp_g5(v >> 6) * 25u + fp_g5((v >> 3) & 7u) * 5u + fp_g5(v & 7u);
+        if (pass < 2) return (key >> (9 * pass)) & 511u;
+        if (npass == 4) return pass == 2 ? (key >> 18) & 511u : ((key >> kKeyStripShift) == kKeyNoStrip ? (uint32_t)K : key >> kKeyStripShift);
+        return (key >> kKeyStripShift) == kKeyNoStrip ? (uint32_t)(K * kQtBinsPerStrip) : (uint32_t)fp_bin3(key);
       };
-      for (int i = tid; i < kFpWarps * kFpBins; i += kQtThreads) f.hist[i] = 0;
+      {
+        uint32_t *h32 = (uint32_t *)hist;
+        for (int i = tid; i < kFpWarps * kFpSortBins / 2; i += kQtThreads) h32[i] = 0u;
+      }
       __syncthreads();
+      uint16_t *myh = hist + wid * kFpSortBins;
       for (int i0 = lo; i0 < hi; i0 += 32)
       {
         const int i = i0 + lane;
-        const uint32_t dg = i < hi ? digit(f.keys[src[i]]) : 0xffffu;
+        uint32_t dg = 0xffffu;
+        if (i < hi) dg = digit(keys[src ? src[i] : i]);
         const unsigned peers = __match_any_sync(FULL, dg);
-        if (i < hi && lane == __ffs(peers) - 1) f.hist[wid * kFpBins + dg] += (uint16_t)__popc(peers);
+        if (i < hi && lane == __ffs(peers) - 1) myh[dg] += (uint16_t)__popc(peers);
         __syncwarp();
       }
       __syncthreads();
-      int tot = 0;
-      if (tid < kFpBins)
-        for (int w = 0; w < kFpWarps; ++w) tot += f.hist[w * kFpBins + tid];
-      int total;
-      const int base = block_exclusive_scan<kQtThreads>(tot, total, s_warp);
-      if (tid < kFpBins)
       {
-        int run = base;
+        // bins 2 tid and 2 tid + 1: totals over the warps, block-wide exclusive scan, per-warp bases
+        uint32_t c0[kFpWarps], c1[kFpWarps];
+        int t0 = 0, t1 = 0;
+#pragma unroll
         for (int w = 0; w < kFpWarps; ++w)
         {
-          const int c = f.hist[w * kFpBins + tid];
-          f.hist[w * kFpBins + tid] = (uint16_t)run;
-          run += c;
+          const uint32_t pr = *(const uint32_t *)(hist + w * kFpSortBins + 2 * tid);
+          c0[w] = pr & 0xffffu, c1[w] = pr >> 16;
+          t0 += (int)c0[w], t1 += (int)c1[w];
         }
-        if (pass == 3 && tid == K) s_m = base; // corners in no strip sort behind everything
+        int total;
+        int run0 = block_exclusive_scan<kQtThreads>(t0 + t1, total, s_warp);
+        int run1 = run0 + t0;
+        const int last_bin = npass == 4 ? K : K * kQtBinsPerStrip; // "in no strip": sorts behind everything
+        if (pass == npass - 1)
+        {
+          if (2 * tid == last_bin) s_m = run0;
+          if (2 * tid + 1 == last_bin) s_m = run1;
+        }
+#pragma unroll
+        for (int w = 0; w < kFpWarps; ++w)
+        {
+          *(uint32_t *)(hist + w * kFpSortBins + 2 * tid) = (uint32_t)run0 | ((uint32_t)run1 << 16);
+          run0 += (int)c0[w], run1 += (int)c1[w];
+        }
       }
       __syncthreads();
       for (int i0 = lo; i0 < hi; i0 += 32)
@@ -1408,58 +1479,79 @@ __device__ __noinline__ bool qt_fast_path(QtFast f, const uint32_t *kp, uint16_t
         uint32_t idx = 0, dg = 0xffffu;
         if (i < hi)
         {
-          idx = src[i];
-          dg = digit(f.keys[idx]);
+          idx = src ? src[i] : (uint32_t)i;
+          dg = digit(keys[idx]);
         }
         const unsigned peers = __match_any_sync(FULL, dg);
         uint32_t b = 0;
         if (i < hi)
         {
-          b = f.hist[wid * kFpBins + dg];
+          b = myh[dg];
           dst[b + __popc(peers & lt_mask)] = (uint16_t)idx;
         }
         __syncwarp();
-        if (i < hi && lane == __ffs(peers) - 1) f.hist[wid * kFpBins + dg] = (uint16_t)(b + __popc(peers));
+        if (i < hi && lane == __ffs(peers) - 1) myh[dg] = (uint16_t)(b + __popc(peers));
         __syncwarp();
       }
       __syncthreads();
-      uint16_t *t = src;
       src = dst;
-      dst = t;
+      dst = dst == bufA ? bufB : bufA;
     }
-    // four passes: the sorted order is back in f.ord, `ib` is free from here on (-> lvd)
+    sorted = f.ord();
   }
   const int m = s_m;
   f.m = m;
+  tick(0);
 
-  // ---- F2: L / vd bytes, bin table (start of every (strip, d1, d2, d3) bin in the sorted order), zeroed accumulators
-  for (int p = tid; p <= m; p += kQtThreads)
+  // ---- F2: L / vd bytes, responses by sorted position, bin table (start of every (strip, d1, d2, d3) bin), zeroed accumulators
   {
-    uint32_t l = 0, v = 0;
-    if (p < m)
+    const uint32_t *keys = f.keys();
+    uint8_t *lvd = f.lvd(), *resp = f.resp();
+    for (int p0 = tid; p0 <= m; p0 += 4 * kQtThreads)
     {
-      const uint32_t key = f.keys[f.ord[p]];
-      const uint32_t t7 = key & (key >> 1) & (key >> 2) & 0x01249249u; // bit 0 of every digit that equals 7
-      v = t7 ? (uint32_t)((27 - (31 - __clz((int)t7))) / 3 - 1) : (uint32_t)kFpKeyDepth;
-      if (p > 0)
+      uint32_t r[4], lv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
       {
-        const uint32_t x = key ^ f.keys[f.ord[p - 1]];
-        if (x == 0)
-          l = kFpKeyDepth + 1;
-        else
+        const int p = p0 + u * kQtThreads;
+        r[u] = 0, lv[u] = 0;
+        if (p < m)
         {
-          const int hb = 31 - __clz((int)x);
-          l = hb >= kKeyStripShift ? 0u : (uint32_t)((29 - hb) / 3);
+          const uint32_t idx = sorted[p];
+          r[u] = kp[idx]; // global (L2): the four loads of a batch are in flight together
+          const uint32_t key = keys[idx];
+          const uint32_t t7 = key & (key >> 1) & (key >> 2) & 0x01249249u; // bit 0 of every digit that equals 7
+          const uint32_t v = t7 ? (uint32_t)((27 - (31 - __clz((int)t7))) / 3 - 1) : (uint32_t)kFpKeyDepth;
+          uint32_t l = 0;
+          if (p > 0)
+          {
+            const uint32_t x = key ^ keys[sorted[p - 1]];
+            if (x == 0)
+              l = kFpKeyDepth + 1;
+            else
+            {
+              const int hb = 31 - __clz((int)x);
+              l = hb >= kKeyStripShift ? 0u : (uint32_t)((29 - hb) / 3);
+            }
+          }
+          lv[u] = l | (v << 4);
         }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        const int p = p0 + u * kQtThreads;
+        if (p <= m) lvd[p] = (uint8_t)lv[u];
+        if (p < m) resp[p] = (uint8_t)(r[u] >> 24);
+      }
     }
-    f.lvd[p] = (uint8_t)(l | (v << 4));
   }
   for (int i = tid; i < 256; i += kQtThreads) f.D[i] = 0;
-  for (int i = tid; i <= (int)f.hash_mask; i += kQtThreads) f.hash[i] = kFpHashEmpty;
+  for (int i = tid; i <= (int)f.hash_mask(); i += kQtThreads) f.hash()[i] = kFpHashEmpty;
+  if (tid < kFpWarps * kFpSmall) (&s_small[0][0])[tid] = 0;
   if (tid == 0)
   {
-    s_live0 = 0, s_dbig = 0, s_neg = 0, s_deep = 0, s_cstar = 0, s_before = 0, s_nS = 0, s_R0 = 0, s_k = 0, s_nleaf = 0, s_mode = kRun;
+    s_live0 = 0, s_dbig = 0, s_neg = 0, s_deep = 0, s_cstar = 0, s_before = 0, s_nS = 0, s_k = 0, s_nleaf = 0, s_mode = kRun, s_first = 0x7fffffff;
     s_amax = 0ull;
   }
   __syncthreads();
@@ -1470,24 +1562,22 @@ __device__ __noinline__ bool qt_fast_path(QtFast f, const uint32_t *kp, uint16_t
       for (int b = tid; b <= nb; b += kQtThreads) f.bin_start[b] = 0;
     }
     else
+    {
       for (int p = tid; p < m; p += kQtThreads)
       {
         if (p > 0 && fp_L(f, p) > 3) continue; // same bin as the predecessor
-        const int b = fp_bin3(f.keys[f.ord[p]]);
-        const int pb = p > 0 ? fp_bin3(f.keys[f.ord[p - 1]]) : -1;
+        const int b = fp_bin3(f.keys()[sorted[p]]);
+        const int pb = p > 0 ? fp_bin3(f.keys()[sorted[p - 1]]) : -1;
         for (int bb = pb + 1; bb <= b; ++bb) f.bin_start[bb] = p;
       }
+      const int last = fp_bin3(f.keys()[sorted[m - 1]]);
+      for (int b = last + 1 + tid; b <= nb; b += kQtThreads) f.bin_start[b] = m;
+    }
   }
   __syncthreads();
-  if (m > 0)
-  {
-    const int nb = K * kQtBinsPerStrip;
-    const int last = fp_bin3(f.keys[f.ord[m - 1]]);
-    for (int b = last + 1 + tid; b <= nb; b += kQtThreads) f.bin_start[b] = m;
-  }
-  __syncthreads();
+  tick(1);
 
-  // ---- F3: deltas of all nodes by count
+  // ---- F3: deltas of all nodes by count (counts below kFpSmall -- most nodes -- in per-warp counters: no hot shared address)
   if (tid < K) atomicAdd(&s_live0, f.bin_start[(tid + 1) * kQtBinsPerStrip] > f.bin_start[tid * kQtBinsPerStrip] ? 1 : 0);
   for (int p = tid; p < m; p += kQtThreads)
     fp_nodes_at(f, p, [&](int d, int cnt, int ne) {
@@ -1497,77 +1587,108 @@ __device__ __noinline__ bool qt_fast_path(QtFast f, const uint32_t *kp, uint16_t
       {
         const int delta = ne - 1;
         if (delta < 0) atomicMax(&s_neg, cnt);
-        if (cnt < 256)
+        if (cnt < kFpSmall)
+        {
+          if (delta) atomicAdd(&s_small[wid][cnt], delta);
+        }
+        else if (cnt < 256)
           atomicAdd(&f.D[cnt], delta);
         else
           atomicAdd(&s_dbig, delta);
       }
     });
   __syncthreads();
+  tick(2);
 
-  // ---- F4: where does the loop stop?
-  if (tid == 0)
+  // ---- F4: where does the loop stop?  thread t <-> count c = 255 - t: after(c) = node count once every node of >= c corners popped
   {
-    const int live0 = s_live0, hard = max(s_neg, s_deep);
-    int mode = kRun;
-    if (live0 == 0)
-      mode = kEmpty;
-    else if (live0 >= need)
-      mode = kNoPop;
-    else
+    const int c = 255 - tid;
+    int d = 0;
+    if (c >= kFpSmall)
+      d = f.D[c];
+    else if (c >= 2)
+      for (int w = 0; w < kFpWarps; ++w) d += s_small[w][c];
+    int inc = d; // inclusive scan over t
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
     {
-      int run = live0 + s_dbig, cstar = 0;
-      if (run >= need)
-        mode = kBail; // the loop stops among the nodes of 256+ corners
-      else
-      {
-        for (int c = 255; c >= 2; --c)
-        {
-          const int after = run + f.D[c];
-          if (after >= need)
-          {
-            cstar = c;
-            break;
-          }
-          run = after;
-        }
-        if (cstar == 0)
-          mode = hard >= 2 ? kBail : kEmpty; // starved: the multimap drains (src/ORBExtractor.cc:151), 0 keypoints
-        else if (cstar <= hard)
-          mode = kBail;
-        s_cstar = cstar;
-        s_before = run;
-      }
+      const int t = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += t;
     }
-    s_mode = mode;
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid; ++w) base += s_warp[w];
+    const int live0 = s_live0;
+    const int after = live0 + s_dbig + base + inc;
+    const bool reached = c >= 2 && after >= need;
+    if (reached) atomicMin(&s_first, tid);
+    __syncthreads();
+    if (tid == s_first)
+    {
+      s_cstar = c;
+      s_before = after - d;
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+      const int hard = max(s_neg, s_deep);
+      int mode = kRun;
+      if (live0 == 0)
+        mode = kEmpty;
+      else if (live0 >= need)
+        mode = kNoPop;
+      else if (live0 + s_dbig >= need)
+        mode = kBail; // the loop stops among the nodes of 256+ corners
+      else if (s_first == 0x7fffffff)
+        mode = hard >= 2 ? kBail : kEmpty; // starved: the multimap drains (src/ORBExtractor.cc:151), 0 keypoints
+      else if (s_cstar <= hard || s_cstar >= 255)
+        mode = kBail; // (bucket 255 of the rank pass also holds the larger nodes)
+      if (mode != kRun) s_cstar = 0;
+      s_mode = mode;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (s_mode == kBail) return false;
   const int cstar = s_cstar;
+  tick(3);
 
   if (s_mode == kRun)
   {
-    // ---- F5: records of the nodes that can pop
+    // ---- F5: records of the nodes that can pop (count >= c*), hash (start, depth) -> record, parent links
     for (int p = tid; p < m; p += kQtThreads)
+    {
+      // the nodes below depth 3 that start here lie inside one (strip, d1, d2, d3) bin: nothing to record if the bin is too small
+      const int l0 = fp_L(f, p);
+      if (l0 >= 3)
+      {
+        const int b3 = fp_bin3(f.keys()[sorted[p]]);
+        if (f.bin_start[b3 + 1] - f.bin_start[b3] < cstar) continue;
+      }
       fp_nodes_at(f, p, [&](int d, int cnt, int ne) {
         if (cnt < cstar) return;
-        const int idx = atomicAdd(&s_nS, 1);
-        if (cnt > cstar) atomicAdd(&s_R0, 1);
-        if (idx >= f.cap_S) return;
-        f.s_pos[idx] = (uint16_t)p;
-        f.s_cnt[idx] = (uint16_t)cnt;
-        f.s_dc[idx] = (uint8_t)((d << 4) | (int)fp_digit(f.keys[f.ord[p]], d));
-        f.s_delta[idx] = (int8_t)(ne - 1);
-        f.s_pop[idx] = 0;
+        const int idx = fp_alloc(&s_nS);
+        if (idx >= f.cap_S()) return;
+        f.s_pos()[idx] = (uint16_t)p;
+        f.s_cnt()[idx] = (uint16_t)cnt;
+        f.s_dc()[idx] = (uint8_t)((d << 4) | (int)fp_digit(f.keys()[sorted[p]], d));
+        f.s_delta()[idx] = (int8_t)(ne - 1);
+        f.s_pop()[idx] = 0;
         fp_hash_insert(f, p, d, idx);
       });
+    }
     __syncthreads();
-    const int nS = s_nS, R0 = s_R0;
-    if (nS > f.cap_S || nS - R0 > kFpWarps * kFpBins) return false; // uniform
-    // parent links
+    const int nS = s_nS;
+    if (nS > f.cap_S()) return false; // uniform
+    // bucket histogram of the records (H aliases D, which is dead now): H[b], b = min(count, 255)
+    int *H = f.D;
+    for (int i = tid; i < 256; i += kQtThreads) H[i] = 0;
+    __syncthreads();
     for (int v = tid; v < nS; v += kQtThreads)
     {
-      const int d = f.s_dc[v] >> 4, p = f.s_pos[v];
+      atomicAdd(&H[min((int)f.s_cnt()[v], 255)], 1);
+      // parent link
+      const int d = f.s_dc()[v] >> 4, p = f.s_pos()[v];
       uint32_t par = kFpRoot;
       if (d > 0)
       {
@@ -1576,12 +1697,13 @@ __device__ __noinline__ bool qt_fast_path(QtFast f, const uint32_t *kp, uint16_t
         {
           // the parent's run starts earlier: lower bound of the (strip, d1 .. d(d-1)) prefix
           const int sh = kKeyStripShift - 3 * (d - 1);
-          const uint32_t want = f.keys[f.ord[p]] >> sh;
+          const uint32_t want = f.keys()[sorted[p]] >> sh;
           int lo = 0, hi = p;
+          if (d - 1 >= 3) lo = f.bin_start[fp_bin3(f.keys()[sorted[p]])]; // ... inside the depth-3 bin
           while (lo < hi)
           {
             const int mid = (lo + hi) >> 1;
-            if ((f.keys[f.ord[mid]] >> sh) < want)
+            if ((f.keys()[sorted[mid]] >> sh) < want)
               lo = mid + 1;
             else
               hi = mid;
@@ -1591,35 +1713,64 @@ __device__ __noinline__ bool qt_fast_path(QtFast f, const uint32_t *kp, uint16_t
         const int q = fp_hash_find(f, pp, d - 1);
         par = q < 0 ? 0xfffeu : (uint32_t)q;
       }
-      f.s_par[v] = (uint16_t)par;
+      f.s_par()[v] = (uint16_t)par;
       if (par == 0xfffeu) s_mode = kBail; // cannot happen: a parent holds at least as many corners as its child
     }
     __syncthreads();
     if (s_mode == kBail) return false;
+    tick(4);
 
-    // ---- F6: pop rank of every record
+    // ---- F6: pop rank of every record = records in higher buckets + position inside its own bucket (ancestor-count chains).
+    // start[b] = records in buckets above b (thread t <-> bucket 255 - t); list = the records grouped by bucket.
+    int *start = (int *)f.hist();                 // [256]
+    int *cursor = start + 256;                    // [256]   (the radix-histogram region: 2 KB)
+    uint16_t *list = (uint16_t *)f.lf_I();        // [nS]    (the leaf arrays are not in use yet)
+    uint16_t *dlt = f.lf_best();                  // [H[c*]] deltas of bucket c* in pop order
+    {
+      const int b = 255 - tid;
+      const int h = H[b];
+      int inc = h;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) s_warp[wid] = inc;
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < wid; ++w) base += s_warp[w];
+      start[b] = base + inc - h;
+      cursor[b] = base + inc - h;
+    }
+    __syncthreads();
+    for (int v = tid; v < nS; v += kQtThreads) list[atomicAdd(&cursor[min((int)f.s_cnt()[v], 255)], 1)] = (uint16_t)v;
+    __syncthreads();
+    const int R0 = start[cstar], mb = H[cstar];
     for (int v = tid; v < nS; v += kQtThreads)
     {
-      const uint32_t cv = f.s_cnt[v];
-      int r = 0;
-      for (int u = 0; u < nS; ++u)
+      const uint32_t cv = f.s_cnt()[v];
+      const int b = min((int)cv, 255);
+      const int j0 = start[b], j1 = j0 + H[b];
+      int r = j0;
+      for (int j = j0; j < j1; ++j)
       {
-        if (u == v) continue;
-        const uint32_t cu = f.s_cnt[u];
-        r += cu != cv ? (cu > cv) : fp_chain_before(f, (uint32_t)u, (uint32_t)v);
+        const uint32_t u = list[j];
+        if (u == (uint32_t)v) continue;
+        const uint32_t cu = f.s_cnt()[u]; // differs only inside the 255+ bucket
+        r += cu != cv ? (cu > cv) : fp_chain_before(f, u, (uint32_t)v);
       }
-      f.s_rank[v] = (uint16_t)r;
-      if ((int)cv == cstar) f.hist[r - R0] = (uint16_t)f.s_delta[v]; // deltas of bucket c* in pop order (all >= 0 here)
+      f.s_rank()[v] = (uint16_t)r;
+      if ((int)cv == cstar) dlt[r - R0] = (uint16_t)f.s_delta()[v]; // all >= 0 here (c* lies above every negative delta)
     }
     __syncthreads();
     if (wid == 0)
     {
-      const int mb = nS - R0;
       int run = s_before, k = 0;
       for (int j0 = 0; j0 < mb; j0 += 32)
       {
         const int j = j0 + lane;
-        const int val = j < mb ? (int)f.hist[j] : 0;
+        const int val = j < mb ? (int)dlt[j] : 0;
         int inc = val;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
@@ -1637,76 +1788,81 @@ __device__ __noinline__ bool qt_fast_path(QtFast f, const uint32_t *kp, uint16_t
     }
     __syncthreads();
     const int k = s_k;
-    for (int v = tid; v < nS; v += kQtThreads) f.s_pop[v] = ((int)f.s_cnt[v] > cstar || (int)f.s_rank[v] - R0 < k) ? 1 : 0;
+    for (int v = tid; v < nS; v += kQtThreads) f.s_pop()[v] = ((int)f.s_cnt()[v] > cstar || (int)f.s_rank()[v] - R0 < k) ? 1 : 0;
     __syncthreads();
   }
+  tick(5);
 
   // ---- F7: leaves (children of popped nodes -- and of the root -- that did not pop), best response of each
   if (s_mode != kEmpty)
   {
     const int nS = s_mode == kRun ? s_nS : 0;
+    const uint8_t *resp = f.resp();
     for (int item = tid; item <= nS; item += kQtThreads)
     {
       int p = 0, cnt = 0, d = -1;
       uint32_t prank = 0;
       if (item < nS)
       {
-        if (!f.s_pop[item]) continue;
-        p = f.s_pos[item], cnt = f.s_cnt[item], d = f.s_dc[item] >> 4;
-        prank = (uint32_t)f.s_rank[item] + 1u;
+        if (!f.s_pop()[item]) continue;
+        p = f.s_pos()[item], cnt = f.s_cnt()[item], d = f.s_dc()[item] >> 4;
+        prank = (uint32_t)f.s_rank()[item] + 1u;
       }
       fp_children(f, p, cnt, d, [&](int dg, int a, int b) {
         const int ccnt = b - a;
         if (cstar > 0 && ccnt >= cstar && ccnt >= 2)
         {
           const int q = fp_hash_find(f, a, d + 1);
-          if (q >= 0 && f.s_pop[q]) return; // popped itself: its children stand in for it
+          if (q >= 0 && f.s_pop()[q]) return; // popped itself: its children stand in for it
         }
         uint32_t best = 0, best_i = 0;
         for (int pos = a; pos < b; ++pos)
         {
-          const uint32_t idx = f.ord[pos];
-          const uint32_t r = kp[idx] >> 24;
-          if (r > best || (r == best && r > 0 && idx < best_i))
+          const uint32_t r = resp[pos];
+          if (r >= best && r > 0)
           {
-            best = r;
-            best_i = idx;
+            const uint32_t idx = sorted[pos];
+            if (r > best || idx < best_i) best = r, best_i = idx;
           }
         }
-        const int li = atomicAdd(&s_nleaf, 1);
-        if (li < f.cap_S)
+        const int li = fp_alloc(&s_nleaf);
+        if (li < f.cap_S())
         {
-          f.lf_best[li] = (uint16_t)best_i;
-          f.lf_cnt[li] = (uint16_t)ccnt;
-          f.lf_I[li] = (prank << 3) | (uint32_t)dg;
+          f.lf_best()[li] = (uint16_t)best_i;
+          f.lf_cnt()[li] = (uint16_t)ccnt;
+          f.lf_I()[li] = (prank << 3) | (uint32_t)dg;
         }
       });
     }
   }
   __syncthreads();
   const int nleaf = s_nleaf;
-  if (nleaf > f.cap_S) return false; // uniform
+  if (nleaf > f.cap_S()) return false; // uniform
+  tick(6);
   // nodes2kpoints (:182-192): the first min(need, |M|) entries in (count desc, insertion order); drop the rest from the end
   const int surplus = nleaf - min(need, nleaf);
   for (int it = 0; it < surplus; ++it)
   {
     for (int li = tid; li < nleaf; li += kQtThreads)
-      if (f.lf_cnt[li] != 0xffffu) atomicMax(&s_amax, ((unsigned long long)(0xffffu - f.lf_cnt[li]) << 32) | (unsigned long long)(f.lf_I[li] + 1u));
+      if (f.lf_cnt()[li] != 0xffffu)
+        atomicMax(&s_amax, ((unsigned long long)(0xffffu - f.lf_cnt()[li]) << 32) | (unsigned long long)(f.lf_I()[li] + 1u));
     __syncthreads();
     const unsigned long long top = s_amax;
     for (int li = tid; li < nleaf; li += kQtThreads)
-      if (f.lf_cnt[li] != 0xffffu && (((unsigned long long)(0xffffu - f.lf_cnt[li]) << 32) | (unsigned long long)(f.lf_I[li] + 1u)) == top) f.lf_cnt[li] = 0xffffu;
+      if (f.lf_cnt()[li] != 0xffffu && (((unsigned long long)(0xffffu - f.lf_cnt()[li]) << 32) | (unsigned long long)(f.lf_I()[li] + 1u)) == top)
+        f.lf_cnt()[li] = 0xffffu;
     __syncthreads();
     if (tid == 0) s_amax = 0ull;
     __syncthreads();
   }
   // flags (the key array is dead from here on)
-  uint32_t *flag = f.keys;
+  uint32_t *flag = f.keys();
   for (int i = tid; i < n; i += kQtThreads) flag[i] = 0u;
   __syncthreads();
   for (int li = tid; li < nleaf; li += kQtThreads)
-    if (f.lf_cnt[li] != 0xffffu && (int)f.lf_best[li] < n) flag[f.lf_best[li]] = 1u;
+    if (f.lf_cnt()[li] != 0xffffu && (int)f.lf_best()[li] < n) flag[f.lf_best()[li]] = 1u;
   __syncthreads();
+  tick(7);
   return true;
 }
 
@@ -1731,7 +1887,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   uint32_t *sel_out = p.sel + (size_t)img * p.sel_entries + L.sel_off;
 
   // ---- Phase A: per-cell offsets (exclusive scan of the cell counts) and the total number of corners on the level
-  int *cell_off = (int *)(smem + qt_align16((size_t)p.qt_node_cap * kNodeBytes));
+  int *cell_off = (int *)(smem + qt_pool_bytes(p.qt_node_cap));
   const int per_c = (ncell + kQtThreads - 1) / kQtThreads;
   const int c0i = min(tid * per_c, ncell), c1i = min(c0i + per_c, ncell);
   int mysum = 0;
@@ -1764,7 +1920,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
     q.np.prev = q.np.next + node_cap;
     q.np.free_ids = q.np.prev + node_cap;
     q.np.state = (uint8_t *)(q.np.free_ids + node_cap);
-    w = smem + qt_align16((size_t)node_cap * kNodeBytes) + qt_align16((size_t)p.qt_cell_cap * sizeof(int));
+    w = smem + qt_pool_bytes(node_cap) + qt_align16((size_t)p.qt_cell_cap * sizeof(int));
     q.bhead = (uint16_t *)w;
     q.btail = q.bhead + kQtBuckets;
     w += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
@@ -1810,34 +1966,11 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
 
   // ---- fast path (see qt_fast_path): the usual case -- keys decide everything -- needs no sequential loop at all
   bool done = false;
-  if (p.qt_fast && use_keys && K >= 1 && K <= kQtMaxBinStrips && need >= 2 && in_smem)
+  if (p.qt_fast && use_keys && K >= 1 && K <= kQtMaxBinStrips && need >= 2 && n < p.qt_smem_cap)
   {
-    gather(true);
+    gather(false);
     __syncthreads();
-    QtFast f;
-    const size_t nc = (size_t)node_cap;
-    f.keys = keys;
-    f.ord = ia16;
-    f.lvd = (uint8_t *)ib16;
-    f.hist = (uint16_t *)(lists + qt_align16((size_t)p.qt_smem_cap * 8));
-    f.hash = (uint32_t *)((uint8_t *)f.hist + qt_align16((size_t)8 * 128 * sizeof(uint16_t)));
-    f.hash_mask = (uint32_t)fp_hash_size(node_cap) - 1u;
-    f.D = (int *)q.bhead;
-    f.bin_start = s_bin_start;
-    f.lf_I = (uint32_t *)smem;
-    f.s_pos = (uint16_t *)(smem + 4 * nc);
-    f.s_cnt = f.s_pos + nc;
-    f.s_par = f.s_cnt + nc;
-    f.s_rank = f.s_par + nc;
-    f.lf_best = f.s_rank + nc;
-    f.lf_cnt = f.lf_best + nc;
-    f.s_dc = (uint8_t *)(f.lf_cnt + nc);
-    f.s_pop = f.s_dc + nc;
-    f.s_delta = (int8_t *)(f.s_pop + nc);
-    f.cap_S = min(node_cap, kFpMaxS);
-    f.m = 0;
-    f.K = K;
-    done = qt_fast_path(f, kp, ib16, n, need, s_warp);
+    done = qt_fast_path(smem, lists, (int *)q.bhead, s_bin_start, p.qt_smem_cap, node_cap, K, kp, n, need, s_warp, p.qt_stats);
   }
   uint32_t *flag = keys; // the key array doubles as the "selected" flag array at the end
   if (tid == 0 && p.qt_stats) atomicAdd(&p.qt_stats[done ? 0 : 1], 1ull);
