@@ -378,8 +378,8 @@ int orbx_debug_level_selected(orbx_ctx *ctx, int image, int level, int32_t *xs, 
 /* How many (image, level) quadtree problems this context solved with the loop-free formulation of Quadtree::split() and how
  * many needed the sequential loop (corners that must be split below the key depth, nodes whose corners all sit on split
  * lines, more than 8 root strips, quota < 2, levels denser than the shared-memory list).  ORBX_QT_FAST=0 forces the loop.
- * phase_cycles (optional, [8]): SM clock cycles the loop-free problems spent per phase, summed over problems (sort | run table |
- * node deltas | stop bucket | records + parents | pop ranks | leaves | surplus + flags). */
+ * phase_cycles (optional, [8]): SM clock cycles the loop-free problems spent per phase, summed over problems (table nodes |
+ * level-by-level descent | stop bucket | responses + pop ranks | leaves | surplus + flags | unused | unused). */
 int orbx_debug_quadtree_stats(orbx_ctx *ctx, int64_t *fast, int64_t *sequential, int64_t *phase_cycles);
 /* Runs ONLY the quadtree kernel (Quadtree::split + nodes2kpoints, src/ORBExtractor.cc:126-192) of image 0 on a caller-
  * supplied corner list for `level` (ROI coordinates, detection order; the other levels get no corners), so that the

@@ -617,20 +617,13 @@ __device__ __forceinline__ int qt_rec_depth(uint2 r) { return (int)((r.y >> 24) 
 __device__ __forceinline__ int qt_rec_buf(uint2 r) { return (int)(r.y >> 31); }
 
 __host__ __device__ inline size_t qt_align16(size_t b) { return (b + 15) & ~(size_t)15; }
-__host__ __device__ inline int fp_hash_size(int node_cap)
-{
-  int h = 64;
-  while (h < 2 * node_cap) h <<= 1;
-  return h;
-}
 
 // shared memory: node pool | bucket heads+tails | big-node list | (smem path) ia, ib (u16), key (u32)
-// node-pool region: the sequential path's node pool; the loop-free path keeps its radix histograms (8 warps x 512 bins, u16)
-// there during the sort and its records / leaves afterwards
+// node-pool region: the sequential path's node pool / the loop-free path's records
+static_assert(kNodeBytes <= 20, "the node-pool region is sized for 20 bytes per node");
 __host__ __device__ inline size_t qt_pool_bytes(int node_cap)
 {
-  const size_t b = qt_align16((size_t)node_cap * kNodeBytes);
-  return b > 8192 ? b : 8192;
+  return qt_align16((size_t)node_cap * 20 + 16); // 19 B per node (sequential path) / 20 B per record (loop-free path)
 }
 
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells)
@@ -640,9 +633,9 @@ size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_leve
   b += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
   b += qt_align16((size_t)big_cap * sizeof(uint16_t));
   b += qt_align16((size_t)list_cap * (2 * sizeof(uint16_t) + sizeof(uint32_t)));
-  // fast path: radix histograms (8 warps x 128 bins, u16) and the (start, depth) -> record hash
-  b += qt_align16((size_t)8 * 128 * sizeof(uint16_t));
-  b += qt_align16((size_t)fp_hash_size(node_cap) * sizeof(uint32_t));
+  // loop-free path: 2 KB of histogram / bucket tables and 8 B per leaf
+  b += 2048;
+  b += qt_align16((size_t)node_cap * 8);
   return b + 64;
 }
 
@@ -1194,183 +1187,30 @@ __device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K3 fast path: Quadtree::split() without the loop.
+// K3 fast path: Quadtree::split() without the priority loop.
 //   A child never holds more corners than its parent, so the multimap's pop sequence is the list of ALL tree nodes ordered
 //   by (count desc, pop position of the parent, child index), cut at the first prefix whose running node count reaches
 //   `need`; unrolled, two nodes of equal count compare by the counts of their ancestors (parent first, +inf for the root),
-//   then by their path.  Once the corners are SORTED by descent key every node is a contiguous run, its count is the run
-//   length and its children are sub-runs -- all known before any pop.  So the whole block computes, with no serial chain:
-//     F1  stable LSD radix sort of the corner indices by key (3 passes of three base-5 digits + 1 pass over the strips)
-//     F2  L[p] = key components shared with the predecessor, vd[p] = depth of the corner's last real node; bin table
-//     F3  every node with >= 2 corners (thread <-> run start): count, number of non-empty children -> histogram of the
-//         node-count deltas by count
-//     F4  the bucket c* in which the loop stops (running node count reaches `need`)
-//     F5  the nodes that can pop (count >= c*) -> records, hash (start, depth) -> record, parent links
-//     F6  pop rank of every record (all pairs, ancestor-count chains) -> how many nodes of bucket c* pop
-//     F7  leaves = children of popped nodes that did not pop; best response per leaf; the surplus beyond `need` (at most 3)
+//   then by their path.  With D[c] = sum over the nodes of c corners of (non-empty children - 1), the loop stops inside the
+//   bucket c* = the largest c whose suffix sum lifts the node count to `need`, and it pops every node above c* plus a prefix of
+//   bucket c* in that order.  So the block builds the tree level by level instead of pop by pop, and only where it can matter:
+//     V1  nodes of depths 0..2 straight from the bin table of the presort (counts of every (strip, d1, d2, d3) prefix)
+//     V2  level-synchronous descent from depth 3: a node is split (a thread partitions its corners by the next key digit)
+//         only if its count reaches the running LOWER BOUND of c* (the crossing computed from the deltas known so far: an
+//         unsplit node is smaller than the bound, so the suffix sums at and above the bound are already exact)
+//     V3  exact c*; pop rank of every record of count >= c* (bucket lists + ancestor-count chains) -> how much of bucket c* pops
+//     V4  leaves = children of popped records that did not pop; best response per leaf; the surplus beyond `need` (at most 3)
 //         leaves from the END of the (count desc, insertion) order
-//   It bails out (returns false, the sequential loop runs instead) exactly where the keys do not decide: a node at the key
-//   depth that would have to be split, a popped node whose corners all sit on split lines (negative delta: the running
-//   count is not monotone), c* >= 256, capacity limits.  scripts/devtests/quadtree_parallel_model.py is the CPU model of
-//   this formulation (checked against the oracle).
+//   It bails out (returns false: the sequential loop runs instead) exactly where the keys do not decide: a node at the key depth
+//   that would have to be split, a popped node whose corners all sit on split lines (negative delta: the running count is not
+//   monotone), c* >= 255, record capacity.  scripts/devtests/quadtree_parallel_model.py is the CPU model of this formulation.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kFpWarps = kQtThreads / 32;
-constexpr uint32_t kFpHashEmpty = 0xffffffffu;
-constexpr uint32_t kFpRoot = 0xffffu;
-constexpr int kFpMaxS = 4095;           // record index bits in a hash entry
-constexpr int kFpKeyDepth = kKeyLevels; // 9
-
-// Views into the CTA's dynamic shared memory, derived from three numbers (a by-value table of pointers would live in local memory):
-//   node-pool region  lf_I u32[nc] | s_pos s_cnt s_par s_rank lf_best lf_cnt u16[nc] | s_dc s_pop s_delta u8[nc]   (19 B per node)
-//   lists region      keys u32[cap] | ord u16[cap] | lvd u8[cap] resp u8[cap] (the second index array of the sort) | hist | hash
-struct QtFast
-{
-  uint8_t *pool;   // node-pool region
-  uint8_t *lists;  // lists region
-  int *D;          // [256] sum of deltas per node count (the bucket heads / tails of the sequential path)
-  int *bin_start;  // [K * 125 + 1]
-  int cap, nc;     // list capacity (qt_smem_cap), node capacity
-  int m, K;
-  uint32_t hmask;  // hash size - 1
-  __device__ __forceinline__ uint32_t *keys() const { return (uint32_t *)lists; }                       // descent key per corner; flag array at the end
-  __device__ __forceinline__ uint16_t *ord() const { return (uint16_t *)(lists + 4 * (size_t)cap); }    // sorted position -> corner
-  __device__ __forceinline__ uint16_t *ib() const { return (uint16_t *)(lists + 6 * (size_t)cap); }     // second index array of the sort
-  __device__ __forceinline__ uint8_t *lvd() const { return lists + 6 * (size_t)cap; }                   // [m + 1] L | vd << 4
-  __device__ __forceinline__ uint8_t *resp() const { return lists + 7 * (size_t)cap; }                  // [m] response by sorted position
-  __device__ __forceinline__ uint16_t *hist() const { return (uint16_t *)(lists + qt_align16(8 * (size_t)cap)); }
-  __device__ __forceinline__ uint32_t *hash() const { return (uint32_t *)(lists + qt_align16(8 * (size_t)cap) + qt_align16((size_t)8 * 128 * sizeof(uint16_t))); }
-  __device__ __forceinline__ uint32_t hash_mask() const { return hmask; }
-  __device__ __forceinline__ int cap_S() const { return min(nc, kFpMaxS); }
-  __device__ __forceinline__ uint32_t *lf_I() const { return (uint32_t *)pool; }
-  __device__ __forceinline__ uint16_t *u16(int k) const { return (uint16_t *)(pool + 4 * (size_t)nc) + (size_t)k * nc; }
-  __device__ __forceinline__ uint16_t *s_pos() const { return u16(0); }
-  __device__ __forceinline__ uint16_t *s_cnt() const { return u16(1); }
-  __device__ __forceinline__ uint16_t *s_par() const { return u16(2); }
-  __device__ __forceinline__ uint16_t *s_rank() const { return u16(3); }
-  __device__ __forceinline__ uint16_t *lf_best() const { return u16(4); }
-  __device__ __forceinline__ uint16_t *lf_cnt() const { return u16(5); }
-  __device__ __forceinline__ uint8_t *s_dc() const { return pool + 16 * (size_t)nc; }
-  __device__ __forceinline__ uint8_t *s_pop() const { return pool + 17 * (size_t)nc; }
-  __device__ __forceinline__ int8_t *s_delta() const { return (int8_t *)(pool + 18 * (size_t)nc); }
-};
-
-__device__ __forceinline__ uint32_t fp_g5(uint32_t d) { return min(d, 4u); }
-__device__ __forceinline__ int fp_bin3(uint32_t key)
-{
-  return (int)((((key >> kKeyStripShift) * 5u + fp_g5((key >> 24) & 7u)) * 5u + fp_g5((key >> 21) & 7u)) * 5u + fp_g5((key >> 18) & 7u));
-}
-__device__ __forceinline__ uint32_t fp_digit(uint32_t key, int d) // d == 0: strip
-{
-  return d == 0 ? key >> kKeyStripShift : (key >> (kKeyStripShift - 3 * d)) & 7u;
-}
-__device__ __forceinline__ int fp_L(const QtFast &f, int p) { return f.lvd()[p] & 15; }
-__device__ __forceinline__ int fp_vd(const QtFast &f, int p) { return f.lvd()[p] >> 4; }
-
-__device__ __forceinline__ void fp_hash_insert(const QtFast &f, int pos, int depth, int idx)
-{
-  const uint32_t k = ((uint32_t)pos << 4) | (uint32_t)depth, e = (k << 12) | (uint32_t)idx;
-  uint32_t h = (k * 2654435761u) & f.hash_mask();
-  while (atomicCAS(&f.hash()[h], kFpHashEmpty, e) != kFpHashEmpty) h = (h + 1) & f.hash_mask();
-}
-__device__ __forceinline__ int fp_hash_find(const QtFast &f, int pos, int depth)
-{
-  const uint32_t k = ((uint32_t)pos << 4) | (uint32_t)depth;
-  uint32_t h = (k * 2654435761u) & f.hash_mask();
-  for (;;)
-  {
-    const uint32_t e = f.hash()[h];
-    if (e == kFpHashEmpty) return -1;
-    if ((e >> 12) == k) return (int)(e & 0xfffu);
-    h = (h + 1) & f.hash_mask();
-  }
-}
-
-// the nodes (>= 2 corners) whose run starts at sorted position p: fn(depth, count, non-empty children or -1 at the key depth)
-template <class Fn> __device__ __forceinline__ void fp_nodes_at(const QtFast &f, int p, Fn fn)
-{
-  const int l0 = fp_L(f, p), l1 = fp_L(f, p + 1);
-  const int dmax = min(min(l1 - 1, fp_vd(f, p)), kFpKeyDepth);
-  if (dmax < l0) return;
-  const int b3 = fp_bin3(f.keys()[f.ord()[p]]);
-  for (int d = l0; d <= dmax; ++d)
-  {
-    int cnt, ne;
-    if (d <= 2)
-    {
-      const int span = d == 0 ? 125 : (d == 1 ? 25 : 5), w = span / 5;
-      const int B = (b3 / span) * span;
-      cnt = f.bin_start[B + span] - p;
-      ne = 0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) ne += f.bin_start[B + (c + 1) * w] > f.bin_start[B + c * w];
-    }
-    else
-    {
-      int q = p + 1, groups = 1;
-      while (q < f.m)
-      {
-        const int l = fp_L(f, q);
-        if (l <= d) break;
-        groups += l == d + 1;
-        ++q;
-      }
-      cnt = q - p;
-      ne = d == kFpKeyDepth ? -1 : groups - (fp_vd(f, q - 1) == d ? 1 : 0);
-    }
-    fn(d, cnt, ne);
-  }
-}
-
-// children of the depth-d node [p, p + cnt) (d == -1: the root, children = strips): fn(digit, start, end) per non-empty child
-template <class Fn> __device__ __forceinline__ void fp_children(const QtFast &f, int p, int cnt, int d, Fn fn)
-{
-  if (d < 0)
-  {
-    for (int s = 0; s < f.K; ++s)
-    {
-      const int a = f.bin_start[s * kQtBinsPerStrip], b = f.bin_start[(s + 1) * kQtBinsPerStrip];
-      if (b > a) fn(s, a, b);
-    }
-  }
-  else if (d <= 2)
-  {
-    const int span = d == 0 ? 125 : (d == 1 ? 25 : 5), w = span / 5;
-    const int B = (fp_bin3(f.keys()[f.ord()[p]]) / span) * span;
-    for (int c = 0; c < 4; ++c)
-    {
-      const int a = f.bin_start[B + c * w], b = f.bin_start[B + (c + 1) * w];
-      if (b > a) fn(c, a, b);
-    }
-  }
-  else
-  {
-    const int end = p + cnt;
-    int g0 = p;
-    for (int q = p + 1; q <= end; ++q)
-      if (q == end || fp_L(f, q) == d + 1)
-      {
-        const uint32_t dg = fp_digit(f.keys()[f.ord()[g0]], d + 1);
-        if (dg != kDigitDrop) fn((int)dg, g0, q);
-        g0 = q;
-      }
-  }
-}
-
-// equal counts: does record u pop before record v?  (ancestor counts, parent first; the root counts as +inf; then the path)
-__device__ __forceinline__ bool fp_chain_before(const QtFast &f, uint32_t u, uint32_t v)
-{
-  uint32_t a = u, b = v;
-  for (;;)
-  {
-    const uint32_t pa = a, pb = b;
-    a = f.s_par()[a];
-    b = f.s_par()[b];
-    if (a == b) return (f.s_dc()[pa] & 15u) < (f.s_dc()[pb] & 15u);
-    const uint32_t ca = a == kFpRoot ? 0x10000u : f.s_cnt()[a], cb = b == kFpRoot ? 0x10000u : f.s_cnt()[b];
-    if (ca != cb) return ca > cb;
-    if (a == kFpRoot || b == kFpRoot) return a == kFpRoot; // unreachable (counts differ), keeps the loop finite
-  }
-}
+constexpr int kFpSmall = 8;        // node counts below this are accumulated in per-warp counters (the hot histogram bins)
+constexpr int kFpRecBytes = 20;    // shared memory per record
+static_assert(kFpRecBytes == 20, "qt_pool_bytes");
+constexpr uint32_t kFpNone = 0xffffu;
+constexpr uint8_t kFpActive = 1, kFpPopped = 2, kFpKidsBuf = 0x80;
 
 // warp-aggregated slot allocation: the lanes that execute this together take consecutive indices with ONE shared-memory atomic
 __device__ __forceinline__ int fp_alloc(int *counter)
@@ -1383,22 +1223,61 @@ __device__ __forceinline__ int fp_alloc(int *counter)
   return base + __popc(act & ((1u << lane) - 1u));
 }
 
-constexpr int kFpSortBins = 512;  // radix bins per pass (three raw 3-bit digits); per-warp histograms of u16 live in the node-pool region
-constexpr int kFpSmall = 8;       // node counts below this are accumulated in per-warp counters (they are the hot histogram bins)
-
-__device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *D, int *bin_start, int cap, int nc, int K_, const uint32_t *kp, int n, int need,
-                                          int *s_warp, unsigned long long *stats)
+// views into the CTA's shared memory (derived from a few numbers; a by-value table of pointers would live in local memory)
+struct QtFast
 {
-  __shared__ int s_m, s_live0, s_dbig, s_neg, s_deep, s_cstar, s_before, s_nS, s_k, s_nleaf, s_mode, s_first;
+  uint8_t *pool;   // records: u16 lo cnt par rank t0 t1 t2 t3 [nc] | u8 kidpop meta delta state [nc]
+  uint8_t *lists;  // keys u32[cap] | ia u16[cap] | ib u16[cap]
+  int *scr;        // 2 KB: D[256] during the descent, start[256] + cursor[256] during the ranking
+  uint8_t *lf;     // leaves: I u32[nc] | best u16[nc] | cnt u16[nc]   (the ranking keeps its bucket list and deltas here before)
+  int cap, nc;
+  __device__ __forceinline__ uint32_t *keys() const { return (uint32_t *)lists; }
+  __device__ __forceinline__ uint8_t *resp() const { return lists; } // responses by corner, once the keys are dead
+  __device__ __forceinline__ uint16_t *arr(int buf) const { return (uint16_t *)(lists + (4 + 2 * (size_t)buf) * cap); }
+  __device__ __forceinline__ uint16_t *u16(int k) const { return (uint16_t *)pool + (size_t)k * nc; }
+  __device__ __forceinline__ uint16_t *r_lo() const { return u16(0); }
+  __device__ __forceinline__ uint16_t *r_cnt() const { return u16(1); }
+  __device__ __forceinline__ uint16_t *r_par() const { return u16(2); }
+  __device__ __forceinline__ uint16_t *r_rank() const { return u16(3); }
+  __device__ __forceinline__ uint16_t *r_t(int k) const { return u16(4 + k); }
+  __device__ __forceinline__ uint8_t *r_kidpop() const { return pool + 16 * (size_t)nc; }
+  __device__ __forceinline__ uint8_t *r_meta() const { return pool + 17 * (size_t)nc; } // depth << 4 | child << 1 | buffer of its corners
+  __device__ __forceinline__ int8_t *r_delta() const { return (int8_t *)(pool + 18 * (size_t)nc); }
+  __device__ __forceinline__ uint8_t *r_state() const { return pool + 19 * (size_t)nc; }
+  __device__ __forceinline__ uint32_t *lf_I() const { return (uint32_t *)lf; }
+  __device__ __forceinline__ uint16_t *lf_best() const { return (uint16_t *)(lf + 4 * (size_t)nc); }
+  __device__ __forceinline__ uint16_t *lf_cnt() const { return (uint16_t *)(lf + 6 * (size_t)nc); }
+};
+
+// equal counts: does record u pop before record v?  (ancestor counts, parent first; the root -- record 0 -- counts as +inf;
+// then the child index below the first common ancestor)
+__device__ __forceinline__ bool fp_chain_before(const QtFast &f, uint32_t u, uint32_t v)
+{
+  uint32_t a = u, b = v;
+  for (;;)
+  {
+    const uint32_t pa = a, pb = b;
+    a = f.r_par()[a];
+    b = f.r_par()[b];
+    if (a == b) return ((f.r_meta()[pa] >> 1) & 7u) < ((f.r_meta()[pb] >> 1) & 7u);
+    const uint32_t ca = a == 0 ? 0x10000u : f.r_cnt()[a], cb = b == 0 ? 0x10000u : f.r_cnt()[b];
+    if (ca != cb) return ca > cb;
+  }
+}
+
+__device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *scr, uint8_t *lf, const int *bin_start, int cap, int nc, int K,
+                                          const uint32_t *kp, int n, int need, int *s_warp, unsigned long long *stats)
+{
+  __shared__ int s_live0, s_dbig, s_neg, s_deep, s_cstar, s_before, s_first, s_nrec, s_f1, s_k, s_nleaf, s_over;
   __shared__ int s_small[kFpWarps][kFpSmall];
+  __shared__ uint16_t s_tab[kQtMaxBinStrips * 31]; // record of every depth 0..2 prefix (kFpNone: no node)
   __shared__ unsigned long long s_amax;
   QtFast f;
-  f.pool = pool, f.lists = lists, f.D = D, f.bin_start = bin_start, f.cap = cap, f.nc = nc, f.m = 0, f.K = K_;
-  f.hmask = (uint32_t)fp_hash_size(nc) - 1u;
+  f.pool = pool, f.lists = lists, f.scr = scr, f.lf = lf, f.cap = cap, f.nc = nc;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
-  const int K = f.K;
+  const unsigned FULL = 0xffffffffu;
   enum { kRun = 0, kEmpty = 1, kNoPop = 2, kBail = 3 };
+  int *D = f.scr;
   long long t_prev = clock64();
   auto tick = [&](int phase) {
     if (tid == 0 && stats)
@@ -1408,327 +1287,265 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *D,
       t_prev = t;
     }
   };
-
-  // ---- F1: stable LSD radix sort of the corner indices by key: three raw digits (9 bits) per pass, low digits first; the last
-  // pass folds the strip in (K <= 4: strip * 125 + the three digits in base 5) or is followed by a pass over the strips.  Every
-  // warp owns a contiguous segment of the input; equal digits inside a 32-element step are ranked with __match_any_sync, so
-  // there are no atomics and every pass is stable.  The first pass reads the identity order, so no index array is initialised.
-  uint16_t *sorted;
-  {
-    uint16_t *hist = (uint16_t *)pool; // [kFpWarps][kFpSortBins], dead before the records are built
-    const int npass = K <= 4 ? 3 : 4;
-    uint16_t *bufA = npass == 3 ? f.ord() : f.ib(), *bufB = npass == 3 ? f.ib() : f.ord(); // the last pass lands in f.ord()
-    const uint16_t *src = nullptr;
-    uint16_t *dst = bufA;
-    const int seg = (n + kFpWarps - 1) / kFpWarps, lo = min(wid * seg, n), hi = min(lo + seg, n);
-    const uint32_t *keys = f.keys();
-    for (int pass = 0; pass < npass; ++pass)
-    {
-      auto digit = [&](uint32_t key) -> uint32_t {
-        if (pass < 2) return (key >> (9 * pass)) & 511u;
-        if (npass == 4) return pass == 2 ? (key >> 18) & 511u : ((key >> kKeyStripShift) == kKeyNoStrip ? (uint32_t)K : key >> kKeyStripShift);
-        return (key >> kKeyStripShift) == kKeyNoStrip ? (uint32_t)(K * kQtBinsPerStrip) : (uint32_t)fp_bin3(key);
-      };
-      {
-        uint32_t *h32 = (uint32_t *)hist;
-        for (int i = tid; i < kFpWarps * kFpSortBins / 2; i += kQtThreads) h32[i] = 0u;
-      }
-      __syncthreads();
-      uint16_t *myh = hist + wid * kFpSortBins;
-      for (int i0 = lo; i0 < hi; i0 += 32)
-      {
-        const int i = i0 + lane;
-        uint32_t dg = 0xffffu;
-        if (i < hi) dg = digit(keys[src ? src[i] : i]);
-        const unsigned peers = __match_any_sync(FULL, dg);
-        if (i < hi && lane == __ffs(peers) - 1) myh[dg] += (uint16_t)__popc(peers);
-        __syncwarp();
-      }
-      __syncthreads();
-      {
-        // bins 2 tid and 2 tid + 1: totals over the warps, block-wide exclusive scan, per-warp bases
-        uint32_t c0[kFpWarps], c1[kFpWarps];
-        int t0 = 0, t1 = 0;
-#pragma unroll
-        for (int w = 0; w < kFpWarps; ++w)
-        {
-          const uint32_t pr = *(const uint32_t *)(hist + w * kFpSortBins + 2 * tid);
-          c0[w] = pr & 0xffffu, c1[w] = pr >> 16;
-          t0 += (int)c0[w], t1 += (int)c1[w];
-        }
-        int total;
-        int run0 = block_exclusive_scan<kQtThreads>(t0 + t1, total, s_warp);
-        int run1 = run0 + t0;
-        const int last_bin = npass == 4 ? K : K * kQtBinsPerStrip; // "in no strip": sorts behind everything
-        if (pass == npass - 1)
-        {
-          if (2 * tid == last_bin) s_m = run0;
-          if (2 * tid + 1 == last_bin) s_m = run1;
-        }
-#pragma unroll
-        for (int w = 0; w < kFpWarps; ++w)
-        {
-          *(uint32_t *)(hist + w * kFpSortBins + 2 * tid) = (uint32_t)run0 | ((uint32_t)run1 << 16);
-          run0 += (int)c0[w], run1 += (int)c1[w];
-        }
-      }
-      __syncthreads();
-      for (int i0 = lo; i0 < hi; i0 += 32)
-      {
-        const int i = i0 + lane;
-        uint32_t idx = 0, dg = 0xffffu;
-        if (i < hi)
-        {
-          idx = src ? src[i] : (uint32_t)i;
-          dg = digit(keys[idx]);
-        }
-        const unsigned peers = __match_any_sync(FULL, dg);
-        uint32_t b = 0;
-        if (i < hi)
-        {
-          b = myh[dg];
-          dst[b + __popc(peers & lt_mask)] = (uint16_t)idx;
-        }
-        __syncwarp();
-        if (i < hi && lane == __ffs(peers) - 1) myh[dg] = (uint16_t)(b + __popc(peers));
-        __syncwarp();
-      }
-      __syncthreads();
-      src = dst;
-      dst = dst == bufA ? bufB : bufA;
-    }
-    sorted = f.ord();
-  }
-  const int m = s_m;
-  f.m = m;
-  tick(0);
-
-  // ---- F2: L / vd bytes, responses by sorted position, bin table (start of every (strip, d1, d2, d3) bin), zeroed accumulators
-  {
-    const uint32_t *keys = f.keys();
-    uint8_t *lvd = f.lvd(), *resp = f.resp();
-    for (int p0 = tid; p0 <= m; p0 += 4 * kQtThreads)
-    {
-      uint32_t r[4], lv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-      {
-        const int p = p0 + u * kQtThreads;
-        r[u] = 0, lv[u] = 0;
-        if (p < m)
-        {
-          const uint32_t idx = sorted[p];
-          r[u] = kp[idx]; // global (L2): the four loads of a batch are in flight together
-          const uint32_t key = keys[idx];
-          const uint32_t t7 = key & (key >> 1) & (key >> 2) & 0x01249249u; // bit 0 of every digit that equals 7
-          const uint32_t v = t7 ? (uint32_t)((27 - (31 - __clz((int)t7))) / 3 - 1) : (uint32_t)kFpKeyDepth;
-          uint32_t l = 0;
-          if (p > 0)
-          {
-            const uint32_t x = key ^ keys[sorted[p - 1]];
-            if (x == 0)
-              l = kFpKeyDepth + 1;
-            else
-            {
-              const int hb = 31 - __clz((int)x);
-              l = hb >= kKeyStripShift ? 0u : (uint32_t)((29 - hb) / 3);
-            }
-          }
-          lv[u] = l | (v << 4);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-      {
-        const int p = p0 + u * kQtThreads;
-        if (p <= m) lvd[p] = (uint8_t)lv[u];
-        if (p < m) resp[p] = (uint8_t)(r[u] >> 24);
-      }
-    }
-  }
-  for (int i = tid; i < 256; i += kQtThreads) f.D[i] = 0;
-  for (int i = tid; i <= (int)f.hash_mask(); i += kQtThreads) f.hash()[i] = kFpHashEmpty;
-  if (tid < kFpWarps * kFpSmall) (&s_small[0][0])[tid] = 0;
-  if (tid == 0)
-  {
-    s_live0 = 0, s_dbig = 0, s_neg = 0, s_deep = 0, s_cstar = 0, s_before = 0, s_nS = 0, s_k = 0, s_nleaf = 0, s_mode = kRun, s_first = 0x7fffffff;
-    s_amax = 0ull;
-  }
-  __syncthreads();
-  {
-    const int nb = K * kQtBinsPerStrip;
-    if (m == 0)
-    {
-      for (int b = tid; b <= nb; b += kQtThreads) f.bin_start[b] = 0;
-    }
+  auto add_delta = [&](int cnt, int delta) {
+    if (delta < 0) atomicMax(&s_neg, cnt);
+    if (delta == 0) return;
+    if (cnt < kFpSmall)
+      atomicAdd(&s_small[wid][cnt], delta);
+    else if (cnt < 256)
+      atomicAdd(&D[cnt], delta);
     else
-    {
-      for (int p = tid; p < m; p += kQtThreads)
-      {
-        if (p > 0 && fp_L(f, p) > 3) continue; // same bin as the predecessor
-        const int b = fp_bin3(f.keys()[sorted[p]]);
-        const int pb = p > 0 ? fp_bin3(f.keys()[sorted[p - 1]]) : -1;
-        for (int bb = pb + 1; bb <= b; ++bb) f.bin_start[bb] = p;
-      }
-      const int last = fp_bin3(f.keys()[sorted[m - 1]]);
-      for (int b = last + 1 + tid; b <= nb; b += kQtThreads) f.bin_start[b] = m;
-    }
-  }
-  __syncthreads();
-  tick(1);
-
-  // ---- F3: deltas of all nodes by count (counts below kFpSmall -- most nodes -- in per-warp counters: no hot shared address)
-  if (tid < K) atomicAdd(&s_live0, f.bin_start[(tid + 1) * kQtBinsPerStrip] > f.bin_start[tid * kQtBinsPerStrip] ? 1 : 0);
-  for (int p = tid; p < m; p += kQtThreads)
-    fp_nodes_at(f, p, [&](int d, int cnt, int ne) {
-      if (ne < 0)
-        atomicMax(&s_deep, cnt);
-      else
-      {
-        const int delta = ne - 1;
-        if (delta < 0) atomicMax(&s_neg, cnt);
-        if (cnt < kFpSmall)
-        {
-          if (delta) atomicAdd(&s_small[wid][cnt], delta);
-        }
-        else if (cnt < 256)
-          atomicAdd(&f.D[cnt], delta);
-        else
-          atomicAdd(&s_dbig, delta);
-      }
-    });
-  __syncthreads();
-  tick(2);
-
-  // ---- F4: where does the loop stop?  thread t <-> count c = 255 - t: after(c) = node count once every node of >= c corners popped
-  {
+      atomicAdd(&s_dbig, delta);
+  };
+  // The crossing of the node count over `need` in the deltas known so far: thread t <-> count c = 255 - t,
+  // after(c) = live0 + sum of the deltas of all nodes of >= c corners.  s_first = 255 - c* (0x7fffffff: none), s_before = after(c* + 1).
+  auto find_cross = [&]() {
     const int c = 255 - tid;
     int d = 0;
     if (c >= kFpSmall)
-      d = f.D[c];
+      d = D[c];
     else if (c >= 2)
       for (int w = 0; w < kFpWarps; ++w) d += s_small[w][c];
-    int inc = d; // inclusive scan over t
+    int inc = d;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
       const int t = __shfl_up_sync(FULL, inc, o);
       if (lane >= o) inc += t;
     }
+    if (tid == 0) s_first = 0x7fffffff;
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     int base = 0;
     for (int w = 0; w < wid; ++w) base += s_warp[w];
-    const int live0 = s_live0;
-    const int after = live0 + s_dbig + base + inc;
-    const bool reached = c >= 2 && after >= need;
-    if (reached) atomicMin(&s_first, tid);
+    const int after = s_live0 + s_dbig + base + inc;
+    if (c >= 2 && after >= need) atomicMin(&s_first, tid);
     __syncthreads();
     if (tid == s_first)
     {
       s_cstar = c;
       s_before = after - d;
     }
+    if (tid == 0 && s_first == 0x7fffffff) s_cstar = 0;
     __syncthreads();
-    if (tid == 0)
+  };
+
+  // ---- V0: accumulators, the root record, the strips
+  for (int i = tid; i < 256; i += kQtThreads) D[i] = 0;
+  if (tid < kFpWarps * kFpSmall) (&s_small[0][0])[tid] = 0;
+  for (int i = tid; i < kQtMaxBinStrips * 31; i += kQtThreads) s_tab[i] = (uint16_t)kFpNone;
+  if (tid == 0)
+  {
+    s_live0 = 0, s_dbig = 0, s_neg = 0, s_deep = 0, s_cstar = 0, s_before = 0, s_nrec = 1, s_k = 0, s_nleaf = 0, s_over = 0;
+    s_amax = 0ull;
+    f.r_cnt()[0] = 0xffffu;
+    f.r_par()[0] = (uint16_t)kFpNone;
+    f.r_meta()[0] = 0;
+    f.r_state()[0] = kFpActive | kFpPopped; // the loop always pops the root first (need >= 2)
+    f.r_rank()[0] = 0;
+  }
+  for (int i = tid; i < nc; i += kQtThreads) f.r_kidpop()[i] = 0;
+  __syncthreads();
+  if (tid < K) atomicAdd(&s_live0, bin_start[(tid + 1) * kQtBinsPerStrip] > bin_start[tid * kQtBinsPerStrip] ? 1 : 0);
+  __syncthreads();
+  const int live0 = s_live0;
+  int mode = live0 == 0 ? kEmpty : (live0 >= need ? kNoPop : kRun);
+  int cstar = 0;
+
+  if (mode == kRun)
+  {
+    // ---- V1: the nodes of depths 0..2 from the bin table (thread <-> prefix; depth by depth: a record links to its parent's)
+    int tab0 = 0, pow5 = 1; // first table slot of the depth, 5^depth
+    for (int d = 0; d <= 2; ++d)
+    {
+      const int span = d == 0 ? 125 : (d == 1 ? 25 : 5), w = span / 5;
+      for (int j = tid; j < K * pow5; j += kQtThreads)
+      {
+        const int g_last = j % 5, g_prev = (j / 5) % 5; // a prefix through a "split line" digit (4) is not a node
+        if (d >= 1 && g_last == 4) continue;
+        if (d >= 2 && g_prev == 4) continue;
+        const int B = j * span, lo = bin_start[B], cnt = bin_start[B + span] - lo;
+        if (cnt < 2) continue;
+        int t[4], ne = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          t[k] = bin_start[B + (k + 1) * w] - bin_start[B + k * w];
+          ne += t[k] > 0;
+        }
+        const int idx = fp_alloc(&s_nrec);
+        if (idx >= nc)
+        {
+          s_over = 1;
+          continue;
+        }
+        f.r_lo()[idx] = (uint16_t)lo;
+        f.r_cnt()[idx] = (uint16_t)cnt;
+        f.r_par()[idx] = d == 0 ? (uint16_t)0 : s_tab[tab0 - pow5 / 5 * K + j / 5];
+        f.r_meta()[idx] = (uint8_t)((d << 4) | ((d == 0 ? j : g_last) << 1));
+        f.r_delta()[idx] = (int8_t)(ne - 1);
+        f.r_state()[idx] = kFpActive; // children lie in the same array (bins are contiguous)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f.r_t(k)[idx] = (uint16_t)t[k];
+        s_tab[tab0 + j] = (uint16_t)idx;
+        add_delta(cnt, ne - 1);
+      }
+      __syncthreads();
+      tab0 += K * pow5;
+      pow5 *= 5;
+    }
+    tick(0);
+
+    // ---- V2: descent from depth 3, level by level; a node is split only if its count reaches the running lower bound of c*
+    int f0 = s_nrec; // first depth-3 record (every thread reads it before anybody can get past the barriers of find_cross)
+    find_cross();
+    int bound = max(2, s_cstar); // no crossing yet: every node of >= 2 corners may matter
+    {
+      // depth-3 nodes = bins; parent = the depth-2 prefix j / 5 (slot K + 5 K + j / 5)
+      for (int j = tid; j < K * kQtBinsPerStrip; j += kQtThreads)
+      {
+        if (j % 5 == 4 || (j / 5) % 5 == 4 || (j / 25) % 5 == 4) continue;
+        const int lo = bin_start[j], cnt = bin_start[j + 1] - lo;
+        if (cnt < bound) continue;
+        const int idx = fp_alloc(&s_nrec);
+        if (idx >= nc)
+        {
+          s_over = 1;
+          continue;
+        }
+        f.r_lo()[idx] = (uint16_t)lo;
+        f.r_cnt()[idx] = (uint16_t)cnt;
+        f.r_par()[idx] = s_tab[6 * K + j / 5];
+        f.r_meta()[idx] = (uint8_t)((3 << 4) | ((j % 5) << 1));
+        f.r_state()[idx] = 0;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_f1 = s_nrec;
+    __syncthreads();
+    for (int level = 3; level <= 8; ++level)
+    {
+      const int f1 = min(s_f1, nc);
+      if (f1 <= f0 || s_over) break; // uniform
+      if (level > 3)
+      {
+        find_cross();
+        bound = max(bound, max(2, s_cstar));
+      }
+      const uint32_t *keys = f.keys();
+      const int shift = kKeyStripShift - 3 * (level + 1);
+      for (int v = f0 + tid; v < f1; v += kQtThreads)
+      {
+        const int cnt = f.r_cnt()[v];
+        if (cnt < bound) continue; // stays unsplit: it can never pop
+        const int lo = f.r_lo()[v], buf = f.r_meta()[v] & 1;
+        const uint16_t *src = f.arr(buf) + lo;
+        uint16_t *dst = f.arr(buf ^ 1);
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        for (int i = 0; i < cnt; ++i)
+        {
+          const uint32_t dg = (keys[src[i]] >> shift) & 7u;
+          c0 += dg == 0, c1 += dg == 1, c2 += dg == 2, c3 += dg == 3;
+        }
+        int o0 = lo, o1 = o0 + c0, o2 = o1 + c1, o3 = o2 + c2;
+        for (int i = 0; i < cnt; ++i)
+        {
+          const uint32_t idx = src[i], dg = (keys[idx] >> shift) & 7u;
+          if (dg == 0) dst[o0++] = (uint16_t)idx;
+          if (dg == 1) dst[o1++] = (uint16_t)idx;
+          if (dg == 2) dst[o2++] = (uint16_t)idx;
+          if (dg == 3) dst[o3++] = (uint16_t)idx;
+        }
+        const int t[4] = {c0, c1, c2, c3};
+        const int ne = (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
+        f.r_t(0)[v] = (uint16_t)c0, f.r_t(1)[v] = (uint16_t)c1, f.r_t(2)[v] = (uint16_t)c2, f.r_t(3)[v] = (uint16_t)c3;
+        f.r_delta()[v] = (int8_t)(ne - 1);
+        f.r_state()[v] = (uint8_t)(kFpActive | ((buf ^ 1) ? kFpKidsBuf : 0));
+        add_delta(cnt, ne - 1);
+        int base = lo;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+          const int tk = t[k];
+          if (tk >= 2)
+          {
+            if (level + 1 > 8)
+              atomicMax(&s_deep, tk); // a node AT the key depth with >= 2 corners: the keys cannot split it
+            else if (tk >= bound)
+            {
+              const int idx = fp_alloc(&s_nrec);
+              if (idx >= nc)
+                s_over = 1;
+              else
+              {
+                f.r_lo()[idx] = (uint16_t)base;
+                f.r_cnt()[idx] = (uint16_t)tk;
+                f.r_par()[idx] = (uint16_t)v;
+                f.r_meta()[idx] = (uint8_t)(((level + 1) << 4) | (k << 1) | (buf ^ 1));
+                f.r_state()[idx] = 0;
+              }
+            }
+          }
+          base += tk;
+        }
+      }
+      __syncthreads();
+      f0 = f1;
+      if (tid == 0) s_f1 = s_nrec;
+      __syncthreads();
+    }
+    if (s_over || s_nrec > nc) return false; // uniform: more records than the pool holds
+    tick(1);
+
+    // ---- V3: exact c*
+    find_cross();
+    cstar = s_cstar;
     {
       const int hard = max(s_neg, s_deep);
-      int mode = kRun;
-      if (live0 == 0)
-        mode = kEmpty;
-      else if (live0 >= need)
-        mode = kNoPop;
-      else if (live0 + s_dbig >= need)
+      if (live0 + s_dbig >= need)
         mode = kBail; // the loop stops among the nodes of 256+ corners
-      else if (s_first == 0x7fffffff)
+      else if (cstar == 0)
         mode = hard >= 2 ? kBail : kEmpty; // starved: the multimap drains (src/ORBExtractor.cc:151), 0 keypoints
-      else if (s_cstar <= hard || s_cstar >= 255)
-        mode = kBail; // (bucket 255 of the rank pass also holds the larger nodes)
-      if (mode != kRun) s_cstar = 0;
-      s_mode = mode;
+      else if (cstar <= hard || cstar >= 255 || cstar < bound)
+        mode = kBail;
     }
-    __syncthreads();
+    if (mode == kBail) return false; // uniform (shared values)
+    tick(2);
   }
-  if (s_mode == kBail) return false;
-  const int cstar = s_cstar;
-  tick(3);
 
-  if (s_mode == kRun)
+  // responses by corner index over the (dead) keys: the leaf scans below stay in shared memory
+  __syncthreads();
   {
-    // ---- F5: records of the nodes that can pop (count >= c*), hash (start, depth) -> record, parent links
-    for (int p = tid; p < m; p += kQtThreads)
+    uint8_t *resp = f.resp();
+    for (int i0 = tid; i0 < n; i0 += 4 * kQtThreads)
     {
-      // the nodes below depth 3 that start here lie inside one (strip, d1, d2, d3) bin: nothing to record if the bin is too small
-      const int l0 = fp_L(f, p);
-      if (l0 >= 3)
-      {
-        const int b3 = fp_bin3(f.keys()[sorted[p]]);
-        if (f.bin_start[b3 + 1] - f.bin_start[b3] < cstar) continue;
-      }
-      fp_nodes_at(f, p, [&](int d, int cnt, int ne) {
-        if (cnt < cstar) return;
-        const int idx = fp_alloc(&s_nS);
-        if (idx >= f.cap_S()) return;
-        f.s_pos()[idx] = (uint16_t)p;
-        f.s_cnt()[idx] = (uint16_t)cnt;
-        f.s_dc()[idx] = (uint8_t)((d << 4) | (int)fp_digit(f.keys()[sorted[p]], d));
-        f.s_delta()[idx] = (int8_t)(ne - 1);
-        f.s_pop()[idx] = 0;
-        fp_hash_insert(f, p, d, idx);
-      });
+      uint32_t r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = i0 + u * kQtThreads < n ? kp[i0 + u * kQtThreads] : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * kQtThreads < n) resp[i0 + u * kQtThreads] = (uint8_t)(r[u] >> 24);
     }
-    __syncthreads();
-    const int nS = s_nS;
-    if (nS > f.cap_S()) return false; // uniform
-    // bucket histogram of the records (H aliases D, which is dead now): H[b], b = min(count, 255)
-    int *H = f.D;
-    for (int i = tid; i < 256; i += kQtThreads) H[i] = 0;
-    __syncthreads();
-    for (int v = tid; v < nS; v += kQtThreads)
-    {
-      atomicAdd(&H[min((int)f.s_cnt()[v], 255)], 1);
-      // parent link
-      const int d = f.s_dc()[v] >> 4, p = f.s_pos()[v];
-      uint32_t par = kFpRoot;
-      if (d > 0)
-      {
-        int pp = p;
-        if (d - 1 < fp_L(f, p))
-        {
-          // the parent's run starts earlier: lower bound of the (strip, d1 .. d(d-1)) prefix
-          const int sh = kKeyStripShift - 3 * (d - 1);
-          const uint32_t want = f.keys()[sorted[p]] >> sh;
-          int lo = 0, hi = p;
-          if (d - 1 >= 3) lo = f.bin_start[fp_bin3(f.keys()[sorted[p]])]; // ... inside the depth-3 bin
-          while (lo < hi)
-          {
-            const int mid = (lo + hi) >> 1;
-            if ((f.keys()[sorted[mid]] >> sh) < want)
-              lo = mid + 1;
-            else
-              hi = mid;
-          }
-          pp = lo;
-        }
-        const int q = fp_hash_find(f, pp, d - 1);
-        par = q < 0 ? 0xfffeu : (uint32_t)q;
-      }
-      f.s_par()[v] = (uint16_t)par;
-      if (par == 0xfffeu) s_mode = kBail; // cannot happen: a parent holds at least as many corners as its child
-    }
-    __syncthreads();
-    if (s_mode == kBail) return false;
-    tick(4);
+  }
+  const int nrec = mode == kRun ? s_nrec : 1;
 
-    // ---- F6: pop rank of every record = records in higher buckets + position inside its own bucket (ancestor-count chains).
-    // start[b] = records in buckets above b (thread t <-> bucket 255 - t); list = the records grouped by bucket.
-    int *start = (int *)f.hist();                 // [256]
-    int *cursor = start + 256;                    // [256]   (the radix-histogram region: 2 KB)
-    uint16_t *list = (uint16_t *)f.lf_I();        // [nS]    (the leaf arrays are not in use yet)
-    uint16_t *dlt = f.lf_best();                  // [H[c*]] deltas of bucket c* in pop order
+  if (mode == kRun)
+  {
+    // ---- V3b: pop rank of every record of >= c* corners = records in higher buckets + position inside its own bucket.
+    // start[b] = records in buckets above b (thread t <-> bucket 255 - t); list = those records grouped by bucket.
+    int *start = f.scr, *cursor = f.scr + 256; // D is dead
+    uint16_t *list = (uint16_t *)f.lf;          // [<= nrec]
+    uint16_t *dlt = list + nc;                  // [bucket c*] deltas in pop order
+    __syncthreads();
+    for (int i = tid; i < 512; i += kQtThreads) f.scr[i] = 0;
+    __syncthreads();
+    auto in_S = [&](int v) { return (f.r_state()[v] & kFpActive) && (int)f.r_cnt()[v] >= cstar; };
+    for (int v = 1 + tid; v < nrec; v += kQtThreads)
+      if (in_S(v)) atomicAdd(&cursor[min((int)f.r_cnt()[v], 255)], 1); // cursor = bucket sizes for now
+    __syncthreads();
     {
       const int b = 255 - tid;
-      const int h = H[b];
+      const int h = cursor[b];
       int inc = h;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1)
@@ -1741,27 +1558,30 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *D,
       int base = 0;
       for (int w = 0; w < wid; ++w) base += s_warp[w];
       start[b] = base + inc - h;
+      __syncthreads();
       cursor[b] = base + inc - h;
     }
     __syncthreads();
-    for (int v = tid; v < nS; v += kQtThreads) list[atomicAdd(&cursor[min((int)f.s_cnt()[v], 255)], 1)] = (uint16_t)v;
+    for (int v = 1 + tid; v < nrec; v += kQtThreads)
+      if (in_S(v)) list[atomicAdd(&cursor[min((int)f.r_cnt()[v], 255)], 1)] = (uint16_t)v;
     __syncthreads();
-    const int R0 = start[cstar], mb = H[cstar];
-    for (int v = tid; v < nS; v += kQtThreads)
+    const int R0 = start[cstar], mb = cursor[cstar] - R0; // cursor[b] = end of bucket b now
+    for (int v = 1 + tid; v < nrec; v += kQtThreads)
     {
-      const uint32_t cv = f.s_cnt()[v];
+      if (!in_S(v)) continue;
+      const uint32_t cv = f.r_cnt()[v];
       const int b = min((int)cv, 255);
-      const int j0 = start[b], j1 = j0 + H[b];
+      const int j0 = start[b], j1 = cursor[b];
       int r = j0;
       for (int j = j0; j < j1; ++j)
       {
         const uint32_t u = list[j];
         if (u == (uint32_t)v) continue;
-        const uint32_t cu = f.s_cnt()[u]; // differs only inside the 255+ bucket
+        const uint32_t cu = f.r_cnt()[u]; // differs only inside the 255+ bucket
         r += cu != cv ? (cu > cv) : fp_chain_before(f, u, (uint32_t)v);
       }
-      f.s_rank()[v] = (uint16_t)r;
-      if ((int)cv == cstar) dlt[r - R0] = (uint16_t)f.s_delta()[v]; // all >= 0 here (c* lies above every negative delta)
+      f.r_rank()[v] = (uint16_t)(r + 1); // the root popped first
+      if ((int)cv == cstar) dlt[r - R0] = (uint16_t)f.r_delta()[v]; // all >= 0 here (c* lies above every negative delta)
     }
     __syncthreads();
     if (wid == 0)
@@ -1788,57 +1608,67 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *D,
     }
     __syncthreads();
     const int k = s_k;
-    for (int v = tid; v < nS; v += kQtThreads) f.s_pop()[v] = ((int)f.s_cnt()[v] > cstar || (int)f.s_rank()[v] - R0 < k) ? 1 : 0;
-    __syncthreads();
-  }
-  tick(5);
-
-  // ---- F7: leaves (children of popped nodes -- and of the root -- that did not pop), best response of each
-  if (s_mode != kEmpty)
-  {
-    const int nS = s_mode == kRun ? s_nS : 0;
-    const uint8_t *resp = f.resp();
-    for (int item = tid; item <= nS; item += kQtThreads)
+    for (int v = 1 + tid; v < nrec; v += kQtThreads)
     {
-      int p = 0, cnt = 0, d = -1;
-      uint32_t prank = 0;
-      if (item < nS)
+      if (!in_S(v)) continue;
+      if ((int)f.r_cnt()[v] > cstar || (int)f.r_rank()[v] - 1 - R0 < k)
       {
-        if (!f.s_pop()[item]) continue;
-        p = f.s_pos()[item], cnt = f.s_cnt()[item], d = f.s_dc()[item] >> 4;
-        prank = (uint32_t)f.s_rank()[item] + 1u;
+        f.r_state()[v] |= kFpPopped;
+        const uint32_t par = f.r_par()[v], child = (f.r_meta()[v] >> 1) & 7u;
+        atomicOr((unsigned int *)(f.r_kidpop() + (par & ~3u)), 1u << (8u * (par & 3u) + child)); // its children stand in for it
       }
-      fp_children(f, p, cnt, d, [&](int dg, int a, int b) {
-        const int ccnt = b - a;
-        if (cstar > 0 && ccnt >= cstar && ccnt >= 2)
+    }
+    __syncthreads();
+    tick(3);
+  }
+
+  // ---- V4: leaves (children of popped records -- the root included -- that did not pop), best response of each
+  if (mode != kEmpty)
+  {
+    const uint8_t *resp = f.resp();
+    for (int v = tid; v < nrec; v += kQtThreads)
+    {
+      const uint8_t st = f.r_state()[v];
+      if (!(st & kFpPopped)) continue;
+      const uint32_t kidpop = f.r_kidpop()[v];
+      const uint32_t prank = v == 0 ? 0u : (uint32_t)f.r_rank()[v];
+      const uint16_t *arr = f.arr((st & kFpKidsBuf) ? 1 : 0);
+      const int nk = v == 0 ? K : 4;
+      int base = v == 0 ? 0 : (int)f.r_lo()[v];
+      for (int k = 0; k < nk; ++k)
+      {
+        int tk;
+        if (v == 0)
         {
-          const int q = fp_hash_find(f, a, d + 1);
-          if (q >= 0 && f.s_pop()[q]) return; // popped itself: its children stand in for it
+          base = bin_start[k * kQtBinsPerStrip];
+          tk = bin_start[(k + 1) * kQtBinsPerStrip] - base;
         }
-        uint32_t best = 0, best_i = 0;
-        for (int pos = a; pos < b; ++pos)
+        else
+          tk = f.r_t(k)[v];
+        if (tk > 0 && !((kidpop >> k) & 1u))
         {
-          const uint32_t r = resp[pos];
-          if (r >= best && r > 0)
+          uint32_t best = 0, best_i = 0;
+          for (int pos = base; pos < base + tk; ++pos)
           {
-            const uint32_t idx = sorted[pos];
-            if (r > best || idx < best_i) best = r, best_i = idx;
+            const uint32_t idx = arr[pos], r = resp[idx];
+            if (r > best || (r == best && r > 0 && idx < best_i)) best = r, best_i = idx;
+          }
+          const int li = fp_alloc(&s_nleaf);
+          if (li < nc)
+          {
+            f.lf_best()[li] = (uint16_t)best_i;
+            f.lf_cnt()[li] = (uint16_t)tk;
+            f.lf_I()[li] = (prank << 3) | (uint32_t)k;
           }
         }
-        const int li = fp_alloc(&s_nleaf);
-        if (li < f.cap_S())
-        {
-          f.lf_best()[li] = (uint16_t)best_i;
-          f.lf_cnt()[li] = (uint16_t)ccnt;
-          f.lf_I()[li] = (prank << 3) | (uint32_t)dg;
-        }
-      });
+        base += tk;
+      }
     }
   }
   __syncthreads();
   const int nleaf = s_nleaf;
-  if (nleaf > f.cap_S()) return false; // uniform
-  tick(6);
+  if (nleaf > nc) return false; // uniform
+  tick(4);
   // nodes2kpoints (:182-192): the first min(need, |M|) entries in (count desc, insertion order); drop the rest from the end
   const int surplus = nleaf - min(need, nleaf);
   for (int it = 0; it < surplus; ++it)
@@ -1855,14 +1685,14 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *D,
     if (tid == 0) s_amax = 0ull;
     __syncthreads();
   }
-  // flags (the key array is dead from here on)
+  // flags (over the response bytes, which are dead now)
   uint32_t *flag = f.keys();
   for (int i = tid; i < n; i += kQtThreads) flag[i] = 0u;
   __syncthreads();
   for (int li = tid; li < nleaf; li += kQtThreads)
     if (f.lf_cnt()[li] != 0xffffu && (int)f.lf_best()[li] < n) flag[f.lf_best()[li]] = 1u;
   __syncthreads();
-  tick(7);
+  tick(5);
   return true;
 }
 
@@ -1964,114 +1794,125 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
     }
   };
 
-  // ---- fast path (see qt_fast_path): the usual case -- keys decide everything -- needs no sequential loop at all
-  bool done = false;
-  if (p.qt_fast && use_keys && K >= 1 && K <= kQtMaxBinStrips && need >= 2 && n < p.qt_smem_cap)
-  {
-    gather(false);
+  // ---- Phase B': root.  With need <= 1 the reference never pops the root (:151); otherwise its first pop is the root,
+  // whose children are the strips: partition the corners by strip with the whole block (stable: K ordered scans).
+  gather(false);
+  const bool split_root_here = use_keys && need > 1;
+  const bool presort = split_root_here && K <= kQtMaxBinStrips;
+  auto root_partition = [&]() {
+    if (tid < 32) s_strip_cnt[tid] = 0;
     __syncthreads();
-    done = qt_fast_path(smem, lists, (int *)q.bhead, s_bin_start, p.qt_smem_cap, node_cap, K, kp, n, need, s_warp, p.qt_stats);
+    if (presort)
+    {
+      // counting sort by (strip, depth-1 digit, depth-2 digit), "on a split line" (7) last; order inside a bin is arbitrary
+      // (nothing downstream depends on the order of a node's list: the best-response pick breaks ties by lowest index)
+      const int nb = K * kQtBinsPerStrip;
+      int *s_bin_cur = in_smem ? (int *)ib16 : (int *)ib32; // scatter cursors: the second index array is still unused here
+      auto bin_of = [&](uint32_t key) -> int {
+        const uint32_t sidx = key >> kKeyStripShift;
+        if (sidx == kKeyNoStrip) return -1;
+        uint32_t b = sidx;
+#pragma unroll
+        for (int j = 1; j <= kQtPresort; ++j) b = b * 5u + min((key >> (kKeyStripShift - 3 * j)) & 7u, 4u);
+        return (int)b;
+      };
+      for (int i = tid; i <= nb; i += kQtThreads) s_bin_start[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += kQtThreads)
+      {
+        const int b = bin_of(keys[i]);
+        if (b >= 0) atomicAdd(&s_bin_start[b + 1], 1);
+      }
+      __syncthreads();
+      {
+        // exclusive scan over the bins: a contiguous run of bins per thread
+        const int per = (nb + kQtThreads - 1) / kQtThreads;
+        const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
+        int mine = 0;
+        for (int b = b0; b < b1; ++b) mine += s_bin_start[b + 1];
+        int total;
+        int off = block_exclusive_scan<kQtThreads>(mine, total, s_warp);
+        for (int b = b0; b < b1; ++b)
+        {
+          const int c = s_bin_start[b + 1];
+          s_bin_cur[b] = off;
+          off += c;
+        }
+        __syncthreads();
+        for (int b = b0; b < b1; ++b) s_bin_start[b] = s_bin_cur[b];
+        if (tid == 0) s_bin_start[nb] = total;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += kQtThreads)
+      {
+        const int b = bin_of(keys[i]);
+        if (b >= 0)
+        {
+          const int pos = atomicAdd(&s_bin_cur[b], 1);
+          if (in_smem)
+            ia16[pos] = (uint16_t)i;
+          else
+            ia32[pos] = (uint32_t)i;
+        }
+      }
+      if (tid < K) s_strip_cnt[tid] = s_bin_start[(tid + 1) * kQtBinsPerStrip] - s_bin_start[tid * kQtBinsPerStrip];
+    }
+    else if (split_root_here)
+    {
+      const int per = (n + kQtThreads - 1) / kQtThreads;
+      const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+      int base = 0;
+      for (int k = 0; k < K; ++k)
+      {
+        int mine = 0;
+        for (int i = i0; i < i1; ++i) mine += (keys[i] >> kKeyStripShift) == (uint32_t)k;
+        int total;
+        int off = base + block_exclusive_scan<kQtThreads>(mine, total, s_warp);
+        for (int i = i0; i < i1; ++i)
+          if ((keys[i] >> kKeyStripShift) == (uint32_t)k)
+          {
+            if (in_smem)
+              ia16[off] = (uint16_t)i;
+            else
+              ia32[off] = (uint32_t)i;
+            ++off;
+          }
+        if (tid == 0) s_strip_cnt[k] = total;
+        base += total;
+      }
+    }
+    else
+    {
+      if (in_smem)
+        for (int i = tid; i < n; i += kQtThreads) ia16[i] = (uint16_t)i; // root holds every corner (:26-27)
+      else
+        for (int i = tid; i < n; i += kQtThreads) ia32[i] = (uint32_t)i;
+    }
+
+    __syncthreads();
+  };
+  root_partition();
+
+  // ---- loop-free path (see qt_fast_path): the usual case -- the keys decide everything -- needs no sequential loop at all.
+  // It works on the presorted corners (index array grouped by (strip, d1, d2, d3) bin + the bin table); if it has to give up
+  // after it has started to partition nodes, the presort is simply redone for the sequential loop.
+  bool done = false;
+  if (p.qt_fast && presort && in_smem)
+  {
+    uint8_t *scr = lists + qt_align16((size_t)p.qt_smem_cap * 8);
+    done = qt_fast_path(smem, lists, (int *)scr, scr + 2048, s_bin_start, p.qt_smem_cap, node_cap, K, kp, n, need, s_warp, p.qt_stats);
+    if (!done)
+    { // start over for the sequential loop (the loop-free path reuses the key / index arrays)
+      gather(false);
+      root_partition();
+    }
   }
   uint32_t *flag = keys; // the key array doubles as the "selected" flag array at the end
   if (tid == 0 && p.qt_stats) atomicAdd(&p.qt_stats[done ? 0 : 1], 1ull);
   if (!done)
   {
-  gather(false);
   for (int i = tid; i < 2 * kQtBuckets; i += kQtThreads) q.bhead[i] = (uint16_t)kNil; // heads and tails are contiguous
   for (int i = tid; i < node_cap; i += kQtThreads) q.np.state[i] = 0;
-  if (tid < 32) s_strip_cnt[tid] = 0;
-  __syncthreads();
-
-  // ---- Phase B': root.  With need <= 1 the reference never pops the root (:151); otherwise its first pop is the root,
-  // whose children are the strips: partition the corners by strip with the whole block (stable: K ordered scans).
-  const bool split_root_here = use_keys && need > 1;
-  const bool presort = split_root_here && K <= kQtMaxBinStrips;
-  if (presort)
-  {
-    // counting sort by (strip, depth-1 digit, depth-2 digit), "on a split line" (7) last; order inside a bin is arbitrary
-    // (nothing downstream depends on the order of a node's list: the best-response pick breaks ties by lowest index)
-    const int nb = K * kQtBinsPerStrip;
-    int *s_bin_cur = in_smem ? (int *)ib16 : (int *)ib32; // scatter cursors: the second index array is still unused here
-    auto bin_of = [&](uint32_t key) -> int {
-      const uint32_t sidx = key >> kKeyStripShift;
-      if (sidx == kKeyNoStrip) return -1;
-      uint32_t b = sidx;
-#pragma unroll
-      for (int j = 1; j <= kQtPresort; ++j) b = b * 5u + min((key >> (kKeyStripShift - 3 * j)) & 7u, 4u);
-      return (int)b;
-    };
-    for (int i = tid; i <= nb; i += kQtThreads) s_bin_start[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += kQtThreads)
-    {
-      const int b = bin_of(keys[i]);
-      if (b >= 0) atomicAdd(&s_bin_start[b + 1], 1);
-    }
-    __syncthreads();
-    {
-      // exclusive scan over the bins: a contiguous run of bins per thread
-      const int per = (nb + kQtThreads - 1) / kQtThreads;
-      const int b0 = min(tid * per, nb), b1 = min(b0 + per, nb);
-      int mine = 0;
-      for (int b = b0; b < b1; ++b) mine += s_bin_start[b + 1];
-      int total;
-      int off = block_exclusive_scan<kQtThreads>(mine, total, s_warp);
-      for (int b = b0; b < b1; ++b)
-      {
-        const int c = s_bin_start[b + 1];
-        s_bin_cur[b] = off;
-        off += c;
-      }
-      __syncthreads();
-      for (int b = b0; b < b1; ++b) s_bin_start[b] = s_bin_cur[b];
-      if (tid == 0) s_bin_start[nb] = total;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += kQtThreads)
-    {
-      const int b = bin_of(keys[i]);
-      if (b >= 0)
-      {
-        const int pos = atomicAdd(&s_bin_cur[b], 1);
-        if (in_smem)
-          ia16[pos] = (uint16_t)i;
-        else
-          ia32[pos] = (uint32_t)i;
-      }
-    }
-    if (tid < K) s_strip_cnt[tid] = s_bin_start[(tid + 1) * kQtBinsPerStrip] - s_bin_start[tid * kQtBinsPerStrip];
-  }
-  else if (split_root_here)
-  {
-    const int per = (n + kQtThreads - 1) / kQtThreads;
-    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
-    int base = 0;
-    for (int k = 0; k < K; ++k)
-    {
-      int mine = 0;
-      for (int i = i0; i < i1; ++i) mine += (keys[i] >> kKeyStripShift) == (uint32_t)k;
-      int total;
-      int off = base + block_exclusive_scan<kQtThreads>(mine, total, s_warp);
-      for (int i = i0; i < i1; ++i)
-        if ((keys[i] >> kKeyStripShift) == (uint32_t)k)
-        {
-          if (in_smem)
-            ia16[off] = (uint16_t)i;
-          else
-            ia32[off] = (uint32_t)i;
-          ++off;
-        }
-      if (tid == 0) s_strip_cnt[k] = total;
-      base += total;
-    }
-  }
-  else
-  {
-    if (in_smem)
-      for (int i = tid; i < n; i += kQtThreads) ia16[i] = (uint16_t)i; // root holds every corner (:26-27)
-    else
-      for (int i = tid; i < n; i += kQtThreads) ia32[i] = (uint32_t)i;
-  }
   __syncthreads();
 
   // ---- Phase C: the priority loop, warp 0 only
