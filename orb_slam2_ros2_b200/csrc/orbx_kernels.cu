@@ -1396,29 +1396,41 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     }
     tick(0);
 
-    // ---- V2: descent from depth 3, level by level; a node is split only if its count reaches the running lower bound of c*
-    int f0 = s_nrec; // first depth-3 record (every thread reads it before anybody can get past the barriers of find_cross)
+    // ---- V2: descent from depth 3, level by level.  The deltas are always known ONE level below the records (a cheap count-only
+    // look at the next key digit of every child), so the bound that decides which children get a record -- and will be split --
+    // already includes them: bound = the crossing computed from all nodes down to that level, a lower bound of c*.
+    const uint32_t *keys = f.keys();
+    for (int j = tid; j < K * kQtBinsPerStrip; j += kQtThreads)
+    {
+      // look-ahead for depth 3: every (strip, d1, d2, d3) bin of >= 2 corners is a node; its children = the digits-4 present
+      if (j % 5 == 4 || (j / 5) % 5 == 4 || (j / 25) % 5 == 4) continue;
+      const int lo = bin_start[j], cnt = bin_start[j + 1] - lo;
+      if (cnt < 2) continue;
+      const uint16_t *src = f.arr(0) + lo;
+      uint32_t mask = 0;
+      for (int i = 0; i < cnt; ++i) mask |= 1u << ((keys[src[i]] >> (kKeyStripShift - 12)) & 7u);
+      add_delta(cnt, __popc(mask & 15u) - 1);
+    }
+    __syncthreads();
     find_cross();
     int bound = max(2, s_cstar); // no crossing yet: every node of >= 2 corners may matter
+    int f0 = s_nrec;             // first depth-3 record (read by every thread before anybody allocates: barriers of find_cross)
+    for (int j = tid; j < K * kQtBinsPerStrip; j += kQtThreads)
     {
-      // depth-3 nodes = bins; parent = the depth-2 prefix j / 5 (slot K + 5 K + j / 5)
-      for (int j = tid; j < K * kQtBinsPerStrip; j += kQtThreads)
+      if (j % 5 == 4 || (j / 5) % 5 == 4 || (j / 25) % 5 == 4) continue;
+      const int lo = bin_start[j], cnt = bin_start[j + 1] - lo;
+      if (cnt < bound) continue;
+      const int idx = fp_alloc(&s_nrec);
+      if (idx >= nc)
       {
-        if (j % 5 == 4 || (j / 5) % 5 == 4 || (j / 25) % 5 == 4) continue;
-        const int lo = bin_start[j], cnt = bin_start[j + 1] - lo;
-        if (cnt < bound) continue;
-        const int idx = fp_alloc(&s_nrec);
-        if (idx >= nc)
-        {
-          s_over = 1;
-          continue;
-        }
-        f.r_lo()[idx] = (uint16_t)lo;
-        f.r_cnt()[idx] = (uint16_t)cnt;
-        f.r_par()[idx] = s_tab[6 * K + j / 5];
-        f.r_meta()[idx] = (uint8_t)((3 << 4) | ((j % 5) << 1));
-        f.r_state()[idx] = 0;
+        s_over = 1;
+        continue;
       }
+      f.r_lo()[idx] = (uint16_t)lo;
+      f.r_cnt()[idx] = (uint16_t)cnt;
+      f.r_par()[idx] = s_tab[6 * K + j / 5]; // the depth-2 prefix
+      f.r_meta()[idx] = (uint8_t)((3 << 4) | ((j % 5) << 1));
+      f.r_state()[idx] = 0;
     }
     __syncthreads();
     if (tid == 0) s_f1 = s_nrec;
@@ -1427,18 +1439,12 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     {
       const int f1 = min(s_f1, nc);
       if (f1 <= f0 || s_over) break; // uniform
-      if (level > 3)
-      {
-        find_cross();
-        bound = max(bound, max(2, s_cstar));
-      }
-      const uint32_t *keys = f.keys();
+      // pass A: split every record of this level (stable 4-way partition by the next digit into the other index array) and
+      // look one digit further into its children
       const int shift = kKeyStripShift - 3 * (level + 1);
       for (int v = f0 + tid; v < f1; v += kQtThreads)
       {
-        const int cnt = f.r_cnt()[v];
-        if (cnt < bound) continue; // stays unsplit: it can never pop
-        const int lo = f.r_lo()[v], buf = f.r_meta()[v] & 1;
+        const int cnt = f.r_cnt()[v], lo = f.r_lo()[v], buf = f.r_meta()[v] & 1;
         const uint16_t *src = f.arr(buf) + lo;
         uint16_t *dst = f.arr(buf ^ 1);
         int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
@@ -1448,42 +1454,57 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
           c0 += dg == 0, c1 += dg == 1, c2 += dg == 2, c3 += dg == 3;
         }
         int o0 = lo, o1 = o0 + c0, o2 = o1 + c1, o3 = o2 + c2;
+        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0; // digits (level + 2) present in each child
         for (int i = 0; i < cnt; ++i)
         {
-          const uint32_t idx = src[i], dg = (keys[idx] >> shift) & 7u;
-          if (dg == 0) dst[o0++] = (uint16_t)idx;
-          if (dg == 1) dst[o1++] = (uint16_t)idx;
-          if (dg == 2) dst[o2++] = (uint16_t)idx;
-          if (dg == 3) dst[o3++] = (uint16_t)idx;
+          const uint32_t idx = src[i], key = keys[idx], dg = (key >> shift) & 7u;
+          const uint32_t nx = level < 8 ? 1u << ((key >> (shift - 3)) & 7u) : 0u;
+          if (dg == 0) dst[o0++] = (uint16_t)idx, m0 |= nx;
+          if (dg == 1) dst[o1++] = (uint16_t)idx, m1 |= nx;
+          if (dg == 2) dst[o2++] = (uint16_t)idx, m2 |= nx;
+          if (dg == 3) dst[o3++] = (uint16_t)idx, m3 |= nx;
         }
-        const int t[4] = {c0, c1, c2, c3};
         const int ne = (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
         f.r_t(0)[v] = (uint16_t)c0, f.r_t(1)[v] = (uint16_t)c1, f.r_t(2)[v] = (uint16_t)c2, f.r_t(3)[v] = (uint16_t)c3;
         f.r_delta()[v] = (int8_t)(ne - 1);
         f.r_state()[v] = (uint8_t)(kFpActive | ((buf ^ 1) ? kFpKidsBuf : 0));
-        add_delta(cnt, ne - 1);
-        int base = lo;
+        const int t[4] = {c0, c1, c2, c3};
+        const uint32_t mk[4] = {m0, m1, m2, m3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (t[k] >= 2)
+          {
+            if (level == 8)
+              atomicMax(&s_deep, t[k]); // a node AT the key depth with >= 2 corners: the keys cannot split it
+            else
+              add_delta(t[k], __popc(mk[k] & 15u) - 1);
+          }
+      }
+      __syncthreads();
+      if (level == 8) break; // uniform
+      find_cross();
+      bound = max(bound, max(2, s_cstar));
+      // pass B: records for the children that may still pop
+      for (int v = f0 + tid; v < f1; v += kQtThreads)
+      {
+        const int buf = f.r_meta()[v] & 1;
+        int base = f.r_lo()[v];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
         {
-          const int tk = t[k];
-          if (tk >= 2)
+          const int tk = f.r_t(k)[v];
+          if (tk >= bound)
           {
-            if (level + 1 > 8)
-              atomicMax(&s_deep, tk); // a node AT the key depth with >= 2 corners: the keys cannot split it
-            else if (tk >= bound)
+            const int idx = fp_alloc(&s_nrec);
+            if (idx >= nc)
+              s_over = 1;
+            else
             {
-              const int idx = fp_alloc(&s_nrec);
-              if (idx >= nc)
-                s_over = 1;
-              else
-              {
-                f.r_lo()[idx] = (uint16_t)base;
-                f.r_cnt()[idx] = (uint16_t)tk;
-                f.r_par()[idx] = (uint16_t)v;
-                f.r_meta()[idx] = (uint8_t)(((level + 1) << 4) | (k << 1) | (buf ^ 1));
-                f.r_state()[idx] = 0;
-              }
+              f.r_lo()[idx] = (uint16_t)base;
+              f.r_cnt()[idx] = (uint16_t)tk;
+              f.r_par()[idx] = (uint16_t)v;
+              f.r_meta()[idx] = (uint8_t)(((level + 1) << 4) | (k << 1) | (buf ^ 1));
+              f.r_state()[idx] = 0;
             }
           }
           base += tk;
