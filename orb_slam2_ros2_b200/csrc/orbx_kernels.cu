@@ -1265,6 +1265,14 @@ __device__ __forceinline__ bool fp_chain_before(const QtFast &f, uint32_t u, uin
   }
 }
 
+// block barrier of the loop-free path: thread-dependent branches (one thread publishing a result, lanes with and without work)
+// precede most of them, so the warp is explicitly reconverged before the aligned barrier
+__device__ __forceinline__ void fp_sync()
+{
+  __syncwarp();
+  __syncthreads();
+}
+
 __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *scr, uint8_t *lf, const int *bin_start, int cap, int nc, int K,
                                           const uint32_t *kp, int n, int need, int *s_warp, unsigned long long *stats)
 {
@@ -1315,19 +1323,19 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     }
     if (tid == 0) s_first = 0x7fffffff;
     if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
+    fp_sync();
     int base = 0;
     for (int w = 0; w < wid; ++w) base += s_warp[w];
     const int after = s_live0 + s_dbig + base + inc;
     if (c >= 2 && after >= need) atomicMin(&s_first, tid);
-    __syncthreads();
+    fp_sync();
     if (tid == s_first)
     {
       s_cstar = c;
       s_before = after - d;
     }
     if (tid == 0 && s_first == 0x7fffffff) s_cstar = 0;
-    __syncthreads();
+    fp_sync();
   };
 
   // ---- V0: accumulators, the root record, the strips
@@ -1345,9 +1353,9 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     f.r_rank()[0] = 0;
   }
   for (int i = tid; i < nc; i += kQtThreads) f.r_kidpop()[i] = 0;
-  __syncthreads();
+  fp_sync();
   if (tid < K) atomicAdd(&s_live0, bin_start[(tid + 1) * kQtBinsPerStrip] > bin_start[tid * kQtBinsPerStrip] ? 1 : 0);
-  __syncthreads();
+  fp_sync();
   const int live0 = s_live0;
   int mode = live0 == 0 ? kEmpty : (live0 >= need ? kNoPop : kRun);
   int cstar = 0;
@@ -1390,7 +1398,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
         s_tab[tab0 + j] = (uint16_t)idx;
         add_delta(cnt, ne - 1);
       }
-      __syncthreads();
+      fp_sync();
       tab0 += K * pow5;
       pow5 *= 5;
     }
@@ -1411,10 +1419,10 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
       for (int i = 0; i < cnt; ++i) mask |= 1u << ((keys[src[i]] >> (kKeyStripShift - 12)) & 7u);
       add_delta(cnt, __popc(mask & 15u) - 1);
     }
-    __syncthreads();
+    fp_sync();
+    int f0 = s_nrec; // first depth-3 record: read by every thread BEFORE the barriers of find_cross, i.e. before anybody allocates again
     find_cross();
     int bound = max(2, s_cstar); // no crossing yet: every node of >= 2 corners may matter
-    int f0 = s_nrec;             // first depth-3 record (read by every thread before anybody allocates: barriers of find_cross)
     for (int j = tid; j < K * kQtBinsPerStrip; j += kQtThreads)
     {
       if (j % 5 == 4 || (j / 5) % 5 == 4 || (j / 25) % 5 == 4) continue;
@@ -1432,9 +1440,9 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
       f.r_meta()[idx] = (uint8_t)((3 << 4) | ((j % 5) << 1));
       f.r_state()[idx] = 0;
     }
-    __syncthreads();
+    fp_sync();
     if (tid == 0) s_f1 = s_nrec;
-    __syncthreads();
+    fp_sync();
     for (int level = 3; level <= 8; ++level)
     {
       const int f1 = min(s_f1, nc);
@@ -1480,7 +1488,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
               add_delta(t[k], __popc(mk[k] & 15u) - 1);
           }
       }
-      __syncthreads();
+      fp_sync();
       if (level == 8) break; // uniform
       find_cross();
       bound = max(bound, max(2, s_cstar));
@@ -1510,10 +1518,10 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
           base += tk;
         }
       }
-      __syncthreads();
+      fp_sync();
       f0 = f1;
       if (tid == 0) s_f1 = s_nrec;
-      __syncthreads();
+      fp_sync();
     }
     if (s_over || s_nrec > nc) return false; // uniform: more records than the pool holds
     tick(1);
@@ -1535,7 +1543,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
   }
 
   // responses by corner index over the (dead) keys: the leaf scans below stay in shared memory
-  __syncthreads();
+  fp_sync();
   {
     uint8_t *resp = f.resp();
     for (int i0 = tid; i0 < n; i0 += 4 * kQtThreads)
@@ -1557,13 +1565,13 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     int *start = f.scr, *cursor = f.scr + 256; // D is dead
     uint16_t *list = (uint16_t *)f.lf;          // [<= nrec]
     uint16_t *dlt = list + nc;                  // [bucket c*] deltas in pop order
-    __syncthreads();
+    fp_sync();
     for (int i = tid; i < 512; i += kQtThreads) f.scr[i] = 0;
-    __syncthreads();
+    fp_sync();
     auto in_S = [&](int v) { return (f.r_state()[v] & kFpActive) && (int)f.r_cnt()[v] >= cstar; };
     for (int v = 1 + tid; v < nrec; v += kQtThreads)
       if (in_S(v)) atomicAdd(&cursor[min((int)f.r_cnt()[v], 255)], 1); // cursor = bucket sizes for now
-    __syncthreads();
+    fp_sync();
     {
       const int b = 255 - tid;
       const int h = cursor[b];
@@ -1575,17 +1583,17 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
         if (lane >= o) inc += t;
       }
       if (lane == 31) s_warp[wid] = inc;
-      __syncthreads();
+      fp_sync();
       int base = 0;
       for (int w = 0; w < wid; ++w) base += s_warp[w];
       start[b] = base + inc - h;
-      __syncthreads();
+      fp_sync();
       cursor[b] = base + inc - h;
     }
-    __syncthreads();
+    fp_sync();
     for (int v = 1 + tid; v < nrec; v += kQtThreads)
       if (in_S(v)) list[atomicAdd(&cursor[min((int)f.r_cnt()[v], 255)], 1)] = (uint16_t)v;
-    __syncthreads();
+    fp_sync();
     const int R0 = start[cstar], mb = cursor[cstar] - R0; // cursor[b] = end of bucket b now
     for (int v = 1 + tid; v < nrec; v += kQtThreads)
     {
@@ -1604,7 +1612,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
       f.r_rank()[v] = (uint16_t)(r + 1); // the root popped first
       if ((int)cv == cstar) dlt[r - R0] = (uint16_t)f.r_delta()[v]; // all >= 0 here (c* lies above every negative delta)
     }
-    __syncthreads();
+    fp_sync();
     if (wid == 0)
     {
       int run = s_before, k = 0;
@@ -1627,7 +1635,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
       }
       if (lane == 0) s_k = k;
     }
-    __syncthreads();
+    fp_sync();
     const int k = s_k;
     for (int v = 1 + tid; v < nrec; v += kQtThreads)
     {
@@ -1639,7 +1647,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
         atomicOr((unsigned int *)(f.r_kidpop() + (par & ~3u)), 1u << (8u * (par & 3u) + child)); // its children stand in for it
       }
     }
-    __syncthreads();
+    fp_sync();
     tick(3);
   }
 
@@ -1686,7 +1694,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
       }
     }
   }
-  __syncthreads();
+  fp_sync();
   const int nleaf = s_nleaf;
   if (nleaf > nc) return false; // uniform
   tick(4);
@@ -1697,22 +1705,22 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     for (int li = tid; li < nleaf; li += kQtThreads)
       if (f.lf_cnt()[li] != 0xffffu)
         atomicMax(&s_amax, ((unsigned long long)(0xffffu - f.lf_cnt()[li]) << 32) | (unsigned long long)(f.lf_I()[li] + 1u));
-    __syncthreads();
+    fp_sync();
     const unsigned long long top = s_amax;
     for (int li = tid; li < nleaf; li += kQtThreads)
       if (f.lf_cnt()[li] != 0xffffu && (((unsigned long long)(0xffffu - f.lf_cnt()[li]) << 32) | (unsigned long long)(f.lf_I()[li] + 1u)) == top)
         f.lf_cnt()[li] = 0xffffu;
-    __syncthreads();
+    fp_sync();
     if (tid == 0) s_amax = 0ull;
-    __syncthreads();
+    fp_sync();
   }
   // flags (over the response bytes, which are dead now)
   uint32_t *flag = f.keys();
   for (int i = tid; i < n; i += kQtThreads) flag[i] = 0u;
-  __syncthreads();
+  fp_sync();
   for (int li = tid; li < nleaf; li += kQtThreads)
     if (f.lf_cnt()[li] != 0xffffu && (int)f.lf_best()[li] < n) flag[f.lf_best()[li]] = 1u;
-  __syncthreads();
+  fp_sync();
   tick(5);
   return true;
 }

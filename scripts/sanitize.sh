@@ -24,6 +24,18 @@ ctx4 = api.Context(320, 240, 500, 4, 1.2, camera=api.Camera(300.0, 300.0, 160.0,
 b4 = ctx4.stereo_batch(np.stack([l, l, l, l]), np.stack([r, r, r, r]))
 assert int(b4.n_matches[3]) == res.n_matches
 ctx4.close()
+# frame-sharded sequence on two ranks sharing the device (peer-memory gather) + the CUDA-graph single-pair path
+ranks = [api.Context(320, 240, 500, 4, 1.2, camera=api.Camera(300.0, 300.0, 160.0, 120.0, 0.1), max_batch=2) for _ in range(2)]
+comms = api.Communicator.local(ranks, 5)
+seq_l, seq_r = np.stack([l] * 5), np.stack([r] * 5)
+for rk in range(2):
+    blk = api.frame_range(5, rk, 2)
+    rec, _, _ = ranks[rk].sequence_stereo(seq_l[blk.start:blk.stop], seq_r[blk.start:blk.stop], 5, comms[rk], gather_to_host=False)
+    assert int(rec[0]["n_matches"]) == res.n_matches
+for o in comms + ranks:
+    o.close()
+for _ in range(3):
+    assert ctx.stereo_frame(l, r).n_matches == res.n_matches
 noise = np.random.default_rng(1).integers(0, 256, (240, 320), dtype=np.uint8)
 ctx.stereo_frame(noise, noise)
 ctx.stereo_frame(np.zeros((240, 320), np.uint8), np.zeros((240, 320), np.uint8))
