@@ -248,7 +248,7 @@ int build_tables(orbx_ctx *c)
     {
       const size_t fixed = quadtree_smem_bytes(0, p.qt_node_cap, p.qt_big_cap, p.qt_cell_cap);
       const size_t budget = 160 * 1024;
-      if (budget > fixed + 8 * 3584) cap = std::min(max_list, (int)((budget - fixed) / 8) & ~255);
+      if (budget > fixed + 9 * 3584) cap = std::min(max_list, (int)((budget - fixed) / 9) & ~255);
     }
     const size_t bytes = quadtree_smem_bytes(cap, p.qt_node_cap, p.qt_big_cap, p.qt_cell_cap);
     if (bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree shared-memory pool");

@@ -620,22 +620,29 @@ __host__ __device__ inline size_t qt_align16(size_t b) { return (b + 15) & ~(siz
 
 // shared memory: node pool | bucket heads+tails | big-node list | (smem path) ia, ib (u16), key (u32)
 // node-pool region: the sequential path's node pool / the loop-free path's records
-static_assert(kNodeBytes <= 20, "the node-pool region is sized for 20 bytes per node");
+static_assert(kNodeBytes <= 22, "the node-pool region is sized for 22 bytes per node");
 __host__ __device__ inline size_t qt_pool_bytes(int node_cap)
 {
-  return qt_align16((size_t)node_cap * 20 + 16); // 19 B per node (sequential path) / 20 B per record (loop-free path)
+  return qt_align16((size_t)node_cap * 22 + 16); // 19 B per node (sequential path) / 22 B per record (loop-free path)
 }
 
+// The two formulations never run at the same time, so their private tables share one region:
+//   sequential loop   bucket heads + tails (1 KB) | list of the nodes of 256+ corners
+//   loop-free path    2 KB of histogram / bucket tables | 8 B per leaf | best-response corner of every (strip, d1, d2, d3) bin
+__host__ __device__ inline size_t qt_union_bytes(int node_cap, int big_cap)
+{
+  const size_t seq = qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t)) + qt_align16((size_t)big_cap * sizeof(uint16_t));
+  const size_t fast = 2048 + qt_align16((size_t)node_cap * 8) + qt_align16((size_t)kQtMaxBinStrips * kQtBinsPerStrip * sizeof(uint16_t));
+  return seq > fast ? seq : fast;
+}
+
+// shared memory: node pool / records | per-cell offsets | the union above | keys u32, ia u16, ib u16, responses u8 per list slot
 size_t quadtree_smem_bytes(int list_cap, int node_cap, int big_cap, int max_level_cells)
 {
   size_t b = qt_pool_bytes(node_cap);
   b += qt_align16((size_t)max_level_cells * sizeof(int));
-  b += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
-  b += qt_align16((size_t)big_cap * sizeof(uint16_t));
-  b += qt_align16((size_t)list_cap * (2 * sizeof(uint16_t) + sizeof(uint32_t)));
-  // loop-free path: 2 KB of histogram / bucket tables and 8 B per leaf
-  b += 2048;
-  b += qt_align16((size_t)node_cap * 8);
+  b += qt_union_bytes(node_cap, big_cap);
+  b += qt_align16((size_t)list_cap * 9);
   return b + 64;
 }
 
@@ -1207,8 +1214,8 @@ __device__ void qt_select(const QtNodePool &np, const uint32_t *kp, const IdxT *
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kFpWarps = kQtThreads / 32;
 constexpr int kFpSmall = 8;        // node counts below this are accumulated in per-warp counters (the hot histogram bins)
-constexpr int kFpRecBytes = 20;    // shared memory per record
-static_assert(kFpRecBytes == 20, "qt_pool_bytes");
+constexpr int kFpRecBytes = 22;    // shared memory per record
+static_assert(kFpRecBytes == 22, "qt_pool_bytes");
 constexpr uint32_t kFpNone = 0xffffu;
 constexpr uint8_t kFpActive = 1, kFpPopped = 2, kFpKidsBuf = 0x80;
 
@@ -1226,28 +1233,51 @@ __device__ __forceinline__ int fp_alloc(int *counter)
 // views into the CTA's shared memory (derived from a few numbers; a by-value table of pointers would live in local memory)
 struct QtFast
 {
-  uint8_t *pool;   // records: u16 lo cnt par rank t0 t1 t2 t3 [nc] | u8 kidpop meta delta state [nc]
-  uint8_t *lists;  // keys u32[cap] | ia u16[cap] | ib u16[cap]
+  uint8_t *pool;   // records: u16 lo cnt par rank best t0 t1 t2 t3 [nc] | u8 kidrec meta delta state [nc]      (22 B per record)
+  uint8_t *lists;  // keys u32[cap] | ia u16[cap] | ib u16[cap] | resp u8[cap]
   int *scr;        // 2 KB: D[256] during the descent, start[256] + cursor[256] during the ranking
   uint8_t *lf;     // leaves: I u32[nc] | best u16[nc] | cnt u16[nc]   (the ranking keeps its bucket list and deltas here before)
+  uint16_t *bin_best; // best-response corner of every (strip, d1, d2, d3) bin (kFpNone: empty)
   int cap, nc;
   __device__ __forceinline__ uint32_t *keys() const { return (uint32_t *)lists; }
-  __device__ __forceinline__ uint8_t *resp() const { return lists; } // responses by corner, once the keys are dead
   __device__ __forceinline__ uint16_t *arr(int buf) const { return (uint16_t *)(lists + (4 + 2 * (size_t)buf) * cap); }
+  __device__ __forceinline__ const uint8_t *resp() const { return lists + 8 * (size_t)cap; } // response (FAST score) by corner
   __device__ __forceinline__ uint16_t *u16(int k) const { return (uint16_t *)pool + (size_t)k * nc; }
-  __device__ __forceinline__ uint16_t *r_lo() const { return u16(0); }
+  __device__ __forceinline__ uint16_t *r_lo() const { return u16(0); }   // first position of its corners (table records: first bin)
   __device__ __forceinline__ uint16_t *r_cnt() const { return u16(1); }
   __device__ __forceinline__ uint16_t *r_par() const { return u16(2); }
   __device__ __forceinline__ uint16_t *r_rank() const { return u16(3); }
-  __device__ __forceinline__ uint16_t *r_t(int k) const { return u16(4 + k); }
-  __device__ __forceinline__ uint8_t *r_kidpop() const { return pool + 16 * (size_t)nc; }
-  __device__ __forceinline__ uint8_t *r_meta() const { return pool + 17 * (size_t)nc; } // depth << 4 | child << 1 | buffer of its corners
-  __device__ __forceinline__ int8_t *r_delta() const { return (int8_t *)(pool + 18 * (size_t)nc); }
-  __device__ __forceinline__ uint8_t *r_state() const { return pool + 19 * (size_t)nc; }
+  __device__ __forceinline__ uint16_t *r_best() const { return u16(4); } // best-response corner, taken while its list was intact
+  __device__ __forceinline__ uint16_t *r_t(int k) const { return u16(5 + k); }
+  __device__ __forceinline__ uint8_t *r_kidrec() const { return pool + 18 * (size_t)nc; } // children that have a record of their own
+  __device__ __forceinline__ uint8_t *r_meta() const { return pool + 19 * (size_t)nc; }   // depth << 4 | child << 1 | buffer of its corners
+  __device__ __forceinline__ int8_t *r_delta() const { return (int8_t *)(pool + 20 * (size_t)nc); }
+  __device__ __forceinline__ uint8_t *r_state() const { return pool + 21 * (size_t)nc; }
   __device__ __forceinline__ uint32_t *lf_I() const { return (uint32_t *)lf; }
   __device__ __forceinline__ uint16_t *lf_best() const { return (uint16_t *)(lf + 4 * (size_t)nc); }
   __device__ __forceinline__ uint16_t *lf_cnt() const { return (uint16_t *)(lf + 6 * (size_t)nc); }
 };
+
+// a child announces its record to the parent (several threads may do so for one parent: atomic on the containing word)
+__device__ __forceinline__ void fp_mark_kid(const QtFast &f, uint32_t par, uint32_t child)
+{
+  atomicOr((unsigned int *)(f.r_kidrec() + (par & ~3u)), 1u << (8u * (par & 3u) + child));
+}
+
+// best response over the bins [b0, b1): lowest corner index among the maxima (getFeature :103-117; bins hold their own best)
+__device__ __forceinline__ uint32_t fp_best_of_bins(const QtFast &f, int b0, int b1)
+{
+  const uint8_t *resp = f.resp();
+  uint32_t best = 0, best_i = 0;
+  for (int b = b0; b < b1; ++b)
+  {
+    const uint32_t idx = f.bin_best[b];
+    if (idx == kFpNone) continue;
+    const uint32_t r = resp[idx];
+    if (r > best || (r == best && r > 0 && idx < best_i)) best = r, best_i = idx;
+  }
+  return best_i;
+}
 
 // equal counts: does record u pop before record v?  (ancestor counts, parent first; the root -- record 0 -- counts as +inf;
 // then the child index below the first common ancestor)
@@ -1273,15 +1303,15 @@ __device__ __forceinline__ void fp_sync()
   __syncthreads();
 }
 
-__device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *scr, uint8_t *lf, const int *bin_start, int cap, int nc, int K,
-                                          const uint32_t *kp, int n, int need, int *s_warp, unsigned long long *stats)
+__device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *scr, uint8_t *lf, uint16_t *bin_best, const int *bin_start, int cap, int nc, int K,
+                                          int n, int need, int *s_warp, unsigned long long *stats)
 {
   __shared__ int s_live0, s_dbig, s_neg, s_deep, s_cstar, s_before, s_first, s_nrec, s_f1, s_k, s_nleaf, s_over;
   __shared__ int s_small[kFpWarps][kFpSmall];
   __shared__ uint16_t s_tab[kQtMaxBinStrips * 31]; // record of every depth 0..2 prefix (kFpNone: no node)
   __shared__ unsigned long long s_amax;
   QtFast f;
-  f.pool = pool, f.lists = lists, f.scr = scr, f.lf = lf, f.cap = cap, f.nc = nc;
+  f.pool = pool, f.lists = lists, f.scr = scr, f.lf = lf, f.bin_best = bin_best, f.cap = cap, f.nc = nc;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned FULL = 0xffffffffu;
   enum { kRun = 0, kEmpty = 1, kNoPop = 2, kBail = 3 };
@@ -1352,13 +1382,38 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     f.r_state()[0] = kFpActive | kFpPopped; // the loop always pops the root first (need >= 2)
     f.r_rank()[0] = 0;
   }
-  for (int i = tid; i < nc; i += kQtThreads) f.r_kidpop()[i] = 0;
+  for (int i = tid; i < nc; i += kQtThreads) f.r_kidrec()[i] = 0;
   fp_sync();
   if (tid < K) atomicAdd(&s_live0, bin_start[(tid + 1) * kQtBinsPerStrip] > bin_start[tid * kQtBinsPerStrip] ? 1 : 0);
   fp_sync();
   const int live0 = s_live0;
   int mode = live0 == 0 ? kEmpty : (live0 >= need ? kNoPop : kRun);
   int cstar = 0;
+
+  // ---- V0b: every (strip, d1, d2, d3) bin once: its best-response corner (leaves are read off these: a node's own list may be
+  // overwritten by its grandchildren later), and -- the bin being a depth-3 node when it holds >= 2 corners -- the number of its
+  // children (the fourth key digits present), i.e. the deltas one level below the table
+  {
+    const uint32_t *keys = f.keys();
+    const uint8_t *resp = f.resp();
+    for (int j = tid; j < K * kQtBinsPerStrip; j += kQtThreads)
+    {
+      const int lo = bin_start[j], cnt = bin_start[j + 1] - lo;
+      const uint16_t *src = f.arr(0) + lo;
+      uint32_t mask = 0, best = 0, best_i = 0;
+      for (int i = 0; i < cnt; ++i)
+      {
+        const uint32_t idx = src[i], r = resp[idx];
+        mask |= 1u << ((keys[idx] >> (kKeyStripShift - 12)) & 7u);
+        if (r > best || (r == best && r > 0 && idx < best_i)) best = r, best_i = idx;
+      }
+      f.bin_best[j] = best > 0 ? (uint16_t)best_i : (uint16_t)kFpNone; // no positive response: getFeature's default (index 0) applies
+
+      const bool node = !(j % 5 == 4 || (j / 5) % 5 == 4 || (j / 25) % 5 == 4) && cnt >= 2;
+      if (node && mode == kRun) add_delta(cnt, __popc(mask & 15u) - 1);
+    }
+  }
+  fp_sync();
 
   if (mode == kRun)
   {
@@ -1387,12 +1442,15 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
           s_over = 1;
           continue;
         }
-        f.r_lo()[idx] = (uint16_t)lo;
+        const uint32_t par = d == 0 ? 0u : (uint32_t)s_tab[tab0 - pow5 / 5 * K + j / 5], child = (uint32_t)(d == 0 ? j : g_last);
+        f.r_lo()[idx] = (uint16_t)B; // table records keep their first bin (their corners are the bins [B, B + span))
         f.r_cnt()[idx] = (uint16_t)cnt;
-        f.r_par()[idx] = d == 0 ? (uint16_t)0 : s_tab[tab0 - pow5 / 5 * K + j / 5];
-        f.r_meta()[idx] = (uint8_t)((d << 4) | ((d == 0 ? j : g_last) << 1));
+        f.r_par()[idx] = (uint16_t)par;
+        f.r_meta()[idx] = (uint8_t)((d << 4) | (child << 1));
         f.r_delta()[idx] = (int8_t)(ne - 1);
-        f.r_state()[idx] = kFpActive; // children lie in the same array (bins are contiguous)
+        f.r_state()[idx] = kFpActive;
+        f.r_best()[idx] = (uint16_t)fp_best_of_bins(f, B, B + span);
+        fp_mark_kid(f, par, child);
 #pragma unroll
         for (int k = 0; k < 4; ++k) f.r_t(k)[idx] = (uint16_t)t[k];
         s_tab[tab0 + j] = (uint16_t)idx;
@@ -1408,18 +1466,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     // look at the next key digit of every child), so the bound that decides which children get a record -- and will be split --
     // already includes them: bound = the crossing computed from all nodes down to that level, a lower bound of c*.
     const uint32_t *keys = f.keys();
-    for (int j = tid; j < K * kQtBinsPerStrip; j += kQtThreads)
-    {
-      // look-ahead for depth 3: every (strip, d1, d2, d3) bin of >= 2 corners is a node; its children = the digits-4 present
-      if (j % 5 == 4 || (j / 5) % 5 == 4 || (j / 25) % 5 == 4) continue;
-      const int lo = bin_start[j], cnt = bin_start[j + 1] - lo;
-      if (cnt < 2) continue;
-      const uint16_t *src = f.arr(0) + lo;
-      uint32_t mask = 0;
-      for (int i = 0; i < cnt; ++i) mask |= 1u << ((keys[src[i]] >> (kKeyStripShift - 12)) & 7u);
-      add_delta(cnt, __popc(mask & 15u) - 1);
-    }
-    fp_sync();
+    const uint8_t *resp = f.resp();
     int f0 = s_nrec; // first depth-3 record: read by every thread BEFORE the barriers of find_cross, i.e. before anybody allocates again
     find_cross();
     int bound = max(2, s_cstar); // no crossing yet: every node of >= 2 corners may matter
@@ -1434,11 +1481,14 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
         s_over = 1;
         continue;
       }
+      const uint32_t par = s_tab[6 * K + j / 5]; // the depth-2 prefix
       f.r_lo()[idx] = (uint16_t)lo;
       f.r_cnt()[idx] = (uint16_t)cnt;
-      f.r_par()[idx] = s_tab[6 * K + j / 5]; // the depth-2 prefix
+      f.r_par()[idx] = (uint16_t)par;
       f.r_meta()[idx] = (uint8_t)((3 << 4) | ((j % 5) << 1));
       f.r_state()[idx] = 0;
+      f.r_best()[idx] = f.bin_best[j] == kFpNone ? (uint16_t)0 : f.bin_best[j];
+      fp_mark_kid(f, par, (uint32_t)(j % 5));
     }
     fp_sync();
     if (tid == 0) s_f1 = s_nrec;
@@ -1463,9 +1513,15 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
         }
         int o0 = lo, o1 = o0 + c0, o2 = o1 + c1, o3 = o2 + c2;
         uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0; // digits (level + 2) present in each child
+        uint32_t best = 0, best_i = 0;
         for (int i = 0; i < cnt; ++i)
         {
           const uint32_t idx = src[i], key = keys[idx], dg = (key >> shift) & 7u;
+          if (level > 3)
+          { // its own best response, while the list is intact (depth-3 records took theirs from the bin)
+            const uint32_t r = resp[idx];
+            if (r > best || (r == best && r > 0 && idx < best_i)) best = r, best_i = idx;
+          }
           const uint32_t nx = level < 8 ? 1u << ((key >> (shift - 3)) & 7u) : 0u;
           if (dg == 0) dst[o0++] = (uint16_t)idx, m0 |= nx;
           if (dg == 1) dst[o1++] = (uint16_t)idx, m1 |= nx;
@@ -1476,6 +1532,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
         f.r_t(0)[v] = (uint16_t)c0, f.r_t(1)[v] = (uint16_t)c1, f.r_t(2)[v] = (uint16_t)c2, f.r_t(3)[v] = (uint16_t)c3;
         f.r_delta()[v] = (int8_t)(ne - 1);
         f.r_state()[v] = (uint8_t)(kFpActive | ((buf ^ 1) ? kFpKidsBuf : 0));
+        if (level > 3) f.r_best()[v] = (uint16_t)best_i;
         const int t[4] = {c0, c1, c2, c3};
         const uint32_t mk[4] = {m0, m1, m2, m3};
 #pragma unroll
@@ -1513,6 +1570,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
               f.r_par()[idx] = (uint16_t)v;
               f.r_meta()[idx] = (uint8_t)(((level + 1) << 4) | (k << 1) | (buf ^ 1));
               f.r_state()[idx] = 0;
+              f.r_kidrec()[v] |= (uint8_t)(1u << k);
             }
           }
           base += tk;
@@ -1542,20 +1600,6 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     tick(2);
   }
 
-  // responses by corner index over the (dead) keys: the leaf scans below stay in shared memory
-  fp_sync();
-  {
-    uint8_t *resp = f.resp();
-    for (int i0 = tid; i0 < n; i0 += 4 * kQtThreads)
-    {
-      uint32_t r[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) r[u] = i0 + u * kQtThreads < n ? kp[i0 + u * kQtThreads] : 0u;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i0 + u * kQtThreads < n) resp[i0 + u * kQtThreads] = (uint8_t)(r[u] >> 24);
-    }
-  }
   const int nrec = mode == kRun ? s_nrec : 1;
 
   if (mode == kRun)
@@ -1642,55 +1686,71 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
       if (!in_S(v)) continue;
       if ((int)f.r_cnt()[v] > cstar || (int)f.r_rank()[v] - 1 - R0 < k)
       {
-        f.r_state()[v] |= kFpPopped;
-        const uint32_t par = f.r_par()[v], child = (f.r_meta()[v] >> 1) & 7u;
-        atomicOr((unsigned int *)(f.r_kidpop() + (par & ~3u)), 1u << (8u * (par & 3u) + child)); // its children stand in for it
+        f.r_state()[v] |= kFpPopped; // its children stand in for it
       }
     }
     fp_sync();
     tick(3);
   }
 
-  // ---- V4: leaves (children of popped records -- the root included -- that did not pop), best response of each
+  // ---- V4: leaves = the children of popped records (the root included) that did not pop.  A child WITH a record announces itself
+  // (its best response was taken while its list was intact); children without one -- single corners, nodes below the bound -- are
+  // read by the parent: from the bins under a table record, from the (never overwritten) list of an unsplit child otherwise.
   if (mode != kEmpty)
   {
     const uint8_t *resp = f.resp();
+    auto emit = [&](uint32_t best_i, int cnt, uint32_t key) {
+      const int li = fp_alloc(&s_nleaf);
+      if (li < nc)
+      {
+        f.lf_best()[li] = (uint16_t)best_i;
+        f.lf_cnt()[li] = (uint16_t)cnt;
+        f.lf_I()[li] = key;
+      }
+    };
     for (int v = tid; v < nrec; v += kQtThreads)
     {
       const uint8_t st = f.r_state()[v];
-      if (!(st & kFpPopped)) continue;
-      const uint32_t kidpop = f.r_kidpop()[v];
-      const uint32_t prank = v == 0 ? 0u : (uint32_t)f.r_rank()[v];
-      const uint16_t *arr = f.arr((st & kFpKidsBuf) ? 1 : 0);
-      const int nk = v == 0 ? K : 4;
-      int base = v == 0 ? 0 : (int)f.r_lo()[v];
-      for (int k = 0; k < nk; ++k)
+      const uint32_t meta = f.r_meta()[v];
+      if (!(st & kFpPopped))
       {
-        int tk;
-        if (v == 0)
+        const uint32_t par = f.r_par()[v];
+        if (v > 0 && (f.r_state()[par] & kFpPopped)) emit(f.r_best()[v], f.r_cnt()[v], ((uint32_t)f.r_rank()[par] << 3) | ((meta >> 1) & 7u));
+        continue;
+      }
+      const uint32_t kidrec = f.r_kidrec()[v];
+      const uint32_t prank = (uint32_t)f.r_rank()[v]; // 0 for the root
+      const int depth = v == 0 ? -1 : (int)(meta >> 4);
+      if (depth <= 2)
+      {
+        // children = bin ranges: strips under the root, five times finer under every table record
+        const int span = depth < 0 ? kQtBinsPerStrip : (depth == 0 ? 25 : (depth == 1 ? 5 : 1));
+        const int B = depth < 0 ? 0 : (int)f.r_lo()[v], nk = depth < 0 ? K : 4;
+        for (int k = 0; k < nk; ++k)
         {
-          base = bin_start[k * kQtBinsPerStrip];
-          tk = bin_start[(k + 1) * kQtBinsPerStrip] - base;
+          const int b0 = B + k * span, tk = bin_start[b0 + span] - bin_start[b0];
+          if (tk > 0 && !((kidrec >> k) & 1u)) emit(fp_best_of_bins(f, b0, b0 + span), tk, (prank << 3) | (uint32_t)k);
         }
-        else
-          tk = f.r_t(k)[v];
-        if (tk > 0 && !((kidpop >> k) & 1u))
+      }
+      else
+      {
+        const uint16_t *arr = f.arr((st & kFpKidsBuf) ? 1 : 0);
+        int base = f.r_lo()[v];
+        for (int k = 0; k < 4; ++k)
         {
-          uint32_t best = 0, best_i = 0;
-          for (int pos = base; pos < base + tk; ++pos)
+          const int tk = f.r_t(k)[v];
+          if (tk > 0 && !((kidrec >> k) & 1u))
           {
-            const uint32_t idx = arr[pos], r = resp[idx];
-            if (r > best || (r == best && r > 0 && idx < best_i)) best = r, best_i = idx;
+            uint32_t best = 0, best_i = 0;
+            for (int pos = base; pos < base + tk; ++pos)
+            {
+              const uint32_t idx = arr[pos], r = resp[idx];
+              if (r > best || (r == best && r > 0 && idx < best_i)) best = r, best_i = idx;
+            }
+            emit(best_i, tk, (prank << 3) | (uint32_t)k);
           }
-          const int li = fp_alloc(&s_nleaf);
-          if (li < nc)
-          {
-            f.lf_best()[li] = (uint16_t)best_i;
-            f.lf_cnt()[li] = (uint16_t)tk;
-            f.lf_I()[li] = (prank << 3) | (uint32_t)k;
-          }
+          base += tk;
         }
-        base += tk;
       }
     }
   }
@@ -1714,7 +1774,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
     if (tid == 0) s_amax = 0ull;
     fp_sync();
   }
-  // flags (over the response bytes, which are dead now)
+  // flags (the key array is dead by now)
   uint32_t *flag = f.keys();
   for (int i = tid; i < n; i += kQtThreads) flag[i] = 0u;
   fp_sync();
@@ -1765,7 +1825,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   // carve shared memory
   const int node_cap = p.qt_node_cap;
   QtState q;
-  uint8_t *lists;
+  uint8_t *lists, *fast_tables;
   {
     uint8_t *w = smem;
     // node bounds: global scratch behind the level's lists (only nodes below the key depth ever read or write them)
@@ -1782,9 +1842,9 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
     w = smem + qt_pool_bytes(node_cap) + qt_align16((size_t)p.qt_cell_cap * sizeof(int));
     q.bhead = (uint16_t *)w;
     q.btail = q.bhead + kQtBuckets;
-    w += qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t));
-    q.big = (uint16_t *)w;
-    w += qt_align16((size_t)p.qt_big_cap * sizeof(uint16_t));
+    q.big = (uint16_t *)(w + qt_align16((size_t)2 * kQtBuckets * sizeof(uint16_t)));
+    fast_tables = w; // the loop-free path's tables share this region with the two above
+    w += qt_union_bytes(node_cap, p.qt_big_cap);
     lists = w;
     q.nbig = 0;
     q.seq_ctr = 0;
@@ -1803,7 +1863,8 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   // ---- Phase B: gather the cell lists (cell-row-major, row-major inside a cell == the reference's detection order),
   // one thread per corner: binary search of the corner's cell in the offsets, then load + key
   __syncthreads();
-  auto gather = [&](bool identity_order) {
+  uint8_t *resp8 = lists + 8 * (size_t)p.qt_smem_cap; // FAST score by corner (loop-free path)
+  auto gather = [&]() {
     const uint32_t *cl = p.cell_list + (size_t)img * p.cell_entries;
     for (int i = tid; i < n; i += kQtThreads)
     {
@@ -1819,13 +1880,13 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
       const uint32_t e = cl[cells[lo_c].slot + (i - cell_off[lo_c])];
       kp[i] = e;
       if (use_keys) keys[i] = qt_make_key(e, cols, K, L.roi_h);
-      if (identity_order) ia16[i] = (uint16_t)i;
+      if (in_smem) resp8[i] = (uint8_t)(e >> 24);
     }
   };
 
   // ---- Phase B': root.  With need <= 1 the reference never pops the root (:151); otherwise its first pop is the root,
   // whose children are the strips: partition the corners by strip with the whole block (stable: K ordered scans).
-  gather(false);
+  gather();
   const bool split_root_here = use_keys && need > 1;
   const bool presort = split_root_here && K <= kQtMaxBinStrips;
   auto root_partition = [&]() {
@@ -1928,11 +1989,12 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   bool done = false;
   if (p.qt_fast && presort && in_smem)
   {
-    uint8_t *scr = lists + qt_align16((size_t)p.qt_smem_cap * 8);
-    done = qt_fast_path(smem, lists, (int *)scr, scr + 2048, s_bin_start, p.qt_smem_cap, node_cap, K, kp, n, need, s_warp, p.qt_stats);
+    uint8_t *lf = fast_tables + 2048;
+    done = qt_fast_path(smem, lists, (int *)fast_tables, lf, (uint16_t *)(lf + qt_align16((size_t)node_cap * 8)), s_bin_start, p.qt_smem_cap, node_cap, K, n, need,
+                        s_warp, p.qt_stats);
     if (!done)
     { // start over for the sequential loop (the loop-free path reuses the key / index arrays)
-      gather(false);
+      gather();
       root_partition();
     }
   }
