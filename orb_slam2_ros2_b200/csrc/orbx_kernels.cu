@@ -1242,17 +1242,19 @@ struct QtFast
   __device__ __forceinline__ uint32_t *keys() const { return (uint32_t *)lists; }
   __device__ __forceinline__ uint16_t *arr(int buf) const { return (uint16_t *)(lists + (4 + 2 * (size_t)buf) * cap); }
   __device__ __forceinline__ const uint8_t *resp() const { return lists + 8 * (size_t)cap; } // response (FAST score) by corner
-  __device__ __forceinline__ uint16_t *u16(int k) const { return (uint16_t *)pool + (size_t)k * nc; }
+  // layout: kidrec u8[nc rounded up to 16] (first: it takes 32-bit atomics) | nine u16 arrays | three u8 arrays
+  __device__ __forceinline__ size_t pad() const { return ((size_t)nc + 15) & ~(size_t)15; }
+  __device__ __forceinline__ uint16_t *u16(int k) const { return (uint16_t *)(pool + pad()) + (size_t)k * nc; }
   __device__ __forceinline__ uint16_t *r_lo() const { return u16(0); }   // first position of its corners (table records: first bin)
   __device__ __forceinline__ uint16_t *r_cnt() const { return u16(1); }
   __device__ __forceinline__ uint16_t *r_par() const { return u16(2); }
   __device__ __forceinline__ uint16_t *r_rank() const { return u16(3); }
   __device__ __forceinline__ uint16_t *r_best() const { return u16(4); } // best-response corner, taken while its list was intact
   __device__ __forceinline__ uint16_t *r_t(int k) const { return u16(5 + k); }
-  __device__ __forceinline__ uint8_t *r_kidrec() const { return pool + 18 * (size_t)nc; } // children that have a record of their own
-  __device__ __forceinline__ uint8_t *r_meta() const { return pool + 19 * (size_t)nc; }   // depth << 4 | child << 1 | buffer of its corners
-  __device__ __forceinline__ int8_t *r_delta() const { return (int8_t *)(pool + 20 * (size_t)nc); }
-  __device__ __forceinline__ uint8_t *r_state() const { return pool + 21 * (size_t)nc; }
+  __device__ __forceinline__ uint8_t *r_kidrec() const { return pool; } // children that have a record of their own
+  __device__ __forceinline__ uint8_t *r_meta() const { return pool + pad() + 18 * (size_t)nc; }   // depth << 4 | child << 1 | buffer of its corners
+  __device__ __forceinline__ int8_t *r_delta() const { return (int8_t *)(pool + pad() + 19 * (size_t)nc); }
+  __device__ __forceinline__ uint8_t *r_state() const { return pool + pad() + 20 * (size_t)nc; }
   __device__ __forceinline__ uint32_t *lf_I() const { return (uint32_t *)lf; }
   __device__ __forceinline__ uint16_t *lf_best() const { return (uint16_t *)(lf + 4 * (size_t)nc); }
   __device__ __forceinline__ uint16_t *lf_cnt() const { return (uint16_t *)(lf + 6 * (size_t)nc); }
