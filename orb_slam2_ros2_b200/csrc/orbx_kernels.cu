@@ -1450,8 +1450,7 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
         f.r_par()[idx] = (uint16_t)par;
         f.r_meta()[idx] = (uint8_t)((d << 4) | (child << 1));
         f.r_delta()[idx] = (int8_t)(ne - 1);
-        f.r_state()[idx] = kFpActive;
-        f.r_best()[idx] = (uint16_t)fp_best_of_bins(f, B, B + span);
+        f.r_state()[idx] = kFpActive; // (its best response, should it end up as a leaf, is read off the bins then)
         fp_mark_kid(f, par, child);
 #pragma unroll
         for (int k = 0; k < 4; ++k) f.r_t(k)[idx] = (uint16_t)t[k];
@@ -1717,7 +1716,13 @@ __device__ __noinline__ bool qt_fast_path(uint8_t *pool, uint8_t *lists, int *sc
       if (!(st & kFpPopped))
       {
         const uint32_t par = f.r_par()[v];
-        if (v > 0 && (f.r_state()[par] & kFpPopped)) emit(f.r_best()[v], f.r_cnt()[v], ((uint32_t)f.r_rank()[par] << 3) | ((meta >> 1) & 7u));
+        if (v > 0 && (f.r_state()[par] & kFpPopped))
+        {
+          const int depth = (int)(meta >> 4);
+          const int B = f.r_lo()[v], span = depth == 0 ? 125 : (depth == 1 ? 25 : 5); // (table records only)
+          const uint32_t best_i = depth <= 2 ? fp_best_of_bins(f, B, B + span) : (uint32_t)f.r_best()[v];
+          emit(best_i, f.r_cnt()[v], ((uint32_t)f.r_rank()[par] << 3) | ((meta >> 1) & 7u));
+        }
         continue;
       }
       const uint32_t kidrec = f.r_kidrec()[v];
