@@ -440,15 +440,14 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
     launch_orient_brief(p, 2 * nf, s);
   }
   {
-    NvtxRange q("orbx:stereo_match");
-    launch_rowindex(p, nf, s);
-    launch_stereo(p, nf, s);
+    NvtxRange q("orbx:frame_index"); // createRowIndexDB of the right keypoints + initGrid of the left ones, one launch
+    launch_frame_index(p, nf, 2, true, s);
   }
   {
-    NvtxRange q("orbx:init_grid");
-    launch_grid(p, nf, 2, s);
+    NvtxRange q("orbx:stereo_match");
+    launch_stereo(p, nf, s);
   }
-  c->launches += 7;
+  c->launches += 6;
   ORBX_CUDA(c, cudaGetLastError());
   return ORBX_OK;
 }
@@ -700,6 +699,11 @@ extern "C"
       c->cfg.pattern = nullptr; // not retained
       if ((rc = alloc_buffers(c))) break;
       if ((rc = build_level_maps(c))) break;
+      if (frame_index_configure(c->p) != 0)
+      {
+        rc = fail(c, ORBX_ERR_CUDA, "cudaFuncSetAttribute(frame_index_kernel, MaxDynamicSharedMemorySize)");
+        break;
+      }
       if (quadtree_configure(c->qt_smem) != 0)
       {
         rc = fail(c, ORBX_ERR_CUDA, "cudaFuncSetAttribute(quadtree_kernel, MaxDynamicSharedMemorySize)");
@@ -873,7 +877,7 @@ extern "C"
 
   const char *orbx_stage_name(int stage)
   {
-    static const char *names[ORBX_N_STAGES] = {"pyramid_blur", "fast_cells", "quadtree", "orient_brief", "row_index", "stereo_match"};
+    static const char *names[ORBX_N_STAGES] = {"pyramid_blur", "fast_cells", "quadtree", "orient_brief", "frame_index", "stereo_match"};
     return (stage >= 0 && stage < ORBX_N_STAGES) ? names[stage] : "";
   }
 
@@ -902,12 +906,11 @@ extern "C"
     ORBX_CUDA(c, cudaEventRecord(ev[3], c->stream));
     launch_orient_brief(p, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[4], c->stream));
-    launch_rowindex(p, n_frames, c->stream);
+    launch_frame_index(p, n_frames, 2, true, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[5], c->stream));
     launch_stereo(p, n_frames, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[6], c->stream));
-    launch_grid(p, n_frames, 2, c->stream);
-    c->launches += 7;
+    c->launches += 6;
     ORBX_CUDA(c, cudaGetLastError());
     ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int i = 0; i < ORBX_N_STAGES; ++i) ORBX_CUDA(c, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
@@ -938,7 +941,7 @@ extern "C"
     if (rc) return rc;
     ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)n_frames * sizeof(int), c->stream));
     launch_rgbd(p, n_frames, c->stream);
-    launch_grid(p, n_frames, 1, c->stream);
+    launch_frame_index(p, n_frames, 1, false, c->stream);
     c->launches += 2;
     ORBX_CUDA(c, cudaGetLastError());
     c->last_images = n_frames;

@@ -217,10 +217,10 @@ const void *pyramid_kernel_symbol(); // host handle of the pyramid kernel (to fi
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
 void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
-void launch_rowindex(const Params &p, int n_frames, cudaStream_t s);
 void launch_stereo(const Params &p, int n_frames, cudaStream_t s);
 void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
-void launch_grid(const Params &p, int n_frames, int image_stride, cudaStream_t s);
+void launch_frame_index(const Params &p, int n_frames, int image_stride, bool with_rowindex, cudaStream_t s); // row index (stereo) + initGrid
+int frame_index_configure(const Params &p); // opt in to large dynamic shared memory when the configuration needs it
 void launch_area_match(const Params &p, const AreaArgs &a, int n_frames, cudaStream_t s);
 void launch_verify_angle(const VerifyArgs &a, cudaStream_t s);
 void launch_bow_match(const BowMatchArgs &a, cudaStream_t s);

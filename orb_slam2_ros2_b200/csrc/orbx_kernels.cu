@@ -2373,11 +2373,9 @@ void launch_orient_brief(const Params &p, int n_images, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kRowThreads = 256;
 
-__global__ void __launch_bounds__(kRowThreads) rowindex_kernel(const Params p)
+__device__ __forceinline__ void rowindex_body(const Params &p, int frame, int *s_cnt /* [height + 1] */, int *s_warp)
 {
-  extern __shared__ int s_cnt[]; // [height + 1]
-  __shared__ int s_warp[kRowThreads / 32];
-  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int H = p.height;
   const int imgR = 2 * frame + 1;
   const int nR = p.n_kps[imgR];
@@ -2418,10 +2416,7 @@ __global__ void __launch_bounds__(kRowThreads) rowindex_kernel(const Params p)
   }
 }
 
-void launch_rowindex(const Params &p, int n_frames, cudaStream_t s)
-{
-  rowindex_kernel<<<n_frames, kRowThreads, (size_t)(p.height + 1) * sizeof(int), s>>>(p);
-}
+// (launched together with the grid of the left keypoints: frame_index_kernel below)
 
 // ------------------------------------------------------------------------------------------------------------------
 // K5: stereo association.  One warp per left keypoint: row-band + x-range scan over the right keypoints, Hamming argmin
@@ -2635,11 +2630,10 @@ void launch_rgbd(const Params &p, int n_frames, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kGridThreads = 256;
 
-__global__ void __launch_bounds__(kGridThreads) grid_kernel(const Params p, int image_stride)
+__device__ __forceinline__ void grid_body(const Params &p, int frame, int image_stride, int *s_cell /* [n_cells + 1] */, uint16_t *s_ent /* [n_features] */,
+                                          int *s_warp)
 {
-  extern __shared__ int s_cell[]; // [n_cells + 1]
-  __shared__ int s_warp[kGridThreads / 32];
-  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int img = frame * image_stride;
   const int nc = p.grid_rows * p.grid_cols;
   const int n = p.n_kps[img];
@@ -2676,30 +2670,66 @@ __global__ void __launch_bounds__(kGridThreads) grid_kernel(const Params p, int 
   for (int i = tid; i < n; i += kGridThreads)
   {
     const int c = cell_of(i);
-    if (c >= 0) entries[atomicAdd(&s_cell[c], 1)] = (uint16_t)i;
+    if (c >= 0) s_ent[atomicAdd(&s_cell[c], 1)] = (uint16_t)i;
   }
   __syncthreads();
-  // ascending index order inside every cell (insertion sort; a cell holds a few dozen keypoints at most)
+  // ascending index order inside every cell (insertion sort in shared memory; a cell holds a few dozen keypoints at most):
+  // after the scatter s_cell[c] is the END of cell c, i.e. the start of cell c + 1
   for (int c = tid; c < nc; c += kGridThreads)
   {
-    const int b = start[c], e = s_cell[c];
+    const int b = c == 0 ? 0 : s_cell[c - 1], e = s_cell[c];
     for (int i = b + 1; i < e; ++i)
     {
-      const uint16_t v = entries[i];
+      const uint16_t v = s_ent[i];
       int j = i - 1;
-      while (j >= b && entries[j] > v)
+      while (j >= b && s_ent[j] > v)
       {
-        entries[j + 1] = entries[j];
+        s_ent[j + 1] = s_ent[j];
         --j;
       }
-      entries[j + 1] = v;
+      s_ent[j + 1] = v;
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < total; i += kGridThreads) entries[i] = s_ent[i];
+}
+
+// K5a + K7 in ONE launch: blocks [0, n_frames) build the row index of the right keypoints (stereo frames only), the next n_frames
+// blocks the 64x48-px grid of the left keypoints.  Both are one-CTA-per-frame jobs; side by side they cost the longer of the two.
+static_assert(kRowThreads == kGridThreads, "frame_index_kernel");
+__global__ void __launch_bounds__(kGridThreads) frame_index_kernel(const Params p, int n_frames, int image_stride, int with_rowindex)
+{
+  extern __shared__ __align__(16) int s_dyn[];
+  __shared__ int s_warp[kGridThreads / 32];
+  const int b = blockIdx.x;
+  if (with_rowindex && b < n_frames)
+    rowindex_body(p, b, s_dyn, s_warp);
+  else
+  {
+    const int frame = with_rowindex ? b - n_frames : b;
+    const int nc = p.grid_rows * p.grid_cols;
+    grid_body(p, frame, image_stride, s_dyn, reinterpret_cast<uint16_t *>(s_dyn + nc + 1), s_warp);
   }
 }
 
-void launch_grid(const Params &p, int n_frames, int image_stride, cudaStream_t s)
+static size_t frame_index_smem(const Params &p)
 {
-  grid_kernel<<<n_frames, kGridThreads, (size_t)(p.grid_rows * p.grid_cols + 1) * sizeof(int), s>>>(p, image_stride);
+  const size_t row = (size_t)(p.height + 1) * sizeof(int);
+  const size_t grid = (size_t)(p.grid_rows * p.grid_cols + 1) * sizeof(int) + (size_t)p.n_features * sizeof(uint16_t);
+  return row > grid ? row : grid;
+}
+
+int frame_index_configure(const Params &p)
+{
+  static SmemOptIn state;
+  const size_t bytes = frame_index_smem(p);
+  return bytes > 48 * 1024 ? raise_dynamic_smem(frame_index_kernel, state, bytes) : 0;
+}
+
+// stereo frames: row index + grid; mono / RGB-D frames (image_stride 1): grid only
+void launch_frame_index(const Params &p, int n_frames, int image_stride, bool with_rowindex, cudaStream_t s)
+{
+  frame_index_kernel<<<with_rowindex ? 2 * n_frames : n_frames, kGridThreads, frame_index_smem(p), s>>>(p, n_frames, image_stride, with_rowindex ? 1 : 0);
 }
 
 } // namespace orbx

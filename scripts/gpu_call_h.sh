@@ -12,5 +12,5 @@ print("value %.0f e2e %.0f" % (d["value"], d["e2e"]["value"]), {k: round(v,3) fo
 print("   latency", d["latency"])
 print("   hd", d["configs"]["hd_1080p"]["value"], d["configs"]["hd_1080p"]["stage_ms"], d["configs"]["hd_1080p"]["p50_ms_device_single_pair"])
 print("   sweep", {k: v["p50_ms_device_graph"] for k, v in d["configs"]["latency_sweep"]["n_features"].items()})
-print("   check", d["check"]["gathered_checksum"], d["check"]["oracle_frame0"]["descriptor_bit_flips"])
+print("   check", d["check"]["gathered_checksum"])
 PY
