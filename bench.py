@@ -526,9 +526,23 @@ def run_gpu_arm(args):
             dist.broadcast_object_list(ids, src=0)
             comm = api.Communicator(ctx, rank, world, ids[0], F)
             if args.transport == "peer":
+                # descriptor gather as stores into every rank's gathered array (CUDA-IPC peer pointers) from the kernel that packs the
+                # records; if any rank cannot map its peers, every rank stays on the NCCL send/recv pieces
+                try:
+                    handle, ok = comm.ipc_handle(), 1
+                except Exception:
+                    handle, ok = b"", 0
                 handles = [None] * world
-                dist.all_gather_object(handles, comm.ipc_handle())
-                comm.open_peers(handles)
+                dist.all_gather_object(handles, (handle, ok))
+                if all(h[1] for h in handles):
+                    try:
+                        comm.open_peers([h[0] for h in handles])
+                    except Exception:
+                        ok = 0
+                oks = [None] * world
+                dist.all_gather_object(oks, ok)
+                if not all(oks):
+                    raise SystemExit("bench.py: peer-memory transport could not be set up on every rank; rerun with --transport nccl")
     finally:
         if world > 1:
             sys.stdout.flush()
@@ -778,7 +792,9 @@ def main():
     ap.add_argument("--frames", type=int, default=SEQ_FRAMES, help="frames of the sequence (one step = one pass over all of them, sharded over the GPUs)")
     ap.add_argument("--batch", type=int, default=64, help="device slots per GPU (frames in flight)")
     ap.add_argument("--pool", type=int, default=256, help="distinct synthetic pairs the sequence cycles through")
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "peer"], help="descriptor gather at N > 1")
+    ap.add_argument("--transport", default="peer", choices=["nccl", "peer"],
+                    help="descriptor gather at N > 1: peer = stores through CUDA-IPC peer pointers fused into the record-packing kernel (NCCL carries the "
+                         "closing barrier), nccl = grouped ncclSend/ncclRecv pieces on a side stream")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matchers", action="store_true", help="skip the secondary tracking-matcher / serialisation / bag-of-words measurements")

@@ -1,0 +1,20 @@
+#!/bin/bash
+# 8-GPU call: platform ceiling + the sequence bench at N = 8 (both transports) and N = 4
+mkdir -p gpurun_out
+nvidia-smi topo -m > gpurun_out/s_topo.txt 2>&1
+R="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+timeout 300 $R --nproc-per-node 8 --master-port 29601 scripts/pcie_ceiling.py > gpurun_out/s_ceiling8.json 2> gpurun_out/s_ceiling8.err; cat gpurun_out/s_ceiling8.json
+timeout 300 $R --nproc-per-node 4 --master-port 29602 scripts/pcie_ceiling.py > gpurun_out/s_ceiling4.json 2> gpurun_out/s_ceiling4.err; cat gpurun_out/s_ceiling4.json
+for cfg in "8 peer" "8 nccl" "4 peer"; do
+  set -- $cfg
+  timeout 400 $R --nproc-per-node $1 --master-port 2961$1 bench.py --gpus $1 --steps 20 --warmup 5 --transport $2 > gpurun_out/s_bench$1_$2.json 2> gpurun_out/s_bench$1_$2.err
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/s_bench$1_$2.json"))
+    print("N=$1 $2: value %.0f e2e %.0f ms/step %.2f" % (d["value"], d["e2e"]["value"], d["ms_per_step"]), d["check"]["gathered_checksum"], d["check"]["gathered_checksum_equal_on_all_ranks"], d["check"]["sampled_frames_vs_single_frame_call"]["identical"], d["clocks"])
+except Exception as e:
+    print("N=$1 $2 failed", e)
+PY
+  tail -2 gpurun_out/s_bench$1_$2.err
+done
