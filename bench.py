@@ -682,6 +682,41 @@ def run_gpu_arm(args):
         check["host_records_equal_device_records"] = bool(torch.equal(h_rec[:n_local], d_rec[:n_local].cpu()))
     h2d = 2 * F * fsz
     d2h = F * rs
+
+    # ---- platform ceiling of `e2e`: the same bytes as bare pinned-memory copies (8-frame chunks, H2D and D2H on two streams, all
+    # ranks at once, no kernels).  `e2e` cannot exceed what the box moves between host and device memory.
+    ceiling = None
+    if n_local >= 64 or world > 1:
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        d_in = torch.empty((2, 64, fsz), dtype=torch.uint8, device="cuda")
+        d_out = torch.empty((64, rs), dtype=torch.uint8, device="cuda")
+        hl, hr, hrec = h_left.view(-1, fsz), h_right.view(-1, fsz), h_rec
+
+        def bare_pass():
+            for f0 in range(0, n_local, 8):
+                nf = min(8, n_local - f0)
+                o = (f0 // 8 % 8) * 8
+                with torch.cuda.stream(s_in):
+                    d_in[0, o:o + nf].copy_(hl[f0:f0 + nf], non_blocking=True)
+                    d_in[1, o:o + nf].copy_(hr[f0:f0 + nf], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    hrec[f0:f0 + nf].copy_(d_out[o:o + nf], non_blocking=True)
+            torch.cuda.synchronize()
+
+        bare_pass()
+        barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            bare_pass()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cfps = reps * F / float(t.item())
+        ceiling = {"value": cfps, "unit": UNIT, "h2d_GBps": cfps * 2 * fsz / 1e9, "d2h_GBps": cfps * rs / 1e9,
+                   "what": "bare cudaMemcpyAsync of the same pinned buffers (8-frame chunks, H2D and D2H on two streams, all ranks at once, no kernels)"}
+        del d_in, d_out
     ctx.set_stream(stream.cuda_stream)
 
     # ---- per-stage device times of one 64-frame slot batch -> roofline of the dominant kernel ------------------------------
@@ -770,6 +805,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "platform_ceiling": ceiling, "fraction_of_platform_ceiling": (e2e_value / ceiling["value"]) if ceiling else None,
                     "note": "the same orbx_sequence_stereo call with every rank's block in pinned host memory and its records landing in pinned host memory; "
                             "the gathered descriptors stay in HBM (they are consumed there)"},
             "gpu_launches": int(launches), "transport": (comm.info()["transport"] if comm else 0), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
