@@ -230,6 +230,28 @@ def test_stereo_matches_oracle(oracle, cfg):
     ctx.close()
 
 
+@pytest.mark.parametrize("cfg", [STEREO[0], STEREO[5]], ids=["K2000_d17", "T1000_d17"])
+def test_stereo_matches_the_compiled_reference(oracle, have_ref, template_path, cfg):
+    """the CUDA path against oracle/_ref/libref.so DIRECTLY (the reference's own ORBExtractor.cc / ORBMatcher.cc translation
+    units, prebuilt where /root/reference was mounted and shipped with the snapshot) -- not through the restatement or goldens"""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libref.so is not in this tree")
+    name, c, nf, seed, disp = cfg
+    cam = api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"])
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], seed, disp)
+    oracle.ref_reset()
+    bf = oracle.ref_set_camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"], None)
+    ref = oracle.ref_stereo(left, right, template_path, nf, c["n_levels"], c["scale_factor"])
+    assert ref["status"] == 0
+    ctx = api.Context(c["width"], c["height"], nf, c["n_levels"], c["scale_factor"], camera=cam)
+    r = ctx.stereo_frame(left, right)
+    _cmp_kps(r.kps_left, ref["kl"], r.desc_left, ref["dl"], name + " left vs libref")
+    _cmp_kps(r.kps_right, ref["kr"], r.desc_right, ref["dr"], name + " right vs libref")
+    assert r.n_matches == ref["n_matches"] and float(cam.bf) == float(bf)
+    assert np.abs(r.u_right - ref["u_right"]).max() <= 1e-3 and np.abs(r.depth - ref["depth"]).max() <= 1e-3 * np.abs(ref["depth"]).max()
+    ctx.close()
+
+
 def test_stereo_with_distortion_uses_undistorted_left(oracle):
     """Frame.cc:106 undistorts the left keypoints before searchByStereo; mild distortion keeps SAD windows inside"""
     c = synth.KITTI
