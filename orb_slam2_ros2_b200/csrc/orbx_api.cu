@@ -140,9 +140,18 @@ int build_tables(orbx_ctx *c)
       build_resize_axis(g.width, L.w, true, tab_ofs, tab_coef);
       L.tab_y = (int)tab_ofs.size();
       build_resize_axis(g.height, L.h, false, tab_ofs, tab_coef);
+      // pyramid_levels_kernel fetches the taps of two adjacent columns with one aligned 8-byte window when that always works
+      L.pair_window = 1;
+      auto eff = [&](int gx) { const int sx = tab_ofs[L.tab_x + gx]; return sx + 1 > g.width - 1 ? g.width - 2 : sx; };
+      for (int gx = 0; gx + 1 < L.w; ++gx)
+      {
+        const int a = eff(gx), b = eff(gx + 1);
+        if (std::max(a, b) + 1 - (std::min(a, b) & ~3) > 7) L.pair_window = 0;
+      }
     }
     for (int y0 = 0; y0 < L.h; y0 += kTileH)
       for (int x0 = 0; x0 < L.w; x0 += kTileW) c->tiles.push_back(Tile{l, x0, y0, 0});
+    if (l == 0) c->n_tiles0 = (int)c->tiles.size();
 
     // FAST cell grid (:334-362)
     const int maxBX = L.w - kEdge, maxBY = L.h - kEdge;
@@ -221,6 +230,7 @@ int build_tables(orbx_ctx *c)
   p.ini_th = g.ini_th_fast;
   p.min_th = g.min_th_fast;
   p.n_tiles = (int)c->tiles.size();
+  p.n_tiles0 = c->n_tiles0;
   p.n_cells = (int)c->cells.size();
   p.width = g.width;
   p.height = g.height;
@@ -447,7 +457,7 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
     NvtxRange q("orbx:stereo_match");
     launch_stereo(p, nf, s);
   }
-  c->launches += 6;
+  c->launches += 5 + kPyramidLaunches;
   ORBX_CUDA(c, cudaGetLastError());
   return ORBX_OK;
 }
@@ -567,7 +577,7 @@ int run_extract(orbx_ctx *c, const Params &p, int n_images)
   launch_fast(p, c->maps, n_images, c->stream);
   launch_quadtree(p, n_images, c->qt_smem, c->stream);
   launch_orient_brief(p, n_images, c->stream);
-  c->launches += 4;
+  c->launches += 3 + kPyramidLaunches;
   ORBX_CUDA(c, cudaGetLastError());
   return ORBX_OK;
 }
@@ -910,7 +920,7 @@ extern "C"
     ORBX_CUDA(c, cudaEventRecord(ev[5], c->stream));
     launch_stereo(p, n_frames, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[6], c->stream));
-    c->launches += 6;
+    c->launches += 5 + kPyramidLaunches;
     ORBX_CUDA(c, cudaGetLastError());
     ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int i = 0; i < ORBX_N_STAGES; ++i) ORBX_CUDA(c, cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));

@@ -43,6 +43,7 @@ struct Level
   int quota;        // mvnFeatures[level]
   int tab_x, tab_y; // offsets into the resize tables (unused for level 0)
   int area2x;       // exact 2x2 decimation: cv::resize re-routes INTER_LINEAR to INTER_AREA
+  int pair_window;  // resize: the taps of two adjacent columns always lie inside one aligned 8-byte window of a level-0 row
   // FAST cell grid (src/ORBExtractor.cc:334-343)
   int n_cols, n_rows, w_cell, h_cell;
   int fast_box_h;   // rows of the TMA box that fetches one FAST patch of this level (its tallest patch)
@@ -88,6 +89,7 @@ struct Params
 {
   int n_levels, n_features, ini_th, min_th;
   int n_tiles, n_cells;
+  int n_tiles0; // tiles of level 0 (first in the tile table): pyramid_level0_kernel; the rest: pyramid_levels_kernel
   int width, height;
   int stereo; // images are interleaved left/right pairs
   const Level *levels;
@@ -211,9 +213,10 @@ struct BowArgs
   int *fv_nodes, *fv_start /* [frame][n_features + 1] */, *fv_feats, *n_fv;
 };
 
-// launchers (orbx_kernels.cu / orbx_match.cu / orbx_serialize.cu / orbx_bow.cu); every call enqueues exactly one kernel on `s`
-void launch_pyramid(const Params &p, int n_images, cudaStream_t s);
-const void *pyramid_kernel_symbol(); // host handle of the pyramid kernel (to find its node in a captured graph)
+// launchers (orbx_kernels.cu / orbx_match.cu / orbx_serialize.cu / orbx_bow.cu); every call enqueues exactly one kernel on `s` (launch_pyramid: two)
+constexpr int kPyramidLaunches = 2;
+void launch_pyramid(const Params &p, int n_images, cudaStream_t s); // kPyramidLaunches kernels: level 0, then the resized levels
+const void *pyramid_kernel_symbol(); // host handle of the level-0 pyramid kernel, the only reader of the caller's images (to find its node in a captured graph)
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
 void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);

@@ -14,6 +14,7 @@ struct orbx_ctx
   int n_img_max = 0;
   std::vector<orbx::Level> levels;
   std::vector<orbx::Tile> tiles;
+  int n_tiles0 = 0; // level-0 tiles (first in `tiles`)
   std::vector<orbx::Cell> cells;
   orbx::Params p;            // template: geometry + base pointers
   size_t qt_smem = 0;

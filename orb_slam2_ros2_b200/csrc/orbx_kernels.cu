@@ -69,8 +69,17 @@ template <int NT> __device__ __forceinline__ int block_exclusive_scan(int v, int
 // K1: pyramid level (resize from level 0) fused with the 7x7 Gaussian blur.  One CTA per kTileW x kTileH output tile.
 //   cv::resize INTER_LINEAR 8UC1: 11-bit coefficient tables (built on the host exactly like OpenCV does), int32 maths.
 //   cv::GaussianBlur 7x7 sigma 2: 8.8 fixed-point kernel {18,34,48,56,48,34,18}, u16 rows, (v + 32768) >> 16.
-//   Stage A  thread <-> tile column (coefficients in registers), loop over rows: 4 byte gathers from level 0 per pixel
-//            (second tap at an immediate +1, vertical weights by multiply-high, no clamp: the weights sum to 2048)
+// Two launches per batch:
+//   pyramid_level0_kernel   level 0 = the caller's image.  Stage A copies the tile (+ 3-px halo) with aligned word loads
+//                           (two LDG.32 + one funnel shift per 4 pixels whatever the row's alignment; the caller's rows
+//                           have an arbitrary stride) into shared memory; the level-0 image lands in the 16-byte
+//                           aligned pyramid buffer.
+//   pyramid_levels_kernel   levels >= 1, resized FROM THAT ALIGNED COPY (L2-resident): a row of it starts 16-byte aligned,
+//                           so a thread's word alignment is the same in every row.  Stage A: thread <-> two adjacent
+//                           columns; the 2 x 2 bytes they need from a source row lie inside one aligned 8-byte window
+//                           (scale < 3), fetched with two LDG.32; each horizontal tap pair is one PRMT (per-thread
+//                           constant selector) + one DP2A against the packed 11-bit coefficients; vertical weights by
+//                           multiply-high (no clamp: the weights sum to 2048).
 //   Stage B  horizontal pass on packed bytes: 3 aligned LDS.32 + funnel shifts + 8 DP4A per 4 pixels -> u16
 //   Stage C  vertical pass: one item per 4 columns x 2 rows, LDS.128 of vertically paired u16, DP2A (exact integers)
 //   The tile is stored with pixel 0 at byte 16 of a 96-byte row, so the level image leaves as LDS.128 / STG.128.
@@ -79,217 +88,330 @@ constexpr int kSrcW = kTileW + 2 * kHalo;      // 70
 constexpr int kSrcH = kTileH + 2 * kHalo;      // tile rows + halo
 constexpr int kSrcPitch = 96;                  // bytes, 16-byte multiple
 constexpr int kSrcCol0 = 13;                   // byte of source column 0 inside a row: tile pixel 0 sits at byte 16 (LDS.128 rows)
-constexpr int kColStride = 72;                 // stage A: thread <-> source column, kColGroups row-interleaved groups
-constexpr int kColGroups = kPyrThreads / kColStride;
+constexpr int kSrcWord0 = 3;                   // first word of a row that holds tile (+ halo) pixels: bytes 12..83 = columns -4..67
+constexpr int kSrcWords = 18;
+constexpr int kPairs = 36;                     // stage A of the resized levels: byte pairs 12 + 2q, 13 + 2q <-> columns 2q - 4, 2q - 3
+constexpr int kPairRows = kPyrThreads / kPairs; // 7 rows per pass (252 threads)
+constexpr int kWordRows = kPyrThreads / kSrcWords; // level 0: 14 rows per pass (252 threads)
 
-__global__ void __launch_bounds__(kPyrThreads) pyramid_blur_kernel(const Params p)
+struct PyrShared
 {
-  __shared__ __align__(16) uint8_t s_src[kSrcH * kSrcPitch];
-  __shared__ __align__(16) uint16_t s_h[kSrcH * kTileW];
+  __align__(16) uint8_t src[kSrcH * kSrcPitch];
+  __align__(16) uint16_t h[kSrcH * kTileW];
   // per source row: byte offsets of the two level-0 rows and the vertical coefficients pre-shifted by 16, so that
-  // (b * (h >> 4)) >> 16 is one multiply-high (level 0 / exact 2x decimation: .z = 0xff keep-mask instead)
-  __shared__ __align__(16) uint4 s_row[kSrcH];
+  // (b * (h >> 4)) >> 16 is one multiply-high (level 0: .x = row offset, .z = 1 when the row may be read with word loads)
+  __align__(16) uint4 row[kSrcH];
+};
 
-  const Tile t = p.tiles[blockIdx.x];
-  const int img = blockIdx.y;
-  const Level &L = p.levels[t.level];
-  const int lw = L.w, lh = L.h, pitch = L.pitch;
-  const uint8_t *__restrict__ src = input_image(p, img);
-  const uint32_t sstride = (uint32_t)p.in_stride;
-  const int W = p.width, H = p.height;
-  const int level = t.level, area2x = L.area2x;
-  const int tid = threadIdx.x;
+// rows of the tile (+ halo) that exist: rows beyond level row lh + kHalo - 1 are never consumed
+__device__ __forceinline__ int tile_rows(const Tile &t, int lh) { return min(kSrcH, lh + 2 * kHalo - t.y0); }
 
-  // Rows beyond the level + halo are never used; they read row 0 with zero weights / a zero mask so that stage A has no
-  // per-row branch and the loads of several rows are in flight together.
-  if (tid < kSrcH)
-  {
-    const int ry = t.y0 + tid - kHalo;
-    uint32_t o0 = 0, o1 = 0, z = 0, w = 0;
-    if (ry < lh + kHalo)
-    {
-      const int gy = refl101(ry, lh);
-      if (level == 0)
-      {
-        o0 = o1 = (uint32_t)gy * sstride;
-        z = 0xffu;
-      }
-      else if (area2x)
-      {
-        o0 = (uint32_t)(2 * gy) * sstride;
-        o1 = o0 + sstride;
-        z = 0xffu;
-      }
-      else
-      {
-        const int sy = p.tab_ofs[L.tab_y + gy];
-        const short2 b = p.tab_coef[L.tab_y + gy];
-        o0 = (uint32_t)min(max(sy, 0), H - 1) * sstride; // rows are clamped, not re-weighted (cv::resize)
-        o1 = (uint32_t)min(max(sy + 1, 0), H - 1) * sstride;
-        z = (uint32_t)b.x << 16, w = (uint32_t)b.y << 16; // coefficients are in [0, 2048]
-      }
-    }
-    s_row[tid] = make_uint4(o0, o1, z, w);
-  }
-  __syncthreads();
-
-  // stage A: the tile plus a 3-pixel halo of the (resized) level image, REFLECT_101 at the level's borders.
-  {
-    const int col = tid % kColStride, grp = tid / kColStride;
-    const int rx = t.x0 + col - kHalo;
-    if (grp < kColGroups && col < kSrcW)
-    {
-      const bool col_ok = rx < lw + kHalo;
-      const uint32_t gx = col_ok ? (uint32_t)refl101(rx, lw) : 0u;
-      uint8_t *dst = s_src + kSrcCol0 + col;
-      if (!col_ok)
-      {
-        for (int ty = grp; ty < kSrcH; ty += kColGroups) dst[ty * kSrcPitch] = 0;
-      }
-      else if (level == 0)
-      {
-        const uint8_t *__restrict__ col_src = src + gx;
-        constexpr int U = 8; // rows per batch: all loads of a batch are issued before the first use
-        for (int ty0 = grp; ty0 < kSrcH; ty0 += U * kColGroups)
-        {
-          uint32_t v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-          {
-            const uint4 r = s_row[min(ty0 + u * kColGroups, kSrcH - 1)];
-            v[u] = col_src[(size_t)r.x] & r.z;
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (ty0 + u * kColGroups < kSrcH) dst[(ty0 + u * kColGroups) * kSrcPitch] = (uint8_t)v[u];
-        }
-      }
-      else if (area2x)
-      {
-        const uint8_t *__restrict__ col_src = src + 2 * gx;
-#pragma unroll 2
-        for (int ty = grp; ty < kSrcH; ty += kColGroups)
-        {
-          const uint4 r = s_row[ty];
-          const uint8_t *q0 = col_src + (size_t)r.x, *q1 = col_src + (size_t)r.y;
-          dst[ty * kSrcPitch] = (uint8_t)(((q0[0] + q0[1] + q1[0] + q1[1] + 2) >> 2) & r.z);
-        }
-      }
-      else
-      {
-        // value = src[sx] * ax + src[min(sx + 1, W - 1)] * ay.  The second tap is always read at +1 (an immediate): in the
-        // last column (sx == W - 1, where the table has ay == 0) the pair is moved one pixel left with the weights swapped.
-        uint32_t sx = (uint32_t)p.tab_ofs[L.tab_x + gx];
-        const short2 a = p.tab_coef[L.tab_x + gx];
-        uint32_t ax = (uint32_t)a.x, ay = (uint32_t)a.y;
-        if (sx + 1u > (uint32_t)(W - 1))
-        {
-          sx = (uint32_t)(W - 2);
-          ay = ax + ay;
-          ax = 0;
-        }
-        const uint8_t *__restrict__ col_src = src + sx;
-        constexpr int U = 4; // rows per batch: 16 byte loads in flight per thread
-        for (int ty0 = grp; ty0 < kSrcH; ty0 += U * kColGroups)
-        {
-          uint32_t p00[U], p01[U], p10[U], p11[U], bz[U], bw[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-          {
-            const uint4 r = s_row[min(ty0 + u * kColGroups, kSrcH - 1)];
-            const uint8_t *q0 = col_src + (size_t)r.x, *q1 = col_src + (size_t)r.y; // 64-bit: the +1 folds into the load's immediate
-            p00[u] = q0[0], p01[u] = q0[1], p10[u] = q1[0], p11[u] = q1[1];
-            bz[u] = r.z, bw[u] = r.w;
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-          {
-            const uint32_t h0 = p00[u] * ax + p01[u] * ay;
-            const uint32_t h1 = p10[u] * ax + p11[u] * ay;
-            // (((bx * (h0 >> 4)) >> 16) + ((by * (h1 >> 4)) >> 16) + 2) >> 2; at most 255 because bx + by == 2048
-            const uint32_t v = (__umulhi(bz[u], h0 >> 4) + __umulhi(bw[u], h1 >> 4) + 2u) >> 2;
-            if (ty0 + u * kColGroups < kSrcH) dst[(ty0 + u * kColGroups) * kSrcPitch] = (uint8_t)v;
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  uint8_t *__restrict__ pyr = p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off;
-  uint8_t *__restrict__ blr = p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off;
-
-  // the level image itself (getPyramid(); FAST, orientation and the stereo SAD read it): 16 pixels per load/store
-  for (int i = tid; i < kTileH * (kTileW / 16); i += kPyrThreads)
+// the level image itself (getPyramid(); FAST, orientation and the stereo SAD read it): 16 pixels per load/store
+__device__ __forceinline__ void pyr_store_level(const PyrShared &sm, const Tile &t, int lh, int pitch, uint8_t *__restrict__ pyr)
+{
+  for (int i = threadIdx.x; i < kTileH * (kTileW / 16); i += kPyrThreads)
   {
     const int ty = i >> 2, tx = (i & 3) * 16;
     const int gx = t.x0 + tx, gy = t.y0 + ty;
     if (gy < lh && gx < pitch)
-      *reinterpret_cast<uint4 *>(pyr + (size_t)gy * pitch + gx) = *reinterpret_cast<const uint4 *>(&s_src[(ty + kHalo) * kSrcPitch + 16 + tx]);
+      *reinterpret_cast<uint4 *>(pyr + (size_t)gy * pitch + gx) = *reinterpret_cast<const uint4 *>(&sm.src[(ty + kHalo) * kSrcPitch + 16 + tx]);
   }
+}
 
-  // stage B: horizontal pass, 2 rows x 4 outputs per item from 3 aligned words per row; output pixel 4g + k needs source
-  // bytes 4g + 13 + k .. + 6 of the row = words 3 + g .. 5 + g shifted by 8 (k + 1) bits; sums fit u16 (255 * 256).
-  // The two rows of a pair share a word (row 2j low, row 2j + 1 high) so that the vertical pass can use DP2A.
+// stage B: horizontal pass, 2 rows x 4 outputs per item from 3 aligned words per row; output pixel 4g + k needs source
+// bytes 4g + 13 + k .. + 6 of the row = words 3 + g .. 5 + g shifted by 8 (k + 1) bits; sums fit u16 (255 * 256).
+// The two rows of a pair share a word (row 2j low, row 2j + 1 high) so that the vertical pass can use DP2A.
+__device__ __forceinline__ void pyr_blur_rows(PyrShared &sm, int rows)
+{
+  constexpr uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24); // taps 0..3
+  constexpr uint32_t K1 = 48u | (34u << 8) | (18u << 16);               // taps 4..6
+  const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sm.src);
+  uint4 *h4 = reinterpret_cast<uint4 *>(sm.h);
+  const int g = threadIdx.x & 15;
+  const int n_pairs = (rows + 1) >> 1;
+  for (int j = threadIdx.x >> 4; j < n_pairs; j += kPyrThreads / 16)
   {
-    constexpr uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24); // taps 0..3
-    constexpr uint32_t K1 = 48u | (34u << 8) | (18u << 16);               // taps 4..6
-    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s_src);
-    uint4 *h4 = reinterpret_cast<uint4 *>(s_h);
-    for (int i = tid; i < (kSrcH / 2) * (kTileW / 4); i += kPyrThreads)
-    {
-      const int j = i >> 4, g = i & 15;
-      const uint32_t *row = s32 + (2 * j) * (kSrcPitch / 4) + 3 + g;
-      uint32_t o[2][4];
+    const uint32_t *row = s32 + (2 * j) * (kSrcPitch / 4) + 3 + g;
+    uint32_t o[2][4];
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < 2; ++r)
+    {
+      const uint32_t w0 = row[r * (kSrcPitch / 4)], w1 = row[r * (kSrcPitch / 4) + 1], w2 = row[r * (kSrcPitch / 4) + 2];
+      o[r][0] = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
+      o[r][1] = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
+      o[r][2] = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
+      o[r][3] = __dp4a(w1, K0, __dp4a(w2, K1, 0u));
+    }
+    h4[j * 16 + g] = make_uint4(o[0][0] | (o[1][0] << 16), o[0][1] | (o[1][1] << 16), o[0][2] | (o[1][2] << 16), o[0][3] | (o[1][3] << 16));
+  }
+}
+
+// stage C: vertical pass + rounding; one item per 4 columns x 2 output rows (2y, 2y + 1).  Both rows read the same four
+// row pairs y .. y + 3: the even row weighs them (18,34) (48,56) (48,34) (18,0), the odd row (0,18) (34,48) (56,48)
+// (34,18) -- low / high byte pairs of the same weight registers (DP2A.LO / DP2A.HI).
+__device__ __forceinline__ void pyr_blur_cols(const PyrShared &sm, const Tile &t, int lh, int pitch, uint8_t *__restrict__ blr)
+{
+  const int g = threadIdx.x & 15;
+  const int gx = t.x0 + g * 4;
+  if (gx >= pitch) return;
+  const int n_out = min(kTileH / 2, (lh - t.y0 + 1) >> 1);
+  const uint4 *h4 = reinterpret_cast<const uint4 *>(sm.h);
+  for (int yp = threadIdx.x >> 4; yp < n_out; yp += kPyrThreads / 16)
+  {
+    const int gy = t.y0 + 2 * yp;
+    constexpr uint32_t W0 = 18u | (34u << 8) | (0u << 16) | (18u << 24), W1 = 48u | (56u << 8) | (34u << 16) | (48u << 24);
+    constexpr uint32_t W2 = 48u | (34u << 8) | (56u << 16) | (48u << 24), W3 = 18u | (0u << 8) | (34u << 16) | (18u << 24);
+    const uint4 p0 = h4[yp * 16 + g], p1 = h4[(yp + 1) * 16 + g], p2 = h4[(yp + 2) * 16 + g], p3 = h4[(yp + 3) * 16 + g];
+    const uint32_t c0[4] = {p0.x, p0.y, p0.z, p0.w}, c1[4] = {p1.x, p1.y, p1.z, p1.w}, c2[4] = {p2.x, p2.y, p2.z, p2.w}, c3[4] = {p3.x, p3.y, p3.z, p3.w};
+    uint32_t we = 0, wo = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      const uint32_t e = __dp2a_lo(c3[k], W3, __dp2a_lo(c2[k], W2, __dp2a_lo(c1[k], W1, __dp2a_lo(c0[k], W0, 32768u))));
+      const uint32_t o = __dp2a_hi(c3[k], W3, __dp2a_hi(c2[k], W2, __dp2a_hi(c1[k], W1, __dp2a_hi(c0[k], W0, 32768u))));
+      we |= (e >> 16) << (8 * k);
+      wo |= (o >> 16) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t *>(blr + (size_t)gy * pitch + gx) = we;
+    if (gy + 1 < lh) *reinterpret_cast<uint32_t *>(blr + (size_t)(gy + 1) * pitch + gx) = wo;
+  }
+}
+
+__global__ void __launch_bounds__(kPyrThreads) pyramid_level0_kernel(const Params p)
+{
+  __shared__ PyrShared sm;
+  const Tile t = p.tiles[blockIdx.x];
+  const int img = blockIdx.y;
+  const Level &L = p.levels[0];
+  const int lw = L.w, lh = L.h, pitch = L.pitch;
+  const uint8_t *__restrict__ src = input_image(p, img);
+  const uint32_t sstride = (uint32_t)p.in_stride;
+  const int tid = threadIdx.x;
+  const int rows = tile_rows(t, lh);
+
+  if (tid < rows)
+  {
+    const int gy = refl101(t.y0 + tid - kHalo, lh);
+    // rows 0 and lh - 1 are gathered byte by byte: an aligned word may reach up to 3 bytes outside the caller's buffer there
+    sm.row[tid] = make_uint4((uint32_t)gy * sstride, 0u, (gy > 0 && gy < lh - 1) ? 1u : 0u, 0u);
+  }
+  __syncthreads();
+
+  // stage A: thread <-> word column j (source columns x0 - 4 + 4 j .. + 3), kWordRows rows per pass
+  {
+    const int j = tid % kSrcWords, grp = tid / kSrcWords;
+    if (grp < kWordRows)
+    {
+      const int rx = t.x0 - 4 + 4 * j;
+      const bool col_fast = rx >= 0 && rx + 4 <= lw;
+      uint32_t *dst = reinterpret_cast<uint32_t *>(sm.src) + kSrcWord0 + j;
+      const uint8_t *__restrict__ col_src = src + rx;
+      constexpr int U = 5; // 70 rows = 14 rows per pass x 5: all loads of a tile are issued before the first use
+      uint32_t w0[U], w1[U], sh[U];
+      bool fast[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
       {
-        const uint32_t w0 = row[r * (kSrcPitch / 4)], w1 = row[r * (kSrcPitch / 4) + 1], w2 = row[r * (kSrcPitch / 4) + 2];
-        o[r][0] = __dp4a(__funnelshift_r(w0, w1, 8), K0, __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
-        o[r][1] = __dp4a(__funnelshift_r(w0, w1, 16), K0, __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
-        o[r][2] = __dp4a(__funnelshift_r(w0, w1, 24), K0, __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
-        o[r][3] = __dp4a(w1, K0, __dp4a(w2, K1, 0u));
+        const int ty = min(grp + u * kWordRows, rows - 1);
+        const uint4 r = sm.row[ty];
+        const uint8_t *a = col_src + (size_t)r.x;
+        fast[u] = col_fast && r.z != 0u;
+        if (fast[u])
+        {
+          const uint32_t *al = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
+          w0[u] = al[0], w1[u] = al[1];
+          sh[u] = (uint32_t)reinterpret_cast<uintptr_t>(a) << 3; // funnel shifts take the amount modulo 32
+        }
+        else
+        {
+          // borders: REFLECT_101 per byte; columns beyond the level + halo are zero
+          const uint8_t *rowp = src + (size_t)r.x;
+          uint32_t v = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+          {
+            const int cx = rx + k;
+            if (cx < lw + kHalo) v |= (uint32_t)rowp[refl101(cx, lw)] << (8 * k);
+          }
+          w0[u] = v, w1[u] = 0u, sh[u] = 0u;
+        }
       }
-      h4[i] = make_uint4(o[0][0] | (o[1][0] << 16), o[0][1] | (o[1][1] << 16), o[0][2] | (o[1][2] << 16), o[0][3] | (o[1][3] << 16));
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (grp + u * kWordRows < rows) dst[(grp + u * kWordRows) * (kSrcPitch / 4)] = __funnelshift_r(w0[u], w1[u], sh[u]);
     }
   }
   __syncthreads();
 
-  // stage C: vertical pass + rounding; one item per 4 columns x 2 output rows (2y, 2y + 1).  Both rows read the same four
-  // row pairs y .. y + 3: the even row weighs them (18,34) (48,56) (48,34) (18,0), the odd row (0,18) (34,48) (56,48)
-  // (34,18) -- low / high byte pairs of the same weight registers (DP2A.LO / DP2A.HI).
-  for (int i = tid; i < (kTileH / 2) * (kTileW / 4); i += kPyrThreads)
+  pyr_store_level(sm, t, lh, pitch, p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off);
+  pyr_blur_rows(sm, rows);
+  __syncthreads();
+  pyr_blur_cols(sm, t, lh, pitch, p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off);
+}
+
+// one column of a resized level: source column, packed coefficients (ax | ay << 16)
+__device__ __forceinline__ void resize_column(const Params &p, const Level &L, int rx, int W, uint32_t &sx, uint32_t &coef)
+{
+  sx = 0u, coef = 0u; // columns beyond the level + halo: weight 0 -> value 0
+  if (rx < L.w + kHalo)
   {
-    const int g = i & 15, yp = i >> 4;
-    const int gx = t.x0 + g * 4, gy = t.y0 + 2 * yp;
-    if (gy < lh && gx < pitch)
+    const int gx = refl101(rx, L.w);
+    sx = (uint32_t)p.tab_ofs[L.tab_x + gx];
+    const short2 a = p.tab_coef[L.tab_x + gx];
+    uint32_t ax = (uint32_t)a.x, ay = (uint32_t)a.y;
+    // value = src[sx] * ax + src[min(sx + 1, W - 1)] * ay.  The second tap is always read at +1: in the last column
+    // (sx == W - 1, where the table has ay == 0) the pair is moved one pixel left with the weights swapped.
+    if (sx + 1u > (uint32_t)(W - 1))
     {
-      constexpr uint32_t W0 = 18u | (34u << 8) | (0u << 16) | (18u << 24), W1 = 48u | (56u << 8) | (34u << 16) | (48u << 24);
-      constexpr uint32_t W2 = 48u | (34u << 8) | (56u << 16) | (48u << 24), W3 = 18u | (0u << 8) | (34u << 16) | (18u << 24);
-      const uint4 *h4 = reinterpret_cast<const uint4 *>(s_h);
-      const uint4 p0 = h4[yp * 16 + g], p1 = h4[(yp + 1) * 16 + g], p2 = h4[(yp + 2) * 16 + g], p3 = h4[(yp + 3) * 16 + g];
-      const uint32_t c0[4] = {p0.x, p0.y, p0.z, p0.w}, c1[4] = {p1.x, p1.y, p1.z, p1.w}, c2[4] = {p2.x, p2.y, p2.z, p2.w}, c3[4] = {p3.x, p3.y, p3.z, p3.w};
-      uint32_t we = 0, wo = 0;
+      sx = (uint32_t)(W - 2);
+      ay = ax + ay;
+      ax = 0;
+    }
+    coef = ax | (ay << 16);
+  }
+}
+
+template <bool kSharedWindow> __device__ __forceinline__ void resize_rows(PyrShared &sm, const uint8_t *__restrict__ l0, int rows, int q, int grp,
+                                                                           uint32_t base_a, uint32_t base_b, uint32_t sel_a, uint32_t sel_b,
+                                                                           uint32_t coef_a, uint32_t coef_b)
+{
+  // No clamps, no store predicate: the row table is valid for all kSrcH entries (rows beyond `rows` repeat row 0) and a
+  // pass may write up to kPairRows * (U - 1) rows past `rows` -- still inside the tile buffer, never consumed.
+  uint16_t *dst = reinterpret_cast<uint16_t *>(sm.src) + (kSrcWord0 * 2 + q) + grp * (kSrcPitch / 2);
+  const uint4 *rp = sm.row + grp;
+  const uint8_t *pa = l0 + base_a, *pb = l0 + base_b;
+  // keep the two window pointers in register pairs: a row address is then ONE IMAD.WIDE.U32 (pointer + 32-bit row offset)
+  // instead of a chain of 3-input adds that rebuilds the image base from its uniform parts
+  asm volatile("" : "+l"(pa), "+l"(pb));
+  constexpr int U = 2; // rows per batch: 8 (16) word loads in flight per thread
+  static_assert(kSrcH % (U * kPairRows) == 0, "the row passes tile the buffer exactly");
+  for (int ty0 = grp; ty0 < rows; ty0 += U * kPairRows, rp += U * kPairRows, dst += U * kPairRows * (kSrcPitch / 2))
+  {
+    uint32_t a0[U], a1[U], a2[U], a3[U], b0[U], b1[U], b2[U], b3[U], bz[U], bw[U];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+    for (int u = 0; u < U; ++u)
+    {
+      const uint4 r = rp[u * kPairRows];
+      const uint32_t *q0 = reinterpret_cast<const uint32_t *>(pa + r.x), *q1 = reinterpret_cast<const uint32_t *>(pa + r.y);
+      a0[u] = q0[0], a1[u] = q0[1], a2[u] = q1[0], a3[u] = q1[1];
+      if (!kSharedWindow)
       {
-        const uint32_t e = __dp2a_lo(c3[k], W3, __dp2a_lo(c2[k], W2, __dp2a_lo(c1[k], W1, __dp2a_lo(c0[k], W0, 32768u))));
-        const uint32_t o = __dp2a_hi(c3[k], W3, __dp2a_hi(c2[k], W2, __dp2a_hi(c1[k], W1, __dp2a_hi(c0[k], W0, 32768u))));
-        we |= (e >> 16) << (8 * k);
-        wo |= (o >> 16) << (8 * k);
+        const uint32_t *s0 = reinterpret_cast<const uint32_t *>(pb + r.x), *s1 = reinterpret_cast<const uint32_t *>(pb + r.y);
+        b0[u] = s0[0], b1[u] = s0[1], b2[u] = s1[0], b3[u] = s1[1];
       }
-      *reinterpret_cast<uint32_t *>(blr + (size_t)gy * pitch + gx) = we;
-      if (gy + 1 < lh) *reinterpret_cast<uint32_t *>(blr + (size_t)(gy + 1) * pitch + gx) = wo;
+      else
+        b0[u] = a0[u], b1[u] = a1[u], b2[u] = a2[u], b3[u] = a3[u];
+      bz[u] = r.z, bw[u] = r.w;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const uint32_t ha0 = __dp2a_lo(coef_a, __byte_perm(a0[u], a1[u], sel_a), 0u), ha1 = __dp2a_lo(coef_a, __byte_perm(a2[u], a3[u], sel_a), 0u);
+      const uint32_t hb0 = __dp2a_lo(coef_b, __byte_perm(b0[u], b1[u], sel_b), 0u), hb1 = __dp2a_lo(coef_b, __byte_perm(b2[u], b3[u], sel_b), 0u);
+      // (((bx * (h0 >> 4)) >> 16) + ((by * (h1 >> 4)) >> 16) + 2) >> 2; at most 255 because bx + by == 2048
+      const uint32_t va = (__umulhi(bz[u], ha0 >> 4) + __umulhi(bw[u], ha1 >> 4) + 2u) >> 2;
+      const uint32_t vb = (__umulhi(bz[u], hb0 >> 4) + __umulhi(bw[u], hb1 >> 4) + 2u) >> 2;
+      dst[u * kPairRows * (kSrcPitch / 2)] = (uint16_t)(va | (vb << 8));
     }
   }
 }
 
-const void *pyramid_kernel_symbol() { return reinterpret_cast<const void *>(&pyramid_blur_kernel); }
+__global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Params p)
+{
+  __shared__ PyrShared sm;
+  const Tile t = p.tiles[p.n_tiles0 + blockIdx.x];
+  const int img = blockIdx.y;
+  const Level &L = p.levels[t.level];
+  const int lw = L.w, lh = L.h, pitch = L.pitch;
+  const int W = p.width, H = p.height;
+  const int area2x = L.area2x;
+  const int tid = threadIdx.x;
+  const int rows = tile_rows(t, lh);
+  const uint32_t pitch0 = (uint32_t)p.levels[0].pitch;
+  // level 0 of this image inside the pyramid buffer (written by pyramid_level0_kernel, same stream)
+  const uint8_t *__restrict__ l0 = p.pyr + (size_t)img * p.pyr_img_stride + p.levels[0].pyr_off;
 
+  if (tid < rows)
+  {
+    const int gy = refl101(t.y0 + tid - kHalo, lh);
+    uint32_t o0, o1, z = 0, w = 0;
+    if (area2x)
+    {
+      o0 = (uint32_t)(2 * gy) * pitch0;
+      o1 = o0 + pitch0;
+    }
+    else
+    {
+      const int sy = p.tab_ofs[L.tab_y + gy];
+      const short2 b = p.tab_coef[L.tab_y + gy];
+      o0 = (uint32_t)min(max(sy, 0), H - 1) * pitch0; // rows are clamped, not re-weighted (cv::resize)
+      o1 = (uint32_t)min(max(sy + 1, 0), H - 1) * pitch0;
+      z = (uint32_t)b.x << 16, w = (uint32_t)b.y << 16; // coefficients are in [0, 2048]
+    }
+    sm.row[tid] = make_uint4(o0, o1, z, w);
+  }
+  else if (tid < kSrcH)
+    sm.row[tid] = make_uint4(0u, 0u, 0u, 0u); // rows beyond the level: any valid source row, weights 0 (never consumed)
+  __syncthreads();
+
+  // stage A: the tile plus a 3-pixel halo of the resized level image, REFLECT_101 at the level's borders.
+  if (area2x)
+  {
+    // exact 2x decimation: cv::resize re-routes INTER_LINEAR to INTER_AREA = rounded 2x2 means
+    for (int i = tid; i < rows * kSrcW; i += kPyrThreads)
+    {
+      const int ty = i / kSrcW, col = i - ty * kSrcW;
+      const int rx = t.x0 + col - kHalo;
+      uint32_t v = 0;
+      if (rx < lw + kHalo)
+      {
+        const uint4 r = sm.row[ty];
+        const uint8_t *q0 = l0 + r.x + 2 * refl101(rx, lw), *q1 = l0 + r.y + 2 * refl101(rx, lw);
+        v = (q0[0] + q0[1] + q1[0] + q1[1] + 2) >> 2;
+      }
+      sm.src[ty * kSrcPitch + kSrcCol0 + col] = (uint8_t)v;
+    }
+  }
+  else
+  {
+    const int q = tid % kPairs, grp = tid / kPairs;
+    if (grp < kPairRows)
+    {
+      const int rx = t.x0 - 4 + 2 * q; // columns rx, rx + 1 (rx = x0 - 4 and x0 + 67 are not used by anybody)
+      uint32_t sxa, sxb, coef_a, coef_b;
+      resize_column(p, L, rx, W, sxa, coef_a);
+      resize_column(p, L, rx + 1, W, sxb, coef_b);
+      if (L.pair_window)
+      {
+        // both tap pairs inside the aligned 8 bytes that start at the lower column's word (host-checked for the level)
+        const uint32_t lo = (coef_a == 0u) ? sxb : ((coef_b == 0u) ? sxa : min(sxa, sxb));
+        const uint32_t base = lo & ~3u;
+        const uint32_t oa = (coef_a == 0u) ? 0u : sxa - base, ob = (coef_b == 0u) ? 0u : sxb - base;
+        resize_rows<true>(sm, l0, rows, q, grp, base, base, oa | ((oa + 1u) << 4), ob | ((ob + 1u) << 4), coef_a, coef_b);
+      }
+      else
+      {
+        const uint32_t base_a = sxa & ~3u, base_b = sxb & ~3u;
+        const uint32_t oa = sxa - base_a, ob = sxb - base_b;
+        resize_rows<false>(sm, l0, rows, q, grp, base_a, base_b, oa | ((oa + 1u) << 4), ob | ((ob + 1u) << 4), coef_a, coef_b);
+      }
+    }
+  }
+  __syncthreads();
+
+  pyr_store_level(sm, t, lh, pitch, p.pyr + (size_t)img * p.pyr_img_stride + L.pyr_off);
+  pyr_blur_rows(sm, rows);
+  __syncthreads();
+  pyr_blur_cols(sm, t, lh, pitch, p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off);
+}
+
+const void *pyramid_kernel_symbol() { return reinterpret_cast<const void *>(&pyramid_level0_kernel); }
+
+// two launches: level 0 (reads the caller's images), then the resized levels (read level 0 from the pyramid buffer)
 void launch_pyramid(const Params &p, int n_images, cudaStream_t s)
 {
-  dim3 grid(p.n_tiles, n_images);
-  pyramid_blur_kernel<<<grid, kPyrThreads, 0, s>>>(p);
+  pyramid_level0_kernel<<<dim3(p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p);
+  if (p.n_tiles > p.n_tiles0) pyramid_levels_kernel<<<dim3(p.n_tiles - p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -415,7 +415,7 @@ def test_device_batch_and_launch_count():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     before = ctx.launch_count
     res = ctx.stereo_batch_device(n, dl.data_ptr(), dr.data_ptr(), c["width"], c["width"] * c["height"])
-    assert ctx.launch_count - before == 6  # pyramid+blur, FAST, quadtree, orientation+BRIEF, frame index (row index + grid), stereo (one chunk: n <= 8)
+    assert ctx.launch_count - before == 7  # pyramid level 0, pyramid levels >= 1 (+blur), FAST, quadtree, orientation+BRIEF, frame index (row index + grid), stereo (one chunk: n <= 8)
     nm = ctx.read_device(res.n_matches, (n,), np.int32)
     assert np.array_equal(nm, host.n_matches) and (nm > 500).all()
     desc = ctx.read_device(res.desc, (2 * n, 2000, 32), np.uint8)
