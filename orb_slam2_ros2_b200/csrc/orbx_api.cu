@@ -239,6 +239,26 @@ int build_tables(orbx_ctx *c)
   p.sel_entries = sel_off;
   p.qt_scratch_img_stride = scratch_off;
   p.qt_node_cap = max_quota + max_ini + 8;
+  {
+    // FAST kernel: one warp per cell, each with its own slice of dynamic shared memory sized for the largest cell
+    int zw = 1, zh = 1, box_h = 1;
+    int area = 1;
+    for (auto &ce : c->cells)
+      zw = std::max(zw, ce.pw - 6), zh = std::max(zh, ce.ph - 6), box_h = std::max(box_h, ce.box_h), area = std::max(area, (ce.pw - 6) * (ce.ph - 6));
+    auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+    int off = up((box_h + 3) * 80 + 16, 128);  // TMA box rows of 80 bytes + slack: stage 1 steps 4 rows at a time and loads whole words
+    p.fast_off_bar = off;
+    off += 16;
+    p.fast_map_pitch = up(zw + 2, 4);
+    p.fast_off_map = off;
+    off += up((zh + 2) * p.fast_map_pitch + 16, 16);
+    p.fast_off_cand = off;
+    off += up(area * 2, 16); // worst case: every zone pixel is a stage-1 candidate
+    p.fast_off_mask = off;
+    off += 2 * 64 * 8; // stage-1 row masks + keep masks (64 rows each)
+    p.fast_warp_bytes = up(off, 128);
+    if (4 * (size_t)p.fast_warp_bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cells too large for shared memory");
+  }
   p.qt_fast = 1;
   if (const char *e = std::getenv("ORBX_QT_FAST")) p.qt_fast = std::atoi(e) != 0;
   if (p.qt_node_cap >= 60000) return fail(c, ORBX_ERR_INVALID_ARG, "n_features too large for the quadtree node pool");
@@ -709,6 +729,11 @@ extern "C"
       c->cfg.pattern = nullptr; // not retained
       if ((rc = alloc_buffers(c))) break;
       if ((rc = build_level_maps(c))) break;
+      if (fast_configure(c->p) != 0)
+      {
+        rc = fail(c, ORBX_ERR_CUDA, "cudaFuncSetAttribute(fast_cells_kernel, MaxDynamicSharedMemorySize)");
+        break;
+      }
       if (frame_index_configure(c->p) != 0)
       {
         rc = fail(c, ORBX_ERR_CUDA, "cudaFuncSetAttribute(frame_index_kernel, MaxDynamicSharedMemorySize)");

@@ -92,6 +92,8 @@ struct Params
   int n_tiles0; // tiles of level 0 (first in the tile table): pyramid_level0_kernel; the rest: pyramid_levels_kernel
   int width, height;
   int stereo; // images are interleaved left/right pairs
+  // per-warp shared-memory slice of the FAST kernel (one warp per cell): patch at 0, then these offsets
+  int fast_off_bar, fast_off_map, fast_off_cand, fast_off_mask, fast_map_pitch, fast_warp_bytes;
   const Level *levels;
   const Tile *tiles;
   const Cell *cells;
@@ -218,6 +220,7 @@ constexpr int kPyramidLaunches = 2;
 void launch_pyramid(const Params &p, int n_images, cudaStream_t s); // kPyramidLaunches kernels: level 0, then the resized levels
 const void *pyramid_kernel_symbol(); // host handle of the level-0 pyramid kernel, the only reader of the caller's images (to find its node in a captured graph)
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
+int fast_configure(const Params &p); // opt in to the dynamic shared memory of the FAST kernel
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
 void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
 void launch_stereo(const Params &p, int n_frames, cudaStream_t s);

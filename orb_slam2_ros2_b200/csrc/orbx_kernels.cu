@@ -385,13 +385,13 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Param
       {
         // both tap pairs inside the aligned 8 bytes that start at the lower column's word (host-checked for the level)
         const uint32_t lo = (coef_a == 0u) ? sxb : ((coef_b == 0u) ? sxa : min(sxa, sxb));
-        const uint32_t base = lo & ~3u;
+        const uint32_t base = min(lo & ~3u, pitch0 - 8u); // the window never leaves the row's pitch (the clamp keeps offsets <= 6)
         const uint32_t oa = (coef_a == 0u) ? 0u : sxa - base, ob = (coef_b == 0u) ? 0u : sxb - base;
         resize_rows<true>(sm, l0, rows, q, grp, base, base, oa | ((oa + 1u) << 4), ob | ((ob + 1u) << 4), coef_a, coef_b);
       }
       else
       {
-        const uint32_t base_a = sxa & ~3u, base_b = sxb & ~3u;
+        const uint32_t base_a = min(sxa & ~3u, pitch0 - 8u), base_b = min(sxb & ~3u, pitch0 - 8u);
         const uint32_t oa = sxa - base_a, ob = sxb - base_b;
         resize_rows<false>(sm, l0, rows, q, grp, base_a, base_b, oa | ((oa + 1u) << 4), ob | ((ob + 1u) << 4), coef_a, coef_b);
       }
@@ -415,14 +415,13 @@ void launch_pyramid(const Params &p, int n_images, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K2: FAST-9/16 with non-max suppression per 30-px cell and the iniTh -> minTh fallback.  One CTA per cell.
+// K2: FAST-9/16 with non-max suppression per 30-px cell and the iniTh -> minTh fallback.  One warp per cell.
 //   arc value m(p) = max over the 16 arcs of 9 contiguous ring pixels of min(+-(I(p) - I(ring)));
 //   corner at threshold t  <=>  m > t;  cv score = m - 1;  keep iff score > all 8 neighbours' scores (strict), where a
 //   neighbour that is not a corner at t, or lies outside the cell's detection zone, scores 0.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kPatPitch = 80;                 // bytes = width of the TMA box: (x0 & 15) + patch width (<= 65)
 constexpr int kZoneMax = 64;                  // detection zone edge (patch edge - 6); one 64-bit mask per zone row
-constexpr int kMapPitch = kZoneMax + 4;       // 68
 
 __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
 {
@@ -514,42 +513,74 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
 }
 
 constexpr int kFastWarps = kFastThreads / 32;
-constexpr int kCandSeg = (kZoneMax / kFastWarps) * kZoneMax; // candidates one warp can produce (its rows x 64)
 
-__global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Params p, const __grid_constant__ LevelMaps maps)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
-  __shared__ __align__(128) uint8_t s_pat[(kZoneMax + 6) * kPatPitch];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ __align__(16) uint8_t s_map[(kZoneMax + 2) * kMapPitch + 16]; // + 16: zeroed with 16-byte stores
-  __shared__ uint16_t s_cand[kFastWarps * kCandSeg];
-  __shared__ unsigned long long s_keep[kZoneMax];
-  __shared__ int s_warp[kFastWarps], s_ccnt[kFastWarps];
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 
-  const Cell c = p.cells[blockIdx.x];
+// Stage-1 test on two pixels at once (16-bit halves of a register, VIMNMX.U16x2): "two ADJACENT compass ring pixels are
+// brighter (darker) than the centre by more than t".  c1 = 0x80008000 - (t + 1) * 0x00010001: bit 15 of a half of
+// hi2 - v + c1 is set iff hi2 - v > t (every half stays inside [0, 65535], so the 32-bit add never carries between halves).
+__device__ __forceinline__ uint32_t fast_pretest2(uint32_t v, uint32_t dn, uint32_t rt, uint32_t up, uint32_t lf, uint32_t c1)
+{
+  const uint32_t hi2 = __vminu2(__vmaxu2(dn, up), __vmaxu2(rt, lf)), lo2 = __vmaxu2(__vminu2(dn, up), __vminu2(rt, lf));
+  return ((hi2 - v + c1) | (v - lo2 + c1)) & 0x80008000u;
+}
+
+// One WARP per cell: a 30 x 30-px cell is too small for a thread block -- its serial phases (map zeroing, suppression over
+// ~40 corners, the output scan) would run on all warps for a handful of active lanes, and every phase boundary would be a
+// block barrier.  A CTA is just kFastWarps independent cells; each warp owns a slice of the dynamic shared memory:
+//   patch (TMA box) | mbarrier | score map | candidate list | stage-1 row masks | keep masks
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p, const __grid_constant__ LevelMaps maps)
+{
+  extern __shared__ __align__(128) uint8_t fast_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int cell = blockIdx.x * kFastWarps + wid;
+  if (cell >= p.n_cells) return;
   const int img = blockIdx.y;
+  uint8_t *const wbase = fast_smem + (size_t)wid * p.fast_warp_bytes;
+  uint8_t *const s_pat = wbase;
+  uint64_t *const s_bar = reinterpret_cast<uint64_t *>(wbase + p.fast_off_bar);
+  uint8_t *const s_map = wbase + p.fast_off_map;
+  unsigned long long *const s_mask = reinterpret_cast<unsigned long long *>(wbase + p.fast_off_mask);
+  unsigned long long *const s_keep = s_mask + kZoneMax;
+  const uint32_t cand_u32 = smem_u32(wbase + p.fast_off_cand);
+  const int mp = p.fast_map_pitch;
+
+  const Cell c = p.cells[cell];
   const int pw = c.pw, ph = c.ph;
   const int zw = pw - 6, zh = ph - 6; // detection zone: FAST looks at [3, w-3) x [3, h-3) of the patch
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned FULL = 0xffffffffu;
   if (zw <= 0 || zh <= 0)
   {
-    if (tid == 0) p.cell_cnt[(size_t)img * p.n_cells + blockIdx.x] = 0;
+    if (lane == 0) p.cell_cnt[(size_t)img * p.n_cells + cell] = 0;
     return;
   }
 
   // The patch (plus whatever lies right of / below it up to the box size; out-of-range bytes are zero-filled) arrives
-  // through one TMA box load issued by thread 0; the map zeroing of the first threshold pass overlaps it.
-  if (tid == 0)
+  // through one TMA box load issued by lane 0; the map zeroing of the first threshold pass overlaps it.
+  if (lane == 0)
   {
-    mbar_init(&s_bar, 1);
-    mbar_expect_tx(&s_bar, (uint32_t)(kPatPitch * c.box_h));
-    tma_load_3d(s_pat, &maps.m[c.level], c.x0 & ~15, c.y0, p.img0 + img, &s_bar); // TMA needs 16-byte aligned row starts
+    mbar_init(s_bar, 1);
+    mbar_expect_tx(s_bar, (uint32_t)(kPatPitch * c.box_h));
+    tma_load_3d(s_pat, &maps.m[c.level], c.x0 & ~15, c.y0, p.img0 + img, s_bar); // TMA needs 16-byte aligned row starts
   }
-  const uint8_t *pat0 = s_pat + 3 * kPatPitch + 3 + (c.x0 & 15); // zone pixel (0,0); 15 + 65 <= the 80-byte box
+  __syncwarp();
+  const int a0 = 3 + (c.x0 & 15);                    // byte of zone column 0 inside a patch row; 15 + 65 <= the 80-byte box
+  const uint8_t *pat0 = s_pat + 3 * kPatPitch + a0;  // zone pixel (0,0)
+  const uint32_t pat_u32 = smem_u32(s_pat);
+
+  // stage 1: lane <-> 4 adjacent zone pixels, 8 lanes per row, 4 rows per step; zones wider than 32 px take two column passes
+  const int n_xp = zw > 32 ? 2 : 1;
+  const int xi = lane & 7, yq = lane >> 3;
+  uint32_t *const s_mask32 = reinterpret_cast<uint32_t *>(s_mask); // [row][column pass]: bit 8 k + i <-> zone column 32 pass + 4 i + k
+  const uint32_t sel_q = (uint32_t)yq | ((uint32_t)(4 + yq) << 4);  // PRMT: byte yq of two ballots
 
   bool patch_ready = false;
-  const uint32_t cand0_u32 = smem_u32(s_cand), cand_u32 = cand0_u32 + 2u * (uint32_t)(wid * kCandSeg); // this warp's segment
-  unsigned long long keep = 0ull;
+  unsigned long long keep0 = 0ull, keep1 = 0ull;
 
   // cv::FAST(cell, iniThFAST); only if its post-NMS list is empty, cv::FAST(cell, minThFAST) (src/ORBExtractor.cc:365-367).
   // Running the thresholds one after the other (instead of computing everything at the lower one) keeps the second,
@@ -559,131 +590,179 @@ __global__ void __launch_bounds__(kFastThreads, 10) fast_cells_kernel(const Para
     const int t = pass == 0 ? p.ini_th : p.min_th;
     {
       uint4 *m128 = reinterpret_cast<uint4 *>(s_map);
-      for (int i = tid; i < ((zh + 2) * kMapPitch + 15) / 16; i += kFastThreads) m128[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (tid < kZoneMax) s_keep[tid] = 0ull;
+      for (int i = lane; i < ((zh + 2) * mp + 15) / 16; i += 32) m128[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = lane; i < zh; i += 32) s_keep[i] = 0ull;
     }
-    __syncthreads(); // also orders thread 0's mbarrier init before everybody's wait
+    __syncwarp();
     if (!patch_ready)
     {
-      mbar_wait(&s_bar, 0);
+      mbar_wait(s_bar, 0);
       patch_ready = true;
     }
 
     // Stage 1 (every zone pixel): two adjacent compass ring pixels are brighter (darker) than the centre by more than t
-    // -- a necessary condition for a 9-arc.  Survivors go to a per-warp candidate segment (warp-local end address, no
-    // atomics), so that the next stage runs on dense lanes.
-    const unsigned lt_mask = (1u << lane) - 1u;
-    uint32_t wend = cand_u32; // shared address one past the warp's last candidate
-    for (int zx0 = 0; zx0 < zw; zx0 += 32) // one chunk for every cell narrower than 33 px (the usual 30-32)
+    // -- a necessary condition for a 9-arc: 9 contiguous ring pixels always contain two ADJACENT compass pixels, i.e. one
+    // of {0, 8} and one of {4, 12}; brighter arc => min(max(r0, r8), max(r4, r12)) > v + t, darker arc =>
+    // max(min(r0, r8), min(r4, r12)) < v - t.  Four pixels per lane from aligned words, two per register half.
     {
-      const int zx = zx0 + lane;
-      const int tl = zx < zw ? t : 0x10000; // lanes beyond the zone read inside the patch buffer (pitch 80 > 3 + 64 + 3) and can never pass
-      const uint8_t *q = pat0 + wid * kPatPitch + min(zx, kZoneMax - 1);
-      uint32_t code = wid * kZoneMax + zx;
-#pragma unroll 2
-      for (int zy = wid; zy < zh; zy += kFastWarps, q += kFastWarps * kPatPitch, code += kFastWarps * kZoneMax)
+      const uint32_t c1 = 0x80008000u - (uint32_t)(t + 1) * 0x00010001u;
+      for (int xp = 0; xp < n_xp; ++xp)
       {
-        const int v = q[0];
-        const int r0 = q[3 * kPatPitch], r4 = q[3], r8 = q[-3 * kPatPitch], r12 = q[-3];
-        // 9 contiguous ring pixels always contain two ADJACENT compass pixels, i.e. one of {0, 8} and one of {4, 12}:
-        // brighter arc => min(max(r0, r8), max(r4, r12)) > v + t, darker arc => max(min(r0, r8), min(r4, r12)) < v - t
-        const int hi2 = min(max(r0, r8), max(r4, r12)), lo2 = max(min(r0, r8), min(r4, r12));
-        const bool cand = max(hi2 - v, v - lo2) > tl;
-        const unsigned m = __ballot_sync(FULL, cand);
-        sts_u16_if(wend + 2u * __popc(m & lt_mask), code, cand);
-        wend += 2u * __popc(m);
+        const int zx0 = 32 * xp + 4 * xi, n_valid = zw - zx0;
+        const uint32_t vm = n_valid >= 4 ? 0xFu : (n_valid <= 0 ? 0u : (1u << n_valid) - 1u);
+        // flag masks of the lane's valid pixels: pixels (0, 2) live in bits 15 / 31 of one register, (1, 3) of another
+        const uint32_t ma = ((vm & 1u) ? 0x8000u : 0u) | ((vm & 4u) ? 0x80000000u : 0u), mb = ((vm & 2u) ? 0x8000u : 0u) | ((vm & 8u) ? 0x80000000u : 0u);
+        const uint32_t bv = (uint32_t)(a0 + min(zx0, (zw - 1) & ~3)); // first byte of the item in its patch row (idle lanes stay inside the row)
+        const uint32_t row0 = pat_u32 + (uint32_t)(yq + 3) * kPatPitch;
+        // aligned word + funnel shift: the 4 pixels, their left (x - 3) and right (x + 3) compass neighbours
+        uint32_t pv = row0 + (bv & ~3u), pl = row0 + ((bv - 3u) & ~3u), pr = row0 + ((bv + 3u) & ~3u);
+        const uint32_t sv = (bv & 3u) * 8u, sl = ((bv - 3u) & 3u) * 8u, sr = ((bv + 3u) & 3u) * 8u;
+        // rows past the zone (the last step of 4) read the slack rows below the patch and are masked out of the ballots
+        for (int y0 = 0; y0 < zh; y0 += 4, pv += 4 * kPatPitch, pl += 4 * kPatPitch, pr += 4 * kPatPitch)
+        {
+          const bool row_ok = y0 + yq < zh;
+          const uint32_t v = __funnelshift_r(lds_u32(pv), lds_u32(pv + 4u), sv);
+          const uint32_t lf = __funnelshift_r(lds_u32(pl), lds_u32(pl + 4u), sl);
+          const uint32_t rt = __funnelshift_r(lds_u32(pr), lds_u32(pr + 4u), sr);
+          const uint32_t up = __funnelshift_r(lds_u32(pv - 3 * kPatPitch), lds_u32(pv - 3 * kPatPitch + 4u), sv);
+          const uint32_t dn = __funnelshift_r(lds_u32(pv + 3 * kPatPitch), lds_u32(pv + 3 * kPatPitch + 4u), sv);
+          const uint32_t fa = fast_pretest2(v & 0x00ff00ffu, dn & 0x00ff00ffu, rt & 0x00ff00ffu, up & 0x00ff00ffu, lf & 0x00ff00ffu, c1) & ma;
+          const uint32_t fb = fast_pretest2(__byte_perm(v, 0u, 0x4341), __byte_perm(dn, 0u, 0x4341), __byte_perm(rt, 0u, 0x4341),
+                                            __byte_perm(up, 0u, 0x4341), __byte_perm(lf, 0u, 0x4341), c1) & mb;
+          // four ballots (one per pixel of the items) instead of a bit interleave: byte q of ballot k = row q, pixels 4 i + k
+          const unsigned b0 = __ballot_sync(FULL, row_ok && (fa & 0x8000u)), b1 = __ballot_sync(FULL, row_ok && (fb & 0x8000u));
+          const unsigned b2 = __ballot_sync(FULL, row_ok && (fa >> 31)), b3 = __ballot_sync(FULL, row_ok && (fb >> 31));
+          const uint32_t w = __byte_perm(__byte_perm(b0, b1, sel_q), __byte_perm(b2, b3, sel_q), 0x5410);
+          if (xi == 0 && row_ok) s_mask32[2 * (y0 + yq) + xp] = w;
+        }
       }
     }
-    const int wcnt = (int)(wend - cand_u32) >> 1;
+    __syncwarp();
+
+    // row masks -> dense candidate list (lane <-> rows lane and lane + 32), so that the next stage runs on dense lanes
+    int n_cand;
+    {
+      uint32_t m[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+      {
+        const bool ok = lane + 32 * h < zh;
+        m[2 * h] = ok ? s_mask32[2 * (lane + 32 * h)] : 0u;
+        m[2 * h + 1] = (ok && n_xp == 2) ? s_mask32[2 * (lane + 32 * h) + 1] : 0u;
+      }
+      const int cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const int up = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += up;
+      }
+      n_cand = __shfl_sync(FULL, inc, 31);
+      uint32_t wa = cand_u32 + 2u * (uint32_t)(inc - cnt);
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+      {
+        uint32_t w = m[h];
+        const uint32_t code0 = (uint32_t)((lane + 32 * (h >> 1)) * kZoneMax + 32 * (h & 1));
+        while (w)
+        {
+          const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+          w &= w - 1u;
+          sts_u16_if(wa, code0 + 4u * (b & 7u) + (b >> 3), true);
+          wa += 2u;
+        }
+      }
+    }
     __syncwarp();
 
     // Stage 2 (stage-1 survivors, dense lanes): the arc value m decides (corner at t <=> m > t) and is the score the
-    // non-max suppression needs, so it goes straight into the map.  The segment is compacted in place to the corners
+    // non-max suppression needs, so it goes straight into the map.  The list is compacted in place to the corners
     // (every chunk is read before it is overwritten).
+    const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t cend = cand_u32;
-    for (int k0 = 0; k0 < wcnt; k0 += 32)
+    for (int k0 = 0; k0 < n_cand; k0 += 32)
     {
       const int k = k0 + lane;
       bool corner = false;
       uint32_t i = 0;
-      if (k < wcnt)
+      if (k < n_cand)
       {
         i = lds_u16(cand_u32 + 2u * k);
         const int zy = i >> 6, zx = i & (kZoneMax - 1);
         const int m = fast_arc_value(pat0 + zy * kPatPitch + zx);
         corner = m > t;
-        if (corner) s_map[(zy + 1) * kMapPitch + zx + 1] = (uint8_t)m;
+        if (corner) s_map[(zy + 1) * mp + zx + 1] = (uint8_t)m;
       }
       __syncwarp();
       const unsigned m = __ballot_sync(FULL, corner);
       sts_u16_if(cend + 2u * __popc(m & lt_mask), i, corner);
       cend += 2u * __popc(m);
     }
-
-    // The suppression runs over the block-wide corner list (the four warp segments back to back) so that the lanes stay
-    // dense even when a warp found only a handful of corners: corner k lives in segment w at k - first[w].
-    static_assert(kFastWarps == 4, "corner_at assumes four warp segments");
-    if (lane == 0) s_ccnt[wid] = (int)(cend - cand_u32) >> 1;
-    __syncthreads();
-    const int f1 = s_ccnt[0], f2 = f1 + s_ccnt[1], f3 = f2 + s_ccnt[2], n_corners = f3 + s_ccnt[3];
-    auto corner_at = [&](int k) -> int {
-      const int adj = k >= f3 ? 3 * kCandSeg - f3 : (k >= f2 ? 2 * kCandSeg - f2 : (k >= f1 ? kCandSeg - f1 : 0));
-      return (int)lds_u16(cand0_u32 + 2u * (uint32_t)(k + adj));
-    };
+    const int n_corners = (int)(cend - cand_u32) >> 1;
+    __syncwarp();
 
     // Non-max suppression: keep  <=>  score m - 1 > the scores of all 8 neighbours (strict), where a neighbour that is not
     // a corner at this threshold (map 0) scores 0; the map q -> (q ? q - 1 : 0) is monotone, so only the largest neighbour
     // matters.
-    for (int k = tid; k < n_corners; k += kFastThreads)
+    for (int k = lane; k < n_corners; k += 32)
     {
-      const int i = corner_at(k);
+      const int i = (int)lds_u16(cand_u32 + 2u * (uint32_t)k);
       const int zy = i >> 6, zx = i & (kZoneMax - 1);
-      const uint8_t *mp = &s_map[(zy + 1) * kMapPitch + zx + 1];
-      const int m = mp[0];
-      const int q = max(max(max((int)mp[-1], (int)mp[1]), max((int)mp[-kMapPitch - 1], (int)mp[-kMapPitch])),
-                        max(max((int)mp[-kMapPitch + 1], (int)mp[kMapPitch - 1]), max((int)mp[kMapPitch], (int)mp[kMapPitch + 1])));
+      const uint8_t *mq = &s_map[(zy + 1) * mp + zx + 1];
+      const int m = mq[0];
+      const int q = max(max(max((int)mq[-1], (int)mq[1]), max((int)mq[-mp - 1], (int)mq[-mp])),
+                        max(max((int)mq[-mp + 1], (int)mq[mp - 1]), max((int)mq[mp], (int)mq[mp + 1])));
       if (m - 1 > (q ? q - 1 : 0)) atomicOr(&s_keep[zy], 1ull << zx);
     }
-    __syncthreads();
-    keep = tid < zh ? s_keep[tid] : 0ull;
-    if (__syncthreads_or(keep != 0ull)) break; // fallback iff the post-NMS list is empty (:366)
+    __syncwarp();
+    keep0 = lane < zh ? s_keep[lane] : 0ull;
+    keep1 = lane + 32 < zh ? s_keep[lane + 32] : 0ull;
+    if (__any_sync(FULL, (keep0 | keep1) != 0ull)) break; // fallback iff the post-NMS list is empty (:366)
   }
 
-  // thread <-> zone row (zh <= 64: warps 0 and 1), row-major output order: exclusive scan of the rows' corner counts
-  static_assert(kZoneMax <= 64, "the output scan covers two warps");
-  const int row_cnt = __popcll(keep);
-  int inc = row_cnt;
-  if (wid < 2)
-  {
+  // lane <-> zone rows lane and lane + 32, row-major output order: exclusive scans of the rows' corner counts
+  static_assert(kZoneMax <= 64, "the output scan covers two rows per lane");
+  const int cnt0 = __popcll(keep0), cnt1 = __popcll(keep1);
+  int inc0 = cnt0, inc1 = cnt1;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      const int up = __shfl_up_sync(FULL, inc, o);
-      if (lane >= o) inc += up;
-    }
-    if (lane == 31) s_warp[wid] = inc;
-  }
-  __syncthreads();
-  const int total = s_warp[0] + s_warp[1];
-  int off = inc - row_cnt + (wid == 1 ? s_warp[0] : 0);
-  uint32_t *slot = p.cell_list + (size_t)img * p.cell_entries + c.slot;
-  const uint32_t y = (uint32_t)(c.y0 - kEdge + 3 + tid); // ROI coordinates (:368-372)
-  while (keep)
+  for (int o = 1; o < 32; o <<= 1)
   {
-    const int zx = __ffsll((long long)keep) - 1;
-    keep &= keep - 1;
-    const uint32_t score = (uint32_t)s_map[(tid + 1) * kMapPitch + zx + 1] - 1u;
-    const uint32_t x = (uint32_t)(c.x0 - kEdge + 3 + zx);
-    if (off < c.cap) slot[off] = x | (y << 12) | (score << 24);
-    ++off;
+    const int u0 = __shfl_up_sync(FULL, inc0, o), u1 = __shfl_up_sync(FULL, inc1, o);
+    if (lane >= o) inc0 += u0, inc1 += u1;
   }
-  if (tid == 0) p.cell_cnt[(size_t)img * p.n_cells + blockIdx.x] = min(total, c.cap); // only thread 0 needs the address
+  const int tot0 = __shfl_sync(FULL, inc0, 31), total = tot0 + __shfl_sync(FULL, inc1, 31);
+  uint32_t *slot = p.cell_list + (size_t)img * p.cell_entries + c.slot;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+  {
+    unsigned long long keep = h == 0 ? keep0 : keep1;
+    int off = h == 0 ? inc0 - cnt0 : tot0 + inc1 - cnt1;
+    const int zy = lane + 32 * h;
+    const uint32_t y = (uint32_t)(c.y0 - kEdge + 3 + zy); // ROI coordinates (:368-372)
+    while (keep)
+    {
+      const int zx = __ffsll((long long)keep) - 1;
+      keep &= keep - 1;
+      const uint32_t score = (uint32_t)s_map[(zy + 1) * mp + zx + 1] - 1u;
+      const uint32_t x = (uint32_t)(c.x0 - kEdge + 3 + zx);
+      if (off < c.cap) slot[off] = x | (y << 12) | (score << 24);
+      ++off;
+    }
+  }
+  if (lane == 0) p.cell_cnt[(size_t)img * p.n_cells + cell] = min(total, c.cap);
+}
+
+int fast_configure(const Params &p)
+{
+  static SmemOptIn state;
+  return raise_dynamic_smem(fast_cells_kernel, state, (size_t)kFastWarps * p.fast_warp_bytes);
 }
 
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s)
 {
-  dim3 grid(p.n_cells, n_images);
-  fast_cells_kernel<<<grid, kFastThreads, 0, s>>>(p, maps);
+  dim3 grid((p.n_cells + kFastWarps - 1) / kFastWarps, n_images);
+  fast_cells_kernel<<<grid, kFastThreads, (size_t)kFastWarps * p.fast_warp_bytes, s>>>(p, maps);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
