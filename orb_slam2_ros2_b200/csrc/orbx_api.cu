@@ -246,7 +246,9 @@ int build_tables(orbx_ctx *c)
     for (auto &ce : c->cells)
       zw = std::max(zw, ce.pw - 6), zh = std::max(zh, ce.ph - 6), box_h = std::max(box_h, ce.box_h), area = std::max(area, (ce.pw - 6) * (ce.ph - 6));
     auto up = [](int v, int a) { return (v + a - 1) / a * a; };
-    int off = up((box_h + 3) * 80 + 16, 128);  // TMA box rows of 80 bytes + slack: stage 1 steps 4 rows at a time and loads whole words
+    // TMA box rows of 80 bytes.  Stage 1 may read up to 13 rows (+ a word) past the zone's patch: that lands in the warp's own map /
+    // candidate area behind the patch (>= 1.1 KB), never outside the slice, and the flags of such rows are masked out.
+    int off = up(box_h * 80, 16);
     p.fast_off_bar = off;
     off += 16;
     p.fast_map_pitch = up(zw + 2, 4);
@@ -255,7 +257,7 @@ int build_tables(orbx_ctx *c)
     p.fast_off_cand = off;
     off += up(area * 2, 16); // worst case: every zone pixel is a stage-1 candidate
     p.fast_off_mask = off;
-    off += 2 * 64 * 8; // stage-1 row masks + keep masks (64 rows each)
+    off += up(zh * 8, 16); // keep masks (one 64-bit mask per zone row)
     p.fast_warp_bytes = up(off, 128);
     if (4 * (size_t)p.fast_warp_bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cells too large for shared memory");
   }

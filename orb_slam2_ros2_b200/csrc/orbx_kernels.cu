@@ -522,18 +522,22 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 }
 
 // Stage-1 test on two pixels at once (16-bit halves of a register, VIMNMX.U16x2): "two ADJACENT compass ring pixels are
-// brighter (darker) than the centre by more than t".  c1 = 0x80008000 - (t + 1) * 0x00010001: bit 15 of a half of
+// brighter (darker) than the centre by more than t".  The operands carry each pixel in the HIGH byte of its half (the low
+// byte is whatever neighbour came along): an unsigned 16-bit max / min is decided by the high bytes, so the high bytes of
+// hi2 / lo2 are exact and only v, hi2 and lo2 need unpacking.  c1 = 0x80008000 - (t + 1) * 0x00010001: bit 15 of a half of
 // hi2 - v + c1 is set iff hi2 - v > t (every half stays inside [0, 65535], so the 32-bit add never carries between halves).
-__device__ __forceinline__ uint32_t fast_pretest2(uint32_t v, uint32_t dn, uint32_t rt, uint32_t up, uint32_t lf, uint32_t c1)
+__device__ __forceinline__ uint32_t fast_pretest2(uint32_t v, uint32_t dn, uint32_t rt, uint32_t up, uint32_t lf, uint32_t c1, uint32_t mask)
 {
-  const uint32_t hi2 = __vminu2(__vmaxu2(dn, up), __vmaxu2(rt, lf)), lo2 = __vmaxu2(__vminu2(dn, up), __vminu2(rt, lf));
-  return ((hi2 - v + c1) | (v - lo2 + c1)) & 0x80008000u;
+  const uint32_t hi2 = __byte_perm(__vminu2(__vmaxu2(dn, up), __vmaxu2(rt, lf)), 0u, 0x4341);
+  const uint32_t lo2 = __byte_perm(__vmaxu2(__vminu2(dn, up), __vminu2(rt, lf)), 0u, 0x4341);
+  const uint32_t vc = __byte_perm(v, 0u, 0x4341);
+  return ((hi2 - vc + c1) | (vc - lo2 + c1)) & mask;
 }
 
 // One WARP per cell: a 30 x 30-px cell is too small for a thread block -- its serial phases (map zeroing, suppression over
 // ~40 corners, the output scan) would run on all warps for a handful of active lanes, and every phase boundary would be a
 // block barrier.  A CTA is just kFastWarps independent cells; each warp owns a slice of the dynamic shared memory:
-//   patch (TMA box) | mbarrier | score map | candidate list | stage-1 row masks | keep masks
+//   patch (TMA box) | mbarrier | score map | candidate list | keep masks
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p, const __grid_constant__ LevelMaps maps)
 {
   extern __shared__ __align__(128) uint8_t fast_smem[];
@@ -545,8 +549,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
   uint8_t *const s_pat = wbase;
   uint64_t *const s_bar = reinterpret_cast<uint64_t *>(wbase + p.fast_off_bar);
   uint8_t *const s_map = wbase + p.fast_off_map;
-  unsigned long long *const s_mask = reinterpret_cast<unsigned long long *>(wbase + p.fast_off_mask);
-  unsigned long long *const s_keep = s_mask + kZoneMax;
+  unsigned long long *const s_keep = reinterpret_cast<unsigned long long *>(wbase + p.fast_off_mask);
   const uint32_t cand_u32 = smem_u32(wbase + p.fast_off_cand);
   const int mp = p.fast_map_pitch;
 
@@ -576,8 +579,13 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
   // stage 1: lane <-> 4 adjacent zone pixels, 8 lanes per row, 4 rows per step; zones wider than 32 px take two column passes
   const int n_xp = zw > 32 ? 2 : 1;
   const int xi = lane & 7, yq = lane >> 3;
-  uint32_t *const s_mask32 = reinterpret_cast<uint32_t *>(s_mask); // [row][column pass]: bit 8 k + i <-> zone column 32 pass + 4 i + k
-  const uint32_t sel_q = (uint32_t)yq | ((uint32_t)(4 + yq) << 4);  // PRMT: byte yq of two ballots
+  // A step works on the four rows r0 + 2 yq (yq = 0..3): two rows apart, because the 80-byte patch pitch puts rows y and
+  // y + 2 exactly 8 banks apart (40 words), so the 4 x 8 words of one load instruction fall into 32 different banks
+  // (consecutive rows, 20 words apart, collide two-way).  Steps come in pairs: rows 8 s + 2 yq, then rows 8 s + 1 + 2 yq.
+  const int n_steps2 = (zh + 7) >> 3;                                 // <= 8
+  // flag bit of (pair s, row parity e) = 8 e + s; the bits whose row 8 s + e + 2 yq lies inside the zone (both halves):
+  const int ne = max(0, (zh - 2 * yq + 7) >> 3), no = max(0, (zh - 2 * yq - 1 + 7) >> 3);
+  const uint32_t step_ok = (((1u << ne) - 1u) | (((1u << no) - 1u) << 8)) * 0x00010001u;
 
   bool patch_ready = false;
   unsigned long long keep0 = 0ull, keep1 = 0ull;
@@ -604,6 +612,10 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
     // -- a necessary condition for a 9-arc: 9 contiguous ring pixels always contain two ADJACENT compass pixels, i.e. one
     // of {0, 8} and one of {4, 12}; brighter arc => min(max(r0, r8), max(r4, r12)) > v + t, darker arc =>
     // max(min(r0, r8), min(r4, r12)) < v - t.  Four pixels per lane from aligned words, two per register half.
+    // The flags stay in the lane: bit 8 e + s of the low / high half of acc_a = pixels 0 / 2 of the lane's item in row
+    // 8 s + e + 2 yq, acc_b likewise pixels 1 / 3.  Then the lanes expand their bits into the dense candidate list (exclusive scan
+    // of the counts), so that the next stage runs on dense lanes.
+    int n_cand = 0;
     {
       const uint32_t c1 = 0x80008000u - (uint32_t)(t + 1) * 0x00010001u;
       for (int xp = 0; xp < n_xp; ++xp)
@@ -613,64 +625,51 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
         // flag masks of the lane's valid pixels: pixels (0, 2) live in bits 15 / 31 of one register, (1, 3) of another
         const uint32_t ma = ((vm & 1u) ? 0x8000u : 0u) | ((vm & 4u) ? 0x80000000u : 0u), mb = ((vm & 2u) ? 0x8000u : 0u) | ((vm & 8u) ? 0x80000000u : 0u);
         const uint32_t bv = (uint32_t)(a0 + min(zx0, (zw - 1) & ~3)); // first byte of the item in its patch row (idle lanes stay inside the row)
-        const uint32_t row0 = pat_u32 + (uint32_t)(yq + 3) * kPatPitch;
+        const uint32_t row0 = pat_u32 + (uint32_t)(2 * yq + 3) * kPatPitch;
         // aligned word + funnel shift: the 4 pixels, their left (x - 3) and right (x + 3) compass neighbours
         uint32_t pv = row0 + (bv & ~3u), pl = row0 + ((bv - 3u) & ~3u), pr = row0 + ((bv + 3u) & ~3u);
         const uint32_t sv = (bv & 3u) * 8u, sl = ((bv - 3u) & 3u) * 8u, sr = ((bv + 3u) & 3u) * 8u;
-        // rows past the zone (the last step of 4) read the slack rows below the patch and are masked out of the ballots
-        for (int y0 = 0; y0 < zh; y0 += 4, pv += 4 * kPatPitch, pl += 4 * kPatPitch, pr += 4 * kPatPitch)
+        uint32_t acc_a = 0u, acc_b = 0u;
+        // rows past the zone read whatever follows the patch inside the warp's slice; their flags are dropped by step_ok
+        auto pretest_rows = [&](uint32_t o, int bit, uint32_t &fa, uint32_t &fb) {
+          const uint32_t v = __funnelshift_r(lds_u32(pv + o), lds_u32(pv + o + 4u), sv);
+          const uint32_t lf = __funnelshift_r(lds_u32(pl + o), lds_u32(pl + o + 4u), sl);
+          const uint32_t rt = __funnelshift_r(lds_u32(pr + o), lds_u32(pr + o + 4u), sr);
+          const uint32_t up = __funnelshift_r(lds_u32(pv + o - 3 * kPatPitch), lds_u32(pv + o - 3 * kPatPitch + 4u), sv);
+          const uint32_t dn = __funnelshift_r(lds_u32(pv + o + 3 * kPatPitch), lds_u32(pv + o + 3 * kPatPitch + 4u), sv);
+          // pixels (1, 3) sit in the high bytes of the halves as loaded, pixels (0, 2) after a shift by one byte
+          fb |= fast_pretest2(v, dn, rt, up, lf, c1, mb) >> (15 - bit);
+          fa |= fast_pretest2(v << 8, dn << 8, rt << 8, up << 8, lf << 8, c1, ma) >> (15 - bit);
+        };
+        for (int s2 = 0; s2 < n_steps2; ++s2, pv += 8 * kPatPitch, pl += 8 * kPatPitch, pr += 8 * kPatPitch)
         {
-          const bool row_ok = y0 + yq < zh;
-          const uint32_t v = __funnelshift_r(lds_u32(pv), lds_u32(pv + 4u), sv);
-          const uint32_t lf = __funnelshift_r(lds_u32(pl), lds_u32(pl + 4u), sl);
-          const uint32_t rt = __funnelshift_r(lds_u32(pr), lds_u32(pr + 4u), sr);
-          const uint32_t up = __funnelshift_r(lds_u32(pv - 3 * kPatPitch), lds_u32(pv - 3 * kPatPitch + 4u), sv);
-          const uint32_t dn = __funnelshift_r(lds_u32(pv + 3 * kPatPitch), lds_u32(pv + 3 * kPatPitch + 4u), sv);
-          const uint32_t fa = fast_pretest2(v & 0x00ff00ffu, dn & 0x00ff00ffu, rt & 0x00ff00ffu, up & 0x00ff00ffu, lf & 0x00ff00ffu, c1) & ma;
-          const uint32_t fb = fast_pretest2(__byte_perm(v, 0u, 0x4341), __byte_perm(dn, 0u, 0x4341), __byte_perm(rt, 0u, 0x4341),
-                                            __byte_perm(up, 0u, 0x4341), __byte_perm(lf, 0u, 0x4341), c1) & mb;
-          // four ballots (one per pixel of the items) instead of a bit interleave: byte q of ballot k = row q, pixels 4 i + k
-          const unsigned b0 = __ballot_sync(FULL, row_ok && (fa & 0x8000u)), b1 = __ballot_sync(FULL, row_ok && (fb & 0x8000u));
-          const unsigned b2 = __ballot_sync(FULL, row_ok && (fa >> 31)), b3 = __ballot_sync(FULL, row_ok && (fb >> 31));
-          const uint32_t w = __byte_perm(__byte_perm(b0, b1, sel_q), __byte_perm(b2, b3, sel_q), 0x5410);
-          if (xi == 0 && row_ok) s_mask32[2 * (y0 + yq) + xp] = w;
+          pretest_rows(0u, s2, acc_a, acc_b);
+          pretest_rows((uint32_t)kPatPitch, 8 + s2, acc_a, acc_b);
         }
-      }
-    }
-    __syncwarp();
-
-    // row masks -> dense candidate list (lane <-> rows lane and lane + 32), so that the next stage runs on dense lanes
-    int n_cand;
-    {
-      uint32_t m[4];
+        acc_a &= step_ok;
+        acc_b &= step_ok;
+        const int cnt = __popc(acc_a) + __popc(acc_b);
+        int inc = cnt;
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-      {
-        const bool ok = lane + 32 * h < zh;
-        m[2 * h] = ok ? s_mask32[2 * (lane + 32 * h)] : 0u;
-        m[2 * h + 1] = (ok && n_xp == 2) ? s_mask32[2 * (lane + 32 * h) + 1] : 0u;
-      }
-      const int cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-      int inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-      {
-        const int up = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += up;
-      }
-      n_cand = __shfl_sync(FULL, inc, 31);
-      uint32_t wa = cand_u32 + 2u * (uint32_t)(inc - cnt);
-#pragma unroll
-      for (int h = 0; h < 4; ++h)
-      {
-        uint32_t w = m[h];
-        const uint32_t code0 = (uint32_t)((lane + 32 * (h >> 1)) * kZoneMax + 32 * (h & 1));
-        while (w)
+        for (int o = 1; o < 32; o <<= 1)
         {
-          const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
-          w &= w - 1u;
-          sts_u16_if(wa, code0 + 4u * (b & 7u) + (b >> 3), true);
-          wa += 2u;
+          const int up = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += up;
+        }
+        uint32_t wa = cand_u32 + 2u * (uint32_t)(n_cand + inc - cnt);
+        n_cand += __shfl_sync(FULL, inc, 31);
+        const uint32_t code0 = (uint32_t)(2 * yq * kZoneMax + zx0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+        {
+          uint32_t w = h == 0 ? acc_a : acc_b;
+          while (w)
+          {
+            const uint32_t b = (uint32_t)__ffs((int)w) - 1u; // pair s = b & 7, row parity e = (b >> 3) & 1, pixel = 2 (b >> 4) + h
+            w &= w - 1u;
+            sts_u16_if(wa, code0 + (b & 7u) * (8u * kZoneMax) + ((b >> 3) & 1u) * kZoneMax + (b >> 4) * 2u + (uint32_t)h, true);
+            wa += 2u;
+          }
         }
       }
     }
