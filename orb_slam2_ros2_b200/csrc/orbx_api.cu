@@ -99,6 +99,7 @@ int build_tables(orbx_ctx *c)
   c->levels.assign(nl, Level());
   std::vector<int> tab_ofs;
   std::vector<short2> tab_coef;
+  std::vector<uint4> tab_pair;
   std::vector<long long> strips; // 24.40 fixed point
 
   // scale factors (:283-289), per-level quotas (:291-301), level sizes (:305-317)
@@ -147,6 +148,38 @@ int build_tables(orbx_ctx *c)
       {
         const int a = eff(gx), b = eff(gx + 1);
         if (std::max(a, b) + 1 - (std::min(a, b) & ~3) > 7) L.pair_window = 0;
+      }
+      // One entry per pair of columns (rx, rx + 1), rx = -4 + 2 j, of the tile grid incl. the 3-px halo (REFLECT_101):
+      // value = src[sx] * ax + src[min(sx + 1, W - 1)] * ay; the second tap is always read at +1: in the last column (sx == W - 1,
+      // where the table has ay == 0) the pair moves one pixel left with the weights swapped.
+      L.tab_pair = (int)tab_pair.size();
+      const uint32_t pitch0 = (uint32_t)c->levels[0].pitch;
+      auto column = [&](int rx, uint32_t &sx, uint32_t &coef) {
+        sx = 0, coef = 0; // columns beyond the level + halo: weight 0 -> value 0
+        if (rx >= L.w + kHalo) return;
+        const int gx = rx < 0 ? -rx : (rx >= L.w ? 2 * (L.w - 1) - rx : rx);
+        sx = (uint32_t)tab_ofs[L.tab_x + gx];
+        uint32_t ax = (uint32_t)tab_coef[L.tab_x + gx].x, ay = (uint32_t)tab_coef[L.tab_x + gx].y;
+        if (sx + 1u > (uint32_t)(g.width - 1)) sx = (uint32_t)(g.width - 2), ay = ax + ay, ax = 0;
+        coef = ax | (ay << 16);
+      };
+      const int n_tx = (L.w + kTileW - 1) / kTileW;
+      for (int j = 0; j < n_tx * (kTileW / 2) + 4; ++j)
+      {
+        uint32_t sxa, sxb, ca, cb;
+        column(-4 + 2 * j, sxa, ca);
+        column(-3 + 2 * j, sxb, cb);
+        uint32_t base_a, base_b;
+        if (L.pair_window)
+        { // both tap pairs inside the aligned 8 bytes that start at the lower column's word, never beyond the row's pitch
+          const uint32_t lo = ca == 0u ? sxb : (cb == 0u ? sxa : std::min(sxa, sxb));
+          base_a = base_b = std::min(lo & ~3u, pitch0 - 8u);
+        }
+        else
+          base_a = std::min(sxa & ~3u, pitch0 - 8u), base_b = std::min(sxb & ~3u, pitch0 - 8u);
+        const uint32_t oa = ca == 0u ? 0u : sxa - base_a, ob = cb == 0u ? 0u : sxb - base_b;
+        if (oa > 6u || ob > 6u) return fail(c, ORBX_ERR_INVALID_ARG, "resize window does not fit 8 bytes");
+        tab_pair.push_back(make_uint4(base_a | ((oa | ((oa + 1u) << 4)) << 16), base_b | ((ob | ((ob + 1u) << 4)) << 16), ca, cb));
       }
     }
     for (int y0 = 0; y0 < L.h; y0 += kTileH)
@@ -347,6 +380,7 @@ int build_tables(orbx_ctx *c)
   if ((rc = dev_upload(c, &p.cells, c->cells))) return rc;
   if ((rc = dev_upload(c, &p.tab_ofs, tab_ofs))) return rc;
   if ((rc = dev_upload(c, &p.tab_coef, tab_coef))) return rc;
+  if ((rc = dev_upload(c, &p.tab_pair, tab_pair))) return rc;
   if ((rc = dev_upload(c, &p.strips_fx, strips))) return rc;
   if ((rc = dev_upload(c, &p.pattern, pat))) return rc;
 

@@ -43,6 +43,7 @@ struct Level
   int quota;        // mvnFeatures[level]
   int tab_x, tab_y; // offsets into the resize tables (unused for level 0)
   int area2x;       // exact 2x2 decimation: cv::resize re-routes INTER_LINEAR to INTER_AREA
+  int tab_pair;     // offset into Params::tab_pair (one entry per pair of adjacent columns of the tile grid, incl. halo)
   int pair_window;  // resize: the taps of two adjacent columns always lie inside one aligned 8-byte window of a level-0 row
   // FAST cell grid (src/ORBExtractor.cc:334-343)
   int n_cols, n_rows, w_cell, h_cell;
@@ -99,6 +100,7 @@ struct Params
   const Cell *cells;
   const int *tab_ofs;     // resize source index per destination index
   const short2 *tab_coef; // resize 11-bit coefficients
+  const uint4 *tab_pair;  // resize, two adjacent columns: {window_a | sel_a << 16, window_b | sel_b << 16, coef_a, coef_b}
   const long long *strips_fx; // root strip column bounds, 24.40 fixed point (exact: they are float-rounded values)
   const char4 *pattern;   // 256 x (x1, y1, x2, y2)
   // inputs

@@ -249,28 +249,6 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_level0_kernel(const Param
   pyr_blur_cols(sm, t, lh, pitch, p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off);
 }
 
-// one column of a resized level: source column, packed coefficients (ax | ay << 16)
-__device__ __forceinline__ void resize_column(const Params &p, const Level &L, int rx, int W, uint32_t &sx, uint32_t &coef)
-{
-  sx = 0u, coef = 0u; // columns beyond the level + halo: weight 0 -> value 0
-  if (rx < L.w + kHalo)
-  {
-    const int gx = refl101(rx, L.w);
-    sx = (uint32_t)p.tab_ofs[L.tab_x + gx];
-    const short2 a = p.tab_coef[L.tab_x + gx];
-    uint32_t ax = (uint32_t)a.x, ay = (uint32_t)a.y;
-    // value = src[sx] * ax + src[min(sx + 1, W - 1)] * ay.  The second tap is always read at +1: in the last column
-    // (sx == W - 1, where the table has ay == 0) the pair is moved one pixel left with the weights swapped.
-    if (sx + 1u > (uint32_t)(W - 1))
-    {
-      sx = (uint32_t)(W - 2);
-      ay = ax + ay;
-      ax = 0;
-    }
-    coef = ax | (ay << 16);
-  }
-}
-
 template <bool kSharedWindow> __device__ __forceinline__ void resize_rows(PyrShared &sm, const uint8_t *__restrict__ l0, int rows, int q, int grp,
                                                                            uint32_t base_a, uint32_t base_b, uint32_t sel_a, uint32_t sel_b,
                                                                            uint32_t coef_a, uint32_t coef_b)
@@ -323,7 +301,7 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Param
   const int img = blockIdx.y;
   const Level &L = p.levels[t.level];
   const int lw = L.w, lh = L.h, pitch = L.pitch;
-  const int W = p.width, H = p.height;
+  const int H = p.height;
   const int area2x = L.area2x;
   const int tid = threadIdx.x;
   const int rows = tile_rows(t, lh);
@@ -377,24 +355,14 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Param
     const int q = tid % kPairs, grp = tid / kPairs;
     if (grp < kPairRows)
     {
-      const int rx = t.x0 - 4 + 2 * q; // columns rx, rx + 1 (rx = x0 - 4 and x0 + 67 are not used by anybody)
-      uint32_t sxa, sxb, coef_a, coef_b;
-      resize_column(p, L, rx, W, sxa, coef_a);
-      resize_column(p, L, rx + 1, W, sxb, coef_b);
+      // columns rx = x0 - 4 + 2 q and rx + 1 (x0 - 4 and x0 + 67 are not used by anybody): their taps come from the level's
+      // pair table (built on the host next to the resize tables): window offsets into a level-0 row, PRMT selectors of the two
+      // tap pairs, packed coefficients ax | ay << 16 (0 for columns beyond the level + halo: value 0)
+      const uint4 e = p.tab_pair[L.tab_pair + (t.x0 >> 1) + q];
       if (L.pair_window)
-      {
-        // both tap pairs inside the aligned 8 bytes that start at the lower column's word (host-checked for the level)
-        const uint32_t lo = (coef_a == 0u) ? sxb : ((coef_b == 0u) ? sxa : min(sxa, sxb));
-        const uint32_t base = min(lo & ~3u, pitch0 - 8u); // the window never leaves the row's pitch (the clamp keeps offsets <= 6)
-        const uint32_t oa = (coef_a == 0u) ? 0u : sxa - base, ob = (coef_b == 0u) ? 0u : sxb - base;
-        resize_rows<true>(sm, l0, rows, q, grp, base, base, oa | ((oa + 1u) << 4), ob | ((ob + 1u) << 4), coef_a, coef_b);
-      }
+        resize_rows<true>(sm, l0, rows, q, grp, e.x & 0xffffu, e.x & 0xffffu, e.x >> 16, e.y >> 16, e.z, e.w);
       else
-      {
-        const uint32_t base_a = min(sxa & ~3u, pitch0 - 8u), base_b = min(sxb & ~3u, pitch0 - 8u);
-        const uint32_t oa = sxa - base_a, ob = sxb - base_b;
-        resize_rows<false>(sm, l0, rows, q, grp, base_a, base_b, oa | ((oa + 1u) << 4), ob | ((ob + 1u) << 4), coef_a, coef_b);
-      }
+        resize_rows<false>(sm, l0, rows, q, grp, e.x & 0xffffu, e.y & 0xffffu, e.x >> 16, e.y >> 16, e.z, e.w);
     }
   }
   __syncthreads();
