@@ -503,7 +503,7 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
   }
   {
     NvtxRange q("orbx:orient_brief");
-    launch_orient_brief(p, 2 * nf, s);
+    launch_orient_brief(p, c->maps_blur, 2 * nf, s);
   }
   {
     NvtxRange q("orbx:frame_index"); // createRowIndexDB of the right keypoints + initGrid of the left ones, one launch
@@ -608,20 +608,25 @@ int build_level_maps(orbx_ctx *c)
   cudaDriverEntryPointQueryResult qres;
   ORBX_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, ORBX_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
-  std::vector<CUtensorMap> maps(c->levels.size());
+  // FAST: box = 80 bytes x the level's tallest patch over `pyr`; BRIEF: box = 64 bytes x 37 rows (the blurred patch a rotated
+  // pattern can reach) over `blur`
+  std::memset(&c->maps, 0, sizeof(c->maps));
+  std::memset(&c->maps_blur, 0, sizeof(c->maps_blur));
   for (size_t l = 0; l < c->levels.size(); ++l)
   {
     const Level &L = c->levels[l];
     const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)c->n_img_max};
     const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)c->p.pyr_img_stride};
-    const cuuint32_t box[3] = {80u, (cuuint32_t)L.fast_box_h, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = ((EncodeFn)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->p.pyr + L.pyr_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint32_t box[3] = {80u, (cuuint32_t)L.fast_box_h, 1u};
+    CUresult r = ((EncodeFn)fn)(&c->maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->p.pyr + L.pyr_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(c, ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed for level " + std::to_string(l));
+    const cuuint32_t box_b[3] = {64u, 37u, 1u};
+    r = ((EncodeFn)fn)(&c->maps_blur.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->p.blur + L.pyr_off, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (blur) failed for level " + std::to_string(l));
   }
-  std::memset(&c->maps, 0, sizeof(c->maps));
-  for (size_t l = 0; l < maps.size(); ++l) c->maps.m[l] = maps[l];
   c->p.img0 = 0;
   return ORBX_OK;
 }
@@ -632,7 +637,7 @@ int run_extract(orbx_ctx *c, const Params &p, int n_images)
   launch_pyramid(p, n_images, c->stream);
   launch_fast(p, c->maps, n_images, c->stream);
   launch_quadtree(p, n_images, c->qt_smem, c->stream);
-  launch_orient_brief(p, n_images, c->stream);
+  launch_orient_brief(p, c->maps_blur, n_images, c->stream);
   c->launches += 3 + kPyramidLaunches;
   ORBX_CUDA(c, cudaGetLastError());
   return ORBX_OK;
@@ -975,7 +980,7 @@ extern "C"
     ORBX_CUDA(c, cudaEventRecord(ev[2], c->stream));
     launch_quadtree(p, ni, c->qt_smem, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[3], c->stream));
-    launch_orient_brief(p, ni, c->stream);
+    launch_orient_brief(p, c->maps_blur, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[4], c->stream));
     launch_frame_index(p, n_frames, 2, true, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[5], c->stream));

@@ -224,7 +224,7 @@ const void *pyramid_kernel_symbol(); // host handle of the level-0 pyramid kerne
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 int fast_configure(const Params &p); // opt in to the dynamic shared memory of the FAST kernel
 void launch_quadtree(const Params &p, int n_images, size_t smem_bytes, cudaStream_t s);
-void launch_orient_brief(const Params &p, int n_images, cudaStream_t s);
+void launch_orient_brief(const Params &p, const LevelMaps &blur_maps, int n_images, cudaStream_t s);
 void launch_stereo(const Params &p, int n_frames, cudaStream_t s);
 void launch_rgbd(const Params &p, int n_frames, cudaStream_t s);
 void launch_frame_index(const Params &p, int n_frames, int image_stride, bool with_rowindex, cudaStream_t s); // row index (stereo) + initGrid

@@ -2291,7 +2291,8 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 constexpr int kBriefWarps = 8;
 constexpr int kBriefReach = 18;                          // cvRound of the largest rotated pattern radius, |(13, 13)| = 18.38
 constexpr int kBriefPatchRows = 2 * kBriefReach + 1;     // 37
-constexpr uint32_t kBriefPatchPitch = 40;                // bytes: 37 + up to 3 bytes of alignment shift
+constexpr uint32_t kBriefPatchPitch = 64;                // bytes = width of the TMA box: up to 15 bytes of alignment shift + 37
+constexpr int kBriefPatchBytes = 2432;                   // 37 rows x 64 bytes, rounded up to the 128-byte alignment of a TMA destination
 
 __device__ __forceinline__ void undistort_point(const Params &p, float u, float v, float &uo, float &vo)
 {
@@ -2328,7 +2329,7 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a_u8x4, uint32_t b_s8x4, int 
 
 // kBriefGroup keypoints per warp: lane j < kBriefGroup evaluates atan2 / sincos of keypoint j (once, not 32 times).  Large
 // batches use 8 (throughput), a handful of images 2 (shorter warps: single-frame latency).
-template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const Params p)
+template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5) orient_brief_kernel(const Params p, const __grid_constant__ LevelMaps blur_maps)
 {
   // Per-lane DP4A weights of the radius-15 disc for the moment pass below (lane <-> word wk of row 3 i + rg, see there):
   // byte b of s_wx[i][lane] = dx of that byte if it lies inside the disc (|dx| <= umax[|dy|]), else 0; s_wy: dy likewise.
@@ -2379,7 +2380,6 @@ template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5
   if (slot0 >= total) return;
   const int n_here = min(kBriefGroup, total - slot0);
   const uint8_t *__restrict__ pyr_img = p.pyr + (size_t)img * p.pyr_img_stride;
-  const uint8_t *__restrict__ blr_img = p.blur + (size_t)img * p.pyr_img_stride;
 
   // Pass 1, keypoint by keypoint: getGrayCentroid (:465-487), moments over the radius-15 disc of the un-blurred level.
   // The disc's 31 rows are fetched as aligned words, 3 rows x 9 words per warp request (3 cache lines); a lane takes its
@@ -2423,46 +2423,53 @@ template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5
     if (lane == j) my_e = e, my_level = level, my_m10 = m10, my_m01 = m01;
   }
 
+  // Pass 2, keypoint by keypoint: computeBRIEF (:427-456) with rotateTemplate (:534-540): double products, float result,
+  // float add, round-half-even; lane <-> descriptor byte.
+  // The rotated pattern stays within 18 px of the keypoint (|(13, 13)| = 18.4): the 37 x 37 blurred patch around it arrives in
+  // shared memory through ONE TMA box load (cp.async.bulk.tensor.3d from the level's {pitch, rows, images} byte tensor over
+  // `blur`; box = 64 bytes x 37 rows, its first column aligned down to 16 bytes as TMA requires), so that the 512 scattered
+  // byte gathers of the descriptor hit shared-memory banks instead of 512 different L1 sectors.  Two buffers per warp: the
+  // patch of keypoint j + 1 is in flight while keypoint j is evaluated; the first one is requested before atan2 / sincos.
+  // Keypoints keep 19 px from the border (mnBorderSize), so rows y - 18 .. y + 18 exist; whatever the box covers beyond the
+  // level's pitch is zero-filled and never read.
+  __shared__ __align__(128) uint8_t s_patch[kBriefWarps][2][kBriefPatchBytes];
+  __shared__ __align__(8) uint64_t s_bar[kBriefWarps][2];
+  const int wid = threadIdx.x >> 5;
+  if (lane == 0)
+  {
+    mbar_init(&s_bar[wid][0], 1);
+    mbar_init(&s_bar[wid][1], 1);
+  }
+  __syncwarp();
+  auto request_patch = [&](int j) { // all lanes call; lane 0 issues the load of keypoint j's patch into buffer j & 1
+    const uint32_t e = __shfl_sync(FULL, my_e, j);
+    const int level = __shfl_sync(FULL, my_level, j);
+    if (lane == 0)
+    {
+      const int kx_i = (int)(e & 0xfffu), ky_i = (int)((e >> 12) & 0xfffu);
+      mbar_expect_tx(&s_bar[wid][j & 1], kBriefPatchRows * kBriefPatchPitch);
+      tma_load_3d(s_patch[wid][j & 1], &blur_maps.m[level], (kx_i - kBriefReach) & ~15, ky_i - kBriefReach, p.img0 + img, &s_bar[wid][j & 1]);
+    }
+  };
+  request_patch(0);
+
   // orientation of keypoint `lane` (lanes >= n_here compute on zeros and are ignored)
   const double theta = atan2((double)my_m01, (double)my_m10);
   double sn, cs;
   sincos(theta, &sn, &cs);
 
-  // Pass 2, keypoint by keypoint: computeBRIEF (:427-456) with rotateTemplate (:534-540): double products, float result,
-  // float add, round-half-even; lane <-> descriptor byte
-  __shared__ uint32_t s_patch[kBriefWarps][kBriefPatchRows * (kBriefPatchPitch / 4)];
-  uint32_t *my_patch = s_patch[threadIdx.x >> 5];
-  const int srg = min(lane / 10, 2), swk = lane - 10 * (lane / 10); // staging: lane <-> word swk of row 3 i + srg (lanes 30, 31 duplicate 20, 21)
 #pragma unroll 1
   for (int j = 0; j < n_here; ++j)
   {
     const uint32_t e = __shfl_sync(FULL, my_e, j);
-    const int level = __shfl_sync(FULL, my_level, j);
     const double sj = __shfl_sync(FULL, sn, j), cj = __shfl_sync(FULL, cs, j);
-    const Level &L = p.levels[level];
     const float fx = (float)(e & 0xfffu), fy = (float)((e >> 12) & 0xfffu);
-    // The rotated pattern stays within 18 px of the keypoint (|(13, 13)| = 18.4): the 37 x 37 blurred patch around it is staged
-    // in shared memory with coalesced word loads (3 rows x 10 aligned words per warp request, 13 requests), so that the 512
-    // scattered byte gathers of the descriptor hit shared-memory banks instead of 512 different L1 sectors.  Keypoints keep
-    // 19 px from the border (mnBorderSize), so rows y - 18 .. y + 18 exist; the aligned 40-byte row window may start up to
-    // 3 bytes left of / end a few bytes right of the image row, which is still inside the level's pitch-padded buffer.
     const int kx_i = (int)(e & 0xfffu), ky_i = (int)((e >> 12) & 0xfffu);
-    const size_t pitch = (size_t)L.pitch;
-    const uint8_t *src0 = blr_img + L.pyr_off + (size_t)(ky_i - kBriefReach) * pitch + (kx_i - kBriefReach);
-    const uint32_t mis = (uint32_t)(size_t)src0 & 3u;
-    {
-      const uint8_t *gp = src0 - mis + 4 * swk + (size_t)srg * pitch;
-      const uint32_t pitch3 = 3u * (uint32_t)pitch;
-      uint32_t w[13];
-#pragma unroll
-      for (int i = 0; i < 12; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t *>(gp + (uint64_t)pitch3 * (uint32_t)i)); // one IMAD.WIDE per address
-      w[12] = __ldg(reinterpret_cast<const uint32_t *>(src0 - mis + 4 * swk + 36 * pitch)); // row 36 (all lanes: duplicates are benign)
-      __syncwarp(); // the previous keypoint's gathers are done
-#pragma unroll
-      for (int i = 0; i < 12; ++i) my_patch[(3 * i + srg) * (kBriefPatchPitch / 4) + swk] = w[i];
-      my_patch[36 * (kBriefPatchPitch / 4) + swk] = w[12];
-      __syncwarp();
-    }
+    __syncwarp(); // keypoint j - 1's gathers from the other buffer are done
+    if (j + 1 < n_here) request_patch(j + 1);
+    mbar_wait(&s_bar[wid][j & 1], (uint32_t)((j >> 1) & 1));
+    const uint32_t mis = (uint32_t)(kx_i - kBriefReach) & 15u; // column of the patch origin inside the box
+    const uint32_t *my_patch = reinterpret_cast<const uint32_t *>(s_patch[wid][j & 1]);
     // cvRound without the conversion unit (below) leaves 0x4B400000 in both coordinates; that, the patch origin and the
     // alignment shift fold into one constant (modulo 2^32), so one 32-bit multiply-add gives the byte index into the patch
     uint32_t kofs = mis - 0x4B400000u * (kBriefPatchPitch + 1u) - (uint32_t)(ky_i - kBriefReach) * kBriefPatchPitch - (uint32_t)(kx_i - kBriefReach);
@@ -2519,17 +2526,17 @@ template <int kBriefGroup> __global__ void __launch_bounds__(kBriefWarps * 32, 5
   }
 }
 
-void launch_orient_brief(const Params &p, int n_images, cudaStream_t s)
+void launch_orient_brief(const Params &p, const LevelMaps &blur_maps, int n_images, cudaStream_t s)
 {
   if (n_images > 4)
   {
     dim3 grid((p.n_features + kBriefWarps * 8 - 1) / (kBriefWarps * 8), n_images);
-    orient_brief_kernel<8><<<grid, kBriefWarps * 32, 0, s>>>(p);
+    orient_brief_kernel<8><<<grid, kBriefWarps * 32, 0, s>>>(p, blur_maps);
   }
   else
   {
     dim3 grid((p.n_features + kBriefWarps * 2 - 1) / (kBriefWarps * 2), n_images);
-    orient_brief_kernel<2><<<grid, kBriefWarps * 32, 0, s>>>(p);
+    orient_brief_kernel<2><<<grid, kBriefWarps * 32, 0, s>>>(p, blur_maps);
   }
 }
 
