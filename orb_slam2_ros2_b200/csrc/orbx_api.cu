@@ -291,6 +291,8 @@ int build_tables(orbx_ctx *c)
     off += up(area * 2, 16); // worst case: every zone pixel is a stage-1 candidate
     p.fast_off_mask = off;
     off += up(zh * 8, 16); // keep masks (one 64-bit mask per zone row)
+    p.fast_off_lut = off;
+    off += 64;             // the 32-entry flag-bit -> code table of the candidate expansion
     p.fast_warp_bytes = up(off, 128);
     if (4 * (size_t)p.fast_warp_bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cells too large for shared memory");
   }

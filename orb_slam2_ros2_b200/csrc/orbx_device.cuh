@@ -94,7 +94,7 @@ struct Params
   int width, height;
   int stereo; // images are interleaved left/right pairs
   // per-warp shared-memory slice of the FAST kernel (one warp per cell): patch at 0, then these offsets
-  int fast_off_bar, fast_off_map, fast_off_cand, fast_off_mask, fast_map_pitch, fast_warp_bytes;
+  int fast_off_bar, fast_off_map, fast_off_cand, fast_off_mask, fast_off_lut, fast_map_pitch, fast_warp_bytes;
   const Level *levels;
   const Tile *tiles;
   const Cell *cells;

@@ -189,56 +189,73 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_level0_kernel(const Param
   const int tid = threadIdx.x;
   const int rows = tile_rows(t, lh);
 
-  if (tid < rows)
+  // Row table for all kSrcH entries (rows beyond `rows` repeat row 0 and are never consumed): .x = byte offset of the source row,
+  // .z = 1 when the row may be read with aligned word loads.  Rows 0 and lh - 1 are gathered byte by byte: an aligned word
+  // may reach up to 3 bytes outside the caller's buffer there.
+  if (tid < kSrcH)
   {
-    const int gy = refl101(t.y0 + tid - kHalo, lh);
-    // rows 0 and lh - 1 are gathered byte by byte: an aligned word may reach up to 3 bytes outside the caller's buffer there
-    sm.row[tid] = make_uint4((uint32_t)gy * sstride, 0u, (gy > 0 && gy < lh - 1) ? 1u : 0u, 0u);
+    const int gy = tid < rows ? refl101(t.y0 + tid - kHalo, lh) : 0;
+    sm.row[tid] = make_uint4((uint32_t)gy * sstride, 0u, (tid < rows && gy > 0 && gy < lh - 1) ? 1u : 0u, 0u);
   }
   __syncthreads();
 
-  // stage A: thread <-> word column j (source columns x0 - 4 + 4 j .. + 3), kWordRows rows per pass
+  // stage A: thread <-> word column j (source columns x0 - 4 + 4 j .. + 3), kWordRows rows per pass.  Word columns jl .. jh lie
+  // completely inside the image: two aligned loads + a funnel shift per word, no per-row branch.  The others (the left / right
+  // borders: REFLECT_101, zero beyond the level + halo) and the first / last image row are patched byte by byte afterwards.
+  const int jl = t.x0 == 0 ? 1 : 0, jh = min(kSrcWords - 1, (lw - t.x0) >> 2);
   {
     const int j = tid % kSrcWords, grp = tid / kSrcWords;
-    if (grp < kWordRows)
+    if (grp < kWordRows && j >= jl && j <= jh)
     {
-      const int rx = t.x0 - 4 + 4 * j;
-      const bool col_fast = rx >= 0 && rx + 4 <= lw;
-      uint32_t *dst = reinterpret_cast<uint32_t *>(sm.src) + kSrcWord0 + j;
-      const uint8_t *__restrict__ col_src = src + rx;
+      uint32_t *dst = reinterpret_cast<uint32_t *>(sm.src) + kSrcWord0 + j + grp * (kSrcPitch / 4);
+      const uint8_t *col_src = src + (t.x0 - 4 + 4 * j);
+      asm volatile("" : "+l"(col_src)); // one register pair: a row address is one IMAD.WIDE.U32
+      const uint4 *rp = sm.row + grp;
       constexpr int U = 5; // 70 rows = 14 rows per pass x 5: all loads of a tile are issued before the first use
-      uint32_t w0[U], w1[U], sh[U];
-      bool fast[U];
+      static_assert(kWordRows * U == kSrcH, "the row passes tile the buffer exactly");
+      uint32_t w0[U], w1[U], sh[U], ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
       {
-        const int ty = min(grp + u * kWordRows, rows - 1);
-        const uint4 r = sm.row[ty];
-        const uint8_t *a = col_src + (size_t)r.x;
-        fast[u] = col_fast && r.z != 0u;
-        if (fast[u])
+        const uint4 r = rp[u * kWordRows];
+        const uint8_t *a = col_src + r.x;
+        ok[u] = r.z;
+        w0[u] = w1[u] = 0u;
+        if (ok[u])
         {
           const uint32_t *al = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
           w0[u] = al[0], w1[u] = al[1];
-          sh[u] = (uint32_t)reinterpret_cast<uintptr_t>(a) << 3; // funnel shifts take the amount modulo 32
         }
-        else
-        {
-          // borders: REFLECT_101 per byte; columns beyond the level + halo are zero
-          const uint8_t *rowp = src + (size_t)r.x;
-          uint32_t v = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-          {
-            const int cx = rx + k;
-            if (cx < lw + kHalo) v |= (uint32_t)rowp[refl101(cx, lw)] << (8 * k);
-          }
-          w0[u] = v, w1[u] = 0u, sh[u] = 0u;
-        }
+        sh[u] = (uint32_t)reinterpret_cast<uintptr_t>(a) << 3; // funnel shifts take the amount modulo 32
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (grp + u * kWordRows < rows) dst[(grp + u * kWordRows) * (kSrcPitch / 4)] = __funnelshift_r(w0[u], w1[u], sh[u]);
+        if (ok[u]) dst[u * kWordRows * (kSrcPitch / 4)] = __funnelshift_r(w0[u], w1[u], sh[u]);
+    }
+  }
+  {
+    auto gather_word = [&](int ty, int j) { // REFLECT_101 per byte; columns beyond the level + halo are zero
+      const uint8_t *rowp = src + (size_t)sm.row[ty].x;
+      const int rx = t.x0 - 4 + 4 * j;
+      uint32_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (rx + k < lw + kHalo) v |= (uint32_t)rowp[refl101(rx + k, lw)] << (8 * k);
+      reinterpret_cast<uint32_t *>(sm.src)[ty * (kSrcPitch / 4) + kSrcWord0 + j] = v;
+    };
+    // border word columns [0, jl) and (jh, kSrcWords), all rows
+    const int n_slow = jl + (kSrcWords - 1 - jh);
+    for (int i = tid; i < rows * n_slow; i += kPyrThreads)
+    {
+      const int ty = i / n_slow, k = i - ty * n_slow;
+      gather_word(ty, k < jl ? k : jh + 1 + (k - jl));
+    }
+    // image rows 0 and lh - 1 (at most one tile row each), inner word columns
+    const int ty_first = kHalo - t.y0, ty_last = lh - 1 + kHalo - t.y0;
+    for (int i = tid; i < 2 * kSrcWords; i += kPyrThreads)
+    {
+      const int ty = i < kSrcWords ? ty_first : ty_last, j = i < kSrcWords ? i : i - kSrcWords;
+      if (ty >= 0 && ty < rows && j >= jl && j <= jh && (i < kSrcWords || ty_last != ty_first)) gather_word(ty, j);
     }
   }
   __syncthreads();
@@ -519,6 +536,9 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
   uint8_t *const s_map = wbase + p.fast_off_map;
   unsigned long long *const s_keep = reinterpret_cast<unsigned long long *>(wbase + p.fast_off_mask);
   const uint32_t cand_u32 = smem_u32(wbase + p.fast_off_cand);
+  // flag bit -> candidate code offset (rows 8 s + e, pixel 2 (b >> 4)): a 32-entry table instead of four ALU operations per candidate
+  const uint32_t lut_u32 = smem_u32(wbase + p.fast_off_lut);
+  sts_u16_if(lut_u32 + 2u * (uint32_t)(threadIdx.x & 31), (uint32_t)(((threadIdx.x & 7) * 8 + ((threadIdx.x >> 3) & 1)) * kZoneMax + ((threadIdx.x >> 4) & 1) * 2), true);
   const int mp = p.fast_map_pitch;
 
   const Cell c = p.cells[cell];
@@ -635,7 +655,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p
           {
             const uint32_t b = (uint32_t)__ffs((int)w) - 1u; // pair s = b & 7, row parity e = (b >> 3) & 1, pixel = 2 (b >> 4) + h
             w &= w - 1u;
-            sts_u16_if(wa, code0 + (b & 7u) * (8u * kZoneMax) + ((b >> 3) & 1u) * kZoneMax + (b >> 4) * 2u + (uint32_t)h, true);
+            sts_u16_if(wa, code0 + lds_u16(lut_u32 + 2u * b) + (uint32_t)h, true);
             wa += 2u;
           }
         }
