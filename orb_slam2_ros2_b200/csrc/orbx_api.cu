@@ -177,13 +177,47 @@ int build_tables(orbx_ctx *c)
         }
         else
           base_a = std::min(sxa & ~3u, pitch0 - 8u), base_b = std::min(sxb & ~3u, pitch0 - 8u);
+        if (ca == 0u && cb == 0u && !tab_pair.empty() && (int)tab_pair.size() > L.tab_pair)
+          base_a = base_b = tab_pair.back().x & 0xffffu; // columns beyond the level: weight 0, any window inside the tile's source box
         const uint32_t oa = ca == 0u ? 0u : sxa - base_a, ob = cb == 0u ? 0u : sxb - base_b;
         if (oa > 6u || ob > 6u) return fail(c, ORBX_ERR_INVALID_ARG, "resize window does not fit 8 bytes");
         tab_pair.push_back(make_uint4(base_a | ((oa | ((oa + 1u) << 4)) << 16), base_b | ((ob | ((ob + 1u) << 4)) << 16), ca, cb));
       }
     }
-    for (int y0 = 0; y0 < L.h; y0 += kTileH)
-      for (int x0 = 0; x0 < L.w; x0 += kTileW) c->tiles.push_back(Tile{l, x0, y0, 0});
+    {
+      // level-0 source rectangle of every tile (pyramid_levels_kernel stages it through TMA when the level's box fits)
+      const size_t first_tile = c->tiles.size();
+      int box_w = 0, box_h = 0;
+      for (int y0 = 0; y0 < L.h; y0 += kTileH)
+        for (int x0 = 0; x0 < L.w; x0 += kTileW)
+        {
+          Tile t{l, x0, y0, 0};
+          if (l > 0 && !L.area2x)
+          {
+            uint32_t b_lo = 0xffffffffu, b_hi = 0;
+            for (int q = 0; q < kTileW / 2 + 4; ++q)
+            {
+              const uint4 e = tab_pair[(size_t)L.tab_pair + (x0 >> 1) + q];
+              b_lo = std::min(b_lo, std::min(e.x & 0xffffu, e.y & 0xffffu));
+              b_hi = std::max(b_hi, std::max(e.x & 0xffffu, e.y & 0xffffu));
+            }
+            const int sx0 = (int)(b_lo & ~15u);
+            const int gy_lo = std::max(y0 - kHalo, 0), gy_hi = std::min(y0 + kTileH + kHalo - 1, L.h - 1);
+            const int sy0 = std::min(std::max(tab_ofs[L.tab_y + gy_lo], 0), g.height - 1);
+            const int sy1 = std::min(std::max(tab_ofs[L.tab_y + gy_hi] + 1, 0), g.height - 1);
+            box_w = std::max(box_w, (int)b_hi + 8 - sx0);
+            box_h = std::max(box_h, sy1 - sy0 + 1);
+            t.src = sx0 | (sy0 << 16);
+          }
+          c->tiles.push_back(t);
+        }
+      box_w = (box_w + 15) & ~15;
+      L.src_box_w = L.src_box_h = 0;
+      if (box_w > 0 && box_w <= 256 && box_h <= 256 && box_w * box_h <= kPyrBoxBytesHost && !std::getenv("ORBX_PYR_NO_TMA"))
+        L.src_box_w = box_w, L.src_box_h = box_h;
+      else
+        for (size_t i = first_tile; i < c->tiles.size(); ++i) c->tiles[i].src = 0;
+    }
     if (l == 0) c->n_tiles0 = (int)c->tiles.size();
 
     // FAST cell grid (:334-362)
@@ -493,7 +527,7 @@ int run_stereo_range(orbx_ctx *c, cudaStream_t s, int frame0, int nf, const uint
   ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)nf * sizeof(int), s));
   {
     NvtxRange q("orbx:pyramid_blur");
-    launch_pyramid(p, 2 * nf, s);
+    launch_pyramid(p, c->maps_src, 2 * nf, s);
   }
   {
     NvtxRange q("orbx:fast_cells");
@@ -614,6 +648,7 @@ int build_level_maps(orbx_ctx *c)
   // pattern can reach) over `blur`
   std::memset(&c->maps, 0, sizeof(c->maps));
   std::memset(&c->maps_blur, 0, sizeof(c->maps_blur));
+  std::memset(&c->maps_src, 0, sizeof(c->maps_src));
   for (size_t l = 0; l < c->levels.size(); ++l)
   {
     const Level &L = c->levels[l];
@@ -624,6 +659,16 @@ int build_level_maps(orbx_ctx *c)
     CUresult r = ((EncodeFn)fn)(&c->maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->p.pyr + L.pyr_off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(c, ORBX_ERR_CUDA, "cuTensorMapEncodeTiled failed for level " + std::to_string(l));
+    if (L.src_box_w)
+    { // level-0 source rectangles of this level's tiles: the tensor is level 0 of `pyr`
+      const Level &L0 = c->levels[0];
+      const cuuint64_t dims0[3] = {(cuuint64_t)L0.pitch, (cuuint64_t)L0.h, (cuuint64_t)c->n_img_max};
+      const cuuint64_t strides0[2] = {(cuuint64_t)L0.pitch, (cuuint64_t)c->p.pyr_img_stride};
+      const cuuint32_t box_s[3] = {(cuuint32_t)L.src_box_w, (cuuint32_t)L.src_box_h, 1u};
+      r = ((EncodeFn)fn)(&c->maps_src.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->p.pyr + L0.pyr_off, dims0, strides0, box_s, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(c, ORBX_ERR_CUDA, "cuTensorMapEncodeTiled (resize source) failed for level " + std::to_string(l));
+    }
     const cuuint32_t box_b[3] = {64u, 37u, 1u};
     r = ((EncodeFn)fn)(&c->maps_blur.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->p.blur + L.pyr_off, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -636,7 +681,7 @@ int build_level_maps(orbx_ctx *c)
 // ORBExtractor ctor + extract for n_images device-resident images
 int run_extract(orbx_ctx *c, const Params &p, int n_images)
 {
-  launch_pyramid(p, n_images, c->stream);
+  launch_pyramid(p, c->maps_src, n_images, c->stream);
   launch_fast(p, c->maps, n_images, c->stream);
   launch_quadtree(p, n_images, c->qt_smem, c->stream);
   launch_orient_brief(p, c->maps_blur, n_images, c->stream);
@@ -976,7 +1021,7 @@ extern "C"
     const int ni = 2 * n_frames;
     ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)n_frames * sizeof(int), c->stream));
     ORBX_CUDA(c, cudaEventRecord(ev[0], c->stream));
-    launch_pyramid(p, ni, c->stream);
+    launch_pyramid(p, c->maps_src, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[1], c->stream));
     launch_fast(p, c->maps, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[2], c->stream));

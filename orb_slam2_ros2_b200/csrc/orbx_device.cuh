@@ -44,6 +44,7 @@ struct Level
   int tab_x, tab_y; // offsets into the resize tables (unused for level 0)
   int area2x;       // exact 2x2 decimation: cv::resize re-routes INTER_LINEAR to INTER_AREA
   int tab_pair;     // offset into Params::tab_pair (one entry per pair of adjacent columns of the tile grid, incl. halo)
+  int src_box_w, src_box_h; // TMA box that holds the level-0 source rectangle of any tile of this level (0: taps gathered from global memory)
   int pair_window;  // resize: the taps of two adjacent columns always lie inside one aligned 8-byte window of a level-0 row
   // FAST cell grid (src/ORBExtractor.cc:334-343)
   int n_cols, n_rows, w_cell, h_cell;
@@ -60,7 +61,8 @@ struct Level
 
 struct Tile
 {
-  int level, x0, y0, pad;
+  int level, x0, y0;
+  int src; // pyramid_levels_kernel: origin of the tile's level-0 source rectangle (TMA box), x | y << 16
 };
 
 struct Cell
@@ -219,7 +221,8 @@ struct BowArgs
 
 // launchers (orbx_kernels.cu / orbx_match.cu / orbx_serialize.cu / orbx_bow.cu); every call enqueues exactly one kernel on `s` (launch_pyramid: two)
 constexpr int kPyramidLaunches = 2;
-void launch_pyramid(const Params &p, int n_images, cudaStream_t s); // kPyramidLaunches kernels: level 0, then the resized levels
+constexpr int kPyrBoxBytesHost = 18 * 1024; // = kPyrBoxBytes of orbx_kernels.cu: shared-memory bytes a level's source box may take
+void launch_pyramid(const Params &p, const LevelMaps &src_maps, int n_images, cudaStream_t s); // kPyramidLaunches kernels: level 0, then the resized levels
 const void *pyramid_kernel_symbol(); // host handle of the level-0 pyramid kernel, the only reader of the caller's images (to find its node in a captured graph)
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 int fast_configure(const Params &p); // opt in to the dynamic shared memory of the FAST kernel

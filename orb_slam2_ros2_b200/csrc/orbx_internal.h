@@ -31,6 +31,7 @@ struct orbx_ctx
   int last_frames = 0;
   orbx::LevelMaps maps;      // TMA descriptors of the pyramid levels, FAST patch boxes (kernel parameter, __grid_constant__)
   orbx::LevelMaps maps_blur; // TMA descriptors of the blurred levels, BRIEF patch boxes
+  orbx::LevelMaps maps_src;  // TMA descriptors over level 0 of `pyr`, one box size per resized level (its tiles' source rectangles)
   float min_u = 0, min_v = 0, max_u = 0, max_v = 0; // undistorted image bounds (VirtualFrame ctor, Frame.h:33-43)
   // host-batch pipeline: chunks of frames round-robin over kPipe streams so that H2D, kernels and D2H overlap
   static constexpr int kPipeMax = 8;

@@ -65,6 +65,62 @@ template <int NT> __device__ __forceinline__ int block_exclusive_scan(int v, int
   return base + inc - v;
 }
 
+// shared-memory accesses of the compaction lists by 32-bit shared address: one LDS / STS each, no generic-pointer arithmetic
+__device__ __forceinline__ void sts_u16_if(uint32_t addr, uint32_t v, bool pred)
+{
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p st.shared.u16 [%0], %1;\n}" ::"r"(addr), "h"((unsigned short)v), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// one 3-D box {x .. x + boxW, y .. y + boxH, z} of a byte tensor -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
+               "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // K1: pyramid level (resize from level 0) fused with the 7x7 Gaussian blur.  One CTA per kTileW x kTileH output tile.
 //   cv::resize INTER_LINEAR 8UC1: 11-bit coefficient tables (built on the host exactly like OpenCV does), int32 maths.
@@ -94,20 +150,27 @@ constexpr int kPairs = 36;                     // stage A of the resized levels:
 constexpr int kPairRows = kPyrThreads / kPairs; // 7 rows per pass (252 threads)
 constexpr int kWordRows = kPyrThreads / kSrcWords; // level 0: 14 rows per pass (252 threads)
 
-struct PyrShared
+constexpr int kPyrBoxBytes = 18 * 1024; // largest level-0 source rectangle staged through TMA (levels whose box fits)
+
+template <int kHBytes> struct PyrSharedT
 {
   __align__(16) uint8_t src[kSrcH * kSrcPitch];
-  __align__(16) uint16_t h[kSrcH * kTileW];
+  // horizontal-pass output (u16); in pyramid_levels_kernel the same bytes first receive the tile's level-0 source rectangle (TMA box)
+  __align__(128) uint8_t hbuf[kHBytes];
+  __device__ __forceinline__ uint16_t *h() { return reinterpret_cast<uint16_t *>(hbuf); }
+  __device__ __forceinline__ const uint16_t *h() const { return reinterpret_cast<const uint16_t *>(hbuf); }
   // per source row: byte offsets of the two level-0 rows and the vertical coefficients pre-shifted by 16, so that
   // (b * (h >> 4)) >> 16 is one multiply-high (level 0: .x = row offset, .z = 1 when the row may be read with word loads)
   __align__(16) uint4 row[kSrcH];
 };
+using PyrShared = PyrSharedT<kSrcH * kTileW * 2>;
+using PyrSharedBox = PyrSharedT<kPyrBoxBytes>;
 
 // rows of the tile (+ halo) that exist: rows beyond level row lh + kHalo - 1 are never consumed
 __device__ __forceinline__ int tile_rows(const Tile &t, int lh) { return min(kSrcH, lh + 2 * kHalo - t.y0); }
 
 // the level image itself (getPyramid(); FAST, orientation and the stereo SAD read it): 16 pixels per load/store
-__device__ __forceinline__ void pyr_store_level(const PyrShared &sm, const Tile &t, int lh, int pitch, uint8_t *__restrict__ pyr)
+template <class S> __device__ __forceinline__ void pyr_store_level(const S &sm, const Tile &t, int lh, int pitch, uint8_t *__restrict__ pyr)
 {
   for (int i = threadIdx.x; i < kTileH * (kTileW / 16); i += kPyrThreads)
   {
@@ -121,12 +184,12 @@ __device__ __forceinline__ void pyr_store_level(const PyrShared &sm, const Tile 
 // stage B: horizontal pass, 2 rows x 4 outputs per item from 3 aligned words per row; output pixel 4g + k needs source
 // bytes 4g + 13 + k .. + 6 of the row = words 3 + g .. 5 + g shifted by 8 (k + 1) bits; sums fit u16 (255 * 256).
 // The two rows of a pair share a word (row 2j low, row 2j + 1 high) so that the vertical pass can use DP2A.
-__device__ __forceinline__ void pyr_blur_rows(PyrShared &sm, int rows)
+template <class S> __device__ __forceinline__ void pyr_blur_rows(S &sm, int rows)
 {
   constexpr uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24); // taps 0..3
   constexpr uint32_t K1 = 48u | (34u << 8) | (18u << 16);               // taps 4..6
   const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sm.src);
-  uint4 *h4 = reinterpret_cast<uint4 *>(sm.h);
+  uint4 *h4 = reinterpret_cast<uint4 *>(sm.h());
   const int g = threadIdx.x & 15;
   const int n_pairs = (rows + 1) >> 1;
   for (int j = threadIdx.x >> 4; j < n_pairs; j += kPyrThreads / 16)
@@ -149,13 +212,13 @@ __device__ __forceinline__ void pyr_blur_rows(PyrShared &sm, int rows)
 // stage C: vertical pass + rounding; one item per 4 columns x 2 output rows (2y, 2y + 1).  Both rows read the same four
 // row pairs y .. y + 3: the even row weighs them (18,34) (48,56) (48,34) (18,0), the odd row (0,18) (34,48) (56,48)
 // (34,18) -- low / high byte pairs of the same weight registers (DP2A.LO / DP2A.HI).
-__device__ __forceinline__ void pyr_blur_cols(const PyrShared &sm, const Tile &t, int lh, int pitch, uint8_t *__restrict__ blr)
+template <class S> __device__ __forceinline__ void pyr_blur_cols(const S &sm, const Tile &t, int lh, int pitch, uint8_t *__restrict__ blr)
 {
   const int g = threadIdx.x & 15;
   const int gx = t.x0 + g * 4;
   if (gx >= pitch) return;
   const int n_out = min(kTileH / 2, (lh - t.y0 + 1) >> 1);
-  const uint4 *h4 = reinterpret_cast<const uint4 *>(sm.h);
+  const uint4 *h4 = reinterpret_cast<const uint4 *>(sm.h());
   for (int yp = threadIdx.x >> 4; yp < n_out; yp += kPyrThreads / 16)
   {
     const int gy = t.y0 + 2 * yp;
@@ -266,7 +329,7 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_level0_kernel(const Param
   pyr_blur_cols(sm, t, lh, pitch, p.blur + (size_t)img * p.pyr_img_stride + L.pyr_off);
 }
 
-template <bool kSharedWindow> __device__ __forceinline__ void resize_rows(PyrShared &sm, const uint8_t *__restrict__ l0, int rows, int q, int grp,
+template <bool kSharedWindow, bool kBox, class S> __device__ __forceinline__ void resize_rows(S &sm, const uint8_t *__restrict__ l0, uint32_t box_u32, int rows, int q, int grp,
                                                                            uint32_t base_a, uint32_t base_b, uint32_t sel_a, uint32_t sel_b,
                                                                            uint32_t coef_a, uint32_t coef_b)
 {
@@ -287,15 +350,27 @@ template <bool kSharedWindow> __device__ __forceinline__ void resize_rows(PyrSha
     for (int u = 0; u < U; ++u)
     {
       const uint4 r = rp[u * kPairRows];
-      const uint32_t *q0 = reinterpret_cast<const uint32_t *>(pa + r.x), *q1 = reinterpret_cast<const uint32_t *>(pa + r.y);
-      a0[u] = q0[0], a1[u] = q0[1], a2[u] = q1[0], a3[u] = q1[1];
-      if (!kSharedWindow)
-      {
-        const uint32_t *s0 = reinterpret_cast<const uint32_t *>(pb + r.x), *s1 = reinterpret_cast<const uint32_t *>(pb + r.y);
-        b0[u] = s0[0], b1[u] = s0[1], b2[u] = s1[0], b3[u] = s1[1];
+      if (kBox)
+      { // the source rectangle is in shared memory (TMA box): row offsets and window offsets are relative to the box
+        const uint32_t q0 = box_u32 + base_a + r.x, q1 = box_u32 + base_a + r.y;
+        a0[u] = lds_u32(q0), a1[u] = lds_u32(q0 + 4u), a2[u] = lds_u32(q1), a3[u] = lds_u32(q1 + 4u);
+        if (!kSharedWindow)
+        {
+          const uint32_t s0 = box_u32 + base_b + r.x, s1 = box_u32 + base_b + r.y;
+          b0[u] = lds_u32(s0), b1[u] = lds_u32(s0 + 4u), b2[u] = lds_u32(s1), b3[u] = lds_u32(s1 + 4u);
+        }
       }
       else
-        b0[u] = a0[u], b1[u] = a1[u], b2[u] = a2[u], b3[u] = a3[u];
+      {
+        const uint32_t *q0 = reinterpret_cast<const uint32_t *>(pa + r.x), *q1 = reinterpret_cast<const uint32_t *>(pa + r.y);
+        a0[u] = q0[0], a1[u] = q0[1], a2[u] = q1[0], a3[u] = q1[1];
+        if (!kSharedWindow)
+        {
+          const uint32_t *s0 = reinterpret_cast<const uint32_t *>(pb + r.x), *s1 = reinterpret_cast<const uint32_t *>(pb + r.y);
+          b0[u] = s0[0], b1[u] = s0[1], b2[u] = s1[0], b3[u] = s1[1];
+        }
+      }
+      if (kSharedWindow) b0[u] = a0[u], b1[u] = a1[u], b2[u] = a2[u], b3[u] = a3[u];
       bz[u] = r.z, bw[u] = r.w;
     }
 #pragma unroll
@@ -311,9 +386,10 @@ template <bool kSharedWindow> __device__ __forceinline__ void resize_rows(PyrSha
   }
 }
 
-__global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Params p)
+__global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Params p, const __grid_constant__ LevelMaps src_maps)
 {
-  __shared__ PyrShared sm;
+  __shared__ PyrSharedBox sm;
+  __shared__ __align__(8) uint64_t s_bar;
   const Tile t = p.tiles[p.n_tiles0 + blockIdx.x];
   const int img = blockIdx.y;
   const Level &L = p.levels[t.level];
@@ -322,9 +398,22 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Param
   const int area2x = L.area2x;
   const int tid = threadIdx.x;
   const int rows = tile_rows(t, lh);
-  const uint32_t pitch0 = (uint32_t)p.levels[0].pitch;
   // level 0 of this image inside the pyramid buffer (written by pyramid_level0_kernel, same stream)
   const uint8_t *__restrict__ l0 = p.pyr + (size_t)img * p.pyr_img_stride + p.levels[0].pyr_off;
+  // Levels whose per-tile source rectangle fits (scale < 2 at the usual 1.2 pyramid: most of the resized pixels) stage it in
+  // shared memory through ONE TMA box load from the aligned level-0 copy: box origin (sx0, sy0) from the tile record (sx0 a
+  // multiple of 16), box size per level.  The other levels gather their taps from global memory (L2) with the same arithmetic.
+  const int box_w = L.src_box_w, box_h = L.src_box_h;
+  const bool boxed = box_w != 0;
+  const int sx0 = t.src & 0xffff, sy0 = t.src >> 16;
+  if (boxed && tid == 0)
+  {
+    mbar_init(&s_bar, 1);
+    mbar_expect_tx(&s_bar, (uint32_t)(box_w * box_h));
+    tma_load_3d(sm.hbuf, &src_maps.m[t.level], sx0, sy0, p.img0 + img, &s_bar);
+  }
+  const uint32_t row_pitch = boxed ? (uint32_t)box_w : (uint32_t)p.levels[0].pitch;
+  const int row_org = boxed ? sy0 : 0;
 
   if (tid < rows)
   {
@@ -332,22 +421,23 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Param
     uint32_t o0, o1, z = 0, w = 0;
     if (area2x)
     {
-      o0 = (uint32_t)(2 * gy) * pitch0;
-      o1 = o0 + pitch0;
+      o0 = (uint32_t)(2 * gy) * row_pitch;
+      o1 = o0 + row_pitch;
     }
     else
     {
       const int sy = p.tab_ofs[L.tab_y + gy];
       const short2 b = p.tab_coef[L.tab_y + gy];
-      o0 = (uint32_t)min(max(sy, 0), H - 1) * pitch0; // rows are clamped, not re-weighted (cv::resize)
-      o1 = (uint32_t)min(max(sy + 1, 0), H - 1) * pitch0;
+      o0 = (uint32_t)(min(max(sy, 0), H - 1) - row_org) * row_pitch; // rows are clamped, not re-weighted (cv::resize)
+      o1 = (uint32_t)(min(max(sy + 1, 0), H - 1) - row_org) * row_pitch;
       z = (uint32_t)b.x << 16, w = (uint32_t)b.y << 16; // coefficients are in [0, 2048]
     }
     sm.row[tid] = make_uint4(o0, o1, z, w);
   }
   else if (tid < kSrcH)
     sm.row[tid] = make_uint4(0u, 0u, 0u, 0u); // rows beyond the level: any valid source row, weights 0 (never consumed)
-  __syncthreads();
+  __syncthreads(); // also orders thread 0's mbarrier init before everybody's wait
+  if (boxed) mbar_wait(&s_bar, 0);
 
   // stage A: the tile plus a 3-pixel halo of the resized level image, REFLECT_101 at the level's borders.
   if (area2x)
@@ -376,10 +466,18 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Param
       // pair table (built on the host next to the resize tables): window offsets into a level-0 row, PRMT selectors of the two
       // tap pairs, packed coefficients ax | ay << 16 (0 for columns beyond the level + halo: value 0)
       const uint4 e = p.tab_pair[L.tab_pair + (t.x0 >> 1) + q];
-      if (L.pair_window)
-        resize_rows<true>(sm, l0, rows, q, grp, e.x & 0xffffu, e.x & 0xffffu, e.x >> 16, e.y >> 16, e.z, e.w);
+      const uint32_t box_u32 = smem_u32(sm.hbuf) - (uint32_t)sx0; // window offsets are level-0 columns
+      if (boxed)
+      {
+        if (L.pair_window)
+          resize_rows<true, true>(sm, l0, box_u32, rows, q, grp, e.x & 0xffffu, e.x & 0xffffu, e.x >> 16, e.y >> 16, e.z, e.w);
+        else
+          resize_rows<false, true>(sm, l0, box_u32, rows, q, grp, e.x & 0xffffu, e.y & 0xffffu, e.x >> 16, e.y >> 16, e.z, e.w);
+      }
+      else if (L.pair_window)
+        resize_rows<true, false>(sm, l0, 0u, rows, q, grp, e.x & 0xffffu, e.x & 0xffffu, e.x >> 16, e.y >> 16, e.z, e.w);
       else
-        resize_rows<false>(sm, l0, rows, q, grp, e.x & 0xffffu, e.y & 0xffffu, e.x >> 16, e.y >> 16, e.z, e.w);
+        resize_rows<false, false>(sm, l0, 0u, rows, q, grp, e.x & 0xffffu, e.y & 0xffffu, e.x >> 16, e.y >> 16, e.z, e.w);
     }
   }
   __syncthreads();
@@ -393,10 +491,10 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Param
 const void *pyramid_kernel_symbol() { return reinterpret_cast<const void *>(&pyramid_level0_kernel); }
 
 // two launches: level 0 (reads the caller's images), then the resized levels (read level 0 from the pyramid buffer)
-void launch_pyramid(const Params &p, int n_images, cudaStream_t s)
+void launch_pyramid(const Params &p, const LevelMaps &src_maps, int n_images, cudaStream_t s)
 {
   pyramid_level0_kernel<<<dim3(p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p);
-  if (p.n_tiles > p.n_tiles0) pyramid_levels_kernel<<<dim3(p.n_tiles - p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p);
+  if (p.n_tiles > p.n_tiles0) pyramid_levels_kernel<<<dim3(p.n_tiles - p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p, src_maps);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -448,63 +546,7 @@ __device__ __forceinline__ int fast_arc_value(const uint8_t *c)
   return max(darker, brighter);
 }
 
-// shared-memory accesses of the compaction lists by 32-bit shared address: one LDS / STS each, no generic-pointer arithmetic
-__device__ __forceinline__ void sts_u16_if(uint32_t addr, uint32_t v, bool pred)
-{
-  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p st.shared.u16 [%0], %1;\n}" ::"r"(addr), "h"((unsigned short)v), "r"((uint32_t)pred) : "memory");
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
-{
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
-  return v;
-}
-
-// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-// one 3-D box {x .. x + boxW, y .. y + boxH, z} of a byte tensor -> shared memory, completion on an mbarrier
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
-{
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
-               "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
-               : "memory");
-}
-
 constexpr int kFastWarps = kFastThreads / 32;
-
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
-{
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
 
 // Stage-1 test on two pixels at once (16-bit halves of a register, VIMNMX.U16x2): "two ADJACENT compass ring pixels are
 // brighter (darker) than the centre by more than t".  The operands carry each pixel in the HIGH byte of its half (the low
