@@ -354,11 +354,11 @@ int orbx_search_by_bow(orbx_ctx *ctx, int frame, int n_kf_nodes, const int32_t *
                        int32_t *n_candidates);
 
 /* ---- introspection for benchmarks / profiles ----------------------------------------------------------- */
-#define ORBX_N_STAGES 6
+#define ORBX_N_STAGES 7
 /* Same work as orbx_stereo_batch_device, with a CUDA event recorded on the stream after every kernel; blocks until
  * done and returns the device time of each stage in milliseconds:
- * [0] pyramid+blur  [1] FAST cells  [2] quadtree  [3] orientation+BRIEF  [4] frame index (row index of the right keypoints +
- * grid of the left ones)  [5] stereo match */
+ * [0] pyramid level 0 (+blur)  [1] pyramid levels >= 1 (+blur)  [2] FAST cells  [3] quadtree  [4] orientation+BRIEF
+ * [5] frame index (row index of the right keypoints + grid of the left ones)  [6] stereo match */
 int orbx_profile_stereo_batch_device(orbx_ctx *ctx, int n_frames, const uint8_t *d_left, const uint8_t *d_right,
                                      size_t stride, size_t frame_stride, float *stage_ms /* [ORBX_N_STAGES] */);
 /* name of stage i of the list above */

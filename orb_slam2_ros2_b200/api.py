@@ -33,7 +33,7 @@ ORBX_ERR_COMM = -8
 COMM_ID_BYTES, IPC_HANDLE_BYTES = 128, 64
 TRANSPORT_NONE, TRANSPORT_NCCL, TRANSPORT_PEER = 0, 1, 2
 DEPTH_U16, DEPTH_F32 = 0, 1
-N_STAGES = 6  # ORBX_N_STAGES
+N_STAGES = 7  # ORBX_N_STAGES
 
 
 # the reference's exception types (include/ORB_SLAM2/Error.h:13-98)

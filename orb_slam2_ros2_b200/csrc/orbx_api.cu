@@ -1000,7 +1000,7 @@ extern "C"
 
   const char *orbx_stage_name(int stage)
   {
-    static const char *names[ORBX_N_STAGES] = {"pyramid_blur", "fast_cells", "quadtree", "orient_brief", "frame_index", "stereo_match"};
+    static const char *names[ORBX_N_STAGES] = {"pyramid_level0", "pyramid_levels", "fast_cells", "quadtree", "orient_brief", "frame_index", "stereo_match"};
     return (stage >= 0 && stage < ORBX_N_STAGES) ? names[stage] : "";
   }
 
@@ -1021,18 +1021,20 @@ extern "C"
     const int ni = 2 * n_frames;
     ORBX_CUDA(c, cudaMemsetAsync(p.n_matches, 0, (size_t)n_frames * sizeof(int), c->stream));
     ORBX_CUDA(c, cudaEventRecord(ev[0], c->stream));
-    launch_pyramid(p, c->maps_src, ni, c->stream);
+    launch_pyramid_level0(p, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[1], c->stream));
-    launch_fast(p, c->maps, ni, c->stream);
+    launch_pyramid_levels(p, c->maps_src, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[2], c->stream));
-    launch_quadtree(p, ni, c->qt_smem, c->stream);
+    launch_fast(p, c->maps, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[3], c->stream));
-    launch_orient_brief(p, c->maps_blur, ni, c->stream);
+    launch_quadtree(p, ni, c->qt_smem, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[4], c->stream));
-    launch_frame_index(p, n_frames, 2, true, c->stream);
+    launch_orient_brief(p, c->maps_blur, ni, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[5], c->stream));
-    launch_stereo(p, n_frames, c->stream);
+    launch_frame_index(p, n_frames, 2, true, c->stream);
     ORBX_CUDA(c, cudaEventRecord(ev[6], c->stream));
+    launch_stereo(p, n_frames, c->stream);
+    ORBX_CUDA(c, cudaEventRecord(ev[7], c->stream));
     c->launches += 5 + kPyramidLaunches;
     ORBX_CUDA(c, cudaGetLastError());
     ORBX_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -223,6 +223,8 @@ struct BowArgs
 constexpr int kPyramidLaunches = 2;
 constexpr int kPyrBoxBytesHost = 18 * 1024; // = kPyrBoxBytes of orbx_kernels.cu: shared-memory bytes a level's source box may take
 void launch_pyramid(const Params &p, const LevelMaps &src_maps, int n_images, cudaStream_t s); // kPyramidLaunches kernels: level 0, then the resized levels
+void launch_pyramid_level0(const Params &p, int n_images, cudaStream_t s);
+void launch_pyramid_levels(const Params &p, const LevelMaps &src_maps, int n_images, cudaStream_t s);
 const void *pyramid_kernel_symbol(); // host handle of the level-0 pyramid kernel, the only reader of the caller's images (to find its node in a captured graph)
 void launch_fast(const Params &p, const LevelMaps &maps, int n_images, cudaStream_t s);
 int fast_configure(const Params &p); // opt in to the dynamic shared memory of the FAST kernel

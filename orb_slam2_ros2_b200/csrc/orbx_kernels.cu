@@ -1,7 +1,7 @@
 // orbx_kernels.cu -- hand-written sm_100a kernels of the ORB front-end.
 //
 // One kernel per stage of the reference's CPU path (citations relative to /root/reference/src/ORB_SLAM2/):
-//   pyramid_blur_kernel  ORBExtractor::initPyramid            src/ORBExtractor.cc:304-319  (cv::resize + cv::GaussianBlur)
+//   pyramid_level0_kernel / pyramid_levels_kernel  ORBExtractor::initPyramid  src/ORBExtractor.cc:304-319  (cv::resize + cv::GaussianBlur)
 //   fast_cells_kernel    ORBExtractor::extractFast, FAST part  src/ORBExtractor.cc:346-375  (cv::FAST + threshold fallback)
 //   quadtree_kernel      Quadtree::split / nodes2kpoints       src/ORBExtractor.cc:19-192,376-386
 //   orient_brief_kernel  getGrayCentroid + computeBRIEF        src/ORBExtractor.cc:397-487,534-540
@@ -491,10 +491,17 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_levels_kernel(const Param
 const void *pyramid_kernel_symbol() { return reinterpret_cast<const void *>(&pyramid_level0_kernel); }
 
 // two launches: level 0 (reads the caller's images), then the resized levels (read level 0 from the pyramid buffer)
+void launch_pyramid_level0(const Params &p, int n_images, cudaStream_t s) { pyramid_level0_kernel<<<dim3(p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p); }
+
+void launch_pyramid_levels(const Params &p, const LevelMaps &src_maps, int n_images, cudaStream_t s)
+{
+  if (p.n_tiles > p.n_tiles0) pyramid_levels_kernel<<<dim3(p.n_tiles - p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p, src_maps);
+}
+
 void launch_pyramid(const Params &p, const LevelMaps &src_maps, int n_images, cudaStream_t s)
 {
-  pyramid_level0_kernel<<<dim3(p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p);
-  if (p.n_tiles > p.n_tiles0) pyramid_levels_kernel<<<dim3(p.n_tiles - p.n_tiles0, n_images), kPyrThreads, 0, s>>>(p, src_maps);
+  launch_pyramid_level0(p, n_images, s);
+  launch_pyramid_levels(p, src_maps, n_images, s);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

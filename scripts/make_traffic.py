@@ -7,9 +7,9 @@ import re
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r1_final_all_kernels_full.txt")
+src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r2_all_kernels_full.txt")
 txt = open(src).read()
-names = {"pyramid_blur": "pyramid_blur", "fast_cells": "fast_cells", "quadtree": "quadtree", "orient_brief": "orient_brief", "frame_index": "frame_index",
+names = {"pyramid_level0": "pyramid_level0", "pyramid_levels": "pyramid_levels", "fast_cells": "fast_cells", "quadtree": "quadtree", "orient_brief": "orient_brief", "frame_index": "frame_index",
          "stereo": "stereo_match", "grid": "grid", "area_match": "area_match", "serialize": "serialize"}
 out = {}
 for blk in txt.split("## ")[1:]:
