@@ -27,7 +27,7 @@ for f in re.split(r"\n\s*Function : ", txt)[1:]:
     vals = [cnt("UTMALDG"), cnt("SYNCS"), cnt("LDG"), cnt("LDS"), cnt("STS"), cnt("STG"), cnt("VIMNMX"), cnt("IDP"), cnt("MATCH"), cnt("REDUX"), cnt("ATOMS"),
             cnt("DMUL", "DADD", "DFMA", "DSETP", "F2F.F64", "I2F.F64", "F2F.F32.F64"), cnt("BAR")]
     print("%-44s %6d " % (dn[:44], sum(ops.values())) + " ".join("%7d" % v for v in vals))
-print("# fast_cells_kernel: the FAST patch arrives through ONE cp.async.bulk.tensor.3d (UTMALDG.3D) completing on an mbarrier (SYNCS.*TRYWAIT)")
+print("# TMA box loads (cp.async.bulk.tensor.3d = UTMALDG.3D, completion on an mbarrier = SYNCS.*TRYWAIT) of fast_cells (cell patch), pyramid_levels (level-0 source rectangle) and orient_brief (blurred 37x37 patch):")
 for line in txt.splitlines():
     if "UTMALDG" in line or "SYNCS" in line:
         print("#   " + line.strip()[:150])
