@@ -976,9 +976,13 @@ __device__ __forceinline__ uint32_t qt_make_key(uint32_t e, const long long *col
       }
   if (strip < 0) return kKeyNoStrip << kKeyStripShift;
   const unsigned long long ux = (unsigned long long)(x - cols[strip]) << kKeyLevels, wx = (unsigned long long)(cols[strip + 1] - cols[strip]);
-  const unsigned long long qx64 = ux / wx;
-  const bool x_exact = qx64 * wx == ux;
-  const uint32_t qx = (uint32_t)qx64;
+  // floor(ux / wx) < 2^kKeyLevels because the corner lies inside the strip: a float quotient is off by less than one, and one
+  // exact 64-bit correction step in either direction replaces the (emulated, ~100-instruction) 64-bit division
+  uint32_t qx = (uint32_t)__fdividef((float)ux, (float)wx);
+  long long rem = (long long)(ux - (unsigned long long)qx * wx);
+  if (rem < 0) --qx, rem += (long long)wx;
+  if (rem >= (long long)wx) ++qx, rem -= (long long)wx;
+  const bool x_exact = rem == 0;
   const uint32_t uy = yi << kKeyLevels, qy = uy / (uint32_t)roi_h;
   const bool y_exact = qy * (uint32_t)roi_h == uy;
   // first depth at which the corner sits on a midline (kKeyLevels + 1: none within the key)
@@ -2039,6 +2043,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
 
   // grid = (images, levels): CTAs are dispatched x-fastest, so every image's level 0 (the longest chain) starts first
   // and the short high levels fill the tail
+  const long long t_kernel0 = clock64();
   const int level = blockIdx.y, img = blockIdx.x;
   const Level &L = p.levels[level];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -2110,21 +2115,47 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   uint8_t *resp8 = lists + 8 * (size_t)p.qt_smem_cap; // FAST score by corner (loop-free path)
   auto gather = [&]() {
     const uint32_t *cl = p.cell_list + (size_t)img * p.cell_entries;
-    for (int i = tid; i < n; i += kQtThreads)
+    // where cell c's list starts in the cell-list buffer, relative to its offset in the level's list: corner i of cell c is
+    // cl[i + delta[c]].  Kept in the (still unused) second index array so that the corner's load does not wait for a global load
+    // of the cell record first.
+    int *cell_delta = (int *)ib16;
+    const bool delta_ok = (size_t)ncell * sizeof(int) <= (size_t)p.qt_smem_cap * sizeof(uint16_t);
+    if (delta_ok)
+      for (int c = tid; c < ncell; c += kQtThreads) cell_delta[c] = cells[c].slot - cell_off[c];
+    __syncthreads();
+    int n_steps = 0; // binary search steps: the same for every corner
+    while ((1 << n_steps) < ncell) ++n_steps;
+    constexpr int G = 4; // corners per thread in flight: the searches and the loads of a batch are independent
+    for (int i0 = tid; i0 < n; i0 += G * kQtThreads)
     {
-      int lo_c = 0, hi_c = ncell; // largest c with cell_off[c] <= i
-      while (hi_c - lo_c > 1)
+      int idx[G], lo_c[G], hi_c[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) idx[g] = min(i0 + g * kQtThreads, n - 1), lo_c[g] = 0, hi_c[g] = ncell; // largest c with cell_off[c] <= i
+      for (int st = 0; st < n_steps; ++st)
       {
-        const int mid = (lo_c + hi_c) >> 1;
-        if (cell_off[mid] <= i)
-          lo_c = mid;
-        else
-          hi_c = mid;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (hi_c[g] - lo_c[g] > 1)
+          {
+            const int mid = (lo_c[g] + hi_c[g]) >> 1;
+            if (cell_off[mid] <= idx[g])
+              lo_c[g] = mid;
+            else
+              hi_c[g] = mid;
+          }
       }
-      const uint32_t e = cl[cells[lo_c].slot + (i - cell_off[lo_c])];
-      kp[i] = e;
-      if (use_keys) keys[i] = qt_make_key(e, cols, K, L.roi_h);
-      if (in_smem) resp8[i] = (uint8_t)(e >> 24);
+      uint32_t e[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) e[g] = delta_ok ? cl[idx[g] + cell_delta[lo_c[g]]] : cl[cells[lo_c[g]].slot + (idx[g] - cell_off[lo_c[g]])];
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (i0 + g * kQtThreads < n)
+        {
+          const int i = idx[g];
+          kp[i] = e[g];
+          if (use_keys) keys[i] = qt_make_key(e[g], cols, K, L.roi_h);
+          if (in_smem) resp8[i] = (uint8_t)(e[g] >> 24);
+        }
     }
   };
 
@@ -2231,6 +2262,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   // It works on the presorted corners (index array grouped by (strip, d1, d2, d3) bin + the bin table); if it has to give up
   // after it has started to partition nodes, the presort is simply redone for the sequential loop.
   bool done = false;
+  if (tid == 0 && p.qt_stats) atomicAdd(&p.qt_stats[2 + 6], (unsigned long long)(clock64() - t_kernel0)); // phases A, B, B'
   if (p.qt_fast && presort && in_smem)
   {
     uint8_t *lf = fast_tables + 2048;
@@ -2244,6 +2276,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   }
   uint32_t *flag = keys; // the key array doubles as the "selected" flag array at the end
   if (tid == 0 && p.qt_stats) atomicAdd(&p.qt_stats[done ? 0 : 1], 1ull);
+  const long long t_post0 = clock64();
   if (!done)
   {
   for (int i = tid; i < 2 * kQtBuckets; i += kQtThreads) q.bhead[i] = (uint16_t)kNil; // heads and tails are contiguous
@@ -2338,6 +2371,7 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
       }
     if (tid == 0) *sel_cnt = min(total, need);
   }
+  if (tid == 0 && p.qt_stats && done) atomicAdd(&p.qt_stats[2 + 7], (unsigned long long)(clock64() - t_post0)); // ordered emit
 }
 
 int quadtree_configure(size_t smem_bytes)

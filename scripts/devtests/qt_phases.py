@@ -8,7 +8,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from orb_slam2_ros2_b200 import api, synth  # noqa: E402
 
-NAMES = ["table nodes", "descent", "c*", "resp+ranks", "leaves", "surplus+flags", "-", "-"]
+NAMES = ["table nodes", "descent", "c*", "resp+ranks", "leaves", "surplus+flags", "PRE: cell scan + gather + keys + presort", "POST: ordered emit"]
 for name, (h, w, nf, nl, seed) in {"K2000": (376, 1241, 2000, 8, 0), "K500": (376, 1241, 500, 8, 1), "K4000": (376, 1241, 4000, 8, 2), "T1000": (480, 640, 1000, 8, 3),
                                    "H5000": (1080, 1920, 5000, 12, 4)}.items():
     img = synth.synth_image(h, w, seed)
