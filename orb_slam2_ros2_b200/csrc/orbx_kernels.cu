@@ -2649,7 +2649,7 @@ void launch_orient_brief(const Params &p, const LevelMaps &blur_maps, int n_imag
 // matter: the search takes the lexicographic minimum of (distance, index), which equals the reference's first minimum
 // over ascending indices.)
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kRowThreads = 256;
+constexpr int kRowThreads = 1024;
 
 __device__ __forceinline__ void rowindex_body(const Params &p, int frame, int *s_cnt /* [height + 1] */, int *s_warp)
 {
@@ -2662,10 +2662,17 @@ __device__ __forceinline__ void rowindex_body(const Params &p, int frame, int *s
   uint16_t *entries = p.row_entries + (size_t)frame * p.row_cap;
   for (int i = tid; i <= H; i += kRowThreads) s_cnt[i] = 0;
   __syncthreads();
-  for (int j = tid; j < nR; j += kRowThreads)
+  // four band records per thread are in flight before the first one is used (the loop is latency-bound: one CTA per frame)
+  constexpr int U = 4;
+  for (int j0 = tid; j0 < nR; j0 += U * kRowThreads)
   {
-    const RTab t = rt[j];
-    for (int r = t.min_row; r < t.max_row; ++r) atomicAdd(&s_cnt[r], 1);
+    RTab t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) t[u] = rt[min(j0 + u * kRowThreads, nR - 1)];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (j0 + u * kRowThreads < nR)
+        for (int r = t[u].min_row; r < t[u].max_row; ++r) atomicAdd(&s_cnt[r], 1);
   }
   __syncthreads();
   const int per = (H + kRowThreads - 1) / kRowThreads;
@@ -2683,14 +2690,19 @@ __device__ __forceinline__ void rowindex_body(const Params &p, int frame, int *s
   }
   if (tid == 0) row_start[H] = total;
   __syncthreads();
-  for (int j = tid; j < nR; j += kRowThreads)
+  for (int j0 = tid; j0 < nR; j0 += U * kRowThreads)
   {
-    const RTab t = rt[j];
-    for (int r = t.min_row; r < t.max_row; ++r)
-    {
-      const int pos = atomicAdd(&s_cnt[r], 1);
-      if (pos < p.row_cap) entries[pos] = (uint16_t)j;
-    }
+    RTab t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) t[u] = rt[min(j0 + u * kRowThreads, nR - 1)];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (j0 + u * kRowThreads < nR)
+        for (int r = t[u].min_row; r < t[u].max_row; ++r)
+        {
+          const int pos = atomicAdd(&s_cnt[r], 1);
+          if (pos < p.row_cap) entries[pos] = (uint16_t)(j0 + u * kRowThreads);
+        }
   }
 }
 
@@ -2906,7 +2918,7 @@ void launch_rgbd(const Params &p, int n_frames, cudaStream_t s)
 // rowIdx = cvFloor(pt.y / 48), colIdx = cvFloor(pt.x / 64) in float; a cell lists its keypoints in ascending index order
 // (the reference push_backs them in keypoint order).  One CTA per frame: histogram, scan, fill, per-cell sort.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kGridThreads = 256;
+constexpr int kGridThreads = 1024;
 
 __device__ __forceinline__ void grid_body(const Params &p, int frame, int image_stride, int *s_cell /* [n_cells + 1] */, uint16_t *s_ent /* [n_features] */,
                                           int *s_warp)
@@ -2924,10 +2936,15 @@ __device__ __forceinline__ void grid_body(const Params &p, int frame, int image_
   };
   for (int i = tid; i <= nc; i += kGridThreads) s_cell[i] = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += kGridThreads)
+  constexpr int U = 4; // keypoints per thread in flight (their coordinates come from global memory in every pass)
+  for (int i0 = tid; i0 < n; i0 += U * kGridThreads)
   {
-    const int c = cell_of(i);
-    if (c >= 0) atomicAdd(&s_cell[c], 1);
+    int c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = cell_of(min(i0 + u * kGridThreads, n - 1));
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * kGridThreads < n && c[u] >= 0) atomicAdd(&s_cell[c[u]], 1);
   }
   __syncthreads();
   const int per = (nc + kGridThreads - 1) / kGridThreads;
@@ -2945,31 +2962,36 @@ __device__ __forceinline__ void grid_body(const Params &p, int frame, int image_
   }
   if (tid == 0) start[nc] = total;
   __syncthreads();
-  for (int i = tid; i < n; i += kGridThreads)
+  for (int i0 = tid; i0 < n; i0 += U * kGridThreads)
   {
-    const int c = cell_of(i);
-    if (c >= 0) s_ent[atomicAdd(&s_cell[c], 1)] = (uint16_t)i;
+    int c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = cell_of(min(i0 + u * kGridThreads, n - 1));
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * kGridThreads < n && c[u] >= 0) s_ent[atomicAdd(&s_cell[c[u]], 1)] = (uint16_t)(i0 + u * kGridThreads);
   }
   __syncthreads();
-  // ascending index order inside every cell (insertion sort in shared memory; a cell holds a few dozen keypoints at most):
-  // after the scatter s_cell[c] is the END of cell c, i.e. the start of cell c + 1
-  for (int c = tid; c < nc; c += kGridThreads)
+  // ascending index order inside every cell (the reference's push_back order), by rank: keypoint i goes to the cell's start +
+  // the number of cell members with a smaller index.  One thread per keypoint scans its cell (a few dozen entries, independent
+  // shared-memory reads) instead of one thread per cell running a dependent insertion sort; the ranks are distinct, so the
+  // entries go straight to global memory.  After the scatter s_cell[c] is the END of cell c, i.e. the start of cell c + 1.
+  for (int i0 = tid; i0 < n; i0 += U * kGridThreads)
   {
-    const int b = c == 0 ? 0 : s_cell[c - 1], e = s_cell[c];
-    for (int i = b + 1; i < e; ++i)
+    int c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = cell_of(min(i0 + u * kGridThreads, n - 1));
+#pragma unroll
+    for (int u = 0; u < U; ++u)
     {
-      const uint16_t v = s_ent[i];
-      int j = i - 1;
-      while (j >= b && s_ent[j] > v)
-      {
-        s_ent[j + 1] = s_ent[j];
-        --j;
-      }
-      s_ent[j + 1] = v;
+      const int i = i0 + u * kGridThreads;
+      if (i >= n || c[u] < 0) continue;
+      const int b = c[u] == 0 ? 0 : s_cell[c[u] - 1], e = s_cell[c[u]];
+      int rank = 0;
+      for (int j = b; j < e; ++j) rank += (int)(s_ent[j] < (uint16_t)i);
+      entries[b + rank] = (uint16_t)i;
     }
   }
-  __syncthreads();
-  for (int i = tid; i < total; i += kGridThreads) entries[i] = s_ent[i];
 }
 
 // K5a + K7 in ONE launch: blocks [0, n_frames) build the row index of the right keypoints (stereo frames only), the next n_frames
