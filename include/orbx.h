@@ -297,6 +297,15 @@ int orbx_verify_angle(orbx_ctx *ctx, int n_matches, int32_t *query_idx, int32_t 
 int64_t orbx_serialized_capacity(const orbx_ctx *ctx); /* upper bound of one record for this context (multiple of 16) */
 int orbx_serialize_keyframe(orbx_ctx *ctx, int frame, uint64_t id, const float *pose_rt /* [12] or NULL */,
                             int with_map_points, uint8_t *out, size_t cap, int64_t *n_bytes);
+/* replaces: the TEXT variant of the same record, std::ostream &operator<<(std::ostream &, KeyFrame &) (src/KeyFrame.cc:423-533),
+ * for a keyframe made from frame `frame`: optionally the one-off header line "nextId scale_0 .. scale_{L-1} " (:458-467), then
+ * "id maxU maxV minU minV", the keypoints "x y octave angle rightU depth " each, the descriptors as decimal bytes, the empty
+ * BoW / FeatureVector lines, the pose (R row-major then t), the empty connection / child / loop-edge lines and the map-point
+ * ids (-1 each), every line closed by '\n' -- numbers exactly as the reference's stream prints them (operator<< of float /
+ * double = "%g" with 6 significant digits).  This format is host-side glue in the reference and here: the arrays come back in
+ * one copy per array and are formatted by the calling thread.  *n_bytes is set even when cap is too small (ORBX_ERR_CAPACITY). */
+int orbx_serialize_keyframe_text(orbx_ctx *ctx, int frame, uint64_t id, const float *pose_rt /* [12] or NULL */, int with_map_points,
+                                 int with_scale_header, uint64_t next_id, char *out, size_t cap, int64_t *n_bytes);
 /* frames 0..n_frames-1 of the most recent *_device call into DEVICE memory, asynchronous on the context's stream: record f
  * (id = id0 + f, pose d_pose_rt[f * 12 ..] or identity) at d_out + f * frame_stride (>= orbx_serialized_capacity, both
  * 4-byte aligned), its size in d_sizes[f]. */

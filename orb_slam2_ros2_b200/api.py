@@ -76,7 +76,7 @@ EXPORTS = [
     "orbx_stereo_batch_device", "orbx_extract_batch_device", "orbx_rgbd_batch_device", "orbx_synchronize", "orbx_launch_count", "orbx_algorithmic_bytes",
     "orbx_debug_level_corners", "orbx_debug_level_selected", "orbx_read_device", "orbx_profile_stereo_batch_device", "orbx_stage_name", "orbx_debug_run_quadtree", "orbx_grid_info", "orbx_get_grid",
     "orbx_search_in_area", "orbx_search_in_area_batch_device", "orbx_verify_angle",
-    "orbx_serialized_capacity", "orbx_serialize_keyframe", "orbx_serialize_keyframes_device",
+    "orbx_serialized_capacity", "orbx_serialize_keyframe", "orbx_serialize_keyframe_text", "orbx_serialize_keyframes_device",
     "orbx_vocab_create", "orbx_vocab_load_text", "orbx_vocab_destroy", "orbx_vocab_info", "orbx_bow_transform", "orbx_bow_transform_batch_device",
     "orbx_search_by_bow",
     "orbx_frame_epoch", "orbx_set_graph", "orbx_debug_quadtree_stats", "orbx_frame_range", "orbx_comm_unique_id", "orbx_comm_create", "orbx_comm_ipc_handle", "orbx_comm_open_peers",
@@ -162,6 +162,7 @@ def load_library(build_if_missing: bool = True):
     L.orbx_serialized_capacity.restype = C.c_int64
     L.orbx_serialize_keyframe.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, vp, sz, C.POINTER(C.c_int64)]
     L.orbx_serialize_keyframes_device.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, vp, sz, vp]
+    L.orbx_serialize_keyframe_text.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, C.c_int, C.c_uint64, vp, sz, C.POINTER(C.c_int64)]
     L.orbx_vocab_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(vp)]
     L.orbx_vocab_load_text.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.orbx_vocab_destroy.argtypes = [vp]
@@ -458,6 +459,19 @@ class Context:
         rc = self._L.orbx_serialize_keyframe(self._h, frame, kf_id, pose.ctypes.data if pose is not None else None, int(with_map_points), out.ctypes.data, cap,
                                              C.byref(n))
         _check(self._h, rc, "orbx_serialize_keyframe")
+        return out[: n.value].tobytes()
+
+    def serialize_keyframe_text(self, kf_id: int, pose_rt=None, with_map_points: bool = True, frame: int = 0, scale_header_next_id=None) -> bytes:
+        """the text variant of the keyframe record, operator<<(std::ostream &, KeyFrame &) (src/KeyFrame.cc:423-533); the one-off
+        "nextId scales" header line is written when scale_header_next_id is given"""
+        cap = 256 + self.n_features * 320
+        out = np.zeros(cap, np.uint8)
+        pose = None if pose_rt is None else np.ascontiguousarray(pose_rt, np.float32)
+        assert pose is None or pose.size == 12
+        n = C.c_int64(0)
+        rc = self._L.orbx_serialize_keyframe_text(self._h, frame, kf_id, pose.ctypes.data if pose is not None else None, int(with_map_points),
+                                                  int(scale_header_next_id is not None), int(scale_header_next_id or 0), out.ctypes.data, cap, C.byref(n))
+        _check(self._h, rc, "orbx_serialize_keyframe_text")
         return out[: n.value].tobytes()
 
     def serialize_keyframes_device(self, n_frames, id0, d_out, frame_stride, d_sizes, d_pose_rt=0, with_map_points=True):

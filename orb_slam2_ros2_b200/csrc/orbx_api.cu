@@ -1490,6 +1490,74 @@ extern "C"
     return ORBX_OK;
   }
 
+  int orbx_serialize_keyframe_text(orbx_ctx *c, int frame, uint64_t id, const float *pose_rt, int with_map_points, int with_scale_header, uint64_t next_id,
+                                   char *out, size_t cap, int64_t *n_bytes)
+  {
+    if (!c || frame < 0 || !out || !n_bytes) return ORBX_ERR_INVALID_ARG;
+    if (frame >= c->last_frames) return fail(c, ORBX_ERR_STATE, "no frame with that index has been processed by a stereo / RGB-D call");
+    ORBX_CUDA(c, cudaSetDevice(c->device));
+    ORBX_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int img = frame * (c->last_stereo ? 2 : 1);
+    const size_t N = (size_t)c->cfg.n_features;
+    int n = 0;
+    ORBX_CUDA(c, cudaMemcpy(&n, c->p.n_kps + img, sizeof(int), cudaMemcpyDeviceToHost));
+    n = std::max(0, std::min(n, (int)N));
+    std::vector<orbx_keypoint> kps((size_t)n);
+    std::vector<uint8_t> desc((size_t)n * 32);
+    std::vector<double> ur((size_t)n), dp((size_t)n);
+    if (n)
+    {
+      ORBX_CUDA(c, cudaMemcpy(kps.data(), c->p.kps_und + (size_t)img * N, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost));
+      ORBX_CUDA(c, cudaMemcpy(desc.data(), c->p.desc + (size_t)img * N * 32, (size_t)n * 32, cudaMemcpyDeviceToHost));
+      ORBX_CUDA(c, cudaMemcpy(ur.data(), c->p.u_right + (size_t)frame * N, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+      ORBX_CUDA(c, cudaMemcpy(dp.data(), c->p.depth + (size_t)frame * N, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    std::string t;
+    t.reserve((size_t)n * 200 + 256);
+    char buf[64];
+    auto num = [&](double v) { // std::ostream << float / double: "%g", 6 significant digits
+      t.append(buf, (size_t)std::snprintf(buf, sizeof(buf), "%g", v));
+      t.push_back(' ');
+    };
+    auto integer = [&](long long v) {
+      t.append(buf, (size_t)std::snprintf(buf, sizeof(buf), "%lld", v));
+      t.push_back(' ');
+    };
+    if (with_scale_header)
+    { // :458-467
+      t.append(buf, (size_t)std::snprintf(buf, sizeof(buf), "%llu ", (unsigned long long)next_id));
+      for (auto &L : c->levels) num((double)L.sf);
+      t.push_back('\n');
+    }
+    // :470  os << id << " " << maxU << " " << maxV << " " << minU << " " << minV << endl   (no blank before the line end)
+    t.append(buf, (size_t)std::snprintf(buf, sizeof(buf), "%llu %g %g %g %g\n", (unsigned long long)id, (double)c->max_u, (double)c->max_v, (double)c->min_u,
+                                        (double)c->min_v));
+    for (int i = 0; i < n; ++i)
+    { // :473-478
+      num((double)kps[(size_t)i].x), num((double)kps[(size_t)i].y), integer(kps[(size_t)i].octave), num((double)kps[(size_t)i].angle);
+      num(ur[(size_t)i]), num(dp[(size_t)i]);
+    }
+    t.push_back('\n');
+    for (size_t i = 0; i < (size_t)n * 32; ++i) integer(desc[i]); // :482-487
+    t.push_back('\n');
+    t.push_back('\n'); // bag-of-words vector of a fresh frame: empty (:490-492)
+    t.push_back('\n'); // feature vector: empty (:495-501)
+    static const float eye[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    const float *pose = pose_rt ? pose_rt : eye;
+    for (int i = 0; i < 12; ++i) num((double)pose[i]); // :504-509
+    t.push_back('\n');
+    t.push_back('\n'); // connected keyframes (:512-514)
+    t.push_back('\n'); // children (:517-519)
+    t.push_back('\n'); // loop edges (:522-524)
+    if (with_map_points)
+      for (int i = 0; i < n; ++i) t.append("-1 "); // :527-529
+    t.push_back('\n');
+    *n_bytes = (int64_t)t.size();
+    if (t.size() > cap) return fail(c, ORBX_ERR_CAPACITY, "output buffer too small for the text record (see *n_bytes)");
+    std::memcpy(out, t.data(), t.size());
+    return ORBX_OK;
+  }
+
   // ---------------------------------------------------------------------------------------------------------------
   // bag-of-words transform
   void orbx_vocab_destroy(orbx_vocab *v)

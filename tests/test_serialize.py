@@ -146,3 +146,61 @@ def test_cuda_serializer_batch_device(oracle):
         assert bytes(out[f, : int(sizes[f])].cpu().numpy()) == exp, f
     ctx.set_stream(None)
     ctx.close()
+
+
+# ---- text variant (operator<<(std::ostream &, KeyFrame &), src/KeyFrame.cc:423-533) -----------------------------------------
+def _g(v) -> str:
+    """std::ostream << float / double in the classic locale: printf("%g"), 6 significant digits"""
+    return "%g" % float(v)
+
+
+def _expected_text(kps, desc, u_right, depth, kf_id, bounds, pose, with_map_points, scales=None, next_id=None) -> bytes:
+    min_u, min_v, max_u, max_v = bounds  # Context.grid_info()[2:]
+    t = []
+    if scales is not None:
+        t.append(f"{next_id} " + "".join(_g(s) + " " for s in scales) + "\n")
+    t.append(f"{kf_id} {_g(max_u)} {_g(max_v)} {_g(min_u)} {_g(min_v)}\n")
+    t.append("".join(f"{_g(k['x'])} {_g(k['y'])} {int(k['octave'])} {_g(k['angle'])} {_g(u)} {_g(d)} " for k, u, d in zip(kps, u_right, depth)) + "\n")
+    t.append("".join(f"{int(b)} " for b in np.asarray(desc, np.uint8).reshape(-1)) + "\n")
+    t.append("\n\n")
+    p = np.asarray([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float32) if pose is None else np.asarray(pose, np.float32)
+    t.append("".join(_g(v) + " " for v in p) + "\n")
+    t.append("\n\n\n")
+    t.append(("-1 " * len(kps) if with_map_points else "") + "\n")
+    return "".join(t).encode()
+
+
+def test_stream_formatting_rule_is_percent_g(tmp_path):
+    """pins the formatting rule the text record relies on against the real thing: a C++ ostream printing floats and doubles"""
+    import shutil
+    import subprocess
+
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    vals = [0.0, -1.0, 1.0, 0.5, 123.456, 1241.0, 607.1928, 1e-5, 9.99999e-5, 123456.7, 999999.5, 1e6, 3.4e7, 386.1457, 359.99997, 0.1, 2.0736, 1e-7]
+    src = tmp_path / "fmt.cpp"
+    src.write_text("#include <iostream>\nint main(){ float f; double d; while (std::cin >> d) { f = (float)d; std::cout << f << ' ' << (double)f << '\\n'; } }\n")
+    exe = tmp_path / "fmt"
+    subprocess.run(["g++", "-O1", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], input="\n".join(repr(v) for v in vals), capture_output=True, text=True, check=True).stdout.split("\n")
+    for v, line in zip(vals, out):
+        f = np.float32(v)
+        assert line == f"{_g(f)} {_g(float(f))}", (v, line)
+
+
+@pytest.mark.gpu
+def test_text_record_equals_stream_formatting():
+    c = synth.KITTI
+    left, right = synth.synth_stereo_pair(c["height"], c["width"], 4, 17)
+    ctx = api.Context(c["width"], c["height"], 1500, 8, 1.2, camera=api.Camera(c["fx"], c["fy"], c["cx"], c["cy"], c["bl"]))
+    r = ctx.stereo_frame(left, right)
+    b = ctx.grid_info()[2:]
+    pose = (np.arange(12, dtype=np.float32) - 3.0) / 7.0
+    scales = [np.float32(1.2) ** 0] + [np.float32(np.float64(1.2) ** l) for l in range(1, 8)]
+    got = ctx.serialize_keyframe_text(7, pose_rt=pose, with_map_points=True, scale_header_next_id=8)
+    assert got == _expected_text(r.kps_left, r.desc_left, r.u_right, r.depth, 7, b, pose, True, scales, 8)
+    got = ctx.serialize_keyframe_text(9)
+    assert got == _expected_text(r.kps_left, r.desc_left, r.u_right, r.depth, 9, b, None, True)
+    assert got.count(b"\n") == 10 and len(got.split(b"\n")[1].split()) == 6 * len(r.kps_left)
+    assert ctx.serialize_keyframe_text(9, with_map_points=False).endswith(b"\n\n\n\n\n")
+    ctx.close()
