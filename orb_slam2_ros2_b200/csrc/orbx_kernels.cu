@@ -2106,7 +2106,12 @@ __global__ void __launch_bounds__(kQtThreads, 4) quadtree_kernel(const Params p)
   uint32_t *ia32 = kp + 2 * (size_t)L.list_cap, *ib32 = ia32 + L.list_cap;
   const int K = L.n_ini;
   const bool use_keys = K <= 31;
-  const long long *cols = p.strips_fx + L.strip_off;
+  // the strip bounds are read several times per corner (strip search, key division): one copy in shared memory instead of
+  // dependent global loads (kMaxStrips + 1 entries would be 2 KB; the key path needs at most 32 of them)
+  __shared__ long long s_cols[33];
+  const bool cols_in_smem = K <= 32;
+  if (cols_in_smem && tid <= K) s_cols[tid] = p.strips_fx[L.strip_off + tid];
+  const long long *cols = cols_in_smem ? s_cols : p.strips_fx + L.strip_off;
   const long long roi_h_fx = (long long)L.roi_h << kFixShift, roi_w_fx = (long long)L.roi_w << kFixShift;
 
   // ---- Phase B: gather the cell lists (cell-row-major, row-major inside a cell == the reference's detection order),
