@@ -133,6 +133,24 @@ def test_exact_decimation_and_extreme_scale_factors(oracle, cfg):
     ctx.close()
 
 
+@pytest.mark.parametrize("no_tma", [False, True], ids=["tma-staged", "l2-gather"])
+def test_resize_source_paths_agree(oracle, monkeypatch, no_tma):
+    """levels 1-3 of the 1.2 pyramid take their level-0 source rectangle through a TMA box load, the others (and every level with
+    ORBX_PYR_NO_TMA set, read at context creation) gather the same taps from L2: both must give the reference's pixels"""
+    if no_tma:
+        monkeypatch.setenv("ORBX_PYR_NO_TMA", "1")
+    w, h, nl = 1241, 376, 8
+    img = synth.synth_image(h, w, 31)
+    strided = np.ascontiguousarray(np.pad(img, ((0, 0), (0, 7))))[:, :w]  # rows at an odd stride (1248), like a caller's ROI
+    ctx = api.Context(w, h, 2000, nl, 1.2)
+    ctx.extract(strided)
+    e = oracle.extract(img, 2000, nl, 1.2)
+    for l in range(nl):
+        assert np.array_equal(ctx.get_pyramid(0)[l], e.pyr.level(l)), f"level {l}"
+        assert np.array_equal(ctx.get_pyramid(0, True)[l], e.pyr.blurred(l)), f"blurred level {l}"
+    ctx.close()
+
+
 def test_degenerate_images(oracle):
     ctx = api.Context(320, 240, 1000, 4, 1.2)
     kps, desc = ctx.extract(np.zeros((240, 320), np.uint8))
