@@ -328,7 +328,7 @@ int build_tables(orbx_ctx *c)
     p.fast_off_lut = off;
     off += 64;             // the 32-entry flag-bit -> code table of the candidate expansion
     p.fast_warp_bytes = up(off, 128);
-    if (4 * (size_t)p.fast_warp_bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cells too large for shared memory");
+    if ((size_t)(kFastThreads / 32) * (size_t)p.fast_warp_bytes > 200 * 1024) return fail(c, ORBX_ERR_INVALID_ARG, "FAST cells too large for shared memory");
   }
   p.qt_fast = 1;
   if (const char *e = std::getenv("ORBX_QT_FAST")) p.qt_fast = std::atoi(e) != 0;

@@ -29,7 +29,7 @@ constexpr int kTileW = 64;      // pyramid/blur output tile
 constexpr int kTileH = 64;
 constexpr int kHalo = 3;        // 7x7 Gaussian
 constexpr int kPyrThreads = 256;
-constexpr int kFastThreads = 32;
+constexpr int kFastThreads = 32;  // one warp = one FAST cell per CTA
 constexpr int kQtThreads = 256;
 constexpr int kMaxPatch = 65;   // largest FAST cell patch edge: a cell is at most 59 px wide, + 6 px apron
 constexpr int kMaxStrips = 255; // root split fan-out: round(w/h) vertical strips

@@ -570,8 +570,9 @@ __device__ __forceinline__ uint32_t fast_pretest2(uint32_t v, uint32_t dn, uint3
 
 // One WARP per cell: a 30 x 30-px cell is too small for a thread block -- its serial phases (map zeroing, suppression over
 // ~40 corners, the output scan) would run on all warps for a handful of active lanes, and every phase boundary would be a
-// block barrier.  A CTA is just kFastWarps independent cells; each warp owns a slice of the dynamic shared memory:
-//   patch (TMA box) | mbarrier | score map | candidate list | keep masks
+// block barrier.  A CTA is kFastWarps independent cells (ONE since the cells differ in length: a cell that needs the minThFAST
+// pass would hold its neighbours' slots); each warp owns a slice of the dynamic shared memory:
+//   patch (TMA box) | mbarrier | score map | candidate list | keep masks | flag-bit -> code table
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const Params p, const __grid_constant__ LevelMaps maps)
 {
   extern __shared__ __align__(128) uint8_t fast_smem[];
